@@ -1,0 +1,231 @@
+"""ctypes binding of the CPU oracle (oracle/libknox_oracle.so).
+
+TEST INFRASTRUCTURE ONLY — imported by tests/, __graft_entry__.smoke() and the
+cpu_baseline / --impl reference legs of bench.py; never by the product package.
+"""
+import ctypes as C
+import os
+import subprocess
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ODIR = os.path.join(ROOT, "oracle")
+SO = os.path.join(ODIR, "libknox_oracle.so")
+
+# element types (types.BlockType) and ops (types.FilterMode)
+I64, I32, I16, I8, U64, U32, U16, U8, F64, F32 = range(1, 11)
+EQ, NE, GT, GE, LT, LE, IN, NI, RG = range(1, 10)
+TCONST, TDELTA, TRUNEND, TBITPACK, TDICT, TS8B, TRAW, TFLOATRAW = 1, 2, 3, 4, 5, 6, 7, 15
+
+NP = {I64: np.int64, I32: np.int32, I16: np.int16, I8: np.int8, U64: np.uint64, U32: np.uint32,
+      U16: np.uint16, U8: np.uint8, F64: np.float64, F32: np.float32}
+TYPE_BY_NAME = {"int64": I64, "int32": I32, "int16": I16, "int8": I8, "uint64": U64, "uint32": U32,
+                "uint16": U16, "uint8": U8, "float64": F64, "float32": F32}
+OP_BY_NAME = {"eq": EQ, "ne": NE, "gt": GT, "ge": GE, "lt": LT, "le": LE, "bw": RG, "in": IN, "ni": NI}
+
+
+def build(force=False):
+    srcs = [os.path.join(ODIR, f) for f in os.listdir(ODIR) if f.endswith((".c", ".h"))]
+    if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["make", "-C", ODIR, "-s"])
+    return SO
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(SO)
+        u8p, u64p, vp = C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_void_p
+        sig = {
+            "ko_put_uvarint": (C.c_int, [vp, C.c_uint64]),
+            "ko_uvarint": (C.c_int, [vp, u64p]),
+            "ko_cmp": (C.c_int64, [C.c_int, C.c_int, vp, C.c_size_t, C.c_uint64, C.c_uint64, vp]),
+            "ko_bitset_and": (None, [vp, vp, C.c_size_t]),
+            "ko_bitset_and_flag": (None, [vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+            "ko_bitset_andnot": (None, [vp, vp, C.c_size_t]),
+            "ko_bitset_or": (None, [vp, vp, C.c_size_t]),
+            "ko_bitset_or_flag": (None, [vp, vp, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+            "ko_bitset_xor": (None, [vp, vp, C.c_size_t]),
+            "ko_bitset_neg": (None, [vp, C.c_size_t]),
+            "ko_bitset_one": (None, [vp, C.c_size_t]),
+            "ko_bitset_set_range": (None, [vp, C.c_size_t, C.c_int64, C.c_int64]),
+            "ko_bitset_popcount": (C.c_int64, [vp, C.c_size_t]),
+            "ko_bitset_indexes": (C.c_size_t, [vp, C.c_size_t, vp]),
+            "ko_bitpack_size": (C.c_size_t, [C.c_int, C.c_size_t]),
+            "ko_log2range": (C.c_int, [C.c_int, C.c_uint64, C.c_uint64]),
+            "ko_bitpack_encode": (C.c_size_t, [vp, vp, C.c_size_t, C.c_int, C.c_uint64]),
+            "ko_bitpack_decode": (None, [vp, vp, C.c_size_t, C.c_int, C.c_uint64]),
+            "ko_bitpack_cmp": (None, [C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, vp]),
+            "ko_container_load": (C.c_long, [C.c_int, vp, C.c_size_t, C.POINTER(vp)]),
+            "ko_container_free": (None, [vp]),
+            "ko_container_get": (C.c_uint64, [vp, C.c_size_t]),
+            "ko_container_decode": (None, [vp, vp]),
+            "ko_container_match": (None, [vp, C.c_int, C.c_uint64, C.c_uint64, vp]),
+            "ko_container_match_set": (None, [vp, C.c_int, vp, C.c_size_t, vp]),
+            "ko_store_const": (C.c_size_t, [vp, C.c_uint64, C.c_size_t]),
+            "ko_store_delta": (C.c_size_t, [vp, C.c_uint64, C.c_uint64, C.c_size_t]),
+            "ko_store_raw": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
+            "ko_store_bitpack": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
+            "ko_store_best": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t, C.c_int]),
+            "ko_store_dict": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
+            "ko_store_runend": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
+            "ko_store_s8b": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
+            "ko_store_bound": (C.c_size_t, [C.c_int, C.c_size_t]),
+            "ko_s8b_encode": (C.c_size_t, [vp, vp, C.c_size_t, C.c_uint64]),
+            "ko_s8b_decode": (C.c_size_t, [vp, C.c_size_t, vp, C.c_size_t, C.c_uint64]),
+            "ko_xxh3_u64": (C.c_uint64, [C.c_uint64]),
+            "ko_xxh3_u32": (C.c_uint64, [C.c_uint32]),
+            "ko_xxh3_u16": (C.c_uint64, [C.c_uint16]),
+            "ko_xxh3_u8": (C.c_uint64, [C.c_uint8]),
+            "ko_xxh3_bytes": (C.c_uint64, [vp, C.c_size_t]),
+            "ko_bloom_bytes": (C.c_size_t, [C.c_size_t]),
+            "ko_bloom_init": (None, [vp, C.c_size_t]),
+            "ko_bloom_add": (None, [vp, C.c_size_t, C.c_uint64]),
+            "ko_bloom_contains": (C.c_int, [vp, C.c_size_t, C.c_uint64]),
+            "ko_reduce": (None, [C.c_int, vp, C.c_size_t, vp, vp]),
+            "ko_tree_eval": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_size_t, vp]),
+            "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
+            "ko_baseline_bitpack_scan": (C.c_int64, [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_int]),
+        }
+        for name, (res, args) in sig.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _p(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None and a.size else None
+
+
+def as_u64(type_, values):
+    """Sign-/zero-extended u64 carrier of a typed numpy array (floats: IEEE bits)."""
+    a = np.ascontiguousarray(values, dtype=NP[type_])
+    if type_ == F64:
+        return a.view(np.uint64).copy()
+    if type_ == F32:
+        return a.view(np.uint32).astype(np.uint64)
+    return a.astype(np.int64).view(np.uint64) if type_ <= I8 else a.astype(np.uint64)
+
+
+def scalar_u64(type_, v):
+    return int(as_u64(type_, np.array([v], dtype=NP[type_]))[0])
+
+
+def nbytes(n):
+    return (n + 7) // 8
+
+
+def cmp(type_, op, src, a, b=0):
+    """oracle compare kernel → (bitset bytes ndarray, count). a/b as raw u64 patterns."""
+    src = np.ascontiguousarray(src, dtype=NP[type_])
+    bits = np.zeros(nbytes(src.size) + 32, dtype=np.uint8)
+    bits[nbytes(src.size):] = 0xFA  # poison guard like internal/cmp/tests/gen.go:13-44
+    cnt = lib().ko_cmp(type_, op, _p(src), src.size, a & (2**64 - 1), b & (2**64 - 1), _p(bits))
+    assert (bits[nbytes(src.size):] == 0xFA).all(), "oracle wrote past the bitset"
+    return bits[:nbytes(src.size)].copy(), int(cnt)
+
+
+class Container:
+    """A loaded oracle container over encoded bytes (keeps the buffer alive)."""
+
+    def __init__(self, type_, buf):
+        self.type = type_
+        self.buf = np.frombuffer(bytes(buf), dtype=np.uint8).copy()
+        h = C.c_void_p()
+        used = lib().ko_container_load(type_, _p(self.buf), self.buf.size, C.byref(h))
+        if used < 0:
+            raise ValueError("oracle: cannot load container")
+        self.used, self.h = used, h
+        self.n = int(C.cast(h, C.POINTER(_KoContainer)).contents.n)
+        self.ctype = int(C.cast(h, C.POINTER(_KoContainer)).contents.ctype)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().ko_container_free(self.h)
+            self.h = None
+
+    def decode(self):
+        out = np.zeros(max(self.n, 1), dtype=np.uint64)
+        lib().ko_container_decode(self.h, _p(out))
+        return out[:self.n]
+
+    def value_delta_sequences(self):
+        """Decoded sequences of delta containers that see the ORIGINAL predicate operands
+        (the container itself, or the Values child of nested run-end containers)."""
+        out = []
+        h = self.h
+        while h:
+            st = C.cast(h, C.POINTER(_KoContainer)).contents
+            if st.ctype == TDELTA:
+                seq = np.zeros(max(st.n, 1), dtype=np.uint64)
+                lib().ko_container_decode(h, _p(seq))
+                out.append(seq[:st.n].view(np.int64) if self.type <= I8 else seq[:st.n])
+            h = C.c_void_p(st.child[0]) if st.ctype == TRUNEND and st.child[0] else None
+        return out
+
+    def match(self, op, a, b=0):
+        bits = np.zeros(nbytes(self.n) + 8, dtype=np.uint8)
+        lib().ko_container_match(self.h, op, a & (2**64 - 1), b & (2**64 - 1), _p(bits))
+        return bits[:nbytes(self.n)].copy()
+
+    def match_set(self, values_u64, negate=False):
+        s = np.unique(np.asarray(values_u64, dtype=np.uint64))
+        bits = np.zeros(nbytes(self.n) + 8, dtype=np.uint8)
+        lib().ko_container_match_set(self.h, int(negate), _p(s), s.size, _p(bits))
+        return bits[:nbytes(self.n)].copy()
+
+
+class _KoContainer(C.Structure):
+    _fields_ = [("ctype", C.c_int), ("type", C.c_int), ("n", C.c_size_t), ("val", C.c_uint64),
+                ("delta", C.c_uint64), ("log2", C.c_int), ("payload", C.c_void_p),
+                ("payload_len", C.c_size_t), ("child", C.c_void_p * 2)]
+
+
+def store(kind, type_, values=None, **kw):
+    """Encode values (typed numpy array) with the named scheme → bytes (container only)."""
+    L = lib()
+    if kind == "const":
+        buf = np.zeros(64, dtype=np.uint8)
+        n = L.ko_store_const(_p(buf), scalar_u64(type_, kw["val"]), kw["n"])
+        return buf[:n].tobytes()
+    if kind == "delta":
+        buf = np.zeros(64, dtype=np.uint8)
+        n = L.ko_store_delta(_p(buf), scalar_u64(type_, kw["base"]), scalar_u64(type_, kw["delta"]), kw["n"])
+        return buf[:n].tobytes()
+    v = as_u64(type_, values)
+    buf = np.zeros(L.ko_store_bound(type_, v.size), dtype=np.uint8)
+    fn = {"raw": L.ko_store_raw, "bitpack": L.ko_store_bitpack, "dict": L.ko_store_dict,
+          "runend": L.ko_store_runend, "s8b": L.ko_store_s8b}.get(kind)
+    if kind == "best":
+        n = L.ko_store_best(_p(buf), type_, _p(v), v.size, kw.get("lvl", 3))
+    else:
+        n = fn(_p(buf), type_, _p(v), v.size)
+    return buf[:n].tobytes()
+
+
+class Agg(C.Structure):
+    _fields_ = [("count", C.c_int64), ("sum_bits", C.c_uint64), ("min_bits", C.c_uint64),
+                ("max_bits", C.c_uint64), ("valid", C.c_int)]
+
+
+def reduce(type_, values, bits=None, state=None):
+    v = as_u64(type_, values)
+    st = state or Agg()
+    b = np.ascontiguousarray(bits, dtype=np.uint8) if bits is not None else None
+    lib().ko_reduce(type_, _p(v), v.size, _p(b) if b is not None else None, C.byref(st))
+    return st
+
+
+def tree_eval(postfix, leaf_bits, n):
+    pf = np.asarray(postfix, dtype=np.uint8)
+    arrs = [np.ascontiguousarray(b, dtype=np.uint8) for b in leaf_bits]
+    ptrs = (C.c_void_p * len(arrs))(*[a.ctypes.data for a in arrs])
+    out = np.zeros(nbytes(n) + 8, dtype=np.uint8)
+    rc = lib().ko_tree_eval(_p(pf), pf.size, ptrs, len(arrs), n, _p(out))
+    assert rc == 0
+    return out[:nbytes(n)].copy()
