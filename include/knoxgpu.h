@@ -1,0 +1,212 @@
+/*
+ * knoxgpu.h — C ABI of libknoxgpu.so, the B200 (sm_100a) implementation of KnoxDB's
+ * pack-engine scan path: decode compressed column blocks → evaluate filter predicates
+ * into LSB-first bitsets → reduce matching rows to count/sum/min/max.
+ *
+ * The reference has no FFI for this path; the seams a replacement sits behind are Go
+ * interfaces.  Each entry point names the reference interface it
+ * replaces (paths relative to the knoxdb repository root).  INTEGRATION.md shows the
+ * cgo stubs that bind these symbols behind those interfaces.
+ *
+ * Conventions
+ *   - plain pointers + sizes, no C++/torch types; all functions are re-entrant per ctx
+ *   - return 0 on success, <0 (KX_E*) on error; kx_last_error(ctx) gives the message
+ *   - host pointers are never retained after return (cgo rule); kx_block_put copies
+ *   - bitsets: bit i of a pack ↔ byte i>>3, bit i&7 (internal/bitset/bitset.go:23-29),
+ *     ceil(n/8) bytes, tail bits zero
+ *   - element types are types.BlockType values, modes are types.FilterMode values
+ *   - there is NO CPU fallback: every call fails with KX_ENODEV without a CUDA device
+ */
+#ifndef KNOXGPU_H
+#define KNOXGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KX_ABI_VERSION 1
+
+/* error codes */
+enum {
+    KX_OK = 0, KX_EINVAL = -1, KX_ENODEV = -2, KX_ENOMEM = -3, KX_ECUDA = -4,
+    KX_ENOTFOUND = -5, KX_EFORMAT = -6, KX_EUNSUPPORTED = -7,
+};
+
+/* internal/types/block.go:20-36 (BlockType) */
+enum {
+    KX_INT64 = 1, KX_INT32 = 2, KX_INT16 = 3, KX_INT8 = 4,
+    KX_UINT64 = 5, KX_UINT32 = 6, KX_UINT16 = 7, KX_UINT8 = 8,
+    KX_FLOAT64 = 9, KX_FLOAT32 = 10,
+};
+
+/* internal/types/mode.go:14-23 (FilterMode) */
+enum {
+    KX_MODE_EQ = 1, KX_MODE_NE = 2, KX_MODE_GT = 3, KX_MODE_GE = 4, KX_MODE_LT = 5,
+    KX_MODE_LE = 6, KX_MODE_IN = 7, KX_MODE_NIN = 8, KX_MODE_RANGE = 9,
+};
+
+/* postfix program opcodes (filter tree, internal/operator/filter/node.go): a byte < 0x80
+ * pushes the bitset of leaf <byte>; KX_OP_AND / KX_OP_OR combine the two topmost. */
+#define KX_OP_AND 0xFE
+#define KX_OP_OR  0xFF
+#define KX_MAX_LEAVES 8
+#define KX_MAX_AGGS 4
+
+typedef struct kx_ctx kx_ctx;
+typedef struct kx_prog kx_prog;
+
+/* ---------------------------------------------------------------- lifecycle
+ * New (no reference counterpart; closest: engine options, pkg/knox/interface.go:29-50).
+ * device: CUDA ordinal; hbm_budget: max bytes of resident blocks (0 = 80% of free HBM). */
+int  kx_abi_version(void);
+int  kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out);
+void kx_ctx_destroy(kx_ctx* ctx);
+const char* kx_last_error(kx_ctx* ctx);   /* ctx may be NULL: error of the last failed kx_ctx_create */
+
+/* pinned host memory for encoded blocks / result buffers that cross PCIe at full speed
+ * (replaces internal/arena allocations for buffers handed to the scan) */
+void* kx_host_alloc(kx_ctx* ctx, size_t bytes);
+void  kx_host_free(kx_ctx* ctx, void* p);
+
+/* ---------------------------------------------------------------- device pack store
+ * Immutable (pack key, version, field id) → encoded block, exactly the bytes produced by
+ * Container.Store (internal/encode/int_*.go, float_raw.go) WITHOUT the outer compression
+ * byte of block.Encode (internal/block/encode.go:194-226; outer s2/lz4/zstd is undone on the
+ * host).  Replaces Package.LoadFromDisk + block.Decode → encode.LoadInt/LoadFloat
+ * (internal/pack/storage.go:128-190, internal/encode/int.go:109-115) as the source of
+ * column vectors for the scan.  Copies `len` bytes; returns the block's row count. */
+int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, uint8_t block_type,
+                 const void* enc, size_t len, uint32_t* nrows_out);
+int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field);
+int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes);
+
+/* ---------------------------------------------------------------- predicate program
+ * One leaf = one filter.Filter (internal/operator/filter/filter.go) with its Matcher
+ * (match_num.go:327-817): field, type, mode, operand(s).  a/b carry the operand as the
+ * 64-bit pattern of the type (sign-extended ints, IEEE bits for floats); RANGE uses [a,b].
+ * IN/NIN pass the set flattened to u64 values (xroar.Bitmap contents, `uint64(v)` of each
+ * member, internal/encode/int_raw.go:339-357); order and duplicates do not matter. */
+typedef struct kx_leaf {
+    uint16_t field;
+    uint8_t  block_type;
+    uint8_t  mode;
+    uint32_t nset;
+    uint64_t a, b;
+    const uint64_t* set;
+} kx_leaf;
+
+/* Replaces the compiled filter tree that filter.Match walks (match_core.go:14-215). */
+int  kx_prog_compile(kx_ctx* ctx, const kx_leaf* leaves, int nleaves,
+                     const uint8_t* postfix, int npost, kx_prog** out);
+void kx_prog_free(kx_prog* prog);
+
+/* ---------------------------------------------------------------- scan
+ * Replaces the per-pack hot loop Reader.nextQueryMatch → filter.Match → bits.Indexes /
+ * CountResult.Append / StreamResult.Append + Reducer.Reduce
+ * (internal/pack/table/reader.go:288-450, query/result.go:44-51,96-152,
+ * reducer/reducer.go:138-314) for a whole batch of packs in one call.
+ *
+ * aggregates: count/sum/min/max over the matching rows of one value column each. */
+typedef struct kx_packref { uint32_t pack, version; } kx_packref;
+typedef struct kx_agg_req { uint16_t field; uint8_t block_type; uint8_t reserved; } kx_agg_req;
+typedef struct kx_agg_out {
+    int64_t  count;       /* CountReducer */
+    uint64_t sum_bits;    /* SumReducer: ints wrap in T (pattern sign-extended to 64 bit); float64: IEEE bits */
+    double   sum_err;     /* float64: compensation term (sum = hi + err), 0 for ints */
+    uint64_t min_bits;    /* MinReducer / MaxReducer as 64-bit pattern of T */
+    uint64_t max_bits;
+    int32_t  valid;       /* 0 when no row matched (reducer Value() ok == false) */
+    int32_t  reserved;
+} kx_agg_out;
+
+/* bitsets (nullable): caller buffer; pack i's bitset starts at bitset_off[i] (multiple of
+ * 8) and spans ceil(n_i/8) bytes.  counts (nullable): npacks match counts.  agg_out
+ * (naggs entries) is combined over all packs of the call in pack order. */
+int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks,
+            uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
+            const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out);
+
+/* Same scan over blocks that still live in HOST memory (cold device cache): the blocks of
+ * all referenced fields are uploaded, scanned and dropped in pipelined batches.
+ * blocks[i*nfields + f] / block_len[...] = encoded block of pack i, field fields[f]. */
+int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks,
+                 const uint16_t* fields, const uint8_t* field_types, int nfields,
+                 const void* const* blocks, const size_t* block_len,
+                 uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
+                 const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out);
+
+/* Deterministic combine of per-shard partial aggregates (multi-GPU: the 64-byte partials
+ * are exchanged with ONE NCCL all-gather and combined in rank order). */
+int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_agg_out* out);
+
+/* Timing of the last kx_scan / kx_scan_host on this ctx (CUDA events on the scan stream):
+ * kernel_ms = device time of the scan kernels only, total_ms = first copy/launch → results
+ * on host.  launches = kernels launched.  (QueryStats: internal/query/stats.go:15-60) */
+int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* launches);
+
+/* ---------------------------------------------------------------- narrow drop-ins
+ * Host-pointer kernels with the signatures of the reference's leaf functions; used behind
+ * the assignable function variables / NumberMatcher methods and by the parity tests.
+ * Each call uploads, runs the same CUDA kernels as kx_scan, and downloads.
+ *
+ * kx_cmp: cmp.<Type><Op>(src []T, val T, bits []byte) int64 and <Type>Between(src, a, b, bits)
+ *         (internal/cmp/cmp.go:6-114, number.go:13-243, float.go:13-242).  mode ∈ EQ..LE, RANGE. */
+int64_t kx_cmp(kx_ctx* ctx, uint8_t block_type, uint8_t mode, const void* src, size_t n,
+               uint64_t a, uint64_t b, uint8_t* bits);
+
+/* kx_bitpack_cmp: bitpack.Equal/NotEqual/Less/LessEqual/Greater/GreaterEqual/Between
+ *         (buf, log2, val[, val2], n, bits) (internal/encode/bitpack/cmp.go:20-46);
+ *         operands are already in the min-FOR domain. Returns the match count. */
+int64_t kx_bitpack_cmp(kx_ctx* ctx, uint8_t mode, const void* packed, int log2, uint64_t a, uint64_t b,
+                       size_t n, uint8_t* bits);
+
+/* kx_bitpack_decode: bitpack.Decode(dst, buf, log2, minv) (bitpack/decode.go:131-208) into
+ *         n values of block_type. */
+int kx_bitpack_decode(kx_ctx* ctx, uint8_t block_type, const void* packed, int log2, uint64_t minv,
+                      size_t n, void* dst);
+
+/* kx_container_match: types.NumberMatcher[T].Match{Equal..Between,InSet,NotInSet}(val, bits, mask)
+ *         on an encoded container (internal/types/number.go:37-47, internal/block/access.go:42-44,
+ *         internal/encode/int_*.go Match*).  bits: ceil(n/8) bytes, overwritten. Returns count. */
+int64_t kx_container_match(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, uint8_t mode,
+                           uint64_t a, uint64_t b, const uint64_t* set, uint32_t nset, uint8_t* bits);
+
+/* kx_container_decode: NumberContainer[T].AppendTo(dst, nil) (internal/encode/int_*.go) */
+int kx_container_decode(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, void* dst, size_t dst_cap_rows);
+
+/* bitset.{And,AndFlag,AndNot,Or,OrFlag,Xor,Neg,PopCount} and Bitset.Indexes
+ * (internal/bitset/bitset.go:400-531, generic/bitset.go:13-396, iterator.go:269-290) */
+enum { KX_BIT_AND = 0, KX_BIT_ANDNOT = 1, KX_BIT_OR = 2, KX_BIT_XOR = 3 };
+int     kx_bitset_op(kx_ctx* ctx, int op, uint8_t* dst, const uint8_t* src, size_t nbits, int* any, int* all);
+int     kx_bitset_neg(kx_ctx* ctx, uint8_t* buf, size_t nbits);
+int64_t kx_bitset_popcount(kx_ctx* ctx, const uint8_t* buf, size_t nbits);
+int64_t kx_bitset_indexes(kx_ctx* ctx, const uint8_t* buf, size_t nbits, uint32_t* dst);
+
+/* ---------------------------------------------------------------- pruning
+ * Zone-map + bloom pruning of candidate packs, replacing stats.matchVector →
+ * Matcher.MatchRangeVectors + bloom.Filter.Contains per candidate
+ * (internal/pack/stats/match.go:92-195, operator/filter/match_num.go MatchRangeVectors,
+ * internal/filter/bloom/bloom.go:136-150,182-184).
+ * mins/maxs: npacks × nleaves 64-bit patterns (row-major: pack, leaf) of the leaf's column.
+ * blooms (nullable): npacks × nleaves pointers to bloom buffers ([k][m/8 bytes]) or NULL;
+ * bloom_len their byte lengths; hashes: per leaf the XXH3-64 of the probe value(s)
+ * (EQ: 1 hash; IN: nset hashes, concatenated; hash_off[nleaves+1]).
+ * out: ceil(npacks/8) bytes, bit set = pack may match. Returns number of surviving packs. */
+int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks,
+                 const uint64_t* mins, const uint64_t* maxs,
+                 const void* const* blooms, const size_t* bloom_len,
+                 const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out);
+
+/* hash.Uint64/Uint32/Uint16/Uint8 and hash.Hash ([]byte) (internal/hash/hash.go:26,67-92,
+ * xxh3.go:22-58): XXH3-64, seed 0.  Computed on the host side of the library (one hash per
+ * probe value per query). */
+uint64_t kx_hash_value(uint8_t block_type, uint64_t pattern);
+uint64_t kx_hash_bytes(const void* p, size_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KNOXGPU_H */

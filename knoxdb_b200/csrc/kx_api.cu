@@ -1,0 +1,1006 @@
+// kx_api.cu — C ABI of libknoxgpu.so (see include/knoxgpu.h): context, device pack store,
+// predicate programs, batched scans and the narrow drop-in entry points.
+//
+// There is no CPU fallback anywhere in this file: every entry point needs a CUDA device and
+// fails with KX_ENODEV / KX_ECUDA otherwise.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <tuple>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/knoxgpu.h"
+#include "kx_host.h"
+#include "kx_kernels.h"
+#include "kx_types.h"
+
+using namespace kx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+constexpr size_t STREAM_PAD = 64;      // slack after every bit stream (TMA 16 B rounding, idx+2 over-read)
+constexpr size_t SLAB_BYTES = 256ull << 20;
+
+size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// grow-only device / pinned buffers
+struct DevBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = round_up(std::max(n, size_t(4096)) * 5 / 4, 4096);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) { cap = want; e = cudaMemset(p, 0, want); }
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+};
+struct PinBuf {
+    void* p = nullptr; size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        size_t want = round_up(std::max(n, size_t(4096)) * 5 / 4, 4096);
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    ~PinBuf() { if (p) cudaFreeHost(p); }
+};
+
+// slab allocator for resident blocks: 256 B aligned bump allocation, slabs are released when
+// all their blocks were dropped
+struct Slab { uint8_t* base; size_t cap, used, live; };
+
+struct StoredBlock {
+    ColView view{};
+    std::vector<uint64_t> dict;     // host copy of dictionary values (leaf translation)
+    std::vector<std::pair<int, size_t>> allocs;   // (slab index, bytes)
+    size_t enc_len = 0;
+};
+
+struct BlockKey {
+    uint32_t pack, ver; uint16_t field;
+    bool operator<(const BlockKey& o) const { return std::tie(pack, ver, field) < std::tie(o.pack, o.ver, o.field); }
+};
+
+}  // namespace
+
+struct kx_prog {
+    kx_ctx* ctx = nullptr;
+    std::vector<LeafSpec> leaves;
+    std::vector<uint8_t> postfix;
+    std::vector<uint64_t> sets;          // concatenated sorted sets
+    uint32_t set_off[MAX_LEAVES + 1] = {0};
+    uint64_t* dev_sets = nullptr;
+};
+
+struct kx_ctx {
+    int device = 0;
+    int num_sms = 148;
+    size_t budget = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_k0 = nullptr, ev_k1 = nullptr, ev_end = nullptr;
+    std::mutex mu;
+    std::string err;
+
+    std::vector<Slab> slabs;
+    std::map<BlockKey, StoredBlock> store;
+    size_t store_enc_bytes = 0, store_dev_bytes = 0;
+
+    // scratch (grow only)
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc;
+    PinBuf h_desc, h_res;
+
+    double last_kernel_ms = 0, last_total_ms = 0;
+    int last_launches = 0;
+};
+
+namespace {
+
+int fail(kx_ctx* c, int code, const std::string& msg) {
+    if (c) c->err = msg; else g_create_error = msg;
+    return code;
+}
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(ctx, KX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
+    } while (0)
+
+// ------------------------------------------------------------------ slab allocation
+int slab_alloc(kx_ctx* ctx, size_t bytes, uint8_t** out, int* slab_idx) {
+    bytes = round_up(bytes, 256);
+    for (size_t i = 0; i < ctx->slabs.size(); ++i) {
+        Slab& s = ctx->slabs[i];
+        if (s.base && s.cap - s.used >= bytes) {
+            *out = s.base + s.used; s.used += bytes; s.live += bytes; *slab_idx = int(i);
+            return KX_OK;
+        }
+    }
+    if (ctx->budget && ctx->store_dev_bytes + bytes > ctx->budget) return fail(ctx, KX_ENOMEM, "HBM budget exceeded");
+    size_t cap = std::max(bytes, SLAB_BYTES);
+    uint8_t* p = nullptr;
+    cudaError_t e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, KX_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
+    size_t idx = ctx->slabs.size();
+    for (size_t i = 0; i < ctx->slabs.size(); ++i) if (!ctx->slabs[i].base) { idx = i; break; }
+    if (idx == ctx->slabs.size()) ctx->slabs.push_back(Slab{});
+    ctx->slabs[idx] = Slab{p, cap, bytes, bytes};
+    *out = p; *slab_idx = int(idx);
+    return KX_OK;
+}
+
+void slab_release(kx_ctx* ctx, int idx, size_t bytes) {
+    Slab& s = ctx->slabs[size_t(idx)];
+    s.live -= round_up(bytes, 256);
+    if (s.live == 0 && s.base) { cudaFree(s.base); s = Slab{nullptr, 0, 0, 0}; }
+}
+
+// upload one normalised block; `into` receives device pointers.  Synchronous w.r.t. the host
+// buffers only if they are pageable (cudaMemcpyAsync semantics); pinned sources stay async.
+int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
+    sb.view = lay.view;
+    auto put = [&](const void* src, size_t len, const uint8_t** devp) -> int {
+        uint8_t* d = nullptr; int si = 0;
+        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &si);
+        if (rc) return rc;
+        sb.allocs.push_back({si, len + STREAM_PAD});
+        ctx->store_dev_bytes += round_up(len + STREAM_PAD, 256);
+        if (len) CK(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(d + len, 0, STREAM_PAD, ctx->stream));
+        *devp = d;
+        return KX_OK;
+    };
+    int rc;
+    const ColView& v = lay.view;
+    if (v.kind == CK_BITS || v.kind == CK_DICT) {
+        const void* src = lay.owned.empty() ? (const void*)lay.stream : (const void*)lay.owned.data();
+        size_t len = lay.owned.empty() ? lay.stream_len : lay.owned.size();
+        if ((rc = put(src, len, &sb.view.data))) return rc;
+    }
+    if (v.kind == CK_DICT) {
+        if ((rc = put(lay.aux64.data(), lay.aux64.size() * 8, &sb.view.aux))) return rc;
+        sb.dict = lay.aux64;
+    }
+    if (v.kind == CK_RUNEND) {
+        if ((rc = put(lay.aux64.data(), lay.aux64.size() * 8, &sb.view.data))) return rc;
+        if ((rc = put(lay.aux32.data(), lay.aux32.size() * 4, &sb.view.aux))) return rc;
+    }
+    if (!lay.owned.empty() || v.kind == CK_DICT || v.kind == CK_RUNEND) {
+        // host-owned temporaries (lay.owned / aux vectors) die with `lay`: finish the copies now
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return KX_OK;
+}
+
+void free_block(kx_ctx* ctx, StoredBlock& sb) {
+    for (auto& a : sb.allocs) { slab_release(ctx, a.first, a.second); ctx->store_dev_bytes -= round_up(a.second, 256); }
+    sb.allocs.clear();
+}
+
+// ------------------------------------------------------------------ the scan driver
+struct ScanJob {
+    int npacks = 0;
+    std::vector<uint32_t> nrows;               // [npacks]
+    std::vector<ColView> leaf_views;           // [npacks][nleaves]
+    std::vector<const uint64_t*> leaf_dicts;   // [npacks][nleaves] host dict copies (or null)
+    std::vector<ColView> agg_views;            // [npacks][naggs]
+};
+
+int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bitsets, const size_t* bitset_off,
+             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    const int npacks = job.npacks, nleaves = int(prog->leaves.size());
+    ctx->last_kernel_ms = ctx->last_total_ms = 0; ctx->last_launches = 0;
+    if (naggs < 0 || naggs > MAX_AGGS) return fail(ctx, KX_EINVAL, "too many aggregates");
+    for (int j = 0; j < naggs; ++j) {
+        int t = aggs[j].block_type;
+        if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
+    }
+    if (npacks == 0) {
+        for (int j = 0; j < naggs; ++j) agg_out[j] = kx_agg_out{};
+        return KX_OK;
+    }
+    if (bitsets && !bitset_off) return fail(ctx, KX_EINVAL, "bitsets without bitset_off");
+
+    // ---- per-pack / per-leaf descriptors (host), pinned staging
+    size_t sz_packs = sizeof(PackInfo) * size_t(npacks), sz_leaves = sizeof(PackLeaf) * size_t(npacks) * size_t(nleaves);
+    size_t nviews = size_t(npacks) * size_t(nleaves + naggs), sz_views = sizeof(ColView) * nviews;
+    size_t off_leaves = round_up(sz_packs, 256), off_views = off_leaves + round_up(sz_leaves, 256);
+    size_t off_tiles = off_views + round_up(sz_views, 256);
+
+    // tile geometry: widest staged bits/row over all packs decides R (rows per tile = 256 R)
+    std::vector<PackLeaf> pl(size_t(npacks) * size_t(nleaves));
+    uint32_t max_stage_bits = 0;
+    bool uniform = true;
+    for (int p = 0; p < npacks; ++p) {
+        uint32_t bits = 0;
+        for (int l = 0; l < nleaves; ++l) {
+            const ColView& v = job.leaf_views[size_t(p) * nleaves + l];
+            if (v.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
+            PackLeaf& o = pl[size_t(p) * nleaves + l];
+            compile_leaf(v, job.leaf_dicts[size_t(p) * nleaves + l], prog->leaves[size_t(l)], uint32_t(size_t(p) * nleaves + l), o);
+            bits += uint32_t(leaf_stage_width(o));
+        }
+        for (int j = 0; j < naggs; ++j)
+            if (job.agg_views[size_t(p) * naggs + j].n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "value block length differs from pack");
+        max_stage_bits = std::max(max_stage_bits, bits);
+        if (job.nrows[size_t(p)] != job.nrows[0]) uniform = false;
+    }
+    uint32_t R = 32;
+    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + 16u * size_t(nleaves) + 16, 128); };
+    while (R > 1 && stage_bytes_for(R) > 24 * 1024) R >>= 1;
+    const uint32_t tile_rows = 256 * R;
+    const size_t stage_bytes = stage_bytes_for(R);
+    const size_t smem_bytes = 128 + STAGES * stage_bytes;
+
+    uint64_t ntiles64 = 0;
+    std::vector<uint32_t> tile0(size_t(npacks) + 1);
+    for (int p = 0; p < npacks; ++p) {
+        tile0[size_t(p)] = uint32_t(ntiles64);
+        ntiles64 += (uint64_t(job.nrows[size_t(p)]) + tile_rows - 1) / tile_rows;
+    }
+    if (ntiles64 > 0xfffffff0ull) return fail(ctx, KX_EINVAL, "too many tiles in one scan call");
+    const uint32_t ntiles = uint32_t(ntiles64);
+    size_t sz_tiles = uniform ? 0 : sizeof(uint32_t) * size_t(ntiles);
+    size_t desc_bytes = off_tiles + round_up(sz_tiles, 256);
+
+    CK(ctx->h_desc.reserve(desc_bytes));
+    CK(ctx->d_packs.reserve(desc_bytes));
+    uint8_t* hd = static_cast<uint8_t*>(ctx->h_desc.p);
+    PackInfo* h_packs = reinterpret_cast<PackInfo*>(hd);
+    size_t bitset_total = 0;
+    for (int p = 0; p < npacks; ++p) {
+        size_t off = bitsets ? bitset_off[p] : 0;
+        if (bitsets && (off & 7)) return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8");
+        h_packs[p] = PackInfo{job.nrows[size_t(p)], tile0[size_t(p)], off};
+        if (bitsets) bitset_total = std::max(bitset_total, off + (size_t(job.nrows[size_t(p)]) + 7) / 8);
+    }
+    std::memcpy(hd + off_leaves, pl.data(), sz_leaves);
+    ColView* h_views = reinterpret_cast<ColView*>(hd + off_views);
+    if (nleaves) std::memcpy(h_views, job.leaf_views.data(), sizeof(ColView) * size_t(npacks) * nleaves);
+    if (naggs) std::memcpy(h_views + size_t(npacks) * nleaves, job.agg_views.data(), sizeof(ColView) * size_t(npacks) * naggs);
+    if (!uniform) {
+        uint32_t* tp = reinterpret_cast<uint32_t*>(hd + off_tiles);
+        for (int p = 0; p < npacks; ++p)
+            for (uint32_t t = tile0[size_t(p)]; t < (p + 1 < npacks ? tile0[size_t(p) + 1] : ntiles); ++t) tp[t] = uint32_t(p);
+    }
+
+    // ---- launch geometry: persistent grid, static round-robin tile assignment
+    int occ = int(std::min<size_t>(2, (227 * 1024) / (smem_bytes + 1024)));
+    if (occ < 1) occ = 1;
+    int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * occ));
+    if (grid < 1) grid = 1;
+
+    CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
+    if (bitsets) CK(ctx->d_bitsets.reserve(round_up(bitset_total, 8) + 64));
+    if (naggs) {
+        CK(ctx->d_partials.reserve(sizeof(AggPartial) * size_t(grid) * naggs));
+        CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS));
+        CK(ctx->d_aggtype.reserve(16));
+    }
+    CK(ctx->h_res.reserve(sizeof(unsigned long long) * size_t(npacks) + sizeof(AggPartial) * MAX_AGGS + 64));
+
+    uint8_t* dd = static_cast<uint8_t*>(ctx->d_packs.p);
+    ScanParams P{};
+    P.packs = reinterpret_cast<const PackInfo*>(dd);
+    P.leaves = reinterpret_cast<const PackLeaf*>(dd + off_leaves);
+    P.views = reinterpret_cast<const ColView*>(dd + off_views);
+    P.tile_pack = uniform ? nullptr : reinterpret_cast<const uint32_t*>(dd + off_tiles);
+    P.set_vals = prog->dev_sets;
+    P.bitsets = bitsets ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
+    P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
+    P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
+    P.npacks = uint32_t(npacks); P.ntiles = ntiles;
+    P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size()); P.naggs = uint32_t(naggs);
+    P.R = R; P.tiles_per_pack = uniform ? (ntiles / uint32_t(npacks)) : 0; P.stage_bytes = uint32_t(stage_bytes);
+    std::memcpy(P.set_off, prog->set_off, sizeof(P.set_off));
+    P.agg_view0 = uint32_t(size_t(npacks) * nleaves); P.leaf_view0 = 0;
+    std::memcpy(P.postfix, prog->postfix.data(), prog->postfix.size());
+    for (int j = 0; j < naggs; ++j) P.agg_type[j] = aggs[j].block_type;
+    if (uniform && P.tiles_per_pack == 0) P.tiles_per_pack = 1;   // all packs empty
+
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * size_t(npacks), ctx->stream));
+    if (naggs) CK(cudaMemcpyAsync(ctx->d_aggtype.p, P.agg_type, MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, ctx->stream)); ctx->last_launches++; }
+    if (naggs) {
+        if (ntiles) {
+            CK(launch_finalize(P.partials, uint32_t(grid), uint32_t(naggs), static_cast<const uint8_t*>(ctx->d_aggtype.p),
+                               static_cast<AggPartial*>(ctx->d_aggout.p), ctx->stream));
+            ctx->last_launches++;
+        } else CK(cudaMemsetAsync(ctx->d_aggout.p, 0, sizeof(AggPartial) * MAX_AGGS, ctx->stream));
+    }
+    CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+
+    // ---- results back to the host
+    uint8_t* hr = static_cast<uint8_t*>(ctx->h_res.p);
+    size_t res_counts = sizeof(unsigned long long) * size_t(npacks);
+    if (counts) CK(cudaMemcpyAsync(hr, ctx->d_counts.p, res_counts, cudaMemcpyDeviceToHost, ctx->stream));
+    if (naggs) CK(cudaMemcpyAsync(hr + round_up(res_counts, 64), ctx->d_aggout.p, sizeof(AggPartial) * size_t(naggs), cudaMemcpyDeviceToHost, ctx->stream));
+    if (bitsets && bitset_total) CK(cudaMemcpyAsync(bitsets, ctx->d_bitsets.p, bitset_total, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1)); ctx->last_kernel_ms = ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end)); ctx->last_total_ms = ms;
+
+    if (counts) for (int p = 0; p < npacks; ++p) counts[p] = int64_t(reinterpret_cast<unsigned long long*>(hr)[p]);
+    const AggPartial* fin = reinterpret_cast<const AggPartial*>(hr + round_up(res_counts, 64));
+    for (int j = 0; j < naggs; ++j) {
+        kx_agg_out o{};
+        const AggPartial& a = fin[j];
+        int t = aggs[j].block_type;
+        o.count = int64_t(a.count); o.valid = a.valid ? 1 : 0;
+        if (a.valid) {
+            if (t == KX_FLOAT64) {
+                double hi, s; std::memcpy(&hi, &a.sum, 8);
+                s = hi + a.err;
+                std::memcpy(&o.sum_bits, &s, 8);
+                o.sum_err = (hi - s) + a.err;
+                o.min_bits = a.mn; o.max_bits = a.mx;
+            } else {
+                uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
+                o.sum_bits = type_ext(t, a.sum);     // SumReducer wraps in T
+                o.min_bits = a.mn ^ flip; o.max_bits = a.mx ^ flip;
+            }
+        }
+        agg_out[j] = o;
+    }
+    return KX_OK;
+}
+
+int check_prog_job(kx_ctx* ctx, const kx_prog* prog) {
+    if (!prog || prog->ctx != ctx) return fail(ctx, KX_EINVAL, "program does not belong to this context");
+    return KX_OK;
+}
+
+// temporary single-block helpers for the narrow drop-ins
+struct TempBlock {
+    kx_ctx* ctx; StoredBlock sb;
+    explicit TempBlock(kx_ctx* c) : ctx(c) {}
+    ~TempBlock() { free_block(ctx, sb); }
+};
+
+int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* postfix, int npost, kx_prog** out);
+
+int single_leaf_scan(kx_ctx* ctx, const StoredBlock& sb, uint8_t block_type, uint8_t mode, uint64_t a, uint64_t b,
+                     const uint64_t* set, uint32_t nset, uint8_t* bits, int64_t* count) {
+    kx_leaf lf{}; lf.field = 0; lf.block_type = block_type; lf.mode = mode; lf.a = a; lf.b = b; lf.set = set; lf.nset = nset;
+    uint8_t pf = 0;
+    kx_prog* prog = nullptr;
+    int rc = make_prog(ctx, &lf, 1, &pf, 1, &prog);
+    if (rc) return rc;
+    ScanJob job; job.npacks = 1; job.nrows = {sb.view.n}; job.leaf_views = {sb.view};
+    job.leaf_dicts = {sb.dict.empty() ? nullptr : sb.dict.data()};
+    size_t off = 0;
+    rc = run_scan(ctx, prog, job, bits, &off, count, nullptr, 0, nullptr);
+    if (prog->dev_sets) cudaFree(prog->dev_sets);
+    delete prog;
+    return rc;
+}
+
+int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* postfix, int npost, kx_prog** out) {
+    if (!leaves || nleaves < 1 || nleaves > MAX_LEAVES) return fail(ctx, KX_EINVAL, "program needs 1..8 leaves");
+    if (!postfix || npost < 1 || npost > MAX_POSTFIX) return fail(ctx, KX_EINVAL, "bad postfix length");
+    int depth = 0;
+    for (int i = 0; i < npost; ++i) {
+        if (postfix[i] < 0x80) { if (postfix[i] >= nleaves) return fail(ctx, KX_EINVAL, "postfix references unknown leaf"); depth++; }
+        else if (postfix[i] == KX_OP_AND || postfix[i] == KX_OP_OR) { if (depth < 2) return fail(ctx, KX_EINVAL, "postfix stack underflow"); depth--; }
+        else return fail(ctx, KX_EINVAL, "bad postfix opcode");
+    }
+    if (depth != 1) return fail(ctx, KX_EINVAL, "postfix does not reduce to one bitset");
+    auto p = std::make_unique<kx_prog>();
+    p->ctx = ctx;
+    p->postfix.assign(postfix, postfix + npost);
+    for (int l = 0; l < nleaves; ++l) {
+        const kx_leaf& in = leaves[l];
+        LeafSpec s; s.field = in.field; s.type = in.block_type; s.mode = in.mode; s.a = in.a; s.b = in.b;
+        if (type_bits(s.type) == 0) return fail(ctx, KX_EINVAL, "leaf: unsupported block type");
+        if (s.mode < KX_MODE_EQ || s.mode > KX_MODE_RANGE) return fail(ctx, KX_EINVAL, "leaf: unsupported filter mode");
+        if (s.mode == KX_MODE_IN || s.mode == KX_MODE_NIN) {
+            // float IN/NIN are no-ops in the reference containers (float_raw.go:209-210) and are
+            // matched by a separate matcher; out of scope here
+            if (type_is_float(s.type)) return fail(ctx, KX_EUNSUPPORTED, "IN/NIN on float blocks is not supported");
+            if (in.nset && !in.set) return fail(ctx, KX_EINVAL, "leaf: set pointer missing");
+            s.set.assign(in.set, in.set + in.nset);
+            std::sort(s.set.begin(), s.set.end());
+            s.set.erase(std::unique(s.set.begin(), s.set.end()), s.set.end());
+        }
+        s.set_off = uint32_t(p->sets.size());
+        p->set_off[l] = s.set_off;
+        p->sets.insert(p->sets.end(), s.set.begin(), s.set.end());
+        p->leaves.push_back(std::move(s));
+    }
+    for (int l = nleaves; l <= MAX_LEAVES; ++l) p->set_off[l] = uint32_t(p->sets.size());
+    if (!p->sets.empty()) {
+        CK(cudaMalloc(&p->dev_sets, p->sets.size() * 8));
+        CK(cudaMemcpyAsync(p->dev_sets, p->sets.data(), p->sets.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    *out = p.release();
+    return KX_OK;
+}
+
+}  // namespace
+
+// =============================================================================== C ABI
+extern "C" {
+
+int kx_abi_version(void) { return KX_ABI_VERSION; }
+
+int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
+    if (!out) return KX_EINVAL;
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(nullptr, KX_ENODEV, std::string("no CUDA device: ") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0"));
+    }
+    if (device < 0 || device >= ndev) return fail(nullptr, KX_EINVAL, "bad device ordinal");
+    kx_ctx* ctx = nullptr;   // for CK
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    CK(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 9) return fail(nullptr, KX_ENODEV, "libknoxgpu needs an sm_100a (Blackwell) device");
+    auto c = std::make_unique<kx_ctx>();
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    CK(cudaMemGetInfo(&free_b, &total_b));
+    c->budget = hbm_budget ? hbm_budget : free_b / 10 * 8;
+    CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CK(cudaEventCreate(&c->ev_start)); CK(cudaEventCreate(&c->ev_k0)); CK(cudaEventCreate(&c->ev_k1)); CK(cudaEventCreate(&c->ev_end));
+    *out = c.release();
+    return KX_OK;
+}
+
+void kx_ctx_destroy(kx_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& s : ctx->slabs) if (s.base) cudaFree(s.base);
+    cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* kx_last_error(kx_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+void* kx_host_alloc(kx_ctx* ctx, size_t bytes) {
+    if (!ctx) return nullptr;
+    cudaSetDevice(ctx->device);
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) { cudaGetLastError(); ctx->err = "cudaMallocHost failed"; return nullptr; }
+    return p;
+}
+void kx_host_free(kx_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->device); cudaFreeHost(p); } }
+
+int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, uint8_t block_type, const void* enc, size_t len,
+                 uint32_t* nrows_out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!enc || !len) return fail(ctx, KX_EINVAL, "empty block");
+    CK(cudaSetDevice(ctx->device));
+    BlockLayout lay; std::string err;
+    int rc = normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
+    if (rc) return fail(ctx, rc, "kx_block_put: " + err);
+    BlockKey key{pack, version, field};
+    auto it = ctx->store.find(key);
+    if (it != ctx->store.end()) { ctx->store_enc_bytes -= it->second.enc_len; free_block(ctx, it->second); ctx->store.erase(it); }
+    StoredBlock sb;
+    rc = upload_block(ctx, lay, sb);
+    if (rc) { free_block(ctx, sb); return rc; }
+    // the caller's buffer may be reused after return (cgo rule): finish the copy
+    CK(cudaStreamSynchronize(ctx->stream));
+    sb.enc_len = len;
+    ctx->store_enc_bytes += len;
+    if (nrows_out) *nrows_out = sb.view.n;
+    ctx->store.emplace(key, std::move(sb));
+    return KX_OK;
+}
+
+int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->store.find(BlockKey{pack, version, field});
+    if (it == ctx->store.end()) return fail(ctx, KX_ENOTFOUND, "block not resident");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->store_enc_bytes -= it->second.enc_len;
+    free_block(ctx, it->second);
+    ctx->store.erase(it);
+    return KX_OK;
+}
+
+int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nblocks) *nblocks = ctx->store.size();
+    if (encoded_bytes) *encoded_bytes = ctx->store_enc_bytes;
+    if (device_bytes) *device_bytes = ctx->store_dev_bytes;
+    return KX_OK;
+}
+
+int kx_prog_compile(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* postfix, int npost, kx_prog** out) {
+    if (!ctx || !out) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    CK(cudaSetDevice(ctx->device));
+    return make_prog(ctx, leaves, nleaves, postfix, npost, out);
+}
+
+void kx_prog_free(kx_prog* prog) {
+    if (!prog) return;
+    if (prog->dev_sets) { cudaSetDevice(prog->ctx->device); cudaFree(prog->dev_sets); }
+    delete prog;
+}
+
+int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint8_t* bitsets, const size_t* bitset_off,
+            int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog);
+    if (rc) return rc;
+    if (npacks < 0 || (npacks && !packs)) return fail(ctx, KX_EINVAL, "bad pack list");
+    if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
+    CK(cudaSetDevice(ctx->device));
+    const int nleaves = int(prog->leaves.size());
+    ScanJob job; job.npacks = npacks;
+    job.nrows.resize(size_t(npacks));
+    job.leaf_views.resize(size_t(npacks) * nleaves);
+    job.leaf_dicts.resize(size_t(npacks) * nleaves);
+    job.agg_views.resize(size_t(npacks) * size_t(naggs));
+    for (int p = 0; p < npacks; ++p) {
+        for (int l = 0; l < nleaves; ++l) {
+            auto it = ctx->store.find(BlockKey{packs[p].pack, packs[p].version, prog->leaves[size_t(l)].field});
+            if (it == ctx->store.end()) return fail(ctx, KX_ENOTFOUND, "filter block not resident: pack " + std::to_string(packs[p].pack));
+            if (it->second.view.type != prog->leaves[size_t(l)].type) return fail(ctx, KX_EINVAL, "leaf / block type mismatch");
+            job.leaf_views[size_t(p) * nleaves + l] = it->second.view;
+            job.leaf_dicts[size_t(p) * nleaves + l] = it->second.dict.empty() ? nullptr : it->second.dict.data();
+            if (l == 0) job.nrows[size_t(p)] = it->second.view.n;
+        }
+        for (int j = 0; j < naggs; ++j) {
+            auto it = ctx->store.find(BlockKey{packs[p].pack, packs[p].version, aggs[j].field});
+            if (it == ctx->store.end()) return fail(ctx, KX_ENOTFOUND, "value block not resident: pack " + std::to_string(packs[p].pack));
+            if (it->second.view.type != aggs[j].block_type) return fail(ctx, KX_EINVAL, "aggregate / block type mismatch");
+            job.agg_views[size_t(p) * naggs + j] = it->second.view;
+        }
+    }
+    return run_scan(ctx, prog, job, bitsets, bitset_off, counts, aggs, naggs, agg_out);
+}
+
+int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,
+                 const void* const* blocks, const size_t* block_len, uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
+                 const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog);
+    if (rc) return rc;
+    if (npacks < 0 || nfields < 1 || !fields || !field_types || (npacks && (!blocks || !block_len))) return fail(ctx, KX_EINVAL, "bad block table");
+    if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
+    CK(cudaSetDevice(ctx->device));
+    const int nleaves = int(prog->leaves.size());
+    auto field_index = [&](uint16_t f) { for (int i = 0; i < nfields; ++i) if (fields[i] == f) return i; return -1; };
+    std::vector<int> leaf_fi(static_cast<size_t>(nleaves)), agg_fi(static_cast<size_t>(naggs));
+    for (int l = 0; l < nleaves; ++l) {
+        leaf_fi[size_t(l)] = field_index(prog->leaves[size_t(l)].field);
+        if (leaf_fi[size_t(l)] < 0) return fail(ctx, KX_EINVAL, "leaf field missing from block table");
+        if (field_types[leaf_fi[size_t(l)]] != prog->leaves[size_t(l)].type) return fail(ctx, KX_EINVAL, "leaf / block type mismatch");
+    }
+    for (int j = 0; j < naggs; ++j) {
+        agg_fi[size_t(j)] = field_index(aggs[j].field);
+        if (agg_fi[size_t(j)] < 0) return fail(ctx, KX_EINVAL, "aggregate field missing from block table");
+        if (field_types[agg_fi[size_t(j)]] != aggs[j].block_type) return fail(ctx, KX_EINVAL, "aggregate / block type mismatch");
+    }
+
+    // Batches bounded by encoded bytes so the transient device footprint stays small; the
+    // H2D copies of a batch are queued asynchronously (pinned sources) ahead of its kernel.
+    const size_t BATCH_BYTES = 2048ull << 20;
+    std::vector<kx_agg_out> part(static_cast<size_t>(naggs));
+    std::vector<std::vector<kx_agg_out>> parts(static_cast<size_t>(naggs));
+    double kms = 0, tms = 0; int launches = 0;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    CK(cudaEventRecord(e0, ctx->stream));
+    int p0 = 0;
+    while (p0 < npacks) {
+        size_t bytes = 0; int p1 = p0;
+        while (p1 < npacks) {
+            size_t b = 0;
+            for (int f = 0; f < nfields; ++f) b += block_len[size_t(p1) * nfields + f];
+            if (p1 > p0 && bytes + b > BATCH_BYTES) break;
+            bytes += b; ++p1;
+        }
+        const int nb = p1 - p0;
+        std::vector<StoredBlock> tmp(size_t(nb) * nfields);
+        auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); for (auto& sb : tmp) free_block(ctx, sb); };
+        for (int p = 0; p < nb; ++p) {
+            for (int f = 0; f < nfields; ++f) {
+                size_t bi = size_t(p0 + p) * nfields + f;
+                BlockLayout lay; std::string err;
+                rc = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lay, err);
+                if (rc) { cleanup(); return fail(ctx, rc, "kx_scan_host: " + err); }
+                rc = upload_block(ctx, lay, tmp[size_t(p) * nfields + f]);
+                if (rc) { cleanup(); return rc; }
+            }
+        }
+        ScanJob job; job.npacks = nb;
+        job.nrows.resize(size_t(nb)); job.leaf_views.resize(size_t(nb) * nleaves); job.leaf_dicts.resize(size_t(nb) * nleaves);
+        job.agg_views.resize(size_t(nb) * size_t(naggs));
+        for (int p = 0; p < nb; ++p) {
+            job.nrows[size_t(p)] = tmp[size_t(p) * nfields].view.n;
+            for (int l = 0; l < nleaves; ++l) {
+                const StoredBlock& sb = tmp[size_t(p) * nfields + leaf_fi[size_t(l)]];
+                job.leaf_views[size_t(p) * nleaves + l] = sb.view;
+                job.leaf_dicts[size_t(p) * nleaves + l] = sb.dict.empty() ? nullptr : sb.dict.data();
+            }
+            for (int j = 0; j < naggs; ++j) job.agg_views[size_t(p) * naggs + j] = tmp[size_t(p) * nfields + agg_fi[size_t(j)]].view;
+        }
+        // bitset offsets of this batch are relative to the caller's buffer start; shift so the
+        // device buffer only spans the batch
+        std::vector<size_t> offs;
+        uint8_t* bdst = nullptr;
+        if (bitsets) {
+            size_t base = bitset_off[p0];
+            for (int p = 0; p < nb; ++p) {
+                if (bitset_off[p0 + p] < base) { cleanup(); return fail(ctx, KX_EINVAL, "bitset_off must be ascending"); }
+                offs.push_back(bitset_off[p0 + p] - base);
+            }
+            if (base & 7) { cleanup(); return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8"); }
+            bdst = bitsets + base;
+        }
+        rc = run_scan(ctx, prog, job, bdst, bitsets ? offs.data() : nullptr, counts ? counts + p0 : nullptr, aggs, naggs,
+                      naggs ? part.data() : nullptr);
+        kms += ctx->last_kernel_ms; launches += ctx->last_launches;
+        cleanup();
+        if (rc) return rc;
+        for (int j = 0; j < naggs; ++j) parts[size_t(j)].push_back(part[size_t(j)]);
+        p0 = p1;
+    }
+    CK(cudaEventRecord(e1, ctx->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1)); tms = ms;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    for (int j = 0; j < naggs; ++j) {
+        if (parts[size_t(j)].empty()) agg_out[j] = kx_agg_out{};
+        else kx_agg_combine(aggs[j].block_type, parts[size_t(j)].data(), int(parts[size_t(j)].size()), &agg_out[j]);
+    }
+    ctx->last_kernel_ms = kms; ctx->last_total_ms = tms; ctx->last_launches = launches;
+    return KX_OK;
+}
+
+int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_agg_out* out) {
+    if (!out || nparts < 0 || (nparts && !parts)) return KX_EINVAL;
+    int t = block_type;
+    if (type_bits(t) == 0) return KX_EINVAL;
+    kx_agg_out r{};
+    double fs = 0, fe = 0;
+    for (int i = 0; i < nparts; ++i) {
+        const kx_agg_out& p = parts[i];
+        if (!p.valid) continue;
+        double ps = 0; std::memcpy(&ps, &p.sum_bits, 8);
+        if (!r.valid) {
+            r = p; fs = ps; fe = p.sum_err;
+            continue;
+        }
+        r.count += p.count;
+        if (t == KX_FLOAT64) {
+            double tt = fs + ps;
+            double c = (std::abs(fs) >= std::abs(ps)) ? ((fs - tt) + ps) : ((ps - tt) + fs);
+            fs = tt; fe += p.sum_err + c;
+            double a, b; std::memcpy(&a, &r.min_bits, 8); std::memcpy(&b, &p.min_bits, 8); if (b < a) r.min_bits = p.min_bits;
+            std::memcpy(&a, &r.max_bits, 8); std::memcpy(&b, &p.max_bits, 8); if (b > a) r.max_bits = p.max_bits;
+        } else {
+            r.sum_bits = type_ext(t, r.sum_bits + p.sum_bits);
+            bool sg = type_is_signed(t);
+            auto lt = [&](uint64_t x, uint64_t y) { return sg ? int64_t(x) < int64_t(y) : x < y; };
+            if (lt(p.min_bits, r.min_bits)) r.min_bits = p.min_bits;
+            if (lt(r.max_bits, p.max_bits)) r.max_bits = p.max_bits;
+        }
+    }
+    if (r.valid && t == KX_FLOAT64) {
+        double s = fs + fe;
+        std::memcpy(&r.sum_bits, &s, 8);
+        r.sum_err = (fs - s) + fe;
+    }
+    *out = r;
+    return KX_OK;
+}
+
+int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* launches) {
+    if (!ctx) return KX_EINVAL;
+    if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
+    if (total_ms) *total_ms = ctx->last_total_ms;
+    if (launches) *launches = ctx->last_launches;
+    return KX_OK;
+}
+
+// ------------------------------------------------------------------ narrow drop-ins
+int64_t kx_cmp(kx_ctx* ctx, uint8_t block_type, uint8_t mode, const void* src, size_t n, uint64_t a, uint64_t b, uint8_t* bits) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int w = type_bits(block_type);
+    if (!w) return fail(ctx, KX_EINVAL, "kx_cmp: unsupported type");
+    if (mode == KX_MODE_IN || mode == KX_MODE_NIN || mode < KX_MODE_EQ || mode > KX_MODE_RANGE) return fail(ctx, KX_EINVAL, "kx_cmp: unsupported mode");
+    if (n == 0) return 0;
+    if (!src || !bits || n > 0xffffffffull) return fail(ctx, KX_EINVAL, "kx_cmp: bad arguments");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    BlockLayout lay;
+    lay.view.kind = CK_BITS; lay.view.type = block_type; lay.view.width = uint8_t(w); lay.view.is_raw = 1; lay.view.n = uint32_t(n);
+    lay.stream = static_cast<const uint8_t*>(src); lay.stream_len = n * size_t(w / 8);
+    TempBlock tb(ctx);
+    int rc = upload_block(ctx, lay, tb.sb);
+    if (rc) return rc;
+    int64_t count = 0;
+    rc = single_leaf_scan(ctx, tb.sb, block_type, mode, a, b, nullptr, 0, bits, &count);
+    return rc ? rc : count;
+}
+
+int64_t kx_bitpack_cmp(kx_ctx* ctx, uint8_t mode, const void* packed, int log2, uint64_t a, uint64_t b, size_t n, uint8_t* bits) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (log2 < 0 || log2 > 64) return fail(ctx, KX_EINVAL, "kx_bitpack_cmp: bad width");
+    if (mode == KX_MODE_IN || mode == KX_MODE_NIN || mode < KX_MODE_EQ || mode > KX_MODE_RANGE) return fail(ctx, KX_EINVAL, "kx_bitpack_cmp: unsupported mode");
+    if (n == 0) return 0;
+    if (!bits || (log2 && !packed) || n > 0xffffffffull) return fail(ctx, KX_EINVAL, "kx_bitpack_cmp: bad arguments");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    BlockLayout lay;
+    lay.view.kind = log2 ? CK_BITS : CK_CONST; lay.view.type = KX_UINT64; lay.view.width = uint8_t(log2); lay.view.is_raw = 0;
+    lay.view.n = uint32_t(n); lay.view.base = 0;
+    lay.stream = static_cast<const uint8_t*>(packed); lay.stream_len = bitpack_bytes(log2, n);
+    TempBlock tb(ctx);
+    int rc = upload_block(ctx, lay, tb.sb);
+    if (rc) return rc;
+    int64_t count = 0;
+    rc = single_leaf_scan(ctx, tb.sb, KX_UINT64, mode, a, b, nullptr, 0, bits, &count);
+    return rc ? rc : count;
+}
+
+static int decode_view_to_host(kx_ctx* ctx, const ColView& v, void* dst) {
+    size_t bytes = size_t(v.n) * size_t(type_bits(v.type) / 8);
+    if (!bytes) return KX_OK;
+    CK(ctx->d_tmp.reserve(bytes));
+    CK(launch_decode(v, ctx->d_tmp.p, ctx->stream));
+    CK(cudaMemcpyAsync(dst, ctx->d_tmp.p, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KX_OK;
+}
+
+int kx_bitpack_decode(kx_ctx* ctx, uint8_t block_type, const void* packed, int log2, uint64_t minv, size_t n, void* dst) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (log2 < 0 || log2 > 64 || type_bits(block_type) == 0 || type_is_float(block_type)) return fail(ctx, KX_EINVAL, "kx_bitpack_decode: bad arguments");
+    if (n == 0) return KX_OK;
+    if (!dst || (log2 && !packed) || n > 0xffffffffull) return fail(ctx, KX_EINVAL, "kx_bitpack_decode: bad arguments");
+    CK(cudaSetDevice(ctx->device));
+    BlockLayout lay;
+    lay.view.kind = log2 ? CK_BITS : CK_CONST; lay.view.type = block_type; lay.view.width = uint8_t(log2); lay.view.n = uint32_t(n);
+    lay.view.base = type_ext(block_type, minv);
+    lay.stream = static_cast<const uint8_t*>(packed); lay.stream_len = bitpack_bytes(log2, n);
+    TempBlock tb(ctx);
+    int rc = upload_block(ctx, lay, tb.sb);
+    if (rc) return rc;
+    return decode_view_to_host(ctx, tb.sb.view, dst);
+}
+
+int64_t kx_container_match(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, uint8_t mode, uint64_t a, uint64_t b,
+                           const uint64_t* set, uint32_t nset, uint8_t* bits) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!enc || !len) return fail(ctx, KX_EINVAL, "kx_container_match: empty block");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    BlockLayout lay; std::string err;
+    int rc = normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
+    if (rc) return fail(ctx, rc, "kx_container_match: " + err);
+    if (lay.view.n == 0) return 0;
+    if (!bits) return fail(ctx, KX_EINVAL, "kx_container_match: bits missing");
+    TempBlock tb(ctx);
+    rc = upload_block(ctx, lay, tb.sb);
+    if (rc) return rc;
+    int64_t count = 0;
+    rc = single_leaf_scan(ctx, tb.sb, block_type, mode, a, b, set, nset, bits, &count);
+    return rc ? rc : count;
+}
+
+int kx_container_decode(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, void* dst, size_t dst_cap_rows) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!enc || !len) return fail(ctx, KX_EINVAL, "kx_container_decode: empty block");
+    CK(cudaSetDevice(ctx->device));
+    BlockLayout lay; std::string err;
+    int rc = normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
+    if (rc) return fail(ctx, rc, "kx_container_decode: " + err);
+    if (lay.view.n > dst_cap_rows) return fail(ctx, KX_EINVAL, "kx_container_decode: destination too small");
+    if (lay.view.n && !dst) return fail(ctx, KX_EINVAL, "kx_container_decode: dst missing");
+    TempBlock tb(ctx);
+    rc = upload_block(ctx, lay, tb.sb);
+    if (rc) return rc;
+    return decode_view_to_host(ctx, tb.sb.view, dst);
+}
+
+// ------------------------------------------------------------------ bitsets
+static int upload_bits(kx_ctx* ctx, DevBuf& buf, const uint8_t* src, size_t nbits) {
+    size_t nbytes = (nbits + 7) / 8, padded = round_up(nbytes, 4) + 8;
+    CK(buf.reserve(padded));
+    CK(cudaMemsetAsync(static_cast<uint8_t*>(buf.p) + (nbytes & ~size_t(3)), 0, padded - (nbytes & ~size_t(3)), ctx->stream));
+    CK(cudaMemcpyAsync(buf.p, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
+    return KX_OK;
+}
+
+int kx_bitset_op(kx_ctx* ctx, int op, uint8_t* dst, const uint8_t* src, size_t nbits, int* any, int* all) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (op < KX_BIT_AND || op > KX_BIT_XOR) return fail(ctx, KX_EINVAL, "kx_bitset_op: bad op");
+    if (nbits == 0) { if (any) *any = 0; if (all) *all = 1; return KX_OK; }
+    if (!dst || !src) return fail(ctx, KX_EINVAL, "kx_bitset_op: null bitset");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload_bits(ctx, ctx->d_tmp, dst, nbits)) || (rc = upload_bits(ctx, ctx->d_tmp2, src, nbits))) return rc;
+    CK(ctx->d_misc.reserve(64));
+    CK(cudaMemsetAsync(ctx->d_misc.p, 0, 8, ctx->stream));
+    CK(launch_bitset_op(static_cast<uint32_t*>(ctx->d_tmp.p), static_cast<const uint32_t*>(ctx->d_tmp2.p), nbits, op,
+                        static_cast<unsigned int*>(ctx->d_misc.p), ctx->stream));
+    unsigned int flags[2] = {0, 0};
+    CK(cudaMemcpyAsync(dst, ctx->d_tmp.p, (nbits + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(flags, ctx->d_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (any) *any = flags[0] != 0;
+    if (all) *all = flags[1] == 0;
+    return KX_OK;
+}
+
+int kx_bitset_neg(kx_ctx* ctx, uint8_t* buf, size_t nbits) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nbits == 0) return KX_OK;
+    if (!buf) return fail(ctx, KX_EINVAL, "kx_bitset_neg: null bitset");
+    CK(cudaSetDevice(ctx->device));
+    int rc = upload_bits(ctx, ctx->d_tmp, buf, nbits);
+    if (rc) return rc;
+    CK(launch_bitset_neg(static_cast<uint32_t*>(ctx->d_tmp.p), nbits, ctx->stream));
+    CK(cudaMemcpyAsync(buf, ctx->d_tmp.p, (nbits + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KX_OK;
+}
+
+int64_t kx_bitset_popcount(kx_ctx* ctx, const uint8_t* buf, size_t nbits) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nbits == 0) return 0;
+    if (!buf) return fail(ctx, KX_EINVAL, "kx_bitset_popcount: null bitset");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    int rc = upload_bits(ctx, ctx->d_tmp, buf, nbits);
+    if (rc) return rc;
+    CK(ctx->d_misc.reserve(64));
+    CK(cudaMemsetAsync(ctx->d_misc.p, 0, 8, ctx->stream));
+    CK(launch_bitset_popcount(static_cast<const uint32_t*>(ctx->d_tmp.p), nbits, static_cast<unsigned long long*>(ctx->d_misc.p), ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, ctx->d_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return int64_t(c);
+}
+
+int64_t kx_bitset_indexes(kx_ctx* ctx, const uint8_t* buf, size_t nbits, uint32_t* dst) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nbits == 0) return 0;
+    if (!buf || !dst || nbits > 0xffffffffull) return fail(ctx, KX_EINVAL, "kx_bitset_indexes: bad arguments");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    int rc = upload_bits(ctx, ctx->d_tmp, buf, nbits);
+    if (rc) return rc;
+    size_t nwords = (nbits + 31) / 32, nblocks = (nwords + 255) / 256;
+    CK(ctx->d_misc.reserve(64 + nblocks * 4));
+    CK(ctx->d_tmp2.reserve(nbits * 4 + 64));
+    unsigned long long* total = static_cast<unsigned long long*>(ctx->d_misc.p);
+    uint32_t* block_tmp = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->d_misc.p) + 64);
+    CK(launch_bitset_indexes(static_cast<const uint32_t*>(ctx->d_tmp.p), nbits, block_tmp, total, static_cast<uint32_t*>(ctx->d_tmp2.p), ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(&c, total, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (c) {
+        CK(cudaMemcpyAsync(dst, ctx->d_tmp2.p, size_t(c) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return int64_t(c);
+}
+
+// ------------------------------------------------------------------ pruning
+int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* mins, const uint64_t* maxs, const void* const* blooms,
+                 const size_t* bloom_len, const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog);
+    if (rc) return rc;
+    if (npacks == 0) return 0;
+    if (npacks < 0 || !mins || !maxs || !out) return fail(ctx, KX_EINVAL, "kx_prune: bad arguments");
+    if (blooms && (!bloom_len || !hashes || !hash_off)) return fail(ctx, KX_EINVAL, "kx_prune: bloom tables incomplete");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    const int nleaves = int(prog->leaves.size());
+    const size_t cells = size_t(npacks) * nleaves;
+
+    PruneParams P{};
+    P.npacks = uint32_t(npacks); P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size());
+    std::memcpy(P.postfix, prog->postfix.data(), prog->postfix.size());
+    for (int l = 0; l < nleaves; ++l) {
+        const LeafSpec& s = prog->leaves[size_t(l)];
+        PruneLeaf& pl = P.leaves[l];
+        pl.a = type_is_float(s.type) ? s.a : type_ext(s.type, s.a);
+        pl.b = type_is_float(s.type) ? s.b : type_ext(s.type, s.b);
+        pl.flip = type_is_signed(s.type) ? 0x8000000000000000ull : 0;
+        pl.mode = s.mode; pl.is_float = type_is_float(s.type);
+        pl.set_off = s.set_off; pl.nset = uint32_t(s.set.size());
+        if (s.type == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_prune: float32 zone maps are not supported");
+    }
+    size_t nhash = 0;
+    if (blooms) { for (int l = 0; l <= nleaves; ++l) P.hash_off[l] = hash_off[l]; nhash = hash_off[nleaves]; }
+
+    // device layout: mins | maxs | bloom ptr table | bloom lens | hashes | out words | count | bloom payloads
+    size_t off_max = cells * 8, off_bp = off_max + cells * 8, off_bl = off_bp + (blooms ? cells * 8 : 0);
+    size_t off_h = off_bl + (blooms ? cells * 8 : 0), off_out = round_up(off_h + nhash * 8, 8);
+    size_t out_words = (size_t(npacks) + 31) / 32, off_cnt = round_up(off_out + out_words * 4, 8), off_pay = round_up(off_cnt + 8, 256);
+    size_t pay = 0;
+    std::vector<size_t> pay_off(blooms ? cells : 0);
+    if (blooms) for (size_t i = 0; i < cells; ++i) if (blooms[i] && bloom_len[i] > 1) { pay_off[i] = pay; pay += round_up(bloom_len[i], 32); }
+    CK(ctx->d_tmp.reserve(off_pay + pay + 64));
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
+    CK(cudaMemcpyAsync(d, mins, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + off_max, maxs, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint64_t> ptrs, lens;
+    if (blooms) {
+        ptrs.resize(cells); lens.resize(cells);
+        for (size_t i = 0; i < cells; ++i) {
+            bool has = blooms[i] && bloom_len[i] > 1;
+            // the buffer must hold k + a power-of-two number of bits (bloom.go:83-100); others are ignored
+            if (has) { size_t m = (bloom_len[i] - 1) * 8; if (m & (m - 1)) has = false; }
+            ptrs[i] = has ? uint64_t(reinterpret_cast<uintptr_t>(d + off_pay + pay_off[i])) : 0;
+            lens[i] = has ? bloom_len[i] : 0;
+            if (has) CK(cudaMemcpyAsync(d + off_pay + pay_off[i], blooms[i], bloom_len[i], cudaMemcpyHostToDevice, ctx->stream));
+        }
+        CK(cudaMemcpyAsync(d + off_bp, ptrs.data(), cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(d + off_bl, lens.data(), cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (nhash) CK(cudaMemcpyAsync(d + off_h, hashes, nhash * 8, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(cudaMemsetAsync(d + off_out, 0, off_pay - off_out, ctx->stream));
+    P.mins = reinterpret_cast<const uint64_t*>(d); P.maxs = reinterpret_cast<const uint64_t*>(d + off_max);
+    P.blooms = blooms ? reinterpret_cast<const uint8_t* const*>(d + off_bp) : nullptr;
+    P.bloom_len = reinterpret_cast<const uint64_t*>(d + off_bl);
+    P.hashes = reinterpret_cast<const uint64_t*>(d + off_h);
+    P.set_vals = prog->dev_sets;
+    P.out = reinterpret_cast<uint32_t*>(d + off_out);
+    P.count = reinterpret_cast<unsigned long long*>(d + off_cnt);
+    CK(launch_prune(P, ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(out, d + off_out, (size_t(npacks) + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&c, d + off_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return int64_t(c);
+}
+
+uint64_t kx_hash_value(uint8_t block_type, uint64_t pattern) {
+    switch (type_bits(block_type)) {   // hash.HashT: internal/hash/hash.go:67-92 (floats hash their IEEE bytes)
+    case 64: return xxh3_u64(pattern);
+    case 32: return xxh3_u32(uint32_t(pattern));
+    case 16: return xxh3_u16(uint16_t(pattern));
+    case 8: return xxh3_u8(uint8_t(pattern));
+    }
+    return 0;
+}
+uint64_t kx_hash_bytes(const void* p, size_t len) { return xxh3_bytes(static_cast<const uint8_t*>(p), len); }
+
+}  // extern "C"

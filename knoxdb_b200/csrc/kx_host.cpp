@@ -1,0 +1,728 @@
+// kx_host.cpp — container parsing, block normalisation and leaf translation (host side).
+//
+// Reference behaviour followed (paths relative to the knoxdb repository):
+//   wire format        internal/encode/container.go:20-55, int.go:109-115, pkg/num/varint.go:85-192
+//   container headers  internal/encode/int_{const,delta,raw,bitpack,dict,runend,s8b}.go (Load), float_raw.go
+//   leaf translation   internal/encode/int_bitpack.go:163-247, int_delta.go:149-449, int_dict.go:181-359,
+//                      int_const.go:133-173, internal/cmp/number.go:13-243
+#include "kx_host.h"
+
+#include <algorithm>
+#include <cstring>
+
+namespace kx {
+
+// ---------------------------------------------------------------------------------- varint
+// SQLite4-style varint of pkg/num/varint.go: 0..240 in one byte, two/three byte forms with
+// an offset, then a length byte 250..255 followed by 3..8 big-endian bytes.
+int put_uvarint(uint8_t* b, uint64_t x) {
+    if (x <= 240) { b[0] = uint8_t(x); return 1; }
+    if (x <= 2287) { x -= 240; b[0] = uint8_t(241 + (x >> 8)); b[1] = uint8_t(x); return 2; }
+    if (x <= 67823) { x -= 2288; b[0] = 249; b[1] = uint8_t(x >> 8); b[2] = uint8_t(x); return 3; }
+    int nb = 3;
+    while (nb < 8 && (x >> (8 * nb)) != 0) nb++;
+    b[0] = uint8_t(247 + nb);
+    for (int i = 0; i < nb; i++) b[1 + i] = uint8_t(x >> (8 * (nb - 1 - i)));
+    return nb + 1;
+}
+
+int get_uvarint(const uint8_t* b, size_t avail, uint64_t* x) {
+    if (avail < 1) return 0;
+    unsigned b0 = b[0];
+    if (b0 <= 240) { *x = b0; return 1; }
+    if (b0 <= 248) { if (avail < 2) return 0; *x = 240 + (uint64_t(b0 - 241) << 8) + b[1]; return 2; }
+    if (b0 == 249) { if (avail < 3) return 0; *x = 2288 + (uint64_t(b[1]) << 8) + b[2]; return 3; }
+    int nb = int(b0) - 247;
+    if (avail < size_t(nb) + 1) return 0;
+    uint64_t v = 0;
+    for (int i = 0; i < nb; i++) v = (v << 8) | b[1 + i];
+    *x = v;
+    return nb + 1;
+}
+
+size_t bitpack_bytes(int log2, size_t n) { return ((size_t(log2) * n + 63) & ~size_t(63)) / 8; }
+
+// ---------------------------------------------------------------------------------- parsing
+namespace {
+
+struct Reader {
+    const uint8_t* p; size_t left; bool ok = true;
+    uint64_t uv() {
+        uint64_t v = 0; int k = get_uvarint(p, left, &v);
+        if (!k) { ok = false; return 0; }
+        p += k; left -= size_t(k); return v;
+    }
+    const uint8_t* take(size_t nbytes) {
+        if (nbytes > left) { ok = false; return nullptr; }
+        const uint8_t* q = p; p += nbytes; left -= nbytes; return q;
+    }
+};
+
+const int S8_COUNT[16] = {128, 128, 60, 30, 20, 15, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1};
+const int S8_WIDTH[16] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 60};
+
+uint64_t load_le(const uint8_t* p, int nbytes) { uint64_t v = 0; std::memcpy(&v, p, size_t(nbytes)); return v; }
+
+uint64_t bit_field(const uint8_t* stream, size_t stream_len, size_t row, int w) {
+    if (w == 0) return 0;
+    size_t bit = row * size_t(w), byte = bit >> 3;
+    int sh = int(bit & 7);
+    // gather up to 9 bytes
+    unsigned __int128 acc = 0;
+    for (int i = 0; i < 9 && byte + size_t(i) < stream_len; i++) acc |= (unsigned __int128)stream[byte + size_t(i)] << (8 * i);
+    return uint64_t(acc >> sh) & width_mask(w);
+}
+
+}  // namespace
+
+long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err) {
+    if (len < 1) { err = "empty container"; return -1; }
+    auto c = std::make_unique<Container>();
+    c->ctype = buf[0];
+    c->type = type;
+    Reader r{buf + 1, len - 1};
+    switch (c->ctype) {
+    case T_CONST:
+        c->val = type_ext(type, r.uv()); c->n = r.uv();
+        break;
+    case T_DELTA:
+        c->val = type_ext(type, r.uv()); c->delta = type_ext(type, r.uv()); c->n = r.uv();
+        break;
+    case T_BITPACK:
+        c->val = type_ext(type, r.uv()); c->log2 = int(r.uv()); c->n = r.uv();
+        if (c->log2 < 0 || c->log2 > 64) { err = "bitpack: bad width"; return -1; }
+        c->payload_len = bitpack_bytes(c->log2, c->n);
+        c->payload = r.take(c->payload_len);
+        break;
+    case T_RAW:
+    case T_FLOATRAW:
+        if ((c->ctype == T_FLOATRAW) != type_is_float(type)) { err = "raw container / block type mismatch"; return -1; }
+        c->n = r.uv();
+        c->payload_len = c->n * size_t(type_bits(type) / 8);
+        c->payload = r.take(c->payload_len);
+        break;
+    case T_S8B: {
+        c->val = type_ext(type, r.uv()); c->n = r.uv();
+        c->payload_len = r.uv();
+        c->payload = r.take(c->payload_len);
+        break;
+    }
+    case T_DICT:
+    case T_RUNEND: {
+        long k = parse_container(type, r.p, r.left, c->child[0], err);
+        if (k < 0) return -1;
+        r.take(size_t(k));
+        k = parse_container(c->ctype == T_DICT ? 7 /*uint16*/ : 6 /*uint32*/, r.p, r.left, c->child[1], err);
+        if (k < 0) return -1;
+        r.take(size_t(k));
+        if (c->ctype == T_DICT) c->n = c->child[1]->n;
+        else {
+            // N = last(Ends) + 1 (int_runend.go:108-111)
+            std::vector<uint64_t> ends;
+            if (!decode_container(*c->child[1], ends, err)) return -1;
+            c->n = ends.empty() ? 0 : size_t(ends.back()) + 1;
+            if (c->child[0]->n != c->child[1]->n) { err = "runend: values/ends length mismatch"; return -1; }
+        }
+        break;
+    }
+    default:
+        err = "unsupported container type " + std::to_string(c->ctype);
+        return -1;
+    }
+    if (!r.ok) { err = "truncated container"; return -1; }
+    if (c->n > 0xffffffffull) { err = "block longer than 2^32 rows"; return -1; }
+    out = std::move(c);
+    return long(len - r.left);
+}
+
+bool decode_container(const Container& c, std::vector<uint64_t>& out, std::string& err) {
+    out.resize(c.n);
+    switch (c.ctype) {
+    case T_CONST:
+        std::fill(out.begin(), out.end(), c.val);
+        return true;
+    case T_DELTA:
+        for (size_t i = 0; i < c.n; i++) out[i] = type_ext(c.type, uint64_t(i) * c.delta + c.val);
+        return true;
+    case T_BITPACK:
+        for (size_t i = 0; i < c.n; i++) out[i] = type_ext(c.type, bit_field(c.payload, c.payload_len, i, c.log2) + c.val);
+        return true;
+    case T_RAW:
+    case T_FLOATRAW: {
+        int nb = type_bits(c.type) / 8;
+        for (size_t i = 0; i < c.n; i++) {
+            uint64_t v = load_le(c.payload + i * size_t(nb), nb);
+            out[i] = type_is_float(c.type) ? v : type_ext(c.type, v);
+        }
+        return true;
+    }
+    case T_S8B: {
+        size_t j = 0;
+        for (size_t wi = 0; wi + 8 <= c.payload_len && j < c.n; wi += 8) {
+            uint64_t w = load_le(c.payload + wi, 8);
+            int sel = int(w >> 60), cnt = S8_COUNT[sel], bits = S8_WIDTH[sel];
+            for (int q = 0; q < cnt && j < c.n; q++) {
+                uint64_t f = sel == 0 ? 0 : sel == 1 ? 1 : (w >> (q * bits)) & width_mask(bits);
+                out[j++] = type_ext(c.type, f + c.val);
+            }
+        }
+        if (j != c.n) { err = "simple8b: short stream"; return false; }
+        return true;
+    }
+    case T_DICT: {
+        std::vector<uint64_t> dict, codes;
+        if (!decode_container(*c.child[0], dict, err) || !decode_container(*c.child[1], codes, err)) return false;
+        for (size_t i = 0; i < c.n; i++) {
+            if (codes[i] >= dict.size()) { err = "dict: code out of range"; return false; }
+            out[i] = dict[codes[i]];
+        }
+        return true;
+    }
+    case T_RUNEND: {
+        std::vector<uint64_t> vals, ends;
+        if (!decode_container(*c.child[0], vals, err) || !decode_container(*c.child[1], ends, err)) return false;
+        size_t i = 0;
+        for (size_t r = 0; r < ends.size(); r++) {
+            if (ends[r] >= c.n) { err = "runend: end out of range"; return false; }
+            for (; i <= ends[r]; i++) out[i] = vals[r];
+        }
+        return true;
+    }
+    }
+    err = "decode: unsupported container";
+    return false;
+}
+
+// ---------------------------------------------------------------------------------- normalise
+namespace {
+
+// host bit-packer for blocks that are transcoded at registration (simple8b, exotic children)
+void pack_stream(const std::vector<uint64_t>& fields, int w, std::vector<uint8_t>& out) {
+    out.assign(bitpack_bytes(w, fields.size()), 0);
+    uint64_t* words = reinterpret_cast<uint64_t*>(out.data());
+    size_t bit = 0;
+    for (uint64_t f : fields) {
+        size_t wi = bit >> 6; int sh = int(bit & 63);
+        words[wi] |= f << sh;
+        if (sh + w > 64) words[wi + 1] |= f >> (64 - sh);
+        bit += size_t(w);
+    }
+}
+
+// fills view/stream for a leaf-level stream container (bitpack / raw); false if not stream-like
+bool stream_view(const Container& c, BlockLayout& out) {
+    ColView& v = out.view;
+    if (c.ctype == T_BITPACK) {
+        v.kind = c.log2 == 0 ? CK_CONST : CK_BITS;
+        v.base = c.val; v.width = uint8_t(c.log2); v.is_raw = 0;
+        out.stream = c.payload; out.stream_len = c.payload_len;
+        return true;
+    }
+    if (c.ctype == T_RAW || c.ctype == T_FLOATRAW) {
+        v.kind = CK_BITS; v.base = 0; v.width = uint8_t(type_bits(c.type)); v.is_raw = 1;
+        out.stream = c.payload; out.stream_len = c.payload_len;
+        return true;
+    }
+    return false;
+}
+
+int log2_range(uint64_t lo, uint64_t hi) { uint64_t d = hi - lo; return d ? 64 - __builtin_clzll(d) : 0; }
+
+}  // namespace
+
+int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, std::string& err) {
+    std::unique_ptr<Container> c;
+    if (type_bits(type) == 0) { err = "unsupported block type"; return -6; }
+    long used = parse_container(type, enc, len, c, err);
+    if (used < 0) return -6;
+    ColView& v = out.view;
+    v = ColView{};
+    v.type = uint8_t(type);
+    v.n = uint32_t(c->n);
+    switch (c->ctype) {
+    case T_CONST:
+        v.kind = CK_CONST; v.base = c->val;
+        return 0;
+    case T_DELTA:
+        v.kind = CK_DELTA; v.base = c->val; v.delta = c->delta;
+        return 0;
+    case T_BITPACK:
+    case T_RAW:
+    case T_FLOATRAW:
+        stream_view(*c, out);
+        return 0;
+    case T_S8B: {
+        // legacy scheme (never selected for new data, context.go:275-282): transcode to a
+        // min-FOR bit stream once at registration so the scan kernels see one stream format
+        std::vector<uint64_t> vals;
+        if (!decode_container(*c, vals, err)) return -6;
+        uint64_t mx = 0;
+        for (auto& x : vals) { x = x - c->val; mx = std::max(mx, x); }
+        int w = log2_range(0, mx);
+        v.kind = w == 0 ? CK_CONST : CK_BITS; v.base = c->val; v.width = uint8_t(w); v.is_raw = 0;
+        if (w) pack_stream(vals, w, out.owned);
+        return 0;
+    }
+    case T_DICT: {
+        if (!decode_container(*c->child[0], out.aux64, err)) return -6;
+        v.kind = CK_DICT; v.naux = uint32_t(out.aux64.size());
+        const Container& codes = *c->child[1];
+        BlockLayout tmp;
+        if (stream_view(codes, tmp) && tmp.view.kind == CK_BITS) {
+            v.width = tmp.view.width; v.delta = tmp.view.base; v.is_raw = tmp.view.is_raw;
+            out.stream = tmp.stream; out.stream_len = tmp.stream_len;
+        } else {
+            std::vector<uint64_t> cv;
+            if (!decode_container(codes, cv, err)) return -6;
+            v.width = 16; v.delta = 0; v.is_raw = 1;
+            pack_stream(cv, 16, out.owned);
+        }
+        return 0;
+    }
+    case T_RUNEND: {
+        std::vector<uint64_t> ends;
+        if (!decode_container(*c->child[0], out.aux64, err) || !decode_container(*c->child[1], ends, err)) return -6;
+        out.aux32.assign(ends.begin(), ends.end());
+        v.kind = CK_RUNEND; v.naux = uint32_t(ends.size());
+        return 0;
+    }
+    }
+    err = "normalize: unsupported container";
+    return -7;
+}
+
+// ---------------------------------------------------------------------------------- predicates
+namespace {
+
+inline bool t_lt(int t, uint64_t a, uint64_t b) { return type_is_signed(t) ? int64_t(a) < int64_t(b) : a < b; }
+inline bool t_le(int t, uint64_t a, uint64_t b) { return !t_lt(t, b, a); }
+inline uint64_t t_min(int t) { return type_is_signed(t) ? uint64_t(-(int64_t(1) << (type_bits(t) - 1))) : 0; }
+inline uint64_t t_max(int t) {
+    int w = type_bits(t);
+    return type_is_signed(t) ? (uint64_t(1) << (w - 1)) - 1 : width_mask(w);
+}
+
+void set_const(PackLeaf& o, bool all) { o.mode = all ? LM_ALL : LM_NONE; o.data = nullptr; o.width = 0; o.neg = 0; }
+
+// closed interval [lo, hi] of T values (lo <= hi in T order) on a raw stream of `w` bits
+void raw_interval(PackLeaf& o, int w, uint64_t lo, uint64_t hi, bool neg) {
+    uint64_t wm = width_mask(w);
+    o.mode = w <= 32 ? LM_RANGE32 : LM_RANGE64;
+    o.a = lo & wm; o.d = (hi - lo) & wm; o.wm = wm; o.neg = neg;
+}
+
+// ((field - a) <=u64 d) on a min-FOR field of width w, 64-bit arithmetic like bitpack/cmp.go
+void packed_range(PackLeaf& o, int w, uint64_t a, uint64_t d, bool neg) {
+    if (w <= 32) {
+        if (d < 0xffffffff00000000ull) {            // no 64-bit wrap-around range
+            if (a > 0xffffffffull) { set_const(o, neg); return; }
+            uint64_t room = 0xffffffffull - a;
+            o.mode = LM_RANGE32; o.a = a; o.d = std::min(d, room); o.wm = 0xffffffffull; o.neg = neg;
+            return;
+        }
+    }
+    o.mode = LM_RANGE64; o.a = a; o.d = d; o.wm = ~0ull; o.neg = neg;
+}
+
+// leaf on a CK_BITS stream of integer type t
+void compile_bits_int(PackLeaf& o, int t, int w, uint64_t base, bool is_raw, int mode, uint64_t a, uint64_t b) {
+    a = type_ext(t, a); b = type_ext(t, b);
+    if (is_raw) {
+        // cmp.<T><Op> on the reinterpreted slice: internal/encode/int_raw.go:122-337
+        uint64_t mn = t_min(t), mx = t_max(t);
+        switch (mode) {
+        case M_EQ: raw_interval(o, w, a, a, false); return;
+        case M_NE: raw_interval(o, w, a, a, true); return;
+        case M_LT: if (a == mn) set_const(o, false); else raw_interval(o, w, mn, a - 1, false); return;
+        case M_LE: raw_interval(o, w, mn, a, false); return;
+        case M_GT: if (a == mx) set_const(o, false); else raw_interval(o, w, a + 1, mx, false); return;
+        case M_GE: raw_interval(o, w, a, mx, false); return;
+        case M_RANGE: {  // U(v - a) <= U(b - a): internal/cmp/number.go:211-243
+            uint64_t wm = width_mask(w);
+            o.mode = w <= 32 ? LM_RANGE32 : LM_RANGE64;
+            o.a = a & wm; o.d = (b - a) & wm; o.wm = wm; o.neg = 0;
+            return;
+        }
+        }
+        set_const(o, false);
+        return;
+    }
+    // bit-packed: `val < For` pre-checks, then compare in the min-FOR domain (int_bitpack.go:163-247)
+    if (mode == M_RANGE) {
+        if (t_lt(t, b, base)) { set_const(o, false); return; }
+        if (t_lt(t, a, base)) a = base;
+        uint64_t fa = type_ext(t, a - base), fb = type_ext(t, b - base);
+        packed_range(o, w, fa, fb - fa, false);
+        return;
+    }
+    if (t_lt(t, a, base)) { set_const(o, mode == M_NE || mode == M_GT || mode == M_GE); return; }
+    uint64_t fa = type_ext(t, a - base);
+    switch (mode) {
+    case M_EQ: packed_range(o, w, fa, 0, false); return;
+    case M_NE: packed_range(o, w, fa, 0, true); return;
+    case M_LT: if (fa == 0) set_const(o, false); else packed_range(o, w, 0, fa - 1, false); return;   // field < fa
+    case M_LE: packed_range(o, w, 0, fa, false); return;                                                 // field <= fa
+    case M_GT: packed_range(o, w, 0, fa, true); return;                                                  // ^(field <= fa)
+    case M_GE: if (fa == 0) set_const(o, true); else packed_range(o, w, 0, fa - 1, true); return;       // ^(field < fa)
+    }
+    set_const(o, false);
+}
+
+int64_t go_div(int64_t a, int64_t b) { return b == -1 ? int64_t(0 - uint64_t(a)) : a / b; }
+int64_t go_mod(int64_t a, int64_t b) { return b == -1 ? 0 : a % b; }
+
+// bits.SetRange(start, end) clamped like internal/bitset/bitset.go:156-200
+void row_range(PackLeaf& o, int64_t n, int64_t start, int64_t end, bool neg) {
+    if (start > n) { set_const(o, neg); return; }
+    start = std::max<int64_t>(0, start);
+    end = std::min<int64_t>(n - 1, end);
+    if (start > end) { set_const(o, neg); return; }
+    if (start == 0 && end == n - 1) { set_const(o, !neg); return; }
+    o.mode = LM_ROWRANGE; o.a = uint64_t(start); o.d = uint64_t(end - start); o.neg = neg; o.data = nullptr; o.width = 0;
+}
+
+// DeltaContainer.Match*: closed-form index arithmetic in int64 space, int_delta.go:149-449
+void compile_delta(PackLeaf& o, const ColView& v, int mode, uint64_t a, uint64_t b) {
+    int t = v.type;
+    a = type_ext(t, a); b = type_ext(t, b);
+    int64_t N = int64_t(v.n);
+    if (N == 0) { set_const(o, false); return; }
+    uint64_t For = v.base;
+    bool dpos = type_is_signed(t) ? int64_t(v.delta) > 0 : v.delta > 0;
+    int64_t d64 = int64_t(v.delta), v64 = int64_t(a) - int64_t(For);
+    auto lt = [&](uint64_t x, uint64_t y) { return t_lt(t, x, y); };
+    auto gt = [&](uint64_t x, uint64_t y) { return t_lt(t, y, x); };
+
+    if (mode == M_EQ || mode == M_NE) {
+        bool ne = mode == M_NE;
+        if (dpos ? lt(a, For) : gt(a, For)) { set_const(o, ne); return; }
+        uint64_t val = type_ext(t, a - For);
+        bool divisible; int64_t q;
+        if (type_is_signed(t)) { divisible = go_mod(int64_t(val), d64) == 0; q = go_div(int64_t(val), d64); }
+        else { divisible = v.delta != 0 && val % v.delta == 0; q = v.delta ? int64_t(val / v.delta) : -1; }
+        bool hit = (ne ? (v.delta == 1 || divisible) : divisible) && q >= 0 && q < N;
+        if (!hit) { set_const(o, ne); return; }
+        if (N == 1) { set_const(o, !ne); return; }
+        o.mode = LM_ROWRANGE; o.a = uint64_t(q); o.d = 0; o.neg = ne; o.data = nullptr; o.width = 0;
+        return;
+    }
+    int64_t last = d64 * (N - 1);
+    switch (mode) {
+    case M_LT:
+        if (dpos) {
+            if (lt(a, For)) { set_const(o, false); return; }
+            if (last < v64) { set_const(o, true); return; }
+            int64_t n = go_div(v64, d64); if (go_mod(v64, d64) == 0) n--;
+            row_range(o, N, 0, n, false);
+        } else {
+            if (gt(a, For)) { set_const(o, true); return; }
+            if (last >= v64) { set_const(o, false); return; }
+            row_range(o, N, go_div(v64, d64) + 1, N - 1, false);
+        }
+        return;
+    case M_LE:
+        if (dpos) {
+            if (lt(a, For)) { set_const(o, false); return; }
+            if (last < v64) { set_const(o, true); return; }
+            row_range(o, N, 0, go_div(v64, d64), false);
+        } else {
+            if (!lt(a, For)) { set_const(o, true); return; }
+            if (last > v64) { set_const(o, false); return; }
+            int64_t n = go_div(v64, d64); if (go_mod(v64, d64) != 0) n++;
+            row_range(o, N, n, N - 1, false);
+        }
+        return;
+    case M_GT:
+        if (dpos) {
+            if (lt(a, For)) { set_const(o, true); return; }
+            if (last < v64) { set_const(o, false); return; }
+            row_range(o, N, go_div(v64, d64) + 1, N - 1, false);
+        } else {
+            if (gt(a, For)) { set_const(o, false); return; }
+            if (last > v64) { set_const(o, true); return; }
+            int64_t n = go_div(v64, d64); if (go_mod(v64, d64) == 0) n--;
+            row_range(o, N, 0, n, false);
+        }
+        return;
+    case M_GE:
+        if (dpos) {
+            if (!gt(a, For)) { set_const(o, true); return; }
+            if (last < v64) { set_const(o, false); return; }
+            int64_t n = go_div(v64, d64); if (go_mod(v64, d64) > 0) n++;
+            row_range(o, N, n, N - 1, false);
+        } else {
+            if (gt(a, For)) { set_const(o, false); return; }
+            if (last > v64) { set_const(o, true); return; }
+            row_range(o, N, 0, go_div(v64, d64), false);
+        }
+        return;
+    case M_RANGE: {
+        int64_t a64 = int64_t(a) - int64_t(For), b64 = int64_t(b) - int64_t(For);
+        if (dpos) {
+            if (lt(b, For) || a64 > last) { set_const(o, false); return; }
+            int64_t na = go_div(a64, d64), nb = go_div(b64, d64);
+            if (go_mod(a64, d64) != 0) na++;      // also for a below For: reference behaviour, see DESIGN.md
+            nb = std::min(nb, N - 1);
+            row_range(o, N, na, nb, false);
+        } else {
+            if (gt(a, For) || b64 < last) { set_const(o, false); return; }
+            int64_t na = go_div(a64, d64), nb = go_div(b64, d64);
+            if (go_mod(b64, d64) != 0) nb++;
+            nb = std::min(nb, N - 1);
+            row_range(o, N, nb, na, false);
+        }
+        return;
+    }
+    }
+    set_const(o, false);
+}
+
+// first index with dict[i] >= val (strict: > val), dict sorted ascending in T order
+size_t dict_lower(const uint64_t* d, size_t l, int t, uint64_t val, bool strict) {
+    size_t lo = 0, hi = l;
+    while (lo < hi) {
+        size_t m = (lo + hi) / 2;
+        bool ok = strict ? t_lt(t, val, d[m]) : !t_lt(t, d[m], val);
+        if (ok) hi = m; else lo = m + 1;
+    }
+    return lo;
+}
+
+// DictionaryContainer.Match*: value predicate → code predicate, int_dict.go:181-359
+void compile_dict(PackLeaf& o, const ColView& v, const uint64_t* d, int mode, uint64_t a, uint64_t b) {
+    int t = v.type; size_t l = v.naux;
+    a = type_ext(t, a); b = type_ext(t, b);
+    if (l == 0 || d == nullptr) { set_const(o, false); return; }
+    uint64_t first = d[0], last = d[l - 1];
+    auto codes = [&](int cmode, uint64_t ca, uint64_t cb) {
+        compile_bits_int(o, 7 /*uint16*/, v.width, v.delta, v.is_raw != 0, cmode, ca, cb);
+    };
+    size_t idx;
+    switch (mode) {
+    case M_EQ:
+        if (t_lt(t, a, first) || t_lt(t, last, a)) { set_const(o, false); return; }
+        idx = dict_lower(d, l, t, a, false);
+        if (idx == l || d[idx] != a) { set_const(o, false); return; }
+        codes(M_EQ, idx, 0); return;
+    case M_NE:
+        if (t_lt(t, a, first) || t_lt(t, last, a)) { set_const(o, true); return; }
+        idx = dict_lower(d, l, t, a, false);
+        if (idx == l || d[idx] != a) { set_const(o, true); return; }
+        codes(M_NE, idx, 0); return;
+    case M_LT:
+        if (t_lt(t, a, first)) { set_const(o, false); return; }
+        if (t_lt(t, last, a)) { set_const(o, true); return; }
+        idx = dict_lower(d, l, t, a, false); if (idx == l) idx--;
+        codes(M_LT, idx, 0); return;
+    case M_LE:
+        if (t_lt(t, a, first)) { set_const(o, false); return; }
+        if (!t_lt(t, a, last)) { set_const(o, true); return; }
+        idx = dict_lower(d, l, t, a, false);
+        if (idx == l || t_lt(t, a, d[idx])) idx--;
+        codes(M_LE, idx, 0); return;
+    case M_GT:
+        if (t_lt(t, a, first)) { set_const(o, true); return; }
+        if (!t_lt(t, a, last)) { set_const(o, false); return; }
+        idx = dict_lower(d, l, t, a, true);
+        codes(M_GE, idx, 0); return;
+    case M_GE:
+        if (t_lt(t, a, first)) { set_const(o, true); return; }
+        if (t_lt(t, last, a)) { set_const(o, false); return; }
+        idx = dict_lower(d, l, t, a, false);
+        codes(M_GE, idx, 0); return;
+    case M_RANGE: {
+        if (t_lt(t, b, first) || t_lt(t, last, a)) { set_const(o, false); return; }
+        if (t_le(t, a, first) && t_le(t, last, b)) { set_const(o, true); return; }
+        size_t ai = dict_lower(d, l, t, a, false), bi = dict_lower(d, l, t, b, false);
+        uint64_t x = d[ai];
+        if (ai == bi && x != a && x != b) { set_const(o, false); return; }   // range inside a dictionary gap
+        if (bi == l || d[bi] != b) bi--;
+        codes(M_RANGE, ai, bi); return;
+    }
+    }
+    set_const(o, false);
+}
+
+// scalar predicate on a decoded value → ((v ^ flip) - A) <= D
+void compile_valrange(PackLeaf& o, int t, int mode, uint64_t a, uint64_t b) {
+    a = type_ext(t, a); b = type_ext(t, b);
+    uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
+    uint64_t mn = t_min(t), mx = t_max(t);
+    auto iv = [&](uint64_t lo, uint64_t hi, bool neg) {
+        o.mode = LM_VALRANGE; o.a = lo ^ flip; o.d = (hi ^ flip) - (lo ^ flip); o.wm = flip; o.neg = neg;
+    };
+    switch (mode) {
+    case M_EQ: iv(a, a, false); return;
+    case M_NE: iv(a, a, true); return;
+    case M_LT: if (a == mn) set_const(o, false); else iv(mn, a - 1, false); return;
+    case M_LE: iv(mn, a, false); return;
+    case M_GT: if (a == mx) set_const(o, false); else iv(a + 1, mx, false); return;
+    case M_GE: iv(a, mx, false); return;
+    case M_RANGE: o.mode = LM_VALRANGE; o.a = a ^ flip; o.d = b - a; o.wm = flip; o.neg = 0; return;
+    }
+    set_const(o, false);
+}
+
+}  // namespace
+
+bool set_contains(const std::vector<uint64_t>& s, uint64_t v) { return std::binary_search(s.begin(), s.end(), v); }
+
+bool scalar_match(int t, int mode, uint64_t v, uint64_t a, uint64_t b) {
+    if (type_is_float(t)) {
+        double x, y, z;
+        if (t == 10) {
+            float fx, fy, fz; uint32_t u;
+            u = uint32_t(v); std::memcpy(&fx, &u, 4); u = uint32_t(a); std::memcpy(&fy, &u, 4); u = uint32_t(b); std::memcpy(&fz, &u, 4);
+            x = fx; y = fy; z = fz;
+        } else { std::memcpy(&x, &v, 8); std::memcpy(&y, &a, 8); std::memcpy(&z, &b, 8); }
+        switch (mode) {
+        case M_EQ: return x == y; case M_NE: return x != y; case M_LT: return x < y; case M_LE: return x <= y;
+        case M_GT: return x > y; case M_GE: return x >= y; case M_RANGE: return y <= x && x <= z;
+        }
+        return false;
+    }
+    a = type_ext(t, a); b = type_ext(t, b);
+    switch (mode) {
+    case M_EQ: return v == a;
+    case M_NE: return v != a;
+    case M_LT: return t_lt(t, v, a);
+    case M_LE: return t_le(t, v, a);
+    case M_GT: return t_lt(t, a, v);
+    case M_GE: return t_le(t, a, v);
+    case M_RANGE: return t_le(t, a, v) && t_le(t, v, b);
+    }
+    return false;
+}
+
+void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& leaf, uint32_t view_index, PackLeaf& o) {
+    o = PackLeaf{};
+    o.view = view_index;
+    int mode = leaf.mode, t = v.type;
+    bool is_set = mode == M_IN || mode == M_NIN;
+    if (v.n == 0) { set_const(o, false); return; }
+
+    if (is_set) {
+        bool neg = mode == M_NIN;
+        if (leaf.set.empty()) { set_const(o, neg); return; }
+        if (v.kind == CK_CONST) { set_const(o, set_contains(leaf.set, v.base) != neg); return; }
+        // decoded value ∈ set, evaluated per row on the device (BITS / DICT stage their stream)
+        o.mode = LM_SET; o.neg = neg;
+        o.a = leaf.set_off; o.d = leaf.set.size();
+        if (v.kind == CK_BITS || v.kind == CK_DICT) { o.data = v.data; o.width = v.width; }
+        return;
+    }
+
+    switch (v.kind) {
+    case CK_CONST:   // ConstContainer.Match*: all-or-nothing, int_const.go:133-173
+        set_const(o, scalar_match(t, mode, v.base, leaf.a, leaf.b));
+        return;
+    case CK_DELTA:
+        compile_delta(o, v, mode, leaf.a, leaf.b);
+        return;
+    case CK_BITS:
+        if (type_is_float(t)) {   // FloatRawContainer.Match* → cmp.Float64<Op>, float_raw.go:116-207
+            o.mode = LM_FLOAT; o.fop = uint8_t(mode); o.a = leaf.a; o.d = leaf.b;
+        } else {
+            compile_bits_int(o, t, v.width, v.base, v.is_raw != 0, mode, leaf.a, leaf.b);
+        }
+        if (o.mode != LM_NONE && o.mode != LM_ALL) { o.data = v.data; o.width = v.width; }
+        return;
+    case CK_DICT:
+        compile_dict(o, v, dict_host, mode, leaf.a, leaf.b);
+        if (o.mode != LM_NONE && o.mode != LM_ALL) { o.data = v.data; o.width = v.width; }
+        return;
+    case CK_RUNEND:  // RunEndContainer.Match*: predicate on the run values, int_runend.go:224-318
+        compile_valrange(o, t, mode, leaf.a, leaf.b);
+        return;
+    }
+    set_const(o, false);
+}
+
+// ---------------------------------------------------------------------------------- XXH3-64
+namespace {
+constexpr uint64_t P32_1 = 0x9E3779B1ull, P32_2 = 0x85EBCA77ull, P32_3 = 0xC2B2AE3Dull;
+constexpr uint64_t P64_1 = 0x9E3779B185EBCA87ull, P64_2 = 0xC2B2AE3D27D4EB4Full, P64_3 = 0x165667B19E3779F9ull,
+                   P64_4 = 0x85EBCA77C2B2AE63ull, P64_5 = 0x27D4EB2F165667C5ull;
+// default XXH3 secret (xxHash v0.8); the reference's key64_008 / key64_016 / key32_* constants
+// (internal/hash/xxh3.go:11-20) are the little-endian words at offsets 8, 16, 0 and 4 of it
+const uint8_t SECRET[192] = {
+    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
+    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
+    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
+    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
+    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
+    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
+    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
+    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
+    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
+    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
+    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
+    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
+};
+inline uint64_t r64(const uint8_t* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
+inline uint32_t r32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
+inline uint64_t rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
+inline uint64_t fold(uint64_t a, uint64_t b) { unsigned __int128 m = (unsigned __int128)a * b; return uint64_t(m) ^ uint64_t(m >> 64); }
+inline uint64_t aval64(uint64_t h) { h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32; return h; }
+inline uint64_t aval3(uint64_t h) { h ^= h >> 37; h *= 0x165667919E3779F9ull; h ^= h >> 32; return h; }
+inline uint64_t rrmxmx(uint64_t h, uint64_t len) {
+    h ^= rotl(h, 49) ^ rotl(h, 24); h *= 0x9FB21C651E98DF25ull; h ^= (h >> 35) + len; h *= 0x9FB21C651E98DF25ull;
+    return h ^ (h >> 28);
+}
+inline uint64_t mix(const uint8_t* in, const uint8_t* s) { return fold(r64(in) ^ r64(s), r64(in + 8) ^ r64(s + 8)); }
+void stripe(uint64_t* acc, const uint8_t* in, const uint8_t* s) {
+    for (int i = 0; i < 8; i++) {
+        uint64_t v = r64(in + 8 * i), k = v ^ r64(s + 8 * i);
+        acc[i ^ 1] += v; acc[i] += uint64_t(uint32_t(k)) * (k >> 32);
+    }
+}
+}  // namespace
+
+uint64_t xxh3_bytes(const uint8_t* in, size_t len) {
+    const uint8_t* s = SECRET;
+    if (len == 0) return aval64(r64(s + 56) ^ r64(s + 64));
+    if (len < 4) {
+        uint32_t c = (uint32_t(in[0]) << 16) | (uint32_t(in[len >> 1]) << 24) | in[len - 1] | (uint32_t(len) << 8);
+        return aval64(uint64_t(c) ^ uint64_t(r32(s) ^ r32(s + 4)));
+    }
+    if (len <= 8) return rrmxmx((uint64_t(r32(in + len - 4)) + (uint64_t(r32(in)) << 32)) ^ (r64(s + 8) ^ r64(s + 16)), len);
+    if (len <= 16) {
+        uint64_t lo = r64(in) ^ (r64(s + 24) ^ r64(s + 32)), hi = r64(in + len - 8) ^ (r64(s + 40) ^ r64(s + 48));
+        return aval3(len + __builtin_bswap64(lo) + hi + fold(lo, hi));
+    }
+    if (len <= 128) {
+        uint64_t acc = len * P64_1;
+        size_t pairs = (len - 1) / 32;   // 0..3 extra (front, back) pairs beyond the outermost one
+        for (size_t i = pairs; i > 0; i--) { acc += mix(in + 16 * i, s + 32 * i); acc += mix(in + len - 16 * (i + 1), s + 32 * i + 16); }
+        acc += mix(in, s); acc += mix(in + len - 16, s + 16);
+        return aval3(acc);
+    }
+    if (len <= 240) {
+        uint64_t acc = len * P64_1;
+        for (size_t i = 0; i < 8; i++) acc += mix(in + 16 * i, s + 16 * i);
+        acc = aval3(acc);
+        for (size_t i = 8; i < len / 16; i++) acc += mix(in + 16 * i, s + 16 * (i - 8) + 3);
+        acc += mix(in + len - 16, s + 119);
+        return aval3(acc);
+    }
+    uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
+    const size_t per_block = 16, block = per_block * 64;
+    size_t nblocks = (len - 1) / block;
+    for (size_t b = 0; b < nblocks; b++) {
+        for (size_t k = 0; k < per_block; k++) stripe(acc, in + b * block + k * 64, s + 8 * k);
+        for (int i = 0; i < 8; i++) { uint64_t x = acc[i]; x ^= x >> 47; x ^= r64(s + 128 + 8 * i); acc[i] = x * P32_1; }
+    }
+    size_t tail = ((len - 1) - nblocks * block) / 64;
+    for (size_t k = 0; k < tail; k++) stripe(acc, in + nblocks * block + k * 64, s + 8 * k);
+    stripe(acc, in + len - 64, s + 121);
+    uint64_t h = len * P64_1;
+    for (int i = 0; i < 4; i++) h += fold(acc[2 * i] ^ r64(s + 11 + 16 * i), acc[2 * i + 1] ^ r64(s + 19 + 16 * i));
+    return aval3(h);
+}
+
+uint64_t xxh3_u64(uint64_t v) { uint8_t b[8]; std::memcpy(b, &v, 8); return xxh3_bytes(b, 8); }
+uint64_t xxh3_u32(uint32_t v) { uint8_t b[4]; std::memcpy(b, &v, 4); return xxh3_bytes(b, 4); }
+uint64_t xxh3_u16(uint16_t v) { uint8_t b[2]; std::memcpy(b, &v, 2); return xxh3_bytes(b, 2); }
+uint64_t xxh3_u8(uint8_t v) { return xxh3_bytes(&v, 1); }
+
+}  // namespace kx

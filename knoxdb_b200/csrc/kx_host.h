@@ -1,0 +1,74 @@
+// kx_host.h — host-side runtime pieces of libknoxgpu: parsing of KnoxDB's encoded column
+// containers, normalisation into device ColViews and translation of filter leaves into
+// per-pack PackLeaf records.  Pure C++ (no CUDA), so it is unit-testable on a CPU box.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kx_types.h"
+
+namespace kx {
+
+// container ids, internal/encode/container.go:20-55
+enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATRAW = 15 };
+// types.FilterMode, internal/types/mode.go:14-23
+enum : int { M_EQ = 1, M_NE = 2, M_GT = 3, M_GE = 4, M_LT = 5, M_LE = 6, M_IN = 7, M_NIN = 8, M_RANGE = 9 };
+
+int  put_uvarint(uint8_t* b, uint64_t x);
+int  get_uvarint(const uint8_t* b, size_t avail, uint64_t* x);   // 0 on truncated input
+
+// parsed (not yet normalised) container tree; payload pointers alias the caller's buffer
+struct Container {
+    int ctype = 0, type = 0, log2 = 0;
+    size_t n = 0;
+    uint64_t val = 0, delta = 0;
+    const uint8_t* payload = nullptr;
+    size_t payload_len = 0;
+    std::unique_ptr<Container> child[2];
+};
+long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err);
+bool decode_container(const Container& c, std::vector<uint64_t>& out, std::string& err);
+
+// normalised block, ready for upload
+struct BlockLayout {
+    ColView view{};                     // pointers filled after upload
+    const uint8_t* stream = nullptr;    // verbatim packed / raw bytes inside the caller's buffer …
+    size_t stream_len = 0;
+    std::vector<uint8_t> owned;         // … or bytes re-packed on the host (simple8b, exotic code children)
+    std::vector<uint64_t> aux64;        // dict values (CK_DICT) or run values (CK_RUNEND → data)
+    std::vector<uint32_t> aux32;        // run ends (CK_RUNEND → aux)
+};
+int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, std::string& err);
+
+struct LeafSpec {
+    uint16_t field = 0;
+    uint8_t type = 0, mode = 0;
+    uint64_t a = 0, b = 0;
+    std::vector<uint64_t> set;   // sorted unique
+    uint32_t set_off = 0;        // offset into the program's concatenated device set array
+};
+
+// Translate one leaf for one block.  dict_host: host copy of the block's dictionary values
+// (CK_DICT only).  view_index: index of the block's ColView in the launch's view table.
+void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& leaf, uint32_t view_index, PackLeaf& out);
+
+// bits per row the leaf needs staged in shared memory (0 = none)
+inline int leaf_stage_width(const PackLeaf& l) { return l.data ? l.width : 0; }
+
+// scalar predicate on a decoded value (used for constants); a/b/v sign-extended patterns
+bool scalar_match(int type, int mode, uint64_t v, uint64_t a, uint64_t b);
+bool set_contains(const std::vector<uint64_t>& s, uint64_t v);
+
+// XXH3-64 (seed 0): internal/hash/xxh3.go:22-58 and hash.go:26
+uint64_t xxh3_u64(uint64_t v);
+uint64_t xxh3_u32(uint32_t v);
+uint64_t xxh3_u16(uint16_t v);
+uint64_t xxh3_u8(uint8_t v);
+uint64_t xxh3_bytes(const uint8_t* p, size_t len);
+
+size_t bitpack_bytes(int log2, size_t n);   // internal/encode/bitpack/bitpack.go:9-11
+
+}  // namespace kx

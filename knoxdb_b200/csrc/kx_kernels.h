@@ -1,0 +1,43 @@
+// kx_kernels.h — launch interface between the host runtime (kx_api.cu) and the kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kx_types.h"
+
+namespace kx {
+
+struct PruneLeaf {
+    uint64_t a, b;        // operands (64-bit pattern of T)
+    uint64_t flip;        // sign flip making unsigned order == T order
+    uint32_t set_off, nset;
+    uint8_t mode, is_float, pad[6];
+};
+
+struct PruneParams {
+    const uint64_t* mins;          // [npacks][nleaves]
+    const uint64_t* maxs;
+    const uint8_t* const* blooms;  // [npacks][nleaves] device pointers or nullptr (table may be nullptr)
+    const uint64_t* bloom_len;     // bytes of each bloom buffer
+    const uint64_t* hashes;        // concatenated probe hashes
+    const uint64_t* set_vals;      // concatenated sorted IN sets
+    uint32_t* out;                 // ceil(npacks/32) words
+    unsigned long long* count;
+    uint32_t npacks, nleaves, npost;
+    uint32_t hash_off[MAX_LEAVES + 1];
+    PruneLeaf leaves[MAX_LEAVES];
+    uint8_t postfix[MAX_POSTFIX];
+};
+
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream);
+cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,
+                            AggPartial* out, cudaStream_t stream);
+cudaError_t launch_bitset_op(uint32_t* dst, const uint32_t* src, uint64_t nbits, int op, unsigned int* flags, cudaStream_t stream);
+cudaError_t launch_bitset_neg(uint32_t* buf, uint64_t nbits, cudaStream_t stream);
+cudaError_t launch_bitset_popcount(const uint32_t* buf, uint64_t nbits, unsigned long long* out, cudaStream_t stream);
+cudaError_t launch_bitset_indexes(const uint32_t* buf, uint64_t nbits, uint32_t* block_tmp, unsigned long long* total,
+                                  uint32_t* dst, cudaStream_t stream);
+cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream);
+cudaError_t launch_prune(const PruneParams& P, cudaStream_t stream);
+
+}  // namespace kx

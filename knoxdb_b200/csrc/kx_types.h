@@ -1,0 +1,137 @@
+// kx_types.h — structures shared by the host runtime and the CUDA kernels of libknoxgpu.
+//
+// The device never sees KnoxDB's Go object graph.  It sees, per (pack, field), a ColView:
+// a flat description of one encoded column block resident in HBM, and per (pack, leaf) a
+// PackLeaf: a filter leaf already translated by the host into the block's own domain
+// (min-FOR domain for bit-packed blocks, code domain for dictionaries, row-index ranges for
+// affine "delta" blocks).
+#pragma once
+#include <stdint.h>
+
+#ifndef __CUDACC__
+#define KX_HD
+#else
+#define KX_HD __host__ __device__
+#endif
+
+namespace kx {
+
+// how a column block is laid out on the device
+enum ColKind : uint8_t {
+    CK_NONE = 0,
+    CK_CONST = 1,   // every row == base                         (IntConstant, bitpack w = 0)
+    CK_DELTA = 2,   // row i == base + i * delta (in T)          (IntDelta: affine sequence)
+    CK_BITS = 3,    // LSB-first bit stream, `width` bits per row, value = field + base
+                    // (IntBitpacked verbatim; IntRaw / FloatRaw are the width = 8*sizeof(T) case)
+    CK_DICT = 4,    // CK_BITS stream of codes (+ delta as code base); aux = dict values (u64)
+    CK_RUNEND = 5,  // data = run values (u64), aux = inclusive run ends (u32)
+};
+
+struct ColView {
+    const uint8_t* data;
+    const uint8_t* aux;
+    uint64_t base;
+    uint64_t delta;
+    uint32_t n;
+    uint32_t naux;
+    uint8_t kind;
+    uint8_t width;
+    uint8_t type;    // types.BlockType
+    uint8_t is_raw;  // CK_BITS: raw block (compare in T, width-bit modular arithmetic)
+    uint32_t pad;
+};
+
+// how a leaf predicate is evaluated for one pack
+enum LeafMode : uint8_t {
+    LM_NONE = 0,      // no row matches
+    LM_ALL = 1,       // every row matches
+    LM_RANGE32 = 2,   // staged stream, width <= 32: ((field - a) & wm) <= d   (32-bit)
+    LM_RANGE64 = 3,   // staged stream, any width:   ((field - a) & wm) <= d   (64-bit)
+    LM_FLOAT = 4,     // staged raw float stream: IEEE compare fop(a, b)
+    LM_ROWRANGE = 5,  // row index in [a, d] (affine blocks: closed-form index arithmetic)
+    LM_SET = 6,       // decoded value ∈ sorted set (binary search)
+    LM_VALRANGE = 7,  // decoded value v: ((v ^ flip) - a) <= d  (run-end / generic fallback)
+};
+
+struct PackLeaf {
+    const uint8_t* data;   // staged stream (LM_RANGE*, LM_FLOAT, LM_SET on CK_BITS/CK_DICT)
+    uint64_t a, d;         // range / operands (float: IEEE bits of a, b)
+    uint64_t wm;           // modular mask (LM_RANGE*) or sign flip (LM_VALRANGE)
+    uint8_t mode;
+    uint8_t width;         // bits per row of the staged stream (0: nothing staged)
+    uint8_t neg;           // invert the result (NE, GT, GE, NIN)
+    uint8_t fop;           // LM_FLOAT: FilterMode ; float width via `width`
+    uint32_t view;         // LM_SET / LM_VALRANGE: index into the ColView table of this leaf's block
+};
+
+struct PackInfo {
+    uint32_t n;           // rows
+    uint32_t tile0;       // first tile index of this pack
+    uint64_t bitset_off;  // byte offset of the pack's bitset in the output buffer
+};
+
+// per-CTA partial aggregate (combined in fixed order by finalize kernel)
+struct AggPartial {
+    uint64_t count;
+    uint64_t sum;      // integer sum mod 2^64, or IEEE bits of compensated sum (hi)
+    double   err;      // float: compensation (lo)
+    uint64_t mn, mx;   // order-preserving unsigned domain (ints: ^signflip; floats: IEEE bits)
+    uint32_t valid;
+    uint32_t pad;
+};
+
+constexpr int MAX_LEAVES = 8;
+constexpr int MAX_AGGS = 4;
+constexpr int MAX_POSTFIX = 2 * MAX_LEAVES;
+
+constexpr int CONSUMER_WARPS = 8;
+constexpr int SCAN_THREADS = (CONSUMER_WARPS + 1) * 32;   // + 1 TMA producer warp
+constexpr int STAGES = 4;
+
+struct ScanParams {
+    const PackInfo* packs;     // [npacks]
+    const PackLeaf* leaves;    // [npacks][nleaves]
+    const ColView*  views;     // ColView table (leaf blocks first, then agg blocks)
+    const uint32_t* tile_pack; // [ntiles] pack index of each tile (nullptr: uniform packs)
+    const uint64_t* set_vals;  // concatenated sorted sets
+    uint8_t*  bitsets;         // nullable
+    unsigned long long* counts; // [npacks] nullable
+    AggPartial* partials;      // [gridDim.x][naggs]
+    uint32_t npacks, ntiles;
+    uint32_t nleaves, npost, naggs;
+    uint32_t R;                // 32-row iterations per warp per tile; tile rows = 256 * R
+    uint32_t tiles_per_pack;   // uniform case
+    uint32_t stage_bytes;
+    uint32_t set_off[MAX_LEAVES + 1];
+    uint32_t agg_view0;        // views[agg_view0 + pack * naggs + j]
+    uint32_t leaf_view0;       // views[leaf_view0 + pack * nleaves + l]
+    uint8_t  postfix[MAX_POSTFIX];
+    uint8_t  agg_type[MAX_AGGS];
+};
+
+KX_HD inline bool type_is_signed(int t) { return t >= 1 && t <= 4; }
+KX_HD inline bool type_is_float(int t) { return t == 9 || t == 10; }
+KX_HD inline int type_bits(int t) {
+    switch (t) {
+    case 1: case 5: case 9: return 64;
+    case 2: case 6: case 10: return 32;
+    case 3: case 7: return 16;
+    case 4: case 8: return 8;
+    }
+    return 0;
+}
+// T(x): truncate to the width of T and extend back to 64 bit
+KX_HD inline uint64_t type_ext(int t, uint64_t x) {
+    switch (t) {
+    case 2: return (uint64_t)(int64_t)(int32_t)x;
+    case 3: return (uint64_t)(int64_t)(int16_t)x;
+    case 4: return (uint64_t)(int64_t)(int8_t)x;
+    case 6: case 10: return (uint32_t)x;
+    case 7: return (uint16_t)x;
+    case 8: return (uint8_t)x;
+    }
+    return x;
+}
+KX_HD inline uint64_t width_mask(int w) { return w >= 64 ? ~0ull : ((1ull << w) - 1ull); }
+
+}  // namespace kx

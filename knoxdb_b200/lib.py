@@ -1,0 +1,356 @@
+"""ctypes binding of libknoxgpu.so — mirrors include/knoxgpu.h one to one."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+INT64, INT32, INT16, INT8, UINT64, UINT32, UINT16, UINT8, FLOAT64, FLOAT32 = range(1, 11)
+EQ, NE, GT, GE, LT, LE, IN, NIN, RANGE = range(1, 10)
+OP_AND, OP_OR = 0xFE, 0xFF
+NP = {INT64: np.int64, INT32: np.int32, INT16: np.int16, INT8: np.int8, UINT64: np.uint64, UINT32: np.uint32,
+      UINT16: np.uint16, UINT8: np.uint8, FLOAT64: np.float64, FLOAT32: np.float32}
+
+ABI_SYMBOLS = [
+    "kx_abi_version", "kx_ctx_create", "kx_ctx_destroy", "kx_last_error", "kx_host_alloc", "kx_host_free",
+    "kx_block_put", "kx_block_drop", "kx_store_stats", "kx_prog_compile", "kx_prog_free", "kx_scan", "kx_scan_host",
+    "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
+    "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
+    "kx_hash_value", "kx_hash_bytes",
+]
+
+
+class KnoxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libknoxgpu error {code}: {msg}")
+        self.code = code
+
+
+class _Leaf(C.Structure):
+    _fields_ = [("field", C.c_uint16), ("block_type", C.c_uint8), ("mode", C.c_uint8), ("nset", C.c_uint32),
+                ("a", C.c_uint64), ("b", C.c_uint64), ("set", C.POINTER(C.c_uint64))]
+
+
+class _PackRef(C.Structure):
+    _fields_ = [("pack", C.c_uint32), ("version", C.c_uint32)]
+
+
+class _AggReq(C.Structure):
+    _fields_ = [("field", C.c_uint16), ("block_type", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class AggOut(C.Structure):
+    _fields_ = [("count", C.c_int64), ("sum_bits", C.c_uint64), ("sum_err", C.c_double), ("min_bits", C.c_uint64),
+                ("max_bits", C.c_uint64), ("valid", C.c_int32), ("reserved", C.c_int32)]
+
+    def value(self, which, block_type):
+        bits = {"sum": self.sum_bits, "min": self.min_bits, "max": self.max_bits}[which]
+        if block_type == FLOAT64:
+            return float(np.uint64(bits).view(np.float64))
+        if block_type <= INT8:
+            return int(np.uint64(bits).view(np.int64))
+        return int(bits)
+
+
+def library_path():
+    return os.path.join(HERE, "libknoxgpu.so")
+
+
+_lib = None
+
+
+def lib():
+    """Load libknoxgpu.so (building it in-tree first if the sources are newer)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    from . import build as _build
+    if not os.path.exists(library_path()) or _build.stale():
+        _build.build()
+    L = C.CDLL(library_path())
+    vp, u8p, u64p, sz = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_size_t
+    sig = {
+        "kx_abi_version": (C.c_int, []),
+        "kx_ctx_create": (C.c_int, [C.c_int, sz, C.POINTER(vp)]),
+        "kx_ctx_destroy": (None, [vp]),
+        "kx_last_error": (C.c_char_p, [vp]),
+        "kx_host_alloc": (vp, [vp, sz]),
+        "kx_host_free": (None, [vp, vp]),
+        "kx_block_put": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint16, C.c_uint8, vp, sz, C.POINTER(C.c_uint32)]),
+        "kx_block_drop": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint16]),
+        "kx_store_stats": (C.c_int, [vp, u64p, u64p, u64p]),
+        "kx_prog_compile": (C.c_int, [vp, C.POINTER(_Leaf), C.c_int, vp, C.c_int, C.POINTER(vp)]),
+        "kx_prog_free": (None, [vp]),
+        "kx_scan": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
+        "kx_scan_host": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
+        "kx_agg_combine": (C.c_int, [C.c_uint8, C.POINTER(AggOut), C.c_int, C.POINTER(AggOut)]),
+        "kx_last_scan_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
+        "kx_cmp": (C.c_int64, [vp, C.c_uint8, C.c_uint8, vp, sz, C.c_uint64, C.c_uint64, vp]),
+        "kx_bitpack_cmp": (C.c_int64, [vp, C.c_uint8, vp, C.c_int, C.c_uint64, C.c_uint64, sz, vp]),
+        "kx_bitpack_decode": (C.c_int, [vp, C.c_uint8, vp, C.c_int, C.c_uint64, sz, vp]),
+        "kx_container_match": (C.c_int64, [vp, C.c_uint8, vp, sz, C.c_uint8, C.c_uint64, C.c_uint64, vp, C.c_uint32, vp]),
+        "kx_container_decode": (C.c_int, [vp, C.c_uint8, vp, sz, vp, sz]),
+        "kx_bitset_op": (C.c_int, [vp, C.c_int, vp, vp, sz, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "kx_bitset_neg": (C.c_int, [vp, vp, sz]),
+        "kx_bitset_popcount": (C.c_int64, [vp, vp, sz]),
+        "kx_bitset_indexes": (C.c_int64, [vp, vp, sz, vp]),
+        "kx_prune": (C.c_int64, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+        "kx_hash_value": (C.c_uint64, [C.c_uint8, C.c_uint64]),
+        "kx_hash_bytes": (C.c_uint64, [vp, sz]),
+    }
+    assert sorted(sig) == sorted(ABI_SYMBOLS)
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p) if a.size else None
+    return a
+
+
+def _u64(x):
+    return int(x) & (2**64 - 1)
+
+
+def pattern(block_type, v):
+    """64-bit operand pattern of a python / numpy scalar of the block's type."""
+    if block_type == FLOAT64:
+        return int(np.array([v], np.float64).view(np.uint64)[0])
+    if block_type == FLOAT32:
+        return int(np.array([v], np.float32).view(np.uint32)[0])
+    return _u64(int(v))
+
+
+class Leaf:
+    """One filter leaf: (field, block type, mode, operands) — filter.Filter + Matcher."""
+
+    def __init__(self, field, block_type, mode, a=0, b=0, values=None):
+        self.field, self.block_type, self.mode = field, block_type, mode
+        self.a, self.b = pattern(block_type, a), pattern(block_type, b)
+        self.set = None
+        if values is not None:
+            arr = np.asarray(values)
+            if arr.dtype.kind == "i":
+                arr = arr.astype(np.int64).view(np.uint64)
+            self.set = np.ascontiguousarray(arr, dtype=np.uint64)
+
+
+class Program:
+    def __init__(self, ctx, leaves, postfix=None):
+        self.ctx = ctx
+        self.leaves = list(leaves)
+        if postfix is None:  # AND of all leaves
+            postfix = [0] + [x for i in range(1, len(self.leaves)) for x in (i, OP_AND)]
+        self.postfix = np.asarray(postfix, dtype=np.uint8)
+        arr = (_Leaf * len(self.leaves))()
+        for i, lf in enumerate(self.leaves):
+            arr[i].field, arr[i].block_type, arr[i].mode = lf.field, lf.block_type, lf.mode
+            arr[i].a, arr[i].b = lf.a, lf.b
+            if lf.set is not None and lf.set.size:
+                arr[i].nset = lf.set.size
+                arr[i].set = lf.set.ctypes.data_as(C.POINTER(C.c_uint64))
+        h = C.c_void_p()
+        ctx._check(lib().kx_prog_compile(ctx.h, arr, len(self.leaves), _ptr(self.postfix), self.postfix.size, C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().kx_prog_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Context:
+    """kx_ctx wrapper.  Raises KnoxError(KX_ENODEV) when there is no CUDA device."""
+
+    def __init__(self, device=0, hbm_budget=0):
+        h = C.c_void_p()
+        rc = lib().kx_ctx_create(device, hbm_budget, C.byref(h))
+        if rc != 0:
+            raise KnoxError(rc, (lib().kx_last_error(None) or b"").decode())
+        self.h = h
+
+    def _check(self, rc):
+        if rc < 0:
+            raise KnoxError(rc, (lib().kx_last_error(self.h) or b"").decode())
+        return rc
+
+    def close(self):
+        if self.h:
+            lib().kx_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pinned host memory
+    def host_array(self, nbytes):
+        """uint8 numpy array over pinned host memory (freed with the context)."""
+        p = lib().kx_host_alloc(self.h, max(int(nbytes), 1))
+        if not p:
+            raise KnoxError(-3, "kx_host_alloc failed")
+        buf = (C.c_uint8 * max(int(nbytes), 1)).from_address(p)
+        arr = np.frombuffer(buf, dtype=np.uint8, count=int(nbytes))
+        self.__dict__.setdefault("_pinned", []).append(p)
+        return arr
+
+    # ---- device pack store
+    def block_put(self, pack, version, field, block_type, enc):
+        enc = np.frombuffer(enc, dtype=np.uint8) if not isinstance(enc, np.ndarray) else enc
+        n = C.c_uint32()
+        self._check(lib().kx_block_put(self.h, pack, version, field, block_type, _ptr(enc), enc.size, C.byref(n)))
+        return n.value
+
+    def block_drop(self, pack, version, field):
+        self._check(lib().kx_block_drop(self.h, pack, version, field))
+
+    def store_stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().kx_store_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
+        return {"blocks": a.value, "encoded_bytes": b.value, "device_bytes": c.value}
+
+    # ---- scans
+    @staticmethod
+    def bitset_layout(nrows):
+        """8-byte aligned concatenation of per-pack bitsets → (offsets, total bytes)."""
+        offs, total = [], 0
+        for n in nrows:
+            offs.append(total)
+            total += ((int(n) + 7) // 8 + 7) // 8 * 8
+        return np.asarray(offs, dtype=np.uint64), total
+
+    def scan(self, prog, packs, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
+        """packs: list of (pack, version). Returns dict(counts, bitsets(list of arrays), aggs)."""
+        refs = (_PackRef * len(packs))(*[_PackRef(p, v) for p, v in packs])
+        counts = np.zeros(len(packs), dtype=np.int64) if want_counts else None
+        offs = bits = None
+        if want_bitsets:
+            offs, total = self.bitset_layout(nrows)
+            bits = bitset_buf if bitset_buf is not None else np.zeros(total, dtype=np.uint8)
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs), 1))()
+        self._check(lib().kx_scan(self.h, prog.h, refs, len(packs), _ptr(bits), _ptr(offs), _ptr(counts), areq, len(aggs), aout))
+        out = {"counts": counts, "aggs": list(aout)[:len(aggs)]}
+        if want_bitsets:
+            out["bitsets"] = [bits[int(o):int(o) + (int(n) + 7) // 8] for o, n in zip(offs, nrows)]
+        return out
+
+    def scan_host(self, prog, fields, blocks, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
+        """fields: [(field id, block type)]; blocks: per pack a list of encoded blocks (np.uint8 arrays) per field."""
+        npacks, nf = len(blocks), len(fields)
+        keep = [b if isinstance(b, np.ndarray) else np.frombuffer(b, dtype=np.uint8) for row in blocks for b in row]
+        ptrs = (C.c_void_p * max(len(keep), 1))(*[b.ctypes.data for b in keep])
+        lens = (C.c_size_t * max(len(keep), 1))(*[b.size for b in keep])
+        fid = np.asarray([f for f, _ in fields], dtype=np.uint16)
+        fty = np.asarray([t for _, t in fields], dtype=np.uint8)
+        counts = np.zeros(npacks, dtype=np.int64) if want_counts else None
+        offs = bits = None
+        if want_bitsets:
+            offs, total = self.bitset_layout(nrows)
+            bits = bitset_buf if bitset_buf is not None else np.zeros(total, dtype=np.uint8)
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs), 1))()
+        self._check(lib().kx_scan_host(self.h, prog.h, npacks, _ptr(fid), _ptr(fty), nf, ptrs, lens, _ptr(bits), _ptr(offs),
+                                       _ptr(counts), areq, len(aggs), aout))
+        out = {"counts": counts, "aggs": list(aout)[:len(aggs)]}
+        if want_bitsets:
+            out["bitsets"] = [bits[int(o):int(o) + (int(n) + 7) // 8] for o, n in zip(offs, nrows)]
+        return out
+
+    def last_scan_stats(self):
+        k, t, n = C.c_double(), C.c_double(), C.c_int()
+        lib().kx_last_scan_stats(self.h, C.byref(k), C.byref(t), C.byref(n))
+        return {"kernel_ms": k.value, "total_ms": t.value, "launches": n.value}
+
+    # ---- narrow drop-ins
+    def cmp(self, block_type, mode, src, a, b=0):
+        src = np.ascontiguousarray(src, dtype=NP[block_type])
+        bits = np.zeros((src.size + 7) // 8 + 8, dtype=np.uint8)
+        cnt = self._check(lib().kx_cmp(self.h, block_type, mode, _ptr(src), src.size, pattern(block_type, a), pattern(block_type, b), _ptr(bits)))
+        return bits[:(src.size + 7) // 8], cnt
+
+    def bitpack_cmp(self, mode, packed, log2, a, b, n):
+        packed = np.ascontiguousarray(packed)
+        bits = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
+        cnt = self._check(lib().kx_bitpack_cmp(self.h, mode, _ptr(packed), log2, _u64(a), _u64(b), n, _ptr(bits)))
+        return bits[:(n + 7) // 8], cnt
+
+    def bitpack_decode(self, block_type, packed, log2, minv, n):
+        packed = np.ascontiguousarray(packed)
+        out = np.zeros(max(n, 1), dtype=NP[block_type])
+        self._check(lib().kx_bitpack_decode(self.h, block_type, _ptr(packed), log2, _u64(minv), n, _ptr(out)))
+        return out[:n]
+
+    def container_match(self, block_type, enc, mode, a=0, b=0, values=None, nrows=None):
+        enc = np.frombuffer(enc, dtype=np.uint8) if not isinstance(enc, np.ndarray) else enc
+        bits = np.zeros((nrows + 7) // 8 + 8, dtype=np.uint8)
+        s = None
+        if values is not None:
+            s = np.asarray(values)
+            s = s.astype(np.int64).view(np.uint64) if s.dtype.kind == "i" else s.astype(np.uint64)
+            s = np.ascontiguousarray(s)
+        cnt = self._check(lib().kx_container_match(self.h, block_type, _ptr(enc), enc.size, mode, pattern(block_type, a),
+                                                   pattern(block_type, b), _ptr(s), 0 if s is None else s.size, _ptr(bits)))
+        return bits[:(nrows + 7) // 8], cnt
+
+    def container_decode(self, block_type, enc, nrows):
+        enc = np.frombuffer(enc, dtype=np.uint8) if not isinstance(enc, np.ndarray) else enc
+        out = np.zeros(max(nrows, 1), dtype=NP[block_type])
+        self._check(lib().kx_container_decode(self.h, block_type, _ptr(enc), enc.size, _ptr(out), nrows))
+        return out[:nrows]
+
+    def bitset_op(self, op, dst, src, nbits):
+        dst = np.ascontiguousarray(dst, dtype=np.uint8).copy()
+        src = np.ascontiguousarray(src, dtype=np.uint8)
+        any_, all_ = C.c_int(), C.c_int()
+        self._check(lib().kx_bitset_op(self.h, op, _ptr(dst), _ptr(src), nbits, C.byref(any_), C.byref(all_)))
+        return dst, bool(any_.value), bool(all_.value)
+
+    def bitset_neg(self, buf, nbits):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8).copy()
+        self._check(lib().kx_bitset_neg(self.h, _ptr(buf), nbits))
+        return buf
+
+    def bitset_popcount(self, buf, nbits):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        return self._check(lib().kx_bitset_popcount(self.h, _ptr(buf), nbits))
+
+    def bitset_indexes(self, buf, nbits):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        out = np.zeros(nbits + 8, dtype=np.uint32)
+        n = self._check(lib().kx_bitset_indexes(self.h, _ptr(buf), nbits, _ptr(out)))
+        return out[:n]
+
+    def prune(self, prog, mins, maxs, blooms=None, hashes=None):
+        """mins/maxs: [npacks, nleaves] uint64 patterns; blooms: [npacks][nleaves] of np.uint8 arrays or None;
+        hashes: per leaf list of probe hashes."""
+        mins = np.ascontiguousarray(mins, dtype=np.uint64)
+        maxs = np.ascontiguousarray(maxs, dtype=np.uint64)
+        npacks, nleaves = mins.shape
+        out = np.zeros((npacks + 7) // 8 + 8, dtype=np.uint8)
+        bp = bl = hs = ho = None
+        keep = []
+        if blooms is not None:
+            flat = [b for row in blooms for b in row]
+            keep = [None if b is None else np.ascontiguousarray(b, dtype=np.uint8) for b in flat]
+            bp = (C.c_void_p * len(keep))(*[None if b is None else b.ctypes.data for b in keep])
+            bl = (C.c_size_t * len(keep))(*[0 if b is None else b.size for b in keep])
+            hs = np.asarray([h for hl in hashes for h in hl], dtype=np.uint64)
+            ho = np.asarray(np.concatenate([[0], np.cumsum([len(hl) for hl in hashes])]), dtype=np.uint32)
+        n = self._check(lib().kx_prune(self.h, prog.h, npacks, _ptr(mins), _ptr(maxs), bp, bl, _ptr(hs), _ptr(ho), _ptr(out)))
+        return out[:(npacks + 7) // 8], n

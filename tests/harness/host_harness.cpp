@@ -1,0 +1,129 @@
+// host_harness.cpp — TEST INFRASTRUCTURE ONLY (never part of libknoxgpu.so).
+//
+// Links the product's host-side translation code (knoxdb_b200/csrc/kx_host.cpp: container
+// parsing, block normalisation, leaf → PackLeaf translation) into a CPU-only shared library
+// and interprets the resulting PackLeaf records with a scalar emulator of the device
+// semantics documented in kx_types.h.  This lets the CPU test tier check the translation
+// logic (min-FOR pre-checks, dictionary code ranges, affine row ranges …) against the oracle
+// without a GPU.  The CUDA kernels themselves are only exercised by the `-m gpu` tests.
+#include <algorithm>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../knoxdb_b200/csrc/kx_host.h"
+
+using namespace kx;
+
+namespace {
+
+uint64_t field_at(const uint8_t* s, size_t len, uint64_t row, int w) {
+    if (w == 0) return 0;
+    uint64_t bit = row * uint64_t(w); size_t byte = bit >> 3; int sh = int(bit & 7);
+    unsigned __int128 acc = 0;
+    for (int i = 0; i < 9 && byte + i < len; i++) acc |= (unsigned __int128)s[byte + i] << (8 * i);
+    return uint64_t(acc >> sh) & width_mask(w);
+}
+
+struct HostBlock {
+    BlockLayout lay;
+    const uint8_t* stream() const { return lay.owned.empty() ? lay.stream : lay.owned.data(); }
+    size_t stream_len() const { return lay.owned.empty() ? lay.stream_len : lay.owned.size(); }
+    uint64_t value(uint32_t row) const {
+        const ColView& v = lay.view;
+        switch (v.kind) {
+        case CK_CONST: return v.base;
+        case CK_DELTA: return type_ext(v.type, uint64_t(row) * v.delta + v.base);
+        case CK_BITS: {
+            uint64_t f = field_at(stream(), stream_len(), row, v.width);
+            return type_is_float(v.type) ? f : type_ext(v.type, f + v.base);
+        }
+        case CK_DICT: return lay.aux64[field_at(stream(), stream_len(), row, v.width) + v.delta];
+        case CK_RUNEND: {
+            size_t lo = 0, hi = lay.aux32.size();
+            while (lo < hi) { size_t m = (lo + hi) / 2; if (lay.aux32[m] >= row) hi = m; else lo = m + 1; }
+            return lay.aux64[lo];
+        }
+        }
+        return 0;
+    }
+};
+
+bool fpred(int op, double x, double a, double b) {
+    switch (op) {
+    case 1: return x == a; case 2: return x != a; case 3: return x > a; case 4: return x >= a;
+    case 5: return x < a; case 6: return x <= a; case 9: return a <= x && x <= b;
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+// returns rows, or <0 on error; bits: ceil(n/8) bytes pre-zeroed; mode_out: PackLeaf.mode chosen
+long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_t a, uint64_t b,
+               const uint64_t* set, uint32_t nset, uint8_t* bits, int* mode_out) {
+    HostBlock hb; std::string err;
+    if (normalize_block(block_type, enc, len, hb.lay, err)) return -1;
+    const ColView& v = hb.lay.view;
+    LeafSpec leaf; leaf.type = uint8_t(block_type); leaf.mode = uint8_t(mode); leaf.a = a; leaf.b = b;
+    if (set) { leaf.set.assign(set, set + nset); std::sort(leaf.set.begin(), leaf.set.end()); leaf.set.erase(std::unique(leaf.set.begin(), leaf.set.end()), leaf.set.end()); }
+    ColView dv = v;
+    dv.data = hb.stream();   // non-null marks "has a stream" for compile_leaf
+    PackLeaf L;
+    compile_leaf(dv, hb.lay.aux64.empty() ? nullptr : hb.lay.aux64.data(), leaf, 0, L);
+    if (mode_out) *mode_out = L.mode;
+    for (uint32_t row = 0; row < v.n; row++) {
+        bool p = false;
+        switch (L.mode) {
+        case LM_NONE: p = false; break;
+        case LM_ALL: p = true; break;
+        case LM_RANGE32: {
+            uint32_t f = uint32_t(field_at(hb.stream(), hb.stream_len(), row, L.width));
+            p = ((f - uint32_t(L.a)) & uint32_t(L.wm)) <= uint32_t(L.d);
+            break;
+        }
+        case LM_RANGE64: {
+            uint64_t f = field_at(hb.stream(), hb.stream_len(), row, L.width);
+            p = ((f - L.a) & L.wm) <= L.d;
+            break;
+        }
+        case LM_FLOAT: {
+            uint64_t f = field_at(hb.stream(), hb.stream_len(), row, L.width);
+            double x, da, db;
+            if (L.width == 32) {
+                float fx, fa, fb; uint32_t u = uint32_t(f); std::memcpy(&fx, &u, 4);
+                u = uint32_t(L.a); std::memcpy(&fa, &u, 4); u = uint32_t(L.d); std::memcpy(&fb, &u, 4);
+                x = fx; da = fa; db = fb;
+            } else { std::memcpy(&x, &f, 8); std::memcpy(&da, &L.a, 8); std::memcpy(&db, &L.d, 8); }
+            p = fpred(L.fop, x, da, db);
+            break;
+        }
+        case LM_ROWRANGE: p = (uint64_t(row) - L.a) <= L.d; break;
+        case LM_SET: p = set_contains(leaf.set, hb.value(row)); break;
+        case LM_VALRANGE: p = ((hb.value(row) ^ L.wm) - L.a) <= L.d; break;
+        }
+        if (L.neg && L.mode != LM_NONE && L.mode != LM_ALL) p = !p;
+        if (p) bits[row >> 3] |= uint8_t(1u << (row & 7));
+    }
+    return long(v.n);
+}
+
+long kxh_decode(int block_type, const uint8_t* enc, size_t len, uint64_t* dst, size_t cap) {
+    HostBlock hb; std::string err;
+    if (normalize_block(block_type, enc, len, hb.lay, err)) return -1;
+    if (hb.lay.view.n > cap) return -2;
+    for (uint32_t r = 0; r < hb.lay.view.n; r++) dst[r] = hb.value(r);
+    return long(hb.lay.view.n);
+}
+
+int kxh_view_kind(int block_type, const uint8_t* enc, size_t len) {
+    BlockLayout lay; std::string err;
+    if (normalize_block(block_type, enc, len, lay, err)) return -1;
+    return lay.view.kind;
+}
+
+uint64_t kxh_xxh3_bytes(const uint8_t* p, size_t len) { return xxh3_bytes(p, len); }
+
+}  // extern "C"

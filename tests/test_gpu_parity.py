@@ -1,0 +1,364 @@
+"""GPU tier (-m gpu): the CUDA path behind the C ABI against the CPU oracle, bit for bit.
+
+Every call below goes through libknoxgpu.so's exported C symbols (ctypes), i.e. the same
+entry points the cgo adapters bind.  Integer / byte / index results must be bit-exact;
+float64 sums must agree with the oracle's sequential sum within 1e-12 relative.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import kxtest as kt
+import oracle as ko
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(__file__), "golden")
+RNG = np.random.default_rng(1234)
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import knoxdb_b200 as kb
+    c = kb.Context(0)     # raises KnoxError(KX_ENODEV) without a CUDA device: no CPU fallback
+    yield c
+    c.close()
+
+
+def typed_src(tname, patterns):
+    t = ko.TYPE_BY_NAME[tname]
+    if t == ko.F64:
+        return np.array(patterns, dtype=np.uint64).view(np.float64)
+    if t == ko.F32:
+        return np.array(patterns, dtype=np.uint32).view(np.float32)
+    return np.array(patterns, dtype=np.int64 if t <= ko.I8 else np.uint64).astype(ko.NP[t])
+
+
+def from_pattern(t, p):
+    if t == ko.F64:
+        return np.uint64(p).view(np.float64)
+    if t == ko.F32:
+        return np.uint32(p).view(np.float32)
+    return int(np.uint64(p & (2**64 - 1)).view(np.int64)) if t <= ko.I8 else int(p)
+
+
+def test_cmp_golden_vectors(ctx):
+    """the reference's own known-answer vectors (internal/cmp/tests/<type>.go) through kx_cmp"""
+    cmpv = json.load(open(os.path.join(G, "cmp_vectors.json")))["types"]
+    ncases = 0
+    for tname, ops in cmpv.items():
+        t = ko.TYPE_BY_NAME[tname]
+        for opname, cases in ops.items():
+            for c in cases:
+                src = typed_src(tname, c["src"])
+                bits, cnt = ctx.cmp(t, ko.OP_BY_NAME[opname], src, from_pattern(t, c["a"]), from_pattern(t, c["b"]))
+                assert bits.tobytes().hex() == c["bits"], (tname, opname, c["name"])
+                assert cnt == c["count"], (tname, opname, c["name"])
+                ncases += 1
+    assert ncases == 1476
+
+
+def test_bitset_golden_vectors(ctx):
+    bs = json.load(open(os.path.join(G, "bitset_vectors.json")))
+    for c in bs["pop"]:
+        buf = np.frombuffer(bytes.fromhex(c["source"]), dtype=np.uint8)
+        assert ctx.bitset_popcount(buf, c["size"]) == c["count"], c["name"]
+    for c in bs["index"]:
+        buf = np.frombuffer(bytes.fromhex(c["buf"]), dtype=np.uint8)
+        if c["size"] == 0:
+            continue
+        assert ctx.bitset_indexes(buf, c["size"]).tolist() == c["idx"], c["name"]
+
+
+@pytest.mark.parametrize("t", [ko.I64, ko.U64, ko.I32, ko.U32, ko.I16, ko.U16, ko.I8, ko.U8, ko.F64, ko.F32])
+def test_cmp_random_vs_oracle(ctx, t):
+    for n in (1, 31, 32, 33, 1000, 8191, 8192, 8193, 70001):
+        if t in (ko.F64, ko.F32):
+            vals = (RNG.integers(0, 2**40, n) / 100.0).astype(ko.NP[t])
+            vals[::53] = np.nan
+            picks = [(vals[n // 2], vals[n // 2] * 2), (np.nan, 1.0), (0.0, np.inf)]
+        else:
+            vals = kt.typed_rand(RNG, t, n)
+            info = np.iinfo(ko.NP[t])
+            picks = [(int(vals[n // 2]), min(info.max, int(vals[n // 2]) + 1000)), (info.min, info.max), (info.max, info.min), (0, 0)]
+        for a, b in picks:
+            for op in kt.OPS:
+                want, wc = ko.cmp(t, op, vals, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                got, gc = ctx.cmp(t, op, vals, a, b)
+                assert (got == want).all() and gc == wc, (t, n, op, a, b)
+
+
+@pytest.mark.parametrize("w", list(range(0, 65)))
+def test_bitpack_cmp_all_widths(ctx, w):
+    """bitpack.Equal…Between on packed words for every width (reference: bitpack/tests/tests.go:144-298)"""
+    L = ko.lib()
+    for n in (1, 63, 64, 65, 1025, 8192 + 77, 3 * 8192):
+        vals = kt.rnd_bits(RNG, n, w)
+        packed = np.zeros(L.ko_bitpack_size(w, n) // 8 + 1, dtype=np.uint64)
+        L.ko_bitpack_encode(ko._p(packed), ko._p(vals), n, w, 0)
+        top = (1 << w) - 1 if w < 64 else 2**64 - 1
+        for a in (int(vals[0]), int(vals[n // 2]), 0, top, min(top + 1, 2**64 - 1)):
+            for op in kt.OPS:
+                b = min(a + (1 << max(w - 2, 0)), 2**64 - 1)
+                want = np.zeros(ko.nbytes(n) + 8, dtype=np.uint8)
+                L.ko_bitpack_cmp(op, ko._p(packed), w, a, b, n, ko._p(want))
+                got, cnt = ctx.bitpack_cmp(op, packed[:-1] if packed.size > 1 else packed, w, a, b, n)
+                assert (got == want[:ko.nbytes(n)]).all(), (w, n, op, a, b)
+                assert cnt == int(np.unpackbits(want).sum())
+        # decode
+        base = 12345
+        out = ctx.bitpack_decode(ko.U64, packed, w, base, n)
+        assert (out == vals + np.uint64(base)).all(), (w, n)
+
+
+@pytest.mark.parametrize("t", kt.INT_TYPES)
+def test_container_match_and_decode(ctx, t):
+    """types.NumberMatcher[T] on every container scheme (EnsureBits: encode/tests/tests.go:140-205)"""
+    for n in (1, 67, 1025, 9000):
+        for name, vals in kt.shapes(RNG, t, n).items():
+            for kind in kt.container_kinds(t, vals):
+                blob = ko.store(kind, t, vals)
+                oc = ko.Container(t, blob)
+                assert (ctx.container_decode(t, blob, n) == vals).all(), (name, kind)
+                for a in kt.operands(t, vals)[:5]:
+                    b = min(np.iinfo(ko.NP[t]).max, a + 5)
+                    for op in kt.OPS:
+                        want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                        got, cnt = ctx.container_match(t, blob, op, a, b, nrows=n)
+                        if not (got == want).all():
+                            if op == ko.RG and oc.ctype == ko.TRUNEND and oc.value_delta_sequences():
+                                want = kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](b)))
+                            assert (got == want).all(), (ko.NP[t].__name__, n, name, kind, op, a, b)
+                        assert cnt == int(np.unpackbits(got).sum())
+                setv = np.unique(np.concatenate([vals[: min(3, n)], kt.typed_rand(RNG, t, 3)]))
+                su = ko.as_u64(t, setv)
+                for neg, op in ((False, ko.IN), (True, ko.NI)):
+                    got, _ = ctx.container_match(t, blob, op, values=su, nrows=n)
+                    assert (got == oc.match_set(su, negate=neg)).all(), (name, kind, "set", neg)
+
+
+def test_bitset_ops(ctx):
+    import knoxdb_b200 as kb
+    L = ko.lib()
+    import ctypes as C
+    for size in (1, 7, 8, 9, 63, 64, 65, 1000, 4099, 300007):
+        l = ko.nbytes(size)
+        a = RNG.integers(0, 256, l, dtype=np.uint8)
+        b = RNG.integers(0, 256, l, dtype=np.uint8)
+        for op, name, flag in ((0, "ko_bitset_and_flag", True), (1, "ko_bitset_andnot", False), (2, "ko_bitset_or_flag", True), (3, "ko_bitset_xor", False)):
+            d = a.copy()
+            any_, all_ = C.c_int(), C.c_int()
+            if flag:
+                getattr(L, name)(ko._p(d), ko._p(b), size, C.byref(any_), C.byref(all_))
+            else:
+                getattr(L, name)(ko._p(d), ko._p(b), size)
+            got, gany, gall = ctx.bitset_op(op, a, b, size)
+            assert (got == d).all(), (name, size)
+            if flag:
+                assert gany == bool(any_.value) and gall == bool(all_.value), (name, size)
+        d = a.copy(); L.ko_bitset_neg(ko._p(d), size)
+        assert (ctx.bitset_neg(a, size) == d).all()
+        assert ctx.bitset_popcount(a, size) == L.ko_bitset_popcount(ko._p(a), size)
+        idx = np.zeros(size + 8, dtype=np.uint32)
+        k = L.ko_bitset_indexes(ko._p(a), size, ko._p(idx))
+        assert (ctx.bitset_indexes(a, size) == idx[:k]).all()
+
+
+def make_table(rng, npacks, nrows_list):
+    """3-column packs of BASELINE config 3: ts (sorted int64), acct (uint64 dups), amount (int64 + float64)"""
+    packs = []
+    t0 = 1_700_000_000
+    accts = kt.rnd_bits(rng, 500, 40)
+    for p in range(npacks):
+        n = nrows_list[p]
+        ts = (t0 + np.cumsum(rng.integers(0, 3, n))).astype(np.int64)
+        t0 = int(ts[-1]) + 1 if n else t0
+        acct = rng.choice(accts, n).astype(np.uint64)
+        amount = rng.integers(-10**9, 10**9, n).astype(np.int64)
+        famount = (rng.integers(0, 2**50, n) / 100.0).astype(np.float64)
+        packs.append({"ts": ts, "acct": acct, "amount": amount, "famount": famount})
+    return packs, accts
+
+
+F_TS, F_ACCT, F_AMT, F_FAMT = 1, 2, 3, 4
+
+
+def put_table(ctx, packs, acct_kind="dict"):
+    blobs = []
+    for p, cols in enumerate(packs):
+        enc = {F_TS: ko.store("best", ko.I64, cols["ts"]), F_ACCT: ko.store(acct_kind, ko.U64, cols["acct"]),
+               F_AMT: ko.store("best", ko.I64, cols["amount"]), F_FAMT: ko.store("raw", ko.F64, cols["famount"])}
+        for f, t in ((F_TS, ko.I64), (F_ACCT, ko.U64), (F_AMT, ko.I64), (F_FAMT, ko.F64)):
+            assert ctx.block_put(p, 1, f, t, enc[f]) == cols["ts"].size
+        blobs.append(enc)
+    return blobs
+
+
+def oracle_query(packs, blobs, t_lo, t_hi, set_u64, postfix):
+    counts, bitsets = [], []
+    agg_i, agg_f = ko.Agg(), ko.Agg()
+    for cols, enc in zip(packs, blobs):
+        n = cols["ts"].size
+        l0 = ko.Container(ko.I64, enc[F_TS]).match(ko.RG, ko.scalar_u64(ko.I64, t_lo), ko.scalar_u64(ko.I64, t_hi))
+        l1 = ko.Container(ko.U64, enc[F_ACCT]).match_set(set_u64)
+        bits = ko.tree_eval(postfix, [l0, l1], n)
+        bitsets.append(bits)
+        counts.append(int(np.unpackbits(bits).sum()))
+        agg_i = ko.reduce(ko.I64, cols["amount"], bits, agg_i)
+        agg_f = ko.reduce(ko.F64, cols["famount"], bits, agg_f)
+    return counts, bitsets, agg_i, agg_f
+
+
+@pytest.mark.parametrize("acct_kind", ["dict", "bitpack", "raw"])
+def test_multi_predicate_scan_with_aggregates(ctx, acct_kind):
+    """BASELINE config 3: ts BETWEEN AND acct IN {…} → count/sum/min/max over int64 and float64"""
+    import knoxdb_b200 as kb
+    nrows = [4096, 70000, 8192, 1, 33333, 16384]
+    packs, accts = make_table(RNG, len(nrows), nrows)
+    blobs = put_table(ctx, packs, acct_kind)
+    all_ts = np.concatenate([c["ts"] for c in packs])
+    for sel in (0.001, 0.1, 0.9):
+        t_lo = int(all_ts[int(all_ts.size * 0.05)])
+        t_hi = int(all_ts[min(all_ts.size - 1, int(all_ts.size * (0.05 + sel)))])
+        setv = RNG.choice(accts, 64, replace=False)
+        for postfix in ([0, 1, kb.OP_AND], [0, 1, kb.OP_OR]):
+            prog = kb.Program(ctx, [kb.Leaf(F_TS, kb.INT64, kb.RANGE, t_lo, t_hi), kb.Leaf(F_ACCT, kb.UINT64, kb.IN, values=setv)], postfix)
+            res = ctx.scan(prog, [(p, 1) for p in range(len(nrows))], nrows=nrows, want_bitsets=True,
+                           aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64)])
+            counts, bitsets, agg_i, agg_f = oracle_query(packs, blobs, t_lo, t_hi, setv, postfix)
+            assert res["counts"].tolist() == counts
+            for got, want in zip(res["bitsets"], bitsets):
+                assert (got == want).all()
+            gi, gf = res["aggs"]
+            assert gi.count == agg_i.count and gf.count == agg_f.count
+            assert bool(gi.valid) == bool(agg_i.valid)
+            if agg_i.valid:
+                assert gi.sum_bits == agg_i.sum_bits and gi.min_bits == agg_i.min_bits and gi.max_bits == agg_i.max_bits
+                want_sum = np.uint64(agg_f.sum_bits).view(np.float64)
+                got_sum = np.uint64(gf.sum_bits).view(np.float64)
+                assert abs(got_sum - want_sum) <= 1e-12 * abs(want_sum)          # north-star tolerance
+                assert gf.min_bits == agg_f.min_bits and gf.max_bits == agg_f.max_bits
+            prog.close()
+    # the same query over HOST blocks (cold device cache path)
+    prog = kb.Program(ctx, [kb.Leaf(F_TS, kb.INT64, kb.RANGE, t_lo, t_hi), kb.Leaf(F_ACCT, kb.UINT64, kb.IN, values=setv)])
+    fields = [(F_TS, kb.INT64), (F_ACCT, kb.UINT64), (F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64)]
+    hb = [[np.frombuffer(enc[f], np.uint8) for f, _ in fields] for enc in blobs]
+    res_h = ctx.scan_host(prog, fields, hb, nrows=nrows, want_bitsets=True, aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64)])
+    res_d = ctx.scan(prog, [(p, 1) for p in range(len(nrows))], nrows=nrows, want_bitsets=True, aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64)])
+    assert res_h["counts"].tolist() == res_d["counts"].tolist()
+    for x, y in zip(res_h["bitsets"], res_d["bitsets"]):
+        assert (x == y).all()
+    for x, y in zip(res_h["aggs"], res_d["aggs"]):
+        assert (x.count, x.sum_bits, x.min_bits, x.max_bits) == (y.count, y.sum_bits, y.min_bits, y.max_bits)
+    for p in range(len(nrows)):
+        for f in (F_TS, F_ACCT, F_AMT, F_FAMT):
+            ctx.block_drop(p, 1, f)
+    assert ctx.store_stats()["blocks"] == 0
+
+
+def test_full_size_pack_properties(ctx):
+    """BASELINE config 2 at full size: 4M-row bit-packed packs; size-independent checks
+    (count == popcount(bitset) == numpy truth; NE is the complement of EQ; LT ∪ GE covers all rows)"""
+    import knoxdb_b200 as kb
+    n = 4 * 1024 * 1024
+    for w in (8, 20, 33):
+        vals = kt.rnd_bits(RNG, n, w) + np.uint64(1000)
+        blob = ko.store("bitpack", ko.U64, vals)
+        assert ctx.block_put(0, 1, 9, kb.UINT64, blob) == n
+        med = int(np.median(vals))
+        res = {}
+        for mode in (kb.EQ, kb.NE, kb.LT, kb.GE):
+            prog = kb.Program(ctx, [kb.Leaf(9, kb.UINT64, mode, int(vals[12345]) if mode in (kb.EQ, kb.NE) else med)])
+            r = ctx.scan(prog, [(0, 1)], nrows=[n], want_bitsets=True)
+            res[mode] = (int(r["counts"][0]), r["bitsets"][0].copy())
+            prog.close()
+        assert (res[kb.EQ][1] == kt.pack_bits(vals == vals[12345])).all()
+        assert (res[kb.LT][1] == kt.pack_bits(vals < np.uint64(med))).all()
+        for mode in res:
+            assert res[mode][0] == int(np.unpackbits(res[mode][1]).sum())
+        assert ((res[kb.EQ][1] ^ res[kb.NE][1]) == 0xFF).all() and res[kb.EQ][0] + res[kb.NE][0] == n
+        assert ((res[kb.LT][1] | res[kb.GE][1]) == 0xFF).all() and res[kb.LT][0] + res[kb.GE][0] == n
+        ctx.block_drop(0, 1, 9)
+
+
+def test_prune_zone_maps_and_bloom(ctx):
+    """stats.matchVector: zone maps via MatchRangeVectors semantics + bloom probes (config 4 shape)"""
+    import knoxdb_b200 as kb
+    L = ko.lib()
+    npacks = 1000
+    heights = np.arange(npacks, dtype=np.int64) * 100
+    mins = np.stack([heights, RNG.integers(0, 2**40, npacks).astype(np.int64)], axis=1)
+    maxs = np.stack([heights + 99, mins[:, 1] + RNG.integers(0, 2**40, npacks)], axis=1)
+    # bloom per pack over 64 random "addresses" hashed with XXH3 of 20-byte strings
+    m_bits = 64 * 16
+    blooms, members = [], []
+    for p in range(npacks):
+        buf = np.zeros(L.ko_bloom_bytes(m_bits), dtype=np.uint8)
+        L.ko_bloom_init(ko._p(buf), m_bits)
+        addrs = RNG.integers(0, 256, (64, 20), dtype=np.uint8)
+        hs = [L.ko_xxh3_bytes(ko._p(a), 20) for a in addrs]
+        for h in hs:
+            L.ko_bloom_add(ko._p(buf), buf.size, h)
+        blooms.append([None, buf])
+        members.append((addrs, hs))
+    probe_addr = members[417][0][3]
+    probe_hash = kb.lib().kx_hash_bytes(probe_addr.ctypes.data, 20)
+    assert probe_hash == members[417][1][3]            # product hash == oracle hash
+    lo, hi = 30000, 60000
+    probe_val = int(mins[417, 1] + 5)
+    prog = kb.Program(ctx, [kb.Leaf(0, kb.INT64, kb.RANGE, lo, hi), kb.Leaf(1, kb.INT64, kb.EQ, probe_val)])
+    bits, nsurv = ctx.prune(prog, mins.view(np.uint64), maxs.view(np.uint64), blooms, [[], [probe_hash]])
+    want = np.zeros(npacks, dtype=bool)
+    for p in range(npacks):
+        z = L.ko_match_range(ko.I64, ko.RG, ko.scalar_u64(ko.I64, lo), ko.scalar_u64(ko.I64, hi), int(mins[p, 0]) & (2**64 - 1), int(maxs[p, 0]) & (2**64 - 1))
+        z2 = L.ko_match_range(ko.I64, ko.EQ, ko.scalar_u64(ko.I64, probe_val), 0, int(mins[p, 1]) & (2**64 - 1), int(maxs[p, 1]) & (2**64 - 1))
+        bl = L.ko_bloom_contains(ko._p(blooms[p][1]), blooms[p][1].size, probe_hash)
+        want[p] = bool(z and z2 and bl)
+    assert (kt.unpack_bits(bits, npacks) == want).all()
+    assert nsurv == int(want.sum()) and want[417]
+    # without blooms: zone maps only
+    bits2, n2 = ctx.prune(prog, mins.view(np.uint64), maxs.view(np.uint64))
+    assert n2 >= nsurv and kt.unpack_bits(bits2, npacks)[417]
+    prog.close()
+
+
+def test_agg_combine_matches_single_scan(ctx):
+    """fixed-order combine of per-shard partials (multi-GPU epilogue) == one scan over all packs"""
+    import ctypes as C
+    import knoxdb_b200 as kb
+    from knoxdb_b200.lib import AggOut
+    nrows = [50000, 50000, 50000, 50000]
+    packs, accts = make_table(RNG, 4, nrows)
+    blobs = put_table(ctx, packs, "bitpack")
+    prog = kb.Program(ctx, [kb.Leaf(F_AMT, kb.INT64, kb.GT, 0)])
+    aggs = [(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64)]
+    whole = ctx.scan(prog, [(p, 1) for p in range(4)], aggs=aggs)["aggs"]
+    halves = [ctx.scan(prog, [(p, 1) for p in r], aggs=aggs)["aggs"] for r in ((0, 1), (2, 3))]
+    for j, (f, t) in enumerate(aggs):
+        parts = (AggOut * 2)(halves[0][j], halves[1][j])
+        out = AggOut()
+        assert kb.lib().kx_agg_combine(t, parts, 2, C.byref(out)) == 0
+        assert out.count == whole[j].count and out.min_bits == whole[j].min_bits and out.max_bits == whole[j].max_bits
+        if t == kb.INT64:
+            assert out.sum_bits == whole[j].sum_bits
+        else:
+            a, b = np.uint64(out.sum_bits).view(np.float64), np.uint64(whole[j].sum_bits).view(np.float64)
+            assert abs(a - b) <= 1e-14 * abs(b)
+    for p in range(4):
+        for f in (F_TS, F_ACCT, F_AMT, F_FAMT):
+            ctx.block_drop(p, 1, f)
+    prog.close()
+
+
+def test_errors_are_loud(ctx):
+    import knoxdb_b200 as kb
+    prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.EQ, 5)])
+    with pytest.raises(kb.KnoxError):
+        ctx.scan(prog, [(999, 1)])                       # block not resident
+    with pytest.raises(kb.KnoxError):
+        ctx.block_put(0, 0, 0, kb.INT64, b"\x63\x00")    # unknown container id
+    with pytest.raises(kb.KnoxError):
+        kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.EQ, 5)], postfix=[0, kb.OP_AND])
+    prog.close()

@@ -1,0 +1,103 @@
+"""CPU tier: the product's HOST logic (knoxdb_b200/csrc/kx_host.cpp — container parsing,
+normalisation into device views, leaf → per-pack predicate translation) against the oracle.
+The device semantics are emulated by tests/harness/host_harness.cpp (test infrastructure);
+the CUDA kernels are covered by the -m gpu tests."""
+import numpy as np
+import pytest
+
+import kxtest as kt
+import oracle as ko
+
+RNG = np.random.default_rng(42)
+
+
+@pytest.mark.parametrize("t", kt.INT_TYPES)
+def test_leaf_translation_matches_oracle(t):
+    modes_seen = set()
+    for n in (1, 3, 64, 67, 640, 1025):
+        for name, vals in kt.shapes(RNG, t, n).items():
+            for kind in kt.container_kinds(t, vals):
+                blob = ko.store(kind, t, vals)
+                oc = ko.Container(t, blob)
+                # decode parity
+                out = np.zeros(n, dtype=np.uint64)
+                assert kt.harness().kxh_decode(t, np.frombuffer(blob, np.uint8).copy().ctypes.data, len(blob), out.ctypes.data, n) == n
+                assert (out == oc.decode()).all(), (name, kind)
+                for a in kt.operands(t, vals):
+                    b = min(np.iinfo(ko.NP[t]).max, a + 5)
+                    for op in kt.OPS:
+                        want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                        got, mode = kt.host_match(t, blob, n, op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                        modes_seen.add(mode)
+                        if not (got == want).all():
+                            # run-end blocks whose Values child is an affine container inherit the
+                            # reference's MatchBetween rounding quirk; the product
+                            # evaluates the scalar predicate on run values there
+                            if op == ko.RG and oc.ctype == ko.TRUNEND and oc.value_delta_sequences():
+                                truth = kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](b)))
+                                assert (got == truth).all(), (name, kind, op, a, b)
+                                continue
+                            raise AssertionError((ko.NP[t].__name__, n, name, kind, op, a, b, mode))
+                setv = np.unique(np.concatenate([vals[: min(3, n)], kt.typed_rand(RNG, t, 3)]))
+                su = ko.as_u64(t, setv)
+                for neg, op in ((False, ko.IN), (True, ko.NI)):
+                    got, _ = kt.host_match(t, blob, n, op, values=su)
+                    assert (got == oc.match_set(su, negate=neg)).all(), (name, kind, "set", neg)
+    assert len(modes_seen) >= 4
+
+
+def test_delta_quirk_is_reproduced():
+    """The reference's DeltaContainer.MatchBetween rounding below For is reproduced bit for bit."""
+    blob = ko.store("delta", ko.I64, base=100, delta=10, n=8)
+    got, _ = kt.host_match(ko.I64, blob, 8, ko.RG, 95, 135)
+    assert got.tolist() == ko.Container(ko.I64, blob).match(ko.RG, 95, 135).tolist() == [0b00001110]
+
+
+@pytest.mark.parametrize("w", [0, 1, 7, 8, 13, 20, 31, 32, 33, 47, 63, 64])
+def test_bitpack_range_translation_edges(w):
+    """operands at / beyond the field mask, inverted ranges, 32- vs 64-bit path selection"""
+    t = ko.U64
+    n = 333
+    vals = kt.rnd_bits(RNG, n, w)
+    vals[:2] = [0, (1 << w) - 1 if w < 64 else 2**64 - 1]
+    base = 1000 if w < 60 else 0
+    col = vals + np.uint64(base)
+    blob = ko.store("bitpack", t, col)
+    oc = ko.Container(t, blob)
+    top = (1 << w) - 1 if w < 64 else 2**64 - 1
+    cands = [0, 1, base, base + 1, base + top, min(base + top + 1, 2**64 - 1), 2**32 - 1, 2**32, 2**63, 2**64 - 1, int(col[5])]
+    for a in cands:
+        for op in kt.OPS:
+            for b in (a, min(a + 1000, 2**64 - 1), 2**64 - 1, 0):
+                want = oc.match(op, a, b)
+                got, _ = kt.host_match(t, blob, n, op, a, b)
+                assert (got == want).all(), (w, op, a, b)
+                if op != ko.RG:
+                    break
+
+
+def test_float_translation():
+    for t, dt in ((ko.F64, np.float64), (ko.F32, np.float32)):
+        vals = (RNG.integers(0, 2**30, 500) / 100.0).astype(dt)
+        vals[::31] = np.nan
+        vals[3] = np.inf
+        blob = ko.store("raw", t, vals)
+        oc = ko.Container(t, blob)
+        for a, b in ((vals[10], vals[10] * 2), (np.nan, 1.0), (-np.inf, np.inf)):
+            for op in kt.OPS:
+                ua, ub = ko.scalar_u64(t, dt(a)), ko.scalar_u64(t, dt(b))
+                got, _ = kt.host_match(t, blob, 500, op, ua, ub)
+                assert (got == oc.match(op, ua, ub)).all(), (t, op, a, b)
+
+
+def test_xxh3_host_matches_oracle_and_golden():
+    import json
+    import os
+    x = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "xxh3_vectors.json")))
+    for inp, r32, r64 in zip(x["input_bytes"], x["u32"], x["u64"]):
+        b = np.array(inp, dtype=np.uint8)
+        assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, 4) == r32
+        assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, 8) == r64
+    for n in list(range(0, 300, 7)) + [1023, 1024, 1025, 5000]:
+        b = RNG.integers(0, 256, max(n, 1), dtype=np.uint8)
+        assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, n) == ko.lib().ko_xxh3_bytes(b.ctypes.data, n), n
