@@ -67,6 +67,13 @@ class ClockSampler:
 
     def __init__(self, index):
         self.index, self.samples, self.proc = index, [], None
+        self.t0 = self.t1 = None
+
+    def mark_start(self):
+        self.t0 = time.time()
+
+    def mark_stop(self):
+        self.t1 = time.time()
 
     def start(self):
         try:
@@ -79,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -90,7 +97,10 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        for s in self.samples:
+        inwin = [s for (ts, s) in self.samples if self.t0 is None or (self.t0 <= ts <= (self.t1 or ts) + 0.15)]
+        if not inwin:   # timed region shorter than one sampling period: take the nearest samples
+            inwin = [s for (_, s) in self.samples[-3:]]
+        for s in inwin:
             p = [x.strip() for x in s.split(",")]
             if len(p) < 6:
                 continue
@@ -127,7 +137,7 @@ def cpu_baseline(payloads, threshold, nthreads, target_s, npacks_sample):
         total = L.ko_baseline_bitpack_scan(pp, nr, npacks_sample, W_BITS, ko.LT, threshold, 0, bp, nthreads)
         reps += 1
         dt = time.perf_counter() - t0
-        if dt >= target_s or reps >= 64:
+        if dt >= target_s or reps >= 4096:
             break
     rows = reps * npacks_sample * PACK_ROWS
     return rows / dt, dt, reps, int(total), bits
@@ -166,7 +176,7 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--packs", type=int, default=256, help="resident packs per GPU (4 Mi rows each)")
@@ -239,12 +249,13 @@ def main():
         res = ctx.scan(prog, packs, nrows=nrows, want_bitsets=True, bitset_buf=bitbuf)
         return ctx.last_scan_stats(), int(res["counts"].sum())
 
+    sampler = ClockSampler(local); sampler.start()
     for _ in range(args.warmup):
         step_resident()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local); sampler.start()
+    sampler.mark_start()
     t0 = time.perf_counter()
     kernel_ms = 0.0; total_ms = 0.0; launches = 0; matches = 0
     for _ in range(args.steps):
@@ -252,6 +263,7 @@ def main():
         kernel_ms += st["kernel_ms"]; total_ms += st["total_ms"]; launches += st["launches"]
     torch.cuda.synchronize()
     wall = time.perf_counter() - t0
+    sampler.mark_stop()
     if world > 1:
         dist.barrier()
         tmax = torch.tensor([wall, total_ms, kernel_ms], device="cuda", dtype=torch.float64)

@@ -311,17 +311,28 @@ void raw_interval(PackLeaf& o, int w, uint64_t lo, uint64_t hi, bool neg) {
     o.a = lo & wm; o.d = (hi - lo) & wm; o.wm = wm; o.neg = neg;
 }
 
-// ((field - a) <=u64 d) on a min-FOR field of width w, 64-bit arithmetic like bitpack/cmp.go
+// ((field - a) <=u64 d) on a min-FOR field of width w, evaluated by the reference in 64-bit
+// arithmetic (bitpack/cmp.go, cmp_bw.go).  Fields are < 2^w, so the match set is rewritten
+// as a w-bit MODULAR range ((field - a') mod 2^w) <= d' with a', d' < 2^w — the one form the
+// kernels evaluate (top-aligned 32-bit arithmetic for w <= 32):
+//   * a + d does not wrap 2^64 (every sane query): matches [a, a+d] ∩ [0, 2^w)
+//   * a + d wraps (inverted range a > b): matches [a, 2^w) ∪ [0, e], e = a + d - 2^64
 void packed_range(PackLeaf& o, int w, uint64_t a, uint64_t d, bool neg) {
-    if (w <= 32) {
-        if (d < 0xffffffff00000000ull) {            // no 64-bit wrap-around range
-            if (a > 0xffffffffull) { set_const(o, neg); return; }
-            uint64_t room = 0xffffffffull - a;
-            o.mode = LM_RANGE32; o.a = a; o.d = std::min(d, room); o.wm = 0xffffffffull; o.neg = neg;
-            return;
-        }
+    const uint64_t mask = width_mask(w);
+    uint64_t e = a + d;                       // mod 2^64
+    bool wraps = e < a;
+    if (!wraps) {
+        if (a > mask) { set_const(o, neg); return; }
+        d = std::min(d, mask - a);
+        if (a == 0 && d == mask) { set_const(o, !neg); return; }
+    } else {
+        if (a > mask) { a = 0; d = std::min(e, mask); }                 // only the low part [0, e]
+        else if (e >= mask || e + 1 >= a) { set_const(o, !neg); return; }  // the two parts cover the whole field
+        else d = (e - a) & mask;                                        // wrap-around range in w-bit arithmetic
+        if (a == 0 && d == mask) { set_const(o, !neg); return; }
     }
-    o.mode = LM_RANGE64; o.a = a; o.d = d; o.wm = ~0ull; o.neg = neg;
+    o.mode = w <= 32 ? LM_RANGE32 : LM_RANGE64;
+    o.a = a; o.d = d; o.wm = mask; o.neg = neg;
 }
 
 // leaf on a CK_BITS stream of integer type t

@@ -119,29 +119,75 @@ __device__ __forceinline__ bool set_has(const uint64_t* __restrict__ s, uint32_t
 
 // ------------------------------------------------------------------------------ leaf kernels
 // Every function evaluates one leaf for the warp's chunk of 32*R rows and returns the chunk's
-// bitset in "word per lane" form: lane j (< R) holds the ballot word of rows [32j, 32j+32).
-// Lane l handles rows l, l+32, l+64 … so its bit offset advances by exactly w 32-bit words per
-// iteration and its shift stays constant.
+// bitset in "word per lane" form: lane j (< R) holds the bitset word of rows [32j, 32j+32) of
+// the chunk.
 
-template <bool MASKED>
-__device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
-                                                 uint32_t a, uint32_t d, uint32_t wm) {
-    uint32_t bit = (row0 + lane) * w;
-    uint32_t idx = bit >> 5, sh = bit & 31u;
-    uint32_t fm = (uint32_t)width_mask((int)w);
+// ---- fast path, width W <= 32 (compile time): each lane owns 32 CONSECUTIVE rows = exactly W
+// 32-bit words of the stream.  After full unrolling every field position is a constant, so a
+// row costs one shift that brings the field to the TOP of a register (low garbage bits are
+// harmless for the compare), an optional subtract, one compare and one predicated OR — no
+// ballot, no mask, and the W words arrive with 128/64/32-bit shared-memory loads.
+// The compare ((f - a) mod 2^W) <= d becomes (t - (a << K)) <= ((d << K) | (2^K - 1)), K = 32 - W.
+template <int W, bool SUB>
+__device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t a_top, uint32_t lim) {
+    uint32_t x[W + 1];
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            uint4 v = reinterpret_cast<const uint4*>(seg)[i];
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 2; ++i) {
+            uint2 v = reinterpret_cast<const uint2*>(seg)[i];
+            x[2 * i] = v.x; x[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) x[i] = seg[i];
+    }
+    x[W] = 0;
     uint32_t word = 0;
-#pragma unroll 8
-    for (uint32_t it = 0; it < R; ++it) {
-        uint32_t f = __funnelshift_r(sw[idx], sw[idx + 1], sh) & fm;
-        uint32_t x = f - a;
-        if (MASKED) x &= wm;
-        uint32_t b = __ballot_sync(0xffffffffu, x <= d);
-        if (lane == it) word = b;
-        idx += w;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int bit = j * W, wi = bit >> 5, sh = bit & 31;
+        uint32_t t;
+        if (sh + W <= 32) t = x[wi] << (32 - sh - W);
+        else t = __funnelshift_l(x[wi], x[wi + 1], 64 - sh - W);
+        if (SUB) t -= a_top;
+        if (t <= lim) word |= (1u << j);
     }
     return word;
 }
 
+template <bool SUB>
+__device__ __noinline__ uint32_t leaf_b32_dispatch(const uint32_t* __restrict__ sw, uint32_t group, uint32_t w, uint32_t a_top, uint32_t lim) {
+    const uint32_t* seg = sw + group * w;
+    switch (w) {
+#define KX_CASE(W) case W: return leaf_b32<W, SUB>(seg, a_top, lim);
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+        KX_CASE(17) KX_CASE(18) KX_CASE(19) KX_CASE(20) KX_CASE(21) KX_CASE(22) KX_CASE(23) KX_CASE(24)
+        KX_CASE(25) KX_CASE(26) KX_CASE(27) KX_CASE(28) KX_CASE(29) KX_CASE(30) KX_CASE(31) KX_CASE(32)
+#undef KX_CASE
+    }
+    return 0;
+}
+
+// one LM_RANGE32 leaf for the warp chunk; lanes >= R own no rows
+__device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
+                                                 uint32_t a, uint32_t d) {
+    if (lane >= R) return 0;
+    const uint32_t k = 32u - w;
+    const uint32_t a_top = a << k, lim = (d << k) | ((1u << k) - 1u);   // k == 0: a, d
+    const uint32_t group = (row0 >> 5) + lane;
+    return a ? leaf_b32_dispatch<true>(sw, group, w, a_top, lim) : leaf_b32_dispatch<false>(sw, group, w, 0u, lim);
+}
+
+// ---- general path (33..64-bit fields): lane l handles rows l, l+32, l+64 … so its bit offset
+// advances by exactly w 32-bit words per iteration and its shift stays constant; bitset words
+// are built with __ballot_sync.
 __device__ __forceinline__ uint32_t leaf_range64(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
                                                  uint64_t a, uint64_t d, uint64_t wm) {
     uint32_t bit = (row0 + lane) * w;
@@ -275,6 +321,18 @@ __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) 
 }
 
 // ------------------------------------------------------------------------------ the kernel
+// first pack whose tile range contains tile t (packs with zero tiles are skipped)
+__device__ __forceinline__ uint32_t pack_of_tile(const PackInfo* __restrict__ packs, uint32_t npacks, uint32_t t) {
+    uint32_t lo = 0, hi = npacks;   // last pack with tile0 <= t
+    while (hi - lo > 1) {
+        uint32_t m = (lo + hi) >> 1;
+        if (packs[m].tile0 <= t) lo = m; else hi = m;
+    }
+    return lo;
+}
+
+// SIMPLE = one leaf, no aggregates: the hot configuration (fused decode + compare + popcount)
+template <bool SIMPLE>
 __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
@@ -292,21 +350,31 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
     }
     __syncthreads();
 
-    auto tile_to_pack = [&](uint32_t t, uint32_t& pack, uint32_t& chunk) {
-        if (P.tile_pack) { pack = P.tile_pack[t]; chunk = t - P.packs[pack].tile0; }
-        else { pack = t / P.tiles_per_pack; chunk = t - pack * P.tiles_per_pack; }
+    // contiguous tile range of this CTA: consecutive tiles stay inside one pack (descriptor reuse,
+    // sequential DRAM pages) and the split is static, so results are reproducible run to run
+    const uint32_t t_begin = (uint32_t)(((uint64_t)blockIdx.x * P.ntiles) / gridDim.x);
+    const uint32_t t_end = (uint32_t)(((uint64_t)(blockIdx.x + 1) * P.ntiles) / gridDim.x);
+    if (t_begin >= t_end) return;
+
+    uint32_t pack = pack_of_tile(P.packs, P.npacks, t_begin);
+    PackInfo pi = P.packs[pack];
+    uint32_t pack_tiles = (pi.n + tile_rows - 1) / tile_rows;
+    uint32_t chunk = t_begin - pi.tile0;
+    auto next_tile = [&]() {   // advance (pack, chunk) to the following tile
+        if (++chunk >= pack_tiles) {
+            do { ++pack; pi = P.packs[pack]; } while (pi.n == 0);
+            pack_tiles = (pi.n + tile_rows - 1) / tile_rows;
+            chunk = 0;
+        }
     };
 
     if (warp == CONSUMER_WARPS) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
             uint32_t k = 0;
-            for (uint32_t t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++k) {
+            for (uint32_t t = t_begin; t < t_end; ++t, ++k) {
                 uint32_t s = k % STAGES, ph = (k / STAGES) & 1u;
                 mbar_wait(&empty_bar[s], ph ^ 1u);          // slot released by all consumer warps
-                uint32_t pack, chunk;
-                tile_to_pack(t, pack, chunk);
-                const PackInfo pi = P.packs[pack];
                 uint32_t rows = min(tile_rows, pi.n - chunk * tile_rows);
                 const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
                 uint32_t total = 0;
@@ -322,153 +390,166 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
                     tma_load_1d(dst, src, bytes, &full_bar[s]);
                     dst += (tile_rows / 8u) * w + 16u;      // slot = full-tile bytes + over-read pad
                 }
+                if (t + 1 < t_end) next_tile();
             }
         }
-    } else {
-        // ===================== consumers: unpack + filter + reduce =====================
-        AggAcc acc[MAX_AGGS];
+        return;
+    }
+
+    // ===================== consumers: unpack + filter + reduce =====================
+    AggAcc acc[SIMPLE ? 1 : MAX_AGGS];
 #pragma unroll
-        for (int j = 0; j < MAX_AGGS; ++j) { acc[j] = AggAcc{}; }
-        unsigned long long nmatch = 0;   // rows this thread reduced
+    for (int j = 0; j < (SIMPLE ? 1 : MAX_AGGS); ++j) acc[j] = AggAcc{};
+    unsigned long long nmatch = 0;   // rows this thread reduced
+    uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
+    const uint32_t row0 = warp * R * 32u;   // first row of the warp chunk within a tile
 
-        uint32_t k = 0;
-        for (uint32_t t = blockIdx.x; t < P.ntiles; t += gridDim.x, ++k) {
-            uint32_t s = k % STAGES, ph = (k / STAGES) & 1u;
-            uint32_t pack, chunk;
-            tile_to_pack(t, pack, chunk);
-            const PackInfo pi = P.packs[pack];
-            const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
-            const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
-            const uint32_t row0 = warp * R * 32u;                  // first row of the warp chunk within the tile
+    auto flush_count = [&](uint32_t pk) {
+        uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
+        if (P.counts && lane == 0 && c) atomicAdd(P.counts + pk, (unsigned long long)c);
+        lane_cnt = 0;
+    };
 
-            mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
+    uint32_t k = 0;
+    for (uint32_t t = t_begin; t < t_end; ++t, ++k) {
+        const uint32_t s = k % STAGES, ph = (k / STAGES) & 1u;
+        const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
+        const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
+        const uint8_t* stage = stage_base + (size_t)s * P.stage_bytes;
 
-            // ---- evaluate the leaves and the AND/OR program on word-per-lane bitsets
-            uint32_t stack[MAX_LEAVES];
-            int sp = 0;
-            uint32_t leaf_off[MAX_LEAVES];
-            {
-                uint32_t off = 0;
-                for (uint32_t l = 0; l < P.nleaves; ++l) {
-                    leaf_off[l] = off;
-                    if (L[l].data) off += (tile_rows / 8u) * L[l].width + 16u;
+        mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
+
+        auto eval_leaf = [&](const PackLeaf& lf, const uint32_t* sw) -> uint32_t {
+            uint32_t word;
+            switch (lf.mode) {
+            case LM_NONE: word = 0; break;
+            case LM_ALL: word = 0xffffffffu; break;
+            case LM_RANGE32: word = leaf_range32(sw, lf.width, row0, R, lane, (uint32_t)lf.a, (uint32_t)lf.d); break;
+            case LM_RANGE64: word = leaf_range64(sw, lf.width, row0, R, lane, lf.a, lf.d, lf.wm); break;
+            case LM_FLOAT: word = leaf_float(sw, lf.width, row0, R, lane, lf.fop, lf.a, lf.d); break;
+            case LM_ROWRANGE: {
+                // rows [a, a+d] of the pack → bits of this lane's word
+                uint64_t r = (uint64_t)pack_row0 + row0 + lane * 32u;     // first row of the word
+                uint64_t lo = lf.a, hi = lf.a + lf.d;
+                word = 0;
+                if (hi >= r && lo < r + 32u) {
+                    uint32_t b0 = lo > r ? (uint32_t)(lo - r) : 0u;
+                    uint32_t b1 = hi < r + 31u ? (uint32_t)(hi - r) : 31u;
+                    word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
                 }
+                break;
             }
-            const uint8_t* stage = stage_base + (size_t)s * P.stage_bytes;
+            default:
+                word = leaf_generic(lf, P.views[lf.view], lf.data ? sw : nullptr, pack_row0, row0, R, lane, pi.n, P.set_vals);
+                break;
+            }
+            return lf.neg ? ~word : word;
+        };
+
+        uint32_t word;
+        if (SIMPLE) {
+            word = eval_leaf(L[0], reinterpret_cast<const uint32_t*>(stage));
+        } else {
+            // evaluate the leaves and the AND/OR program on word-per-lane bitsets
+            uint32_t stack[MAX_LEAVES];
+            uint32_t leaf_off[MAX_LEAVES];
+            int sp = 0;
+            uint32_t off = 0;
+            for (uint32_t l = 0; l < P.nleaves; ++l) {
+                leaf_off[l] = off;
+                if (L[l].data) off += (tile_rows / 8u) * L[l].width + 16u;
+            }
             for (uint32_t i = 0; i < P.npost; ++i) {
                 uint32_t op = P.postfix[i];
                 if (op < 0x80u) {
-                    const PackLeaf& lf = L[op];
-                    const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage + leaf_off[op]);
-                    uint32_t word;
-                    switch (lf.mode) {
-                    case LM_NONE: word = 0; break;
-                    case LM_ALL: word = 0xffffffffu; break;
-                    case LM_RANGE32:
-                        word = (uint32_t)lf.wm == 0xffffffffu
-                                   ? leaf_range32<false>(sw, lf.width, row0, R, lane, (uint32_t)lf.a, (uint32_t)lf.d, 0xffffffffu)
-                                   : leaf_range32<true>(sw, lf.width, row0, R, lane, (uint32_t)lf.a, (uint32_t)lf.d, (uint32_t)lf.wm);
-                        break;
-                    case LM_RANGE64: word = leaf_range64(sw, lf.width, row0, R, lane, lf.a, lf.d, lf.wm); break;
-                    case LM_FLOAT: word = leaf_float(sw, lf.width, row0, R, lane, lf.fop, lf.a, lf.d); break;
-                    case LM_ROWRANGE: {
-                        // rows [a, a+d] of the pack → bits of this lane's word
-                        uint64_t r = (uint64_t)pack_row0 + row0 + lane * 32u;     // first row of the word
-                        uint64_t lo = lf.a, hi = lf.a + lf.d;
-                        word = 0;
-                        if (hi >= r && lo < r + 32u) {
-                            uint32_t b0 = lo > r ? (uint32_t)(lo - r) : 0u;
-                            uint32_t b1 = hi < r + 31u ? (uint32_t)(hi - r) : 31u;
-                            word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
-                        }
-                        break;
-                    }
-                    default:
-                        word = leaf_generic(lf, P.views[lf.view], lf.data ? sw : nullptr, pack_row0, row0, R, lane, pi.n, P.set_vals);
-                        break;
-                    }
-                    if (lf.neg) word = ~word;
-                    stack[sp++] = word;
+                    stack[sp++] = eval_leaf(L[op], reinterpret_cast<const uint32_t*>(stage + leaf_off[op]));
                 } else {
                     uint32_t y = stack[--sp];
                     stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
                 }
             }
-            uint32_t word = stack[0];
+            word = stack[0];
+        }
 
-            // ---- mask rows past the end of the pack (tail bits must be zero) and lanes >= R
-            {
-                uint64_t wr = (uint64_t)pack_row0 + row0 + lane * 32u;
-                uint32_t valid = 0;
-                if (lane < R && wr < pi.n) {
-                    uint32_t left = pi.n - (uint32_t)wr;
-                    valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
-                }
-                word &= valid;
+        // all shared-memory reads of this stage are done: hand the slot back to the producer early
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+
+        // mask rows past the end of the pack (tail bits must be zero) and lanes >= R
+        const uint64_t wr = (uint64_t)pack_row0 + row0 + lane * 32u;   // first row of this lane's word
+        {
+            uint32_t valid = 0;
+            if (lane < R && wr < pi.n) {
+                uint32_t left = pi.n - (uint32_t)wr;
+                valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
             }
+            word &= valid;
+        }
 
-            // ---- outputs: bitset words (coalesced), per-pack match count
-            if (P.bitsets && lane < R) {
-                uint64_t wr = (uint64_t)pack_row0 + row0 + lane * 32u;
-                if (wr < pi.n) *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
-            }
-            uint32_t cnt = __reduce_add_sync(0xffffffffu, __popc(word));
-            if (P.counts && lane == 0 && cnt) atomicAdd(P.counts + pack, (unsigned long long)cnt);
+        // outputs: bitset words (coalesced 128 B per warp), per-pack match count
+        if (P.bitsets && lane < R && wr < pi.n)
+            *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
+        lane_cnt += __popc(word);
 
-            // ---- fused reduce over the matching rows of the value columns (read on demand)
-            if (P.naggs && cnt) {
-                for (uint32_t it = 0; it < R; ++it) {
-                    uint32_t wd = __shfl_sync(0xffffffffu, word, it);
-                    if (wd == 0) continue;
-                    if ((wd >> lane) & 1u) {
-                        uint32_t row = pack_row0 + row0 + it * 32u + lane;
+        // fused reduce over the matching rows of the value columns (read on demand)
+        if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
+            for (uint32_t it = 0; it < R; ++it) {
+                uint32_t wd = __shfl_sync(0xffffffffu, word, it);
+                if (wd == 0) continue;
+                if ((wd >> lane) & 1u) {
+                    uint32_t row = pack_row0 + row0 + it * 32u + lane;
 #pragma unroll
-                        for (int j = 0; j < MAX_AGGS; ++j) {
-                            if (j < (int)P.naggs) {
-                                const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
-                                agg_add(acc[j], P.agg_type[j], decode_value(v, row, nullptr, 0), nmatch == 0);
-                            }
+                    for (int j = 0; j < MAX_AGGS; ++j) {
+                        if (j < (int)P.naggs) {
+                            const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                            agg_add(acc[SIMPLE ? 0 : j], P.agg_type[j], decode_value(v, row, nullptr, 0), nmatch == 0);
                         }
-                        ++nmatch;
                     }
+                    ++nmatch;
                 }
             }
-
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty_bar[s]);             // release the stage to the producer
         }
 
-        // ---- per-CTA partial aggregates: fixed-order tree inside the warp, then across warps
-        for (uint32_t j = 0; j < P.naggs; ++j) {
-            const int type = P.agg_type[j];
-            AggAcc a = acc[j];
-            unsigned long long c = nmatch;
-            for (int off = 16; off > 0; off >>= 1) {
-                AggAcc b;
+        if (t + 1 < t_end) {
+            const uint32_t prev = pack;
+            next_tile();
+            if (pack != prev) flush_count(prev);
+        }
+    }
+    flush_count(pack);
+
+    if (SIMPLE) return;
+
+    // ---- per-CTA partial aggregates: fixed-order tree inside the warp, then across warps
+    for (uint32_t j = 0; j < P.naggs; ++j) {
+        const int type = P.agg_type[j];
+        AggAcc a = acc[SIMPLE ? 0 : j];
+        unsigned long long c = nmatch;
+        for (int off = 16; off > 0; off >>= 1) {
+            AggAcc b;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) b.s[q] = __shfl_down_sync(0xffffffffu, a.s[q], off);
-                unsigned long long cb = __shfl_down_sync(0xffffffffu, c, off);
-                if (cb) { if (c) agg_merge(a, b, type); else a = b; }
-                c += cb;
-            }
-            if (lane == 0) { warp_acc[warp] = a; warp_cnt[warp] = c; }
-            // consumer-only barrier (the producer warp does not take part)
-            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
-            if (threadIdx.x == 0) {
-                AggAcc r = warp_acc[0];
-                unsigned long long rc = warp_cnt[0];
-                for (int q = 1; q < CONSUMER_WARPS; ++q) {
-                    if (warp_cnt[q]) { if (rc) agg_merge(r, warp_acc[q], type); else r = warp_acc[q]; }
-                    rc += warp_cnt[q];
-                }
-                AggPartial o;
-                o.count = rc; o.valid = rc != 0; o.pad = 0;
-                if (type == 9) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
-                else { o.sum = r.s[0]; o.err = 0.0; o.mn = r.s[1]; o.mx = r.s[2]; }
-                P.partials[(size_t)blockIdx.x * P.naggs + j] = o;
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+            for (int q = 0; q < 4; ++q) b.s[q] = __shfl_down_sync(0xffffffffu, a.s[q], off);
+            unsigned long long cb = __shfl_down_sync(0xffffffffu, c, off);
+            if (cb) { if (c) agg_merge(a, b, type); else a = b; }
+            c += cb;
         }
+        if (lane == 0) { warp_acc[warp] = a; warp_cnt[warp] = c; }
+        // consumer-only barrier (the producer warp has exited)
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+        if (threadIdx.x == 0) {
+            AggAcc r = warp_acc[0];
+            unsigned long long rc = warp_cnt[0];
+            for (int q = 1; q < CONSUMER_WARPS; ++q) {
+                if (warp_cnt[q]) { if (rc) agg_merge(r, warp_acc[q], type); else r = warp_acc[q]; }
+                rc += warp_cnt[q];
+            }
+            AggPartial o;
+            o.count = rc; o.valid = rc != 0; o.pad = 0;
+            if (type == 9) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
+            else { o.sum = r.s[0]; o.err = 0.0; o.mn = r.s[1]; o.mx = r.s[2]; }
+            P.partials[(size_t)blockIdx.x * P.naggs + j] = o;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
     }
 }
 
@@ -711,9 +792,13 @@ __global__ void prune_kernel(PruneParams P) {
 static int grid_for(uint64_t items, uint64_t cap) { uint64_t g = (items + 255) / 256; return (int)(g < cap ? g : cap); }
 
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream) {
-    cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    const bool simple = P.nleaves == 1 && P.naggs == 0;
+    auto kern = simple ? scan_kernel<true> : scan_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) return e;
-    scan_kernel<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
+    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
     return cudaGetLastError();
 }
 

@@ -30,11 +30,13 @@ def test_library_is_sm100a_native():
     import subprocess
     out = subprocess.run(["cuobjdump", "--list-elf", kb.library_path()], capture_output=True, text=True).stdout
     assert "sm_100a" in out
-    sass = subprocess.run(["cuobjdump", "-sass", "-fun", "_ZN2kx11scan_kernelENS_10ScanParamsE", kb.library_path()],
-                          capture_output=True, text=True).stdout
+    sass = subprocess.run(["cuobjdump", "-sass", kb.library_path()], capture_output=True, text=True).stdout
+    i = sass.index("scan_kernelILb1E")          # the single-leaf fused decode+compare+popcount kernel
+    sass = sass[i: sass.index("Function :", i + 10)]
     assert "UBLKCP" in sass          # TMA bulk copy (cp.async.bulk) in the scan kernel
     assert "SYNCS" in sass           # mbarrier arrive / try_wait
-    assert "VOTE" in sass            # ballot-built bitset words
+    assert "LDS.128" in sass         # vectorised shared-memory reads of the packed stream
+    assert "POPC" in sass            # fused popcount
 
 
 def test_no_cpu_fallback_without_device():
