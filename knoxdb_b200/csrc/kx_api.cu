@@ -101,8 +101,8 @@ struct kx_ctx {
     size_t store_enc_bytes = 0, store_dev_bytes = 0;
 
     // scratch (grow only)
-    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc;
-    PinBuf h_desc, h_res;
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage;
+    PinBuf h_desc, h_res, h_aux;
 
     double last_kernel_ms = 0, last_total_ms = 0;
     int last_launches = 0;
@@ -161,7 +161,7 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
         sb.allocs.push_back({si, len + STREAM_PAD});
         ctx->store_dev_bytes += round_up(len + STREAM_PAD, 256);
         if (len) CK(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemsetAsync(d + len, 0, STREAM_PAD, ctx->stream));
+        // the pad only has to be addressable: rows past the end are masked, over-read bits are cut by the field mask
         *devp = d;
         return KX_OK;
     };
@@ -628,29 +628,72 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             bytes += b; ++p1;
         }
         const int nb = p1 - p0;
-        std::vector<StoredBlock> tmp(size_t(nb) * nfields);
-        auto cleanup = [&]() { cudaStreamSynchronize(ctx->stream); for (auto& sb : tmp) free_block(ctx, sb); };
+        // pass 1: parse headers, lay the batch out in the staging arena (256 B aligned streams)
+        std::vector<BlockLayout> lays(size_t(nb) * nfields);
+        std::vector<size_t> off_stream(lays.size(), 0), off_a64(lays.size(), 0), off_a32(lays.size(), 0), aux_src(lays.size(), 0);
+        size_t dev_bytes = 0, aux_bytes = 0;
         for (int p = 0; p < nb; ++p) {
             for (int f = 0; f < nfields; ++f) {
-                size_t bi = size_t(p0 + p) * nfields + f;
-                BlockLayout lay; std::string err;
-                rc = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lay, err);
-                if (rc) { cleanup(); return fail(ctx, rc, "kx_scan_host: " + err); }
-                rc = upload_block(ctx, lay, tmp[size_t(p) * nfields + f]);
-                if (rc) { cleanup(); return rc; }
+                size_t bi = size_t(p0 + p) * nfields + f, li = size_t(p) * nfields + f;
+                std::string err;
+                rc = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lays[li], err);
+                if (rc) return fail(ctx, rc, "kx_scan_host: " + err);
+                BlockLayout& lay = lays[li];
+                if (lay.owned.empty() && lay.stream_len) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.stream_len + STREAM_PAD, 256); }
+                aux_src[li] = aux_bytes;
+                aux_bytes += round_up(lay.owned.size(), 16) + round_up(lay.aux64.size() * 8, 16) + round_up(lay.aux32.size() * 4, 16);
             }
         }
+        // host-built arrays (dictionaries, run values/ends, transcoded streams) go through one pinned buffer
+        const size_t aux_dev0 = dev_bytes;
+        for (size_t li = 0; li < lays.size(); ++li) {
+            BlockLayout& lay = lays[li];
+            if (!lay.owned.empty()) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.owned.size() + STREAM_PAD, 256); }
+            if (!lay.aux64.empty()) { off_a64[li] = dev_bytes; dev_bytes += round_up(lay.aux64.size() * 8 + STREAM_PAD, 256); }
+            if (!lay.aux32.empty()) { off_a32[li] = dev_bytes; dev_bytes += round_up(lay.aux32.size() * 4 + STREAM_PAD, 256); }
+        }
+        (void)aux_dev0;
+        CK(ctx->d_stage.reserve(dev_bytes + 256));
+        CK(ctx->h_aux.reserve(aux_bytes + 64));
+        uint8_t* dbase = static_cast<uint8_t*>(ctx->d_stage.p);
+        uint8_t* hbase = static_cast<uint8_t*>(ctx->h_aux.p);
+        // pass 2: queue the copies (asynchronous when the caller's blocks are pinned)
+        for (size_t li = 0; li < lays.size(); ++li) {
+            BlockLayout& lay = lays[li];
+            ColView& v = lay.view;
+            uint8_t* hp = hbase + aux_src[li];
+            if (lay.owned.empty()) {
+                if (lay.stream_len) CK(cudaMemcpyAsync(dbase + off_stream[li], lay.stream, lay.stream_len, cudaMemcpyHostToDevice, ctx->stream));
+            } else {
+                std::memcpy(hp, lay.owned.data(), lay.owned.size());
+                CK(cudaMemcpyAsync(dbase + off_stream[li], hp, lay.owned.size(), cudaMemcpyHostToDevice, ctx->stream));
+                hp += round_up(lay.owned.size(), 16);
+            }
+            if (!lay.aux64.empty()) {
+                std::memcpy(hp, lay.aux64.data(), lay.aux64.size() * 8);
+                CK(cudaMemcpyAsync(dbase + off_a64[li], hp, lay.aux64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+                hp += round_up(lay.aux64.size() * 8, 16);
+            }
+            if (!lay.aux32.empty()) {
+                std::memcpy(hp, lay.aux32.data(), lay.aux32.size() * 4);
+                CK(cudaMemcpyAsync(dbase + off_a32[li], hp, lay.aux32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+            }
+            if (v.kind == CK_BITS || v.kind == CK_DICT) v.data = dbase + off_stream[li];
+            if (v.kind == CK_DICT) v.aux = dbase + off_a64[li];
+            if (v.kind == CK_RUNEND) { v.data = dbase + off_a64[li]; v.aux = dbase + off_a32[li]; }
+        }
+        auto cleanup = [&]() {};
         ScanJob job; job.npacks = nb;
         job.nrows.resize(size_t(nb)); job.leaf_views.resize(size_t(nb) * nleaves); job.leaf_dicts.resize(size_t(nb) * nleaves);
         job.agg_views.resize(size_t(nb) * size_t(naggs));
         for (int p = 0; p < nb; ++p) {
-            job.nrows[size_t(p)] = tmp[size_t(p) * nfields].view.n;
+            job.nrows[size_t(p)] = lays[size_t(p) * nfields].view.n;
             for (int l = 0; l < nleaves; ++l) {
-                const StoredBlock& sb = tmp[size_t(p) * nfields + leaf_fi[size_t(l)]];
-                job.leaf_views[size_t(p) * nleaves + l] = sb.view;
-                job.leaf_dicts[size_t(p) * nleaves + l] = sb.dict.empty() ? nullptr : sb.dict.data();
+                const BlockLayout& lay = lays[size_t(p) * nfields + leaf_fi[size_t(l)]];
+                job.leaf_views[size_t(p) * nleaves + l] = lay.view;
+                job.leaf_dicts[size_t(p) * nleaves + l] = (lay.view.kind == CK_DICT && !lay.aux64.empty()) ? lay.aux64.data() : nullptr;
             }
-            for (int j = 0; j < naggs; ++j) job.agg_views[size_t(p) * naggs + j] = tmp[size_t(p) * nfields + agg_fi[size_t(j)]].view;
+            for (int j = 0; j < naggs; ++j) job.agg_views[size_t(p) * naggs + j] = lays[size_t(p) * nfields + agg_fi[size_t(j)]].view;
         }
         // bitset offsets of this batch are relative to the caller's buffer start; shift so the
         // device buffer only spans the batch
