@@ -230,17 +230,19 @@ def main():
     truth = np.packbits((fields < np.uint64(thr_field)).astype(np.uint8), bitorder="little")
     assert (r["bitsets"][0][: sample_rows // 8] == truth[: sample_rows // 8]).all(), "GPU scan disagrees with numpy truth"
 
-    part = torch.zeros(8, dtype=torch.int64, device="cuda")
-    gathered = torch.zeros(8 * world, dtype=torch.int64, device="cuda") if world > 1 else None
+    from knoxdb_b200 import shard
+    from knoxdb_b200.lib import AggOut
+    dev = torch.device("cuda", local)
 
     def step_resident():
         res = ctx.scan(prog, packs, nrows=nrows, want_bitsets=False)     # counts only: bitsets stay in HBM
         st = ctx.last_scan_stats()
         total = int(res["counts"].sum())
-        if world > 1:                                                    # ONE small NCCL collective per query
-            part[0] = total; part[1] = len(packs) * PACK_ROWS
-            dist.all_gather_into_tensor(gathered, part)
-            total = int(gathered.view(world, 8)[:, 0].sum().item())
+        if world > 1:
+            # ONE small NCCL collective per query: all-gather of the 64 B per-rank partial, combined in
+            # rank order through kx_agg_combine (the same path sum/min/max partials take)
+            mine = AggOut(); mine.count = total; mine.sum_bits = total; mine.min_bits = total; mine.max_bits = total; mine.valid = 1
+            total = int(shard.allgather_partials([mine], [kb.UINT64], dist, dev)[0].sum_bits)
         return st, total
 
     # the headline kernel writes bitsets too; kx_scan(bitsets=…) would also copy them to the host, so
