@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -84,7 +85,11 @@ struct kx_prog {
     std::vector<uint8_t> postfix;
     std::vector<uint64_t> sets;          // concatenated sorted sets
     uint32_t set_off[MAX_LEAVES + 1] = {0};
-    uint64_t* dev_sets = nullptr;
+    uint64_t* dev_sets = nullptr;        // sets, then the hash tables (one allocation)
+    std::vector<uint64_t> tabs;          // concatenated bucketised hash tables of the IN/NIN leaves
+    uint32_t tab_off[MAX_LEAVES] = {0};
+    uint8_t tab_log2[MAX_LEAVES] = {0};
+    const uint64_t* dev_tabs = nullptr;
 };
 
 struct kx_ctx {
@@ -101,7 +106,7 @@ struct kx_ctx {
     size_t store_enc_bytes = 0, store_dev_bytes = 0;
 
     // scratch (grow only)
-    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage;
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_codebits;
     PinBuf h_desc, h_res, h_aux;
 
     double last_kernel_ms = 0, last_total_ms = 0;
@@ -222,9 +227,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     size_t off_leaves = round_up(sz_packs, 256), off_views = off_leaves + round_up(sz_leaves, 256);
     size_t off_tiles = off_views + round_up(sz_views, 256);
 
-    // tile geometry: widest staged bits/row over all packs decides R (rows per tile = 256 R)
+    // translate every leaf for every pack; the widest staged bits/row over all packs decides the tile
     std::vector<PackLeaf> pl(size_t(npacks) * size_t(nleaves));
-    uint32_t max_stage_bits = 0;
+    std::vector<CodesetJob> cjobs;
+    uint32_t max_stage_bits = 0, code_words = 0;
+    bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
+    uint64_t total_rows = 0;
     bool uniform = true;
     for (int p = 0; p < npacks; ++p) {
         uint32_t bits = 0;
@@ -233,19 +241,52 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             if (v.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
             PackLeaf& o = pl[size_t(p) * nleaves + l];
             compile_leaf(v, job.leaf_dicts[size_t(p) * nleaves + l], prog->leaves[size_t(l)], uint32_t(size_t(p) * nleaves + l), o);
+            if (o.mode == LM_CODESET) {   // dictionary-set translation runs on the device, one job per (pack, leaf)
+                const LeafSpec& ls = prog->leaves[size_t(l)];
+                cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0});
+                o.a = code_words;
+                code_words += (v.naux + 31u) / 32u;
+            }
             bits += uint32_t(leaf_stage_width(o));
+            if (o.mode != LM_RANGE32 && o.mode != LM_NONE && o.mode != LM_ALL) only32 = false;
         }
         for (int j = 0; j < naggs; ++j)
             if (job.agg_views[size_t(p) * naggs + j].n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "value block length differs from pack");
         max_stage_bits = std::max(max_stage_bits, bits);
+        total_rows += job.nrows[size_t(p)];
         if (job.nrows[size_t(p)] != job.nrows[0]) uniform = false;
     }
+
+    // ---- tile geometry.  A tile is 256 R rows (R 32-row groups per consumer warp); the lane-owns-a-group
+    // paths want R >= 32 so that every lane has work.  Measured on B200 (profiles/r1_tune_geometry.txt): big
+    // tiles in a 2-deep ring beat small tiles in a deep ring (per-tile barrier/dispatch cost, larger TMA
+    // copies), narrow ALU-bound columns like 3 CTAs per SM, wide ones 2 (or 1 when 8192 rows need > 50 KB).
+    struct Geo { int ctas, stages; size_t budget; };
+    const bool simple32 = only32 && nleaves == 1 && naggs == 0;
+    const size_t stage_fixed = 16u * size_t(nleaves) + 16;
+    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
+    auto rmax_for = [&](const Geo& g) { return (g.budget - stage_fixed - 128) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)); };
+    const Geo g3{3, 2, 33 * 1024}, g2{2, 2, 50 * 1024}, g1{1, 2, 99 * 1024};
+    Geo geo = g2;
     uint32_t R = 32;
-    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + 16u * size_t(nleaves) + 16, 128); };
-    while (R > 1 && stage_bytes_for(R) > 24 * 1024) R >>= 1;
+    if (max_stage_bits) {
+        if (simple32 && max_stage_bits <= 16) geo = g3;
+        size_t rmax = rmax_for(geo);
+        if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
+        R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
+    }
+    if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
+        int c = 0, st = 0, r = 0;
+        if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 && (r <= 32 || r % 32 == 0) &&
+            128 + size_t(st) * stage_bytes_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
+            geo.ctas = c; geo.stages = st; R = uint32_t(r);
+        }
+    }
+    // small scans: prefer more, smaller tiles so that every CTA of the persistent grid gets work
+    while (R > 32 && total_rows / (uint64_t(256) * R) < uint64_t(4) * ctx->num_sms * geo.ctas) R -= 32;
     const uint32_t tile_rows = 256 * R;
     const size_t stage_bytes = stage_bytes_for(R);
-    const size_t smem_bytes = 128 + STAGES * stage_bytes;
+    const size_t smem_bytes = 128 + size_t(geo.stages) * stage_bytes;
 
     uint64_t ntiles64 = 0;
     std::vector<uint32_t> tile0(size_t(npacks) + 1);
@@ -256,7 +297,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (ntiles64 > 0xfffffff0ull) return fail(ctx, KX_EINVAL, "too many tiles in one scan call");
     const uint32_t ntiles = uint32_t(ntiles64);
     size_t sz_tiles = uniform ? 0 : sizeof(uint32_t) * size_t(ntiles);
-    size_t desc_bytes = off_tiles + round_up(sz_tiles, 256);
+    size_t off_cjobs = off_tiles + round_up(sz_tiles, 256);
+    size_t desc_bytes = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
 
     CK(ctx->h_desc.reserve(desc_bytes));
     CK(ctx->d_packs.reserve(desc_bytes));
@@ -279,11 +321,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             for (uint32_t t = tile0[size_t(p)]; t < (p + 1 < npacks ? tile0[size_t(p) + 1] : ntiles); ++t) tp[t] = uint32_t(p);
     }
 
-    // ---- launch geometry: persistent grid, static round-robin tile assignment
-    int occ = int(std::min<size_t>(2, (227 * 1024) / (smem_bytes + 1024)));
-    if (occ < 1) occ = 1;
-    int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * occ));
+    if (!cjobs.empty()) std::memcpy(hd + off_cjobs, cjobs.data(), sizeof(CodesetJob) * cjobs.size());
+
+    // ---- launch geometry: persistent grid, static contiguous tile ranges
+    int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * geo.ctas));
     if (grid < 1) grid = 1;
+    if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
     CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
     if (bitsets) CK(ctx->d_bitsets.reserve(round_up(bitset_total, 8) + 64));
@@ -301,6 +344,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.views = reinterpret_cast<const ColView*>(dd + off_views);
     P.tile_pack = uniform ? nullptr : reinterpret_cast<const uint32_t*>(dd + off_tiles);
     P.set_vals = prog->dev_sets;
+    P.set_tabs = prog->dev_tabs;
+    P.code_bits = static_cast<const uint32_t*>(ctx->d_codebits.p);
+    std::memcpy(P.tab_off, prog->tab_off, sizeof(P.tab_off));
+    std::memcpy(P.tab_log2, prog->tab_log2, sizeof(P.tab_log2));
+    P.stages = uint32_t(geo.stages);
     P.bitsets = bitsets ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
     P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
     P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
@@ -318,7 +366,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * size_t(npacks), ctx->stream));
     if (naggs) CK(cudaMemcpyAsync(ctx->d_aggtype.p, P.agg_type, MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
-    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, ctx->stream)); ctx->last_launches++; }
+    if (ntiles && !cjobs.empty()) {
+        CK(launch_codeset(reinterpret_cast<const CodesetJob*>(dd + off_cjobs), uint32_t(cjobs.size()), prog->dev_sets,
+                          static_cast<uint32_t*>(ctx->d_codebits.p), ctx->stream));
+        ctx->last_launches++;
+    }
+    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, only32, geo.ctas, ctx->stream)); ctx->last_launches++; }
     if (naggs) {
         if (ntiles) {
             CK(launch_finalize(P.partials, uint32_t(grid), uint32_t(naggs), static_cast<const uint8_t*>(ctx->d_aggtype.p),
@@ -425,12 +478,27 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
         s.set_off = uint32_t(p->sets.size());
         p->set_off[l] = s.set_off;
         p->sets.insert(p->sets.end(), s.set.begin(), s.set.end());
+        if (!s.set.empty()) {
+            std::vector<uint64_t> slots; int lg = 0;
+            if (build_set_table(s.set, slots, lg)) {
+                s.has_table = true;
+                p->tab_off[l] = uint32_t(p->tabs.size()); p->tab_log2[l] = uint8_t(lg);
+                p->tabs.insert(p->tabs.end(), slots.begin(), slots.end());
+            }
+        }
         p->leaves.push_back(std::move(s));
     }
     for (int l = nleaves; l <= MAX_LEAVES; ++l) p->set_off[l] = uint32_t(p->sets.size());
     if (!p->sets.empty()) {
-        CK(cudaMalloc(&p->dev_sets, p->sets.size() * 8));
+        // one allocation: sorted sets, then (32 B aligned) the hash tables
+        size_t set_bytes = round_up(p->sets.size() * 8, 32), tab_bytes = p->tabs.size() * 8;
+        CK(cudaMalloc(&p->dev_sets, set_bytes + tab_bytes + 32));
         CK(cudaMemcpyAsync(p->dev_sets, p->sets.data(), p->sets.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+        if (tab_bytes) {
+            uint8_t* dt = reinterpret_cast<uint8_t*>(p->dev_sets) + set_bytes;
+            CK(cudaMemcpyAsync(dt, p->tabs.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            p->dev_tabs = reinterpret_cast<const uint64_t*>(dt);
+        }
         CK(cudaStreamSynchronize(ctx->stream));
     }
     *out = p.release();

@@ -578,6 +578,36 @@ void compile_valrange(PackLeaf& o, int t, int mode, uint64_t a, uint64_t b) {
 
 bool set_contains(const std::vector<uint64_t>& s, uint64_t v) { return std::binary_search(s.begin(), s.end(), v); }
 
+bool build_set_table(const std::vector<uint64_t>& set, std::vector<uint64_t>& slots, int& log2nb) {
+    slots.clear(); log2nb = 0;
+    if (set.empty()) return false;
+    int lg = 1;
+    while ((size_t(4) << lg) < set.size() * 2) ++lg;          // start at a load factor <= 0.5
+    const int lg_max = std::min(24, lg + 6);
+    std::vector<uint8_t> fill;
+    for (; lg <= lg_max; ++lg) {
+        const size_t nb = size_t(1) << lg;
+        slots.assign(nb * 4, 0); fill.assign(nb, 0);
+        bool ok = true;
+        for (uint64_t v : set) {
+            uint32_t b = set_table_bucket(v, lg);
+            if (fill[b] == 4) { ok = false; break; }
+            slots[size_t(b) * 4 + fill[b]++] = v;
+        }
+        if (!ok) continue;
+        for (size_t b = 0; b < nb; ++b) {
+            uint64_t pad;
+            if (fill[b]) pad = slots[b * 4];
+            else { pad = 0; while (set_table_bucket(pad, lg) == b) ++pad; }   // a key that can never probe bucket b
+            for (int k = fill[b]; k < 4; ++k) slots[b * 4 + size_t(k)] = pad;
+        }
+        log2nb = lg;
+        return true;
+    }
+    slots.clear();
+    return false;
+}
+
 bool scalar_match(int t, int mode, uint64_t v, uint64_t a, uint64_t b) {
     if (type_is_float(t)) {
         double x, y, z;
@@ -616,10 +646,23 @@ void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& l
         bool neg = mode == M_NIN;
         if (leaf.set.empty()) { set_const(o, neg); return; }
         if (v.kind == CK_CONST) { set_const(o, set_contains(leaf.set, v.base) != neg); return; }
-        // decoded value ∈ set, evaluated per row on the device (BITS / DICT stage their stream)
-        o.mode = LM_SET; o.neg = neg;
+        o.neg = neg;
+        if (v.kind == CK_DICT) {
+            // DictionaryContainer.MatchInSet (int_dict.go:361-398): the set is translated into a bitmap
+            // over this pack's codes on the device (codeset_kernel); the launch assigns o.a
+            o.mode = LM_CODESET; o.wm = v.delta; o.d = v.naux; o.a = 0;
+            o.data = v.data; o.width = v.width;
+            return;
+        }
+        if (v.kind == CK_BITS && leaf.has_table && !type_is_float(t)) {
+            // int_bitpack.go:249-291 / int_raw.go:339-380: decoded value looked up in the leaf's hash table
+            o.mode = LM_HASHSET; o.data = v.data; o.width = v.width;
+            return;
+        }
+        // decoded value ∈ sorted set, binary search per row (affine blocks) / per run (run-end blocks)
+        o.mode = LM_SET;
         o.a = leaf.set_off; o.d = leaf.set.size();
-        if (v.kind == CK_BITS || v.kind == CK_DICT) { o.data = v.data; o.width = v.width; }
+        if (v.kind == CK_BITS) { o.data = v.data; o.width = v.width; }
         return;
     }
 

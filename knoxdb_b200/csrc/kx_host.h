@@ -49,7 +49,16 @@ struct LeafSpec {
     uint64_t a = 0, b = 0;
     std::vector<uint64_t> set;   // sorted unique
     uint32_t set_off = 0;        // offset into the program's concatenated device set array
+    bool has_table = false;      // a bucketised hash table of the set exists on the device (LM_HASHSET)
 };
+
+// Bucketised hash table of an IN/NIN set for the device lookup (leaf_hashset in kx_scan.cu):
+// 2^log2nb buckets of 4 keys; key v lives in bucket (v * 0x9E3779B97F4A7C15) >> (64 - log2nb).
+// Unused slots repeat a key of the same bucket, empty buckets hold a key of ANOTHER bucket, so
+// comparing a probe with the four slots of its home bucket is exact.  Returns false (no table)
+// when the set does not fit 4-key buckets at a sane size; the scan then uses the sorted array.
+bool build_set_table(const std::vector<uint64_t>& set, std::vector<uint64_t>& slots, int& log2nb);
+inline uint32_t set_table_bucket(uint64_t v, int log2nb) { return uint32_t((v * 0x9E3779B97F4A7C15ull) >> (64 - log2nb)); }
 
 // Translate one leaf for one block.  dict_host: host copy of the block's dictionary values
 // (CK_DICT only).  view_index: index of the block's ColView in the launch's view table.

@@ -29,7 +29,19 @@ struct PruneParams {
     uint8_t postfix[MAX_POSTFIX];
 };
 
-cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream);
+// one dictionary-set translation job of codeset_kernel: bit c of out[out_off ...] = dict[c] ∈ set
+struct CodesetJob {
+    const uint8_t* dict;   // u64 dictionary values on the device
+    uint32_t ndict;
+    uint32_t set_off, nset;   // sorted set inside the program's set_vals
+    uint32_t out_off;         // first word of the bitmap
+    uint32_t pad;
+};
+
+constexpr size_t SCAN_MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the scan kernel may ask for
+
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,
                             AggPartial* out, cudaStream_t stream);
 cudaError_t launch_bitset_op(uint32_t* dst, const uint32_t* src, uint64_t nbits, int op, unsigned int* flags, cudaStream_t stream);

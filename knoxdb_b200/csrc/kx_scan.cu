@@ -118,9 +118,23 @@ __device__ __forceinline__ bool set_has(const uint64_t* __restrict__ s, uint32_t
 }
 
 // ------------------------------------------------------------------------------ leaf kernels
-// Every function evaluates one leaf for the warp's chunk of 32*R rows and returns the chunk's
-// bitset in "word per lane" form: lane j (< R) holds the bitset word of rows [32j, 32j+32) of
-// the chunk.
+// A tile is 256*R rows: every consumer warp owns R consecutive 32-row groups of it and walks them
+// in passes of up to 32 groups.  Every leaf function evaluates one leaf for one pass and returns
+// the pass's bitset in "word per lane" form: lane j (< Rp) holds the bitset word of group g0 + j
+// of the tile (rows [32 (g0+j), 32 (g0+j) + 32)).
+
+// Shared-memory bank conflicts of the fast path: lane j reads the W words of its own group, i.e.
+// the lanes of a quarter warp are W words apart.  That is conflict-free for every width except
+// W = 8, 16, 24, 32, where the 128-bit chunks of neighbouring lanes fall onto the same banks.  For
+// those widths lane j starts `rot` chunks into its group (wrapping around); because the chunks of
+// these widths hold whole rows the lane simply computes a ROTATED bitset word and rotates it back.
+template <int W> __device__ __forceinline__ int rot_chunks(uint32_t lane) {
+    if constexpr (W == 32) return (int)(lane & 7u);             // 8 chunks of 4 rows
+    else if constexpr (W == 16) return (int)((lane >> 1) & 3u); // 4 chunks of 8 rows
+    else if constexpr (W == 8) return (int)((lane >> 2) & 1u);  // 2 chunks of 16 rows
+    else if constexpr (W == 24) return (int)((lane >> 2) & 1u) * 3;   // 6 chunks, 3 chunks = 16 rows
+    else return 0;
+}
 
 // ---- fast path, width W <= 32 (compile time): each lane owns 32 CONSECUTIVE rows = exactly W
 // 32-bit words of the stream.  After full unrolling every field position is a constant, so a
@@ -129,12 +143,18 @@ __device__ __forceinline__ bool set_has(const uint64_t* __restrict__ s, uint32_t
 // ballot, no mask, and the W words arrive with 128/64/32-bit shared-memory loads.
 // The compare ((f - a) mod 2^W) <= d becomes (t - (a << K)) <= ((d << K) | (2^K - 1)), K = 32 - W.
 template <int W, bool SUB>
-__device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t a_top, uint32_t lim) {
+__device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t lane, uint32_t a_top, uint32_t lim) {
     uint32_t x[W + 1];
+    int rot_rows = 0;
     if constexpr (W % 4 == 0) {
+        constexpr int NC = W / 4;
+        const int rc = rot_chunks<W>(lane);
+        rot_rows = (rc * 128) / W;
 #pragma unroll
-        for (int i = 0; i < W / 4; ++i) {
-            uint4 v = reinterpret_cast<const uint4*>(seg)[i];
+        for (int i = 0; i < NC; ++i) {
+            int c = i + rc;
+            if (c >= NC) c -= NC;
+            uint4 v = reinterpret_cast<const uint4*>(seg)[c];
             x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
         }
     } else if constexpr (W % 2 == 0) {
@@ -158,14 +178,14 @@ __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, u
         if (SUB) t -= a_top;
         if (t <= lim) word |= (1u << j);
     }
+    if constexpr (W == 8 || W == 16 || W == 24 || W == 32) word = __funnelshift_l(word, word, rot_rows);
     return word;
 }
 
 template <bool SUB>
-__device__ __noinline__ uint32_t leaf_b32_dispatch(const uint32_t* __restrict__ sw, uint32_t group, uint32_t w, uint32_t a_top, uint32_t lim) {
-    const uint32_t* seg = sw + group * w;
+__device__ __noinline__ uint32_t leaf_b32_dispatch(const uint32_t* __restrict__ seg, uint32_t lane, uint32_t w, uint32_t a_top, uint32_t lim) {
     switch (w) {
-#define KX_CASE(W) case W: return leaf_b32<W, SUB>(seg, a_top, lim);
+#define KX_CASE(W) case W: return leaf_b32<W, SUB>(seg, lane, a_top, lim);
         KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
         KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
         KX_CASE(17) KX_CASE(18) KX_CASE(19) KX_CASE(20) KX_CASE(21) KX_CASE(22) KX_CASE(23) KX_CASE(24)
@@ -175,89 +195,218 @@ __device__ __noinline__ uint32_t leaf_b32_dispatch(const uint32_t* __restrict__ 
     return 0;
 }
 
-// one LM_RANGE32 leaf for the warp chunk; lanes >= R own no rows
-__device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
+// one LM_RANGE32 leaf for one pass; lanes >= Rp own no group
+__device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  uint32_t a, uint32_t d) {
-    if (lane >= R) return 0;
+    if (lane >= Rp) return 0;
     const uint32_t k = 32u - w;
     const uint32_t a_top = a << k, lim = (d << k) | ((1u << k) - 1u);   // k == 0: a, d
-    const uint32_t group = (row0 >> 5) + lane;
-    return a ? leaf_b32_dispatch<true>(sw, group, w, a_top, lim) : leaf_b32_dispatch<false>(sw, group, w, 0u, lim);
+    const uint32_t* seg = sw + (size_t)(g0 + lane) * w;
+    return a ? leaf_b32_dispatch<true>(seg, lane, w, a_top, lim) : leaf_b32_dispatch<false>(seg, lane, w, 0u, lim);
 }
 
-// ---- general path (33..64-bit fields): lane l handles rows l, l+32, l+64 … so its bit offset
-// advances by exactly w 32-bit words per iteration and its shift stays constant; bitset words
-// are built with __ballot_sync.
-__device__ __forceinline__ uint32_t leaf_range64(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
-                                                 uint64_t a, uint64_t d, uint64_t wm) {
-    uint32_t bit = (row0 + lane) * w;
-    uint32_t idx = bit >> 5, sh = bit & 31u;
-    uint64_t fm = width_mask((int)w);
-    uint32_t word = 0;
-    if (w <= 32) {
-#pragma unroll 4
-        for (uint32_t it = 0; it < R; ++it) {
-            uint64_t f = __funnelshift_r(sw[idx], sw[idx + 1], sh) & (uint32_t)fm;
-            uint32_t b = __ballot_sync(0xffffffffu, ((f - a) & wm) <= d);
-            if (lane == it) word = b;
-            idx += w;
+// ---- fast path for 33..63-bit fields (compile-time width): same lane-owns-32-consecutive-rows layout,
+// 64-bit top-aligned arithmetic: T = field << (64 - W) (low garbage bits harmless), (T - a_top) <= lim.
+template <int W, bool SUB>
+__device__ __forceinline__ uint32_t leaf_b64(const uint32_t* __restrict__ seg, uint64_t a_top, uint64_t lim) {
+    uint32_t x[W + 2];
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            uint4 v = reinterpret_cast<const uint4*>(seg)[i];
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 2; ++i) {
+            uint2 v = reinterpret_cast<const uint2*>(seg)[i];
+            x[2 * i] = v.x; x[2 * i + 1] = v.y;
         }
     } else {
-#pragma unroll 4
-        for (uint32_t it = 0; it < R; ++it) {
-            uint32_t w0 = sw[idx], w1 = sw[idx + 1], w2 = sw[idx + 2];
-            uint64_t f = (((uint64_t)__funnelshift_r(w1, w2, sh) << 32) | __funnelshift_r(w0, w1, sh)) & fm;
-            uint32_t b = __ballot_sync(0xffffffffu, ((f - a) & wm) <= d);
+#pragma unroll
+        for (int i = 0; i < W; ++i) x[i] = seg[i];
+    }
+    x[W] = 0; x[W + 1] = 0;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int bit = j * W, wi = bit >> 5, e = (bit & 31) + W;   // field = bits [e - W, e) of x[wi], x[wi+1], x[wi+2]
+        uint32_t hi, lo;
+        if (e <= 64) { hi = __funnelshift_l(x[wi], x[wi + 1], 64 - e); lo = x[wi] << (64 - e); }
+        else { hi = __funnelshift_l(x[wi + 1], x[wi + 2], 96 - e); lo = __funnelshift_l(x[wi], x[wi + 1], 96 - e); }
+        uint64_t t = ((uint64_t)hi << 32) | lo;
+        if (SUB) t -= a_top;
+        if (t <= lim) word |= (1u << j);
+    }
+    return word;
+}
+
+template <bool SUB>
+__device__ __noinline__ uint32_t leaf_b64_dispatch(const uint32_t* __restrict__ seg, uint32_t w, uint64_t a_top, uint64_t lim) {
+    switch (w) {
+#define KX_CASE(W) case W: return leaf_b64<W, SUB>(seg, a_top, lim);
+        KX_CASE(33) KX_CASE(34) KX_CASE(35) KX_CASE(36) KX_CASE(37) KX_CASE(38) KX_CASE(39) KX_CASE(40)
+        KX_CASE(41) KX_CASE(42) KX_CASE(43) KX_CASE(44) KX_CASE(45) KX_CASE(46) KX_CASE(47) KX_CASE(48)
+        KX_CASE(49) KX_CASE(50) KX_CASE(51) KX_CASE(52) KX_CASE(53) KX_CASE(54) KX_CASE(55) KX_CASE(56)
+        KX_CASE(57) KX_CASE(58) KX_CASE(59) KX_CASE(60) KX_CASE(61) KX_CASE(62) KX_CASE(63)
+#undef KX_CASE
+    }
+    return 0;
+}
+
+// LM_RANGE64 leaf for one pass.  33..63-bit fields take the compile-time-width path above; 64-bit
+// streams (raw uint64/int64, full-width bit-packing) are lane-strided — lane l handles rows l, l+32, …
+// with one LDS.64 per row — and build bitset words with __ballot_sync.
+__device__ __forceinline__ uint32_t leaf_range64(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
+                                                 uint64_t a, uint64_t d, uint64_t wm) {
+    uint32_t word = 0;
+    if (w == 64) {
+        const unsigned long long* s64 = reinterpret_cast<const unsigned long long*>(sw) + (size_t)g0 * 32u + lane;
+#pragma unroll 8
+        for (uint32_t it = 0; it < Rp; ++it) {
+            uint32_t b = __ballot_sync(0xffffffffu, (s64[it * 32u] - a) <= d);
             if (lane == it) word = b;
-            idx += w;
         }
+        return word;
+    }
+    if (w > 32) {
+        if (lane >= Rp) return 0;
+        const uint32_t k = 64u - w;
+        const uint64_t a_top = a << k, lim = (d << k) | ((1ull << k) - 1ull);
+        const uint32_t* seg = sw + (size_t)(g0 + lane) * w;
+        return a ? leaf_b64_dispatch<true>(seg, w, a_top, lim) : leaf_b64_dispatch<false>(seg, w, 0ull, lim);
+    }
+    // <= 32-bit fields evaluated in 64-bit arithmetic (not produced by the host translation; kept for completeness)
+    uint32_t bit = (g0 * 32u + lane) * w;
+    uint32_t idx = bit >> 5, sh = bit & 31u;
+    uint64_t fm = width_mask((int)w);
+#pragma unroll 4
+    for (uint32_t it = 0; it < Rp; ++it) {
+        uint64_t f = __funnelshift_r(sw[idx], sw[idx + 1], sh) & (uint32_t)fm;
+        uint32_t b = __ballot_sync(0xffffffffu, ((f - a) & wm) <= d);
+        if (lane == it) word = b;
+        idx += w;
+    }
+    return word;
+}
+
+// IEEE ordered-quiet compares, != true on NaN (internal/cmp/float.go:13-242); OP = types.FilterMode
+template <int OP, typename F>
+__device__ __forceinline__ bool float_pred(F x, F a, F b) {
+    if constexpr (OP == 1) return x == a;
+    else if constexpr (OP == 2) return x != a;
+    else if constexpr (OP == 3) return x > a;
+    else if constexpr (OP == 4) return x >= a;
+    else if constexpr (OP == 5) return x < a;
+    else if constexpr (OP == 6) return x <= a;
+    else return a <= x && x <= b;
+}
+
+template <int OP, typename F>
+__device__ __forceinline__ uint32_t leaf_float_op(const F* __restrict__ sf, uint32_t Rp, uint32_t lane, F a, F b) {
+    uint32_t word = 0;
+#pragma unroll 8
+    for (uint32_t it = 0; it < Rp; ++it) {
+        uint32_t bal = __ballot_sync(0xffffffffu, float_pred<OP, F>(sf[it * 32u], a, b));
+        if (lane == it) word = bal;
     }
     return word;
 }
 
 template <typename F>
-__device__ __forceinline__ bool float_pred(uint32_t op, F x, F a, F b) {
-    switch (op) {   // IEEE ordered-quiet compares, != true on NaN (internal/cmp/float.go:13-242)
-    case 1: return x == a;
-    case 2: return x != a;
-    case 3: return x > a;
-    case 4: return x >= a;
-    case 5: return x < a;
-    case 6: return x <= a;
-    case 9: return a <= x && x <= b;
+__device__ __forceinline__ uint32_t leaf_float_t(const F* __restrict__ sf, uint32_t Rp, uint32_t lane, uint32_t op, F a, F b) {
+    switch (op) {
+    case 1: return leaf_float_op<1, F>(sf, Rp, lane, a, b);
+    case 2: return leaf_float_op<2, F>(sf, Rp, lane, a, b);
+    case 3: return leaf_float_op<3, F>(sf, Rp, lane, a, b);
+    case 4: return leaf_float_op<4, F>(sf, Rp, lane, a, b);
+    case 5: return leaf_float_op<5, F>(sf, Rp, lane, a, b);
+    case 6: return leaf_float_op<6, F>(sf, Rp, lane, a, b);
+    case 9: return leaf_float_op<9, F>(sf, Rp, lane, a, b);
     }
-    return false;
+    return 0;
 }
 
-__device__ __forceinline__ uint32_t leaf_float(const uint32_t* __restrict__ sw, uint32_t w, uint32_t row0, uint32_t R, uint32_t lane,
+__device__ __forceinline__ uint32_t leaf_float(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                uint32_t op, uint64_t a, uint64_t b) {
-    uint32_t word = 0;
-    if (w == 64) {
-        const double* sd = reinterpret_cast<const double*>(sw);
-        double da = __longlong_as_double((long long)a), db = __longlong_as_double((long long)b);
-#pragma unroll 4
-        for (uint32_t it = 0; it < R; ++it) {
-            uint32_t bal = __ballot_sync(0xffffffffu, float_pred<double>(op, sd[row0 + it * 32 + lane], da, db));
-            if (lane == it) word = bal;
-        }
-    } else {
-        const float* sf = reinterpret_cast<const float*>(sw);
-        float fa = __uint_as_float((uint32_t)a), fb = __uint_as_float((uint32_t)b);
-#pragma unroll 4
-        for (uint32_t it = 0; it < R; ++it) {
-            uint32_t bal = __ballot_sync(0xffffffffu, float_pred<float>(op, sf[row0 + it * 32 + lane], fa, fb));
-            if (lane == it) word = bal;
-        }
+    if (w == 64)
+        return leaf_float_t<double>(reinterpret_cast<const double*>(sw) + (size_t)g0 * 32u + lane, Rp, lane, op,
+                                    __longlong_as_double((long long)a), __longlong_as_double((long long)b));
+    return leaf_float_t<float>(reinterpret_cast<const float*>(sw) + (size_t)g0 * 32u + lane, Rp, lane, op,
+                               __uint_as_float((uint32_t)a), __uint_as_float((uint32_t)b));
+}
+
+// ---- IN / NOT IN on a dictionary block (DictionaryContainer.MatchInSet, int_dict.go:361-398): the set
+// was translated into a bitmap over the pack's codes (translateSet :400) by codeset_kernel; each
+// lane tests the 32 codes of its own group.
+__device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
+                                                 uint32_t code_base, const uint32_t* __restrict__ bm, uint32_t ncodes) {
+    if (lane >= Rp) return 0;
+    const uint32_t* seg = sw + (size_t)(g0 + lane) * w;
+    const uint32_t fm = w >= 32 ? 0xffffffffu : ((1u << w) - 1u);
+    uint32_t word = 0, bit = 0;
+#pragma unroll 8
+    for (uint32_t j = 0; j < 32; ++j, bit += w) {
+        uint32_t wi = bit >> 5, sh = bit & 31u;
+        uint32_t code = (__funnelshift_r(seg[wi], seg[wi + 1], sh) & fm) + code_base;
+        uint32_t hit = code < ncodes ? (__ldg(bm + (code >> 5)) >> (code & 31u)) & 1u : 0u;
+        word |= hit << j;
     }
     return word;
 }
 
-// generic per-row leaves (IN / NIN sets, run-end blocks): value decode + test
-__device__ __forceinline__ uint32_t leaf_generic(const PackLeaf& L, const ColView& v, const uint32_t* staged, uint32_t pack_row0,
-                                                 uint32_t row0, uint32_t R, uint32_t lane, uint32_t nrows, const uint64_t* __restrict__ sets) {
+// ---- IN / NOT IN on a bit-packed / raw integer block (int_bitpack.go:249-291, int_raw.go:339-380): the
+// decoded value T(field + For) is looked up in the leaf's bucketised hash table (4 keys per 32 B bucket,
+// built by the host at kx_prog_compile; empty slots hold keys of other buckets, so a plain compare of the
+// four slots is exact).
+__device__ __forceinline__ uint32_t hash_bucket(uint64_t v, uint32_t log2nb) {
+    return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> (64u - log2nb));
+}
+__device__ __forceinline__ uint32_t leaf_hashset(const uint32_t* __restrict__ sw, const ColView& v, uint32_t g0, uint32_t Rp, uint32_t lane,
+                                                 const ulonglong2* __restrict__ tab, uint32_t log2nb) {
+    if (lane >= Rp) return 0;
+    const uint32_t w = v.width;
+    const int type = v.type;
+    const uint64_t base = v.base;
+    uint32_t bit = (g0 + lane) * 32u * w;
     uint32_t word = 0;
-    for (uint32_t it = 0; it < R; ++it) {
-        uint32_t rt = row0 + it * 32 + lane;        // row within tile
+#pragma unroll 4
+    for (uint32_t j = 0; j < 32; ++j, bit += w) {
+        uint64_t val = type_ext(type, load_field(sw, bit, w) + base);
+        const ulonglong2* b = tab + 2u * (size_t)hash_bucket(val, log2nb);
+        ulonglong2 p = __ldg(b), q = __ldg(b + 1);
+        uint32_t hit = (p.x == val) | (p.y == val) | (q.x == val) | (q.y == val);
+        word |= hit << j;
+    }
+    return word;
+}
+
+// ---- run-end blocks (RunEndContainer.Match* + applyMatch, int_runend.go:224-318): the predicate is
+// evaluated on run VALUES; each lane finds the run of its group's first row once and walks forward.
+__device__ __forceinline__ uint32_t leaf_runend(const PackLeaf& L, const ColView& v, uint32_t grow0, uint32_t nrows, bool active,
+                                                const uint64_t* __restrict__ sets) {
+    if (!active || grow0 >= nrows) return 0;
+    const uint32_t* ends = reinterpret_cast<const uint32_t*>(v.aux);
+    const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(v.data);
+    const uint32_t rend = min(grow0 + 32u, nrows);
+    uint32_t k = run_of_row(ends, v.naux, grow0);
+    uint32_t word = 0, r = grow0;
+    while (r < rend && k < v.naux) {
+        uint32_t hi = min(__ldg(ends + k), rend - 1u);     // inclusive
+        uint64_t val = __ldg(vals + k);
+        bool p = (L.mode == LM_SET) ? set_has(sets + L.a, (uint32_t)L.d, val) : ((val ^ L.wm) - L.a) <= L.d;
+        if (p) word |= (0xffffffffu >> (31u - (hi - grow0))) & (0xffffffffu << (r - grow0));
+        r = hi + 1u; ++k;
+    }
+    return word;
+}
+
+// generic per-row fallback (sets on affine blocks, …): value decode + test
+__device__ __forceinline__ uint32_t leaf_generic(const PackLeaf& L, const ColView& v, const uint32_t* staged, uint32_t pack_row0,
+                                                 uint32_t g0, uint32_t Rp, uint32_t lane, uint32_t nrows, const uint64_t* __restrict__ sets) {
+    uint32_t word = 0;
+    for (uint32_t it = 0; it < Rp; ++it) {
+        uint32_t rt = (g0 + it) * 32u + lane;       // row within tile
         uint32_t row = pack_row0 + rt;              // row within pack
         bool p = false;
         if (row < nrows) {
@@ -271,29 +420,51 @@ __device__ __forceinline__ uint32_t leaf_generic(const PackLeaf& L, const ColVie
     return word;
 }
 
+// Dictionary-set translation (DictionaryContainer.translateSet, int_dict.go:400-440) on the device: one
+// block per (pack, leaf) job, one lane per dictionary entry, binary search in the sorted set, ballot →
+// bitmap word.  Runs on the scan stream right before scan_kernel.
+__global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, const uint64_t* __restrict__ set_vals, uint32_t* __restrict__ out) {
+    const CodesetJob J = jobs[blockIdx.x];
+    const unsigned long long* dict = reinterpret_cast<const unsigned long long*>(J.dict);
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint32_t base = (threadIdx.x >> 5) * 32u; base < J.ndict; base += (blockDim.x >> 5) * 32u) {
+        uint32_t code = base + lane;
+        bool hit = code < J.ndict && set_has(set_vals + J.set_off, J.nset, __ldg(dict + code));
+        uint32_t b = __ballot_sync(0xffffffffu, hit);
+        if (lane == 0) out[J.out_off + (base >> 5)] = b;
+    }
+}
+
 // ------------------------------------------------------------------------------ aggregates
 // Per-thread accumulator of one value column: four 64-bit slots, meaning depends on the type
 //   integers: s0 = sum mod 2^64, s1 = min, s2 = max (order-preserving unsigned domain)
 //   float64 : s0 = running sum, s1 = Neumaier compensation, s2 = min, s3 = max (IEEE bits)
-// The match count / validity is shared by all value columns of a thread.
+// Accumulators start at the identity (min = +max, max = -max); the match count decides validity.
 struct AggAcc { uint64_t s[4]; };
 
 __device__ __forceinline__ double as_f64(uint64_t b) { return __longlong_as_double((long long)b); }
 __device__ __forceinline__ uint64_t as_u64(double d) { return (uint64_t)__double_as_longlong(d); }
 
-__device__ __forceinline__ void agg_add(AggAcc& A, int type, uint64_t bits, bool first) {
+__device__ __forceinline__ AggAcc agg_identity(int type) {
+    AggAcc A;
+    if (type == 9) { A.s[0] = 0; A.s[1] = 0; A.s[2] = 0x7ff0000000000000ull; A.s[3] = 0xfff0000000000000ull; }
+    else { A.s[0] = 0; A.s[1] = ~0ull; A.s[2] = 0; A.s[3] = 0; }
+    return A;
+}
+
+__device__ __forceinline__ void agg_add(AggAcc& A, int type, uint64_t bits) {
     if (type == 9) {   // float64: compensated running sum (deterministic per thread)
         double x = as_f64(bits), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
         double t = sum + x;
         err += (fabs(sum) >= fabs(x)) ? ((sum - t) + x) : ((x - t) + sum);
         A.s[0] = as_u64(t); A.s[1] = as_u64(err);
-        if (first || x < as_f64(A.s[2])) A.s[2] = bits;
-        if (first || x > as_f64(A.s[3])) A.s[3] = bits;
+        if (x < as_f64(A.s[2])) A.s[2] = bits;
+        if (x > as_f64(A.s[3])) A.s[3] = bits;
     } else {
         A.s[0] += bits;   // wraps mod 2^64; narrower T is truncated on the host
         uint64_t k = type_is_signed(type) ? bits ^ 0x8000000000000000ull : bits;
-        if (first || k < A.s[1]) A.s[1] = k;
-        if (first || k > A.s[2]) A.s[2] = k;
+        if (k < A.s[1]) A.s[1] = k;
+        if (k > A.s[2]) A.s[2] = k;
     }
 }
 
@@ -305,7 +476,7 @@ __device__ __forceinline__ void fsum_merge(double& s, double& e, double s2, doub
     e += e2 + c;
 }
 
-// merge B into A; both non-empty
+// merge B into A (identities merge as no-ops)
 __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) {
     if (type == 9) {
         double s = as_f64(A.s[0]), e = as_f64(A.s[1]);
@@ -331,21 +502,25 @@ __device__ __forceinline__ uint32_t pack_of_tile(const PackInfo* __restrict__ pa
     return lo;
 }
 
-// SIMPLE = one leaf, no aggregates: the hot configuration (fused decode + compare + popcount)
-template <bool SIMPLE>
-__global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams P) {
+constexpr int AGG_BATCH = 4;   // 32-row groups whose value loads are issued back to back
+
+// SIMPLE = one leaf, no aggregates: the hot configuration (fused decode + compare + popcount).
+// ONLY32 (with SIMPLE) = every pack's leaf is a <= 32-bit packed range test (or all / none): a lean
+// instantiation without the other leaf paths (small code footprint, fewer registers), MINB CTAs per SM.
+template <bool SIMPLE, bool ONLY32, int MINB>
+__global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
-    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint8_t* stage_base = smem + 128;
     __shared__ AggAcc warp_acc[CONSUMER_WARPS];
     __shared__ unsigned long long warp_cnt[CONSUMER_WARPS];
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    const uint32_t R = P.R, tile_rows = R * 32u * CONSUMER_WARPS;
+    const uint32_t R = P.R, tile_rows = R * 32u * CONSUMER_WARPS, nstages = P.stages;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        for (uint32_t s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
@@ -371,9 +546,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
     if (warp == CONSUMER_WARPS) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
-            uint32_t k = 0;
-            for (uint32_t t = t_begin; t < t_end; ++t, ++k) {
-                uint32_t s = k % STAGES, ph = (k / STAGES) & 1u;
+            uint32_t s = 0, ph = 0;
+            for (uint32_t t = t_begin; t < t_end; ++t) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);          // slot released by all consumer warps
                 uint32_t rows = min(tile_rows, pi.n - chunk * tile_rows);
                 const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
@@ -391,6 +565,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
                     dst += (tile_rows / 8u) * w + 16u;      // slot = full-tile bytes + over-read pad
                 }
                 if (t + 1 < t_end) next_tile();
+                if (++s == nstages) { s = 0; ph ^= 1u; }
             }
         }
         return;
@@ -399,10 +574,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
     // ===================== consumers: unpack + filter + reduce =====================
     AggAcc acc[SIMPLE ? 1 : MAX_AGGS];
 #pragma unroll
-    for (int j = 0; j < (SIMPLE ? 1 : MAX_AGGS); ++j) acc[j] = AggAcc{};
+    for (int j = 0; j < (SIMPLE ? 1 : MAX_AGGS); ++j) acc[j] = agg_identity(SIMPLE ? 0 : P.agg_type[j]);
     unsigned long long nmatch = 0;   // rows this thread reduced
     uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
-    const uint32_t row0 = warp * R * 32u;   // first row of the warp chunk within a tile
+    const uint32_t passes = (R + 31u) >> 5, Rp = min(R, 32u);
 
     auto flush_count = [&](uint32_t pk) {
         uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
@@ -410,102 +585,141 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
         lane_cnt = 0;
     };
 
-    uint32_t k = 0;
-    for (uint32_t t = t_begin; t < t_end; ++t, ++k) {
-        const uint32_t s = k % STAGES, ph = (k / STAGES) & 1u;
+    uint32_t s = 0, ph = 0;
+    for (uint32_t t = t_begin; t < t_end; ++t) {
         const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
         const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
         const uint8_t* stage = stage_base + (size_t)s * P.stage_bytes;
 
-        mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
-
-        auto eval_leaf = [&](const PackLeaf& lf, const uint32_t* sw) -> uint32_t {
-            uint32_t word;
-            switch (lf.mode) {
-            case LM_NONE: word = 0; break;
-            case LM_ALL: word = 0xffffffffu; break;
-            case LM_RANGE32: word = leaf_range32(sw, lf.width, row0, R, lane, (uint32_t)lf.a, (uint32_t)lf.d); break;
-            case LM_RANGE64: word = leaf_range64(sw, lf.width, row0, R, lane, lf.a, lf.d, lf.wm); break;
-            case LM_FLOAT: word = leaf_float(sw, lf.width, row0, R, lane, lf.fop, lf.a, lf.d); break;
-            case LM_ROWRANGE: {
-                // rows [a, a+d] of the pack → bits of this lane's word
-                uint64_t r = (uint64_t)pack_row0 + row0 + lane * 32u;     // first row of the word
-                uint64_t lo = lf.a, hi = lf.a + lf.d;
-                word = 0;
-                if (hi >= r && lo < r + 32u) {
-                    uint32_t b0 = lo > r ? (uint32_t)(lo - r) : 0u;
-                    uint32_t b1 = hi < r + 31u ? (uint32_t)(hi - r) : 31u;
-                    word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
-                }
-                break;
-            }
-            default:
-                word = leaf_generic(lf, P.views[lf.view], lf.data ? sw : nullptr, pack_row0, row0, R, lane, pi.n, P.set_vals);
-                break;
-            }
-            return lf.neg ? ~word : word;
-        };
-
-        uint32_t word;
-        if (SIMPLE) {
-            word = eval_leaf(L[0], reinterpret_cast<const uint32_t*>(stage));
-        } else {
-            // evaluate the leaves and the AND/OR program on word-per-lane bitsets
-            uint32_t stack[MAX_LEAVES];
-            uint32_t leaf_off[MAX_LEAVES];
-            int sp = 0;
+        uint32_t leaf_off[SIMPLE ? 1 : MAX_LEAVES];
+        if (SIMPLE) leaf_off[0] = 0;
+        else {
             uint32_t off = 0;
             for (uint32_t l = 0; l < P.nleaves; ++l) {
                 leaf_off[l] = off;
                 if (L[l].data) off += (tile_rows / 8u) * L[l].width + 16u;
             }
-            for (uint32_t i = 0; i < P.npost; ++i) {
-                uint32_t op = P.postfix[i];
-                if (op < 0x80u) {
-                    stack[sp++] = eval_leaf(L[op], reinterpret_cast<const uint32_t*>(stage + leaf_off[op]));
-                } else {
-                    uint32_t y = stack[--sp];
-                    stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
+        }
+
+        mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
+
+        for (uint32_t pass = 0; pass < passes; ++pass) {
+            const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
+            const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
+
+            auto eval_leaf = [&](uint32_t li) -> uint32_t {
+                const PackLeaf& lf = L[li];
+                const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage + leaf_off[SIMPLE ? 0 : li]);
+                uint32_t word;
+                if constexpr (ONLY32) {
+                    if (lf.mode == LM_RANGE32) word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d);
+                    else word = lf.mode == LM_ALL ? 0xffffffffu : 0u;
+                    return lf.neg ? ~word : word;
                 }
+                switch (lf.mode) {
+                case LM_NONE: word = 0; break;
+                case LM_ALL: word = 0xffffffffu; break;
+                case LM_RANGE32: word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d); break;
+                case LM_RANGE64: word = leaf_range64(sw, lf.width, g0, Rp, lane, lf.a, lf.d, lf.wm); break;
+                case LM_FLOAT: word = leaf_float(sw, lf.width, g0, Rp, lane, lf.fop, lf.a, lf.d); break;
+                case LM_ROWRANGE: {
+                    // rows [a, a+d] of the pack → bits of this lane's word
+                    uint64_t lo = lf.a, hi = lf.a + lf.d;
+                    word = 0;
+                    if (hi >= wr && lo < wr + 32u) {
+                        uint32_t b0 = lo > wr ? (uint32_t)(lo - wr) : 0u;
+                        uint32_t b1 = hi < wr + 31u ? (uint32_t)(hi - wr) : 31u;
+                        word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
+                    }
+                    break;
+                }
+                case LM_CODESET:
+                    word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, P.code_bits + lf.a, (uint32_t)lf.d);
+                    break;
+                case LM_HASHSET:
+                    word = leaf_hashset(sw, P.views[lf.view], g0, Rp, lane,
+                                        reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]), P.tab_log2[li]);
+                    break;
+                default: {
+                    const ColView& v = P.views[lf.view];
+                    if (v.kind == CK_RUNEND) word = leaf_runend(lf, v, (uint32_t)wr, pi.n, lane < Rp, P.set_vals);
+                    else word = leaf_generic(lf, v, lf.data ? sw : nullptr, pack_row0, g0, Rp, lane, pi.n, P.set_vals);
+                    break;
+                }
+                }
+                return lf.neg ? ~word : word;
+            };
+
+            uint32_t word;
+            if (SIMPLE) {
+                word = eval_leaf(0);
+            } else {
+                // evaluate the leaves and the AND/OR program on word-per-lane bitsets
+                uint32_t stack[MAX_LEAVES];
+                int sp = 0;
+                for (uint32_t i = 0; i < P.npost; ++i) {
+                    uint32_t op = P.postfix[i];
+                    if (op < 0x80u) {
+                        stack[sp++] = eval_leaf(op);
+                    } else {
+                        uint32_t y = stack[--sp];
+                        stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
+                    }
+                }
+                word = stack[0];
             }
-            word = stack[0];
-        }
 
-        // all shared-memory reads of this stage are done: hand the slot back to the producer early
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
-
-        // mask rows past the end of the pack (tail bits must be zero) and lanes >= R
-        const uint64_t wr = (uint64_t)pack_row0 + row0 + lane * 32u;   // first row of this lane's word
-        {
-            uint32_t valid = 0;
-            if (lane < R && wr < pi.n) {
-                uint32_t left = pi.n - (uint32_t)wr;
-                valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+            // all shared-memory reads of this stage are done: hand the slot back to the producer early
+            if (pass + 1 == passes) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty_bar[s]);
             }
-            word &= valid;
-        }
 
-        // outputs: bitset words (coalesced 128 B per warp), per-pack match count
-        if (P.bitsets && lane < R && wr < pi.n)
-            *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
-        lane_cnt += __popc(word);
+            // mask rows past the end of the pack (tail bits must be zero) and lanes >= Rp
+            {
+                uint32_t valid = 0;
+                if (lane < Rp && wr < pi.n) {
+                    uint32_t left = pi.n - (uint32_t)wr;
+                    valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+                }
+                word &= valid;
+            }
 
-        // fused reduce over the matching rows of the value columns (read on demand)
-        if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
-            for (uint32_t it = 0; it < R; ++it) {
-                uint32_t wd = __shfl_sync(0xffffffffu, word, it);
-                if (wd == 0) continue;
-                if ((wd >> lane) & 1u) {
-                    uint32_t row = pack_row0 + row0 + it * 32u + lane;
+            // outputs: bitset words (coalesced 128 B per warp), per-pack match count
+            if (P.bitsets && lane < Rp && wr < pi.n)
+                *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
+            lane_cnt += __popc(word);
+
+            // fused reduce over the matching rows of the value columns, read on demand: the loads of
+            // AGG_BATCH groups are issued back to back (memory-level parallelism), groups without a
+            // match cost nothing
+            if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
+                const uint32_t row_base = pack_row0 + g0 * 32u + lane;
+                for (uint32_t it0 = 0; it0 < Rp; it0 += AGG_BATCH) {
+                    uint32_t wd[AGG_BATCH], anyw = 0;
+#pragma unroll
+                    for (int u = 0; u < AGG_BATCH; ++u) {
+                        wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
+                        if (it0 + u >= Rp) wd[u] = 0;
+                        anyw |= wd[u];
+                    }
+                    if (anyw == 0) continue;
 #pragma unroll
                     for (int j = 0; j < MAX_AGGS; ++j) {
                         if (j < (int)P.naggs) {
                             const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
-                            agg_add(acc[SIMPLE ? 0 : j], P.agg_type[j], decode_value(v, row, nullptr, 0), nmatch == 0);
+                            const int type = P.agg_type[j];
+                            uint64_t val[AGG_BATCH];
+#pragma unroll
+                            for (int u = 0; u < AGG_BATCH; ++u)
+                                if ((wd[u] >> lane) & 1u) val[u] = decode_value(v, row_base + (it0 + u) * 32u, nullptr, 0);
+#pragma unroll
+                            for (int u = 0; u < AGG_BATCH; ++u)
+                                if ((wd[u] >> lane) & 1u) agg_add(acc[SIMPLE ? 0 : j], type, val[u]);
                         }
                     }
-                    ++nmatch;
+#pragma unroll
+                    for (int u = 0; u < AGG_BATCH; ++u) nmatch += (wd[u] >> lane) & 1u;
                 }
             }
         }
@@ -515,6 +729,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
             next_tile();
             if (pack != prev) flush_count(prev);
         }
+        if (++s == nstages) { s = 0; ph ^= 1u; }
     }
     flush_count(pack);
 
@@ -530,7 +745,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
 #pragma unroll
             for (int q = 0; q < 4; ++q) b.s[q] = __shfl_down_sync(0xffffffffu, a.s[q], off);
             unsigned long long cb = __shfl_down_sync(0xffffffffu, c, off);
-            if (cb) { if (c) agg_merge(a, b, type); else a = b; }
+            agg_merge(a, b, type);
             c += cb;
         }
         if (lane == 0) { warp_acc[warp] = a; warp_cnt[warp] = c; }
@@ -539,10 +754,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 2) scan_kernel(const ScanParams 
         if (threadIdx.x == 0) {
             AggAcc r = warp_acc[0];
             unsigned long long rc = warp_cnt[0];
-            for (int q = 1; q < CONSUMER_WARPS; ++q) {
-                if (warp_cnt[q]) { if (rc) agg_merge(r, warp_acc[q], type); else r = warp_acc[q]; }
-                rc += warp_cnt[q];
-            }
+            for (int q = 1; q < CONSUMER_WARPS; ++q) { agg_merge(r, warp_acc[q], type); rc += warp_cnt[q]; }
             AggPartial o;
             o.count = rc; o.valid = rc != 0; o.pad = 0;
             if (type == 9) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
@@ -791,14 +1003,32 @@ __global__ void prune_kernel(PruneParams P) {
 // ------------------------------------------------------------------------------ launchers
 static int grid_for(uint64_t items, uint64_t cap) { uint64_t g = (items + 255) / 256; return (int)(g < cap ? g : cap); }
 
-cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream) {
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream) {
     const bool simple = P.nleaves == 1 && P.naggs == 0;
-    auto kern = simple ? scan_kernel<true> : scan_kernel<false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    int variant = !simple ? 0 : (!only32 ? 1 : (ctas_per_sm >= 3 ? 3 : 2));
+    void (*kern)(const ScanParams) = scan_kernel<false, false, 2>;
+    if (variant == 1) kern = scan_kernel<true, false, 2>;
+    if (variant == 2) kern = scan_kernel<true, true, 2>;
+    if (variant == 3) kern = scan_kernel<true, true, 3>;
+    // function attributes are per device and sticky: set them once per (device, variant)
+    static bool configured[64][4] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev][variant]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_MAX_DYN_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev][variant] = true;
+    }
     kern<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream) {
+    if (njobs == 0) return cudaSuccess;
+    codeset_kernel<<<njobs, 256, 0, stream>>>(jobs, set_vals, out);
     return cudaGetLastError();
 }
 

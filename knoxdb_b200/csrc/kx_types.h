@@ -51,6 +51,9 @@ enum LeafMode : uint8_t {
     LM_ROWRANGE = 5,  // row index in [a, d] (affine blocks: closed-form index arithmetic)
     LM_SET = 6,       // decoded value ∈ sorted set (binary search)
     LM_VALRANGE = 7,  // decoded value v: ((v ^ flip) - a) <= d  (run-end / generic fallback)
+    LM_CODESET = 8,   // staged dictionary codes: bit (field + wm) of the pack's code bitmap at code_bits + a
+                      // (d = number of codes); the bitmap is built on the device per (pack, leaf) and query
+    LM_HASHSET = 9,   // staged integer stream: T(field + base) looked up in the leaf's bucketised hash table
 };
 
 struct PackLeaf {
@@ -86,7 +89,7 @@ constexpr int MAX_POSTFIX = 2 * MAX_LEAVES;
 
 constexpr int CONSUMER_WARPS = 8;
 constexpr int SCAN_THREADS = (CONSUMER_WARPS + 1) * 32;   // + 1 TMA producer warp
-constexpr int STAGES = 4;
+constexpr int MAX_STAGES = 8;               // ring depth is chosen per launch (2..8)
 
 struct ScanParams {
     const PackInfo* packs;     // [npacks]
@@ -94,15 +97,20 @@ struct ScanParams {
     const ColView*  views;     // ColView table (leaf blocks first, then agg blocks)
     const uint32_t* tile_pack; // [ntiles] pack index of each tile (nullptr: uniform packs)
     const uint64_t* set_vals;  // concatenated sorted sets
+    const uint64_t* set_tabs;  // bucketised hash tables of the IN/NIN leaves (4 x u64 per bucket)
+    const uint32_t* code_bits; // per (pack, leaf) dictionary-code bitmaps of this launch (LM_CODESET)
     uint8_t*  bitsets;         // nullable
     unsigned long long* counts; // [npacks] nullable
     AggPartial* partials;      // [gridDim.x][naggs]
     uint32_t npacks, ntiles;
     uint32_t nleaves, npost, naggs;
-    uint32_t R;                // 32-row iterations per warp per tile; tile rows = 256 * R
+    uint32_t R;                // 32-row groups per warp per tile; tile rows = 256 * R; R > 32 => multiple of 32
+    uint32_t stages;           // depth of the TMA ring (<= MAX_STAGES)
     uint32_t tiles_per_pack;   // uniform case
     uint32_t stage_bytes;
     uint32_t set_off[MAX_LEAVES + 1];
+    uint32_t tab_off[MAX_LEAVES];     // LM_HASHSET: first u64 of the leaf's table in set_tabs
+    uint8_t  tab_log2[MAX_LEAVES];    //             log2(#buckets) >= 1
     uint32_t agg_view0;        // views[agg_view0 + pack * naggs + j]
     uint32_t leaf_view0;       // views[leaf_view0 + pack * nleaves + l]
     uint8_t  postfix[MAX_POSTFIX];

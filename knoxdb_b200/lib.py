@@ -189,6 +189,7 @@ class Context:
 
     def close(self):
         if self.h:
+            self.free_host_arrays()
             lib().kx_ctx_destroy(self.h)
             self.h = None
 
@@ -200,7 +201,7 @@ class Context:
 
     # ---- pinned host memory
     def host_array(self, nbytes):
-        """uint8 numpy array over pinned host memory (freed with the context)."""
+        """uint8 numpy array over pinned host memory (freed with the context or free_host_arrays)."""
         p = lib().kx_host_alloc(self.h, max(int(nbytes), 1))
         if not p:
             raise KnoxError(-3, "kx_host_alloc failed")
@@ -208,6 +209,12 @@ class Context:
         arr = np.frombuffer(buf, dtype=np.uint8, count=int(nbytes))
         self.__dict__.setdefault("_pinned", []).append(p)
         return arr
+
+    def free_host_arrays(self):
+        """release every pinned array handed out so far (the numpy views must not be used afterwards)"""
+        for p in self.__dict__.get("_pinned", []):
+            lib().kx_host_free(self.h, p)
+        self.__dict__["_pinned"] = []
 
     # ---- device pack store
     def block_put(self, pack, version, field, block_type, enc):
@@ -234,9 +241,14 @@ class Context:
             total += ((int(n) + 7) // 8 + 7) // 8 * 8
         return np.asarray(offs, dtype=np.uint64), total
 
+    @staticmethod
+    def pack_refs(packs):
+        """kx_packref[] of a list of (pack, version) — build once, reuse across scans"""
+        return (_PackRef * len(packs))(*[_PackRef(p, v) for p, v in packs])
+
     def scan(self, prog, packs, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
-        """packs: list of (pack, version). Returns dict(counts, bitsets(list of arrays), aggs)."""
-        refs = (_PackRef * len(packs))(*[_PackRef(p, v) for p, v in packs])
+        """packs: list of (pack, version) or a prebuilt pack_refs() array. Returns dict(counts, bitsets(list of arrays), aggs)."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
         counts = np.zeros(len(packs), dtype=np.int64) if want_counts else None
         offs = bits = None
         if want_bitsets:

@@ -68,7 +68,11 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
     if (normalize_block(block_type, enc, len, hb.lay, err)) return -1;
     const ColView& v = hb.lay.view;
     LeafSpec leaf; leaf.type = uint8_t(block_type); leaf.mode = uint8_t(mode); leaf.a = a; leaf.b = b;
-    if (set) { leaf.set.assign(set, set + nset); std::sort(leaf.set.begin(), leaf.set.end()); leaf.set.erase(std::unique(leaf.set.begin(), leaf.set.end()), leaf.set.end()); }
+    std::vector<uint64_t> tab; int tab_log2 = 0;
+    if (set) {
+        leaf.set.assign(set, set + nset); std::sort(leaf.set.begin(), leaf.set.end()); leaf.set.erase(std::unique(leaf.set.begin(), leaf.set.end()), leaf.set.end());
+        leaf.has_table = build_set_table(leaf.set, tab, tab_log2);
+    }
     ColView dv = v;
     dv.data = hb.stream();   // non-null marks "has a stream" for compile_leaf
     PackLeaf L;
@@ -102,6 +106,17 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
         }
         case LM_ROWRANGE: p = (uint64_t(row) - L.a) <= L.d; break;
         case LM_SET: p = set_contains(leaf.set, hb.value(row)); break;
+        case LM_CODESET: {   // bit (field + code base) of the pack's code bitmap = dict[code] ∈ set (codeset_kernel)
+            uint64_t code = field_at(hb.stream(), hb.stream_len(), row, L.width) + L.wm;
+            p = code < L.d && set_contains(leaf.set, hb.lay.aux64[code]);
+            break;
+        }
+        case LM_HASHSET: {   // leaf_hashset: compare with the four slots of the home bucket
+            uint64_t val = type_ext(v.type, field_at(hb.stream(), hb.stream_len(), row, L.width) + v.base);
+            const uint64_t* b = tab.data() + size_t(set_table_bucket(val, tab_log2)) * 4;
+            p = b[0] == val || b[1] == val || b[2] == val || b[3] == val;
+            break;
+        }
         case LM_VALRANGE: p = ((hb.value(row) ^ L.wm) - L.a) <= L.d; break;
         }
         if (L.neg && L.mode != LM_NONE && L.mode != LM_ALL) p = !p;
