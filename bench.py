@@ -179,7 +179,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--packs", type=int, default=256, help="resident packs per GPU (4 Mi rows each)")
+    ap.add_argument("--packs", type=int, default=1024, help="resident packs per GPU (4 Mi rows each; 1024 packs = 10.7 GB packed)")
     ap.add_argument("--e2e-packs", type=int, default=64, help="packs per e2e step (host-resident blocks)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -213,13 +213,13 @@ def main():
         assert ctx.block_put(p, 1, FIELD, kb.UINT64, pinned[p % len(pinned)]) == PACK_ROWS
     thr_field = 1 << (W_BITS - 1)             # median of the uniform w-bit fields
     prog = kb.Program(ctx, [kb.Leaf(FIELD, kb.UINT64, kb.LT, FOR_BASE + thr_field)])
-    packs = [(p, 1) for p in range(npacks)]
+    packs = ctx.pack_refs([(p, 1) for p in range(npacks)])   # kx_packref[] built once, like a Go caller would
     nrows = [PACK_ROWS] * npacks
     offs, total_bits = ctx.bitset_layout(nrows)
     bitbuf = ctx.host_array(total_bits)       # pinned result buffer
 
     # ---- parity spot check against numpy truth on one pack (full check lives in tests/)
-    r = ctx.scan(prog, packs[:2], nrows=nrows[:2], want_bitsets=True)
+    r = ctx.scan(prog, [(0, 1), (1, 1)], nrows=nrows[:2], want_bitsets=True)
     words = payloads[0].view(np.uint64)
     sample_rows = 100_000
     bitoff = np.arange(sample_rows, dtype=np.uint64) * np.uint64(W_BITS)
@@ -233,6 +233,7 @@ def main():
     from knoxdb_b200 import shard
     from knoxdb_b200.lib import AggOut
     dev = torch.device("cuda", local)
+    exch = shard.PartialExchange(1, dist, dev) if world > 1 else None
 
     def step_resident():
         res = ctx.scan(prog, packs, nrows=nrows, want_bitsets=False)     # counts only: bitsets stay in HBM
@@ -242,7 +243,7 @@ def main():
             # ONE small NCCL collective per query: all-gather of the 64 B per-rank partial, combined in
             # rank order through kx_agg_combine (the same path sum/min/max partials take)
             mine = AggOut(); mine.count = total; mine.sum_bits = total; mine.min_bits = total; mine.max_bits = total; mine.valid = 1
-            total = int(shard.allgather_partials([mine], [kb.UINT64], dist, dev)[0].sum_bits)
+            total = int(exch.exchange([mine], [kb.UINT64])[0].sum_bits)
         return st, total
 
     # the headline kernel writes bitsets too; kx_scan(bitsets=…) would also copy them to the host, so

@@ -40,6 +40,7 @@ enum {
     KX_INT64 = 1, KX_INT32 = 2, KX_INT16 = 3, KX_INT8 = 4,
     KX_UINT64 = 5, KX_UINT32 = 6, KX_UINT16 = 7, KX_UINT8 = 8,
     KX_FLOAT64 = 9, KX_FLOAT32 = 10,
+    KX_BYTES = 12,   /* byte strings: pruning (bloom probes, bloom build) only */
 };
 
 /* internal/types/mode.go:14-23 (FilterMode) */
@@ -199,6 +200,33 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks,
                  const uint64_t* mins, const uint64_t* maxs,
                  const void* const* blooms, const size_t* bloom_len,
                  const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out);
+
+/* ---------------------------------------------------------------- resident statistics index
+ * The same pruning over a statistics index that LIVES on the device: per data pack and column the zone map
+ * (min, max — the min/max columns of the reference's statistics packs, internal/pack/stats/index.go) and
+ * optionally a bloom filter (the buffers stored under encodeFilterKey, internal/pack/stats/filter.go:26-32).
+ * One kx_stats covers any number of data packs (a reference statistics pack holds <= 2048).
+ * mins/maxs are COLUMN-major: [nfields][npacks] 64-bit patterns; byte-string columns (KX_BYTES) carry no
+ * zone map here (their entries are ignored) and are pruned by their filters only. */
+typedef struct kx_stats kx_stats;
+int  kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,
+                     const uint64_t* mins, const uint64_t* maxs, kx_stats** out);
+void kx_stats_free(kx_stats* stats);
+/* attach a stored filter ([k][m/8 bytes], m a power of two: bloom.NewFilterBuffer, bloom.go:83-100); copies */
+int  kx_stats_put_bloom(kx_stats* stats, int field_index, int pack_index, const void* bloom, size_t len);
+/* stats.BuildBloomFilter (internal/pack/stats/filter.go:296-367) on the device: m = pow2(cardinality*factor*8)
+ * bits, k = 4, every value hashed with XXH3-64 (hash.Vec64/Vec32/Vec16/Vec8 for fixed-width types, hash.Hash
+ * for byte strings) and added (bloom.Filter.Add).  values: n elements of block_type in host memory; for
+ * KX_BYTES the concatenated strings with offsets[n+1]. The result is bit-identical to the reference's buffer. */
+int  kx_stats_build_bloom(kx_stats* stats, int field_index, int pack_index, uint8_t block_type, const void* values,
+                          const uint32_t* offsets, size_t n, int cardinality, int factor);
+/* read a filter back as [k][m/8 bytes] (to persist it like the reference does); out may be NULL to query len */
+int  kx_stats_get_bloom(kx_stats* stats, int field_index, int pack_index, void* out, size_t cap, size_t* len);
+/* kx_prune over the resident index: no per-pack host work, no uploads besides the probe hashes.  hashes /
+ * hash_off as in kx_prune; pass NULL/NULL to let the library hash the numeric EQ / IN operands itself
+ * (byte-string leaves then probe nothing).  out: ceil(npacks/8) bytes.  Returns the surviving packs. */
+int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* stats, const uint64_t* hashes, const uint32_t* hash_off,
+                       uint8_t* out);
 
 /* hash.Uint64/Uint32/Uint16/Uint8 and hash.Hash ([]byte) (internal/hash/hash.go:26,67-92,
  * xxh3.go:22-58): XXH3-64, seed 0.  Computed on the host side of the library (one hash per

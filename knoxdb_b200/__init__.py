@@ -6,7 +6,7 @@ the C ABI.  There is no CPU fallback — importing works on a CPU box (so the sy
 be checked), but every compute call needs a CUDA device and raises otherwise.
 """
 from .lib import (  # noqa: F401
-    KnoxError, Context, Program, Leaf, lib, library_path, ABI_SYMBOLS,
-    INT64, INT32, INT16, INT8, UINT64, UINT32, UINT16, UINT8, FLOAT64, FLOAT32,
+    KnoxError, Context, Program, Leaf, Stats, lib, library_path, ABI_SYMBOLS,
+    INT64, INT32, INT16, INT8, UINT64, UINT32, UINT16, UINT8, FLOAT64, FLOAT32, BYTES,
     EQ, NE, GT, GE, LT, LE, IN, NIN, RANGE, OP_AND, OP_OR,
 )

@@ -90,6 +90,7 @@ struct kx_prog {
     uint32_t tab_off[MAX_LEAVES] = {0};
     uint8_t tab_log2[MAX_LEAVES] = {0};
     const uint64_t* dev_tabs = nullptr;
+    bool prune_only = false;             // has a byte-string leaf: usable with kx_prune* only
 };
 
 struct kx_ctx {
@@ -106,11 +107,27 @@ struct kx_ctx {
     size_t store_enc_bytes = 0, store_dev_bytes = 0;
 
     // scratch (grow only)
-    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_codebits;
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_codebits, d_leafbits;
     PinBuf h_desc, h_res, h_aux;
 
     double last_kernel_ms = 0, last_total_ms = 0;
     int last_launches = 0;
+};
+
+// device-resident statistics index (zone maps + bloom filters), see include/knoxgpu.h
+struct kx_stats {
+    kx_ctx* ctx = nullptr;
+    int npacks = 0, nfields = 0;
+    std::vector<uint16_t> fields;
+    std::vector<uint8_t> types;
+    uint64_t* d_mins = nullptr;            // [nfields][npacks]
+    uint64_t* d_maxs = nullptr;
+    std::vector<uint64_t> h_bloom_ptr;     // [nfields][npacks] device address of the bit array, 0 = none
+    std::vector<uint32_t> h_bloom_mask;
+    std::vector<uint8_t> h_bloom_k;
+    uint8_t* d_tab = nullptr;              // ptr | mask | k tables on the device
+    bool dirty = true;
+    std::vector<std::pair<int, size_t>> allocs;   // slab allocations of the bit arrays
 };
 
 namespace {
@@ -230,6 +247,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // translate every leaf for every pack; the widest staged bits/row over all packs decides the tile
     std::vector<PackLeaf> pl(size_t(npacks) * size_t(nleaves));
     std::vector<CodesetJob> cjobs;
+    std::vector<RunFillJob> rjobs;
+    std::vector<size_t> rjob_leaf;     // index into pl of each run-fill job
+    size_t leafbits_bytes = 0;
+    uint32_t max_runs = 0;
     uint32_t max_stage_bits = 0, code_words = 0;
     bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
     uint64_t total_rows = 0;
@@ -246,6 +267,15 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0});
                 o.a = code_words;
                 code_words += (v.naux + 31u) / 32u;
+            }
+            if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
+                // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
+                rjobs.push_back(RunFillJob{v.data, v.aux, o.a, o.d, o.wm, leafbits_bytes, v.naux, v.n, o.mode == LM_SET ? 1u : 0u, 0});
+                rjob_leaf.push_back(size_t(p) * nleaves + l);
+                leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
+                max_runs = std::max(max_runs, v.naux);
+                o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
+                bits += 1;
             }
             bits += uint32_t(leaf_stage_width(o));
             if (o.mode != LM_RANGE32 && o.mode != LM_NONE && o.mode != LM_ALL) only32 = false;
@@ -298,7 +328,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     const uint32_t ntiles = uint32_t(ntiles64);
     size_t sz_tiles = uniform ? 0 : sizeof(uint32_t) * size_t(ntiles);
     size_t off_cjobs = off_tiles + round_up(sz_tiles, 256);
-    size_t desc_bytes = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
+    size_t off_rjobs = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
+    size_t desc_bytes = off_rjobs + round_up(sizeof(RunFillJob) * rjobs.size(), 256);
+    if (!rjobs.empty()) {
+        CK(ctx->d_leafbits.reserve(leafbits_bytes));
+        for (size_t i = 0; i < rjobs.size(); ++i) pl[rjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + rjobs[i].out_off;
+    }
 
     CK(ctx->h_desc.reserve(desc_bytes));
     CK(ctx->d_packs.reserve(desc_bytes));
@@ -322,6 +357,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     }
 
     if (!cjobs.empty()) std::memcpy(hd + off_cjobs, cjobs.data(), sizeof(CodesetJob) * cjobs.size());
+    if (!rjobs.empty()) std::memcpy(hd + off_rjobs, rjobs.data(), sizeof(RunFillJob) * rjobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
     int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * geo.ctas));
@@ -366,6 +402,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * size_t(npacks), ctx->stream));
     if (naggs) CK(cudaMemcpyAsync(ctx->d_aggtype.p, P.agg_type, MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ntiles && !rjobs.empty()) {
+        CK(cudaMemsetAsync(ctx->d_leafbits.p, 0, leafbits_bytes, ctx->stream));
+        CK(launch_runfill(reinterpret_cast<const RunFillJob*>(dd + off_rjobs), uint32_t(rjobs.size()), max_runs, prog->dev_sets,
+                          static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
+        ctx->last_launches++;
+    }
     if (ntiles && !cjobs.empty()) {
         CK(launch_codeset(reinterpret_cast<const CodesetJob*>(dd + off_cjobs), uint32_t(cjobs.size()), prog->dev_sets,
                           static_cast<uint32_t*>(ctx->d_codebits.p), ctx->stream));
@@ -418,8 +460,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     return KX_OK;
 }
 
-int check_prog_job(kx_ctx* ctx, const kx_prog* prog) {
+int check_prog_job(kx_ctx* ctx, const kx_prog* prog, bool scan = false) {
     if (!prog || prog->ctx != ctx) return fail(ctx, KX_EINVAL, "program does not belong to this context");
+    if (scan && prog->prune_only) return fail(ctx, KX_EUNSUPPORTED, "programs with byte-string leaves can only be used for pruning");
     return KX_OK;
 }
 
@@ -464,6 +507,15 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
     for (int l = 0; l < nleaves; ++l) {
         const kx_leaf& in = leaves[l];
         LeafSpec s; s.field = in.field; s.type = in.block_type; s.mode = in.mode; s.a = in.a; s.b = in.b;
+        if (s.type == KX_BYTES) {
+            // byte-string columns take part in pruning only (bloom probes with caller-supplied hashes)
+            if (s.mode != KX_MODE_EQ && s.mode != KX_MODE_IN && s.mode != KX_MODE_NE && s.mode != KX_MODE_NIN)
+                return fail(ctx, KX_EUNSUPPORTED, "leaf: byte-string columns support EQ/NE/IN/NIN (pruning) only");
+            p->prune_only = true;
+            s.set_off = uint32_t(p->sets.size()); p->set_off[l] = s.set_off;
+            p->leaves.push_back(std::move(s));
+            continue;
+        }
         if (type_bits(s.type) == 0) return fail(ctx, KX_EINVAL, "leaf: unsupported block type");
         if (s.mode < KX_MODE_EQ || s.mode > KX_MODE_RANGE) return fail(ctx, KX_EINVAL, "leaf: unsupported filter mode");
         if (s.mode == KX_MODE_IN || s.mode == KX_MODE_NIN) {
@@ -623,7 +675,7 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    int rc = check_prog_job(ctx, prog);
+    int rc = check_prog_job(ctx, prog, true);
     if (rc) return rc;
     if (npacks < 0 || (npacks && !packs)) return fail(ctx, KX_EINVAL, "bad pack list");
     if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
@@ -658,7 +710,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
                  const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
-    int rc = check_prog_job(ctx, prog);
+    int rc = check_prog_job(ctx, prog, true);
     if (rc) return rc;
     if (npacks < 0 || nfields < 1 || !fields || !field_types || (npacks && (!blocks || !block_len))) return fail(ctx, KX_EINVAL, "bad block table");
     if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
@@ -1057,6 +1109,7 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* m
         pl.mode = s.mode; pl.is_float = type_is_float(s.type);
         pl.set_off = s.set_off; pl.nset = uint32_t(s.set.size());
         if (s.type == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_prune: float32 zone maps are not supported");
+        if (s.type == KX_BYTES) return fail(ctx, KX_EUNSUPPORTED, "kx_prune: byte-string columns need the resident index (kx_prune_stats)");
     }
     size_t nhash = 0;
     if (blooms) { for (int l = 0; l <= nleaves; ++l) P.hash_off[l] = hash_off[l]; nhash = hash_off[nleaves]; }
@@ -1100,6 +1153,209 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* m
     CK(cudaMemcpyAsync(out, d + off_out, (size_t(npacks) + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaMemcpyAsync(&c, d + off_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return int64_t(c);
+}
+
+// ------------------------------------------------------------------ resident statistics index
+static int bloom_pow2(size_t v) {   // bloom.pow2 (internal/filter/bloom/bloom.go:242-250)
+    for (size_t i = 8; i < (size_t(1) << 30); i *= 2) if (i >= v) return int(i);
+    return 0;
+}
+
+int kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,
+                    const uint64_t* mins, const uint64_t* maxs, kx_stats** out) {
+    if (!ctx || !out) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    *out = nullptr;
+    if (npacks < 1 || nfields < 1 || nfields > 255 || !fields || !field_types || !mins || !maxs) return fail(ctx, KX_EINVAL, "kx_stats_create: bad arguments");
+    for (int f = 0; f < nfields; ++f)
+        if (type_bits(field_types[f]) == 0 && field_types[f] != KX_BYTES) return fail(ctx, KX_EINVAL, "kx_stats_create: unsupported field type");
+    CK(cudaSetDevice(ctx->device));
+    auto st = std::make_unique<kx_stats>();
+    st->ctx = ctx; st->npacks = npacks; st->nfields = nfields;
+    st->fields.assign(fields, fields + nfields); st->types.assign(field_types, field_types + nfields);
+    const size_t cells = size_t(npacks) * nfields;
+    st->h_bloom_ptr.assign(cells, 0); st->h_bloom_mask.assign(cells, 0); st->h_bloom_k.assign(cells, 0);
+    CK(cudaMalloc(&st->d_mins, cells * 8));
+    CK(cudaMalloc(&st->d_maxs, cells * 8));
+    CK(cudaMalloc(&st->d_tab, cells * 13 + 64));
+    CK(cudaMemcpyAsync(st->d_mins, mins, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st->d_maxs, maxs, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    *out = st.release();
+    return KX_OK;
+}
+
+void kx_stats_free(kx_stats* st) {
+    if (!st) return;
+    kx_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto& a : st->allocs) { slab_release(ctx, a.first, a.second); ctx->store_dev_bytes -= round_up(a.second, 256); }
+    cudaFree(st->d_mins); cudaFree(st->d_maxs); cudaFree(st->d_tab);
+    delete st;
+}
+
+// allocate (or reuse) the bit array of one cell; m bits
+static int stats_bloom_slot(kx_stats* st, size_t cell, size_t m, uint32_t k, uint8_t** bits) {
+    kx_ctx* ctx = st->ctx;
+    if (st->h_bloom_ptr[cell] && st->h_bloom_mask[cell] == uint32_t(m - 1)) {
+        *bits = reinterpret_cast<uint8_t*>(uintptr_t(st->h_bloom_ptr[cell]));
+    } else {
+        uint8_t* d = nullptr; int si = 0;
+        int rc = slab_alloc(ctx, m / 8 + 64, &d, &si);
+        if (rc) return rc;
+        st->allocs.push_back({si, m / 8 + 64});
+        ctx->store_dev_bytes += round_up(m / 8 + 64, 256);
+        *bits = d;
+    }
+    st->h_bloom_ptr[cell] = uint64_t(uintptr_t(*bits)); st->h_bloom_mask[cell] = uint32_t(m - 1); st->h_bloom_k[cell] = uint8_t(k);
+    st->dirty = true;
+    return KX_OK;
+}
+
+int kx_stats_put_bloom(kx_stats* st, int field_index, int pack_index, const void* bloom, size_t len) {
+    if (!st) return KX_EINVAL;
+    kx_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (field_index < 0 || field_index >= st->nfields || pack_index < 0 || pack_index >= st->npacks || !bloom || len < 2)
+        return fail(ctx, KX_EINVAL, "kx_stats_put_bloom: bad arguments");
+    size_t m = (len - 1) * 8;
+    if ((m & (m - 1)) || m < 8) return fail(ctx, KX_EFORMAT, "kx_stats_put_bloom: bit count must be a power of two (bloom.NewFilterBuffer)");
+    CK(cudaSetDevice(ctx->device));
+    const uint8_t* b = static_cast<const uint8_t*>(bloom);
+    uint8_t* bits = nullptr;
+    int rc = stats_bloom_slot(st, size_t(field_index) * st->npacks + pack_index, m, b[0], &bits);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(bits, b + 1, len - 1, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // the caller's buffer is not retained
+    return KX_OK;
+}
+
+int kx_stats_build_bloom(kx_stats* st, int field_index, int pack_index, uint8_t block_type, const void* values, const uint32_t* offsets,
+                         size_t n, int cardinality, int factor) {
+    if (!st) return KX_EINVAL;
+    kx_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (field_index < 0 || field_index >= st->nfields || pack_index < 0 || pack_index >= st->npacks || (n && !values))
+        return fail(ctx, KX_EINVAL, "kx_stats_build_bloom: bad arguments");
+    int eb = block_type == KX_BYTES ? 0 : type_bits(block_type) / 8;
+    if (block_type != KX_BYTES && eb == 0) return fail(ctx, KX_EINVAL, "kx_stats_build_bloom: unsupported value type");
+    if (block_type == KX_BYTES && n && !offsets) return fail(ctx, KX_EINVAL, "kx_stats_build_bloom: byte strings need offsets");
+    if (cardinality <= 0 || factor <= 0) return fail(ctx, KX_EINVAL, "kx_stats_build_bloom: cardinality and factor must be positive");   // BuildBloomFilter returns nil
+    size_t m = size_t(bloom_pow2(size_t(cardinality) * size_t(factor) * 8));
+    if (!m) return fail(ctx, KX_EINVAL, "kx_stats_build_bloom: filter too large");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* bits = nullptr;
+    int rc = stats_bloom_slot(st, size_t(field_index) * st->npacks + pack_index, m, 4, &bits);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(bits, 0, m / 8, ctx->stream));
+    size_t vbytes = eb ? n * size_t(eb) : (n ? size_t(offsets[n]) : 0), obytes = eb ? 0 : (n + 1) * 4;
+    CK(ctx->d_tmp.reserve(round_up(vbytes, 16) + obytes + 64));
+    uint8_t* dv = static_cast<uint8_t*>(ctx->d_tmp.p);
+    uint32_t* doff = reinterpret_cast<uint32_t*>(dv + round_up(vbytes, 16));
+    if (vbytes) CK(cudaMemcpyAsync(dv, values, vbytes, cudaMemcpyHostToDevice, ctx->stream));
+    if (obytes) CK(cudaMemcpyAsync(doff, offsets, obytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_bloom_build(dv, eb ? nullptr : doff, n, eb, reinterpret_cast<uint32_t*>(bits), uint32_t(m - 1), 4, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // host buffers are not retained
+    return KX_OK;
+}
+
+int kx_stats_get_bloom(kx_stats* st, int field_index, int pack_index, void* out, size_t cap, size_t* len) {
+    if (!st) return KX_EINVAL;
+    kx_ctx* ctx = st->ctx;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (field_index < 0 || field_index >= st->nfields || pack_index < 0 || pack_index >= st->npacks || !len)
+        return fail(ctx, KX_EINVAL, "kx_stats_get_bloom: bad arguments");
+    size_t cell = size_t(field_index) * st->npacks + pack_index;
+    if (!st->h_bloom_ptr[cell]) { *len = 0; return KX_OK; }
+    size_t need = 1 + (size_t(st->h_bloom_mask[cell]) + 1) / 8;
+    *len = need;
+    if (!out) return KX_OK;
+    if (cap < need) return fail(ctx, KX_EINVAL, "kx_stats_get_bloom: buffer too small");
+    CK(cudaSetDevice(ctx->device));
+    uint8_t* o = static_cast<uint8_t*>(out);
+    o[0] = st->h_bloom_k[cell];
+    CK(cudaMemcpyAsync(o + 1, reinterpret_cast<const void*>(uintptr_t(st->h_bloom_ptr[cell])), need - 1, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KX_OK;
+}
+
+int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* st, const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog);
+    if (rc) return rc;
+    if (!st || st->ctx != ctx || !out) return fail(ctx, KX_EINVAL, "kx_prune_stats: bad arguments");
+    if ((hashes == nullptr) != (hash_off == nullptr)) return fail(ctx, KX_EINVAL, "kx_prune_stats: hashes and hash_off go together");
+    if (cudaSetDevice(ctx->device) != cudaSuccess) return fail(ctx, KX_ECUDA, "cudaSetDevice");
+    const int nleaves = int(prog->leaves.size()), npacks = st->npacks;
+    const size_t cells = size_t(npacks) * st->nfields;
+
+    PruneStatsParams P{};
+    P.npacks = uint32_t(npacks); P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size());
+    std::memcpy(P.postfix, prog->postfix.data(), prog->postfix.size());
+    std::vector<uint64_t> own_hashes;
+    for (int l = 0; l < nleaves; ++l) {
+        const LeafSpec& s = prog->leaves[size_t(l)];
+        int fi = -1;
+        for (int f = 0; f < st->nfields; ++f) if (st->fields[size_t(f)] == s.field) { fi = f; break; }
+        if (fi < 0) return fail(ctx, KX_ENOTFOUND, "kx_prune_stats: leaf field has no statistics column");
+        if (st->types[size_t(fi)] != s.type) return fail(ctx, KX_EINVAL, "kx_prune_stats: leaf / statistics type mismatch");
+        if (s.type == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_prune_stats: float32 zone maps are not supported");
+        P.leaf_field[l] = uint8_t(fi);
+        P.leaf_nozone[l] = s.type == KX_BYTES;
+        PruneLeaf& pl = P.leaves[l];
+        pl.a = type_is_float(s.type) ? s.a : type_ext(s.type, s.a);
+        pl.b = type_is_float(s.type) ? s.b : type_ext(s.type, s.b);
+        pl.flip = type_is_signed(s.type) ? 0x8000000000000000ull : 0;
+        pl.mode = s.mode; pl.is_float = type_is_float(s.type);
+        pl.set_off = s.set_off; pl.nset = uint32_t(s.set.size());
+        if (hashes) { P.hash_off[l] = hash_off[l]; continue; }
+        // probe hashes of numeric EQ / IN operands: hash.HashT(v) (internal/hash/hash.go:67-92)
+        P.hash_off[l] = uint32_t(own_hashes.size());
+        if (s.type != KX_BYTES && s.mode == KX_MODE_EQ) own_hashes.push_back(kx_hash_value(s.type, pl.a));
+        if (s.type != KX_BYTES && s.mode == KX_MODE_IN) for (uint64_t v : s.set) own_hashes.push_back(kx_hash_value(s.type, v));
+    }
+    P.hash_off[nleaves] = hashes ? hash_off[nleaves] : uint32_t(own_hashes.size());
+    const uint64_t* hsrc = hashes ? hashes : own_hashes.data();
+    const size_t nhash = P.hash_off[nleaves];
+
+    if (st->dirty) {   // (re)upload the filter tables after put/build calls
+        CK(cudaMemcpyAsync(st->d_tab, st->h_bloom_ptr.data(), cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(st->d_tab + cells * 8, st->h_bloom_mask.data(), cells * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(st->d_tab + cells * 12, st->h_bloom_k.data(), cells, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        st->dirty = false;
+    }
+    size_t out_words = (size_t(npacks) + 31) / 32;
+    size_t off_out = round_up(nhash * 8, 8), off_cnt = round_up(off_out + out_words * 4, 8);
+    CK(ctx->d_misc.reserve(off_cnt + 64));
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_misc.p);
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    if (nhash) CK(cudaMemcpyAsync(d, hsrc, nhash * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemsetAsync(d + off_out, 0, off_cnt + 8 - off_out, ctx->stream));
+    P.mins = st->d_mins; P.maxs = st->d_maxs;
+    P.bloom_ptr = reinterpret_cast<const uint64_t*>(st->d_tab);
+    P.bloom_mask = reinterpret_cast<const uint32_t*>(st->d_tab + cells * 8);
+    P.bloom_k = st->d_tab + cells * 12;
+    P.hashes = reinterpret_cast<const uint64_t*>(d);
+    P.set_vals = prog->dev_sets;
+    P.out = reinterpret_cast<uint32_t*>(d + off_out);
+    P.count = reinterpret_cast<unsigned long long*>(d + off_cnt);
+    CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    CK(launch_prune_stats(P, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    unsigned long long c = 0;
+    CK(cudaMemcpyAsync(out, d + off_out, (size_t(npacks) + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&c, d + off_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1) == cudaSuccess) ctx->last_kernel_ms = ms;
+    if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end) == cudaSuccess) ctx->last_total_ms = ms;
+    ctx->last_launches = 1;
     return int64_t(c);
 }
 

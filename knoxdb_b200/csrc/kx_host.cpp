@@ -6,6 +6,7 @@
 //   leaf translation   internal/encode/int_bitpack.go:163-247, int_delta.go:149-449, int_dict.go:181-359,
 //                      int_const.go:133-173, internal/cmp/number.go:13-243
 #include "kx_host.h"
+#include "kx_xxh3.h"
 
 #include <algorithm>
 #include <cstring>
@@ -693,90 +694,11 @@ void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& l
 }
 
 // ---------------------------------------------------------------------------------- XXH3-64
-namespace {
-constexpr uint64_t P32_1 = 0x9E3779B1ull, P32_2 = 0x85EBCA77ull, P32_3 = 0xC2B2AE3Dull;
-constexpr uint64_t P64_1 = 0x9E3779B185EBCA87ull, P64_2 = 0xC2B2AE3D27D4EB4Full, P64_3 = 0x165667B19E3779F9ull,
-                   P64_4 = 0x85EBCA77C2B2AE63ull, P64_5 = 0x27D4EB2F165667C5ull;
-// default XXH3 secret (xxHash v0.8); the reference's key64_008 / key64_016 / key32_* constants
-// (internal/hash/xxh3.go:11-20) are the little-endian words at offsets 8, 16, 0 and 4 of it
-const uint8_t SECRET[192] = {
-    0xb8, 0xfe, 0x6c, 0x39, 0x23, 0xa4, 0x4b, 0xbe, 0x7c, 0x01, 0x81, 0x2c, 0xf7, 0x21, 0xad, 0x1c,
-    0xde, 0xd4, 0x6d, 0xe9, 0x83, 0x90, 0x97, 0xdb, 0x72, 0x40, 0xa4, 0xa4, 0xb7, 0xb3, 0x67, 0x1f,
-    0xcb, 0x79, 0xe6, 0x4e, 0xcc, 0xc0, 0xe5, 0x78, 0x82, 0x5a, 0xd0, 0x7d, 0xcc, 0xff, 0x72, 0x21,
-    0xb8, 0x08, 0x46, 0x74, 0xf7, 0x43, 0x24, 0x8e, 0xe0, 0x35, 0x90, 0xe6, 0x81, 0x3a, 0x26, 0x4c,
-    0x3c, 0x28, 0x52, 0xbb, 0x91, 0xc3, 0x00, 0xcb, 0x88, 0xd0, 0x65, 0x8b, 0x1b, 0x53, 0x2e, 0xa3,
-    0x71, 0x64, 0x48, 0x97, 0xa2, 0x0d, 0xf9, 0x4e, 0x38, 0x19, 0xef, 0x46, 0xa9, 0xde, 0xac, 0xd8,
-    0xa8, 0xfa, 0x76, 0x3f, 0xe3, 0x9c, 0x34, 0x3f, 0xf9, 0xdc, 0xbb, 0xc7, 0xc7, 0x0b, 0x4f, 0x1d,
-    0x8a, 0x51, 0xe0, 0x4b, 0xcd, 0xb4, 0x59, 0x31, 0xc8, 0x9f, 0x7e, 0xc9, 0xd9, 0x78, 0x73, 0x64,
-    0xea, 0xc5, 0xac, 0x83, 0x34, 0xd3, 0xeb, 0xc3, 0xc5, 0x81, 0xa0, 0xff, 0xfa, 0x13, 0x63, 0xeb,
-    0x17, 0x0d, 0xdd, 0x51, 0xb7, 0xf0, 0xda, 0x49, 0xd3, 0x16, 0x55, 0x26, 0x29, 0xd4, 0x68, 0x9e,
-    0x2b, 0x16, 0xbe, 0x58, 0x7d, 0x47, 0xa1, 0xfc, 0x8f, 0xf8, 0xb8, 0xd1, 0x7a, 0xd0, 0x31, 0xce,
-    0x45, 0xcb, 0x3a, 0x8f, 0x95, 0x16, 0x04, 0x28, 0xaf, 0xd7, 0xfb, 0xca, 0xbb, 0x4b, 0x40, 0x7e,
-};
-inline uint64_t r64(const uint8_t* p) { uint64_t v; std::memcpy(&v, p, 8); return v; }
-inline uint32_t r32(const uint8_t* p) { uint32_t v; std::memcpy(&v, p, 4); return v; }
-inline uint64_t rotl(uint64_t x, int r) { return (x << r) | (x >> (64 - r)); }
-inline uint64_t fold(uint64_t a, uint64_t b) { unsigned __int128 m = (unsigned __int128)a * b; return uint64_t(m) ^ uint64_t(m >> 64); }
-inline uint64_t aval64(uint64_t h) { h ^= h >> 33; h *= P64_2; h ^= h >> 29; h *= P64_3; h ^= h >> 32; return h; }
-inline uint64_t aval3(uint64_t h) { h ^= h >> 37; h *= 0x165667919E3779F9ull; h ^= h >> 32; return h; }
-inline uint64_t rrmxmx(uint64_t h, uint64_t len) {
-    h ^= rotl(h, 49) ^ rotl(h, 24); h *= 0x9FB21C651E98DF25ull; h ^= (h >> 35) + len; h *= 0x9FB21C651E98DF25ull;
-    return h ^ (h >> 28);
-}
-inline uint64_t mix(const uint8_t* in, const uint8_t* s) { return fold(r64(in) ^ r64(s), r64(in + 8) ^ r64(s + 8)); }
-void stripe(uint64_t* acc, const uint8_t* in, const uint8_t* s) {
-    for (int i = 0; i < 8; i++) {
-        uint64_t v = r64(in + 8 * i), k = v ^ r64(s + 8 * i);
-        acc[i ^ 1] += v; acc[i] += uint64_t(uint32_t(k)) * (k >> 32);
-    }
-}
-}  // namespace
-
-uint64_t xxh3_bytes(const uint8_t* in, size_t len) {
-    const uint8_t* s = SECRET;
-    if (len == 0) return aval64(r64(s + 56) ^ r64(s + 64));
-    if (len < 4) {
-        uint32_t c = (uint32_t(in[0]) << 16) | (uint32_t(in[len >> 1]) << 24) | in[len - 1] | (uint32_t(len) << 8);
-        return aval64(uint64_t(c) ^ uint64_t(r32(s) ^ r32(s + 4)));
-    }
-    if (len <= 8) return rrmxmx((uint64_t(r32(in + len - 4)) + (uint64_t(r32(in)) << 32)) ^ (r64(s + 8) ^ r64(s + 16)), len);
-    if (len <= 16) {
-        uint64_t lo = r64(in) ^ (r64(s + 24) ^ r64(s + 32)), hi = r64(in + len - 8) ^ (r64(s + 40) ^ r64(s + 48));
-        return aval3(len + __builtin_bswap64(lo) + hi + fold(lo, hi));
-    }
-    if (len <= 128) {
-        uint64_t acc = len * P64_1;
-        size_t pairs = (len - 1) / 32;   // 0..3 extra (front, back) pairs beyond the outermost one
-        for (size_t i = pairs; i > 0; i--) { acc += mix(in + 16 * i, s + 32 * i); acc += mix(in + len - 16 * (i + 1), s + 32 * i + 16); }
-        acc += mix(in, s); acc += mix(in + len - 16, s + 16);
-        return aval3(acc);
-    }
-    if (len <= 240) {
-        uint64_t acc = len * P64_1;
-        for (size_t i = 0; i < 8; i++) acc += mix(in + 16 * i, s + 16 * i);
-        acc = aval3(acc);
-        for (size_t i = 8; i < len / 16; i++) acc += mix(in + 16 * i, s + 16 * (i - 8) + 3);
-        acc += mix(in + len - 16, s + 119);
-        return aval3(acc);
-    }
-    uint64_t acc[8] = {P32_3, P64_1, P64_2, P64_3, P64_4, P32_2, P64_5, P32_1};
-    const size_t per_block = 16, block = per_block * 64;
-    size_t nblocks = (len - 1) / block;
-    for (size_t b = 0; b < nblocks; b++) {
-        for (size_t k = 0; k < per_block; k++) stripe(acc, in + b * block + k * 64, s + 8 * k);
-        for (int i = 0; i < 8; i++) { uint64_t x = acc[i]; x ^= x >> 47; x ^= r64(s + 128 + 8 * i); acc[i] = x * P32_1; }
-    }
-    size_t tail = ((len - 1) - nblocks * block) / 64;
-    for (size_t k = 0; k < tail; k++) stripe(acc, in + nblocks * block + k * 64, s + 8 * k);
-    stripe(acc, in + len - 64, s + 121);
-    uint64_t h = len * P64_1;
-    for (int i = 0; i < 4; i++) h += fold(acc[2 * i] ^ r64(s + 11 + 16 * i), acc[2 * i + 1] ^ r64(s + 19 + 16 * i));
-    return aval3(h);
-}
-
-uint64_t xxh3_u64(uint64_t v) { uint8_t b[8]; std::memcpy(b, &v, 8); return xxh3_bytes(b, 8); }
-uint64_t xxh3_u32(uint32_t v) { uint8_t b[4]; std::memcpy(b, &v, 4); return xxh3_bytes(b, 4); }
-uint64_t xxh3_u16(uint16_t v) { uint8_t b[2]; std::memcpy(b, &v, 2); return xxh3_bytes(b, 2); }
-uint64_t xxh3_u8(uint8_t v) { return xxh3_bytes(&v, 1); }
+// one implementation for host and device: kx_xxh3.h
+uint64_t xxh3_bytes(const uint8_t* in, size_t len) { return xxh3::bytes(in, len); }
+uint64_t xxh3_u64(uint64_t v) { return xxh3::u64(v); }
+uint64_t xxh3_u32(uint32_t v) { return xxh3::u32(v); }
+uint64_t xxh3_u16(uint16_t v) { return xxh3::u16(v); }
+uint64_t xxh3_u8(uint8_t v) { return xxh3::u8(v); }
 
 }  // namespace kx

@@ -38,9 +38,43 @@ struct CodesetJob {
     uint32_t pad;
 };
 
+// one run-end leaf of runfill_kernel: runs whose value satisfies the predicate set rows [start, end] of the
+// leaf bitset at out_base + out_off (zeroed before the launch)
+struct RunFillJob {
+    const uint8_t* vals;   // u64 run values
+    const uint8_t* ends;   // u32 inclusive run ends
+    uint64_t a, d, wm;     // LM_VALRANGE operands, or (set offset, set size) for LM_SET
+    uint64_t out_off;      // byte offset of the leaf bitset
+    uint32_t nruns, nrows;
+    uint32_t is_set, pad;
+};
+
 constexpr size_t SCAN_MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the scan kernel may ask for
 
+// pruning over a device-resident statistics index (kx_stats): statistics are column-major [field][pack]
+struct PruneStatsParams {
+    const uint64_t* mins;
+    const uint64_t* maxs;
+    const uint64_t* bloom_ptr;     // [field][pack] device address of the filter's bit array, 0 = none
+    const uint32_t* bloom_mask;    // m - 1
+    const uint8_t*  bloom_k;
+    const uint64_t* hashes;        // concatenated probe hashes
+    const uint64_t* set_vals;      // concatenated sorted IN sets
+    uint32_t* out;                 // ceil(npacks/32) words
+    unsigned long long* count;
+    uint32_t npacks, nleaves, npost;
+    uint32_t hash_off[MAX_LEAVES + 1];
+    uint8_t  leaf_field[MAX_LEAVES];   // index of the leaf's column in the index
+    uint8_t  leaf_nozone[MAX_LEAVES];  // column carries no zone map (byte strings): filter only
+    PruneLeaf leaves[MAX_LEAVES];
+    uint8_t postfix[MAX_POSTFIX];
+};
+cudaError_t launch_prune_stats(const PruneStatsParams& P, cudaStream_t stream);
+cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, uint64_t n, int elem_bytes, uint32_t* bits, uint32_t mask,
+                               uint32_t k, cudaStream_t stream);
+
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,
                             AggPartial* out, cudaStream_t stream);

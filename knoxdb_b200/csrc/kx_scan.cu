@@ -491,6 +491,94 @@ __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) 
     }
 }
 
+// One pass (<= 32 groups of 32 rows) of the fused reduce for ONE value column.  `word` is the pass's
+// match bitset in word-per-lane form; group `it`'s word is broadcast with a shuffle and lane l reduces
+// row 32*it + l, so every load instruction reads 32 consecutive values (coalesced).  The loads of B
+// groups are issued back to back before they are consumed (memory-level parallelism); batches without
+// a match cost four shuffles.
+template <bool F64>
+__device__ __forceinline__ void agg_pass_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, uint32_t word, uint32_t Rp, uint32_t lane,
+                                               uint64_t base, uint64_t flip) {
+    constexpr int B = 8;
+    for (uint32_t it0 = 0; it0 < Rp; it0 += B) {
+        uint32_t wd[B], anyw = 0;
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
+            if (it0 + u >= Rp) wd[u] = 0;
+            anyw |= wd[u];
+        }
+        if (anyw == 0) continue;
+        uint64_t val[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) val[u] = ((wd[u] >> lane) & 1u) ? __ldg(vp + (size_t)(it0 + u) * 32u) : 0ull;
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            if ((wd[u] >> lane) & 1u) {
+                if (F64) {
+                    double x = as_f64(val[u]), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
+                    double t = sum + x;
+                    err += (fabs(sum) >= fabs(x)) ? ((sum - t) + x) : ((x - t) + sum);
+                    A.s[0] = as_u64(t); A.s[1] = as_u64(err);
+                    if (x < as_f64(A.s[2])) A.s[2] = val[u];
+                    if (x > as_f64(A.s[3])) A.s[3] = val[u];
+                } else {
+                    uint64_t v = val[u] + base, k = v ^ flip;
+                    A.s[0] += v;
+                    if (k < A.s[1]) A.s[1] = k;
+                    if (k > A.s[2]) A.s[2] = k;
+                }
+            }
+        }
+    }
+}
+
+// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types): decode per row
+__device__ __forceinline__ void agg_pass_generic(AggAcc& A, const ColView& v, int type, uint32_t row_base, uint32_t word, uint32_t Rp, uint32_t lane) {
+    constexpr int B = 4;
+    for (uint32_t it0 = 0; it0 < Rp; it0 += B) {
+        uint32_t wd[B], anyw = 0;
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
+            if (it0 + u >= Rp) wd[u] = 0;
+            anyw |= wd[u];
+        }
+        if (anyw == 0) continue;
+        uint64_t val[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+            if ((wd[u] >> lane) & 1u) val[u] = decode_value(v, row_base + (it0 + u) * 32u, nullptr, 0);
+#pragma unroll
+        for (int u = 0; u < B; ++u)
+            if ((wd[u] >> lane) & 1u) agg_add(A, type, val[u]);
+    }
+}
+
+// Run-end blocks: the predicate is evaluated once per RUN by this pre-pass (RunEndContainer.Match* +
+// applyMatch, internal/encode/int_runend.go:224-318: match the run values, SetRange(start, end) per
+// matching run); the scan kernel then streams the resulting per-leaf bitset like a 1-bit column.
+__global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, const uint64_t* __restrict__ set_vals, uint8_t* __restrict__ out_base) {
+    const RunFillJob J = jobs[blockIdx.y];
+    const uint32_t* ends = reinterpret_cast<const uint32_t*>(J.ends);
+    const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(J.vals);
+    uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < J.nruns; k += gridDim.x * blockDim.x) {
+        uint64_t val = __ldg(vals + k);
+        bool p = J.is_set ? set_has(set_vals + J.a, (uint32_t)J.d, val) : ((val ^ J.wm) - J.a) <= J.d;
+        if (!p) continue;
+        uint32_t start = k ? __ldg(ends + k - 1) + 1u : 0u, end = __ldg(ends + k);   // inclusive
+        if (end >= J.nrows) end = J.nrows - 1u;
+        if (start > end) continue;
+        uint32_t w0 = start >> 5, w1 = end >> 5;
+        uint32_t m0 = 0xffffffffu << (start & 31u), m1 = 0xffffffffu >> (31u - (end & 31u));
+        if (w0 == w1) { atomicOr(out + w0, m0 & m1); continue; }
+        atomicOr(out + w0, m0);
+        for (uint32_t w = w0 + 1; w < w1; ++w) out[w] = 0xffffffffu;   // words owned by this run alone
+        atomicOr(out + w1, m1);
+    }
+}
+
 // ------------------------------------------------------------------------------ the kernel
 // first pack whose tile range contains tile t (packs with zero tiles are skipped)
 __device__ __forceinline__ uint32_t pack_of_tile(const PackInfo* __restrict__ packs, uint32_t npacks, uint32_t t) {
@@ -501,8 +589,6 @@ __device__ __forceinline__ uint32_t pack_of_tile(const PackInfo* __restrict__ pa
     }
     return lo;
 }
-
-constexpr int AGG_BATCH = 4;   // 32-row groups whose value loads are issued back to back
 
 // SIMPLE = one leaf, no aggregates: the hot configuration (fused decode + compare + popcount).
 // ONLY32 (with SIMPLE) = every pack's leaf is a <= 32-bit packed range test (or all / none): a lean
@@ -633,6 +719,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                     }
                     break;
                 }
+                case LM_BITS: word = lane < Rp ? sw[g0 + lane] : 0u; break;   // precomputed leaf bitset (run-end pre-pass)
                 case LM_CODESET:
                     word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, P.code_bits + lf.a, (uint32_t)lf.d);
                     break;
@@ -690,37 +777,24 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
             lane_cnt += __popc(word);
 
-            // fused reduce over the matching rows of the value columns, read on demand: the loads of
-            // AGG_BATCH groups are issued back to back (memory-level parallelism), groups without a
-            // match cost nothing
+            // fused reduce over the matching rows of the value columns, read on demand from global memory
+            // (32-row groups without a match are never touched)
             if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
                 const uint32_t row_base = pack_row0 + g0 * 32u + lane;
-                for (uint32_t it0 = 0; it0 < Rp; it0 += AGG_BATCH) {
-                    uint32_t wd[AGG_BATCH], anyw = 0;
-#pragma unroll
-                    for (int u = 0; u < AGG_BATCH; ++u) {
-                        wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
-                        if (it0 + u >= Rp) wd[u] = 0;
-                        anyw |= wd[u];
+                for (uint32_t j = 0; j < P.naggs; ++j) {
+                    const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                    const int type = P.agg_type[j];
+                    AggAcc a = acc[SIMPLE ? 0 : j];
+                    if (v.kind == CK_BITS && v.width == 64) {
+                        const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + row_base;
+                        if (type == 9) agg_pass_raw64<true>(a, vp, word, Rp, lane, 0ull, 0ull);
+                        else agg_pass_raw64<false>(a, vp, word, Rp, lane, v.base, type_is_signed(type) ? 0x8000000000000000ull : 0ull);
+                    } else {
+                        agg_pass_generic(a, v, type, row_base, word, Rp, lane);
                     }
-                    if (anyw == 0) continue;
-#pragma unroll
-                    for (int j = 0; j < MAX_AGGS; ++j) {
-                        if (j < (int)P.naggs) {
-                            const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
-                            const int type = P.agg_type[j];
-                            uint64_t val[AGG_BATCH];
-#pragma unroll
-                            for (int u = 0; u < AGG_BATCH; ++u)
-                                if ((wd[u] >> lane) & 1u) val[u] = decode_value(v, row_base + (it0 + u) * 32u, nullptr, 0);
-#pragma unroll
-                            for (int u = 0; u < AGG_BATCH; ++u)
-                                if ((wd[u] >> lane) & 1u) agg_add(acc[SIMPLE ? 0 : j], type, val[u]);
-                        }
-                    }
-#pragma unroll
-                    for (int u = 0; u < AGG_BATCH; ++u) nmatch += (wd[u] >> lane) & 1u;
+                    acc[SIMPLE ? 0 : j] = a;
                 }
+                nmatch += __popc(word);   // per-CTA totals only: any partition of the matches over threads will do
             }
         }
 
@@ -1023,6 +1097,14 @@ cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool o
         if (dev >= 0 && dev < 64) configured[dev][variant] = true;
     }
     kern<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream) {
+    if (njobs == 0 || max_runs == 0) return cudaSuccess;
+    uint32_t gx = (max_runs + 255u) / 256u;
+    if (gx > 148u * 4u) gx = 148u * 4u;
+    runfill_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs, set_vals, out_base);
     return cudaGetLastError();
 }
 

@@ -54,6 +54,8 @@ enum LeafMode : uint8_t {
     LM_CODESET = 8,   // staged dictionary codes: bit (field + wm) of the pack's code bitmap at code_bits + a
                       // (d = number of codes); the bitmap is built on the device per (pack, leaf) and query
     LM_HASHSET = 9,   // staged integer stream: T(field + base) looked up in the leaf's bucketised hash table
+    LM_BITS = 10,     // staged stream IS the leaf's bitset, 1 bit per row (run-end blocks: filled per run by
+                      // runfill_kernel right before the scan)
 };
 
 struct PackLeaf {

@@ -7,6 +7,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 INT64, INT32, INT16, INT8, UINT64, UINT32, UINT16, UINT8, FLOAT64, FLOAT32 = range(1, 11)
+BYTES = 12
 EQ, NE, GT, GE, LT, LE, IN, NIN, RANGE = range(1, 10)
 OP_AND, OP_OR = 0xFE, 0xFF
 NP = {INT64: np.int64, INT32: np.int32, INT16: np.int16, INT8: np.int8, UINT64: np.uint64, UINT32: np.uint32,
@@ -18,6 +19,7 @@ ABI_SYMBOLS = [
     "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
     "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
     "kx_hash_value", "kx_hash_bytes",
+    "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
 ]
 
 
@@ -96,6 +98,12 @@ def lib():
         "kx_bitset_popcount": (C.c_int64, [vp, vp, sz]),
         "kx_bitset_indexes": (C.c_int64, [vp, vp, sz, vp]),
         "kx_prune": (C.c_int64, [vp, vp, C.c_int, vp, vp, vp, vp, vp, vp, vp]),
+        "kx_stats_create": (C.c_int, [vp, C.c_int, vp, vp, C.c_int, vp, vp, C.POINTER(vp)]),
+        "kx_stats_free": (None, [vp]),
+        "kx_stats_put_bloom": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
+        "kx_stats_build_bloom": (C.c_int, [vp, C.c_int, C.c_int, C.c_uint8, vp, vp, sz, C.c_int, C.c_int]),
+        "kx_stats_get_bloom": (C.c_int, [vp, C.c_int, C.c_int, vp, sz, C.POINTER(sz)]),
+        "kx_prune_stats": (C.c_int64, [vp, vp, vp, vp, vp, vp]),
         "kx_hash_value": (C.c_uint64, [C.c_uint8, C.c_uint64]),
         "kx_hash_bytes": (C.c_uint64, [vp, sz]),
     }
@@ -133,7 +141,7 @@ class Leaf:
 
     def __init__(self, field, block_type, mode, a=0, b=0, values=None):
         self.field, self.block_type, self.mode = field, block_type, mode
-        self.a, self.b = pattern(block_type, a), pattern(block_type, b)
+        self.a, self.b = (0, 0) if block_type == BYTES else (pattern(block_type, a), pattern(block_type, b))
         self.set = None
         if values is not None:
             arr = np.asarray(values)
@@ -366,3 +374,62 @@ class Context:
             ho = np.asarray(np.concatenate([[0], np.cumsum([len(hl) for hl in hashes])]), dtype=np.uint32)
         n = self._check(lib().kx_prune(self.h, prog.h, npacks, _ptr(mins), _ptr(maxs), bp, bl, _ptr(hs), _ptr(ho), _ptr(out)))
         return out[:(npacks + 7) // 8], n
+
+
+class Stats:
+    """kx_stats wrapper: device-resident statistics index (zone maps + bloom filters) of `npacks` data packs.
+    fields: [(field id, block type)]; mins / maxs: [nfields][npacks] uint64 patterns."""
+
+    def __init__(self, ctx, fields, mins, maxs):
+        self.ctx = ctx
+        mins = np.ascontiguousarray(mins, dtype=np.uint64)
+        maxs = np.ascontiguousarray(maxs, dtype=np.uint64)
+        self.nfields, self.npacks = mins.shape
+        fid = np.asarray([f for f, _ in fields], dtype=np.uint16)
+        fty = np.asarray([t for _, t in fields], dtype=np.uint8)
+        h = C.c_void_p()
+        ctx._check(lib().kx_stats_create(ctx.h, self.npacks, _ptr(fid), _ptr(fty), self.nfields, _ptr(mins), _ptr(maxs), C.byref(h)))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            lib().kx_stats_free(self.h)
+            self.h = None
+
+    def put_bloom(self, field_index, pack_index, buf):
+        buf = np.ascontiguousarray(buf, dtype=np.uint8)
+        self.ctx._check(lib().kx_stats_put_bloom(self.h, field_index, pack_index, _ptr(buf), buf.size))
+
+    def build_bloom(self, field_index, pack_index, block_type, values, cardinality, factor, offsets=None):
+        """values: numpy array of the block's type, or (BYTES) a uint8 array of concatenated strings + offsets[n+1]"""
+        if block_type == BYTES:
+            values = np.ascontiguousarray(values, dtype=np.uint8)
+            offsets = np.ascontiguousarray(offsets, dtype=np.uint32)
+            n = offsets.size - 1
+        else:
+            values = np.ascontiguousarray(values, dtype=NP[block_type])
+            n = values.size
+        self.ctx._check(lib().kx_stats_build_bloom(self.h, field_index, pack_index, block_type, _ptr(values), _ptr(offsets), n,
+                                                   int(cardinality), int(factor)))
+
+    def get_bloom(self, field_index, pack_index):
+        n = C.c_size_t()
+        self.ctx._check(lib().kx_stats_get_bloom(self.h, field_index, pack_index, None, 0, C.byref(n)))
+        if n.value == 0:
+            return None
+        out = np.zeros(n.value, dtype=np.uint8)
+        self.ctx._check(lib().kx_stats_get_bloom(self.h, field_index, pack_index, _ptr(out), out.size, C.byref(n)))
+        return out
+
+    def prune(self, prog, hashes=None):
+        """hashes: per leaf a list of probe hashes (None: the library hashes numeric EQ / IN operands itself).
+        Returns (bitset bytes over the packs, number of surviving packs)."""
+        out = np.zeros((self.npacks + 7) // 8 + 8, dtype=np.uint8)
+        hs = ho = None
+        if hashes is not None:
+            hs = np.asarray([h for hl in hashes for h in hl], dtype=np.uint64)
+            ho = np.asarray(np.concatenate([[0], np.cumsum([len(hl) for hl in hashes])]), dtype=np.uint32)
+            if hs.size == 0:
+                hs = np.zeros(1, dtype=np.uint64)
+        n = self.ctx._check(lib().kx_prune_stats(self.ctx.h, prog.h, self.h, _ptr(hs), _ptr(ho), _ptr(out)))
+        return out[:(self.npacks + 7) // 8], n

@@ -55,3 +55,27 @@ def allgather_partials(local_aggs, block_types, dist=None, device=None):
     dist.all_gather_into_tensor(t_all, t_mine)
     allb = t_all.cpu().numpy().reshape(world, n, 64)
     return [combine(block_types[j], [unpack_partial(allb[r, j]) for r in range(world)]) for j in range(n)]
+
+
+class PartialExchange:
+    """The one collective of a sharded query with every buffer preallocated: the per-rank 64 B partials go
+    host (pinned) -> device -> all_gather_into_tensor -> host (pinned) and are combined in rank order."""
+
+    def __init__(self, naggs, dist, device):
+        import torch
+        self.dist, self.n, self.world = dist, naggs, dist.get_world_size()
+        pin = device.type == "cuda"
+        self.h_mine = torch.zeros(64 * naggs, dtype=torch.uint8, pin_memory=pin)
+        self.h_all = torch.zeros(64 * naggs * self.world, dtype=torch.uint8, pin_memory=pin)
+        self.d_mine = torch.zeros(64 * naggs, dtype=torch.uint8, device=device)
+        self.d_all = torch.zeros(64 * naggs * self.world, dtype=torch.uint8, device=device)
+        self.np_mine = self.h_mine.numpy()
+        self.np_all = self.h_all.numpy().reshape(self.world, naggs, 64)
+
+    def exchange(self, local_aggs, block_types):
+        for j, a in enumerate(local_aggs):
+            self.np_mine[64 * j:64 * j + PARTIAL_BYTES] = np.frombuffer(bytes(a), dtype=np.uint8)
+        self.d_mine.copy_(self.h_mine, non_blocking=True)
+        self.dist.all_gather_into_tensor(self.d_all, self.d_mine)
+        self.h_all.copy_(self.d_all)      # synchronous: the combined result is needed on the host
+        return [combine(block_types[j], [unpack_partial(self.np_all[r, j]) for r in range(self.world)]) for j in range(self.n)]

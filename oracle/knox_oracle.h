@@ -133,6 +133,11 @@ size_t  ko_bloom_bytes(size_t m_bits);                    /* 1 + pow2(m)/8 */
 void    ko_bloom_init(uint8_t* buf, size_t m_bits);       /* k = 4 */
 void    ko_bloom_add(uint8_t* buf, size_t buflen, uint64_t h);
 int     ko_bloom_contains(const uint8_t* buf, size_t buflen, uint64_t h);
+/* stats.BuildBloomFilter (internal/pack/stats/filter.go:296-367): m = pow2(cardinality*factor*8) bits, k = 4;
+ * fixed-width values (elem_bytes 8/4/2/1) are hashed with hash.Vec64/32/16/8, byte strings (elem_bytes 0,
+ * offsets[n+1]) with hash.Hash.  Returns the buffer length written ([k][m/8 bytes]), 0 if no filter. */
+size_t  ko_bloom_build(uint8_t* buf, size_t cap, int elem_bytes, const uint8_t* values, const uint32_t* offsets, size_t n,
+                       int cardinality, int factor);
 
 /* ---- reducers over selected rows: internal/reducer/reducer.go:138-314 ----
  * sequential, in type T (i64/u64 wrap, f64 naive left-to-right).  bits may be NULL

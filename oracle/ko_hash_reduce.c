@@ -150,6 +150,29 @@ int ko_bloom_contains(const uint8_t* buf, size_t buflen, uint64_t h) {
     return 1;
 }
 
+size_t ko_bloom_build(uint8_t* buf, size_t cap, int elem_bytes, const uint8_t* values, const uint32_t* offsets, size_t n,
+                      int cardinality, int factor) {
+    if (cardinality <= 0 || factor <= 0) return 0;            /* filter.go:297-299 */
+    size_t m = 8;                                              /* bloom.pow2: smallest power of two >= v, at least 8 */
+    while (m < (size_t)cardinality * (size_t)factor * 8) m <<= 1;
+    size_t len = 1 + (m >> 3);
+    if (len > cap) return 0;
+    memset(buf, 0, len); buf[0] = 4;
+    for (size_t i = 0; i < n; i++) {
+        uint64_t h, v = 0;
+        if (elem_bytes) memcpy(&v, values + i * (size_t)elem_bytes, (size_t)elem_bytes);
+        switch (elem_bytes) {
+        case 8: h = ko_xxh3_u64(v); break;
+        case 4: h = ko_xxh3_u32((uint32_t)v); break;
+        case 2: h = ko_xxh3_u16((uint16_t)v); break;
+        case 1: h = ko_xxh3_u8((uint8_t)v); break;
+        default: h = ko_xxh3_bytes(values + offsets[i], offsets[i + 1] - offsets[i]); break;
+        }
+        ko_bloom_add(buf, len, h);
+    }
+    return len;
+}
+
 /* ------------------------------------------------------------------ reducers
  * internal/reducer/reducer.go:138-149 (Count), :168-179 (Sum: r.v += v in T),
  * :256-267 (Max: first || r.v < v), :286-297 (Min: first || r.v > v), fed row by row

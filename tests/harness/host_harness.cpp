@@ -140,5 +140,9 @@ int kxh_view_kind(int block_type, const uint8_t* enc, size_t len) {
 }
 
 uint64_t kxh_xxh3_bytes(const uint8_t* p, size_t len) { return xxh3_bytes(p, len); }
+uint64_t kxh_xxh3_fixed(int nbytes, uint64_t v) {
+    switch (nbytes) { case 8: return xxh3_u64(v); case 4: return xxh3_u32(uint32_t(v)); case 2: return xxh3_u16(uint16_t(v)); case 1: return xxh3_u8(uint8_t(v)); }
+    return 0;
+}
 
 }  // extern "C"

@@ -105,6 +105,8 @@ def harness():
         L.kxh_decode.argtypes = [C.c_int, vp, C.c_size_t, vp, C.c_size_t]
         L.kxh_view_kind.restype = C.c_int
         L.kxh_view_kind.argtypes = [C.c_int, vp, C.c_size_t]
+        L.kxh_xxh3_fixed.restype = C.c_uint64
+        L.kxh_xxh3_fixed.argtypes = [C.c_int, C.c_uint64]
         L.kxh_xxh3_bytes.restype = C.c_uint64
         L.kxh_xxh3_bytes.argtypes = [vp, C.c_size_t]
         _h = L

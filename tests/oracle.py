@@ -86,6 +86,7 @@ def lib():
             "ko_bloom_init": (None, [vp, C.c_size_t]),
             "ko_bloom_add": (None, [vp, C.c_size_t, C.c_uint64]),
             "ko_bloom_contains": (C.c_int, [vp, C.c_size_t, C.c_uint64]),
+            "ko_bloom_build": (C.c_size_t, [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int]),
             "ko_reduce": (None, [C.c_int, vp, C.c_size_t, vp, vp]),
             "ko_tree_eval": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_size_t, vp]),
             "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
@@ -229,3 +230,20 @@ def tree_eval(postfix, leaf_bits, n):
     rc = lib().ko_tree_eval(_p(pf), pf.size, ptrs, len(arrs), n, _p(out))
     assert rc == 0
     return out[:nbytes(n)].copy()
+
+
+def bloom_build(values, cardinality, factor, elem_bytes=None, offsets=None):
+    """stats.BuildBloomFilter restated: values = typed numpy array, or uint8 bytes + offsets for strings"""
+    if offsets is not None:
+        v = np.ascontiguousarray(values, dtype=np.uint8); off = np.ascontiguousarray(offsets, dtype=np.uint32)
+        n, eb = off.size - 1, 0
+    else:
+        v = np.ascontiguousarray(values); off = None
+        n, eb = v.size, elem_bytes or v.dtype.itemsize
+        v = v.view(np.uint8)
+    m = 8
+    while m < cardinality * factor * 8:
+        m <<= 1
+    buf = np.zeros(1 + m // 8, dtype=np.uint8)
+    ln = lib().ko_bloom_build(_p(buf), buf.size, eb, _p(v), None if off is None else _p(off), n, cardinality, factor)
+    return buf[:ln] if ln else None

@@ -362,3 +362,72 @@ def test_errors_are_loud(ctx):
     with pytest.raises(kb.KnoxError):
         kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.EQ, 5)], postfix=[0, kb.OP_AND])
     prog.close()
+
+
+def test_resident_stats_index_bloom_build_and_prune(ctx):
+    """kx_stats: blooms BUILT on the device are bit-identical to stats.BuildBloomFilter's buffers (oracle), and
+    pruning over the resident index equals zone-map + bloom evaluation pack by pack (stats/match.go:92-195)."""
+    import knoxdb_b200 as kb
+    L = ko.lib()
+    npacks, per_pack = 300, 500
+    heights = np.arange(npacks, dtype=np.int64) * per_pack
+    vals_u64 = [RNG.integers(0, 2**50, per_pack, dtype=np.uint64) for _ in range(npacks)]
+    addr = [RNG.integers(0, 256, (per_pack, 20), dtype=np.uint8) for _ in range(npacks)]
+    offs = (np.arange(per_pack + 1, dtype=np.uint32) * 20)
+    fields = [(1, kb.INT64), (2, kb.UINT64), (3, kb.BYTES)]
+    mins = np.stack([heights.view(np.uint64), np.array([v.min() for v in vals_u64], dtype=np.uint64), np.zeros(npacks, dtype=np.uint64)])
+    maxs = np.stack([(heights + per_pack - 1).view(np.uint64), np.array([v.max() for v in vals_u64], dtype=np.uint64), np.zeros(npacks, dtype=np.uint64)])
+    st = kb.Stats(ctx, fields, mins, maxs)
+    want_u64, want_addr = [], []
+    for p in range(npacks):
+        st.build_bloom(1, p, kb.UINT64, vals_u64[p], per_pack, 2)
+        want_u64.append(ko.bloom_build(vals_u64[p], per_pack, 2))
+        if p % 3:   # every third pack has no address filter: it must survive bloom pruning
+            st.build_bloom(2, p, kb.BYTES, addr[p].reshape(-1), per_pack, 3, offsets=offs)
+            want_addr.append(ko.bloom_build(addr[p].reshape(-1), per_pack, 3, offsets=offs))
+        else:
+            want_addr.append(None)
+    for p in (0, 1, 2, 77, 299):
+        assert (st.get_bloom(1, p) == want_u64[p]).all()
+        got = st.get_bloom(2, p)
+        assert (got is None) == (want_addr[p] is None) and (got is None or (got == want_addr[p]).all())
+    # narrow types and a stored filter attached verbatim
+    for t, ktp in ((np.int32, kb.INT32), (np.uint16, kb.UINT16), (np.uint8, kb.UINT8), (np.float64, kb.FLOAT64)):
+        v = RNG.integers(0, 200, 333).astype(t)
+        st2 = kb.Stats(ctx, [(9, ktp)], np.zeros((1, 1), np.uint64), np.zeros((1, 1), np.uint64))
+        st2.build_bloom(0, 0, ktp, v, 200, 4)
+        assert (st2.get_bloom(0, 0) == ko.bloom_build(v, 200, 4)).all(), t
+        st2.put_bloom(0, 0, want_u64[5])
+        assert (st2.get_bloom(0, 0) == want_u64[5]).all()
+        st2.close()
+    # query: height range AND (value = x OR address = y)
+    x, y = int(vals_u64[123][7]), addr[200][11]
+    hy = kb.lib().kx_hash_bytes(y.ctypes.data, 20)
+    hx = kb.lib().kx_hash_value(kb.UINT64, x)
+    assert hy == L.ko_xxh3_bytes(ko._p(y), 20) and hx == L.ko_xxh3_u64(x)
+    lo, hi = 20 * per_pack + 3, 250 * per_pack
+    prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, lo, hi), kb.Leaf(2, kb.UINT64, kb.EQ, x), kb.Leaf(3, kb.BYTES, kb.EQ)],
+                      postfix=[0, 1, 2, kb.OP_OR, kb.OP_AND])
+    bits, nsurv = st.prune(prog, [[], [hx], [hy]])
+    want = np.zeros(npacks, dtype=bool)
+    for p in range(npacks):
+        z0 = L.ko_match_range(ko.I64, ko.RG, lo, hi, int(mins[0, p]), int(maxs[0, p]))
+        z1 = L.ko_match_range(ko.U64, ko.EQ, x, 0, int(mins[1, p]), int(maxs[1, p])) and L.ko_bloom_contains(ko._p(want_u64[p]), want_u64[p].size, hx)
+        z2 = True if want_addr[p] is None else bool(L.ko_bloom_contains(ko._p(want_addr[p]), want_addr[p].size, hy))
+        want[p] = bool(z0 and (z1 or z2))
+    assert (kt.unpack_bits(bits, npacks) == want).all()
+    assert nsurv == int(want.sum()) and want[123] and want[200]
+    # library-side hashing of numeric operands (hashes = NULL): the address leaf then probes nothing
+    prog2 = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, lo, hi), kb.Leaf(2, kb.UINT64, kb.IN, values=np.array([x, 12345], dtype=np.uint64))])
+    bits2, n2 = st.prune(prog2)
+    want2 = np.zeros(npacks, dtype=bool)
+    h12345 = L.ko_xxh3_u64(12345)
+    for p in range(npacks):
+        z0 = L.ko_match_range(ko.I64, ko.RG, lo, hi, int(mins[0, p]), int(maxs[0, p]))
+        inr = any(int(mins[1, p]) <= v <= int(maxs[1, p]) for v in (x, 12345))
+        bl = any(L.ko_bloom_contains(ko._p(want_u64[p]), want_u64[p].size, h) for h in (hx, h12345))
+        want2[p] = bool(z0 and inr and bl)
+    assert (kt.unpack_bits(bits2, npacks) == want2).all() and n2 == int(want2.sum())
+    with pytest.raises(kb.KnoxError):
+        ctx.scan(prog, [(0, 1)], nrows=[1])      # byte-string programs are prune-only
+    prog.close(); prog2.close(); st.close()

@@ -101,3 +101,17 @@ def test_xxh3_host_matches_oracle_and_golden():
     for n in list(range(0, 300, 7)) + [1023, 1024, 1025, 5000]:
         b = RNG.integers(0, 256, max(n, 1), dtype=np.uint8)
         assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, n) == ko.lib().ko_xxh3_bytes(b.ctypes.data, n), n
+
+
+def test_xxh3_fixed_width_specialisations():
+    """hash.Uint64/Uint32/Uint16/Uint8 (internal/hash/xxh3.go:22-58) = XXH3-64 of the value's LE bytes"""
+    import xxhash
+    L = ko.lib()
+    for v in [0, 1, 0x7F, 0xFF, 0x1234, 0xFFFF, 0xDEADBEEF, 0xFFFFFFFF, 0x0123456789ABCDEF, 2**64 - 1] + [int(x) for x in RNG.integers(0, 2**63, 50)]:
+        for nb, ofn in ((8, L.ko_xxh3_u64), (4, L.ko_xxh3_u32), (2, L.ko_xxh3_u16), (1, L.ko_xxh3_u8)):
+            x = v & ((1 << (8 * nb)) - 1)
+            want = xxhash.xxh3_64_intdigest(x.to_bytes(nb, "little"))
+            assert kt.harness().kxh_xxh3_fixed(nb, x) == want == ofn(x), (nb, hex(x))
+    for n in list(range(0, 260)) + [300, 511, 512, 513, 1024, 4097]:
+        b = RNG.integers(0, 256, max(n, 1), dtype=np.uint8)
+        assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, n) == xxhash.xxh3_64_intdigest(b[:n].tobytes()), n
