@@ -43,6 +43,9 @@ struct DevBuf {
         size_t want = round_up(std::max(n, size_t(4096)) * 5 / 4, 4096);
         cudaError_t e = cudaMalloc(&p, want);
         if (e == cudaSuccess) { cap = want; e = cudaMemset(p, 0, want); }
+        // cudaMemset runs on the legacy default stream, asynchronously to the host, and the context's
+        // stream is non-blocking: without this the zero-fill can land AFTER the first copies into the buffer
+        if (e == cudaSuccess) e = cudaDeviceSynchronize();
         return e;
     }
     ~DevBuf() { if (p) cudaFree(p); }
@@ -189,10 +192,13 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
     };
     int rc;
     const ColView& v = lay.view;
-    if (v.kind == CK_BITS || v.kind == CK_DICT) {
+    if (v.kind == CK_BITS || v.kind == CK_DICT || (v.kind == CK_ALP && v.width)) {
         const void* src = lay.owned.empty() ? (const void*)lay.stream : (const void*)lay.owned.data();
         size_t len = lay.owned.empty() ? lay.stream_len : lay.owned.size();
         if ((rc = put(src, len, &sb.view.data))) return rc;
+    }
+    if (v.kind == CK_ALP && !lay.blob.empty()) {
+        if ((rc = put(lay.blob.data(), lay.blob.size(), &sb.view.aux))) return rc;
     }
     if (v.kind == CK_DICT) {
         if ((rc = put(lay.aux64.data(), lay.aux64.size() * 8, &sb.view.aux))) return rc;
@@ -202,7 +208,7 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
         if ((rc = put(lay.aux64.data(), lay.aux64.size() * 8, &sb.view.data))) return rc;
         if ((rc = put(lay.aux32.data(), lay.aux32.size() * 4, &sb.view.aux))) return rc;
     }
-    if (!lay.owned.empty() || v.kind == CK_DICT || v.kind == CK_RUNEND) {
+    if (!lay.owned.empty() || v.kind == CK_DICT || v.kind == CK_RUNEND || v.kind == CK_ALP) {
         // host-owned temporaries (lay.owned / aux vectors) die with `lay`: finish the copies now
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -249,6 +255,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::vector<CodesetJob> cjobs;
     std::vector<RunFillJob> rjobs;
     std::vector<size_t> rjob_leaf;     // index into pl of each run-fill job
+    std::vector<AlpFixJob> ajobs;
+    std::vector<size_t> ajob_leaf;
+    uint32_t max_patches = 0;
+    bool any_fix = false;
     size_t leafbits_bytes = 0;
     uint32_t max_runs = 0;
     uint32_t max_stage_bits = 0, code_words = 0;
@@ -256,7 +266,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     uint64_t total_rows = 0;
     bool uniform = true;
     for (int p = 0; p < npacks; ++p) {
-        uint32_t bits = 0;
+        uint32_t bits = 0;   // widest staged leaf column of the pack: one ring stage holds ONE column of a tile
         for (int l = 0; l < nleaves; ++l) {
             const ColView& v = job.leaf_views[size_t(p) * nleaves + l];
             if (v.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
@@ -266,7 +276,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 const LeafSpec& ls = prog->leaves[size_t(l)];
                 cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0});
                 o.a = code_words;
-                code_words += (v.naux + 31u) / 32u;
+                // the bitmap spans every code a `width`-bit field can produce (leaf_code32 does not bounds-check)
+                code_words += uint32_t(((uint64_t(1) << v.width) + v.delta + 31u) / 32u) + 1u;
             }
             if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
                 // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
@@ -275,9 +286,22 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                 max_runs = std::max(max_runs, v.naux);
                 o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
-                bits += 1;
+                bits = std::max(bits, 1u);
             }
-            bits += uint32_t(leaf_stage_width(o));
+            if (o.fixmode) {   // ALP block with patches: the correction is a 1-bit stream staged after the leaf's own
+                any_fix = true;
+                bits = std::max(bits, 1u);
+                if (o.fixmode == FIX_ANDNOT_ALL) o.fix = v.aux + alp_mask_off(v.naux);   // resident patch bitmap
+                else {
+                    const LeafSpec& ls = prog->leaves[size_t(l)];
+                    ajobs.push_back(AlpFixJob{v.aux, ls.a, ls.b, leafbits_bytes, v.naux, uint32_t(ls.mode == KX_MODE_NE ? KX_MODE_EQ : ls.mode),
+                                              o.fixmode == FIX_ANDNOT_NPRED ? 1u : 0u, 0});
+                    ajob_leaf.push_back(size_t(p) * nleaves + l);
+                    leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
+                    max_patches = std::max(max_patches, v.naux);
+                }
+            }
+            bits = std::max(bits, uint32_t(leaf_stage_width(o)));
             if (o.mode != LM_RANGE32 && o.mode != LM_NONE && o.mode != LM_ALL) only32 = false;
         }
         for (int j = 0; j < naggs; ++j)
@@ -292,8 +316,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // tiles in a 2-deep ring beat small tiles in a deep ring (per-tile barrier/dispatch cost, larger TMA
     // copies), narrow ALU-bound columns like 3 CTAs per SM, wide ones 2 (or 1 when 8192 rows need > 50 KB).
     struct Geo { int ctas, stages; size_t budget; };
-    const bool simple32 = only32 && nleaves == 1 && naggs == 0;
-    const size_t stage_fixed = 16u * size_t(nleaves) + 16;
+    const bool simple = nleaves == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
+    const bool simple32 = only32 && simple;
+    const size_t stage_fixed = 32;
     auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
     auto rmax_for = [&](const Geo& g) { return (g.budget - stage_fixed - 128) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)); };
     const Geo g3{3, 2, 33 * 1024}, g2{2, 2, 50 * 1024}, g1{1, 2, 99 * 1024};
@@ -304,6 +329,13 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         size_t rmax = rmax_for(geo);
         if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
         R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
+        if (!simple) {
+            // general kernels: one stage = one leaf column of an 8192-row tile (single pass); spend the rest of
+            // the shared memory on ring depth so that the next tile's first columns are already in flight
+            R = std::min<uint32_t>(R, 32);
+            size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(geo.ctas) - 128;
+            geo.stages = int(std::min<size_t>(4, std::max<size_t>(2, per_cta / stage_bytes_for(R))));
+        }
     }
     if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
         int c = 0, st = 0, r = 0;
@@ -329,10 +361,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     size_t sz_tiles = uniform ? 0 : sizeof(uint32_t) * size_t(ntiles);
     size_t off_cjobs = off_tiles + round_up(sz_tiles, 256);
     size_t off_rjobs = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
-    size_t desc_bytes = off_rjobs + round_up(sizeof(RunFillJob) * rjobs.size(), 256);
-    if (!rjobs.empty()) {
+    size_t off_ajobs = off_rjobs + round_up(sizeof(RunFillJob) * rjobs.size(), 256);
+    size_t desc_bytes = off_ajobs + round_up(sizeof(AlpFixJob) * ajobs.size(), 256);
+    if (leafbits_bytes) {
         CK(ctx->d_leafbits.reserve(leafbits_bytes));
         for (size_t i = 0; i < rjobs.size(); ++i) pl[rjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + rjobs[i].out_off;
+        for (size_t i = 0; i < ajobs.size(); ++i) pl[ajob_leaf[i]].fix = static_cast<const uint8_t*>(ctx->d_leafbits.p) + ajobs[i].out_off;
     }
 
     CK(ctx->h_desc.reserve(desc_bytes));
@@ -358,6 +392,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
 
     if (!cjobs.empty()) std::memcpy(hd + off_cjobs, cjobs.data(), sizeof(CodesetJob) * cjobs.size());
     if (!rjobs.empty()) std::memcpy(hd + off_rjobs, rjobs.data(), sizeof(RunFillJob) * rjobs.size());
+    if (!ajobs.empty()) std::memcpy(hd + off_ajobs, ajobs.data(), sizeof(AlpFixJob) * ajobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
     int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * geo.ctas));
@@ -402,18 +437,24 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * size_t(npacks), ctx->stream));
     if (naggs) CK(cudaMemcpyAsync(ctx->d_aggtype.p, P.agg_type, MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (ntiles && leafbits_bytes) CK(cudaMemsetAsync(ctx->d_leafbits.p, 0, leafbits_bytes, ctx->stream));
+    if (ntiles && !ajobs.empty()) {
+        CK(launch_alpfix(reinterpret_cast<const AlpFixJob*>(dd + off_ajobs), uint32_t(ajobs.size()), max_patches,
+                         static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
+        ctx->last_launches++;
+    }
     if (ntiles && !rjobs.empty()) {
-        CK(cudaMemsetAsync(ctx->d_leafbits.p, 0, leafbits_bytes, ctx->stream));
         CK(launch_runfill(reinterpret_cast<const RunFillJob*>(dd + off_rjobs), uint32_t(rjobs.size()), max_runs, prog->dev_sets,
                           static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
         ctx->last_launches++;
     }
     if (ntiles && !cjobs.empty()) {
+        CK(cudaMemsetAsync(ctx->d_codebits.p, 0, size_t(code_words) * 4, ctx->stream));
         CK(launch_codeset(reinterpret_cast<const CodesetJob*>(dd + off_cjobs), uint32_t(cjobs.size()), prog->dev_sets,
                           static_cast<uint32_t*>(ctx->d_codebits.p), ctx->stream));
         ctx->last_launches++;
     }
-    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, only32, geo.ctas, ctx->stream)); ctx->last_launches++; }
+    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, simple, only32, geo.ctas, ctx->stream)); ctx->last_launches++; }
     if (naggs) {
         if (ntiles) {
             CK(launch_finalize(P.partials, uint32_t(grid), uint32_t(naggs), static_cast<const uint8_t*>(ctx->d_aggtype.p),
@@ -750,7 +791,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         const int nb = p1 - p0;
         // pass 1: parse headers, lay the batch out in the staging arena (256 B aligned streams)
         std::vector<BlockLayout> lays(size_t(nb) * nfields);
-        std::vector<size_t> off_stream(lays.size(), 0), off_a64(lays.size(), 0), off_a32(lays.size(), 0), aux_src(lays.size(), 0);
+        std::vector<size_t> off_stream(lays.size(), 0), off_a64(lays.size(), 0), off_a32(lays.size(), 0), off_blob(lays.size(), 0), aux_src(lays.size(), 0);
         size_t dev_bytes = 0, aux_bytes = 0;
         for (int p = 0; p < nb; ++p) {
             for (int f = 0; f < nfields; ++f) {
@@ -761,7 +802,8 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
                 BlockLayout& lay = lays[li];
                 if (lay.owned.empty() && lay.stream_len) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.stream_len + STREAM_PAD, 256); }
                 aux_src[li] = aux_bytes;
-                aux_bytes += round_up(lay.owned.size(), 16) + round_up(lay.aux64.size() * 8, 16) + round_up(lay.aux32.size() * 4, 16);
+                aux_bytes += round_up(lay.owned.size(), 16) + round_up(lay.aux64.size() * 8, 16) + round_up(lay.aux32.size() * 4, 16) +
+                             round_up(lay.blob.size(), 16);
             }
         }
         // host-built arrays (dictionaries, run values/ends, transcoded streams) go through one pinned buffer
@@ -771,6 +813,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             if (!lay.owned.empty()) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.owned.size() + STREAM_PAD, 256); }
             if (!lay.aux64.empty()) { off_a64[li] = dev_bytes; dev_bytes += round_up(lay.aux64.size() * 8 + STREAM_PAD, 256); }
             if (!lay.aux32.empty()) { off_a32[li] = dev_bytes; dev_bytes += round_up(lay.aux32.size() * 4 + STREAM_PAD, 256); }
+            if (!lay.blob.empty()) { off_blob[li] = dev_bytes; dev_bytes += round_up(lay.blob.size() + STREAM_PAD, 256); }
         }
         (void)aux_dev0;
         CK(ctx->d_stage.reserve(dev_bytes + 256));
@@ -797,8 +840,14 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             if (!lay.aux32.empty()) {
                 std::memcpy(hp, lay.aux32.data(), lay.aux32.size() * 4);
                 CK(cudaMemcpyAsync(dbase + off_a32[li], hp, lay.aux32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                hp += round_up(lay.aux32.size() * 4, 16);
             }
-            if (v.kind == CK_BITS || v.kind == CK_DICT) v.data = dbase + off_stream[li];
+            if (!lay.blob.empty()) {
+                std::memcpy(hp, lay.blob.data(), lay.blob.size());
+                CK(cudaMemcpyAsync(dbase + off_blob[li], hp, lay.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+            }
+            if (v.kind == CK_BITS || v.kind == CK_DICT || (v.kind == CK_ALP && v.width)) v.data = dbase + off_stream[li];
+            if (v.kind == CK_ALP && !lay.blob.empty()) v.aux = dbase + off_blob[li];
             if (v.kind == CK_DICT) v.aux = dbase + off_a64[li];
             if (v.kind == CK_RUNEND) { v.data = dbase + off_a64[li]; v.aux = dbase + off_a32[li]; }
         }

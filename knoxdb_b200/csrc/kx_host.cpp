@@ -9,6 +9,7 @@
 #include "kx_xxh3.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstring>
 
 namespace kx {
@@ -42,6 +43,36 @@ int get_uvarint(const uint8_t* b, size_t avail, uint64_t* x) {
 }
 
 size_t bitpack_bytes(int log2, size_t n) { return ((size_t(log2) * n + 63) & ~size_t(63)) / 8; }
+
+// ---------------------------------------------------------------------------------- ALP arithmetic
+// internal/encode/alp/constants.go:88-150, encoder.go:112-125, decoder.go:122-124 (float64 / int64).  Built with
+// -ffp-contract=off: Go on amd64 never fuses v*F10[e]*IF10[f] + SWEET.  Float → int conversions follow Go on
+// amd64 (CVTTSD2SQ: NaN / out of range → 0x8000000000000000), which the reference's matchers rely on.
+namespace {
+const double ALP_F10[24] = {
+    1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0, 1000000.0, 10000000.0, 100000000.0, 1000000000.0, 10000000000.0,
+    100000000000.0, 1000000000000.0, 10000000000000.0, 100000000000000.0, 1000000000000000.0, 10000000000000000.0,
+    100000000000000000.0, 1000000000000000000.0, 10000000000000000000.0, 100000000000000000000.0,
+    1000000000000000000000.0, 10000000000000000000000.0, 100000000000000000000000.0};
+const double ALP_IF10[21] = {
+    1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001, 0.00000001, 0.000000001, 0.0000000001, 0.00000000001,
+    0.000000000001, 0.0000000000001, 0.00000000000001, 0.000000000000001, 0.0000000000000001, 0.00000000000000001,
+    0.000000000000000001, 0.0000000000000000001, 0.00000000000000000001};
+const double ALP_SWEET = 6755399441055744.0;   // 1<<52 + 1<<51
+int64_t go_f2i(double x) {
+    if (!(x >= -9223372036854775808.0 && x < 9223372036854775808.0)) return INT64_MIN;
+    return int64_t(x);
+}
+}  // namespace
+int64_t alp_encode_single(double v, int e, int f, bool* ok) {
+    int64_t enc = go_f2i((v * ALP_F10[e] * ALP_IF10[f] + ALP_SWEET) - ALP_SWEET);
+    double dec = double(enc) * ALP_F10[f] * ALP_IF10[e];
+    *ok = v == dec;
+    return enc;
+}
+int64_t alp_encode_above(double v, int e, int f) { return go_f2i(std::ceil((v * ALP_F10[e] * ALP_IF10[f] + ALP_SWEET) - ALP_SWEET)); }
+int64_t alp_encode_below(double v, int e, int f) { return go_f2i(std::floor((v * ALP_F10[e] * ALP_IF10[f] + ALP_SWEET) - ALP_SWEET)); }
+double alp_decode(int64_t enc, int e, int f) { return double(enc) * ALP_F10[f] * ALP_IF10[e]; }
 
 // ---------------------------------------------------------------------------------- parsing
 namespace {
@@ -126,6 +157,28 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
         }
         break;
     }
+    case T_FLOATALP: {   // float_alp.go:109-165: uv(Exponent) uv(Factor) u8 flags <Values int64> [<Patches T> <Positions uint32>]
+        if (type != 9) { err = "ALP: only float64 blocks are supported"; return -1; }
+        c->alp_e = int(r.uv()); c->alp_f = int(r.uv());
+        const uint8_t* fl = r.take(1);
+        if (!r.ok || !fl) { err = "truncated container"; return -1; }
+        c->alp_flags = *fl;
+        if (c->alp_e > 20 || c->alp_f > 23) { err = "ALP: exponent out of range"; return -1; }
+        long k = parse_container(1 /*int64*/, r.p, r.left, c->child[0], err);
+        if (k < 0) return -1;
+        r.take(size_t(k));
+        if (c->alp_flags & 1) {
+            k = parse_container(type, r.p, r.left, c->child[1], err);
+            if (k < 0) return -1;
+            r.take(size_t(k));
+            k = parse_container(6 /*uint32*/, r.p, r.left, c->child[2], err);
+            if (k < 0) return -1;
+            r.take(size_t(k));
+            if (c->child[1]->n != c->child[2]->n) { err = "ALP: patches/positions length mismatch"; return -1; }
+        }
+        c->n = c->child[0]->n;
+        break;
+    }
     default:
         err = "unsupported container type " + std::to_string(c->ctype);
         return -1;
@@ -176,6 +229,16 @@ bool decode_container(const Container& c, std::vector<uint64_t>& out, std::strin
         for (size_t i = 0; i < c.n; i++) {
             if (codes[i] >= dict.size()) { err = "dict: code out of range"; return false; }
             out[i] = dict[codes[i]];
+        }
+        return true;
+    }
+    case T_FLOATALP: {
+        if (!decode_container(*c.child[0], out, err)) return false;
+        for (size_t i = 0; i < c.n; i++) { double d = alp_decode(int64_t(out[i]), c.alp_e, c.alp_f); std::memcpy(&out[i], &d, 8); }
+        if (c.alp_flags & 1) {
+            std::vector<uint64_t> pv, pp;
+            if (!decode_container(*c.child[1], pv, err) || !decode_container(*c.child[2], pp, err)) return false;
+            for (size_t k = 0; k < pp.size(); k++) { if (pp[k] >= c.n) { err = "ALP: patch position out of range"; return false; } out[pp[k]] = pv[k]; }
         }
         return true;
     }
@@ -252,6 +315,51 @@ int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, 
     case T_FLOATRAW:
         stream_view(*c, out);
         return 0;
+    case T_FLOATALP: {
+        // the encoded int64 values stay a min-FOR bit stream; patches (few) become a small resident blob
+        const Container& vc = *c->child[0];
+        v.kind = CK_ALP; v.delta = (uint64_t(c->alp_e) << 8) | uint64_t(c->alp_f); v.is_raw = 0;
+        BlockLayout tmp;
+        if (vc.ctype == T_BITPACK) {
+            v.base = vc.val; v.width = uint8_t(vc.log2);
+            out.stream = vc.payload; out.stream_len = vc.payload_len;
+        } else if (vc.ctype == T_CONST) {
+            v.base = vc.val; v.width = 0;
+        } else {   // raw / delta / dict / run-end children: re-pack once at registration
+            std::vector<uint64_t> vals;
+            if (!decode_container(vc, vals, err)) return -6;
+            int64_t mn = INT64_MAX, mx = INT64_MIN;
+            for (uint64_t x : vals) { mn = std::min(mn, int64_t(x)); mx = std::max(mx, int64_t(x)); }
+            if (vals.empty()) mn = mx = 0;
+            int w = log2_range(uint64_t(mn), uint64_t(mx));
+            for (auto& x : vals) x -= uint64_t(mn);
+            v.base = uint64_t(mn); v.width = uint8_t(w);
+            if (w) pack_stream(vals, w, out.owned);
+        }
+        if (c->alp_flags & 1) {
+            std::vector<uint64_t> pv, pp;
+            if (!decode_container(*c->child[1], pv, err) || !decode_container(*c->child[2], pp, err)) return -6;
+            const uint32_t np = uint32_t(pp.size());
+            v.naux = np;
+            if (np) {
+                size_t mask_words = (size_t(v.n) + 31) / 32;
+                out.blob.assign(alp_mask_off(np) + mask_words * 4 + 64, 0);
+                uint32_t* bp = reinterpret_cast<uint32_t*>(out.blob.data());
+                uint64_t* bv = reinterpret_cast<uint64_t*>(out.blob.data() + alp_vals_off(np));
+                uint32_t* bm = reinterpret_cast<uint32_t*>(out.blob.data() + alp_mask_off(np));
+                for (uint32_t k = 0; k < np; k++) {
+                    if (pp[k] >= v.n || (k && pp[k] <= pp[k - 1])) { err = "ALP: patch positions must ascend inside the block"; return -6; }
+                    bp[k] = uint32_t(pp[k]); bv[k] = pv[k];
+                    bm[pp[k] >> 5] |= 1u << (pp[k] & 31);
+                }
+                // the encoded value stored at patch positions (Encoder.Encode writes the vector minimum there)
+                const uint8_t* st = out.owned.empty() ? out.stream : out.owned.data();
+                size_t sl = out.owned.empty() ? out.stream_len : out.owned.size();
+                v.extra = v.base + (v.width ? bit_field(st, sl, pp[0], v.width) : 0);
+            }
+        }
+        return 0;
+    }
     case T_S8B: {
         // legacy scheme (never selected for new data, context.go:275-282): transcode to a
         // min-FOR bit stream once at registration so the scan kernels see one stream format
@@ -575,7 +683,81 @@ void compile_valrange(PackLeaf& o, int t, int mode, uint64_t a, uint64_t b) {
     set_const(o, false);
 }
 
+// does the translated integer predicate accept the encoded value x?  (device semantics of LM_RANGE*/ALL/NONE)
+bool packleaf_accepts(const PackLeaf& o, const ColView& vv, uint64_t x) {
+    if (o.mode == LM_ALL) return true;
+    if (o.mode == LM_NONE) return false;
+    uint64_t field = (x - vv.base) & width_mask(vv.width);
+    bool r = ((field - o.a) & o.wm) <= o.d;
+    return r != (o.neg != 0);
+}
+
 }  // namespace
+
+// FloatAlpContainer.Match* (float_alp.go:238-495): translate the float predicate into the encoded integer domain
+// (EncodeSingle / EncodeAbove / EncodeBelow), run the integer matcher of the Values child, then correct the rows
+// that are patches.  All patch slots hold the same replacement value, so the correction is one of: OR in the
+// patches that satisfy the float predicate (replacement did not match) or AND out those that do not (it did).
+static void compile_alp(PackLeaf& o, const ColView& v, int mode, uint64_t ua, uint64_t ub, uint32_t view_index) {
+    double a, b; std::memcpy(&a, &ua, 8); std::memcpy(&b, &ub, 8);
+    const int e = int(v.delta >> 8), f = int(v.delta & 0xff);
+    const bool patched = v.naux > 0;
+    ColView vv = v;   // the encoded values as an int64 min-FOR column
+    vv.kind = v.width ? CK_BITS : CK_CONST; vv.type = 1; vv.is_raw = 0; vv.aux = nullptr; vv.naux = 0;
+    auto inner = [&](int imode, int64_t x, int64_t y) {
+        LeafSpec ls; ls.type = 1; ls.mode = uint8_t(imode); ls.a = uint64_t(x); ls.b = uint64_t(y);
+        compile_leaf(vv, nullptr, ls, view_index, o);
+    };
+    auto fix_by_pred = [&]() {
+        if (patched) o.fixmode = packleaf_accepts(o, vv, v.extra) ? FIX_ANDNOT_NPRED : FIX_OR_PRED;
+    };
+    const bool nan_a = a != a, nan_b = b != b;
+    bool ok = false; int64_t av, bv;
+    switch (mode) {
+    case M_EQ: case M_NE: {   // :238-295
+        bool ran = false;
+        if (!nan_a) { av = alp_encode_single(a, e, f, &ok); if (ok) { inner(M_EQ, av, 0); ran = true; } }
+        if (!ran) { o = PackLeaf{}; o.view = view_index; o.mode = LM_NONE; }
+        if (patched) o.fixmode = (ran && packleaf_accepts(o, vv, v.extra)) ? FIX_ANDNOT_ALL : FIX_OR_PRED;
+        o.neg2 = mode == M_NE;
+        return;
+    }
+    case M_LT:   // :297-330
+        if (nan_a || (std::isinf(a) && a < 0)) { o.mode = LM_NONE; return; }
+        av = alp_encode_single(a, e, f, &ok);
+        if (ok) inner(M_LT, av, 0); else inner(M_LE, alp_encode_below(a, e, f), 0);
+        fix_by_pred();
+        return;
+    case M_LE:   // :332-371
+        if (nan_a) { o.mode = LM_NONE; return; }
+        if (std::isinf(a) && a > 0) { o.mode = LM_ALL; return; }
+        av = alp_encode_single(a, e, f, &ok);
+        inner(M_LE, ok ? av : alp_encode_below(a, e, f), 0);
+        fix_by_pred();
+        return;
+    case M_GT:   // :373-407
+        if (nan_a || (std::isinf(a) && a > 0)) { o.mode = LM_NONE; return; }
+        av = alp_encode_single(a, e, f, &ok);
+        if (ok) inner(M_GT, av, 0); else inner(M_GE, alp_encode_above(a, e, f), 0);
+        fix_by_pred();
+        return;
+    case M_GE:   // :409-448
+        if (nan_a) { o.mode = LM_NONE; return; }
+        if (std::isinf(a) && a < 0) { o.mode = LM_ALL; return; }
+        av = alp_encode_single(a, e, f, &ok);
+        inner(M_GE, ok ? av : alp_encode_above(a, e, f), 0);
+        fix_by_pred();
+        return;
+    case M_RANGE:   // :450-490
+        if (nan_a || nan_b) { o.mode = LM_NONE; return; }
+        av = alp_encode_single(a, e, f, &ok); if (!ok) av = alp_encode_above(a, e, f);
+        bv = alp_encode_single(b, e, f, &ok); if (!ok) bv = alp_encode_below(b, e, f);
+        inner(M_RANGE, av, bv);
+        fix_by_pred();
+        return;
+    }
+    o.mode = LM_NONE;
+}
 
 bool set_contains(const std::vector<uint64_t>& s, uint64_t v) { return std::binary_search(s.begin(), s.end(), v); }
 
@@ -668,6 +850,9 @@ void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& l
     }
 
     switch (v.kind) {
+    case CK_ALP:
+        compile_alp(o, v, mode, leaf.a, leaf.b, view_index);
+        return;
     case CK_CONST:   // ConstContainer.Match*: all-or-nothing, int_const.go:133-173
         set_const(o, scalar_match(t, mode, v.base, leaf.a, leaf.b));
         return;

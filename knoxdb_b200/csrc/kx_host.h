@@ -13,7 +13,7 @@
 namespace kx {
 
 // container ids, internal/encode/container.go:20-55
-enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATRAW = 15 };
+enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATALP = 13, T_FLOATRAW = 15 };
 // types.FilterMode, internal/types/mode.go:14-23
 enum : int { M_EQ = 1, M_NE = 2, M_GT = 3, M_GE = 4, M_LT = 5, M_LE = 6, M_IN = 7, M_NIN = 8, M_RANGE = 9 };
 
@@ -27,7 +27,8 @@ struct Container {
     uint64_t val = 0, delta = 0;
     const uint8_t* payload = nullptr;
     size_t payload_len = 0;
-    std::unique_ptr<Container> child[2];
+    std::unique_ptr<Container> child[3];   // dict: {Dict, Codes}; runend: {Values, Ends}; alp: {Values, Patches, Positions}
+    int alp_e = 0, alp_f = 0, alp_flags = 0;
 };
 long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err);
 bool decode_container(const Container& c, std::vector<uint64_t>& out, std::string& err);
@@ -40,7 +41,15 @@ struct BlockLayout {
     std::vector<uint8_t> owned;         // … or bytes re-packed on the host (simple8b, exotic code children)
     std::vector<uint64_t> aux64;        // dict values (CK_DICT) or run values (CK_RUNEND → data)
     std::vector<uint32_t> aux32;        // run ends (CK_RUNEND → aux)
+    std::vector<uint8_t> blob;          // CK_ALP patch blob (positions | values | patch bitmap), uploaded as aux
 };
+
+// ALP float64 arithmetic of the reference (internal/encode/alp/{constants,encoder,decoder}.go), host side:
+// used to translate float predicates into the encoded integer domain (float_alp.go:238-495)
+int64_t alp_encode_single(double v, int e, int f, bool* ok);
+int64_t alp_encode_above(double v, int e, int f);
+int64_t alp_encode_below(double v, int e, int f);
+double  alp_decode(int64_t enc, int e, int f);
 int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, std::string& err);
 
 struct LeafSpec {

@@ -49,6 +49,15 @@ struct RunFillJob {
     uint32_t is_set, pad;
 };
 
+// one ALP leaf of alpfix_kernel: bit pos[k] of the correction stream = pred(patch value k) (invert: !pred)
+struct AlpFixJob {
+    const uint8_t* blob;   // patch blob of the block (positions | values | bitmap)
+    uint64_t a, b;         // float64 operands (IEEE bits)
+    uint64_t out_off;      // byte offset of the correction stream
+    uint32_t np, mode;     // types.FilterMode of the float predicate (EQ also serves NE)
+    uint32_t invert, pad;
+};
+
 constexpr size_t SCAN_MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the scan kernel may ask for
 
 // pruning over a device-resident statistics index (kx_stats): statistics are column-major [field][pack]
@@ -73,7 +82,8 @@ cudaError_t launch_prune_stats(const PruneStatsParams& P, cudaStream_t stream);
 cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, uint64_t n, int elem_bytes, uint32_t* bits, uint32_t mask,
                                uint32_t k, cudaStream_t stream);
 
-cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool simple, bool only32, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,

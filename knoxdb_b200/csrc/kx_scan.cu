@@ -50,6 +50,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_addr(bar)), "r"(parity)
         : "memory");
 }
+// asynchronous bulk prefetch of a global range into L2 (no completion tracking)
+__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
+}
 // TMA 1-D bulk copy global → shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
@@ -79,6 +83,17 @@ __device__ __forceinline__ uint32_t run_of_row(const uint32_t* __restrict__ ends
     return lo;
 }
 
+// ALP powers of ten, the exact literals of internal/encode/alp/constants.go:88-150
+__device__ const double ALP_F10[24] = {
+    1.0, 10.0, 100.0, 1000.0, 10000.0, 100000.0, 1000000.0, 10000000.0, 100000000.0, 1000000000.0, 10000000000.0,
+    100000000000.0, 1000000000000.0, 10000000000000.0, 100000000000000.0, 1000000000000000.0, 10000000000000000.0,
+    100000000000000000.0, 1000000000000000000.0, 10000000000000000000.0, 100000000000000000000.0,
+    1000000000000000000000.0, 10000000000000000000000.0, 100000000000000000000000.0};
+__device__ const double ALP_IF10[21] = {
+    1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001, 0.00000001, 0.000000001, 0.0000000001, 0.00000000001,
+    0.000000000001, 0.0000000000001, 0.00000000000001, 0.000000000000001, 0.0000000000000001, 0.00000000000000001,
+    0.000000000000000001, 0.0000000000000000001, 0.00000000000000000001};
+
 // value of row `row` of a block as the sign-/zero-extended 64-bit pattern of T (IEEE bits for
 // floats).  `staged`: the tile's bit stream in shared memory (row index relative to the tile),
 // or nullptr to read the block's stream from global memory.
@@ -103,6 +118,22 @@ __device__ __forceinline__ uint64_t decode_value(const ColView& v, uint32_t row,
     case CK_RUNEND: {
         uint32_t k = run_of_row(reinterpret_cast<const uint32_t*>(v.aux), v.naux, row);
         return __ldg(reinterpret_cast<const unsigned long long*>(v.data) + k);
+    }
+    case CK_ALP: {   // Decoder.DecodeValue (internal/encode/alp/decoder.go:97-124): patch or T(val) * F10[f] * IF10[e]
+        if (v.naux) {
+            const uint32_t* pm = reinterpret_cast<const uint32_t*>(v.aux + alp_mask_off(v.naux));
+            if ((__ldg(pm + (row >> 5)) >> (row & 31u)) & 1u) {
+                const uint32_t* pos = reinterpret_cast<const uint32_t*>(v.aux);
+                uint32_t lo = 0, hi = v.naux;
+                while (lo < hi) { uint32_t m = (lo + hi) >> 1; if (__ldg(pos + m) < row) lo = m + 1; else hi = m; }
+                return __ldg(reinterpret_cast<const unsigned long long*>(v.aux + alp_vals_off(v.naux)) + lo);
+            }
+        }
+        uint64_t f = 0;
+        if (v.width) f = staged ? load_field(staged, (uint64_t)row_in_tile * v.width, v.width)
+                                : load_field(reinterpret_cast<const uint32_t*>(v.data), (uint64_t)row * v.width, v.width);
+        double d = __dmul_rn(__dmul_rn(__ll2double_rn((long long)(f + v.base)), ALP_F10[v.delta & 0xffu]), ALP_IF10[(v.delta >> 8) & 0xffu]);
+        return (uint64_t)__double_as_longlong(d);
     }
     }
     return 0;
@@ -144,6 +175,7 @@ template <int W> __device__ __forceinline__ int rot_chunks(uint32_t lane) {
 // The compare ((f - a) mod 2^W) <= d becomes (t - (a << K)) <= ((d << K) | (2^K - 1)), K = 32 - W.
 template <int W, bool SUB>
 __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t lane, uint32_t a_top, uint32_t lim) {
+    __builtin_assume(__isShared(seg));   // the staged stream lives in shared memory: LDS, not generic loads
     uint32_t x[W + 1];
     int rot_rows = 0;
     if constexpr (W % 4 == 0) {
@@ -209,6 +241,7 @@ __device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw
 // 64-bit top-aligned arithmetic: T = field << (64 - W) (low garbage bits harmless), (T - a_top) <= lim.
 template <int W, bool SUB>
 __device__ __forceinline__ uint32_t leaf_b64(const uint32_t* __restrict__ seg, uint64_t a_top, uint64_t lim) {
+    __builtin_assume(__isShared(seg));
     uint32_t x[W + 2];
     if constexpr (W % 4 == 0) {
 #pragma unroll
@@ -259,6 +292,7 @@ __device__ __noinline__ uint32_t leaf_b64_dispatch(const uint32_t* __restrict__ 
 // with one LDS.64 per row — and build bitset words with __ballot_sync.
 __device__ __forceinline__ uint32_t leaf_range64(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  uint64_t a, uint64_t d, uint64_t wm) {
+    __builtin_assume(__isShared(sw));
     uint32_t word = 0;
     if (w == 64) {
         const unsigned long long* s64 = reinterpret_cast<const unsigned long long*>(sw) + (size_t)g0 * 32u + lane;
@@ -304,6 +338,7 @@ __device__ __forceinline__ bool float_pred(F x, F a, F b) {
 
 template <int OP, typename F>
 __device__ __forceinline__ uint32_t leaf_float_op(const F* __restrict__ sf, uint32_t Rp, uint32_t lane, F a, F b) {
+    __builtin_assume(__isShared(sf));
     uint32_t word = 0;
 #pragma unroll 8
     for (uint32_t it = 0; it < Rp; ++it) {
@@ -337,22 +372,56 @@ __device__ __forceinline__ uint32_t leaf_float(const uint32_t* __restrict__ sw, 
 }
 
 // ---- IN / NOT IN on a dictionary block (DictionaryContainer.MatchInSet, int_dict.go:361-398): the set
-// was translated into a bitmap over the pack's codes (translateSet :400) by codeset_kernel; each
-// lane tests the 32 codes of its own group.
-__device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
-                                                 uint32_t code_base, const uint32_t* __restrict__ bm, uint32_t ncodes) {
-    if (lane >= Rp) return 0;
-    const uint32_t* seg = sw + (size_t)(g0 + lane) * w;
-    const uint32_t fm = w >= 32 ? 0xffffffffu : ((1u << w) - 1u);
-    uint32_t word = 0, bit = 0;
-#pragma unroll 8
-    for (uint32_t j = 0; j < 32; ++j, bit += w) {
-        uint32_t wi = bit >> 5, sh = bit & 31u;
-        uint32_t code = (__funnelshift_r(seg[wi], seg[wi + 1], sh) & fm) + code_base;
-        uint32_t hit = code < ncodes ? (__ldg(bm + (code >> 5)) >> (code & 31u)) & 1u : 0u;
-        word |= hit << j;
+// was translated into a bitmap over the pack's codes (translateSet :400) by codeset_kernel; each lane
+// tests the 32 codes of its own group.  The bitmap covers every code a W-bit field can produce (the
+// host sizes and zeroes it), so there is no bounds check; bits are shifted in row by row.
+template <int W>
+__device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg, uint32_t code_base, const uint32_t* __restrict__ bm) {
+    __builtin_assume(__isShared(seg));
+    uint32_t x[W + 1];
+    if constexpr (W % 4 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 4; ++i) {
+            uint4 v = reinterpret_cast<const uint4*>(seg)[i];
+            x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        }
+    } else if constexpr (W % 2 == 0) {
+#pragma unroll
+        for (int i = 0; i < W / 2; ++i) {
+            uint2 v = reinterpret_cast<const uint2*>(seg)[i];
+            x[2 * i] = v.x; x[2 * i + 1] = v.y;
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) x[i] = seg[i];
     }
-    return word;
+    x[W] = 0;
+    uint32_t word = 0;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int bit = j * W, wi = bit >> 5, sh = bit & 31;
+        uint32_t f = (sh + W <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
+        uint32_t code = (f & ((1u << W) - 1u)) + code_base;
+        uint32_t wv = __ldg(bm + (code >> 5));
+        word = __funnelshift_r(word, __funnelshift_r(wv, 0u, code), 1);   // shift bit (code & 31) of wv in from the top
+    }
+    return word;   // after 32 steps row j sits at bit j
+}
+
+__device__ __noinline__ uint32_t leaf_code32_dispatch(const uint32_t* __restrict__ seg, uint32_t w, uint32_t code_base, const uint32_t* __restrict__ bm) {
+    switch (w) {
+#define KX_CASE(W) case W: return leaf_code32<W>(seg, code_base, bm);
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+#undef KX_CASE
+    }
+    return 0;
+}
+
+__device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
+                                                 uint32_t code_base, const uint32_t* __restrict__ bm) {
+    if (lane >= Rp) return 0;
+    return leaf_code32_dispatch(sw + (size_t)(g0 + lane) * w, w, code_base, bm);   // dictionary codes are uint16: w <= 16
 }
 
 // ---- IN / NOT IN on a bit-packed / raw integer block (int_bitpack.go:249-291, int_raw.go:339-380): the
@@ -364,13 +433,14 @@ __device__ __forceinline__ uint32_t hash_bucket(uint64_t v, uint32_t log2nb) {
 }
 __device__ __forceinline__ uint32_t leaf_hashset(const uint32_t* __restrict__ sw, const ColView& v, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  const ulonglong2* __restrict__ tab, uint32_t log2nb) {
+    __builtin_assume(__isShared(sw));
     if (lane >= Rp) return 0;
     const uint32_t w = v.width;
     const int type = v.type;
     const uint64_t base = v.base;
     uint32_t bit = (g0 + lane) * 32u * w;
     uint32_t word = 0;
-#pragma unroll 4
+#pragma unroll 8
     for (uint32_t j = 0; j < 32; ++j, bit += w) {
         uint64_t val = type_ext(type, load_field(sw, bit, w) + base);
         const ulonglong2* b = tab + 2u * (size_t)hash_bucket(val, log2nb);
@@ -555,6 +625,30 @@ __device__ __forceinline__ void agg_pass_generic(AggAcc& A, const ColView& v, in
     }
 }
 
+// ALP blocks: rows that are patches carry their true value outside the encoded stream.  One thread per patch
+// evaluates the float predicate on it (the loops over `vals, pos` of float_alp.go:238-495) and sets the bit of
+// its row in the leaf's correction stream (zeroed before the launch), which the scan ORs in / ANDs out.
+__global__ void alpfix_kernel(const AlpFixJob* __restrict__ jobs, uint8_t* __restrict__ out_base) {
+    const AlpFixJob J = jobs[blockIdx.y];
+    const uint32_t* pos = reinterpret_cast<const uint32_t*>(J.blob);
+    const double* vals = reinterpret_cast<const double*>(J.blob + alp_vals_off(J.np));
+    uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
+    const double a = __longlong_as_double((long long)J.a), b = __longlong_as_double((long long)J.b);
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < J.np; k += gridDim.x * blockDim.x) {
+        const double x = vals[k];
+        bool p;
+        switch (J.mode) {
+        case 1: p = (a != a) ? (x != x) : (x == a); break;   // MatchEqual: a NaN operand matches NaN patches
+        case 3: p = x > a; break;
+        case 4: p = x >= a; break;
+        case 5: p = x < a; break;
+        case 6: p = x <= a; break;
+        default: p = x >= a && x <= b; break;                  // MatchBetween
+        }
+        if (p != (J.invert != 0)) { uint32_t r = pos[k]; atomicOr(out + (r >> 5), 1u << (r & 31u)); }
+    }
+}
+
 // Run-end blocks: the predicate is evaluated once per RUN by this pre-pass (RunEndContainer.Match* +
 // applyMatch, internal/encode/int_runend.go:224-318: match the run values, SetRange(start, end) per
 // matching run); the scan kernel then streams the resulting per-leaf bitset like a 1-bit column.
@@ -601,11 +695,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     uint8_t* stage_base = smem + 128;
     __shared__ AggAcc warp_acc[CONSUMER_WARPS];
     __shared__ unsigned long long warp_cnt[CONSUMER_WARPS];
+    __shared__ unsigned int sm_match, sm_wtiles;   // matches / (warp, tile) pairs finished so far: selectivity feedback for the producer
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t R = P.R, tile_rows = R * 32u * CONSUMER_WARPS, nstages = P.stages;
 
     if (threadIdx.x == 0) {
+        sm_match = 0; sm_wtiles = 0;
         for (uint32_t s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -629,29 +725,35 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         }
     };
 
+    // Ring protocol.  SIMPLE kernels: one stage per TILE (the single leaf's stream; tiles may hold several
+    // passes).  General kernels: one stage per (tile, staged leaf) in postfix order — the stage only has to hold
+    // the widest column of 8192 rows, so multi-predicate programs keep full tiles and two CTAs per SM; the
+    // AND/OR stack lives in registers while the ring advances from one leaf column to the next.
     if (warp == CONSUMER_WARPS) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            for (uint32_t t = t_begin; t < t_end; ++t) {
+            auto load_stream = [&](const uint8_t* data, uint32_t w, uint32_t rows) {
                 mbar_wait(&empty_bar[s], ph ^ 1u);          // slot released by all consumer warps
-                uint32_t rows = min(tile_rows, pi.n - chunk * tile_rows);
+                if (!data) w = 0;
+                uint32_t bytes = w ? ((((rows * w + 7u) >> 3) + 15u) & ~15u) : 0u;
+                mbar_expect_tx(&full_bar[s], bytes);        // arrive (count 1) + expected bytes
+                if (bytes) tma_load_1d(stage_base + (size_t)s * P.stage_bytes, data + (size_t)chunk * (tile_rows / 8u) * w, bytes, &full_bar[s]);
+                if (++s == nstages) { s = 0; ph ^= 1u; }
+            };
+            for (uint32_t t = t_begin; t < t_end; ++t) {
+                const uint32_t rows = min(tile_rows, pi.n - chunk * tile_rows);
                 const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
-                uint32_t total = 0;
-                for (uint32_t l = 0; l < P.nleaves; ++l)
-                    if (L[l].data) total += (((rows * (uint32_t)L[l].width + 7u) >> 3) + 15u) & ~15u;
-                mbar_expect_tx(&full_bar[s], total);        // arrive (count 1) + expected bytes
-                uint8_t* dst = stage_base + (size_t)s * P.stage_bytes;
-                for (uint32_t l = 0; l < P.nleaves; ++l) {
-                    if (!L[l].data) continue;
-                    uint32_t w = L[l].width;
-                    uint32_t bytes = (((rows * w + 7u) >> 3) + 15u) & ~15u;
-                    const uint8_t* src = L[l].data + (size_t)chunk * (tile_rows / 8u) * w;
-                    tma_load_1d(dst, src, bytes, &full_bar[s]);
-                    dst += (tile_rows / 8u) * w + 16u;      // slot = full-tile bytes + over-read pad
+                if (SIMPLE) load_stream(L[0].data, L[0].width, rows);   // (an unstaged leaf still cycles its stage: lockstep)
+                else {
+                    for (uint32_t i = 0; i < P.npost; ++i) {
+                        uint32_t op = P.postfix[i];
+                        if (op >= 0x80u) continue;
+                        if (L[op].data) load_stream(L[op].data, L[op].width, rows);
+                        if (L[op].fixmode) load_stream(L[op].fix, 1u, rows);      // ALP patch correction stream
+                    }
                 }
                 if (t + 1 < t_end) next_tile();
-                if (++s == nstages) { s = 0; ph ^= 1u; }
             }
         }
         return;
@@ -661,9 +763,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     AggAcc acc[SIMPLE ? 1 : MAX_AGGS];
 #pragma unroll
     for (int j = 0; j < (SIMPLE ? 1 : MAX_AGGS); ++j) acc[j] = agg_identity(SIMPLE ? 0 : P.agg_type[j]);
-    unsigned long long nmatch = 0;   // rows this thread reduced
+    unsigned long long nmatch = 0;   // matches this thread accounted for (per-CTA totals only)
     uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
-    const uint32_t passes = (R + 31u) >> 5, Rp = min(R, 32u);
+    uint32_t lane_cnt_tile = 0;      // matches of the current tile (general kernels: one pass per tile)
+    uint32_t pf_m0 = 0, pf_d0 = 0;   // thread 0: selectivity feedback snapshot for the value-column prefetch
+    bool pf_dense = false;
+    const uint32_t passes = SIMPLE ? ((R + 31u) >> 5) : 1u, Rp = min(R, 32u);   // general kernels: R <= 32
 
     auto flush_count = [&](uint32_t pk) {
         uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
@@ -675,108 +780,65 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
         const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
-        const uint8_t* stage = stage_base + (size_t)s * P.stage_bytes;
 
-        uint32_t leaf_off[SIMPLE ? 1 : MAX_LEAVES];
-        if (SIMPLE) leaf_off[0] = 0;
-        else {
-            uint32_t off = 0;
-            for (uint32_t l = 0; l < P.nleaves; ++l) {
-                leaf_off[l] = off;
-                if (L[l].data) off += (tile_rows / 8u) * L[l].width + 16u;
-            }
-        }
-
-        mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
-
-        for (uint32_t pass = 0; pass < passes; ++pass) {
-            const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
-            const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
-
-            auto eval_leaf = [&](uint32_t li) -> uint32_t {
-                const PackLeaf& lf = L[li];
-                const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage + leaf_off[SIMPLE ? 0 : li]);
-                uint32_t word;
-                if constexpr (ONLY32) {
-                    if (lf.mode == LM_RANGE32) word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d);
-                    else word = lf.mode == LM_ALL ? 0xffffffffu : 0u;
-                    return lf.neg ? ~word : word;
-                }
-                switch (lf.mode) {
-                case LM_NONE: word = 0; break;
-                case LM_ALL: word = 0xffffffffu; break;
-                case LM_RANGE32: word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d); break;
-                case LM_RANGE64: word = leaf_range64(sw, lf.width, g0, Rp, lane, lf.a, lf.d, lf.wm); break;
-                case LM_FLOAT: word = leaf_float(sw, lf.width, g0, Rp, lane, lf.fop, lf.a, lf.d); break;
-                case LM_ROWRANGE: {
-                    // rows [a, a+d] of the pack → bits of this lane's word
-                    uint64_t lo = lf.a, hi = lf.a + lf.d;
-                    word = 0;
-                    if (hi >= wr && lo < wr + 32u) {
-                        uint32_t b0 = lo > wr ? (uint32_t)(lo - wr) : 0u;
-                        uint32_t b1 = hi < wr + 31u ? (uint32_t)(hi - wr) : 31u;
-                        word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
-                    }
-                    break;
-                }
-                case LM_BITS: word = lane < Rp ? sw[g0 + lane] : 0u; break;   // precomputed leaf bitset (run-end pre-pass)
-                case LM_CODESET:
-                    word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, P.code_bits + lf.a, (uint32_t)lf.d);
-                    break;
-                case LM_HASHSET:
-                    word = leaf_hashset(sw, P.views[lf.view], g0, Rp, lane,
-                                        reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]), P.tab_log2[li]);
-                    break;
-                default: {
-                    const ColView& v = P.views[lf.view];
-                    if (v.kind == CK_RUNEND) word = leaf_runend(lf, v, (uint32_t)wr, pi.n, lane < Rp, P.set_vals);
-                    else word = leaf_generic(lf, v, lf.data ? sw : nullptr, pack_row0, g0, Rp, lane, pi.n, P.set_vals);
-                    break;
-                }
-                }
-                return lf.neg ? ~word : word;
-            };
-
+        // one leaf for one pass: sw = the leaf's staged stream (or nullptr), g0 = first group of the pass
+        auto eval_leaf = [&](uint32_t li, const uint32_t* sw, uint32_t g0, uint64_t wr) -> uint32_t {
+            const PackLeaf& lf = L[li];
             uint32_t word;
-            if (SIMPLE) {
-                word = eval_leaf(0);
-            } else {
-                // evaluate the leaves and the AND/OR program on word-per-lane bitsets
-                uint32_t stack[MAX_LEAVES];
-                int sp = 0;
-                for (uint32_t i = 0; i < P.npost; ++i) {
-                    uint32_t op = P.postfix[i];
-                    if (op < 0x80u) {
-                        stack[sp++] = eval_leaf(op);
-                    } else {
-                        uint32_t y = stack[--sp];
-                        stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
-                    }
+            if constexpr (ONLY32) {
+                if (lf.mode == LM_RANGE32) word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d);
+                else word = lf.mode == LM_ALL ? 0xffffffffu : 0u;
+                return lf.neg ? ~word : word;
+            }
+            switch (lf.mode) {
+            case LM_NONE: word = 0; break;
+            case LM_ALL: word = 0xffffffffu; break;
+            case LM_RANGE32: word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d); break;
+            case LM_RANGE64: word = leaf_range64(sw, lf.width, g0, Rp, lane, lf.a, lf.d, lf.wm); break;
+            case LM_FLOAT: word = leaf_float(sw, lf.width, g0, Rp, lane, lf.fop, lf.a, lf.d); break;
+            case LM_ROWRANGE: {
+                // rows [a, a+d] of the pack → bits of this lane's word
+                uint64_t lo = lf.a, hi = lf.a + lf.d;
+                word = 0;
+                if (hi >= wr && lo < wr + 32u) {
+                    uint32_t b0 = lo > wr ? (uint32_t)(lo - wr) : 0u;
+                    uint32_t b1 = hi < wr + 31u ? (uint32_t)(hi - wr) : 31u;
+                    word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
                 }
-                word = stack[0];
+                break;
             }
-
-            // all shared-memory reads of this stage are done: hand the slot back to the producer early
-            if (pass + 1 == passes) {
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&empty_bar[s]);
+            case LM_BITS: __builtin_assume(__isShared(sw)); word = lane < Rp ? sw[g0 + lane] : 0u; break;   // precomputed leaf bitset (run-end pre-pass)
+            case LM_CODESET:
+                word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, P.code_bits + lf.a);
+                break;
+            case LM_HASHSET:
+                word = leaf_hashset(sw, P.views[lf.view], g0, Rp, lane,
+                                    reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]), P.tab_log2[li]);
+                break;
+            default: {
+                const ColView& v = P.views[lf.view];
+                if (v.kind == CK_RUNEND) word = leaf_runend(lf, v, (uint32_t)wr, pi.n, lane < Rp, P.set_vals);
+                else word = leaf_generic(lf, v, lf.data ? sw : nullptr, pack_row0, g0, Rp, lane, pi.n, P.set_vals);
+                break;
             }
+            }
+            return lf.neg ? ~word : word;
+        };
 
+        // tail masking, bitset store, popcount and the fused reduce for one pass
+        auto emit = [&](uint32_t word, uint32_t g0, uint64_t wr) {
             // mask rows past the end of the pack (tail bits must be zero) and lanes >= Rp
-            {
-                uint32_t valid = 0;
-                if (lane < Rp && wr < pi.n) {
-                    uint32_t left = pi.n - (uint32_t)wr;
-                    valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
-                }
-                word &= valid;
+            uint32_t valid = 0;
+            if (lane < Rp && wr < pi.n) {
+                uint32_t left = pi.n - (uint32_t)wr;
+                valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
             }
-
+            word &= valid;
             // outputs: bitset words (coalesced 128 B per warp), per-pack match count
             if (P.bitsets && lane < Rp && wr < pi.n)
                 *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
             lane_cnt += __popc(word);
-
+            lane_cnt_tile = __popc(word);
             // fused reduce over the matching rows of the value columns, read on demand from global memory
             // (32-row groups without a match are never touched)
             if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
@@ -796,6 +858,84 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 }
                 nmatch += __popc(word);   // per-CTA totals only: any partition of the matches over threads will do
             }
+        };
+
+        if (SIMPLE) {
+            const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+            mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
+                const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
+                uint32_t word = eval_leaf(0, sw, g0, wr);
+                if (pass + 1 == passes) {   // all shared-memory reads of this stage are done: release it early
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&empty_bar[s]);
+                }
+                emit(word, g0, wr);
+            }
+            if (++s == nstages) { s = 0; ph ^= 1u; }
+        } else {
+            // Value columns are read on demand (rows that do not match cost nothing).  When the recent tiles
+            // matched densely (> 1/16 of their rows: almost every DRAM burst of the column is touched anyway)
+            // one thread prefetches the NEXT tile's slice of the value columns into L2 — one tile ahead only, so
+            // that the 296 CTAs' prefetch windows stay far below the L2 capacity.
+            if (P.naggs && threadIdx.x == 0 && chunk + 1 < pack_tiles) {
+                uint32_t m = *(volatile unsigned int*)&sm_match, d = *(volatile unsigned int*)&sm_wtiles;
+                if (d - pf_d0 >= CONSUMER_WARPS) {
+                    pf_dense = (uint64_t)(m - pf_m0) * 16u * CONSUMER_WARPS > (uint64_t)(d - pf_d0) * tile_rows;
+                    pf_m0 = m; pf_d0 = d;
+                }
+                if (pf_dense) {
+                    const size_t r0 = (size_t)(chunk + 1) * tile_rows, r1 = min((size_t)pi.n, r0 + tile_rows);
+                    for (uint32_t j = 0; j < P.naggs; ++j) {
+                        const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                        if ((v.kind != CK_BITS && v.kind != CK_DICT && v.kind != CK_ALP) || v.width == 0) continue;
+                        size_t b0 = ((r0 * v.width) >> 3) & ~(size_t)15, b1 = (r1 * v.width + 7) >> 3;
+                        tma_prefetch_l2(v.data + b0, (uint32_t)((b1 - b0 + 15) & ~(size_t)15));
+                    }
+                }
+            }
+            // evaluate the leaves and the AND/OR program on word-per-lane bitsets; every staged leaf
+            // consumes (and releases) one ring stage
+            const uint32_t g0 = warp * R;
+            const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;
+            uint32_t stack[MAX_LEAVES];
+            int sp = 0;
+            for (uint32_t i = 0; i < P.npost; ++i) {
+                uint32_t op = P.postfix[i];
+                if (op < 0x80u) {
+                    uint32_t word;
+                    if (L[op].data) {
+                        mbar_wait(&full_bar[s], ph);
+                        word = eval_leaf(op, reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes), g0, wr);
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[s]);
+                        if (++s == nstages) { s = 0; ph ^= 1u; }
+                    } else {
+                        word = eval_leaf(op, nullptr, g0, wr);
+                    }
+                    if (L[op].fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
+                        mbar_wait(&full_bar[s], ph);
+                        const uint32_t* fw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+                        __builtin_assume(__isShared(fw));
+                        uint32_t fx = lane < Rp ? fw[g0 + lane] : 0u;
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&empty_bar[s]);
+                        if (++s == nstages) { s = 0; ph ^= 1u; }
+                        word = L[op].fixmode == FIX_OR_PRED ? (word | fx) : (word & ~fx);
+                    }
+                    if (L[op].neg2) word = ~word;
+                    stack[sp++] = word;
+                } else {
+                    uint32_t y = stack[--sp];
+                    stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
+                }
+            }
+            emit(stack[0], g0, wr);
+            if (P.naggs) {   // selectivity feedback for the producer's value-column prefetch
+                uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt_tile);
+                if (lane == 0) { atomicAdd(&sm_match, c); atomicAdd(&sm_wtiles, 1u); }
+            }
         }
 
         if (t + 1 < t_end) {
@@ -803,7 +943,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             next_tile();
             if (pack != prev) flush_count(prev);
         }
-        if (++s == nstages) { s = 0; ph ^= 1u; }
     }
     flush_count(pack);
 
@@ -1077,8 +1216,7 @@ __global__ void prune_kernel(PruneParams P) {
 // ------------------------------------------------------------------------------ launchers
 static int grid_for(uint64_t items, uint64_t cap) { uint64_t g = (items + 255) / 256; return (int)(g < cap ? g : cap); }
 
-cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream) {
-    const bool simple = P.nleaves == 1 && P.naggs == 0;
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool simple, bool only32, int ctas_per_sm, cudaStream_t stream) {
     int variant = !simple ? 0 : (!only32 ? 1 : (ctas_per_sm >= 3 ? 3 : 2));
     void (*kern)(const ScanParams) = scan_kernel<false, false, 2>;
     if (variant == 1) kern = scan_kernel<true, false, 2>;
@@ -1097,6 +1235,14 @@ cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool o
         if (dev >= 0 && dev < 64) configured[dev][variant] = true;
     }
     kern<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream) {
+    if (njobs == 0 || max_patches == 0) return cudaSuccess;
+    uint32_t gx = (max_patches + 255u) / 256u;
+    if (gx > 148u) gx = 148u;
+    alpfix_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs, out_base);
     return cudaGetLastError();
 }
 

@@ -25,6 +25,10 @@ enum ColKind : uint8_t {
                     // (IntBitpacked verbatim; IntRaw / FloatRaw are the width = 8*sizeof(T) case)
     CK_DICT = 4,    // CK_BITS stream of codes (+ delta as code base); aux = dict values (u64)
     CK_RUNEND = 5,  // data = run values (u64), aux = inclusive run ends (u32)
+    CK_ALP = 6,     // FloatAlp (float64): data = min-FOR bit stream of the encoded int64 values (width, base),
+                    // value = double(field + base) * F10[factor] * IF10[exponent]; delta = exponent << 8 | factor;
+                    // aux = patch blob [positions u32 x naux | values u64 x naux | patch bitmap u32 x ceil(n/32)],
+                    // extra = the encoded replacement value stored at patch positions
 };
 
 struct ColView {
@@ -39,7 +43,11 @@ struct ColView {
     uint8_t type;    // types.BlockType
     uint8_t is_raw;  // CK_BITS: raw block (compare in T, width-bit modular arithmetic)
     uint32_t pad;
+    uint64_t extra;  // CK_ALP: replacement value of the patch slots
 };
+// CK_ALP patch blob offsets (bytes) for naux patches
+KX_HD inline size_t alp_vals_off(uint32_t np) { return ((size_t)np * 4 + 15) & ~(size_t)15; }
+KX_HD inline size_t alp_mask_off(uint32_t np) { return (alp_vals_off(np) + (size_t)np * 8 + 15) & ~(size_t)15; }   // 16 B aligned: TMA source
 
 // how a leaf predicate is evaluated for one pack
 enum LeafMode : uint8_t {
@@ -67,6 +75,19 @@ struct PackLeaf {
     uint8_t neg;           // invert the result (NE, GT, GE, NIN)
     uint8_t fop;           // LM_FLOAT: FilterMode ; float width via `width`
     uint32_t view;         // LM_SET / LM_VALRANGE: index into the ColView table of this leaf's block
+    // ALP blocks: the integer predicate above runs on the encoded values; rows that are PATCHES (values the
+    // encoding could not represent) are then corrected with a per-query 1-bit stream built by alpfix_kernel
+    // (or the block's resident patch bitmap), and the float-level NOT (MatchNotEqual) is applied last.
+    const uint8_t* fix;    // staged after the leaf's own stream when fixmode != 0
+    uint8_t fixmode;       // FIX_*
+    uint8_t neg2;          // invert after the fix
+    uint8_t pad[6];
+};
+enum : uint8_t {
+    FIX_NONE = 0,
+    FIX_OR_PRED = 1,       // word |= {patch rows whose true value satisfies the float predicate}
+    FIX_ANDNOT_NPRED = 2,  // word &= ~{patch rows whose true value does NOT satisfy it}
+    FIX_ANDNOT_ALL = 3,    // word &= ~{all patch rows}   (fix = resident patch bitmap)
 };
 
 struct PackInfo {

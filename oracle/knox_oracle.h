@@ -95,7 +95,8 @@ typedef struct ko_container {
     int      log2;       /* bitpack width */
     const uint8_t* payload; /* raw values / packed words / s8b words */
     size_t   payload_len;
-    struct ko_container* child[2]; /* dict: {Dict, Codes}; runend: {Values, Ends} */
+    struct ko_container* child[3]; /* dict: {Dict, Codes}; runend: {Values, Ends}; alp: {Values, Patches, Positions} */
+    int      alp_e, alp_f, alp_flags; /* FloatAlp: Exponent, Factor, flags (1 = patched, 2 = safe int) */
 } ko_container;
 
 /* parses one container at buf (no outer compression byte); returns bytes consumed or <0 */
@@ -107,6 +108,18 @@ void    ko_container_decode(const ko_container* c, uint64_t* dst);   /* AppendTo
 void    ko_container_match(const ko_container* c, int op, uint64_t a, uint64_t b, uint8_t* bits);
 /* MatchInSet / MatchNotInSet with the roaring set flattened to a sorted unique u64 array */
 void    ko_container_match_set(const ko_container* c, int negate, const uint64_t* set, size_t nset, uint8_t* bits);
+
+/* ---- ALP float64: internal/encode/float_alp.go, internal/encode/alp/{constants,encoder,decoder}.go ---- */
+#define KO_TFLOATALP 13
+int64_t ko_alp_encode_single(double v, int e, int f, int* ok);   /* Encoder.EncodeSingle */
+int64_t ko_alp_encode_above(double v, int e, int f);
+int64_t ko_alp_encode_below(double v, int e, int f);
+double  ko_alp_decode(int64_t enc, int e, int f);                 /* Decoder.decode */
+size_t  ko_store_alp(uint8_t* dst, const uint64_t* vals, size_t n, int e, int f);   /* e < 0: choose exponents */
+long    ko_alp_load(ko_container* c, const uint8_t* buf, size_t len);
+uint64_t ko_alp_get(const ko_container* c, size_t i);
+void    ko_alp_decode_all(const ko_container* c, uint64_t* dst);
+void    ko_alp_match(const ko_container* c, int op, uint64_t a, uint64_t b, uint8_t* bits);
 
 /* Store(): writers used to synthesise packs (return bytes written into dst) */
 size_t  ko_store_const(uint8_t* dst, uint64_t val, size_t n);

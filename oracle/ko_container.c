@@ -92,6 +92,12 @@ long ko_container_load(int type, const uint8_t* buf, size_t len, ko_container** 
         c->n = c->child[1]->n ? (size_t)ko_container_get(c->child[1], c->child[1]->n - 1) + 1 : 0;
         break;
     }
+    case KO_TFLOATALP: { /* float_alp.go:122-165 */
+        long k = ko_alp_load(c, buf, len);
+        if (k < 0) { ko_container_free(c); return -1; }
+        p = buf + k;
+        break;
+    }
     default:
         free(c);
         return -1;
@@ -105,6 +111,7 @@ void ko_container_free(ko_container* c) {
     if (!c) return;
     ko_container_free(c->child[0]);
     ko_container_free(c->child[1]);
+    ko_container_free(c->child[2]);
     free(c);
 }
 
@@ -133,6 +140,7 @@ static size_t run_of(const ko_container* ends, size_t i) {
  * int_raw.go:96, int_dict.go:101-103, int_runend.go:114-120 */
 uint64_t ko_container_get(const ko_container* c, size_t i) {
     switch (c->ctype) {
+    case KO_TFLOATALP: return ko_alp_get(c, i);
     case KO_TCONST: return c->val;
     case KO_TDELTA: return ext(c->type, (uint64_t)i * c->delta + c->val);
     case KO_TBITPACK: {
@@ -156,6 +164,7 @@ uint64_t ko_container_get(const ko_container* c, size_t i) {
 /* AppendTo(dst, nil) */
 void ko_container_decode(const ko_container* c, uint64_t* dst) {
     switch (c->ctype) {
+    case KO_TFLOATALP: ko_alp_decode_all(c, dst); return;
     case KO_TS8B: {
         uint64_t* tmp = (uint64_t*)malloc((c->n + 128) * 8);
         ko_s8b_decode(tmp, c->n + 128, (const uint64_t*)c->payload, c->payload_len / 8, 0);
@@ -455,6 +464,7 @@ void ko_container_match(const ko_container* c, int op, uint64_t a, uint64_t b, u
     case KO_TRAW: case KO_TFLOATRAW: match_raw(c, op, a, b, bits); return;
     case KO_TDICT: match_dict(c, op, a, b, bits); return;
     case KO_TS8B: match_s8b(c, op, a, b, bits); return;
+    case KO_TFLOATALP: ko_alp_match(c, op, a, b, bits); return;
     case KO_TRUNEND: { /* int_runend.go:224-294 */
         size_t nr = c->child[0]->n;
         uint8_t* vbits = (uint8_t*)calloc((nr + 7) / 8 + 8, 1);

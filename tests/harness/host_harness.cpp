@@ -39,6 +39,18 @@ struct HostBlock {
             return type_is_float(v.type) ? f : type_ext(v.type, f + v.base);
         }
         case CK_DICT: return lay.aux64[field_at(stream(), stream_len(), row, v.width) + v.delta];
+        case CK_ALP: {
+            const uint32_t np = v.naux;
+            if (np) {
+                const uint32_t* pos = reinterpret_cast<const uint32_t*>(lay.blob.data());
+                const uint64_t* pv = reinterpret_cast<const uint64_t*>(lay.blob.data() + alp_vals_off(np));
+                const uint32_t* it = std::lower_bound(pos, pos + np, row);
+                if (it != pos + np && *it == row) return pv[it - pos];
+            }
+            uint64_t f = field_at(stream(), stream_len(), row, v.width);
+            double d = alp_decode(int64_t(f + v.base), int(v.delta >> 8), int(v.delta & 0xff));
+            uint64_t u; std::memcpy(&u, &d, 8); return u;
+        }
         case CK_RUNEND: {
             size_t lo = 0, hi = lay.aux32.size();
             while (lo < hi) { size_t m = (lo + hi) / 2; if (lay.aux32[m] >= row) hi = m; else lo = m + 1; }
@@ -120,6 +132,21 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
         case LM_VALRANGE: p = ((hb.value(row) ^ L.wm) - L.a) <= L.d; break;
         }
         if (L.neg && L.mode != LM_NONE && L.mode != LM_ALL) p = !p;
+        if (L.fixmode) {   // ALP patch correction (alpfix_kernel + the fix stage of scan_kernel)
+            const uint32_t np = v.naux;
+            const uint32_t* pos = reinterpret_cast<const uint32_t*>(hb.lay.blob.data());
+            const uint64_t* pvs = reinterpret_cast<const uint64_t*>(hb.lay.blob.data() + alp_vals_off(np));
+            const uint32_t* it = std::lower_bound(pos, pos + np, row);
+            if (it != pos + np && *it == row) {
+                double x, fa, fb; std::memcpy(&x, &pvs[it - pos], 8); std::memcpy(&fa, &a, 8); std::memcpy(&fb, &b, 8);
+                int m = mode == 2 ? 1 : mode;
+                bool pred = m == 1 ? ((fa != fa) ? (x != x) : (x == fa)) : fpred(m, x, fa, fb);
+                if (L.fixmode == FIX_OR_PRED) p = p || pred;
+                else if (L.fixmode == FIX_ANDNOT_NPRED) p = p && pred;
+                else p = false;
+            }
+        }
+        if (L.neg2) p = !p;
         if (p) bits[row >> 3] |= uint8_t(1u << (row & 7));
     }
     return long(v.n);

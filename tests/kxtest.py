@@ -96,7 +96,7 @@ def harness():
         srcs = [os.path.join(HARNESS_DIR, "host_harness.cpp"), os.path.join(ROOT, "knoxdb_b200", "csrc", "kx_host.cpp")]
         deps = srcs + [os.path.join(ROOT, "knoxdb_b200", "csrc", f) for f in ("kx_host.h", "kx_types.h")]
         if not os.path.exists(HARNESS_SO) or any(os.path.getmtime(d) > os.path.getmtime(HARNESS_SO) for d in deps):
-            subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-o", HARNESS_SO] + srcs)
+            subprocess.check_call(["g++", "-std=c++17", "-O2", "-ffp-contract=off", "-fPIC", "-shared", "-o", HARNESS_SO] + srcs)
         L = C.CDLL(HARNESS_SO)
         vp = C.c_void_p
         L.kxh_match.restype = C.c_long

@@ -16,6 +16,7 @@ SO = os.path.join(ODIR, "libknox_oracle.so")
 I64, I32, I16, I8, U64, U32, U16, U8, F64, F32 = range(1, 11)
 EQ, NE, GT, GE, LT, LE, IN, NI, RG = range(1, 10)
 TCONST, TDELTA, TRUNEND, TBITPACK, TDICT, TS8B, TRAW, TFLOATRAW = 1, 2, 3, 4, 5, 6, 7, 15
+TFLOATALP = 13
 
 NP = {I64: np.int64, I32: np.int32, I16: np.int16, I8: np.int8, U64: np.uint64, U32: np.uint32,
       U16: np.uint16, U8: np.uint8, F64: np.float64, F32: np.float32}
@@ -75,6 +76,9 @@ def lib():
             "ko_store_runend": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
             "ko_store_s8b": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t]),
             "ko_store_bound": (C.c_size_t, [C.c_int, C.c_size_t]),
+            "ko_store_alp": (C.c_size_t, [vp, vp, C.c_size_t, C.c_int, C.c_int]),
+            "ko_alp_encode_single": (C.c_int64, [C.c_double, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+            "ko_alp_decode": (C.c_double, [C.c_int64, C.c_int, C.c_int]),
             "ko_s8b_encode": (C.c_size_t, [vp, vp, C.c_size_t, C.c_uint64]),
             "ko_s8b_decode": (C.c_size_t, [vp, C.c_size_t, vp, C.c_size_t, C.c_uint64]),
             "ko_xxh3_u64": (C.c_uint64, [C.c_uint64]),
@@ -184,7 +188,8 @@ class Container:
 class _KoContainer(C.Structure):
     _fields_ = [("ctype", C.c_int), ("type", C.c_int), ("n", C.c_size_t), ("val", C.c_uint64),
                 ("delta", C.c_uint64), ("log2", C.c_int), ("payload", C.c_void_p),
-                ("payload_len", C.c_size_t), ("child", C.c_void_p * 2)]
+                ("payload_len", C.c_size_t), ("child", C.c_void_p * 3), ("alp_e", C.c_int), ("alp_f", C.c_int),
+                ("alp_flags", C.c_int)]
 
 
 def store(kind, type_, values=None, **kw):
@@ -199,6 +204,11 @@ def store(kind, type_, values=None, **kw):
         n = L.ko_store_delta(_p(buf), scalar_u64(type_, kw["base"]), scalar_u64(type_, kw["delta"]), kw["n"])
         return buf[:n].tobytes()
     v = as_u64(type_, values)
+    if kind == "alp":   # FloatAlpContainer[float64,int64]; e/f: exponents (default: chosen by sampling)
+        assert type_ == F64
+        buf = np.zeros(3 * L.ko_store_bound(I64, v.size) + 64, dtype=np.uint8)
+        n = L.ko_store_alp(_p(buf), _p(v), v.size, kw.get("e", -1), kw.get("f", -1))
+        return buf[:n].tobytes()
     buf = np.zeros(L.ko_store_bound(type_, v.size), dtype=np.uint8)
     fn = {"raw": L.ko_store_raw, "bitpack": L.ko_store_bitpack, "dict": L.ko_store_dict,
           "runend": L.ko_store_runend, "s8b": L.ko_store_s8b}.get(kind)

@@ -431,3 +431,50 @@ def test_resident_stats_index_bloom_build_and_prune(ctx):
     with pytest.raises(kb.KnoxError):
         ctx.scan(prog, [(0, 1)], nrows=[1])      # byte-string programs are prune-only
     prog.close(); prog2.close(); st.close()
+
+
+def test_alp_float_blocks(ctx):
+    """FloatAlpContainer on the device: Match* through the encoded integer domain + patch
+    correction stream, AppendTo (decode) and the fused reduce over an ALP value column — all against the oracle's
+    restatement of float_alp.go, bit for bit (bitsets, counts, min/max) / 1e-12 (float sums)."""
+    import knoxdb_b200 as kb
+    import test_host_translation as tht
+    t = ko.F64
+    for n in (1, 33, 1000, 8192 + 77, 70_000):
+        for name, vals in tht.alp_columns(RNG, n).items():
+            blob = ko.store("alp", t, vals)
+            oc = ko.Container(t, blob)
+            got = ctx.container_decode(kb.FLOAT64, blob, n)
+            assert (got.view(np.uint64) == oc.decode()).all(), (n, name)
+            for a in tht.alp_operands(vals)[:: 2 if n > 10_000 else 1]:
+                for b in (a + 2.5, a - 1.0):
+                    for op in kt.OPS:
+                        ua, ub = ko.scalar_u64(t, a), ko.scalar_u64(t, b)
+                        want = oc.match(op, ua, ub)
+                        bits, cnt = ctx.container_match(kb.FLOAT64, blob, op, a, b, nrows=n)
+                        assert (bits == want).all(), (n, name, op, a, b)
+                        assert cnt == int(np.unpackbits(want).sum())
+    # scan with two ALP columns: price < p AND qty >= q, sum/min/max(price) and an int column
+    n = 200_003
+    price = np.round(RNG.uniform(0, 500, n), 2); price[::53] = RNG.uniform(0, 1, price[::53].size)
+    qty = np.round(RNG.uniform(0, 50, n), 1); qty[::101] = RNG.uniform(0, 1, qty[::101].size) * np.pi
+    ident = RNG.integers(0, 10**9, n).astype(np.int64)
+    blobs = {1: (kb.FLOAT64, ko.store("alp", t, price)), 2: (kb.FLOAT64, ko.store("alp", t, qty)), 3: (kb.INT64, ko.store("best", ko.I64, ident))}
+    for f, (bt, b) in blobs.items():
+        assert ctx.block_put(77, 1, f, bt, b) == n
+    prog = kb.Program(ctx, [kb.Leaf(1, kb.FLOAT64, kb.LT, 250.0), kb.Leaf(2, kb.FLOAT64, kb.GE, 12.3)])
+    res = ctx.scan(prog, [(77, 1)], nrows=[n], want_bitsets=True, aggs=[(1, kb.FLOAT64), (3, kb.INT64)])
+    l0 = ko.Container(t, blobs[1][1]).match(ko.LT, ko.scalar_u64(t, 250.0))
+    l1 = ko.Container(t, blobs[2][1]).match(ko.GE, ko.scalar_u64(t, 12.3))
+    want = ko.tree_eval([0, 1, 0xFE], [l0, l1], n)
+    assert (res["bitsets"][0] == want).all() and int(res["counts"][0]) == int(np.unpackbits(want).sum())
+    ap = ko.reduce(t, ko.Container(t, blobs[1][1]).decode().view(np.float64), want)
+    ai = ko.reduce(ko.I64, ident, want)
+    g0, g1 = res["aggs"]
+    assert g0.count == ap.count and (g0.min_bits, g0.max_bits) == (ap.min_bits, ap.max_bits)
+    sa, sb = g0.value("sum", kb.FLOAT64), float(np.uint64(ap.sum_bits).view(np.float64))
+    assert abs(sa - sb) <= 1e-12 * abs(sb)
+    assert (g1.count, g1.sum_bits, g1.min_bits, g1.max_bits) == (ai.count, ai.sum_bits, ai.min_bits, ai.max_bits)
+    prog.close()
+    for f in blobs:
+        ctx.block_drop(77, 1, f)

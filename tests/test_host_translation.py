@@ -115,3 +115,47 @@ def test_xxh3_fixed_width_specialisations():
     for n in list(range(0, 260)) + [300, 511, 512, 513, 1024, 4097]:
         b = RNG.integers(0, 256, max(n, 1), dtype=np.uint8)
         assert kt.harness().kxh_xxh3_bytes(b.ctypes.data, n) == xxhash.xxh3_64_intdigest(b[:n].tobytes()), n
+
+
+def alp_columns(rng, n):
+    """float64 shapes for the ALP container: decimals with a few non-decimal exceptions, specials, all-exception"""
+    dec2 = np.round(rng.uniform(-1000, 1000, n), 2)
+    mixed = dec2.copy()
+    mixed[::37] = rng.uniform(-1, 1, mixed[::37].size)            # not representable with 2 decimals → patches
+    special = mixed.copy()
+    special[1 % n] = np.nan; special[5 % n] = np.inf; special[7 % n] = -np.inf; special[9 % n] = -0.0
+    ints = rng.integers(-50, 50, n).astype(np.float64)
+    const = np.full(n, 12.5)
+    return {"dec2": dec2, "mixed": mixed, "special": special, "ints": ints, "const": const,
+            "allpatch": rng.uniform(0, 1, n)}
+
+
+def alp_operands(vals):
+    fin = vals[np.isfinite(vals)]
+    ops = [float(fin[0]), float(fin[fin.size // 2]), float(fin.min()), float(fin.max()), 0.0, 0.005, -3.3333, 1e300, -1e300,
+           float(fin[0]) + 1e-9, np.nan, np.inf, -np.inf]
+    return ops
+
+
+def test_alp_host_translation_matches_oracle():
+    """FloatAlpContainer.Match* (float_alp.go:238-495): the product's translation into the encoded integer domain +
+    patch correction equals the oracle's restatement, which equals the scalar predicate on the original floats
+    wherever the reference itself is exact."""
+    t = ko.F64
+    for n in (1, 33, 640, 5000):
+        for name, vals in alp_columns(RNG, n).items():
+            for e, f in ((-1, -1), (2, 0), (14, 12)):
+                blob = ko.store("alp", t, vals, e=e, f=f)
+                oc = ko.Container(t, blob)
+                out = np.zeros(n, dtype=np.uint64)
+                assert kt.harness().kxh_decode(t, np.frombuffer(blob, np.uint8).copy().ctypes.data, len(blob), out.ctypes.data, n) == n
+                assert (out == oc.decode()).all(), (name, e, f)
+                # decode is lossless except for the sign of zero (the reference does not special-case -0.0)
+                assert (out.view(np.float64)[~np.isnan(vals)] == vals[~np.isnan(vals)]).all()
+                for a in alp_operands(vals):
+                    for b in (a + 2.5, a, a - 1.0):
+                        for op in kt.OPS:
+                            ua, ub = ko.scalar_u64(t, a), ko.scalar_u64(t, b)
+                            want = oc.match(op, ua, ub)
+                            got, _ = kt.host_match(t, blob, n, op, ua, ub)
+                            assert (got == want).all(), (n, name, e, f, op, a, b)

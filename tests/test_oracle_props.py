@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import oracle as ko
+import kxtest as kt
 
 RNG = np.random.default_rng(20251018)
 SIZES_RT = [1, 7, 15, 16, 128, 1024, 1025]          # bitpack/tests/tests.go:49
@@ -272,3 +273,51 @@ def test_delta_between_reference_quirk():
     assert c.match(ko.RG, 95, 135).tolist() == [0b00001110]
     # aligned below For: correct
     assert c.match(ko.RG, 90, 135).tolist() == [0b00001111]
+
+
+def test_alp_container_roundtrip_and_predicates():
+    """FloatAlpContainer (float_alp.go): Store/Load round trip and Match* against the scalar predicate on the
+    original floats (EnsureBits style, internal/encode/tests/tests.go:140-205) for finite, non-degenerate operands;
+    the reference's behaviour for +Inf / -Inf operands and for ranges narrower than the decimal grid is pinned separately."""
+    rng = np.random.default_rng(11)
+    for n in (1, 7, 64, 1000, 4099):
+        v = np.round(rng.uniform(-500, 500, n), 3)
+        v[::29] = rng.uniform(-1, 1, v[::29].size)
+        if n > 20:
+            v[3] = np.nan; v[11] = np.inf; v[12] = -np.inf
+        blob = ko.store("alp", ko.F64, v)
+        c = ko.Container(ko.F64, blob)
+        assert c.ctype == ko.TFLOATALP and c.n == n
+        assert np.array_equal(c.decode().view(np.float64), v, equal_nan=True)
+        fin = v[np.isfinite(v)]
+        with np.errstate(invalid="ignore"):
+            for a in (float(fin[0]), float(np.median(fin)), 0.0, 0.0005, -77.77, float(fin.max()) + 1, float(fin.min()) - 1):
+                b = a + 10.0
+                for op, fn in kt.OPS.items():
+                    want = kt.pack_bits(fn(v, a, b))
+                    got = c.match(op, ko.scalar_u64(ko.F64, a), ko.scalar_u64(ko.F64, b))
+                    assert (got == want).all(), (n, op, a, b)
+        # NaN operands: EQ matches NaN patches (float_alp.go:273-279), every ordered compare matches nothing
+        nanbits = ko.scalar_u64(ko.F64, np.nan)
+        assert (c.match(ko.EQ, nanbits) == kt.pack_bits(np.isnan(v))).all()
+        for op in (ko.LT, ko.LE, ko.GT, ko.GE, ko.RG):
+            assert not c.match(op, nanbits, nanbits).any()
+
+
+def test_alp_reference_quirks_are_pinned():
+    """Behaviour the reference has on amd64 and the oracle restates (the product must reproduce it, not "fix" it):
+    (1) MatchLess(+Inf) converts the infinite operand with a float→int cast that yields MinInt64 (EncodeBelow), so it
+    matches no encoded value, while MatchLessEqual(+Inf) short-circuits to all ones (float_alp.go:297-371);
+    (2) EncodeAbove / EncodeBelow (alp/encoder.go:118-125) apply the magic-number rounding BEFORE ceil / floor, so an
+    operand between two grid points is moved to the NEAREST grid point: Less(5.9) on an integer grid also matches 6,
+    Between(5.1, 5.9) matches 5 and 6."""
+    v = np.random.default_rng(3).permutation(np.arange(1, 802)).astype(np.float64)   # integer grid (e = f = 0): no patches, bit-packed
+    c = ko.Container(ko.F64, ko.store("alp", ko.F64, v, e=0, f=0))
+    inf = ko.scalar_u64(ko.F64, np.inf)
+    assert not c.match(ko.LT, inf).any()                                  # although every value is < +Inf
+    assert int(np.unpackbits(c.match(ko.LE, inf)).sum()) == v.size        # LE(+Inf) short-circuits to all ones
+    assert int(np.unpackbits(c.match(ko.GT, ko.scalar_u64(ko.F64, -np.inf))).sum()) == v.size   # MinInt64 happens to be right here
+    got = kt.unpack_bits(c.match(ko.LT, ko.scalar_u64(ko.F64, 5.9)), v.size)
+    assert (got == (v <= 6)).all()
+    got = kt.unpack_bits(c.match(ko.RG, ko.scalar_u64(ko.F64, 5.1), ko.scalar_u64(ko.F64, 5.9)), v.size)
+    assert (got == ((v == 5) | (v == 6))).all()
