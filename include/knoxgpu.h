@@ -130,6 +130,23 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
             uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
             const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out);
 
+/* kx_scan that hands back SELECTION VECTORS instead of bitsets: what the reader and PhysicalFilter do with a match
+ * bitset — sel := bits.Indexes(hits); pack.WithSelection(sel) (internal/pack/table/reader.go:432-436,
+ * internal/operator/filter.go:29-37, Bitset.Indexes internal/bitset/iterator.go:269-290).  The bitsets stay on the
+ * device; sel receives the ascending row ids of every pack's matches, concatenated in pack order: pack i owns
+ * sel[sel_off[i] .. sel_off[i+1]).  sel_off has npacks + 1 entries.  If more than sel_cap ids match, nothing is
+ * written to sel, KX_ENOMEM is returned and sel_off[npacks] holds the required capacity. */
+int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks,
+                   uint32_t* sel, size_t sel_cap, uint64_t* sel_off, int64_t* counts,
+                   const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out);
+
+/* NumberContainer.AppendTo(dst, sel) for a batch of packs (internal/encode/int_*.go, float_raw.go, float_alp.go
+ * AppendTo with a selection; query/result.go:196-264 copies the selected rows of the result columns): decode the
+ * selected rows of `field` straight from the resident encoded blocks.  sel / sel_off as produced by
+ * kx_scan_select; dst receives sel_off[npacks] elements of block_type. */
+int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, uint8_t block_type,
+              const uint32_t* sel, const uint64_t* sel_off, void* dst);
+
 /* Same scan over blocks that still live in HOST memory (cold device cache): the blocks of
  * all referenced fields are uploaded, scanned and dropped in pipelined batches.
  * blocks[i*nfields + f] / block_len[...] = encoded block of pack i, field fields[f]. */

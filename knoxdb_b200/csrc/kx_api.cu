@@ -229,9 +229,30 @@ struct ScanJob {
     std::vector<ColView> agg_views;            // [npacks][naggs]
 };
 
+}  // namespace
+static int build_scan_job(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, const kx_agg_req* aggs, int naggs, ScanJob& job);
+namespace {
+
+// optional selection-vector output of a scan (kx_scan_select)
+struct SelectOut {
+    uint32_t* sel = nullptr; size_t cap = 0; uint64_t* off = nullptr;   // caller buffers: ids, capacity in ids, npacks + 1 offsets
+    bool overflow = false;
+};
+
 int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bitsets, const size_t* bitset_off,
-             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, SelectOut* so = nullptr) {
     const int npacks = job.npacks, nleaves = int(prog->leaves.size());
+    // selection vectors are extracted from device-resident bitsets laid out back to back (8-byte aligned)
+    std::vector<size_t> sel_layout;
+    const bool dev_bits = bitsets != nullptr || so != nullptr;
+    if (so) {
+        if (bitsets) return fail(ctx, KX_EINVAL, "selection vectors and host bitsets cannot be requested together");
+        size_t o = 0;
+        sel_layout.resize(size_t(npacks));
+        for (int p = 0; p < npacks; ++p) { sel_layout[size_t(p)] = o; o += round_up((size_t(job.nrows[size_t(p)]) + 7) / 8, 8); }
+        bitset_off = sel_layout.data();
+        for (int p = 0; p <= npacks; ++p) so->off[p] = 0;
+    }
     ctx->last_kernel_ms = ctx->last_total_ms = 0; ctx->last_launches = 0;
     if (naggs < 0 || naggs > MAX_AGGS) return fail(ctx, KX_EINVAL, "too many aggregates");
     for (int j = 0; j < naggs; ++j) {
@@ -243,6 +264,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         return KX_OK;
     }
     if (bitsets && !bitset_off) return fail(ctx, KX_EINVAL, "bitsets without bitset_off");
+    std::vector<int64_t> sel_counts;
+    if (so && !counts) { sel_counts.resize(size_t(npacks)); counts = sel_counts.data(); }
 
     // ---- per-pack / per-leaf descriptors (host), pinned staging
     size_t sz_packs = sizeof(PackInfo) * size_t(npacks), sz_leaves = sizeof(PackLeaf) * size_t(npacks) * size_t(nleaves);
@@ -375,10 +398,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     PackInfo* h_packs = reinterpret_cast<PackInfo*>(hd);
     size_t bitset_total = 0;
     for (int p = 0; p < npacks; ++p) {
-        size_t off = bitsets ? bitset_off[p] : 0;
-        if (bitsets && (off & 7)) return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8");
+        size_t off = dev_bits ? bitset_off[p] : 0;
+        if (dev_bits && (off & 7)) return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8");
         h_packs[p] = PackInfo{job.nrows[size_t(p)], tile0[size_t(p)], off};
-        if (bitsets) bitset_total = std::max(bitset_total, off + (size_t(job.nrows[size_t(p)]) + 7) / 8);
+        if (dev_bits) bitset_total = std::max(bitset_total, off + (size_t(job.nrows[size_t(p)]) + 7) / 8);
     }
     std::memcpy(hd + off_leaves, pl.data(), sz_leaves);
     ColView* h_views = reinterpret_cast<ColView*>(hd + off_views);
@@ -400,7 +423,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
     CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
-    if (bitsets) CK(ctx->d_bitsets.reserve(round_up(bitset_total, 8) + 64));
+    if (dev_bits) CK(ctx->d_bitsets.reserve(round_up(bitset_total, 8) + 64));
+    const uint64_t sel_words = so ? (round_up(bitset_total, 4) / 4) : 0;
+    if (so) {
+        CK(ctx->d_tmp2.reserve(size_t(so->cap) * 4 + 64));                       // selection ids
+        CK(ctx->d_misc.reserve(64 + size_t((sel_words + 255) / 256) * 4));      // total + per-block counts
+    }
     if (naggs) {
         CK(ctx->d_partials.reserve(sizeof(AggPartial) * size_t(grid) * naggs));
         CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS));
@@ -420,7 +448,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::memcpy(P.tab_off, prog->tab_off, sizeof(P.tab_off));
     std::memcpy(P.tab_log2, prog->tab_log2, sizeof(P.tab_log2));
     P.stages = uint32_t(geo.stages);
-    P.bitsets = bitsets ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
+    P.bitsets = dev_bits ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
     P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
     P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
     P.npacks = uint32_t(npacks); P.ntiles = ntiles;
@@ -467,6 +495,23 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // ---- results back to the host
     uint8_t* hr = static_cast<uint8_t*>(ctx->h_res.p);
     size_t res_counts = sizeof(unsigned long long) * size_t(npacks);
+    if (so && ntiles) {
+        // Bitset.Indexes for every pack (reader.go:432-436): ids are written only if they fit the caller's buffer
+        // (the per-pack counts decide that after the copy below)
+        unsigned long long total_matches = 0;
+        CK(cudaMemcpyAsync(hr, ctx->d_counts.p, res_counts, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        for (int p = 0; p < npacks; ++p) total_matches += reinterpret_cast<unsigned long long*>(hr)[p];
+        if (total_matches > so->cap) so->overflow = true;
+        else if (total_matches) {
+            CK(launch_select(P.packs, uint32_t(npacks), static_cast<const uint8_t*>(ctx->d_bitsets.p), sel_words,
+                             reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->d_misc.p) + 64), static_cast<unsigned long long*>(ctx->d_misc.p),
+                             static_cast<uint32_t*>(ctx->d_tmp2.p), ctx->stream));
+            ctx->last_launches += 3;
+            CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+            CK(cudaMemcpyAsync(so->sel, ctx->d_tmp2.p, size_t(total_matches) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
     if (counts) CK(cudaMemcpyAsync(hr, ctx->d_counts.p, res_counts, cudaMemcpyDeviceToHost, ctx->stream));
     if (naggs) CK(cudaMemcpyAsync(hr + round_up(res_counts, 64), ctx->d_aggout.p, sizeof(AggPartial) * size_t(naggs), cudaMemcpyDeviceToHost, ctx->stream));
     if (bitsets && bitset_total) CK(cudaMemcpyAsync(bitsets, ctx->d_bitsets.p, bitset_total, cudaMemcpyDeviceToHost, ctx->stream));
@@ -477,6 +522,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end)); ctx->last_total_ms = ms;
 
     if (counts) for (int p = 0; p < npacks; ++p) counts[p] = int64_t(reinterpret_cast<unsigned long long*>(hr)[p]);
+    if (so) for (int p = 0; p < npacks; ++p) so->off[p + 1] = so->off[p] + uint64_t(counts[p]);
     const AggPartial* fin = reinterpret_cast<const AggPartial*>(hr + round_up(res_counts, 64));
     for (int j = 0; j < naggs; ++j) {
         kx_agg_out o{};
@@ -721,8 +767,16 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
     if (npacks < 0 || (npacks && !packs)) return fail(ctx, KX_EINVAL, "bad pack list");
     if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
     CK(cudaSetDevice(ctx->device));
+    ScanJob job;
+    if ((rc = build_scan_job(ctx, prog, packs, npacks, aggs, naggs, job))) return rc;
+    return run_scan(ctx, prog, job, bitsets, bitset_off, counts, aggs, naggs, agg_out);
+}
+
+}  // extern "C"
+// shared by kx_scan / kx_scan_select: resolve the blocks of a pack list
+static int build_scan_job(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, const kx_agg_req* aggs, int naggs, ScanJob& job) {
     const int nleaves = int(prog->leaves.size());
-    ScanJob job; job.npacks = npacks;
+    job.npacks = npacks;
     job.nrows.resize(size_t(npacks));
     job.leaf_views.resize(size_t(npacks) * nleaves);
     job.leaf_dicts.resize(size_t(npacks) * nleaves);
@@ -743,7 +797,61 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
             job.agg_views[size_t(p) * naggs + j] = it->second.view;
         }
     }
-    return run_scan(ctx, prog, job, bitsets, bitset_off, counts, aggs, naggs, agg_out);
+    return KX_OK;
+}
+
+extern "C" {
+
+int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint32_t* sel, size_t sel_cap, uint64_t* sel_off,
+                   int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog, true);
+    if (rc) return rc;
+    if (npacks < 0 || (npacks && !packs) || !sel_off || (sel_cap && !sel)) return fail(ctx, KX_EINVAL, "kx_scan_select: bad arguments");
+    if (naggs && (!aggs || !agg_out)) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
+    CK(cudaSetDevice(ctx->device));
+    ScanJob job;
+    if ((rc = build_scan_job(ctx, prog, packs, npacks, aggs, naggs, job))) return rc;
+    SelectOut so; so.sel = sel; so.cap = sel_cap; so.off = sel_off;
+    rc = run_scan(ctx, prog, job, nullptr, nullptr, counts, aggs, naggs, agg_out, &so);
+    if (rc) return rc;
+    if (so.overflow) return fail(ctx, KX_ENOMEM, "kx_scan_select: selection buffer too small (sel_off[npacks] holds the required size)");
+    return KX_OK;
+}
+
+int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, uint8_t block_type, const uint32_t* sel,
+              const uint64_t* sel_off, void* dst) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (npacks < 0 || (npacks && (!packs || !sel_off))) return fail(ctx, KX_EINVAL, "kx_gather: bad arguments");
+    const int eb = type_bits(block_type) / 8;
+    if (!eb) return fail(ctx, KX_EINVAL, "kx_gather: unsupported block type");
+    if (npacks == 0 || sel_off[npacks] == 0) return KX_OK;
+    if (!sel || !dst) return fail(ctx, KX_EINVAL, "kx_gather: null buffers");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t total = sel_off[npacks];
+    std::vector<ColView> views(static_cast<size_t>(npacks));
+    for (int p = 0; p < npacks; ++p) {
+        auto it = ctx->store.find(BlockKey{packs[p].pack, packs[p].version, field});
+        if (it == ctx->store.end()) return fail(ctx, KX_ENOTFOUND, "kx_gather: block not resident: pack " + std::to_string(packs[p].pack));
+        if (it->second.view.type != block_type) return fail(ctx, KX_EINVAL, "kx_gather: block type mismatch");
+        if (sel_off[p + 1] < sel_off[p]) return fail(ctx, KX_EINVAL, "kx_gather: sel_off must ascend");
+        views[size_t(p)] = it->second.view;
+    }
+    // device layout: views | sel_off | sel | dst
+    size_t off_so = round_up(sizeof(ColView) * size_t(npacks), 256), off_sel = off_so + round_up(8 * (size_t(npacks) + 1), 256);
+    size_t off_dst = off_sel + round_up(size_t(total) * 4, 256);
+    CK(ctx->d_tmp.reserve(off_dst + size_t(total) * eb + 64));
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
+    CK(cudaMemcpyAsync(d, views.data(), sizeof(ColView) * size_t(npacks), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + off_so, sel_off, 8 * (size_t(npacks) + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + off_sel, sel, size_t(total) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_gather(reinterpret_cast<const ColView*>(d), reinterpret_cast<const unsigned long long*>(d + off_so), uint32_t(npacks),
+                     reinterpret_cast<const uint32_t*>(d + off_sel), total, eb, d + off_dst, ctx->stream));
+    CK(cudaMemcpyAsync(dst, d + off_dst, size_t(total) * eb, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // views / sel are host temporaries
+    return KX_OK;
 }
 
 int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,

@@ -93,6 +93,10 @@ cudaError_t launch_bitset_neg(uint32_t* buf, uint64_t nbits, cudaStream_t stream
 cudaError_t launch_bitset_popcount(const uint32_t* buf, uint64_t nbits, unsigned long long* out, cudaStream_t stream);
 cudaError_t launch_bitset_indexes(const uint32_t* buf, uint64_t nbits, uint32_t* block_tmp, unsigned long long* total,
                                   uint32_t* dst, cudaStream_t stream);
+cudaError_t launch_select(const PackInfo* packs, uint32_t npacks, const uint8_t* bits, uint64_t total_words, uint32_t* block_tmp,
+                          unsigned long long* total, uint32_t* dst, cudaStream_t stream);
+cudaError_t launch_gather(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                          int elem_bytes, void* dst, cudaStream_t stream);
 cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream);
 cudaError_t launch_prune(const PruneParams& P, cudaStream_t stream);
 

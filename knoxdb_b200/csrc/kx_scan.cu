@@ -867,6 +867,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
                 const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
                 uint32_t word = eval_leaf(0, sw, g0, wr);
+                if (L[0].neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
                 if (pass + 1 == passes) {   // all shared-memory reads of this stage are done: release it early
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -1117,6 +1118,65 @@ __global__ void bitset_scatter_kernel(const uint32_t* buf, uint64_t nbits, const
     while (wv) { uint32_t b = __ffs(wv) - 1; dst[pos++] = base + b; wv &= wv - 1; }
 }
 
+// ---- Bitset.Indexes for a whole batch of packs (reader.go:432-436: sel := bits.Indexes(hits) per pack).
+// The packs' bitsets sit at ascending offsets of one device buffer; a thread owns one 32-bit word of that
+// buffer, finds its pack by binary search over the offsets and ignores words that lie in the gaps.
+__device__ __forceinline__ uint32_t sel_word(const PackInfo* __restrict__ packs, uint32_t npacks, const uint8_t* __restrict__ bits, uint64_t w,
+                                             uint64_t total_words, uint32_t* local_word) {
+    if (w >= total_words) return 0;
+    const uint64_t byte = w * 4;
+    uint32_t lo = 0, hi = npacks;   // last pack with bitset_off <= byte
+    while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (packs[m].bitset_off <= byte) lo = m; else hi = m; }
+    const uint64_t lw = (byte - packs[lo].bitset_off) >> 2;
+    if (lw >= ((uint64_t)packs[lo].n + 31) >> 5) return 0;   // gap between two packs
+    *local_word = (uint32_t)lw;
+    return *reinterpret_cast<const uint32_t*>(bits + byte);   // tail bits past n are already zero
+}
+
+__global__ void select_counts_kernel(const PackInfo* __restrict__ packs, uint32_t npacks, const uint8_t* __restrict__ bits, uint64_t total_words,
+                                     uint32_t* __restrict__ block_counts) {
+    uint32_t lw;
+    uint32_t c = __popc(sel_word(packs, npacks, bits, (uint64_t)blockIdx.x * 256 + threadIdx.x, total_words, &lw));
+    __shared__ uint32_t ws[8];
+    uint32_t s = __reduce_add_sync(0xffffffffu, c);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { uint32_t t = 0; for (int q = 0; q < 8; ++q) t += ws[q]; block_counts[blockIdx.x] = t; }
+}
+
+__global__ void select_scatter_kernel(const PackInfo* __restrict__ packs, uint32_t npacks, const uint8_t* __restrict__ bits, uint64_t total_words,
+                                      const uint32_t* __restrict__ block_offs, uint32_t* __restrict__ dst) {
+    uint32_t lw = 0;
+    uint32_t wv = sel_word(packs, npacks, bits, (uint64_t)blockIdx.x * 256 + threadIdx.x, total_words, &lw);
+    uint32_t c = __popc(wv), incl = c;
+    for (int off = 1; off < 32; off <<= 1) { uint32_t y = __shfl_up_sync(0xffffffffu, incl, off); if ((threadIdx.x & 31) >= (uint32_t)off) incl += y; }
+    __shared__ uint32_t ws[8];
+    if ((threadIdx.x & 31) == 31) ws[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (uint32_t q = 0; q < (threadIdx.x >> 5); ++q) woff += ws[q];
+    uint32_t pos = block_offs[blockIdx.x] + woff + incl - c;
+    const uint32_t base = lw << 5;   // row id relative to the pack
+    while (wv) { uint32_t b = __ffs(wv) - 1; dst[pos++] = base + b; wv &= wv - 1; }
+}
+
+// NumberContainer.AppendTo(dst, sel) for a batch of packs (internal/encode/int_*.go AppendTo with a selection;
+// query/result.go:196-264 copies the selected rows): one thread per selected row, decode at index.
+__global__ void gather_kernel(const ColView* __restrict__ views, const unsigned long long* __restrict__ sel_off, uint32_t npacks,
+                              const uint32_t* __restrict__ sel, uint64_t total, int elem_bytes, uint8_t* __restrict__ dst) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = npacks;   // last pack with sel_off <= i
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sel_off[m] <= i) lo = m; else hi = m; }
+        uint64_t x = decode_value(views[lo], sel[i], nullptr, 0);
+        switch (elem_bytes) {
+        case 8: reinterpret_cast<uint64_t*>(dst)[i] = x; break;
+        case 4: reinterpret_cast<uint32_t*>(dst)[i] = (uint32_t)x; break;
+        case 2: reinterpret_cast<uint16_t*>(dst)[i] = (uint16_t)x; break;
+        default: dst[i] = (uint8_t)x; break;
+        }
+    }
+}
+
 // NumberContainer.AppendTo(dst, nil) / bitpack.Decode: one thread per row
 __global__ void decode_kernel(ColView v, uint8_t* dst) {
     int nb = type_bits(v.type) / 8;
@@ -1290,6 +1350,22 @@ cudaError_t launch_bitset_indexes(const uint32_t* buf, uint64_t nbits, uint32_t*
     bitset_block_counts_kernel<<<nblocks, 256, 0, stream>>>(buf, nbits, block_tmp);
     exclusive_scan_kernel<<<1, 1024, 0, stream>>>(block_tmp, nblocks, total);
     bitset_scatter_kernel<<<nblocks, 256, 0, stream>>>(buf, nbits, block_tmp, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_select(const PackInfo* packs, uint32_t npacks, const uint8_t* bits, uint64_t total_words, uint32_t* block_tmp,
+                          unsigned long long* total, uint32_t* dst, cudaStream_t stream) {
+    uint32_t nblocks = (uint32_t)((total_words + 255) / 256);
+    if (nblocks == 0) return cudaMemsetAsync(total, 0, 8, stream);
+    select_counts_kernel<<<nblocks, 256, 0, stream>>>(packs, npacks, bits, total_words, block_tmp);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(block_tmp, nblocks, total);
+    select_scatter_kernel<<<nblocks, 256, 0, stream>>>(packs, npacks, bits, total_words, block_tmp, dst);
+    return cudaGetLastError();
+}
+cudaError_t launch_gather(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                          int elem_bytes, void* dst, cudaStream_t stream) {
+    if (total == 0) return cudaSuccess;
+    int grid = grid_for(total, 148 * 16);
+    gather_kernel<<<grid ? grid : 1, 256, 0, stream>>>(views, sel_off, npacks, sel, total, elem_bytes, reinterpret_cast<uint8_t*>(dst));
     return cudaGetLastError();
 }
 cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream) {

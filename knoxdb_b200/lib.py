@@ -19,6 +19,7 @@ ABI_SYMBOLS = [
     "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
     "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
     "kx_hash_value", "kx_hash_bytes",
+    "kx_scan_select", "kx_gather",
     "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
 ]
 
@@ -85,6 +86,8 @@ def lib():
         "kx_prog_compile": (C.c_int, [vp, C.POINTER(_Leaf), C.c_int, vp, C.c_int, C.POINTER(vp)]),
         "kx_prog_free": (None, [vp]),
         "kx_scan": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
+        "kx_scan_select": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, sz, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
+        "kx_gather": (C.c_int, [vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, vp, vp]),
         "kx_scan_host": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_agg_combine": (C.c_int, [C.c_uint8, C.POINTER(AggOut), C.c_int, C.POINTER(AggOut)]),
         "kx_last_scan_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -269,6 +272,35 @@ class Context:
         if want_bitsets:
             out["bitsets"] = [bits[int(o):int(o) + (int(n) + 7) // 8] for o, n in zip(offs, nrows)]
         return out
+
+    def scan_select(self, prog, packs, cap=None, aggs=()):
+        """kx_scan_select → dict(sel (uint32 ids), sel_off (npacks + 1), counts, aggs).  cap: capacity in ids
+        (default: grows to the required size when the first call reports an overflow)."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        n = len(refs)
+        sel_off = np.zeros(n + 1, dtype=np.uint64)
+        counts = np.zeros(n, dtype=np.int64)
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs), 1))()
+        cap = 1 << 16 if cap is None else cap
+        while True:
+            sel = np.zeros(max(cap, 1), dtype=np.uint32)
+            rc = lib().kx_scan_select(self.h, prog.h, refs, n, _ptr(sel), cap, _ptr(sel_off), _ptr(counts), areq, len(aggs), aout)
+            if rc == -3 and int(sel_off[n]) > cap:
+                cap = int(sel_off[n])
+                continue
+            self._check(rc)
+            break
+        return {"sel": sel[:int(sel_off[n])], "sel_off": sel_off, "counts": counts, "aggs": list(aout)[:len(aggs)]}
+
+    def gather(self, packs, field, block_type, sel, sel_off):
+        """kx_gather: values of `field` at the selected rows, concatenated in pack order"""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        sel_off = np.ascontiguousarray(sel_off, dtype=np.uint64)
+        out = np.zeros(max(int(sel_off[-1]), 1), dtype=NP[block_type])
+        self._check(lib().kx_gather(self.h, refs, len(refs), field, block_type, _ptr(sel), _ptr(sel_off), _ptr(out)))
+        return out[:int(sel_off[-1])]
 
     def scan_host(self, prog, fields, blocks, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
         """fields: [(field id, block type)]; blocks: per pack a list of encoded blocks (np.uint8 arrays) per field."""
