@@ -320,6 +320,14 @@ def main():
     h2d = sum(int(b[0].size) for b in hb)
     d2h = int(e_total_bits) + 8 * e2e_packs
 
+    # DRAM traffic of the same kernel from the committed ncu capture (a 256-pack launch), scaled to this launch's packs
+    traffic, traffic_note = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_ncu_w20_traffic.json")))
+        traffic = (tj["dram_bytes_read"] + tj["dram_bytes_write"]) * (alg_bytes / tj["algorithmic_bytes"])
+        traffic_note = f"ncu dram__bytes_read+write of a {tj['launch']} scaled by packs ({tj['source']})"
+    except Exception:
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -330,12 +338,12 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "packs_per_step": e2e_packs,
                 "note": "kx_scan_host: encoded blocks in pinned host memory, bitsets + counts returned to pinned host memory"},
         "gpu_launches": launches,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_note,
                      "kernel": "kx::scan_kernel", "kernel_ms": k_ms, "algorithmic_bytes": alg_bytes, "peak_kind": peak_kind,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "roofline_bitset": {"achieved": achieved_bits, "unit": "GB/s", "frac": achieved_bits / peak, "kernel_ms": kb_ms,
                             "algorithmic_bytes": npacks * PACK_ROWS * (W_BITS + 1) / 8},
-        "clocks": clocks, "matches_per_step": matches,
+        "clocks": clocks, "matches_per_step": matches, "host_overhead_ms_per_step": 1e3 * wall / args.steps - k_ms,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         ncores = os.cpu_count() or 1

@@ -77,7 +77,14 @@ struct StoredBlock {
 
 struct BlockKey {
     uint32_t pack, ver; uint16_t field;
-    bool operator<(const BlockKey& o) const { return std::tie(pack, ver, field) < std::tie(o.pack, o.ver, o.field); }
+    bool operator==(const BlockKey& o) const { return pack == o.pack && ver == o.ver && field == o.field; }
+};
+struct BlockKeyHash {
+    size_t operator()(const BlockKey& k) const {
+        uint64_t x = (uint64_t(k.pack) << 32 | k.ver) * 0x9E3779B97F4A7C15ull;
+        x ^= (uint64_t(k.field) + 0x632BE59BD9B4E019ull) * 0xD6E8FEB86659FD93ull;
+        return size_t(x ^ (x >> 29));
+    }
 };
 
 }  // namespace
@@ -106,7 +113,7 @@ struct kx_ctx {
     std::string err;
 
     std::vector<Slab> slabs;
-    std::map<BlockKey, StoredBlock> store;
+    std::unordered_map<BlockKey, StoredBlock, BlockKeyHash> store;   // one lookup per (pack, field) and query: O(1)
     size_t store_enc_bytes = 0, store_dev_bytes = 0;
 
     // scratch (grow only)
