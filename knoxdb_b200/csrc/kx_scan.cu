@@ -50,6 +50,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "}\n" ::"r"(smem_addr(bar)), "r"(parity)
         : "memory");
 }
+// producer-side wait: the producer only has to notice a released slot "soon"; sleeping between polls keeps its
+// spin loop from stealing issue slots (and power) from the eight consumer warps of the CTA
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, P1;\n"
+            "}\n" : "=r"(done) : "r"(smem_addr(bar)), "r"(parity) : "memory");
+        if (done) return;
+        __nanosleep(128);
+    }
+}
 // asynchronous bulk prefetch of a global range into L2 (no completion tracking)
 __device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
     asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
@@ -200,7 +215,7 @@ __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, u
         for (int i = 0; i < W; ++i) x[i] = seg[i];
     }
     x[W] = 0;
-    uint32_t word = 0;
+    uint32_t wq[4] = {0, 0, 0, 0};   // four independent accumulators: short dependency chains, one predicated OR per row
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int bit = j * W, wi = bit >> 5, sh = bit & 31;
@@ -208,8 +223,9 @@ __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, u
         if (sh + W <= 32) t = x[wi] << (32 - sh - W);
         else t = __funnelshift_l(x[wi], x[wi + 1], 64 - sh - W);
         if (SUB) t -= a_top;
-        if (t <= lim) word |= (1u << j);
+        if (t <= lim) wq[j & 3] |= (1u << j);
     }
+    uint32_t word = (wq[0] | wq[1]) | (wq[2] | wq[3]);
     if constexpr (W == 8 || W == 16 || W == 24 || W == 32) word = __funnelshift_l(word, word, rot_rows);
     return word;
 }
@@ -734,7 +750,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
             auto load_stream = [&](const uint8_t* data, uint32_t w, uint32_t rows) {
-                mbar_wait(&empty_bar[s], ph ^ 1u);          // slot released by all consumer warps
+                mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);  // slot released by all consumer warps
                 if (!data) w = 0;
                 uint32_t bytes = w ? ((((rows * w + 7u) >> 3) + 15u) & ~15u) : 0u;
                 mbar_expect_tx(&full_bar[s], bytes);        // arrive (count 1) + expected bytes
