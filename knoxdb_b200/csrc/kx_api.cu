@@ -291,7 +291,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     bool any_fix = false;
     size_t leafbits_bytes = 0;
     uint32_t max_runs = 0;
-    uint32_t max_stage_bits = 0, code_words = 0;
+    uint32_t max_stage_bits = 0, code_words = 0, max_code_set = 0;
+    uint32_t code_leaf_words[MAX_LEAVES] = {};   // per leaf: largest code bitmap of any pack (cached in shared memory by the scan)
+    uint32_t max_agg_bits = 0;                   // widest value column that can be staged through the ring
     bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
     uint64_t total_rows = 0;
     bool uniform = true;
@@ -304,10 +306,14 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             compile_leaf(v, job.leaf_dicts[size_t(p) * nleaves + l], prog->leaves[size_t(l)], uint32_t(size_t(p) * nleaves + l), o);
             if (o.mode == LM_CODESET) {   // dictionary-set translation runs on the device, one job per (pack, leaf)
                 const LeafSpec& ls = prog->leaves[size_t(l)];
-                cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0});
+                cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0,
+                                           type_is_signed(v.type) ? 0x8000000000000000ull : 0ull});
+                max_code_set = std::max(max_code_set, uint32_t(ls.set.size()));
                 o.a = code_words;
                 // the bitmap spans every code a `width`-bit field can produce (leaf_code32 does not bounds-check)
-                code_words += uint32_t(((uint64_t(1) << v.width) + v.delta + 31u) / 32u) + 1u;
+                const uint32_t nw = uint32_t(((uint64_t(1) << v.width) + v.delta + 31u) / 32u) + 1u;
+                code_words += nw;
+                code_leaf_words[l] = std::max(code_leaf_words[l], nw);
             }
             if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
                 // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
@@ -334,8 +340,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             bits = std::max(bits, uint32_t(leaf_stage_width(o)));
             if (o.mode != LM_RANGE32 && o.mode != LM_NONE && o.mode != LM_ALL) only32 = false;
         }
-        for (int j = 0; j < naggs; ++j)
-            if (job.agg_views[size_t(p) * naggs + j].n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "value block length differs from pack");
+        for (int j = 0; j < naggs; ++j) {
+            const ColView& av = job.agg_views[size_t(p) * naggs + j];
+            if (av.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "value block length differs from pack");
+            if (agg_stageable(av)) max_agg_bits = std::max<uint32_t>(max_agg_bits, av.width);
+        }
         max_stage_bits = std::max(max_stage_bits, bits);
         total_rows += job.nrows[size_t(p)];
         if (job.nrows[size_t(p)] != job.nrows[0]) uniform = false;
@@ -348,29 +357,68 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     struct Geo { int ctas, stages; size_t budget; };
     const bool simple = nleaves == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
     const bool simple32 = only32 && simple;
+    // dictionary-code bitmaps cached in shared memory behind the ring
+    uint32_t code_smem_off[MAX_LEAVES] = {}, code_smem_words = 0;
+    for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
+    const size_t code_smem_bytes = round_up(size_t(code_smem_words) * 4, 128);
+    // Value columns of the fused reduce can be staged through the ring, agg_chunks (<= 4) stages per tile and column
+    // (KX_AGG_STAGE = never | always | <thr>: stage a tile when recent matches * thr > recent rows).  Measured on B200:
+    // reading matching rows on demand wins below ~1/3 selectivity, bulk staging above.
+    uint32_t agg_chunks = naggs ? 1 : 0, agg_dense_thr = 3;
+    if (naggs && max_agg_bits) {
+        const char* e = getenv("KX_AGG_STAGE");
+        if (e && !strcmp(e, "never")) agg_dense_thr = 0xffffffffu;
+        else if (e && !strcmp(e, "always")) agg_dense_thr = 0;
+        else if (e && atoi(e) > 0) agg_dense_thr = uint32_t(atoi(e));
+        // a chunk (1/8 … 1/1 of the tile's rows of the widest value column) must fit one ring stage
+        max_stage_bits = std::max(max_stage_bits, (max_agg_bits + 7) / 8);
+        while (agg_chunks * max_stage_bits < max_agg_bits) agg_chunks *= 2;
+    }
+    // general kernels keep the AND/OR stack of every warp and the tile's final match words in shared memory
+    uint32_t stack_depth = 0;
+    if (!simple) {
+        uint32_t sp = 0;
+        for (uint8_t op : prog->postfix) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
+    }
+    auto extra_smem_for = [&](uint32_t r) {   // bytes behind the ring: code bitmaps, stacks, final words
+        size_t words = simple ? 0 : size_t(CONSUMER_WARPS) * stack_depth * ((r + 31) / 32) * 32 + (naggs ? size_t(2) * CONSUMER_WARPS * r : 0);
+        return code_smem_bytes + round_up(words * 4, 128);
+    };
     const size_t stage_fixed = 32;
     auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
-    auto rmax_for = [&](const Geo& g) { return (g.budget - stage_fixed - 128) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)); };
+    auto rmax_for = [&](const Geo& g) { return (g.budget - code_smem_bytes / 2 - stage_fixed - 128) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)); };
     const Geo g3{3, 2, 33 * 1024}, g2{2, 2, 50 * 1024}, g1{1, 2, 99 * 1024};
     Geo geo = g2;
     uint32_t R = 32;
-    if (max_stage_bits) {
-        if (simple32 && max_stage_bits <= 16) geo = g3;
-        size_t rmax = rmax_for(geo);
-        if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
-        R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
-        if (!simple) {
-            // general kernels: one stage = one leaf column of an 8192-row tile (single pass); spend the rest of
-            // the shared memory on ring depth so that the next tile's first columns are already in flight
-            R = std::min<uint32_t>(R, 32);
-            size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(geo.ctas) - 128;
-            geo.stages = int(std::min<size_t>(4, std::max<size_t>(2, per_cta / stage_bytes_for(R))));
+    if (simple) {
+        if (max_stage_bits) {
+            if (simple32 && max_stage_bits <= 16) geo = g3;
+            size_t rmax = rmax_for(geo);
+            if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
+            R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
         }
+    } else {
+        // general kernels: one stage = one leaf column (or one value-column chunk) of a whole tile.  Large tiles let a
+        // warp run several passes through one leaf's unrolled body before it moves on (instruction-cache reuse, fewer
+        // barrier round trips per row); at least two stages must fit, more are used when the columns are narrow.
+        bool found = false;
+        for (int ctas = 2; ctas >= 1 && !found; --ctas) {
+            for (uint32_t r : {128u, 96u, 64u, 32u}) {
+                size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(ctas) - 128;
+                size_t extra = extra_smem_for(r), sb = stage_bytes_for(r);
+                if (per_cta < extra + 2 * sb) continue;
+                geo.ctas = ctas; R = r;
+                geo.stages = int(std::min<size_t>(agg_chunks > 1 ? 6 : 4, (per_cta - extra) / sb));
+                found = true;
+                break;
+            }
+        }
+        if (!found) return fail(ctx, KX_EUNSUPPORTED, "scan program does not fit the shared memory of one SM");
     }
     if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
         int c = 0, st = 0, r = 0;
-        if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 && (r <= 32 || r % 32 == 0) &&
-            128 + size_t(st) * stage_bytes_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
+        if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 && (simple ? (r <= 32 || r % 32 == 0) : r % 32 == 0) &&
+            128 + size_t(st) * stage_bytes_for(uint32_t(r)) + extra_smem_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
             geo.ctas = c; geo.stages = st; R = uint32_t(r);
         }
     }
@@ -378,7 +426,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     while (R > 32 && total_rows / (uint64_t(256) * R) < uint64_t(4) * ctx->num_sms * geo.ctas) R -= 32;
     const uint32_t tile_rows = 256 * R;
     const size_t stage_bytes = stage_bytes_for(R);
-    const size_t smem_bytes = 128 + size_t(geo.stages) * stage_bytes;
+    const size_t smem_bytes = 128 + size_t(geo.stages) * stage_bytes + extra_smem_for(R);
 
     uint64_t ntiles64 = 0;
     std::vector<uint32_t> tile0(size_t(npacks) + 1);
@@ -455,6 +503,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::memcpy(P.tab_off, prog->tab_off, sizeof(P.tab_off));
     std::memcpy(P.tab_log2, prog->tab_log2, sizeof(P.tab_log2));
     P.stages = uint32_t(geo.stages);
+    std::memcpy(P.code_smem_off, code_smem_off, sizeof(P.code_smem_off));
+    P.code_smem_words = code_smem_words;
+    P.agg_chunks = agg_chunks;
+    P.stack_off_words = uint32_t(code_smem_bytes / 4);
+    P.stack_depth = stack_depth;
+    P.agg_dense_thr = agg_dense_thr;
     P.bitsets = dev_bits ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
     P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
     P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
@@ -485,7 +539,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     }
     if (ntiles && !cjobs.empty()) {
         CK(cudaMemsetAsync(ctx->d_codebits.p, 0, size_t(code_words) * 4, ctx->stream));
-        CK(launch_codeset(reinterpret_cast<const CodesetJob*>(dd + off_cjobs), uint32_t(cjobs.size()), prog->dev_sets,
+        CK(launch_codeset(reinterpret_cast<const CodesetJob*>(dd + off_cjobs), uint32_t(cjobs.size()), max_code_set, prog->dev_sets,
                           static_cast<uint32_t*>(ctx->d_codebits.p), ctx->stream));
         ctx->last_launches++;
     }

@@ -36,6 +36,7 @@ struct CodesetJob {
     uint32_t set_off, nset;   // sorted set inside the program's set_vals
     uint32_t out_off;         // first word of the bitmap
     uint32_t pad;
+    uint64_t flip;            // sign flip that maps the dictionary's T order to unsigned order
 };
 
 // one run-end leaf of runfill_kernel: runs whose value satisfies the predicate set rows [start, end] of the
@@ -85,7 +86,7 @@ cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, u
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool simple, bool only32, int ctas_per_sm, cudaStream_t stream);
 cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
-cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
+cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, uint32_t max_set, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
 cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,
                             AggPartial* out, cudaStream_t stream);
 cudaError_t launch_bitset_op(uint32_t* dst, const uint32_t* src, uint64_t nbits, int op, unsigned int* flags, cudaStream_t stream);

@@ -388,12 +388,14 @@ __device__ __forceinline__ uint32_t leaf_float(const uint32_t* __restrict__ sw, 
 }
 
 // ---- IN / NOT IN on a dictionary block (DictionaryContainer.MatchInSet, int_dict.go:361-398): the set
-// was translated into a bitmap over the pack's codes (translateSet :400) by codeset_kernel; each lane
-// tests the 32 codes of its own group.  The bitmap covers every code a W-bit field can produce (the
-// host sizes and zeroes it), so there is no bounds check; bits are shifted in row by row.
+// was translated into a bitmap over the pack's codes (translateSet :400) by codeset_kernel; the consumers
+// copy the current pack's bitmap (<= 8 KB) into shared memory and each lane tests the 32 codes of its own
+// group.  The bitmap covers every code a W-bit field can produce (the host sizes and zeroes it), so there
+// is no bounds check; bits are shifted in row by row.
 template <int W>
 __device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg, uint32_t code_base, const uint32_t* __restrict__ bm) {
     __builtin_assume(__isShared(seg));
+    __builtin_assume(__isShared(bm));   // the pack's code bitmap is cached in shared memory (one LDS per row)
     uint32_t x[W + 1];
     if constexpr (W % 4 == 0) {
 #pragma unroll
@@ -418,7 +420,7 @@ __device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg
         const int bit = j * W, wi = bit >> 5, sh = bit & 31;
         uint32_t f = (sh + W <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
         uint32_t code = (f & ((1u << W) - 1u)) + code_base;
-        uint32_t wv = __ldg(bm + (code >> 5));
+        uint32_t wv = bm[code >> 5];
         word = __funnelshift_r(word, __funnelshift_r(wv, 0u, code), 1);   // shift bit (code & 31) of wv in from the top
     }
     return word;   // after 32 steps row j sits at bit j
@@ -506,18 +508,20 @@ __device__ __forceinline__ uint32_t leaf_generic(const PackLeaf& L, const ColVie
     return word;
 }
 
-// Dictionary-set translation (DictionaryContainer.translateSet, int_dict.go:400-440) on the device: one
-// block per (pack, leaf) job, one lane per dictionary entry, binary search in the sorted set, ballot →
-// bitmap word.  Runs on the scan stream right before scan_kernel.
+// Dictionary-set translation (DictionaryContainer.translateSet, int_dict.go:400-440) on the device: one thread per
+// SET value binary-searches the pack's dictionary (sorted, unique, in T order: `flip` maps it to unsigned order) and
+// sets the bit of the code it finds.  Runs on the scan stream right before scan_kernel; blockIdx.y = (pack, leaf) job.
 __global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, const uint64_t* __restrict__ set_vals, uint32_t* __restrict__ out) {
-    const CodesetJob J = jobs[blockIdx.x];
+    const CodesetJob J = jobs[blockIdx.y];
     const unsigned long long* dict = reinterpret_cast<const unsigned long long*>(J.dict);
-    const uint32_t lane = threadIdx.x & 31u;
-    for (uint32_t base = (threadIdx.x >> 5) * 32u; base < J.ndict; base += (blockDim.x >> 5) * 32u) {
-        uint32_t code = base + lane;
-        bool hit = code < J.ndict && set_has(set_vals + J.set_off, J.nset, __ldg(dict + code));
-        uint32_t b = __ballot_sync(0xffffffffu, hit);
-        if (lane == 0) out[J.out_off + (base >> 5)] = b;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < J.nset; i += gridDim.x * blockDim.x) {
+        const uint64_t val = __ldg(set_vals + J.set_off + i), key = val ^ J.flip;
+        uint32_t lo = 0, hi = J.ndict;   // first dictionary entry >= val
+        while (lo < hi) {
+            uint32_t m = (lo + hi) >> 1;
+            if ((__ldg(dict + m) ^ J.flip) < key) lo = m + 1; else hi = m;
+        }
+        if (lo < J.ndict && __ldg(dict + lo) == val) atomicOr(out + J.out_off + (lo >> 5), 1u << (lo & 31u));
     }
 }
 
@@ -577,27 +581,58 @@ __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) 
     }
 }
 
-// One pass (<= 32 groups of 32 rows) of the fused reduce for ONE value column.  `word` is the pass's
-// match bitset in word-per-lane form; group `it`'s word is broadcast with a shuffle and lane l reduces
-// row 32*it + l, so every load instruction reads 32 consecutive values (coalesced).  The loads of B
-// groups are issued back to back before they are consumed (memory-level parallelism); batches without
-// a match cost four shuffles.
-template <bool F64>
-__device__ __forceinline__ void agg_pass_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, uint32_t word, uint32_t Rp, uint32_t lane,
-                                               uint64_t base, uint64_t flip) {
-    constexpr int B = 8;
-    for (uint32_t it0 = 0; it0 < Rp; it0 += B) {
-        uint32_t wd[B], anyw = 0;
+// The fused reduce for ONE value column over `ng` consecutive 32-row groups whose match words sit in shared
+// memory (`fw`).  Lane l first looks at the word of group l: one ballot tells the warp which groups have matches at
+// all, and only those are visited (a sparse tile costs a handful of instructions).  For a visited group lane l
+// reduces row l, so every load instruction reads 32 consecutive values (coalesced); the loads of up to B groups are
+// issued back to back before they are consumed (memory-level parallelism).
+// SMEM: `vp` points into a ring stage (the producer staged the tile's slice of the column); otherwise the matching
+// rows are read on demand from global memory.  Groups are visited in ascending order and the (lane, row) assignment
+// is the same in both variants: a tile gives bit-identical partial sums whichever way its values arrive.
+template <int BD, int BS, typename Body>
+__device__ __forceinline__ void for_matching_groups(const uint32_t* __restrict__ fw, uint32_t ng, uint32_t lane, Body&& body) {
+    __builtin_assume(__isShared(fw));
+    for (uint32_t blk = 0; blk < ng; blk += 32u) {
+        const uint32_t myw = blk + lane < ng ? fw[blk + lane] : 0u;
+        uint32_t mask = __ballot_sync(0xffffffffu, myw != 0u);
+        const uint32_t nb = min(32u, ng - blk);
+        if (__popc(mask) * 2u >= nb) {
+            // most groups have matches: walk them all, BD at a time (no bit scans; words read as shared-memory broadcasts)
+            for (uint32_t it0 = 0; it0 < nb; it0 += BD) {
+                uint32_t gi[BD], wd[BD];
 #pragma unroll
-        for (int u = 0; u < B; ++u) {
-            wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
-            if (it0 + u >= Rp) wd[u] = 0;
-            anyw |= wd[u];
+                for (int u = 0; u < BD; ++u) {
+                    gi[u] = blk + it0 + u;
+                    wd[u] = it0 + u < nb ? fw[gi[u]] : 0u;
+                }
+                body(gi, wd);
+            }
+            continue;
         }
-        if (anyw == 0) continue;
+        while (mask) {   // few groups have matches: visit only those, BS at a time
+            uint32_t gi[BS], wd[BS];
+#pragma unroll
+            for (int u = 0; u < BS; ++u) {
+                gi[u] = mask ? (uint32_t)__ffs((int)mask) - 1u : 0u;
+                wd[u] = __shfl_sync(0xffffffffu, myw, gi[u]);
+                if (!mask) wd[u] = 0u;
+                mask &= mask - 1u;
+                gi[u] += blk;
+            }
+            body(gi, wd);
+        }
+    }
+}
+
+template <bool F64, bool SMEM>
+__device__ __forceinline__ void agg_groups_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, const uint32_t* __restrict__ fw, uint32_t ng,
+                                                 uint32_t lane, uint64_t base, uint64_t flip) {
+    if (SMEM) __builtin_assume(__isShared(vp));
+    for_matching_groups<8, 2>(fw, ng, lane, [&](const auto& gi, const auto& wd) {
+        constexpr int B = (int)(sizeof(gi) / sizeof(gi[0]));
         uint64_t val[B];
 #pragma unroll
-        for (int u = 0; u < B; ++u) val[u] = ((wd[u] >> lane) & 1u) ? __ldg(vp + (size_t)(it0 + u) * 32u) : 0ull;
+        for (int u = 0; u < B; ++u) val[u] = ((wd[u] >> lane) & 1u) ? (SMEM ? vp[(size_t)gi[u] * 32u] : __ldg(vp + (size_t)gi[u] * 32u)) : 0ull;
 #pragma unroll
         for (int u = 0; u < B; ++u) {
             if ((wd[u] >> lane) & 1u) {
@@ -616,29 +651,23 @@ __device__ __forceinline__ void agg_pass_raw64(AggAcc& A, const unsigned long lo
                 }
             }
         }
-    }
+    });
 }
 
-// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types): decode per row
-__device__ __forceinline__ void agg_pass_generic(AggAcc& A, const ColView& v, int type, uint32_t row_base, uint32_t word, uint32_t Rp, uint32_t lane) {
-    constexpr int B = 4;
-    for (uint32_t it0 = 0; it0 < Rp; it0 += B) {
-        uint32_t wd[B], anyw = 0;
-#pragma unroll
-        for (int u = 0; u < B; ++u) {
-            wd[u] = __shfl_sync(0xffffffffu, word, (it0 + u) & 31u);
-            if (it0 + u >= Rp) wd[u] = 0;
-            anyw |= wd[u];
-        }
-        if (anyw == 0) continue;
+// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types, ALP): decode per row.
+// `row0` = pack row of (first group, this lane); `staged` = the column's bit stream from pack row `srow0` on (or nullptr).
+__device__ __forceinline__ void agg_groups_generic(AggAcc& A, const ColView& v, int type, uint32_t row0, const uint32_t* __restrict__ fw, uint32_t ng,
+                                                   uint32_t lane, const uint32_t* staged, uint32_t srow0) {
+    for_matching_groups<4, 2>(fw, ng, lane, [&](const auto& gi, const auto& wd) {
+        constexpr int B = (int)(sizeof(gi) / sizeof(gi[0]));
         uint64_t val[B];
 #pragma unroll
         for (int u = 0; u < B; ++u)
-            if ((wd[u] >> lane) & 1u) val[u] = decode_value(v, row_base + (it0 + u) * 32u, nullptr, 0);
+            if ((wd[u] >> lane) & 1u) val[u] = decode_value(v, row0 + gi[u] * 32u, staged, row0 + gi[u] * 32u - srow0);
 #pragma unroll
         for (int u = 0; u < B; ++u)
             if ((wd[u] >> lane) & 1u) agg_add(A, type, val[u]);
-    }
+    });
 }
 
 // ALP blocks: rows that are patches carry their true value outside the encoded stream.  One thread per patch
@@ -703,7 +732,8 @@ __device__ __forceinline__ uint32_t pack_of_tile(const PackInfo* __restrict__ pa
 // SIMPLE = one leaf, no aggregates: the hot configuration (fused decode + compare + popcount).
 // ONLY32 (with SIMPLE) = every pack's leaf is a <= 32-bit packed range test (or all / none): a lean
 // instantiation without the other leaf paths (small code footprint, fewer registers), MINB CTAs per SM.
-template <bool SIMPLE, bool ONLY32, int MINB>
+// AGG (general kernels only) = the launch reduces value columns; the filter-only instantiation carries none of that code.
+template <bool SIMPLE, bool ONLY32, int MINB, bool AGG>
 __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanParams P) {
     extern __shared__ __align__(128) uint8_t smem[];
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
@@ -712,9 +742,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     __shared__ AggAcc warp_acc[CONSUMER_WARPS];
     __shared__ unsigned long long warp_cnt[CONSUMER_WARPS];
     __shared__ unsigned int sm_match, sm_wtiles;   // matches / (warp, tile) pairs finished so far: selectivity feedback for the producer
+    __shared__ uint32_t stage_flag[MAX_STAGES];    // per ring slot: does the stage carry a value-column chunk (1) or nothing (0)?
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
     const uint32_t R = P.R, tile_rows = R * 32u * CONSUMER_WARPS, nstages = P.stages;
+    uint32_t* code_smem = reinterpret_cast<uint32_t*>(stage_base + (size_t)nstages * P.stage_bytes);   // LM_CODESET bitmaps of the current pack
+    // staged value columns: a tile's slice of a column = agg_chunks ring stages of chunk_rows rows (whole warps)
+    const uint32_t agg_chunks = AGG ? P.agg_chunks : 0u, chunk_rows = agg_chunks ? tile_rows / agg_chunks : 0u;
 
     if (threadIdx.x == 0) {
         sm_match = 0; sm_wtiles = 0;
@@ -749,24 +783,54 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
             uint32_t s = 0, ph = 0;
-            auto load_stream = [&](const uint8_t* data, uint32_t w, uint32_t rows) {
+            auto load_stream = [&](const uint8_t* data, size_t off, uint32_t w, uint32_t rows, uint32_t flag = 0u) {
                 mbar_wait_relaxed(&empty_bar[s], ph ^ 1u);  // slot released by all consumer warps
                 if (!data) w = 0;
+                data += off;
                 uint32_t bytes = w ? ((((rows * w + 7u) >> 3) + 15u) & ~15u) : 0u;
+                stage_flag[s] = flag;                       // published by the arrive below (release) / the consumers' wait (acquire)
                 mbar_expect_tx(&full_bar[s], bytes);        // arrive (count 1) + expected bytes
-                if (bytes) tma_load_1d(stage_base + (size_t)s * P.stage_bytes, data + (size_t)chunk * (tile_rows / 8u) * w, bytes, &full_bar[s]);
+                if (bytes) tma_load_1d(stage_base + (size_t)s * P.stage_bytes, data, bytes, &full_bar[s]);
                 if (++s == nstages) { s = 0; ph ^= 1u; }
             };
+            uint32_t pf_m0 = 0, pf_d0 = 0;   // selectivity feedback snapshot
+            bool dense = P.agg_dense_thr == 0;
             for (uint32_t t = t_begin; t < t_end; ++t) {
                 const uint32_t rows = min(tile_rows, pi.n - chunk * tile_rows);
                 const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
-                if (SIMPLE) load_stream(L[0].data, L[0].width, rows);   // (an unstaged leaf still cycles its stage: lockstep)
+                const size_t tile_byte0 = (size_t)chunk * (tile_rows / 8u);   // * width = first byte of the tile in a stream
+                if constexpr (SIMPLE) load_stream(L[0].data, tile_byte0 * L[0].width, L[0].width, rows);   // (an unstaged leaf still cycles its stage: lockstep)
                 else {
+                    // Value columns: tiles that match densely get their slice of every stageable value column streamed through
+                    // the ring in agg_chunks chunks (full-bandwidth bulk copies); in sparse tiles the matching rows are read on
+                    // demand from global memory.  The decision travels with the tile's first ring stage (stage_flag).
+                    if (agg_chunks && P.agg_dense_thr != 0 && P.agg_dense_thr != 0xffffffffu) {
+                        uint32_t m = *(volatile unsigned int*)&sm_match, d = *(volatile unsigned int*)&sm_wtiles;
+                        if (d - pf_d0 >= CONSUMER_WARPS) {
+                            dense = (uint64_t)(m - pf_m0) * P.agg_dense_thr * CONSUMER_WARPS > (uint64_t)(d - pf_d0) * tile_rows;
+                            pf_m0 = m; pf_d0 = d;
+                        }
+                    }
+                    const uint32_t flag = (agg_chunks && dense) ? 1u : 0u;
+                    bool told = false;
                     for (uint32_t i = 0; i < P.npost; ++i) {
                         uint32_t op = P.postfix[i];
                         if (op >= 0x80u) continue;
-                        if (L[op].data) load_stream(L[op].data, L[op].width, rows);
-                        if (L[op].fixmode) load_stream(L[op].fix, 1u, rows);      // ALP patch correction stream
+                        if (L[op].data) { load_stream(L[op].data, tile_byte0 * L[op].width, L[op].width, rows, flag); told = true; }
+                        if (L[op].fixmode) { load_stream(L[op].fix, tile_byte0, 1u, rows, flag); told = true; }      // ALP patch correction stream
+                    }
+                    if constexpr (AGG) {
+                        if (!told) load_stream(nullptr, 0, 0u, 0u, flag);   // no leaf column is staged: an empty stage carries the decision
+                        if (dense) {
+                            for (uint32_t j = 0; j < P.naggs; ++j) {
+                                const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                                if (!agg_stageable(v)) continue;
+                                for (uint32_t k = 0; k < agg_chunks; ++k) {
+                                    const uint32_t r0 = k * chunk_rows, nr = rows > r0 ? min(chunk_rows, rows - r0) : 0u;
+                                    load_stream(v.data, (tile_byte0 + r0 / 8u) * v.width, v.width, nr, 1u);
+                                }
+                            }
+                        }
                     }
                 }
                 if (t + 1 < t_end) next_tile();
@@ -776,15 +840,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     }
 
     // ===================== consumers: unpack + filter + reduce =====================
-    AggAcc acc[SIMPLE ? 1 : MAX_AGGS];
+    AggAcc acc[AGG ? MAX_AGGS : 1];
 #pragma unroll
-    for (int j = 0; j < (SIMPLE ? 1 : MAX_AGGS); ++j) acc[j] = agg_identity(SIMPLE ? 0 : P.agg_type[j]);
+    for (int j = 0; j < (AGG ? MAX_AGGS : 1); ++j) acc[j] = agg_identity(AGG ? P.agg_type[j] : 0);
     unsigned long long nmatch = 0;   // matches this thread accounted for (per-CTA totals only)
     uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
-    uint32_t lane_cnt_tile = 0;      // matches of the current tile (general kernels: one pass per tile)
-    uint32_t pf_m0 = 0, pf_d0 = 0;   // thread 0: selectivity feedback snapshot for the value-column prefetch
-    bool pf_dense = false;
-    const uint32_t passes = SIMPLE ? ((R + 31u) >> 5) : 1u, Rp = min(R, 32u);   // general kernels: R <= 32
+    uint32_t bm_pack = 0xffffffffu;  // pack whose code bitmaps are cached in shared memory
+    const uint32_t passes = (R + 31u) >> 5, Rp = min(R, 32u);
+    // general kernels (shared memory behind the code bitmaps): the AND/OR stack of this warp, one word per (slot, pass,
+    // lane), and the tile's final match words (CTA-shared, double-buffered by tile parity) for the fused reduce
+    const uint32_t tile_groups = R * CONSUMER_WARPS;
+    uint32_t* stk = code_smem + P.stack_off_words + warp * (P.stack_depth * passes * 32u);
+    uint32_t* fin_base = code_smem + P.stack_off_words + CONSUMER_WARPS * P.stack_depth * passes * 32u;
+    uint32_t fin_sel = 0;
 
     auto flush_count = [&](uint32_t pk) {
         uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
@@ -796,6 +864,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
         const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
+
+        if (!ONLY32 && P.code_smem_words && pack != bm_pack) {
+            // new pack: the consumers copy its code bitmaps (built by codeset_kernel) into shared memory
+            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));   // everybody is done with the previous pack's bitmaps
+            for (uint32_t l = 0; l < P.nleaves; ++l) {
+                if (L[l].mode != LM_CODESET) continue;
+                const uint32_t nw = (((1u << L[l].width) + (uint32_t)L[l].wm + 31u) >> 5) + 1u;
+                const uint32_t* src = P.code_bits + L[l].a;
+                uint32_t* dst = code_smem + P.code_smem_off[l];
+                for (uint32_t i = threadIdx.x; i < nw; i += CONSUMER_WARPS * 32u) dst[i] = __ldg(src + i);
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+            bm_pack = pack;
+        }
 
         // one leaf for one pass: sw = the leaf's staged stream (or nullptr), g0 = first group of the pass
         auto eval_leaf = [&](uint32_t li, const uint32_t* sw, uint32_t g0, uint64_t wr) -> uint32_t {
@@ -825,7 +907,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             }
             case LM_BITS: __builtin_assume(__isShared(sw)); word = lane < Rp ? sw[g0 + lane] : 0u; break;   // precomputed leaf bitset (run-end pre-pass)
             case LM_CODESET:
-                word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, P.code_bits + lf.a);
+                word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, code_smem + P.code_smem_off[li]);
                 break;
             case LM_HASHSET:
                 word = leaf_hashset(sw, P.views[lf.view], g0, Rp, lane,
@@ -841,8 +923,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             return lf.neg ? ~word : word;
         };
 
-        // tail masking, bitset store, popcount and the fused reduce for one pass
-        auto emit = [&](uint32_t word, uint32_t g0, uint64_t wr) {
+        // tail masking, bitset store and popcount of one pass; returns the masked word
+        auto emit = [&](uint32_t word, uint64_t wr) -> uint32_t {
             // mask rows past the end of the pack (tail bits must be zero) and lanes >= Rp
             uint32_t valid = 0;
             if (lane < Rp && wr < pi.n) {
@@ -854,29 +936,15 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             if (P.bitsets && lane < Rp && wr < pi.n)
                 *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
             lane_cnt += __popc(word);
-            lane_cnt_tile = __popc(word);
-            // fused reduce over the matching rows of the value columns, read on demand from global memory
-            // (32-row groups without a match are never touched)
-            if (!SIMPLE && P.naggs && __any_sync(0xffffffffu, word != 0)) {
-                const uint32_t row_base = pack_row0 + g0 * 32u + lane;
-                for (uint32_t j = 0; j < P.naggs; ++j) {
-                    const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
-                    const int type = P.agg_type[j];
-                    AggAcc a = acc[SIMPLE ? 0 : j];
-                    if (v.kind == CK_BITS && v.width == 64) {
-                        const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + row_base;
-                        if (type == 9) agg_pass_raw64<true>(a, vp, word, Rp, lane, 0ull, 0ull);
-                        else agg_pass_raw64<false>(a, vp, word, Rp, lane, v.base, type_is_signed(type) ? 0x8000000000000000ull : 0ull);
-                    } else {
-                        agg_pass_generic(a, v, type, row_base, word, Rp, lane);
-                    }
-                    acc[SIMPLE ? 0 : j] = a;
-                }
-                nmatch += __popc(word);   // per-CTA totals only: any partition of the matches over threads will do
-            }
+            return word;
+        };
+        auto release = [&]() {   // this warp is done with ring stage s
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+            if (++s == nstages) { s = 0; ph ^= 1u; }
         };
 
-        if (SIMPLE) {
+        if constexpr (SIMPLE) {
             const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
             mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
             for (uint32_t pass = 0; pass < passes; ++pass) {
@@ -888,70 +956,126 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&empty_bar[s]);
                 }
-                emit(word, g0, wr);
+                emit(word, wr);
             }
             if (++s == nstages) { s = 0; ph ^= 1u; }
         } else {
-            // Value columns are read on demand (rows that do not match cost nothing).  When the recent tiles
-            // matched densely (> 1/16 of their rows: almost every DRAM burst of the column is touched anyway)
-            // one thread prefetches the NEXT tile's slice of the value columns into L2 — one tile ahead only, so
-            // that the 296 CTAs' prefetch windows stay far below the L2 capacity.
-            if (P.naggs && threadIdx.x == 0 && chunk + 1 < pack_tiles) {
-                uint32_t m = *(volatile unsigned int*)&sm_match, d = *(volatile unsigned int*)&sm_wtiles;
-                if (d - pf_d0 >= CONSUMER_WARPS) {
-                    pf_dense = (uint64_t)(m - pf_m0) * 16u * CONSUMER_WARPS > (uint64_t)(d - pf_d0) * tile_rows;
-                    pf_m0 = m; pf_d0 = d;
-                }
-                if (pf_dense) {
-                    const size_t r0 = (size_t)(chunk + 1) * tile_rows, r1 = min((size_t)pi.n, r0 + tile_rows);
-                    for (uint32_t j = 0; j < P.naggs; ++j) {
-                        const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
-                        if ((v.kind != CK_BITS && v.kind != CK_DICT && v.kind != CK_ALP) || v.width == 0) continue;
-                        size_t b0 = ((r0 * v.width) >> 3) & ~(size_t)15, b1 = (r1 * v.width + 7) >> 3;
-                        tma_prefetch_l2(v.data + b0, (uint32_t)((b1 - b0 + 15) & ~(size_t)15));
-                    }
-                }
-            }
-            // evaluate the leaves and the AND/OR program on word-per-lane bitsets; every staged leaf
-            // consumes (and releases) one ring stage
-            const uint32_t g0 = warp * R;
-            const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;
-            uint32_t stack[MAX_LEAVES];
-            int sp = 0;
+            // ---- leaves and the AND/OR program.  Every staged leaf column is one ring stage holding the column's slice of
+            // the whole tile; a leaf is evaluated for ALL passes of the warp before the next one is touched (its unrolled
+            // body stays hot in the instruction cache), the per-pass words wait on the warp's stack in shared memory.
+            const uint32_t gw0 = warp * R, pstride = passes * 32u;
+            uint32_t sp = 0;
+            bool told = false, dense = false;   // the producer's staging decision arrives with the tile's first ring stage
             for (uint32_t i = 0; i < P.npost; ++i) {
-                uint32_t op = P.postfix[i];
+                const uint32_t op = P.postfix[i];
                 if (op < 0x80u) {
-                    uint32_t word;
-                    if (L[op].data) {
+                    const PackLeaf& lf = L[op];
+                    uint32_t* dst = stk + sp * pstride + lane;
+                    const uint32_t* sw = nullptr;
+                    const bool staged_leaf = lf.data != nullptr;
+                    if (staged_leaf) {
                         mbar_wait(&full_bar[s], ph);
-                        word = eval_leaf(op, reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes), g0, wr);
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[s]);
-                        if (++s == nstages) { s = 0; ph ^= 1u; }
-                    } else {
-                        word = eval_leaf(op, nullptr, g0, wr);
+                        if (!told) { dense = stage_flag[s] != 0; told = true; }
+                        sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                     }
-                    if (L[op].fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
+                    const bool inv = lf.neg2 && !lf.fixmode;
+                    for (uint32_t pass = 0; pass < passes; ++pass) {
+                        const uint32_t g0 = gw0 + pass * 32u;
+                        uint32_t word = eval_leaf(op, sw, g0, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u);
+                        dst[pass * 32u] = inv ? ~word : word;
+                    }
+                    if (staged_leaf) release();
+                    if (lf.fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
                         mbar_wait(&full_bar[s], ph);
+                        if (!told) { dense = stage_flag[s] != 0; told = true; }
                         const uint32_t* fw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                         __builtin_assume(__isShared(fw));
-                        uint32_t fx = lane < Rp ? fw[g0 + lane] : 0u;
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&empty_bar[s]);
-                        if (++s == nstages) { s = 0; ph ^= 1u; }
-                        word = L[op].fixmode == FIX_OR_PRED ? (word | fx) : (word & ~fx);
+                        for (uint32_t pass = 0; pass < passes; ++pass) {
+                            const uint32_t fx = lane < Rp ? fw[gw0 + pass * 32u + lane] : 0u;
+                            uint32_t word = dst[pass * 32u];
+                            word = lf.fixmode == FIX_OR_PRED ? (word | fx) : (word & ~fx);
+                            dst[pass * 32u] = lf.neg2 ? ~word : word;
+                        }
+                        release();
                     }
-                    if (L[op].neg2) word = ~word;
-                    stack[sp++] = word;
+                    ++sp;
                 } else {
-                    uint32_t y = stack[--sp];
-                    stack[sp - 1] = (op == 0xFEu) ? (stack[sp - 1] & y) : (stack[sp - 1] | y);
+                    --sp;
+                    uint32_t* x = stk + (sp - 1u) * pstride + lane;
+                    const uint32_t* y = stk + sp * pstride + lane;
+                    for (uint32_t pass = 0; pass < passes; ++pass)
+                        x[pass * 32u] = (op == 0xFEu) ? (x[pass * 32u] & y[pass * 32u]) : (x[pass * 32u] | y[pass * 32u]);
                 }
             }
-            emit(stack[0], g0, wr);
-            if (P.naggs) {   // selectivity feedback for the producer's value-column prefetch
-                uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt_tile);
-                if (lane == 0) { atomicAdd(&sm_match, c); atomicAdd(&sm_wtiles, 1u); }
+            // ---- outputs of the tile
+            uint32_t* fin = fin_base + fin_sel * tile_groups;
+            uint32_t tile_cnt = 0;
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                const uint32_t g0 = gw0 + pass * 32u;
+                const uint32_t word = emit(stk[pass * 32u + lane], (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u);
+                tile_cnt += __popc(word);
+                if (AGG && lane < Rp) fin[g0 + lane] = word;
+                if (AGG && word && __popc(word) <= 2) {
+                    // sparse matches: start pulling their value rows towards L2 now; the reduce below (after the CTA barrier)
+                    // then pays an L2 hit instead of a DRAM round trip per visited group
+                    for (uint32_t j = 0; j < P.naggs; ++j) {
+                        const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                        if (v.kind != CK_BITS || v.width != 64) continue;
+                        const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + pack_row0 + (g0 + lane) * 32u;
+                        uint32_t b0 = (uint32_t)__ffs((int)word) - 1u, b1 = 31u - (uint32_t)__clz((int)word);
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + b0));
+                        if (b1 != b0) asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + b1));
+                    }
+                }
+            }
+            // ---- fused reduce over the matching rows of the value columns.  The tile's match words are shared by the
+            // CTA: chunk k (groups [k G, (k + 1) G), G = tile groups / chunks) is reduced by ALL warps, warp w taking
+            // G / 8 consecutive groups of it — the same assignment whether the chunk was staged through the ring by the
+            // producer (dense tiles: full-bandwidth bulk copies) or its matching rows are read on demand from global
+            // memory (sparse tiles: groups without a match are never touched; the column cycles ONE empty stage).
+            if constexpr (AGG) {
+                nmatch += tile_cnt;   // per-CTA totals only: any partition of the matches over threads will do
+                const uint32_t c = __reduce_add_sync(0xffffffffu, tile_cnt);
+                if (lane == 0) { atomicAdd(&sm_match, c); atomicAdd(&sm_wtiles, 1u); }   // selectivity feedback for the producer
+                asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));              // the tile's words are complete
+                fin_sel ^= 1u;
+                const uint32_t K = P.agg_chunks, G = tile_groups / K, gpw = G / CONSUMER_WARPS;
+                if (!told) {   // no leaf column was staged: the decision sits in an empty stage
+                    mbar_wait(&full_bar[s], ph);
+                    dense = stage_flag[s] != 0;
+                    release();
+                }
+                for (uint32_t j = 0; j < P.naggs; ++j) {
+                    const ColView& v = P.views[P.agg_view0 + (size_t)pack * P.naggs + j];
+                    const int type = P.agg_type[j];
+                    const bool raw64 = v.kind == CK_BITS && v.width == 64;
+                    const uint64_t flip = type_is_signed(type) ? 0x8000000000000000ull : 0ull;
+                    AggAcc a = acc[j];
+                    const bool staged = dense && agg_stageable(v);
+                    for (uint32_t k = 0; k < K; ++k) {
+                        if (staged) mbar_wait(&full_bar[s], ph);
+                        const uint32_t gk = k * G + warp * gpw;                 // this warp's first group of chunk k
+                        const uint32_t row0 = pack_row0 + gk * 32u + lane;      // pack row of (group gk, this lane)
+                        const uint32_t* fw = fin + gk;
+                        const uint8_t* stg = stage_base + (size_t)s * P.stage_bytes;
+                        if (raw64) {
+                            if (staged) {
+                                const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(stg) + (warp * gpw * 32u + lane);
+                                if (type == 9) agg_groups_raw64<true, true>(a, vp, fw, gpw, lane, 0ull, 0ull);
+                                else agg_groups_raw64<false, true>(a, vp, fw, gpw, lane, v.base, flip);
+                            } else {
+                                const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + row0;
+                                if (type == 9) agg_groups_raw64<true, false>(a, vp, fw, gpw, lane, 0ull, 0ull);
+                                else agg_groups_raw64<false, false>(a, vp, fw, gpw, lane, v.base, flip);
+                            }
+                        } else {
+                            agg_groups_generic(a, v, type, row0, fw, gpw, lane, staged ? reinterpret_cast<const uint32_t*>(stg) : nullptr,
+                                               pack_row0 + k * G * 32u);
+                        }
+                        if (staged) release();
+                    }
+                    acc[j] = a;
+                }
             }
         }
 
@@ -963,12 +1087,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
     }
     flush_count(pack);
 
-    if (SIMPLE) return;
+    if constexpr (AGG) {
 
     // ---- per-CTA partial aggregates: fixed-order tree inside the warp, then across warps
     for (uint32_t j = 0; j < P.naggs; ++j) {
         const int type = P.agg_type[j];
-        AggAcc a = acc[SIMPLE ? 0 : j];
+        AggAcc a = acc[j];
         unsigned long long c = nmatch;
         for (int off = 16; off > 0; off >>= 1) {
             AggAcc b;
@@ -993,6 +1117,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         }
         asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
     }
+    }   // AGG
 }
 
 // Combines the per-CTA partials in CTA order (fixed topology → bit-reproducible results).
@@ -1293,13 +1418,14 @@ __global__ void prune_kernel(PruneParams P) {
 static int grid_for(uint64_t items, uint64_t cap) { uint64_t g = (items + 255) / 256; return (int)(g < cap ? g : cap); }
 
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool simple, bool only32, int ctas_per_sm, cudaStream_t stream) {
-    int variant = !simple ? 0 : (!only32 ? 1 : (ctas_per_sm >= 3 ? 3 : 2));
-    void (*kern)(const ScanParams) = scan_kernel<false, false, 2>;
-    if (variant == 1) kern = scan_kernel<true, false, 2>;
-    if (variant == 2) kern = scan_kernel<true, true, 2>;
-    if (variant == 3) kern = scan_kernel<true, true, 3>;
+    int variant = !simple ? (P.naggs ? 0 : 4) : (!only32 ? 1 : (ctas_per_sm >= 3 ? 3 : 2));
+    void (*kern)(const ScanParams) = scan_kernel<false, false, 2, true>;
+    if (variant == 1) kern = scan_kernel<true, false, 2, false>;
+    if (variant == 2) kern = scan_kernel<true, true, 2, false>;
+    if (variant == 3) kern = scan_kernel<true, true, 3, false>;
+    if (variant == 4) kern = scan_kernel<false, false, 2, false>;
     // function attributes are per device and sticky: set them once per (device, variant)
-    static bool configured[64][4] = {};
+    static bool configured[64][5] = {};
     int dev = 0;
     cudaError_t e = cudaGetDevice(&dev);
     if (e != cudaSuccess) return e;
@@ -1330,9 +1456,11 @@ cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_
     return cudaGetLastError();
 }
 
-cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream) {
-    if (njobs == 0) return cudaSuccess;
-    codeset_kernel<<<njobs, 256, 0, stream>>>(jobs, set_vals, out);
+cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, uint32_t max_set, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream) {
+    if (njobs == 0 || max_set == 0) return cudaSuccess;
+    uint32_t gx = (max_set + 127u) / 128u;
+    if (gx > 32u) gx = 32u;
+    codeset_kernel<<<dim3(gx, njobs), 128, 0, stream>>>(jobs, set_vals, out);
     return cudaGetLastError();
 }
 

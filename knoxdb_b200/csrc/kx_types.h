@@ -138,7 +138,24 @@ struct ScanParams {
     uint32_t leaf_view0;       // views[leaf_view0 + pack * nleaves + l]
     uint8_t  postfix[MAX_POSTFIX];
     uint8_t  agg_type[MAX_AGGS];
+    // LM_CODESET leaves: the current pack's code bitmap of leaf l is cached in shared memory (after the ring) at word
+    // code_smem_off[l]; code_smem_words = size of that area (0: the program has no such leaf)
+    uint32_t code_smem_off[MAX_LEAVES];
+    uint32_t code_smem_words;
+    // general kernels: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp) and the CTA's
+    // double-buffered final match words, both behind the code bitmaps (word offset from their start)
+    uint32_t stack_off_words;
+    uint32_t stack_depth;
+    // value columns of the fused reduce: a tile's slice of one value column is split into agg_chunks (1, 2, 4 or 8)
+    // chunks, each reduced by all consumer warps; tiles that match densely get the chunks staged through the ring
+    uint32_t agg_chunks;       // >= 1 whenever naggs > 0
+    uint32_t agg_dense_thr;    // stage the tile when recent matches * thr > recent rows; 0 = always, 0xffffffff = never
 };
+
+// can the value column be streamed through the ring (bit stream of fixed width per row)?
+KX_HD inline bool agg_stageable(const ColView& v) {
+    return (v.kind == CK_BITS || v.kind == CK_DICT || v.kind == CK_ALP) && v.width != 0;
+}
 
 KX_HD inline bool type_is_signed(int t) { return t >= 1 && t <= 4; }
 KX_HD inline bool type_is_float(int t) { return t == 9 || t == 10; }

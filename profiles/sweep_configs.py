@@ -253,7 +253,7 @@ def build_cases(rng, only):
                     cases.append(Case(f"c3 ts range(50%) AND acct({acct_kind}) in{{{nset}}} sum/min/max {amt_kind}", M1, 256, f,
                                       [rng_leaf(0.5), kb.Leaf(2, kb.UINT64, kb.IN, values=uniq[:: uniq.size // nset][:nset])], aggs=[(3, kbt)],
                                       bytes_per_row=e_ts + e_a + 8.0, note="bytes/row counts the full value column (8 B) as SURVEY 8(d) does"))
-        for frac in (0.001, 0.1, 0.9):
+        for frac in (0.001, 0.1, 0.25, 0.5, 0.9):
             for amt_kind, b_m, kbt, kot in (("i64", b_ai, kb.INT64, ko.I64), ("f64", b_af, kb.FLOAT64, ko.F64)):
                 f = {1: (kb.INT64, b_ts, ko.I64), 3: (kbt, b_m, kot)}
                 cases.append(Case(f"c3 ts range({frac * 100:g}%) sum/min/max {amt_kind}", M1, 256, f, [rng_leaf(frac)], aggs=[(3, kbt)], bytes_per_row=e_ts + 8.0))

@@ -211,8 +211,20 @@ def oracle_query(packs, blobs, t_lo, t_hi, set_u64, postfix):
     return counts, bitsets, agg_i, agg_f
 
 
+@pytest.fixture
+def agg_stage(request, monkeypatch):
+    """KX_AGG_STAGE: how the fused reduce reads value columns (on demand / staged through the ring / by selectivity)"""
+    mode = getattr(request, "param", "auto")
+    if mode == "auto":
+        monkeypatch.delenv("KX_AGG_STAGE", raising=False)
+    else:
+        monkeypatch.setenv("KX_AGG_STAGE", mode)
+    return mode
+
+
+@pytest.mark.parametrize("agg_stage", ["auto", "always", "never"], indirect=True)
 @pytest.mark.parametrize("acct_kind", ["dict", "bitpack", "raw"])
-def test_multi_predicate_scan_with_aggregates(ctx, acct_kind):
+def test_multi_predicate_scan_with_aggregates(ctx, acct_kind, agg_stage):
     """BASELINE config 3: ts BETWEEN AND acct IN {…} → count/sum/min/max over int64 and float64"""
     import knoxdb_b200 as kb
     nrows = [4096, 70000, 8192, 1, 33333, 16384]
@@ -256,6 +268,57 @@ def test_multi_predicate_scan_with_aggregates(ctx, acct_kind):
         for f in (F_TS, F_ACCT, F_AMT, F_FAMT):
             ctx.block_drop(p, 1, f)
     assert ctx.store_stats()["blocks"] == 0
+
+
+def test_staged_and_on_demand_reduce_agree_bit_for_bit(ctx, monkeypatch):
+    """The producer decides per tile, from the selectivity it has seen so far, whether a value column is staged
+    through the ring or read on demand — a timing-dependent choice.  Both paths must therefore give the SAME bits,
+    float sums included (same lane/row assignment and order of additions), on a scan long enough (many tiles per
+    CTA) for the choice to flip inside one launch."""
+    import knoxdb_b200 as kb
+    n, npacks = 300_000, 96
+    base, accts = make_table(RNG, 2, [n, n])
+    base[1]["ts"] = base[0]["ts"]   # same time range in both blocks: the selectivity is uniform over the scan
+    encs = []
+    for cols in base:
+        encs.append({F_TS: ko.store("best", ko.I64, cols["ts"]), F_AMT: ko.store("best", ko.I64, cols["amount"]),
+                     F_FAMT: ko.store("raw", ko.F64, cols["famount"]), F_ACCT: ko.store("dict", ko.U64, cols["acct"])})
+    for p in range(npacks):
+        for f, t in ((F_TS, ko.I64), (F_AMT, ko.I64), (F_FAMT, ko.F64), (F_ACCT, ko.U64)):
+            ctx.block_put(p, 1, f, t, encs[p % 2][f])
+    ts = base[0]["ts"]
+    for sel in (0.02, 0.5, 0.95):
+        t_lo, t_hi = int(ts[int(n * 0.01)]), int(ts[int(n * (0.01 + sel))])
+        prog = kb.Program(ctx, [kb.Leaf(F_TS, kb.INT64, kb.RANGE, t_lo, t_hi)])
+        got = {}
+        for mode in ("never", "always", "3", "auto"):
+            if mode == "auto":
+                monkeypatch.delenv("KX_AGG_STAGE", raising=False)
+            else:
+                monkeypatch.setenv("KX_AGG_STAGE", mode)
+            r = ctx.scan(prog, [(p, 1) for p in range(npacks)], nrows=[n] * npacks,
+                         aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64), (F_ACCT, kb.UINT64)])
+            got[mode] = (r["counts"].tolist(), [(g.count, int(bool(g.valid)), g.sum_bits, g.min_bits, g.max_bits) for g in r["aggs"]])
+        prog.close()
+        assert got["never"] == got["always"] == got["3"] == got["auto"], sel
+        # and the oracle: integer aggregates bit for bit, float sum within the north-star tolerance of the sequential sum
+        agg_i, agg_f, agg_a = ko.Agg(), ko.Agg(), ko.Agg()
+        for p in range(npacks):
+            cols = base[p % 2]
+            bits = ko.Container(ko.I64, encs[p % 2][F_TS]).match(ko.RG, ko.scalar_u64(ko.I64, t_lo), ko.scalar_u64(ko.I64, t_hi))
+            agg_i = ko.reduce(ko.I64, cols["amount"], bits, agg_i)
+            agg_f = ko.reduce(ko.F64, cols["famount"], bits, agg_f)
+            agg_a = ko.reduce(ko.U64, cols["acct"], bits, agg_a)
+        gi, gf, ga = got["auto"][1]
+        assert gi == (agg_i.count, 1, agg_i.sum_bits, agg_i.min_bits, agg_i.max_bits)
+        assert ga == (agg_a.count, 1, agg_a.sum_bits, agg_a.min_bits, agg_a.max_bits)
+        want = np.uint64(agg_f.sum_bits).view(np.float64)
+        assert abs(np.uint64(gf[2]).view(np.float64) - want) <= 1e-12 * abs(want)
+        assert gf[3:] == (agg_f.min_bits, agg_f.max_bits)
+    monkeypatch.delenv("KX_AGG_STAGE", raising=False)
+    for p in range(npacks):
+        for f in (F_TS, F_AMT, F_FAMT, F_ACCT):
+            ctx.block_drop(p, 1, f)
 
 
 def test_full_size_pack_properties(ctx):
@@ -464,6 +527,12 @@ def test_alp_float_blocks(ctx):
         assert ctx.block_put(77, 1, f, bt, b) == n
     prog = kb.Program(ctx, [kb.Leaf(1, kb.FLOAT64, kb.LT, 250.0), kb.Leaf(2, kb.FLOAT64, kb.GE, 12.3)])
     res = ctx.scan(prog, [(77, 1)], nrows=[n], want_bitsets=True, aggs=[(1, kb.FLOAT64), (3, kb.INT64)])
+    os.environ["KX_AGG_STAGE"] = "always"   # the ALP value column staged through the ring: same bits
+    try:
+        res2 = ctx.scan(prog, [(77, 1)], nrows=[n], want_bitsets=True, aggs=[(1, kb.FLOAT64), (3, kb.INT64)])
+    finally:
+        del os.environ["KX_AGG_STAGE"]
+    assert [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res2["aggs"]] == [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res["aggs"]]
     l0 = ko.Container(t, blobs[1][1]).match(ko.LT, ko.scalar_u64(t, 250.0))
     l1 = ko.Container(t, blobs[2][1]).match(ko.GE, ko.scalar_u64(t, 12.3))
     want = ko.tree_eval([0, 1, 0xFE], [l0, l1], n)
