@@ -19,17 +19,48 @@ def stale():
     return any(os.path.getmtime(os.path.join(CSRC, f)) > t for f in SOURCES + HEADERS)
 
 
+INFO = os.path.join(HERE, "build_info.json")
+
+
+def resource_usage(ptxas_log):
+    """per kernel: registers, stack frame and spill bytes from `ptxas -v` (a spill in the persistent scan kernel costs
+    every code path of it dearly: the build fails loudly instead of shipping one)"""
+    import re
+    out, cur = {}, None
+    for line in ptxas_log.splitlines():
+        m = re.search(r"Compiling entry function '(\w+)'", line)
+        if m:
+            cur = m.group(1); out[cur] = {}
+            continue
+        if cur is None:
+            continue
+        m = re.search(r"(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads", line)
+        if m:
+            out[cur].update(stack=int(m.group(1)), spill_stores=int(m.group(2)), spill_loads=int(m.group(3)))
+        m = re.search(r"Used (\d+) registers", line)
+        if m:
+            out[cur]["registers"] = int(m.group(1))
+    return out
+
+
 def build(force=False, verbose=False):
     if not force and not stale():
         return OUT
+    import json
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
         raise RuntimeError("nvcc failed building libknoxgpu.so")
     if verbose:
         sys.stderr.write(res.stderr)
+    usage = resource_usage(res.stderr)
+    json.dump(usage, open(INFO, "w"), indent=1, sort_keys=True)
+    spilled = sorted(k for k, v in usage.items() if "scan_kernel" in k and (v.get("spill_stores") or v.get("spill_loads")))
+    if spilled:
+        os.remove(OUT)
+        raise RuntimeError("register spills in " + ", ".join(spilled) + " (see knoxdb_b200/build_info.json)")
     return OUT
 
 

@@ -100,6 +100,10 @@ struct kx_prog {
     uint32_t tab_off[MAX_LEAVES] = {0};
     uint8_t tab_log2[MAX_LEAVES] = {0};
     const uint64_t* dev_tabs = nullptr;
+    std::vector<uint32_t> pres;          // concatenated prefilter bitmaps of the same leaves
+    uint32_t pre_off[MAX_LEAVES] = {0};
+    uint8_t pre_log2[MAX_LEAVES] = {0};
+    const uint32_t* dev_pres = nullptr;
     bool prune_only = false;             // has a byte-string leaf: usable with kx_prune* only
 };
 
@@ -294,6 +298,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     uint32_t max_stage_bits = 0, code_words = 0, max_code_set = 0;
     uint32_t code_leaf_words[MAX_LEAVES] = {};   // per leaf: largest code bitmap of any pack (cached in shared memory by the scan)
     uint32_t max_agg_bits = 0;                   // widest value column that can be staged through the ring
+    bool hash_leaf[MAX_LEAVES] = {};             // leaf is looked up in its hash set (LM_HASHSET) for some pack
     bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
     uint64_t total_rows = 0;
     bool uniform = true;
@@ -315,6 +320,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 code_words += nw;
                 code_leaf_words[l] = std::max(code_leaf_words[l], nw);
             }
+            if (o.mode == LM_HASHSET) hash_leaf[l] = true;
             if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
                 // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
                 rjobs.push_back(RunFillJob{v.data, v.aux, o.a, o.d, o.wm, leafbits_bytes, v.naux, v.n, o.mode == LM_SET ? 1u : 0u, 0});
@@ -360,6 +366,18 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // dictionary-code bitmaps cached in shared memory behind the ring
     uint32_t code_smem_off[MAX_LEAVES] = {}, code_smem_words = 0;
     for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
+    // hash-set leaves: prefilter bitmap (<= 16 KB) and, when it is small (<= 16 KB), the exact table in shared memory too
+    uint32_t hs_smem_off[MAX_LEAVES] = {}, hs_tab_smem_off[MAX_LEAVES] = {};
+    const uint32_t code_bitmap_words = code_smem_words;
+    code_smem_words = uint32_t(round_up(code_smem_words, 8));   // tables are read with 128-bit loads
+    for (int l = 0; l < nleaves; ++l) {
+        hs_tab_smem_off[l] = 0xffffffffu;
+        if (!hash_leaf[l]) continue;
+        hs_smem_off[l] = code_smem_words;
+        code_smem_words += (1u << prog->pre_log2[l]) / 32u;
+        const uint32_t tab_words = (4u << prog->tab_log2[l]) * 2u;
+        if (tab_words * 4u <= 16u * 1024u) { hs_tab_smem_off[l] = code_smem_words; code_smem_words += tab_words; }
+    }
     const size_t code_smem_bytes = round_up(size_t(code_smem_words) * 4, 128);
     // Value columns of the fused reduce can be staged through the ring, agg_chunks (<= 4) stages per tile and column
     // (KX_AGG_STAGE = never | always | <thr>: stage a tile when recent matches * thr > recent rows).  Measured on B200:
@@ -502,9 +520,15 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.code_bits = static_cast<const uint32_t*>(ctx->d_codebits.p);
     std::memcpy(P.tab_off, prog->tab_off, sizeof(P.tab_off));
     std::memcpy(P.tab_log2, prog->tab_log2, sizeof(P.tab_log2));
+    P.set_pre = prog->dev_pres;
+    std::memcpy(P.pre_off, prog->pre_off, sizeof(P.pre_off));
+    for (int l = 0; l < MAX_LEAVES; ++l) P.pre_log2[l] = hash_leaf[l] ? prog->pre_log2[l] : 0;
+    std::memcpy(P.hs_smem_off, hs_smem_off, sizeof(P.hs_smem_off));
+    std::memcpy(P.hs_tab_smem_off, hs_tab_smem_off, sizeof(P.hs_tab_smem_off));
     P.stages = uint32_t(geo.stages);
     std::memcpy(P.code_smem_off, code_smem_off, sizeof(P.code_smem_off));
     P.code_smem_words = code_smem_words;
+    P.code_bitmap_words = code_bitmap_words;
     P.agg_chunks = agg_chunks;
     P.stack_off_words = uint32_t(code_smem_bytes / 4);
     P.stack_depth = stack_depth;
@@ -684,6 +708,10 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
                 s.has_table = true;
                 p->tab_off[l] = uint32_t(p->tabs.size()); p->tab_log2[l] = uint8_t(lg);
                 p->tabs.insert(p->tabs.end(), slots.begin(), slots.end());
+                std::vector<uint32_t> pre; int plg = 0;
+                build_set_prefilter(s.set, pre, plg);
+                p->pre_off[l] = uint32_t(p->pres.size()); p->pre_log2[l] = uint8_t(plg);
+                p->pres.insert(p->pres.end(), pre.begin(), pre.end());
             }
         }
         p->leaves.push_back(std::move(s));
@@ -691,13 +719,15 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
     for (int l = nleaves; l <= MAX_LEAVES; ++l) p->set_off[l] = uint32_t(p->sets.size());
     if (!p->sets.empty()) {
         // one allocation: sorted sets, then (32 B aligned) the hash tables
-        size_t set_bytes = round_up(p->sets.size() * 8, 32), tab_bytes = p->tabs.size() * 8;
-        CK(cudaMalloc(&p->dev_sets, set_bytes + tab_bytes + 32));
+        size_t set_bytes = round_up(p->sets.size() * 8, 32), tab_bytes = p->tabs.size() * 8, pre_bytes = p->pres.size() * 4;
+        CK(cudaMalloc(&p->dev_sets, set_bytes + tab_bytes + pre_bytes + 32));
         CK(cudaMemcpyAsync(p->dev_sets, p->sets.data(), p->sets.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
         if (tab_bytes) {
             uint8_t* dt = reinterpret_cast<uint8_t*>(p->dev_sets) + set_bytes;
             CK(cudaMemcpyAsync(dt, p->tabs.data(), tab_bytes, cudaMemcpyHostToDevice, ctx->stream));
             p->dev_tabs = reinterpret_cast<const uint64_t*>(dt);
+            CK(cudaMemcpyAsync(dt + tab_bytes, p->pres.data(), pre_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            p->dev_pres = reinterpret_cast<const uint32_t*>(dt + tab_bytes);
         }
         CK(cudaStreamSynchronize(ctx->stream));
     }

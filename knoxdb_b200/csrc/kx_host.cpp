@@ -791,6 +791,17 @@ bool build_set_table(const std::vector<uint64_t>& set, std::vector<uint64_t>& sl
     return false;
 }
 
+void build_set_prefilter(const std::vector<uint64_t>& set, std::vector<uint32_t>& words, int& log2bits) {
+    int lg = 10;
+    while (lg < 17 && (size_t(1) << lg) < set.size() * 256) ++lg;
+    log2bits = lg;
+    words.assign((size_t(1) << lg) / 32, 0u);
+    for (uint64_t v : set) {
+        uint32_t idx = set_hash32(v) >> (32 - lg);
+        words[idx >> 5] |= 1u << (idx & 31u);
+    }
+}
+
 bool scalar_match(int t, int mode, uint64_t v, uint64_t a, uint64_t b) {
     if (type_is_float(t)) {
         double x, y, z;

@@ -62,12 +62,15 @@ struct LeafSpec {
 };
 
 // Bucketised hash table of an IN/NIN set for the device lookup (leaf_hashset in kx_scan.cu):
-// 2^log2nb buckets of 4 keys; key v lives in bucket (v * 0x9E3779B97F4A7C15) >> (64 - log2nb).
+// 2^log2nb buckets of 4 keys; key v lives in bucket set_hash32(v) >> (32 - log2nb).
 // Unused slots repeat a key of the same bucket, empty buckets hold a key of ANOTHER bucket, so
 // comparing a probe with the four slots of its home bucket is exact.  Returns false (no table)
 // when the set does not fit 4-key buckets at a sane size; the scan then uses the sorted array.
 bool build_set_table(const std::vector<uint64_t>& set, std::vector<uint64_t>& slots, int& log2nb);
-inline uint32_t set_table_bucket(uint64_t v, int log2nb) { return uint32_t((v * 0x9E3779B97F4A7C15ull) >> (64 - log2nb)); }
+inline uint32_t set_table_bucket(uint64_t v, int log2nb) { return set_hash32(v) >> (32 - log2nb); }
+// One-hash prefilter bitmap of the set (2^log2bits bits, ~256 bits per key, 1 Ki … 128 Ki bits): the scan tests it for
+// every row out of shared memory and consults the exact table only for the rows that pass.
+void build_set_prefilter(const std::vector<uint64_t>& set, std::vector<uint32_t>& words, int& log2bits);
 
 // Translate one leaf for one block.  dict_host: host copy of the block's dictionary values
 // (CK_DICT only).  view_index: index of the block's ColView in the launch's view table.

@@ -442,31 +442,67 @@ __device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw
     return leaf_code32_dispatch(sw + (size_t)(g0 + lane) * w, w, code_base, bm);   // dictionary codes are uint16: w <= 16
 }
 
-// ---- IN / NOT IN on a bit-packed / raw integer block (int_bitpack.go:249-291, int_raw.go:339-380): the
-// decoded value T(field + For) is looked up in the leaf's bucketised hash table (4 keys per 32 B bucket,
-// built by the host at kx_prog_compile; empty slots hold keys of other buckets, so a plain compare of the
-// four slots is exact).
-__device__ __forceinline__ uint32_t hash_bucket(uint64_t v, uint32_t log2nb) {
-    return (uint32_t)((v * 0x9E3779B97F4A7C15ull) >> (64u - log2nb));
+// ---- IN / NOT IN on a bit-packed / raw integer block (int_bitpack.go:249-291, int_raw.go:339-380).
+// Phase 1 walks the pass lane-strided (lane l takes row 32 it + l: consecutive fields, conflict-free shared-memory
+// reads), hashes the decoded value T(field + For) with two multiply-adds and tests ONE bit of the leaf's prefilter
+// bitmap in shared memory; the ballots of the rows that pass become candidate words (word per lane).  Phase 2: every
+// lane verifies the candidates of its own group against the exact set — a bucketised hash table (4 keys per 32 B
+// bucket, built by the host at kx_prog_compile; empty slots hold keys of other buckets, so a plain compare of the
+// four slots is exact), in shared memory when it is small, else in global memory.
+// field of WIDE ? 33..64 : 1..32 bits at bit offset `bit` of a shared-memory stream, as the 64-bit pattern of T
+// (EXT: T is narrower than 64 bits — truncate and sign-/zero-extend, `sh` = 64 - bits(T))
+template <bool WIDE, bool EXT>
+__device__ __forceinline__ uint64_t hs_value(const uint32_t* __restrict__ sw, uint32_t bit, uint32_t w, uint64_t base, uint32_t sh, bool sgn) {
+    const uint32_t idx = bit >> 5, s = bit & 31u;
+    const uint32_t w0 = sw[idx], w1 = sw[idx + 1];
+    uint64_t f;
+    if (WIDE) {
+        const uint32_t w2 = sw[idx + 2];
+        f = (((uint64_t)__funnelshift_r(w1, w2, s) << 32) | __funnelshift_r(w0, w1, s)) & (w >= 64u ? ~0ull : ((1ull << w) - 1ull));
+    } else {
+        f = __funnelshift_r(w0, w1, s) & (w >= 32u ? 0xffffffffu : ((1u << w) - 1u));
+    }
+    uint64_t val = f + base;
+    if (EXT) val = sgn ? (uint64_t)((int64_t)(val << sh) >> sh) : ((val << sh) >> sh);
+    return val;
 }
-__device__ __forceinline__ uint32_t leaf_hashset(const uint32_t* __restrict__ sw, const ColView& v, uint32_t g0, uint32_t Rp, uint32_t lane,
-                                                 const ulonglong2* __restrict__ tab, uint32_t log2nb) {
+
+template <bool WIDE, bool EXT>
+__device__ __forceinline__ uint32_t leaf_hashset_t(const uint32_t* __restrict__ sw, uint32_t w, uint64_t base, uint32_t sh, bool sgn, uint32_t g0,
+                                                   uint32_t Rp, uint32_t lane, const uint32_t* __restrict__ pre, uint32_t pre_log2,
+                                                   const ulonglong2* __restrict__ tab, uint32_t tab_log2) {
     __builtin_assume(__isShared(sw));
-    if (lane >= Rp) return 0;
-    const uint32_t w = v.width;
-    const int type = v.type;
-    const uint64_t base = v.base;
-    uint32_t bit = (g0 + lane) * 32u * w;
+    __builtin_assume(__isShared(pre));
+    const uint32_t pre_shift = 32u - pre_log2;
+    uint32_t cand = 0;
+    uint32_t bit = (g0 * 32u + lane) * w;
+#pragma unroll 4
+    for (uint32_t it = 0; it < Rp; ++it, bit += 32u * w) {
+        const uint32_t idx = set_hash32(hs_value<WIDE, EXT>(sw, bit, w, base, sh, sgn)) >> pre_shift;
+        const uint32_t b = __ballot_sync(0xffffffffu, (pre[idx >> 5] >> (idx & 31u)) & 1u);
+        if (lane == it) cand = b;
+    }
     uint32_t word = 0;
-#pragma unroll 8
-    for (uint32_t j = 0; j < 32; ++j, bit += w) {
-        uint64_t val = type_ext(type, load_field(sw, bit, w) + base);
-        const ulonglong2* b = tab + 2u * (size_t)hash_bucket(val, log2nb);
-        ulonglong2 p = __ldg(b), q = __ldg(b + 1);
-        uint32_t hit = (p.x == val) | (p.y == val) | (q.x == val) | (q.y == val);
-        word |= hit << j;
+    const uint32_t gbit = (g0 + lane) * 32u * w, tab_shift = 32u - tab_log2;
+    while (cand) {
+        const uint32_t j = (uint32_t)__ffs((int)cand) - 1u;
+        cand &= cand - 1u;
+        const uint64_t val = hs_value<WIDE, EXT>(sw, gbit + j * w, w, base, sh, sgn);
+        const ulonglong2* b = tab + 2u * (size_t)(set_hash32(val) >> tab_shift);
+        const ulonglong2 p = b[0], q = b[1];
+        word |= (uint32_t)((p.x == val) | (p.y == val) | (q.x == val) | (q.y == val)) << j;
     }
     return word;
+}
+
+__device__ __forceinline__ uint32_t leaf_hashset(const uint32_t* __restrict__ sw, uint32_t w, int type, uint64_t base, uint32_t g0, uint32_t Rp, uint32_t lane,
+                                              const uint32_t* __restrict__ pre, uint32_t pre_log2, const ulonglong2* __restrict__ tab, uint32_t tab_log2) {
+    const uint32_t sh = 64u - (uint32_t)type_bits(type);
+    const bool sgn = type_is_signed(type);
+    if (w > 32u) return sh ? leaf_hashset_t<true, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2)
+                           : leaf_hashset_t<true, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2);
+    return sh ? leaf_hashset_t<false, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2)
+              : leaf_hashset_t<false, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2);
 }
 
 // ---- run-end blocks (RunEndContainer.Match* + applyMatch, int_runend.go:224-318): the predicate is
@@ -860,12 +896,30 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         lane_cnt = 0;
     };
 
+    if constexpr (!ONLY32) {
+        // hash-set leaves: prefilter bitmaps (and small exact tables) are the same for every pack — copy them into shared
+        // memory once per CTA
+        bool any = false;
+        for (uint32_t l = 0; l < P.nleaves; ++l) {
+            if (!P.pre_log2[l]) continue;
+            any = true;
+            const uint32_t npre = (1u << P.pre_log2[l]) >> 5;
+            for (uint32_t i = threadIdx.x; i < npre; i += CONSUMER_WARPS * 32u) code_smem[P.hs_smem_off[l] + i] = __ldg(P.set_pre + P.pre_off[l] + i);
+            if (P.hs_tab_smem_off[l] != 0xffffffffu) {
+                const uint32_t nt = 8u << P.tab_log2[l];
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(P.set_tabs + P.tab_off[l]);
+                for (uint32_t i = threadIdx.x; i < nt; i += CONSUMER_WARPS * 32u) code_smem[P.hs_tab_smem_off[l] + i] = __ldg(src + i);
+            }
+        }
+        if (any) asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+    }
+
     uint32_t s = 0, ph = 0;
     for (uint32_t t = t_begin; t < t_end; ++t) {
         const PackLeaf* L = P.leaves + (size_t)pack * P.nleaves;
         const uint32_t pack_row0 = chunk * tile_rows;          // first row of the tile within the pack
 
-        if (!ONLY32 && P.code_smem_words && pack != bm_pack) {
+        if (!ONLY32 && P.code_bitmap_words && pack != bm_pack) {
             // new pack: the consumers copy its code bitmaps (built by codeset_kernel) into shared memory
             asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));   // everybody is done with the previous pack's bitmaps
             for (uint32_t l = 0; l < P.nleaves; ++l) {
@@ -909,10 +963,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             case LM_CODESET:
                 word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, code_smem + P.code_smem_off[li]);
                 break;
-            case LM_HASHSET:
-                word = leaf_hashset(sw, P.views[lf.view], g0, Rp, lane,
-                                    reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]), P.tab_log2[li]);
+            case LM_HASHSET: {
+                const uint32_t to = P.hs_tab_smem_off[li];
+                const ulonglong2* tab = to != 0xffffffffu ? reinterpret_cast<const ulonglong2*>(code_smem + to)
+                                                          : reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]);
+                const ColView& hv = P.views[lf.view];
+                word = leaf_hashset(sw, hv.width, hv.type, hv.base, g0, Rp, lane, code_smem + P.hs_smem_off[li], P.pre_log2[li], tab, P.tab_log2[li]);
                 break;
+            }
             default: {
                 const ColView& v = P.views[lf.view];
                 if (v.kind == CK_RUNEND) word = leaf_runend(lf, v, (uint32_t)wr, pi.n, lane < Rp, P.set_vals);

@@ -134,6 +134,14 @@ struct ScanParams {
     uint32_t set_off[MAX_LEAVES + 1];
     uint32_t tab_off[MAX_LEAVES];     // LM_HASHSET: first u64 of the leaf's table in set_tabs
     uint8_t  tab_log2[MAX_LEAVES];    //             log2(#buckets) >= 1
+    // LM_HASHSET: a one-hash prefilter bitmap of 2^pre_log2 bits per leaf (bit set_hash32(v) >> (32 - pre_log2)), copied
+    // into shared memory at hs_smem_off[l] (word offset behind the code bitmaps); the exact table is copied to
+    // hs_tab_smem_off[l] as well when it is small (0xffffffff: looked up in global memory)
+    const uint32_t* set_pre;          // concatenated prefilter bitmaps
+    uint32_t pre_off[MAX_LEAVES];     // first word of the leaf's bitmap in set_pre
+    uint8_t  pre_log2[MAX_LEAVES];    // 0: leaf has no table
+    uint32_t hs_smem_off[MAX_LEAVES];
+    uint32_t hs_tab_smem_off[MAX_LEAVES];
     uint32_t agg_view0;        // views[agg_view0 + pack * naggs + j]
     uint32_t leaf_view0;       // views[leaf_view0 + pack * nleaves + l]
     uint8_t  postfix[MAX_POSTFIX];
@@ -142,6 +150,7 @@ struct ScanParams {
     // code_smem_off[l]; code_smem_words = size of that area (0: the program has no such leaf)
     uint32_t code_smem_off[MAX_LEAVES];
     uint32_t code_smem_words;
+    uint32_t code_bitmap_words;       // words of that area holding per-pack code bitmaps (0: nothing to reload per pack)
     // general kernels: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp) and the CTA's
     // double-buffered final match words, both behind the code bitmaps (word offset from their start)
     uint32_t stack_off_words;
@@ -181,5 +190,7 @@ KX_HD inline uint64_t type_ext(int t, uint64_t x) {
     return x;
 }
 KX_HD inline uint64_t width_mask(int w) { return w >= 64 ? ~0ull : ((1ull << w) - 1ull); }
+// 32-bit hash of a 64-bit value for the IN/NIN set structures (two multiply-adds; top bits are used)
+KX_HD inline uint32_t set_hash32(uint64_t v) { return uint32_t(v) * 0x9E3779B1u + uint32_t(v >> 32) * 0x85EBCA77u; }
 
 }  // namespace kx

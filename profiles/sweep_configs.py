@@ -25,6 +25,7 @@ import knoxdb_b200 as kb   # noqa: E402
 import oracle as ko        # noqa: E402  (checker only)
 
 PEAK = 6450.0
+M1, M4 = 1 << 20, 1 << 22
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
@@ -176,7 +177,6 @@ def run_case(ctx, case, reps=5):
 
 def build_cases(rng, only):
     cases = []
-    M1, M4 = 1 << 20, 1 << 22
 
     def want(tag):
         return not only or tag in only
@@ -340,6 +340,20 @@ def main():
     rng = np.random.default_rng(1)
     ctx = kb.Context(0)
     results = []
+
+    def canary(tag):
+        """a fixed HBM-bound scan (raw uint64, 256 x 1 Mi rows, range -> count: 8 B/row) timed before and after the
+        sweep: the box is healthy when it runs at >= ~100 % of the measured copy peak; a slow or throttled box shows here"""
+        crng = np.random.default_rng(99)
+        raws = [raw_block(crng.integers(0, 2**60 - 1, M1, dtype=np.uint64)) for _ in range(2)]
+        c = Case(f"canary ({tag}) raw u64 1Mi range count", M1, 256, {1: (kb.UINT64, raws, ko.U64)}, [kb.Leaf(1, kb.UINT64, kb.RANGE, 1 << 58, 3 << 58)], bytes_per_row=8.0)
+        r = run_case(ctx, c, args.reps)
+        r["canary"] = True
+        results.append(r)
+        print(f"{r['case']:<78s} {r['kernel_ms']:8.3f} ms {r['rows_per_s'] / 1e9:9.1f} Grows/s {r['algorithmic_GBps']:8.1f} GB/s {100 * r['frac_of_measured_peak']:5.1f}%", flush=True)
+        return r["frac_of_measured_peak"]
+
+    health = [canary("before")]
     for case in build_cases(rng, only):
         try:
             r = run_case(ctx, case, args.reps)
@@ -352,6 +366,10 @@ def main():
             print(f"{r['case']:<78s} {r['kernel_ms']:8.3f} ms {r['rows_per_s'] / 1e9:9.1f} Grows/s {r['algorithmic_GBps']:8.1f} GB/s {100 * r['frac_of_measured_peak']:5.1f}% sel={r['selectivity']:.4f}", flush=True)
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         json.dump({"peak_GBps": PEAK, "results": results}, open(args.out, "w"), indent=1)
+    health.append(canary("after"))
+    json.dump({"peak_GBps": PEAK, "box_health": {"canary_frac_of_peak": health, "healthy": min(health) >= 0.95}, "results": results}, open(args.out, "w"), indent=1)
+    if min(health) < 0.95:
+        print(f"WARNING: the canary scan ran at {100 * min(health):.0f} % of the measured copy peak: this box is slow or throttled, treat the numbers with care", flush=True)
     if not only or "c4" in only:
         try:
             rs = run_c4(ctx, rng)
@@ -360,7 +378,7 @@ def main():
         for r in rs:
             print(json.dumps(r), flush=True)
         results.extend(rs)
-        json.dump({"peak_GBps": PEAK, "results": results}, open(args.out, "w"), indent=1)
+        json.dump({"peak_GBps": PEAK, "box_health": {"canary_frac_of_peak": health, "healthy": min(health) >= 0.95}, "results": results}, open(args.out, "w"), indent=1)
     ctx.close()
 
 

@@ -64,3 +64,19 @@ def test_product_does_not_reference_the_oracle():
             if f.endswith((".py", ".cu", ".cpp", ".h")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "knox_oracle" not in src and "libknox_oracle" not in src and "import oracle" not in src, f
+
+
+def test_scan_kernels_do_not_spill():
+    """ptxas -v of the build: the persistent scan kernels run at the 96-register budget of two 9-warp CTAs per SM; a
+    spill there slows every code path of the kernel down (measured: 2x), so the build refuses to produce one."""
+    import json
+    import os
+    from knoxdb_b200 import build as kbuild
+    kbuild.build()
+    if not os.path.exists(kbuild.INFO):
+        kbuild.build(force=True)
+    usage = json.load(open(kbuild.INFO))
+    scans = {k: v for k, v in usage.items() if "scan_kernel" in k and "exclusive" not in k}
+    assert len(scans) >= 5, sorted(usage)
+    for k, v in scans.items():
+        assert v["spill_stores"] == 0 and v["spill_loads"] == 0 and v["registers"] <= 96, (k, v)

@@ -139,6 +139,30 @@ def test_container_match_and_decode(ctx, t):
                     assert (got == oc.match_set(su, negate=neg)).all(), (name, kind, "set", neg)
 
 
+@pytest.mark.parametrize("t", [ko.U64, ko.I64, ko.I32, ko.U16])
+def test_in_sets_of_every_size_on_packed_and_raw_blocks(ctx, t):
+    """MatchInSet / MatchNotInSet on bit-packed and raw blocks (int_bitpack.go:249-291, int_raw.go:339-380) through the
+    prefilter + hash-table path: set sizes that keep the exact table in shared memory and sizes that leave it in
+    global memory, members and non-members, tiles with several passes per warp."""
+    n = 150_001
+    info = np.iinfo(ko.NP[t])
+    span = min(int(info.max) - 1000, 1 << 38)
+    lo = max(int(info.min), -span // 2) if info.min < 0 else 0
+    vals = RNG.integers(lo, lo + span, n, dtype=np.int64).astype(ko.NP[t])
+    for kind in ("bitpack", "raw"):
+        blob = ko.store(kind, t, vals)
+        oc = ko.Container(t, blob)
+        for nset in (1, 5, 64, 700, 5000, 40000):
+            members = RNG.choice(vals, min(nset, n) // 2 + 1)
+            others = kt.typed_rand(RNG, t, nset // 2 + 1)
+            su = ko.as_u64(t, np.unique(np.concatenate([members, others])))
+            for neg, op in ((False, ko.IN), (True, ko.NI)):
+                got, cnt = ctx.container_match(t, blob, op, values=su, nrows=n)
+                want = oc.match_set(su, negate=neg)
+                assert (got == want).all(), (kind, nset, neg)
+                assert cnt == int(np.unpackbits(want).sum())
+
+
 def test_bitset_ops(ctx):
     import knoxdb_b200 as kb
     L = ko.lib()
