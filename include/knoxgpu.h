@@ -147,6 +147,20 @@ int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, in
 int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, uint8_t block_type,
               const uint32_t* sel, const uint64_t* sel_off, void* dst);
 
+/* Scan + TIME-BUCKETED reduce (group by time window): what a series query does with every streamed row —
+ * t = Interval.TruncateRelative(ts, Range.From) picks the window, Bucket.Push feeds the window's reducer
+ * (pkg/series/series.go:192-256, internal/reducer/bucket_native.go:104-167) — for the order-independent reducers
+ * count / sum / min / max (internal/reducer/reducer.go:138-297; mean = sum / count).  The caller computes the window
+ * edges with TimeUnit.Next (pkg/util/timeunit.go:234-263; calendar units give irregular windows): `edges` holds
+ * nbuckets + 1 ascending values of the timestamp column's type as 64-bit patterns, window k = [edges[k], edges[k+1]);
+ * matching rows outside [edges[0], edges[nbuckets]) belong to no window.  bucket_counts (nullable): nbuckets match
+ * counts.  out: naggs x nbuckets results, out[j * nbuckets + k] = value column j in window k (integer results are
+ * exact and order-independent; float64 sums are compensated per thread and combined with atomic adds).  counts
+ * (nullable): npacks per-pack match counts of the filter, as in kx_scan. */
+int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks,
+                    uint16_t ts_field, uint8_t ts_type, const uint64_t* edges, int nbuckets,
+                    const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out, int64_t* counts);
+
 /* Same scan over blocks that still live in HOST memory (cold device cache): the blocks of
  * all referenced fields are uploaded, scanned and dropped in pipelined batches.
  * blocks[i*nfields + f] / block_len[...] = encoded block of pack i, field fields[f]. */

@@ -250,19 +250,23 @@ struct SelectOut {
     bool overflow = false;
 };
 
+// keep_layout (optional): leave the match bitsets on the device (ctx->d_bitsets, pack i at keep_layout[i]; PackInfo table
+// at the start of ctx->d_packs) for a follow-up kernel on the same stream (kx_scan_buckets)
 int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bitsets, const size_t* bitset_off,
-             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, SelectOut* so = nullptr) {
+             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, SelectOut* so = nullptr,
+             std::vector<size_t>* keep_layout = nullptr) {
     const int npacks = job.npacks, nleaves = int(prog->leaves.size());
     // selection vectors are extracted from device-resident bitsets laid out back to back (8-byte aligned)
     std::vector<size_t> sel_layout;
-    const bool dev_bits = bitsets != nullptr || so != nullptr;
-    if (so) {
+    const bool dev_bits = bitsets != nullptr || so != nullptr || keep_layout != nullptr;
+    if (so || keep_layout) {
         if (bitsets) return fail(ctx, KX_EINVAL, "selection vectors and host bitsets cannot be requested together");
         size_t o = 0;
         sel_layout.resize(size_t(npacks));
         for (int p = 0; p < npacks; ++p) { sel_layout[size_t(p)] = o; o += round_up((size_t(job.nrows[size_t(p)]) + 7) / 8, 8); }
         bitset_off = sel_layout.data();
-        for (int p = 0; p <= npacks; ++p) so->off[p] = 0;
+        if (so) for (int p = 0; p <= npacks; ++p) so->off[p] = 0;
+        if (keep_layout) *keep_layout = sel_layout;
     }
     ctx->last_kernel_ms = ctx->last_total_ms = 0; ctx->last_launches = 0;
     if (naggs < 0 || naggs > MAX_AGGS) return fail(ctx, KX_EINVAL, "too many aggregates");
@@ -908,6 +912,111 @@ int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, in
     rc = run_scan(ctx, prog, job, nullptr, nullptr, counts, aggs, naggs, agg_out, &so);
     if (rc) return rc;
     if (so.overflow) return fail(ctx, KX_ENOMEM, "kx_scan_select: selection buffer too small (sel_off[npacks] holds the required size)");
+    return KX_OK;
+}
+
+int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint16_t ts_field, uint8_t ts_type,
+                    const uint64_t* edges, int nbuckets, const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out,
+                    int64_t* counts) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog, true);
+    if (rc) return rc;
+    if (npacks < 0 || (npacks && !packs) || nbuckets < 1 || !edges || naggs < 0 || naggs > MAX_AGGS || (naggs && (!aggs || !out)))
+        return fail(ctx, KX_EINVAL, "kx_scan_buckets: bad arguments");
+    if (type_bits(ts_type) == 0 || type_is_float(ts_type)) return fail(ctx, KX_EUNSUPPORTED, "window column must be an integer / timestamp block");
+    const uint64_t ts_flip = type_is_signed(ts_type) ? 0x8000000000000000ull : 0ull;
+    for (int k = 0; k < nbuckets; ++k)
+        if ((edges[k] ^ ts_flip) > (edges[k + 1] ^ ts_flip)) return fail(ctx, KX_EINVAL, "window edges must ascend");
+    for (int j = 0; j < naggs; ++j) {
+        int t = aggs[j].block_type;
+        if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
+    }
+    // the scan proper: filter -> match bitsets that stay on the device; the window column and the value columns ride
+    // along as "aggregate" views of the job (looked up, not reduced by the scan)
+    std::vector<kx_agg_req> cols(size_t(naggs) + 1);
+    cols[0] = kx_agg_req{ts_field, ts_type, 0};
+    for (int j = 0; j < naggs; ++j) cols[size_t(j) + 1] = aggs[j];
+    ScanJob job;
+    rc = build_scan_job(ctx, prog, packs, npacks, cols.data(), naggs + 1, job);
+    if (rc) return rc;
+    std::vector<ColView> views;
+    views.swap(job.agg_views);   // [npacks][1 + naggs]
+    for (int p = 0; p < npacks; ++p)
+        for (int c = 0; c <= naggs; ++c)
+            if (views[size_t(p) * (naggs + 1) + c].n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
+    std::vector<size_t> layout;
+    rc = run_scan(ctx, prog, job, nullptr, nullptr, counts, nullptr, 0, nullptr, nullptr, &layout);
+    if (rc) return rc;
+    const double scan_kernel_ms = ctx->last_kernel_ms, scan_total_ms = ctx->last_total_ms;
+
+    // ---- bucket table + descriptors
+    const size_t ncell = size_t(naggs) + 1, ncells = size_t(nbuckets) * ncell;
+    std::vector<uint32_t> job0(size_t(npacks) + 1);
+    uint64_t njobs = 0;
+    for (int p = 0; p < npacks; ++p) {
+        job0[size_t(p)] = uint32_t(njobs);
+        njobs += ((uint64_t(job.nrows[size_t(p)]) + 31) / 32 + BUCKET_JOB_GROUPS - 1) / BUCKET_JOB_GROUPS;
+    }
+    job0[size_t(npacks)] = uint32_t(njobs);
+    if (njobs > 0xfffffff0ull) return fail(ctx, KX_EINVAL, "too many rows in one kx_scan_buckets call");
+    const size_t off_views = 0, off_edges = round_up(sizeof(ColView) * views.size(), 256);
+    const size_t off_job0 = off_edges + round_up(8 * (size_t(nbuckets) + 1), 256);
+    const size_t off_table = off_job0 + round_up(4 * job0.size(), 256);
+    const size_t total = off_table + sizeof(BucketCell) * ncells;
+    CK(ctx->h_aux.reserve(total));
+    CK(ctx->d_tmp.reserve(total));
+    uint8_t* h = static_cast<uint8_t*>(ctx->h_aux.p);
+    if (!views.empty()) std::memcpy(h + off_views, views.data(), sizeof(ColView) * views.size());
+    uint64_t* hk = reinterpret_cast<uint64_t*>(h + off_edges);
+    for (int k = 0; k <= nbuckets; ++k) hk[k] = edges[k] ^ ts_flip;
+    std::memcpy(h + off_job0, job0.data(), 4 * job0.size());
+    BucketCell* ht = reinterpret_cast<BucketCell*>(h + off_table);
+    for (size_t i = 0; i < ncells; ++i) ht[i] = BucketCell{0, 0, ~0ull, 0};
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
+    BucketParams P{};
+    P.packs = static_cast<const PackInfo*>(ctx->d_packs.p);
+    P.bits = static_cast<const uint8_t*>(ctx->d_bitsets.p);
+    P.views = reinterpret_cast<const ColView*>(d + off_views);
+    P.edges = reinterpret_cast<const uint64_t*>(d + off_edges);
+    P.job0 = reinterpret_cast<const uint32_t*>(d + off_job0);
+    P.table = reinterpret_cast<BucketCell*>(d + off_table);
+    P.ts_flip = ts_flip;
+    P.npacks = uint32_t(npacks); P.njobs = uint32_t(njobs); P.nbuckets = uint32_t(nbuckets); P.naggs = uint32_t(naggs);
+    for (int j = 0; j < naggs; ++j) P.agg_type[j] = aggs[j].block_type;
+    CK(cudaEventRecord(ctx->ev_start, ctx->stream));
+    CK(cudaMemcpyAsync(d, h, total, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
+    if (npacks) { CK(launch_bucket(P, ctx->num_sms, ctx->stream)); ctx->last_launches++; }
+    CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
+    CK(cudaMemcpyAsync(ht, d + off_table, sizeof(BucketCell) * ncells, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaEventRecord(ctx->ev_end, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    float ms = 0;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_k0, ctx->ev_k1)); ctx->last_kernel_ms = scan_kernel_ms + ms;
+    CK(cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end)); ctx->last_total_ms = scan_total_ms + ms;
+
+    for (int k = 0; k < nbuckets; ++k) {
+        if (bucket_counts) bucket_counts[k] = int64_t(ht[size_t(k) * ncell].count);
+        for (int j = 0; j < naggs; ++j) {
+            const BucketCell& c = ht[size_t(k) * ncell + 1 + size_t(j)];
+            kx_agg_out o{};
+            const int t = aggs[j].block_type;
+            o.count = int64_t(c.count); o.valid = c.count ? 1 : 0;
+            if (c.count) {
+                if (t == KX_FLOAT64) {
+                    o.sum_bits = c.sum;
+                    o.min_bits = (c.mn >> 63) ? (c.mn & 0x7fffffffffffffffull) : ~c.mn;   // inverse of the order key
+                    o.max_bits = (c.mx >> 63) ? (c.mx & 0x7fffffffffffffffull) : ~c.mx;
+                } else {
+                    const uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
+                    o.sum_bits = type_ext(t, c.sum);
+                    o.min_bits = c.mn ^ flip; o.max_bits = c.mx ^ flip;
+                }
+            }
+            out[size_t(j) * size_t(nbuckets) + size_t(k)] = o;
+        }
+    }
     return KX_OK;
 }
 

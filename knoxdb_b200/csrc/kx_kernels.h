@@ -59,6 +59,27 @@ struct AlpFixJob {
     uint32_t invert, pad;
 };
 
+// time-bucketed reduce (kx_bucket.cu): one table cell per (window, 1 + value column); cell 0 of a window = match count
+struct BucketCell {
+    uint64_t count;
+    uint64_t sum;      // integer sum mod 2^64, or IEEE bits of the float64 sum
+    uint64_t mn, mx;   // order-preserving unsigned keys (ints: ^ sign flip; floats: f64_key); identities ~0 / 0
+};
+constexpr int BUCKET_THREADS = 128;
+constexpr uint32_t BUCKET_JOB_GROUPS = 64;   // consecutive 32-row groups per warp job (2048 rows)
+struct BucketParams {
+    const PackInfo* packs;      // [npacks] (bitset_off = the pack's bitset inside `bits`)
+    const uint8_t*  bits;       // device-resident match bitsets of the scan
+    const ColView*  views;      // [npacks][1 + naggs]: timestamp column, then the value columns
+    const uint64_t* edges;      // [nbuckets + 1] ascending window edges as order keys (value ^ ts_flip)
+    const uint32_t* job0;       // [npacks + 1] first warp job of every pack
+    BucketCell*     table;      // [nbuckets][1 + naggs]
+    uint64_t ts_flip;
+    uint32_t npacks, njobs, nbuckets, naggs;
+    uint8_t  agg_type[MAX_AGGS];
+};
+cudaError_t launch_bucket(const BucketParams& P, int num_sms, cudaStream_t stream);
+
 constexpr size_t SCAN_MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the scan kernel may ask for
 
 // pruning over a device-resident statistics index (kx_stats): statistics are column-major [field][pack]

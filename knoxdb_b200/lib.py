@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
     "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
     "kx_hash_value", "kx_hash_bytes",
-    "kx_scan_select", "kx_gather",
+    "kx_scan_select", "kx_gather", "kx_scan_buckets",
     "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
 ]
 
@@ -87,6 +87,8 @@ def lib():
         "kx_prog_free": (None, [vp]),
         "kx_scan": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_scan_select": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, sz, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
+        "kx_scan_buckets": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, C.c_int, C.POINTER(_AggReq), C.c_int, vp,
+                                      C.POINTER(AggOut), vp]),
         "kx_gather": (C.c_int, [vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, vp, vp]),
         "kx_scan_host": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_agg_combine": (C.c_int, [C.c_uint8, C.POINTER(AggOut), C.c_int, C.POINTER(AggOut)]),
@@ -292,6 +294,20 @@ class Context:
             self._check(rc)
             break
         return {"sel": sel[:int(sel_off[n])], "sel_off": sel_off, "counts": counts, "aggs": list(aout)[:len(aggs)]}
+
+    def scan_buckets(self, prog, packs, ts_field, ts_type, edges, aggs=()):
+        """kx_scan_buckets → dict(bucket_counts (nbuckets), aggs: per value column a list of nbuckets AggOut, counts (npacks)).
+        edges: nbuckets + 1 ascending window starts (values of the timestamp column's type)."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        n = len(refs)
+        e = np.ascontiguousarray(np.asarray(edges, dtype=NP[ts_type]).astype(np.int64 if ts_type <= INT8 else np.uint64)).view(np.uint64)
+        nb = e.size - 1
+        counts = np.zeros(n, dtype=np.int64)
+        bcounts = np.zeros(max(nb, 1), dtype=np.int64)
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs) * max(nb, 1), 1))()
+        self._check(lib().kx_scan_buckets(self.h, prog.h, refs, n, ts_field, ts_type, _ptr(e), nb, areq, len(aggs), _ptr(bcounts), aout, _ptr(counts)))
+        return {"bucket_counts": bcounts[:nb], "aggs": [[aout[j * nb + k] for k in range(nb)] for j in range(len(aggs))], "counts": counts}
 
     def gather(self, packs, field, block_type, sel, sel_off):
         """kx_gather: values of `field` at the selected rows, concatenated in pack order"""

@@ -162,6 +162,9 @@ typedef struct ko_agg {
     int      valid;      /* 0 until the first row was reduced (r.t.IsZero()) */
 } ko_agg;
 void ko_reduce(int type, const uint64_t* vals, size_t n, const uint8_t* bits, ko_agg* state);
+void ko_bucket_reduce(int type, const uint64_t* vals, int ts_type, const uint64_t* ts, size_t n, const uint8_t* bits,
+                      const uint64_t* edges, int nbuckets, ko_agg* states);
+int ko_window_edges(int64_t from, int64_t to, int64_t step, int64_t* out, int cap);
 
 /* ---- filter tree: internal/operator/filter/match_core.go:14-215 ----
  * postfix program over leaf bitsets: byte < 0x80 → push leaf id, 0xFE = AND, 0xFF = OR

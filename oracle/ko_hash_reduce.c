@@ -177,28 +177,69 @@ size_t ko_bloom_build(uint8_t* buf, size_t cap, int elem_bytes, const uint8_t* v
  * internal/reducer/reducer.go:138-149 (Count), :168-179 (Sum: r.v += v in T),
  * :256-267 (Max: first || r.v < v), :286-297 (Min: first || r.v > v), fed row by row
  * in ascending row order by StreamResult.Append (internal/query/result.go:96-152). */
+static void reduce_one(int type, uint64_t v, ko_agg* st) {
+    st->count++;
+    if (type == KO_F64) {
+        double d, s, mn, mx; memcpy(&d, &v, 8);
+        memcpy(&s, &st->sum_bits, 8); s += d; memcpy(&st->sum_bits, &s, 8);
+        memcpy(&mn, &st->min_bits, 8); memcpy(&mx, &st->max_bits, 8);
+        if (!st->valid || mx < d) memcpy(&st->max_bits, &d, 8);
+        if (!st->valid || mn > d) memcpy(&st->min_bits, &d, 8);
+    } else if (type == KO_I64 || type == KO_I32 || type == KO_I16 || type == KO_I8) {
+        st->sum_bits += v; /* wraps mod 2^64 like int64 `+=` */
+        if (!st->valid || (int64_t)st->max_bits < (int64_t)v) st->max_bits = v;
+        if (!st->valid || (int64_t)st->min_bits > (int64_t)v) st->min_bits = v;
+    } else {
+        st->sum_bits += v;
+        if (!st->valid || st->max_bits < v) st->max_bits = v;
+        if (!st->valid || st->min_bits > v) st->min_bits = v;
+    }
+    st->valid = 1;
+}
+
 void ko_reduce(int type, const uint64_t* vals, size_t n, const uint8_t* bits, ko_agg* st) {
     for (size_t i = 0; i < n; i++) {
         if (bits && !((bits[i >> 3] >> (i & 7)) & 1)) continue;
-        uint64_t v = vals[i];
-        st->count++;
-        if (type == KO_F64) {
-            double d, s, mn, mx; memcpy(&d, &v, 8);
-            memcpy(&s, &st->sum_bits, 8); s += d; memcpy(&st->sum_bits, &s, 8);
-            memcpy(&mn, &st->min_bits, 8); memcpy(&mx, &st->max_bits, 8);
-            if (!st->valid || mx < d) memcpy(&st->max_bits, &d, 8);
-            if (!st->valid || mn > d) memcpy(&st->min_bits, &d, 8);
-        } else if (type == KO_I64 || type == KO_I32 || type == KO_I16 || type == KO_I8) {
-            st->sum_bits += v; /* wraps mod 2^64 like int64 `+=` */
-            if (!st->valid || (int64_t)st->max_bits < (int64_t)v) st->max_bits = v;
-            if (!st->valid || (int64_t)st->min_bits > (int64_t)v) st->min_bits = v;
-        } else {
-            st->sum_bits += v;
-            if (!st->valid || st->max_bits < v) st->max_bits = v;
-            if (!st->valid || st->min_bits > v) st->min_bits = v;
-        }
-        st->valid = 1;
+        reduce_one(type, vals[i], st);
     }
+}
+
+/* ------------------------------------------------------------------ time-bucketed reduce
+ * The series query (pkg/series/series.go:192-256) maps every streamed row to the start of its window,
+ * t = Interval.TruncateRelative(ts, Range.From) — a walk `last, next = base, Next(base)` that advances while
+ * !ts.Before(next) (pkg/util/timeunit.go:234-243) — and NativeBucket.Push (internal/reducer/bucket_native.go:104-167)
+ * feeds the row to that window's Reducer (reducer.go:138-297).  `edges` are the window starts produced by that walk
+ * (edges[0] = From, edges[k+1] = Next(edges[k])); rows before edges[0] or at/after edges[nbuckets] are outside the
+ * query's time range.  states: one ko_agg per window. */
+static int ts_before(int ts_type, uint64_t a, uint64_t b) {
+    if (ts_type == KO_I64 || ts_type == KO_I32 || ts_type == KO_I16 || ts_type == KO_I8) return (int64_t)a < (int64_t)b;
+    return a < b;
+}
+void ko_bucket_reduce(int type, const uint64_t* vals, int ts_type, const uint64_t* ts, size_t n, const uint8_t* bits,
+                      const uint64_t* edges, int nbuckets, ko_agg* states) {
+    for (size_t i = 0; i < n; i++) {
+        if (bits && !((bits[i >> 3] >> (i & 7)) & 1)) continue;
+        if (ts_before(ts_type, ts[i], edges[0]) || !ts_before(ts_type, ts[i], edges[nbuckets])) continue;
+        int k = 0;
+        while (!ts_before(ts_type, ts[i], edges[k + 1])) k++;   /* TruncateRelative's walk */
+        reduce_one(type, vals ? vals[i] : 0, &states[k]);
+    }
+}
+
+/* Window starts of a fixed-duration unit (minutes, hours: `step` in the timestamp's resolution, dividing one day):
+ * TimeUnit.Next(t, 1) = Truncate(t) + Duration (timeunit.go:245-249) with Truncate = time.Truncate(Duration), i.e.
+ * rounding DOWN to a multiple of the step (:196-199; multiples counted from Go's zero time, which is a whole number of
+ * days before the Unix epoch).  out[0] = from, then aligned starts until one is >= to; returns the number of edges. */
+int ko_window_edges(int64_t from, int64_t to, int64_t step, int64_t* out, int cap) {
+    int n = 0;
+    int64_t t = from;
+    while (n < cap) {
+        out[n++] = t;
+        if (t >= to) break;
+        int64_t m = t % step; if (m < 0) m += step;
+        t = (t - m) + step;
+    }
+    return n;
 }
 
 /* ------------------------------------------------------------------ filter tree

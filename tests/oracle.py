@@ -92,6 +92,8 @@ def lib():
             "ko_bloom_contains": (C.c_int, [vp, C.c_size_t, C.c_uint64]),
             "ko_bloom_build": (C.c_size_t, [vp, C.c_size_t, C.c_int, vp, vp, C.c_size_t, C.c_int, C.c_int]),
             "ko_reduce": (None, [C.c_int, vp, C.c_size_t, vp, vp]),
+            "ko_bucket_reduce": (None, [C.c_int, vp, C.c_int, vp, C.c_size_t, vp, vp, C.c_int, vp]),
+            "ko_window_edges": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, vp, C.c_int]),
             "ko_tree_eval": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_size_t, vp]),
             "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
             "ko_baseline_bitpack_scan": (C.c_int64, [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_int]),
@@ -230,6 +232,25 @@ def reduce(type_, values, bits=None, state=None):
     b = np.ascontiguousarray(bits, dtype=np.uint8) if bits is not None else None
     lib().ko_reduce(type_, _p(v), v.size, _p(b) if b is not None else None, C.byref(st))
     return st
+
+
+def bucket_reduce(type_, values, ts_type, ts, bits, edges, states=None):
+    """ko_bucket_reduce: per-window reducer states (list of Agg) of the matching rows; edges = nbuckets + 1 window starts"""
+    ts64 = as_u64(ts_type, ts)
+    e = as_u64(ts_type, np.asarray(edges, dtype=NP[ts_type]))
+    nb = e.size - 1
+    st = states if states is not None else (Agg * nb)()
+    v = as_u64(type_, values) if values is not None else None
+    b = np.ascontiguousarray(bits, dtype=np.uint8) if bits is not None else None
+    lib().ko_bucket_reduce(type_, _p(v) if v is not None else None, ts_type, _p(ts64), ts64.size, _p(b) if b is not None else None, _p(e), nb, st)
+    return st
+
+
+def window_edges(t_from, t_to, step):
+    """ko_window_edges: window starts of a fixed-duration unit (From, then aligned multiples of step) up to >= To"""
+    out = np.zeros(int((t_to - t_from) // step) + 4, dtype=np.int64)
+    n = lib().ko_window_edges(int(t_from), int(t_to), int(step), _p(out), out.size)
+    return out[:n].copy()
 
 
 def tree_eval(postfix, leaf_bits, n):

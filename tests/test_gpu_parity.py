@@ -345,6 +345,70 @@ def test_staged_and_on_demand_reduce_agree_bit_for_bit(ctx, monkeypatch):
             ctx.block_drop(p, 1, f)
 
 
+@pytest.mark.parametrize("ordered", [True, False])
+def test_time_bucketed_reduce(ctx, ordered):
+    """series query shape (pkg/series/series.go:192-256): filter, then count / sum / min / max per time window.
+    Window starts follow TimeUnit.Next (first window starts at From, the following ones at aligned multiples of the
+    step); integer results bit-exact, float64 sums within 1e-12 of the oracle's sequential per-window sum."""
+    import knoxdb_b200 as kb
+    nrows = [50_000, 70_001, 1, 33_333, 2048]
+    packs, accts = make_table(RNG, len(nrows), nrows)
+    if not ordered:   # journal-like packs: rows not in time order
+        for cols in packs:
+            perm = RNG.permutation(cols["ts"].size)
+            for k in cols:
+                cols[k] = cols[k][perm]
+    blobs = put_table(ctx, packs, "dict")
+    all_ts = np.concatenate([c["ts"] for c in packs])
+    t_from, t_to = int(np.sort(all_ts)[all_ts.size // 20]) + 7, int(np.sort(all_ts)[all_ts.size * 9 // 10])
+    refs = [(p, 1) for p in range(len(nrows))]
+    for step in (60, 3600, 7 * 3600):
+        edges = ko.window_edges(t_from, t_to, step)
+        assert edges[0] == t_from and edges[-1] >= t_to and (np.diff(edges) > 0).all()
+        setv = RNG.choice(accts, 200, replace=False)
+        prog = kb.Program(ctx, [kb.Leaf(F_TS, kb.INT64, kb.RANGE, t_from, t_to - 1), kb.Leaf(F_ACCT, kb.UINT64, kb.IN, values=setv)])
+        res = ctx.scan_buckets(prog, refs, F_TS, kb.INT64, edges, aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64), (F_ACCT, kb.UINT64)])
+        nb = edges.size - 1
+        st_i = st_f = st_a = None
+        counts = []
+        for cols, enc in zip(packs, blobs):
+            l0 = ko.Container(ko.I64, enc[F_TS]).match(ko.RG, ko.scalar_u64(ko.I64, t_from), ko.scalar_u64(ko.I64, t_to - 1))
+            l1 = ko.Container(ko.U64, enc[F_ACCT]).match_set(setv)
+            bits = ko.tree_eval([0, 1, 0xFE], [l0, l1], cols["ts"].size)
+            counts.append(int(np.unpackbits(bits).sum()))
+            st_i = ko.bucket_reduce(ko.I64, cols["amount"], ko.I64, cols["ts"], bits, edges, st_i)
+            st_f = ko.bucket_reduce(ko.F64, cols["famount"], ko.I64, cols["ts"], bits, edges, st_f)
+            st_a = ko.bucket_reduce(ko.U64, cols["acct"], ko.I64, cols["ts"], bits, edges, st_a)
+        assert res["counts"].tolist() == counts
+        assert res["bucket_counts"].tolist() == [st_i[k].count for k in range(nb)]
+        assert sum(counts) == int(res["bucket_counts"].sum())   # the range leaf keeps every match inside [From, To)
+        for k in range(nb):
+            gi, gf, ga = res["aggs"][0][k], res["aggs"][1][k], res["aggs"][2][k]
+            assert (gi.count, bool(gi.valid)) == (st_i[k].count, bool(st_i[k].valid)), (step, k)
+            if not st_i[k].valid:
+                continue
+            assert (gi.sum_bits, gi.min_bits, gi.max_bits) == (st_i[k].sum_bits, st_i[k].min_bits, st_i[k].max_bits), (step, k)
+            assert (ga.sum_bits, ga.min_bits, ga.max_bits) == (st_a[k].sum_bits, st_a[k].min_bits, st_a[k].max_bits), (step, k)
+            want = float(np.uint64(st_f[k].sum_bits).view(np.float64))
+            assert abs(gf.value("sum", kb.FLOAT64) - want) <= 1e-12 * abs(want), (step, k)
+            assert (gf.min_bits, gf.max_bits) == (st_f[k].min_bits, st_f[k].max_bits), (step, k)
+        prog.close()
+    # windows that do not cover every match: rows outside [edges[0], edges[-1]) belong to no window
+    prog = kb.Program(ctx, [kb.Leaf(F_AMT, kb.INT64, kb.GT, 0)])
+    edges = ko.window_edges(t_from, t_from + 5000, 600)
+    res = ctx.scan_buckets(prog, refs, F_TS, kb.INT64, edges, aggs=[(F_AMT, kb.INT64)])
+    st = None
+    for cols, enc in zip(packs, blobs):
+        bits = ko.Container(ko.I64, enc[F_AMT]).match(ko.GT, ko.scalar_u64(ko.I64, 0), 0)
+        st = ko.bucket_reduce(ko.I64, cols["amount"], ko.I64, cols["ts"], bits, edges, st)
+    assert [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res["aggs"][0]] == [(s.count, s.sum_bits, s.min_bits, s.max_bits) for s in st]
+    assert int(res["bucket_counts"].sum()) < int(res["counts"].sum())
+    prog.close()
+    for p in range(len(nrows)):
+        for f in (F_TS, F_ACCT, F_AMT, F_FAMT):
+            ctx.block_drop(p, 1, f)
+
+
 def test_full_size_pack_properties(ctx):
     """BASELINE config 2 at full size: 4M-row bit-packed packs; size-independent checks
     (count == popcount(bitset) == numpy truth; NE is the complement of EQ; LT ∪ GE covers all rows)"""

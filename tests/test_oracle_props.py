@@ -321,3 +321,30 @@ def test_alp_reference_quirks_are_pinned():
     assert (got == (v <= 6)).all()
     got = kt.unpack_bits(c.match(ko.RG, ko.scalar_u64(ko.F64, 5.1), ko.scalar_u64(ko.F64, 5.9)), v.size)
     assert (got == ((v == 5) | (v == 6))).all()
+
+
+def test_bucket_reduce_and_window_edges_follow_the_series_walk():
+    """ko_window_edges restates TimeUnit.Next for fixed-duration units (first window starts at From, the next ones at
+    multiples of the step, pkg/util/timeunit.go:196-199, 245-249) and ko_bucket_reduce the TruncateRelative walk +
+    per-window reducers (timeunit.go:234-243, reducer/bucket_native.go:104-167): checked against a direct numpy
+    evaluation, including rows outside the range and negative (pre-epoch) timestamps."""
+    rng = np.random.default_rng(5)
+    for t_from, t_to, step in ((1_700_000_123, 1_700_090_000, 3600), (-7_205, 9_000, 60), (0, 86_400, 7200), (10, 11, 3600)):
+        e = ko.window_edges(t_from, t_to, step)
+        assert e[0] == t_from and e[-1] >= t_to and e[-2] < t_to
+        assert all((int(x) % step) == 0 for x in e[1:]) and all(0 < int(b) - int(a) <= step for a, b in zip(e[:-1], e[1:]))
+        n = 20_000
+        ts = rng.integers(t_from - 2 * step, t_to + 2 * step, n).astype(np.int64)
+        vals = rng.integers(-10**12, 10**12, n).astype(np.int64)
+        bits = kt.pack_bits(rng.random(n) < 0.6)
+        st = ko.bucket_reduce(ko.I64, vals, ko.I64, ts, bits, e)
+        m = np.unpackbits(bits, bitorder="little")[:n].astype(bool)
+        k = np.searchsorted(e, ts, side="right") - 1
+        for b in range(e.size - 1):
+            sel = m & (k == b)
+            assert st[b].count == int(sel.sum())
+            if sel.any():
+                assert np.uint64(st[b].sum_bits).view(np.int64) == vals[sel].sum()
+                assert np.uint64(st[b].min_bits).view(np.int64) == vals[sel].min() and np.uint64(st[b].max_bits).view(np.int64) == vals[sel].max()
+            else:
+                assert not st[b].valid
