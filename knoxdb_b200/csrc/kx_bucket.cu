@@ -72,25 +72,21 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
             cnt = 0;
         };
 
-        for (uint32_t g = g_begin; g < g_end; ++g) {
-            const uint32_t word = __ldg(words + g);
-            if (word == 0) continue;                       // warp-uniform: groups without a match cost one load
-            if (!((word >> lane) & 1u)) continue;
-            const uint32_t row = g * 32u + lane;
-            const uint64_t key = decode_value_at(tsv, row) ^ P.ts_flip;
+        // one matching row: find its window (the lane's current window first), fold the values in
+        auto consume = [&](uint64_t key, const uint64_t (&v)[MAX_AGGS]) {
             if (key < cur_lo || key >= cur_hi) {
                 flush();
                 // window k with edge[k] <= key < edge[k + 1]; rows outside [edge[0], edge[nbuckets]) belong to no window
-                uint32_t a = 0, b = P.nbuckets + 1u;       // first edge > key
+                uint32_t a = 0, b = P.nbuckets + 1u;   // first edge > key
                 while (a < b) { uint32_t m = (a + b) >> 1; if (__ldg(P.edges + m) <= key) a = m + 1; else b = m; }
-                if (a == 0 || a > P.nbuckets) { cur = 0xffffffffu; cur_lo = 1; cur_hi = 0; continue; }
+                if (a == 0 || a > P.nbuckets) { cur = 0xffffffffu; cur_lo = 1; cur_hi = 0; return; }
                 cur = a - 1u; cur_lo = __ldg(P.edges + cur); cur_hi = __ldg(P.edges + cur + 1);
             }
             ++cnt;
 #pragma unroll
             for (int j = 0; j < MAX_AGGS; ++j) {
                 if ((uint32_t)j >= P.naggs) break;
-                const uint64_t bits = decode_value_at(P.views[(size_t)pack * ncell + 1 + j], row);
+                const uint64_t bits = v[j];
                 LaneAcc& A = acc[j];
                 if (P.agg_type[j] == 9) {
                     const double x = __longlong_as_double((long long)bits), sum = __longlong_as_double((long long)A.sum);
@@ -108,8 +104,106 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                     if (k > A.mx) A.mx = k;
                 }
             }
+        };
+
+        // Fast path (the common series shape): bit-packed / raw timestamp column, raw 64-bit value columns.  U groups at a
+        // time: the raw words of every matching row (timestamp words + values) are requested back to back and only
+        // then decoded and consumed in row order, so a warp pays one memory round trip per U groups, not three per group.
+        bool fast = tsv.kind == CK_BITS && tsv.width != 0;
+        const unsigned long long* vptr[MAX_AGGS];
+        uint64_t vbase[MAX_AGGS];
+#pragma unroll
+        for (int j = 0; j < MAX_AGGS; ++j) {
+            vptr[j] = nullptr; vbase[j] = 0;
+            if ((uint32_t)j < P.naggs) {
+                const ColView& av = P.views[(size_t)pack * ncell + 1 + j];
+                if (av.kind == CK_BITS && av.width == 64) { vptr[j] = reinterpret_cast<const unsigned long long*>(av.data); vbase[j] = type_is_float(av.type) ? 0ull : av.base; }
+                else fast = false;
+            }
         }
-        flush();
+        constexpr int U = 4;
+        if (fast) {
+            const uint32_t tw = tsv.width;
+            const uint32_t* tsw = reinterpret_cast<const uint32_t*>(tsv.data);
+            const uint64_t tmask = width_mask((int)tw);
+            for (uint32_t g0 = g_begin; g0 < g_end; g0 += U) {
+                uint32_t wd[U], anyw = 0;
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    wd[u] = g0 + u < g_end ? __ldg(words + g0 + u) : 0u;
+                    anyw |= wd[u];
+                }
+                if (anyw == 0) continue;                   // warp-uniform: groups without a match cost one load each
+                uint32_t t0[U], t1[U], t2[U];
+                uint64_t val[U][MAX_AGGS];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const bool on = (wd[u] >> lane) & 1u;
+                    const uint32_t row = (g0 + u) * 32u + lane;
+                    const uint64_t bit = (uint64_t)row * tw;
+                    const uint32_t* wp = tsw + (bit >> 5);
+                    t0[u] = on ? __ldg(wp) : 0u;
+                    t1[u] = on ? __ldg(wp + 1) : 0u;
+                    t2[u] = (on && tw > 32u) ? __ldg(wp + 2) : 0u;
+#pragma unroll
+                    for (int j = 0; j < MAX_AGGS; ++j) val[u][j] = (on && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (!((wd[u] >> lane) & 1u)) continue;
+                    const uint32_t sh = (uint32_t)(((uint64_t)((g0 + u) * 32u + lane) * tw) & 31u);
+                    const uint64_t f = (((uint64_t)__funnelshift_r(t1[u], t2[u], sh) << 32) | __funnelshift_r(t0[u], t1[u], sh)) & tmask;
+                    uint64_t v[MAX_AGGS];
+#pragma unroll
+                    for (int j = 0; j < MAX_AGGS; ++j) v[j] = val[u][j] + vbase[j];
+                    consume(type_ext(tsv.type, f + tsv.base) ^ P.ts_flip, v);
+                }
+            }
+        } else {
+            // generic path: any container kind, decoded at index row by row
+            for (uint32_t g = g_begin; g < g_end; ++g) {
+                const uint32_t word = __ldg(words + g);
+                if (!((word >> lane) & 1u)) continue;
+                const uint32_t row = g * 32u + lane;
+                uint64_t v[MAX_AGGS];
+#pragma unroll
+                for (int j = 0; j < MAX_AGGS; ++j) v[j] = (uint32_t)j < P.naggs ? decode_value_at(P.views[(size_t)pack * ncell + 1 + j], row) : 0ull;
+                consume(decode_value_at(tsv, row) ^ P.ts_flip, v);
+            }
+        }
+        // end of the job: when every lane that holds rows holds them for the SAME window (time-ordered packs, windows
+        // longer than a job), the warp combines its 32 accumulators with shuffles and flushes once instead of 32 times
+        {
+            const uint32_t holders = __ballot_sync(0xffffffffu, cur != 0xffffffffu && cnt != 0);
+            if (holders) {
+                const uint32_t c0 = __shfl_sync(0xffffffffu, cur, __ffs((int)holders) - 1);
+                if (__all_sync(0xffffffffu, cnt == 0 || cur == 0xffffffffu || cur == c0)) {
+                    if (cur != c0) cnt = 0;   // lanes without rows (their accumulators are at the identity)
+                    for (int off = 16; off > 0; off >>= 1) {
+                        cnt += __shfl_down_sync(0xffffffffu, cnt, off);
+#pragma unroll
+                        for (int j = 0; j < MAX_AGGS; ++j) {
+                            if ((uint32_t)j >= P.naggs) break;
+                            const uint64_t s2 = __shfl_down_sync(0xffffffffu, acc[j].sum, off), e2 = __shfl_down_sync(0xffffffffu, acc[j].err, off);
+                            const uint64_t mn2 = __shfl_down_sync(0xffffffffu, acc[j].mn, off), mx2 = __shfl_down_sync(0xffffffffu, acc[j].mx, off);
+                            if (P.agg_type[j] == 9) {   // double-double style merge of two compensated sums
+                                const double a = __longlong_as_double((long long)acc[j].sum), b = __longlong_as_double((long long)s2);
+                                const double t = a + b, c = (fabs(a) >= fabs(b)) ? ((a - t) + b) : ((b - t) + a);
+                                acc[j].sum = (uint64_t)__double_as_longlong(t);
+                                acc[j].err = (uint64_t)__double_as_longlong(__longlong_as_double((long long)acc[j].err) + __longlong_as_double((long long)e2) + c);
+                            } else {
+                                acc[j].sum += s2;
+                            }
+                            if (mn2 < acc[j].mn) acc[j].mn = mn2;
+                            if (mx2 > acc[j].mx) acc[j].mx = mx2;
+                        }
+                    }
+                    cur = c0;
+                    if (lane != 0) cnt = 0;
+                }
+            }
+            flush();
+        }
     }
 }
 

@@ -66,7 +66,7 @@ struct BucketCell {
     uint64_t mn, mx;   // order-preserving unsigned keys (ints: ^ sign flip; floats: f64_key); identities ~0 / 0
 };
 constexpr int BUCKET_THREADS = 128;
-constexpr uint32_t BUCKET_JOB_GROUPS = 64;   // consecutive 32-row groups per warp job (2048 rows)
+constexpr uint32_t BUCKET_JOB_GROUPS = 256;  // consecutive 32-row groups per warp job (8192 rows)
 struct BucketParams {
     const PackInfo* packs;      // [npacks] (bitset_off = the pack's bitset inside `bits`)
     const uint8_t*  bits;       // device-resident match bitsets of the scan

@@ -12,4 +12,4 @@ echo "$name rc=$? $(tail -1 gpurun_out/plain_$name.log)"
 ncu -i gpurun_out/prof_$name.ncu-rep --page details > gpurun_out/prof_${name}_details.txt 2>/dev/null
 ncu -i gpurun_out/prof_$name.ncu-rep --page raw --csv > gpurun_out/prof_${name}_raw.csv 2>/dev/null
 ncu -i gpurun_out/prof_$name.ncu-rep --page source --csv 2>/dev/null | gzip -9 > gpurun_out/prof_${name}_source.csv.gz
-rm -f gpurun_out/prof_$name.ncu-rep
+case " ${KEEP_REP:-} " in *" $name "*) ;; *) rm -f gpurun_out/prof_$name.ncu-rep ;; esac
