@@ -235,6 +235,97 @@ def oracle_query(packs, blobs, t_lo, t_hi, set_u64, postfix):
     return counts, bitsets, agg_i, agg_f
 
 
+def _random_tree(rng, nleaves):
+    """random binary AND/OR tree over leaves 0..nleaves-1 in postfix form (leaf order shuffled: left-deep, right-deep
+    and bushy shapes all occur, i.e. every stack depth from 2 to nleaves)"""
+    import knoxdb_b200 as kb
+    items = [[int(i)] for i in rng.permutation(nleaves)]
+    while len(items) > 1:
+        i = int(rng.integers(0, len(items) - 1))
+        if rng.random() < 0.35:   # right-deep step: keeps operands on the stack
+            i = len(items) - 2
+        a, b = items[i], items[i + 1]
+        items[i:i + 2] = [a + b + [kb.OP_AND if rng.random() < 0.5 else kb.OP_OR]]
+    return items[0]
+
+
+def test_predicate_trees_of_every_shape_over_every_container(ctx):
+    """filter.Match on arbitrary AND/OR trees (match_core.go:14-215): eight leaves over eight different containers
+    (bit-packed, dictionary, run-end, affine, constant, raw, raw float, ALP float), random tree shapes with stack
+    depths up to 8, ragged packs (1 row … several tiles), with and without aggregates."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(77)
+    nrows = [1, 31, 32, 33, 4097, 70_003, 8192, 140_000]
+    cols, blobs = [], []
+    T = [(1, ko.I64, kb.INT64), (2, ko.U64, kb.UINT64), (3, ko.I32, kb.INT32), (4, ko.U16, kb.UINT16), (5, ko.I8, kb.INT8),
+         (6, ko.U64, kb.UINT64), (7, ko.F64, kb.FLOAT64), (8, ko.F64, kb.FLOAT64)]
+    accts = kt.rnd_bits(rng, 300, 40)
+    for p, n in enumerate(nrows):
+        c = {1: (1_700_000_000 + np.cumsum(rng.integers(0, 3, n))).astype(np.int64),
+             2: rng.choice(accts, n).astype(np.uint64),
+             3: np.repeat(rng.integers(-1000, 1000, n // 7 + 1), 7)[:n].astype(np.int32),
+             4: (100 + 3 * np.arange(n)).astype(np.uint16) if 100 + 3 * n < 65535 else (np.arange(n) % 60000).astype(np.uint16),
+             5: np.full(n, -5, dtype=np.int8),
+             6: kt.rnd_bits(rng, n, 50),
+             7: (rng.integers(0, 2**40, n) / 100.0).astype(np.float64),
+             8: np.round(rng.uniform(0, 500, n), 2)}
+        e = {1: ko.store("best", ko.I64, c[1]), 2: ko.store("dict" if n >= 2 else "raw", ko.U64, c[2]),
+             3: ko.store("runend" if n >= 2 else "raw", ko.I32, c[3]),
+             4: ko.store("delta", ko.U16, base=100, delta=3, n=n) if 100 + 3 * n < 65535 else ko.store("bitpack", ko.U16, c[4]),
+             5: ko.store("const", ko.I8, val=-5, n=n), 6: ko.store("raw", ko.U64, c[6]), 7: ko.store("raw", ko.F64, c[7]),
+             8: ko.store("alp", ko.F64, c[8])}
+        for f, kot, kbt in T:
+            assert ctx.block_put(p, 1, f, kbt, e[f]) == n
+        cols.append(c); blobs.append(e)
+    big = cols[5]
+    setv = rng.choice(accts, 40, replace=False)
+    leaf_defs = [
+        (kb.Leaf(1, kb.INT64, kb.RANGE, int(big[1][1000]), int(big[1][40000])), lambda oc: oc.match(ko.RG, ko.scalar_u64(ko.I64, int(big[1][1000])), ko.scalar_u64(ko.I64, int(big[1][40000])))),
+        (kb.Leaf(2, kb.UINT64, kb.IN, values=setv), lambda oc: oc.match_set(setv)),
+        (kb.Leaf(3, kb.INT32, kb.GT, 100), lambda oc: oc.match(ko.GT, ko.scalar_u64(ko.I32, 100), 0)),
+        (kb.Leaf(4, kb.UINT16, kb.LE, 30000), lambda oc: oc.match(ko.LE, ko.scalar_u64(ko.U16, 30000), 0)),
+        (kb.Leaf(5, kb.INT8, kb.NE, 7), lambda oc: oc.match(ko.NE, ko.scalar_u64(ko.I8, 7), 0)),
+        (kb.Leaf(6, kb.UINT64, kb.LT, 1 << 49), lambda oc: oc.match(ko.LT, ko.scalar_u64(ko.U64, 1 << 49), 0)),
+        (kb.Leaf(7, kb.FLOAT64, kb.GE, 2**39 / 100.0), lambda oc: oc.match(ko.GE, ko.scalar_u64(ko.F64, 2**39 / 100.0), 0)),
+        (kb.Leaf(8, kb.FLOAT64, kb.LT, 250.0), lambda oc: oc.match(ko.LT, ko.scalar_u64(ko.F64, 250.0), 0)),
+    ]
+    kot_of = {f: kot for f, kot, _ in T}
+    leaf_bits = [[fn(ko.Container(kot_of[lf.field], blobs[p][lf.field])) for lf, fn in leaf_defs] for p in range(len(nrows))]
+    refs = [(p, 1) for p in range(len(nrows))]
+    depths = set()
+    for trial in range(24):
+        nl = int(rng.integers(2, 9))
+        pick = [int(i) for i in rng.permutation(8)[:nl]]
+        pf = _random_tree(rng, nl)
+        d = sp = 0
+        for op in pf:
+            sp += 1 if op < 0x80 else -1
+            d = max(d, sp)
+        depths.add(d)
+        prog = kb.Program(ctx, [leaf_defs[i][0] for i in pick], pf)
+        aggs = [(6, kb.UINT64), (7, kb.FLOAT64)] if trial % 2 else []
+        res = ctx.scan(prog, refs, nrows=nrows, want_bitsets=True, aggs=aggs)
+        st_u = st_f = None
+        for p, n in enumerate(nrows):
+            want = ko.tree_eval(pf, [leaf_bits[p][i] for i in pick], n)
+            assert (res["bitsets"][p] == want).all(), (trial, pf, p)
+            assert int(res["counts"][p]) == int(np.unpackbits(want).sum())
+            st_u = ko.reduce(ko.U64, cols[p][6], want, st_u)
+            st_f = ko.reduce(ko.F64, cols[p][7], want, st_f)
+        if aggs:
+            gu, gf = res["aggs"]
+            assert (gu.count, gu.sum_bits, gu.min_bits, gu.max_bits) == (st_u.count, st_u.sum_bits, st_u.min_bits, st_u.max_bits), (trial, pf)
+            if st_f.valid:
+                want_sum = float(np.uint64(st_f.sum_bits).view(np.float64))
+                assert abs(gf.value("sum", kb.FLOAT64) - want_sum) <= 1e-12 * abs(want_sum)
+                assert (gf.min_bits, gf.max_bits) == (st_f.min_bits, st_f.max_bits)
+        prog.close()
+    assert max(depths) >= 5 and min(depths) == 2, depths
+    for p in range(len(nrows)):
+        for f, _, _ in T:
+            ctx.block_drop(p, 1, f)
+
+
 @pytest.fixture
 def agg_stage(request, monkeypatch):
     """KX_AGG_STAGE: how the fused reduce reads value columns (on demand / staged through the ring / by selectivity)"""
