@@ -40,7 +40,7 @@ enum {
     KX_INT64 = 1, KX_INT32 = 2, KX_INT16 = 3, KX_INT8 = 4,
     KX_UINT64 = 5, KX_UINT32 = 6, KX_UINT16 = 7, KX_UINT8 = 8,
     KX_FLOAT64 = 9, KX_FLOAT32 = 10,
-    KX_BYTES = 12,   /* byte strings: pruning (bloom probes, bloom build) only */
+    KX_BYTES = 12,   /* byte strings (BlockBytes): string containers 16..19, row-level predicates, bloom probes / build */
 };
 
 /* internal/types/mode.go:14-23 (FilterMode) */
@@ -78,7 +78,8 @@ void  kx_host_free(kx_ctx* ctx, void* p);
  * byte of block.Encode (internal/block/encode.go:194-226; outer s2/lz4/zstd is undone on the
  * host).  Replaces Package.LoadFromDisk + block.Decode → encode.LoadInt/LoadFloat
  * (internal/pack/storage.go:128-190, internal/encode/int.go:109-115) as the source of
- * column vectors for the scan.  Copies `len` bytes; returns the block's row count. */
+ * column vectors for the scan.  Copies `len` bytes; returns the block's row count.
+ * KX_BYTES blocks: the string containers of internal/encode/string_{const,fixed,compact,dict}.go (ids 16..19). */
 int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, uint8_t block_type,
                  const void* enc, size_t len, uint32_t* nrows_out);
 int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field);
@@ -89,7 +90,11 @@ int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint
  * (match_num.go:327-817): field, type, mode, operand(s).  a/b carry the operand as the
  * 64-bit pattern of the type (sign-extended ints, IEEE bits for floats); RANGE uses [a,b].
  * IN/NIN pass the set flattened to u64 values (xroar.Bitmap contents, `uint64(v)` of each
- * member, internal/encode/int_raw.go:339-357); order and duplicates do not matter. */
+ * member, internal/encode/int_raw.go:339-357); order and duplicates do not matter.
+ * Byte-string leaves (block_type KX_BYTES; types.StringMatcher, internal/encode/string_match.go:13-188: the seven
+ * scalar modes, bytes.Equal / bytes.Compare row by row): nset = 1, `set` points to the operand BYTES, a = length of
+ * the operand, and for RANGE b = length of the upper bound that follows it.  A KX_BYTES leaf with nset = 0 carries
+ * no operand and can only be used for pruning (bloom probes with caller-supplied hashes). */
 typedef struct kx_leaf {
     uint16_t field;
     uint8_t  block_type;

@@ -71,6 +71,7 @@ struct Slab { uint8_t* base; size_t cap, used, live; };
 struct StoredBlock {
     ColView view{};
     std::vector<uint64_t> dict;     // host copy of dictionary values (leaf translation)
+    std::vector<uint8_t> cstr;      // host copy of a constant string block's value (leaf translation)
     std::vector<std::pair<int, size_t>> allocs;   // (slab index, bytes)
     size_t enc_len = 0;
 };
@@ -104,6 +105,8 @@ struct kx_prog {
     uint32_t pre_off[MAX_LEAVES] = {0};
     uint8_t pre_log2[MAX_LEAVES] = {0};
     const uint32_t* dev_pres = nullptr;
+    std::vector<uint8_t> strs;           // operands of the byte-string leaves
+    uint8_t* dev_strs = nullptr;
     bool prune_only = false;             // has a byte-string leaf: usable with kx_prune* only
 };
 
@@ -226,6 +229,27 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
     return KX_OK;
 }
 
+// byte-string block: byte buffer verbatim + flat u32 index array (kx_types.h STR_*)
+int upload_string_block(kx_ctx* ctx, const StrLayout& lay, StoredBlock& sb) {
+    sb.view = lay.view;
+    auto put = [&](const void* src, size_t len, const uint8_t** devp) -> int {
+        uint8_t* d = nullptr; int si = 0;
+        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &si);
+        if (rc) return rc;
+        sb.allocs.push_back({si, len + STREAM_PAD});
+        ctx->store_dev_bytes += round_up(len + STREAM_PAD, 256);
+        if (len) CK(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ctx->stream));
+        *devp = d;
+        return KX_OK;
+    };
+    int rc;
+    if ((rc = put(lay.bytes, lay.nbytes, &sb.view.data))) return rc;
+    if (!lay.idx.empty() && (rc = put(lay.idx.data(), lay.idx.size() * 4, &sb.view.aux))) return rc;
+    if (lay.view.is_raw == STR_CONST) sb.cstr.assign(lay.bytes, lay.bytes + lay.nbytes);
+    CK(cudaStreamSynchronize(ctx->stream));   // lay.idx dies with `lay`
+    return KX_OK;
+}
+
 void free_block(kx_ctx* ctx, StoredBlock& sb) {
     for (auto& a : sb.allocs) { slab_release(ctx, a.first, a.second); ctx->store_dev_bytes -= round_up(a.second, 256); }
     sb.allocs.clear();
@@ -237,6 +261,7 @@ struct ScanJob {
     std::vector<uint32_t> nrows;               // [npacks]
     std::vector<ColView> leaf_views;           // [npacks][nleaves]
     std::vector<const uint64_t*> leaf_dicts;   // [npacks][nleaves] host dict copies (or null)
+    std::vector<const std::vector<uint8_t>*> leaf_cstr;   // [npacks][nleaves] value of a constant string block (or null)
     std::vector<ColView> agg_views;            // [npacks][naggs]
 };
 
@@ -295,6 +320,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::vector<size_t> rjob_leaf;     // index into pl of each run-fill job
     std::vector<AlpFixJob> ajobs;
     std::vector<size_t> ajob_leaf;
+    std::vector<StrJob> sjobs;          // byte-string leaves: predicate per row in a pre-pass (strmatch_kernel)
+    std::vector<size_t> sjob_leaf;
+    uint32_t max_str_rows = 0;
     uint32_t max_patches = 0;
     bool any_fix = false;
     size_t leafbits_bytes = 0;
@@ -312,6 +340,29 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             const ColView& v = job.leaf_views[size_t(p) * nleaves + l];
             if (v.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
             PackLeaf& o = pl[size_t(p) * nleaves + l];
+            if (prog->leaves[size_t(l)].type == KX_BYTES) {
+                // byte-string leaf (StringMatcher.Match*, internal/encode/string_*.go): constant blocks are decided here
+                // (string_const.go:113-153), every other layout by strmatch_kernel into a 1-bit column the scan streams
+                const LeafSpec& ls = prog->leaves[size_t(l)];
+                if (v.kind != CK_STR || !ls.has_str) return fail(ctx, KX_EINVAL, "byte-string leaf over a non-string block (or without operand bytes)");
+                o = PackLeaf{};
+                only32 = false;
+                if (v.n == 0 || v.is_raw == STR_CONST) {
+                    const std::vector<uint8_t>* cv = job.leaf_cstr.empty() ? nullptr : job.leaf_cstr[size_t(p) * nleaves + l];
+                    static const std::vector<uint8_t> empty;
+                    if (!cv) cv = &empty;
+                    const bool all = v.n != 0 && string_pred(ls.mode, cv->data(), cv->size(), ls.sa.data(), ls.sa.size(), ls.sb.data(), ls.sb.size());
+                    o.mode = all ? LM_ALL : LM_NONE;
+                } else {
+                    sjobs.push_back(StrJob{v, leafbits_bytes, ls.sa_off, uint32_t(ls.sa.size()), ls.sb_off, uint32_t(ls.sb.size()), uint32_t(ls.mode), 0});
+                    sjob_leaf.push_back(size_t(p) * nleaves + l);
+                    leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
+                    max_str_rows = std::max(max_str_rows, v.n);
+                    o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
+                    bits = std::max(bits, 1u);
+                }
+                continue;
+            }
             compile_leaf(v, job.leaf_dicts[size_t(p) * nleaves + l], prog->leaves[size_t(l)], uint32_t(size_t(p) * nleaves + l), o);
             if (o.mode == LM_CODESET) {   // dictionary-set translation runs on the device, one job per (pack, leaf)
                 const LeafSpec& ls = prog->leaves[size_t(l)];
@@ -462,11 +513,13 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     size_t off_cjobs = off_tiles + round_up(sz_tiles, 256);
     size_t off_rjobs = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
     size_t off_ajobs = off_rjobs + round_up(sizeof(RunFillJob) * rjobs.size(), 256);
-    size_t desc_bytes = off_ajobs + round_up(sizeof(AlpFixJob) * ajobs.size(), 256);
+    size_t off_sjobs = off_ajobs + round_up(sizeof(AlpFixJob) * ajobs.size(), 256);
+    size_t desc_bytes = off_sjobs + round_up(sizeof(StrJob) * sjobs.size(), 256);
     if (leafbits_bytes) {
         CK(ctx->d_leafbits.reserve(leafbits_bytes));
         for (size_t i = 0; i < rjobs.size(); ++i) pl[rjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + rjobs[i].out_off;
         for (size_t i = 0; i < ajobs.size(); ++i) pl[ajob_leaf[i]].fix = static_cast<const uint8_t*>(ctx->d_leafbits.p) + ajobs[i].out_off;
+        for (size_t i = 0; i < sjobs.size(); ++i) pl[sjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + sjobs[i].out_off;
     }
 
     CK(ctx->h_desc.reserve(desc_bytes));
@@ -493,6 +546,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (!cjobs.empty()) std::memcpy(hd + off_cjobs, cjobs.data(), sizeof(CodesetJob) * cjobs.size());
     if (!rjobs.empty()) std::memcpy(hd + off_rjobs, rjobs.data(), sizeof(RunFillJob) * rjobs.size());
     if (!ajobs.empty()) std::memcpy(hd + off_ajobs, ajobs.data(), sizeof(AlpFixJob) * ajobs.size());
+    if (!sjobs.empty()) std::memcpy(hd + off_sjobs, sjobs.data(), sizeof(StrJob) * sjobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
     int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * geo.ctas));
@@ -558,6 +612,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (ntiles && !ajobs.empty()) {
         CK(launch_alpfix(reinterpret_cast<const AlpFixJob*>(dd + off_ajobs), uint32_t(ajobs.size()), max_patches,
                          static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
+        ctx->last_launches++;
+    }
+    if (ntiles && !sjobs.empty()) {
+        CK(launch_strmatch(reinterpret_cast<const StrJob*>(dd + off_sjobs), uint32_t(sjobs.size()), max_str_rows, prog->dev_strs,
+                           static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
         ctx->last_launches++;
     }
     if (ntiles && !rjobs.empty()) {
@@ -684,11 +743,26 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
         const kx_leaf& in = leaves[l];
         LeafSpec s; s.field = in.field; s.type = in.block_type; s.mode = in.mode; s.a = in.a; s.b = in.b;
         if (s.type == KX_BYTES) {
-            // byte-string columns take part in pruning only (bloom probes with caller-supplied hashes)
-            if (s.mode != KX_MODE_EQ && s.mode != KX_MODE_IN && s.mode != KX_MODE_NE && s.mode != KX_MODE_NIN)
-                return fail(ctx, KX_EUNSUPPORTED, "leaf: byte-string columns support EQ/NE/IN/NIN (pruning) only");
-            p->prune_only = true;
             s.set_off = uint32_t(p->sets.size()); p->set_off[l] = s.set_off;
+            if (in.nset == 1 && in.mode != KX_MODE_IN && in.mode != KX_MODE_NIN) {
+                // row-level string predicate: operand bytes at `set`, a = length of the operand, b = length of the
+                // upper bound that follows it (RANGE); StringMatcher has the seven scalar modes (types/strings.go)
+                if (s.mode < KX_MODE_EQ || s.mode > KX_MODE_RANGE) return fail(ctx, KX_EINVAL, "leaf: unsupported filter mode");
+                if ((in.a || in.b) && !in.set) return fail(ctx, KX_EINVAL, "leaf: operand bytes missing");
+                if (in.a > (1u << 24) || in.b > (1u << 24)) return fail(ctx, KX_EINVAL, "leaf: operand too long");
+                const uint8_t* ob = reinterpret_cast<const uint8_t*>(in.set);
+                s.sa.assign(ob, ob + in.a);
+                if (s.mode == KX_MODE_RANGE) s.sb.assign(ob + in.a, ob + in.a + in.b);
+                s.sa_off = uint32_t(p->strs.size()); p->strs.insert(p->strs.end(), s.sa.begin(), s.sa.end());
+                s.sb_off = uint32_t(p->strs.size()); p->strs.insert(p->strs.end(), s.sb.begin(), s.sb.end());
+                s.a = s.b = 0;
+                s.has_str = true;
+            } else {
+                // no operand: the leaf takes part in pruning only (bloom probes with caller-supplied hashes)
+                if (s.mode != KX_MODE_EQ && s.mode != KX_MODE_IN && s.mode != KX_MODE_NE && s.mode != KX_MODE_NIN)
+                    return fail(ctx, KX_EUNSUPPORTED, "leaf: byte-string leaves without operand bytes support EQ/NE/IN/NIN (pruning) only");
+                p->prune_only = true;
+            }
             p->leaves.push_back(std::move(s));
             continue;
         }
@@ -733,6 +807,11 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
             CK(cudaMemcpyAsync(dt + tab_bytes, p->pres.data(), pre_bytes, cudaMemcpyHostToDevice, ctx->stream));
             p->dev_pres = reinterpret_cast<const uint32_t*>(dt + tab_bytes);
         }
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    if (!p->strs.empty()) {
+        CK(cudaMalloc(&p->dev_strs, p->strs.size() + 16));
+        CK(cudaMemcpyAsync(p->dev_strs, p->strs.data(), p->strs.size(), cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
     }
     *out = p.release();
@@ -800,14 +879,15 @@ int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, u
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!enc || !len) return fail(ctx, KX_EINVAL, "empty block");
     CK(cudaSetDevice(ctx->device));
-    BlockLayout lay; std::string err;
-    int rc = normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
+    BlockLayout lay; StrLayout slay; std::string err;
+    int rc = block_type == KX_BYTES ? normalize_string_block(static_cast<const uint8_t*>(enc), len, slay, err)
+                                    : normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
     if (rc) return fail(ctx, rc, "kx_block_put: " + err);
     BlockKey key{pack, version, field};
     auto it = ctx->store.find(key);
     if (it != ctx->store.end()) { ctx->store_enc_bytes -= it->second.enc_len; free_block(ctx, it->second); ctx->store.erase(it); }
     StoredBlock sb;
-    rc = upload_block(ctx, lay, sb);
+    rc = block_type == KX_BYTES ? upload_string_block(ctx, slay, sb) : upload_block(ctx, lay, sb);
     if (rc) { free_block(ctx, sb); return rc; }
     // the caller's buffer may be reused after return (cgo rule): finish the copy
     CK(cudaStreamSynchronize(ctx->stream));
@@ -850,6 +930,7 @@ int kx_prog_compile(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8
 void kx_prog_free(kx_prog* prog) {
     if (!prog) return;
     if (prog->dev_sets) { cudaSetDevice(prog->ctx->device); cudaFree(prog->dev_sets); }
+    if (prog->dev_strs) { cudaSetDevice(prog->ctx->device); cudaFree(prog->dev_strs); }
     delete prog;
 }
 
@@ -875,6 +956,7 @@ static int build_scan_job(kx_ctx* ctx, const kx_prog* prog, const kx_packref* pa
     job.nrows.resize(size_t(npacks));
     job.leaf_views.resize(size_t(npacks) * nleaves);
     job.leaf_dicts.resize(size_t(npacks) * nleaves);
+    job.leaf_cstr.assign(size_t(npacks) * nleaves, nullptr);
     job.agg_views.resize(size_t(npacks) * size_t(naggs));
     for (int p = 0; p < npacks; ++p) {
         for (int l = 0; l < nleaves; ++l) {
@@ -883,6 +965,7 @@ static int build_scan_job(kx_ctx* ctx, const kx_prog* prog, const kx_packref* pa
             if (it->second.view.type != prog->leaves[size_t(l)].type) return fail(ctx, KX_EINVAL, "leaf / block type mismatch");
             job.leaf_views[size_t(p) * nleaves + l] = it->second.view;
             job.leaf_dicts[size_t(p) * nleaves + l] = it->second.dict.empty() ? nullptr : it->second.dict.data();
+            if (it->second.view.kind == CK_STR && it->second.view.is_raw == STR_CONST) job.leaf_cstr[size_t(p) * nleaves + l] = &it->second.cstr;
             if (l == 0) job.nrows[size_t(p)] = it->second.view.n;
         }
         for (int j = 0; j < naggs; ++j) {

@@ -791,6 +791,90 @@ bool build_set_table(const std::vector<uint64_t>& set, std::vector<uint64_t>& sl
     return false;
 }
 
+// ---- byte-string containers
+static bool load_u32_child(const uint8_t*& p, const uint8_t* end, std::vector<uint32_t>& out, size_t at, std::string& err) {
+    std::unique_ptr<Container> c;
+    long used = parse_container(6 /* uint32 */, p, size_t(end - p), c, err);
+    if (used <= 0) { if (err.empty()) err = "bad nested container of a string block"; return false; }
+    std::vector<uint64_t> v;
+    if (!decode_container(*c, v, err)) return false;
+    if (out.size() < at + v.size()) out.resize(at + v.size());
+    for (size_t i = 0; i < v.size(); ++i) out[at + i] = uint32_t(v[i]);
+    p += used;
+    return true;
+}
+
+int normalize_string_block(const uint8_t* enc, size_t len, StrLayout& out, std::string& err) {
+    if (len < 2) { err = "string block too short"; return -6; }
+    const uint8_t *p = enc + 1, *end = enc + len;
+    ColView& v = out.view;
+    v = ColView{};
+    v.kind = CK_STR; v.type = 12;
+    uint64_t x = 0;
+    auto uv = [&](uint64_t& dst) { int k = get_uvarint(p, size_t(end - p), &dst); if (!k) { err = "truncated string block"; return false; } p += k; return true; };
+    switch (enc[0]) {
+    case T_STRCONST:   // string_const.go:49-69: uv(N) uv(len) val
+        if (!uv(x)) return -6;
+        v.n = uint32_t(x);
+        if (!uv(x) || size_t(end - p) < x) { err = "truncated string block"; return -6; }
+        v.is_raw = STR_CONST; v.delta = x; out.bytes = p; out.nbytes = size_t(x);
+        break;
+    case T_STRFIXED:   // string_fixed.go:59-80: uv(N) uv(sz) N*sz bytes
+        if (!uv(x)) return -6;
+        v.n = uint32_t(x);
+        if (!uv(x) || size_t(end - p) < x * v.n) { err = "truncated string block"; return -6; }
+        v.is_raw = STR_FIXED; v.delta = x; out.bytes = p; out.nbytes = size_t(x) * v.n;
+        break;
+    case T_STRCOMPACT: {   // string_compact.go:64-96: <Ofs> <Len> uv(len(buf)) buf
+        if (!load_u32_child(p, end, out.idx, 0, err)) return -6;
+        const size_t n = out.idx.size();
+        if (!load_u32_child(p, end, out.idx, n, err) || out.idx.size() != 2 * n) { if (err.empty()) err = "string block: offsets / lengths differ in size"; return -6; }
+        if (!uv(x) || size_t(end - p) < x) { err = "truncated string block"; return -6; }
+        v.n = uint32_t(n); v.is_raw = STR_COMPACT; out.bytes = p; out.nbytes = size_t(x);
+        for (size_t i = 0; i < n; ++i)
+            if (uint64_t(out.idx[i]) + out.idx[n + i] > x) { err = "string block: row outside the buffer"; return -6; }
+        break;
+    }
+    case T_STRDICT: {   // string_dict.go:70-109: <Ofs> <Len> <Code> uv(len(dict)) dict
+        std::vector<uint32_t> ofs, ln, code;
+        if (!load_u32_child(p, end, ofs, 0, err) || !load_u32_child(p, end, ln, 0, err) || !load_u32_child(p, end, code, 0, err)) return -6;
+        if (ofs.size() != ln.size()) { err = "string block: offsets / lengths differ in size"; return -6; }
+        if (!uv(x) || size_t(end - p) < x) { err = "truncated string block"; return -6; }
+        const size_t n = code.size(), m = ofs.size();
+        for (size_t i = 0; i < n; ++i) if (code[i] >= m) { err = "string block: code outside the dictionary"; return -6; }
+        for (size_t k = 0; k < m; ++k) if (uint64_t(ofs[k]) + ln[k] > x) { err = "string block: entry outside the dictionary"; return -6; }
+        out.idx.reserve(n + 2 * m);
+        out.idx = code; out.idx.insert(out.idx.end(), ofs.begin(), ofs.end()); out.idx.insert(out.idx.end(), ln.begin(), ln.end());
+        v.n = uint32_t(n); v.naux = uint32_t(m); v.is_raw = STR_DICT; out.bytes = p; out.nbytes = size_t(x);
+        break;
+    }
+    default:
+        err = "unknown string container id " + std::to_string(int(enc[0]));
+        return -6;
+    }
+    v.base = out.nbytes;
+    return 0;
+}
+
+static int bytes_compare(const uint8_t* a, size_t al, const uint8_t* b, size_t bl) {
+    const size_t m = std::min(al, bl);
+    const int c = m ? std::memcmp(a, b, m) : 0;
+    if (c) return c < 0 ? -1 : 1;
+    return al < bl ? -1 : (al > bl ? 1 : 0);
+}
+bool string_pred(int mode, const uint8_t* v, size_t vl, const uint8_t* a, size_t al, const uint8_t* b, size_t bl) {
+    switch (mode) {
+    case M_EQ: return vl == al && (al == 0 || !std::memcmp(v, a, al));
+    case M_NE: return !(vl == al && (al == 0 || !std::memcmp(v, a, al)));
+    case M_LT: return bytes_compare(v, vl, a, al) < 0;
+    case M_LE: return bytes_compare(v, vl, a, al) <= 0;
+    case M_GT: return bytes_compare(v, vl, a, al) > 0;
+    case M_GE: return bytes_compare(v, vl, a, al) >= 0;
+    case M_RANGE: return bytes_compare(v, vl, a, al) >= 0 && bytes_compare(v, vl, b, bl) <= 0;
+    }
+    return false;
+}
+
 void build_set_prefilter(const std::vector<uint64_t>& set, std::vector<uint32_t>& words, int& log2bits) {
     int lg = 10;
     while (lg < 17 && (size_t(1) << lg) < set.size() * 256) ++lg;

@@ -13,7 +13,8 @@
 namespace kx {
 
 // container ids, internal/encode/container.go:20-55
-enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATALP = 13, T_FLOATRAW = 15 };
+enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATALP = 13, T_FLOATRAW = 15,
+             T_STRCONST = 16, T_STRFIXED = 17, T_STRCOMPACT = 18, T_STRDICT = 19 };
 // types.FilterMode, internal/types/mode.go:14-23
 enum : int { M_EQ = 1, M_NE = 2, M_GT = 3, M_GE = 4, M_LT = 5, M_LE = 6, M_IN = 7, M_NIN = 8, M_RANGE = 9 };
 
@@ -52,13 +53,29 @@ int64_t alp_encode_below(double v, int e, int f);
 double  alp_decode(int64_t enc, int e, int f);
 int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, std::string& err);
 
+// Byte-string block (BlockBytes; containers 16..19, internal/encode/string_{const,fixed,compact,dict}.go) normalised for
+// the device: the byte buffer stays verbatim, the nested uint32 containers (offsets, lengths, codes) are decoded once
+// into one flat u32 index array (layout: kx_types.h STR_*).
+struct StrLayout {
+    ColView view{};                  // kind = CK_STR; pointers filled after upload
+    const uint8_t* bytes = nullptr;  // inside the caller's buffer
+    size_t nbytes = 0;
+    std::vector<uint32_t> idx;
+};
+int normalize_string_block(const uint8_t* enc, size_t len, StrLayout& out, std::string& err);
+// bytes.Compare / the seven string predicates of string_match.go on one value (host side: constant blocks)
+bool string_pred(int mode, const uint8_t* v, size_t vl, const uint8_t* a, size_t al, const uint8_t* b, size_t bl);
+
 struct LeafSpec {
     uint16_t field = 0;
     uint8_t type = 0, mode = 0;
     uint64_t a = 0, b = 0;
+    std::vector<uint8_t> sa, sb; // byte-string operands (block type BYTES)
+    uint32_t sa_off = 0, sb_off = 0;   // their offsets in the program's device byte pool
     std::vector<uint64_t> set;   // sorted unique
     uint32_t set_off = 0;        // offset into the program's concatenated device set array
     bool has_table = false;      // a bucketised hash table of the set exists on the device (LM_HASHSET)
+    bool has_str = false;        // byte-string leaf with operand bytes (row-level predicate on CK_STR blocks)
 };
 
 // Bucketised hash table of an IN/NIN set for the device lookup (leaf_hashset in kx_scan.cu):

@@ -50,6 +50,16 @@ struct RunFillJob {
     uint32_t is_set, pad;
 };
 
+// one byte-string leaf of strmatch_kernel: bit i of the leaf bitset at out_base + out_off = pred(row i)
+struct StrJob {
+    ColView view;          // CK_STR block
+    uint64_t out_off;      // byte offset of the leaf bitset
+    uint32_t a_off, a_len; // operand(s) inside the program's byte-string pool
+    uint32_t b_off, b_len;
+    uint32_t mode, pad;    // types.FilterMode (EQ, NE, GT, GE, LT, LE, RANGE)
+};
+cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_rows, const uint8_t* pool, uint8_t* out_base, cudaStream_t stream);
+
 // one ALP leaf of alpfix_kernel: bit pos[k] of the correction stream = pred(patch value k) (invert: !pred)
 struct AlpFixJob {
     const uint8_t* blob;   // patch blob of the block (positions | values | bitmap)

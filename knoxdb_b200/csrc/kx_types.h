@@ -29,6 +29,15 @@ enum ColKind : uint8_t {
                     // value = double(field + base) * F10[factor] * IF10[exponent]; delta = exponent << 8 | factor;
                     // aux = patch blob [positions u32 x naux | values u64 x naux | patch bitmap u32 x ceil(n/32)],
                     // extra = the encoded replacement value stored at patch positions
+    CK_STR = 7,     // byte strings (BlockBytes): data = byte buffer, aux = u32 index array, is_raw = STR_* layout,
+                    // delta = row size (STR_FIXED / STR_CONST), naux = dictionary entries (STR_DICT), base = bytes in data
+};
+// layouts of a CK_STR block: row i = data[ofs .. ofs + len)
+enum : uint8_t {
+    STR_CONST = 0,     // every row = data[0 .. delta)                                   (string_const.go)
+    STR_FIXED = 1,     // ofs = i * delta, len = delta                                    (string_fixed.go)
+    STR_COMPACT = 2,   // ofs = aux[i], len = aux[n + i]                                  (string_compact.go)
+    STR_DICT = 3,      // c = aux[i]; ofs = aux[n + c], len = aux[n + naux + c]           (string_dict.go)
 };
 
 struct ColView {

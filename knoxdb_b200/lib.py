@@ -148,6 +148,12 @@ class Leaf:
         self.field, self.block_type, self.mode = field, block_type, mode
         self.a, self.b = (0, 0) if block_type == BYTES else (pattern(block_type, a), pattern(block_type, b))
         self.set = None
+        self.bytes = None
+        if block_type == BYTES and isinstance(a, (bytes, bytearray)):
+            # row-level string predicate: operand bytes (RANGE: lower bound followed by the upper bound), lengths in a / b
+            b = bytes(b) if isinstance(b, (bytes, bytearray)) else b""
+            self.a, self.b = len(a), len(b) if mode == RANGE else 0
+            self.bytes = np.frombuffer(bytes(a) + (b if mode == RANGE else b"") + b"\0" * 8, dtype=np.uint8).copy()
         if values is not None:
             arr = np.asarray(values)
             if arr.dtype.kind == "i":
@@ -169,6 +175,9 @@ class Program:
             if lf.set is not None and lf.set.size:
                 arr[i].nset = lf.set.size
                 arr[i].set = lf.set.ctypes.data_as(C.POINTER(C.c_uint64))
+            if getattr(lf, "bytes", None) is not None:
+                arr[i].nset = 1
+                arr[i].set = C.cast(lf.bytes.ctypes.data, C.POINTER(C.c_uint64))
         h = C.c_void_p()
         ctx._check(lib().kx_prog_compile(ctx.h, arr, len(self.leaves), _ptr(self.postfix), self.postfix.size, C.byref(h)))
         self.h = h

@@ -50,6 +50,7 @@ enum {
 enum {
     KO_TCONST = 1, KO_TDELTA = 2, KO_TRUNEND = 3, KO_TBITPACK = 4, KO_TDICT = 5,
     KO_TS8B = 6, KO_TRAW = 7, KO_TFLOATRAW = 15,
+    KO_TSTRCONST = 16, KO_TSTRFIXED = 17, KO_TSTRCOMPACT = 18, KO_TSTRDICT = 19,   /* container.go:43-46 */
 };
 
 int ko_type_size(int type);
@@ -165,6 +166,15 @@ void ko_reduce(int type, const uint64_t* vals, size_t n, const uint8_t* bits, ko
 void ko_bucket_reduce(int type, const uint64_t* vals, int ts_type, const uint64_t* ts, size_t n, const uint8_t* bits,
                       const uint64_t* edges, int nbuckets, ko_agg* states);
 int ko_window_edges(int64_t from, int64_t to, int64_t step, int64_t* out, int cap);
+
+/* ---- byte-string containers: internal/encode/string_{const,fixed,compact,dict,match}.go (ko_string.c) ---- */
+typedef struct ko_str ko_str;
+size_t  ko_store_str(int kind, const uint8_t* bytes, const uint32_t* offs, size_t n, uint8_t* dst);
+long    ko_str_load(const uint8_t* enc, size_t len, ko_str** out);
+void    ko_str_free(ko_str* s);
+size_t  ko_str_len(const ko_str* s);
+const uint8_t* ko_str_get(const ko_str* s, size_t i, size_t* len);
+void    ko_str_match(const ko_str* s, int op, const uint8_t* a, size_t al, const uint8_t* b, size_t bl, uint8_t* bits);
 
 /* ---- filter tree: internal/operator/filter/match_core.go:14-215 ----
  * postfix program over leaf bitsets: byte < 0x80 → push leaf id, 0xFE = AND, 0xFF = OR

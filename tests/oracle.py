@@ -95,6 +95,12 @@ def lib():
             "ko_bucket_reduce": (None, [C.c_int, vp, C.c_int, vp, C.c_size_t, vp, vp, C.c_int, vp]),
             "ko_window_edges": (C.c_int, [C.c_int64, C.c_int64, C.c_int64, vp, C.c_int]),
             "ko_tree_eval": (C.c_int, [vp, C.c_int, vp, C.c_int, C.c_size_t, vp]),
+            "ko_store_str": (C.c_size_t, [C.c_int, vp, vp, C.c_size_t, vp]),
+            "ko_str_load": (C.c_long, [vp, C.c_size_t, C.POINTER(vp)]),
+            "ko_str_free": (None, [vp]),
+            "ko_str_len": (C.c_size_t, [vp]),
+            "ko_str_get": (vp, [vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+            "ko_str_match": (None, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp]),
             "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
             "ko_baseline_bitpack_scan": (C.c_int64, [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_int]),
         }
@@ -251,6 +257,50 @@ def window_edges(t_from, t_to, step):
     out = np.zeros(int((t_to - t_from) // step) + 4, dtype=np.int64)
     n = lib().ko_window_edges(int(t_from), int(t_to), int(step), _p(out), out.size)
     return out[:n].copy()
+
+
+vp_t = C.c_void_p
+STR_CONST, STR_FIXED, STR_COMPACT, STR_DICT = 16, 17, 18, 19
+
+
+def store_str(kind, rows):
+    """Encode a list of byte strings with the named string container (ids 16..19) → bytes, or None when the rows do
+    not fit the scheme (constant: all rows equal; fixed: equal lengths)"""
+    flat = np.frombuffer(b"".join(rows), dtype=np.uint8) if rows else np.zeros(0, dtype=np.uint8)
+    offs = np.zeros(len(rows) + 1, dtype=np.uint32)
+    offs[1:] = np.cumsum([len(r) for r in rows])
+    flat = np.ascontiguousarray(np.concatenate([flat, np.zeros(8, dtype=np.uint8)]))
+    buf = np.zeros(flat.size + 3 * lib().ko_store_bound(U32, len(rows) + 1) + 64, dtype=np.uint8)
+    n = lib().ko_store_str(kind, _p(flat), _p(offs), len(rows), _p(buf))
+    return buf[:n].tobytes() if n else None
+
+
+class StrContainer:
+    """ko_str_load + Get / Match<Op> of the string containers"""
+
+    def __init__(self, blob):
+        self.blob = np.frombuffer(blob, dtype=np.uint8).copy()
+        h = vp_t()
+        used = lib().ko_str_load(_p(self.blob), self.blob.size, C.byref(h))
+        assert used == self.blob.size, (used, self.blob.size)
+        self.h, self.n = h, lib().ko_str_len(h)
+
+    def get(self, i):
+        ln = C.c_size_t()
+        p = lib().ko_str_get(self.h, i, C.byref(ln))
+        return C.string_at(p, ln.value)
+
+    def match(self, op, a, b=b""):
+        bits = np.zeros(nbytes(self.n) + 8, dtype=np.uint8)
+        aa, bb = np.frombuffer(a + b"\0", dtype=np.uint8), np.frombuffer(b + b"\0", dtype=np.uint8)
+        lib().ko_str_match(self.h, op, _p(aa), len(a), _p(bb), len(b), _p(bits))
+        return bits[:nbytes(self.n)].copy()
+
+    def __del__(self):
+        try:
+            lib().ko_str_free(self.h)
+        except Exception:
+            pass
 
 
 def tree_eval(postfix, leaf_bits, n):

@@ -500,6 +500,80 @@ def test_time_bucketed_reduce(ctx, ordered):
             ctx.block_drop(p, 1, f)
 
 
+def _string_rows(rng, n, shape):
+    if shape == "fixed20":      # config 4's address column: random 20-byte strings
+        return [bytes(r) for r in rng.integers(0, 256, (n, 20), dtype=np.uint8)]
+    if shape == "dups":         # few distinct values of different lengths (→ dictionary)
+        vocab = [b"", b"a", b"ab", b"abc", b"abd", b"tz1VSUr8wwNhLAzempoch5d6hLRiTh8Cjcjb", b"zzzz", bytes(range(256))]
+        return [vocab[i] for i in rng.integers(0, len(vocab), n)]
+    if shape == "ragged":       # variable lengths 0..40, small alphabet (many shared prefixes)
+        return [bytes(rng.integers(97, 100, int(k), dtype=np.uint8)) for k in rng.integers(0, 41, n)]
+    return [b"same value"] * n  # constant
+
+
+@pytest.mark.parametrize("shape", ["fixed20", "dups", "ragged", "const"])
+def test_string_blocks_match_row_by_row(ctx, shape):
+    """types.StringMatcher on the string containers (internal/encode/string_{const,fixed,compact,dict}.go, matchers
+    string_match.go:13-188): the seven modes, operands that are members, non-members, prefixes and the empty string,
+    every container that can hold the rows, sizes around the 32-row word and tile boundaries; then a string leaf
+    ANDed with an integer leaf (config 4's `height BETWEEN … AND address = X` at row level)."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(11)
+    for n in (1, 31, 33, 1000, 70_003):
+        rows = _string_rows(rng, n, shape)
+        kinds = [k for k in (ko.STR_CONST, ko.STR_FIXED, ko.STR_COMPACT, ko.STR_DICT) if ko.store_str(k, rows) is not None]
+        if n > 5000:
+            kinds = [k for k in kinds if k != ko.STR_DICT or shape in ("dups", "const")]   # the oracle's dictionary build is quadratic
+        assert ko.STR_COMPACT in kinds
+        operands = [rows[0], rows[n // 2], b"", b"ab", rows[-1] + b"\x00", b"\xff" * 3]
+        for kind in kinds:
+            blob = ko.store_str(kind, rows)
+            oc = ko.StrContainer(blob)
+            assert oc.n == n and oc.get(n // 2) == rows[n // 2]
+            assert ctx.block_put(300, 1, 9, kb.BYTES, blob) == n
+            for a in operands:
+                for mode, kom in ((kb.EQ, ko.EQ), (kb.NE, ko.NE), (kb.LT, ko.LT), (kb.LE, ko.LE), (kb.GT, ko.GT), (kb.GE, ko.GE)):
+                    prog = kb.Program(ctx, [kb.Leaf(9, kb.BYTES, mode, a)])
+                    res = ctx.scan(prog, [(300, 1)], nrows=[n], want_bitsets=True)
+                    want = oc.match(kom, a)
+                    assert (res["bitsets"][0] == want).all(), (shape, n, kind, mode, a)
+                    assert int(res["counts"][0]) == int(np.unpackbits(want).sum())
+                    prog.close()
+            for lo, hi in ((b"ab", b"abd"), (rows[0], rows[0]), (b"", b"\xff"), (b"b", b"a")):
+                prog = kb.Program(ctx, [kb.Leaf(9, kb.BYTES, kb.RANGE, lo, hi)])
+                res = ctx.scan(prog, [(300, 1)], nrows=[n], want_bitsets=True)
+                assert (res["bitsets"][0] == oc.match(ko.RG, lo, hi)).all(), (shape, n, kind, "range", lo, hi)
+                prog.close()
+            ctx.block_drop(300, 1, 9)
+    # row-level `height BETWEEN lo AND hi AND address = X` over several packs, aggregate over a value column
+    nrows = [5000, 70_001, 64]
+    packs = []
+    for p, n in enumerate(nrows):
+        rows = _string_rows(rng, n, shape)
+        height = (1000 * p + np.arange(n)).astype(np.int64)
+        amount = rng.integers(-10**6, 10**6, n).astype(np.int64)
+        blob = ko.store_str(ko.STR_COMPACT if shape != "fixed20" else ko.STR_FIXED, rows)
+        ctx.block_put(310 + p, 1, 1, kb.INT64, ko.store("best", ko.I64, height))
+        ctx.block_put(310 + p, 1, 2, kb.BYTES, blob)
+        ctx.block_put(310 + p, 1, 3, kb.INT64, ko.store("best", ko.I64, amount))
+        packs.append((rows, height, amount, blob))
+    x = packs[1][0][777]
+    prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, 500, 60_000), kb.Leaf(2, kb.BYTES, kb.EQ, x)])
+    res = ctx.scan(prog, [(310 + p, 1) for p in range(3)], nrows=nrows, want_bitsets=True, aggs=[(3, kb.INT64)])
+    st = None
+    for p, (rows, height, amount, blob) in enumerate(packs):
+        l0 = kt.pack_bits((height >= 500) & (height <= 60_000))
+        want = ko.tree_eval([0, 1, 0xFE], [l0, ko.StrContainer(blob).match(ko.EQ, x)], nrows[p])
+        assert (res["bitsets"][p] == want).all()
+        st = ko.reduce(ko.I64, amount, want, st)
+    g = res["aggs"][0]
+    assert (g.count, g.sum_bits, g.min_bits, g.max_bits) == (st.count, st.sum_bits, st.min_bits, st.max_bits) and st.count >= 1
+    prog.close()
+    for p in range(3):
+        for f in (1, 2, 3):
+            ctx.block_drop(310 + p, 1, f)
+
+
 def test_full_size_pack_properties(ctx):
     """BASELINE config 2 at full size: 4M-row bit-packed packs; size-independent checks
     (count == popcount(bitset) == numpy truth; NE is the complement of EQ; LT ∪ GE covers all rows)"""

@@ -348,3 +348,24 @@ def test_bucket_reduce_and_window_edges_follow_the_series_walk():
                 assert np.uint64(st[b].min_bits).view(np.int64) == vals[sel].min() and np.uint64(st[b].max_bits).view(np.int64) == vals[sel].max()
             else:
                 assert not st[b].valid
+
+
+def test_string_containers_round_trip_and_match_like_bytes_compare():
+    """string_test.go pins the string containers by round trip only; the oracle's Store/Load/Get and the seven matchers
+    (string_match.go:13-188) are checked here against Python's bytes ordering, which is bytes.Compare."""
+    rng = np.random.default_rng(3)
+    vocab = [b"", b"a", b"ab", b"abc", b"abd", b"b", b"\xff", b"\x00", b"ab\x00"]
+    rows = [vocab[i] for i in rng.integers(0, len(vocab), 500)]
+    fixed = [bytes(r) for r in rng.integers(0, 4, (300, 3), dtype=np.uint8)]
+    ops = {ko.EQ: lambda v, a, b: v == a, ko.NE: lambda v, a, b: v != a, ko.LT: lambda v, a, b: v < a, ko.LE: lambda v, a, b: v <= a,
+           ko.GT: lambda v, a, b: v > a, ko.GE: lambda v, a, b: v >= a, ko.RG: lambda v, a, b: a <= v <= b}
+    assert ko.store_str(ko.STR_FIXED, rows) is None and ko.store_str(ko.STR_CONST, rows) is None
+    for kind, data in ((ko.STR_COMPACT, rows), (ko.STR_DICT, rows), (ko.STR_FIXED, fixed), (ko.STR_COMPACT, fixed), (ko.STR_CONST, [b"xy"] * 77),
+                       (ko.STR_COMPACT, [b""]), (ko.STR_DICT, [b"q"])):
+        c = ko.StrContainer(ko.store_str(kind, data))
+        assert c.n == len(data) and all(c.get(i) == data[i] for i in range(0, len(data), 7))
+        for a in (b"", b"ab", b"abc", data[0], b"\x01\x02\x03", b"\xff\xff"):
+            for op, fn in ops.items():
+                b = a + b"\x01" if op == ko.RG else b""
+                want = kt.pack_bits(np.array([fn(v, a, b) for v in data]))
+                assert (c.match(op, a, b) == want).all(), (kind, op, a)
