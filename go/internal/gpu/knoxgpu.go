@@ -128,6 +128,26 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 				return errors.New("knoxgpu: more than 8 filter leaves")
 			}
 			l := C.kx_leaf{field: C.uint16_t(f.Id), block_type: C.uint8_t(f.Type), mode: C.uint8_t(f.Mode)}
+			if f.Type == types.BlockBytes && f.Mode != types.FilterModeIn && f.Mode != types.FilterModeNotIn {
+				// byte-string leaf (bytesMatcher, internal/operator/filter/match_bytes.go): operand bytes travel in a C
+				// copy behind `set`, nset = 1, a / b = lengths (RANGE: lower bound followed by the upper bound)
+				var lo, hi []byte
+				if f.Mode == types.FilterModeRange {
+					rg := f.Value.([2]any)
+					lo, hi = rg[0].([]byte), rg[1].([]byte)
+				} else {
+					lo = f.Value.([]byte)
+				}
+				p := C.malloc(C.size_t(len(lo) + len(hi) + 1))
+				buf := unsafe.Slice((*byte)(p), len(lo)+len(hi)+1)
+				copy(buf, lo)
+				copy(buf[len(lo):], hi)
+				cbufs = append(cbufs, p)
+				l.set, l.nset, l.a, l.b = (*C.uint64_t)(p), 1, C.uint64_t(len(lo)), C.uint64_t(len(hi))
+				post = append(post, C.uint8_t(len(leaves)))
+				leaves = append(leaves, l)
+				return nil
+			}
 			switch f.Mode {
 			case types.FilterModeRange:
 				rg := f.Value.([2]any)
