@@ -76,11 +76,20 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
         auto consume = [&](uint64_t key, const uint64_t (&v)[MAX_AGGS]) {
             if (key < cur_lo || key >= cur_hi) {
                 flush();
-                // window k with edge[k] <= key < edge[k + 1]; rows outside [edge[0], edge[nbuckets]) belong to no window
-                uint32_t a = 0, b = P.nbuckets + 1u;   // first edge > key
-                while (a < b) { uint32_t m = (a + b) >> 1; if (__ldg(P.edges + m) <= key) a = m + 1; else b = m; }
-                if (a == 0 || a > P.nbuckets) { cur = 0xffffffffu; cur_lo = 1; cur_hi = 0; return; }
-                cur = a - 1u; cur_lo = __ldg(P.edges + cur); cur_hi = __ldg(P.edges + cur + 1);
+                // time-ordered packs walk the windows in order: try the NEXT window before searching (one load instead of
+                // log2(nbuckets) dependent ones)
+                if (cur != 0xffffffffu && cur + 1u < P.nbuckets && key >= cur_hi) {
+                    const uint64_t nh = __ldg(P.edges + cur + 2);
+                    if (key < nh) { ++cur; cur_lo = cur_hi; cur_hi = nh; goto found; }
+                }
+                {
+                    // window k with edge[k] <= key < edge[k + 1]; rows outside [edge[0], edge[nbuckets]) belong to no window
+                    uint32_t a = 0, b = P.nbuckets + 1u;   // first edge > key
+                    while (a < b) { uint32_t m = (a + b) >> 1; if (__ldg(P.edges + m) <= key) a = m + 1; else b = m; }
+                    if (a == 0 || a > P.nbuckets) { cur = 0xffffffffu; cur_lo = 1; cur_hi = 0; return; }
+                    cur = a - 1u; cur_lo = __ldg(P.edges + cur); cur_hi = __ldg(P.edges + cur + 1);
+                }
+            found:;
             }
             ++cnt;
 #pragma unroll
@@ -122,7 +131,55 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
             }
         }
         constexpr int U = 4;
+        // Short windows (a job spans many of them): with lane = row mod 32 every lane would change its window every few
+        // rows and flush each time.  The job's first and last timestamp tell how many windows it spans; when a window is
+        // shorter than ~256 rows each lane takes a run of CONSECUTIVE rows instead (rows_per_lane of them: few window
+        // changes per lane; the strided loads stay in L1 because a lane walks its cache lines to the end).
+        bool consecutive = false;
         if (fast) {
+            const uint32_t r_first = g_begin * 32u, r_last = min(g_end * 32u, pi.n) - 1u;
+            const uint64_t k0 = decode_value_at(tsv, r_first) ^ P.ts_flip, k1 = decode_value_at(tsv, r_last) ^ P.ts_flip;
+            uint32_t a0 = 0, b0 = P.nbuckets + 1u, a1 = 0, b1 = P.nbuckets + 1u;
+            while (a0 < b0) { uint32_t m = (a0 + b0) >> 1; if (__ldg(P.edges + m) <= k0) a0 = m + 1; else b0 = m; }
+            while (a1 < b1) { uint32_t m = (a1 + b1) >> 1; if (__ldg(P.edges + m) <= k1) a1 = m + 1; else b1 = m; }
+            const uint32_t span = a1 > a0 ? a1 - a0 + 1u : a0 - a1 + 1u;
+            consecutive = (uint64_t)span * 256u > (uint64_t)(r_last - r_first + 1u);
+        }
+        if (fast && consecutive) {
+            const uint32_t tw = tsv.width;
+            const uint32_t* tsw = reinterpret_cast<const uint32_t*>(tsv.data);
+            const uint64_t tmask = width_mask((int)tw);
+            const uint32_t r_begin = g_begin * 32u, r_end = min(g_end * 32u, pi.n);
+            const uint32_t per_lane = (r_end - r_begin + 31u) / 32u;
+            const uint32_t my0 = r_begin + lane * per_lane, my1 = min(my0 + per_lane, r_end);
+            for (uint32_t r0 = my0; r0 < my1; r0 += U) {
+                bool on[U];
+                uint32_t t0[U], t1[U], t2[U];
+                uint64_t val[U][MAX_AGGS];
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    const uint32_t row = r0 + u;
+                    on[u] = row < my1 && ((__ldg(words + (row >> 5)) >> (row & 31u)) & 1u);
+                    const uint64_t bit = (uint64_t)row * tw;
+                    const uint32_t* wp = tsw + (bit >> 5);
+                    t0[u] = on[u] ? __ldg(wp) : 0u;
+                    t1[u] = on[u] ? __ldg(wp + 1) : 0u;
+                    t2[u] = (on[u] && tw > 32u) ? __ldg(wp + 2) : 0u;
+#pragma unroll
+                    for (int j = 0; j < MAX_AGGS; ++j) val[u][j] = (on[u] && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
+                }
+#pragma unroll
+                for (int u = 0; u < U; ++u) {
+                    if (!on[u]) continue;
+                    const uint32_t sh = (uint32_t)(((uint64_t)(r0 + u) * tw) & 31u);
+                    const uint64_t f = (((uint64_t)__funnelshift_r(t1[u], t2[u], sh) << 32) | __funnelshift_r(t0[u], t1[u], sh)) & tmask;
+                    uint64_t v[MAX_AGGS];
+#pragma unroll
+                    for (int j = 0; j < MAX_AGGS; ++j) v[j] = val[u][j] + vbase[j];
+                    consume(type_ext(tsv.type, f + tsv.base) ^ P.ts_flip, v);
+                }
+            }
+        } else if (fast) {
             const uint32_t tw = tsv.width;
             const uint32_t* tsw = reinterpret_cast<const uint32_t*>(tsv.data);
             const uint64_t tmask = width_mask((int)tw);

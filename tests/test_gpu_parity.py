@@ -574,6 +574,39 @@ def test_string_blocks_match_row_by_row(ctx, shape):
             ctx.block_drop(310 + p, 1, f)
 
 
+def test_repeated_scans_are_bit_reproducible(ctx):
+    """The general kernel shares match words between warps, recycles ring stages and lets the producer pick the way
+    value columns arrive from timing-dependent feedback: a race or an order dependence would show as run-to-run
+    differences.  40 repetitions of a three-leaf scan with three aggregates must agree bit for bit (float sum included)."""
+    import knoxdb_b200 as kb
+    n, npacks = 200_000, 64
+    base, accts = make_table(RNG, 2, [n, n])
+    encs = []
+    for cols in base:
+        encs.append({F_TS: ko.store("best", ko.I64, cols["ts"]), F_AMT: ko.store("best", ko.I64, cols["amount"]),
+                     F_FAMT: ko.store("raw", ko.F64, cols["famount"]), F_ACCT: ko.store("dict", ko.U64, cols["acct"])})
+    for p in range(npacks):
+        for f, t in ((F_TS, ko.I64), (F_AMT, ko.I64), (F_FAMT, ko.F64), (F_ACCT, ko.U64)):
+            ctx.block_put(p, 1, f, t, encs[p % 2][f])
+    ts = base[0]["ts"]
+    prog = kb.Program(ctx, [kb.Leaf(F_TS, kb.INT64, kb.RANGE, int(ts[n // 10]), int(ts[n * 6 // 10])),
+                            kb.Leaf(F_ACCT, kb.UINT64, kb.IN, values=RNG.choice(accts, 250, replace=False)),
+                            kb.Leaf(F_AMT, kb.INT64, kb.GT, -5 * 10**8)], [0, 1, kb.OP_AND, 2, kb.OP_OR])
+    refs = ctx.pack_refs([(p, 1) for p in range(npacks)])
+    first = None
+    for rep in range(40):
+        r = ctx.scan(prog, refs, nrows=[n] * npacks, want_bitsets=True, aggs=[(F_AMT, kb.INT64), (F_FAMT, kb.FLOAT64), (F_ACCT, kb.UINT64)])
+        got = (r["counts"].tobytes(), b"".join(b.tobytes() for b in r["bitsets"]),
+               [(g.count, g.sum_bits, g.sum_err, g.min_bits, g.max_bits) for g in r["aggs"]])
+        if first is None:
+            first = got
+        assert got == first, rep
+    prog.close()
+    for p in range(npacks):
+        for f in (F_TS, F_AMT, F_FAMT, F_ACCT):
+            ctx.block_drop(p, 1, f)
+
+
 def test_full_size_pack_properties(ctx):
     """BASELINE config 2 at full size: 4M-row bit-packed packs; size-independent checks
     (count == popcount(bitset) == numpy truth; NE is the complement of EQ; LT ∪ GE covers all rows)"""
