@@ -421,8 +421,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // dictionary-code bitmaps cached in shared memory behind the ring
     uint32_t code_smem_off[MAX_LEAVES] = {}, code_smem_words = 0;
     for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
-    // hash-set leaves: prefilter bitmap (<= 16 KB) and, when it is small (<= 16 KB), the exact table in shared memory too
+    // hash-set leaves: prefilter bitmap (<= 16 KB) and, when it is small (<= 16 KB: sets up to ~500 keys), the exact table
+    // in shared memory too; larger tables stay in global memory (L2) and only candidates are verified against them
     uint32_t hs_smem_off[MAX_LEAVES] = {}, hs_tab_smem_off[MAX_LEAVES] = {};
+    uint32_t hs_tab_limit = 16u * 1024u;
+    if (const char* e = getenv("KX_HASH_SMEM_KB")) hs_tab_limit = uint32_t(atoi(e)) * 1024u;   // tuning hook
     const uint32_t code_bitmap_words = code_smem_words;
     code_smem_words = uint32_t(round_up(code_smem_words, 8));   // tables are read with 128-bit loads
     for (int l = 0; l < nleaves; ++l) {
@@ -431,7 +434,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         hs_smem_off[l] = code_smem_words;
         code_smem_words += (1u << prog->pre_log2[l]) / 32u;
         const uint32_t tab_words = (4u << prog->tab_log2[l]) * 2u;
-        if (tab_words * 4u <= 16u * 1024u) { hs_tab_smem_off[l] = code_smem_words; code_smem_words += tab_words; }
+        // (all bitmaps and tables together stay below 96 KB, so that a two-stage ring still fits beside them)
+        if (tab_words * 4u <= hs_tab_limit && (size_t(code_smem_words) + tab_words) * 4u <= 96u * 1024u) { hs_tab_smem_off[l] = code_smem_words; code_smem_words += tab_words; }
     }
     const size_t code_smem_bytes = round_up(size_t(code_smem_words) * 4, 128);
     // Value columns of the fused reduce can be staged through the ring, agg_chunks (<= 4) stages per tile and column
@@ -459,7 +463,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     };
     const size_t stage_fixed = 32;
     auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
-    auto rmax_for = [&](const Geo& g) { return (g.budget - code_smem_bytes / 2 - stage_fixed - 128) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)); };
+    auto rmax_for = [&](const Geo& g) {
+        const size_t fixed = code_smem_bytes / 2 + stage_fixed + 128;
+        return g.budget > fixed ? (g.budget - fixed) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)) : size_t(0);
+    };
     const Geo g3{3, 2, 33 * 1024}, g2{2, 2, 50 * 1024}, g1{1, 2, 99 * 1024};
     Geo geo = g2;
     uint32_t R = 32;
