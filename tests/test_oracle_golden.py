@@ -102,3 +102,19 @@ def test_varint_roundtrip():
     buf = np.zeros(16, dtype=np.uint8)
     ko.lib().ko_put_uvarint(ko._p(buf), 241); assert buf[:2].tolist() == [241, 1]
     ko.lib().ko_put_uvarint(ko._p(buf), 2288); assert buf[:3].tolist() == [249, 0, 0]
+
+
+def test_window_edges_match_the_reference_timeunit_next_table():
+    """ko_window_edges restates TimeUnit.Next for fixed-duration units; the reference pins Next with a table
+    (pkg/util/timeunit_test.go:162-228, transcribed by tests/golden/extract_timeunit_vectors.py): the second edge of a
+    walk that starts at `in` is Next(in, 1)."""
+    import json
+    import os
+    d = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "timeunit_vectors.json")))
+    assert len(d["cases"]) >= 15
+    for c in d["cases"]:
+        e = ko.window_edges(c["in"], c["in"] + 1, c["step_s"])
+        assert int(e[0]) == c["in"] and int(e[1]) == c["next"], c
+        # and the walk continues in whole steps from there (TestSteps: consecutive steps are one Duration apart)
+        e = ko.window_edges(c["in"], c["in"] + 5 * c["step_s"], c["step_s"])
+        assert all(int(b) - int(a) == c["step_s"] for a, b in zip(e[1:-1], e[2:]))
