@@ -711,6 +711,33 @@ def test_errors_are_loud(ctx):
     with pytest.raises(kb.KnoxError):
         kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.EQ, 5)], postfix=[0, kb.OP_AND])
     prog.close()
+    # string blocks and leaves
+    with pytest.raises(kb.KnoxError):
+        ctx.block_put(0, 0, 0, kb.BYTES, b"\x63\x00\x00")    # unknown string container id
+    with pytest.raises(kb.KnoxError):
+        ctx.block_put(0, 0, 0, kb.BYTES, ko.store_str(ko.STR_FIXED, [b"abc", b"abd"])[:-2])   # truncated buffer
+    vals = np.arange(100, dtype=np.int64)
+    ctx.block_put(900, 1, 1, kb.INT64, ko.store("raw", ko.I64, vals))
+    ctx.block_put(900, 1, 2, kb.BYTES, ko.store_str(ko.STR_COMPACT, [b"x%d" % i for i in range(100)]))
+    p_str_on_int = kb.Program(ctx, [kb.Leaf(1, kb.BYTES, kb.EQ, b"x")])
+    p_int_on_str = kb.Program(ctx, [kb.Leaf(2, kb.INT64, kb.EQ, 5)])
+    p_prune_only = kb.Program(ctx, [kb.Leaf(2, kb.BYTES, kb.EQ)])
+    for bad in (p_str_on_int, p_int_on_str, p_prune_only):
+        with pytest.raises(kb.KnoxError):
+            ctx.scan(bad, [(900, 1)])
+        bad.close()
+    # time-bucketed scans: edges must ascend, the window column must be an integer block, blocks must be resident
+    ok = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.GE, 0)])
+    r = ctx.scan_buckets(ok, [(900, 1)], 1, kb.INT64, [0, 50, 100], aggs=[(1, kb.INT64)])
+    assert r["bucket_counts"].tolist() == [50, 50] and [g.sum_bits for g in r["aggs"][0]] == [int(vals[:50].sum()), int(vals[50:].sum())]
+    with pytest.raises(kb.KnoxError):
+        ctx.scan_buckets(ok, [(900, 1)], 1, kb.INT64, [0, 100, 50])
+    with pytest.raises(kb.KnoxError):
+        ctx.scan_buckets(ok, [(900, 1)], 2, kb.INT64, [0, 50, 100])          # window column is a string block
+    with pytest.raises(kb.KnoxError):
+        ctx.scan_buckets(ok, [(901, 1)], 1, kb.INT64, [0, 50, 100])          # pack not resident
+    ok.close()
+    ctx.block_drop(900, 1, 1); ctx.block_drop(900, 1, 2)
 
 
 def test_resident_stats_index_bloom_build_and_prune(ctx):
