@@ -301,7 +301,11 @@ def main():
     _, e_total_bits = ctx.bitset_layout(e_nrows)
     fields_spec = [(FIELD, kb.UINT64)]
     for _ in range(2):
-        ctx.scan_host(prog, fields_spec, hb, nrows=e_nrows, want_bitsets=True, bitset_buf=bitbuf)
+        res_e = ctx.scan_host(prog, fields_spec, hb, nrows=e_nrows, want_bitsets=True, bitset_buf=bitbuf)
+    # the host-block path (pipelined uploads, several batches per call) must give what the resident packs give
+    res_r = ctx.scan(prog, ctx.pack_refs([(p, 1) for p in range(e2e_packs)]), nrows=e_nrows, want_bitsets=True)
+    assert res_e["counts"].tolist() == res_r["counts"].tolist(), "kx_scan_host disagrees with the resident scan"
+    assert all((x == y).all() for x, y in zip(res_e["bitsets"], res_r["bitsets"])), "kx_scan_host bitsets disagree with the resident scan"
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()

@@ -124,8 +124,10 @@ struct kx_ctx {
     size_t store_enc_bytes = 0, store_dev_bytes = 0;
 
     // scratch (grow only)
-    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_codebits, d_leafbits;
-    PinBuf h_desc, h_res, h_aux;
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_stage2, d_codebits, d_leafbits;
+    PinBuf h_desc, h_res, h_aux, h_aux2;
+    cudaStream_t copy_stream = nullptr;            // kx_scan_host: uploads of batch b + 1 run beside the scan of batch b
+    cudaEvent_t ev_copy[2] = {nullptr, nullptr};
 
     double last_kernel_ms = 0, last_total_ms = 0;
     int last_launches = 0;
@@ -855,6 +857,8 @@ int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
     c->budget = hbm_budget ? hbm_budget : free_b / 10 * 8;
     CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CK(cudaEventCreate(&c->ev_start)); CK(cudaEventCreate(&c->ev_k0)); CK(cudaEventCreate(&c->ev_k1)); CK(cudaEventCreate(&c->ev_end));
+    CK(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&c->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_copy[1], cudaEventDisableTiming));
     *out = c.release();
     return KX_OK;
 }
@@ -865,6 +869,9 @@ void kx_ctx_destroy(kx_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     for (auto& s : ctx->slabs) if (s.base) cudaFree(s.base);
     cudaEventDestroy(ctx->ev_start); cudaEventDestroy(ctx->ev_k0); cudaEventDestroy(ctx->ev_k1); cudaEventDestroy(ctx->ev_end);
+    if (ctx->ev_copy[0]) cudaEventDestroy(ctx->ev_copy[0]);
+    if (ctx->ev_copy[1]) cudaEventDestroy(ctx->ev_copy[1]);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1168,8 +1175,10 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         if (field_types[agg_fi[size_t(j)]] != aggs[j].block_type) return fail(ctx, KX_EINVAL, "aggregate / block type mismatch");
     }
 
-    // Batches bounded by encoded bytes so the transient device footprint stays small; the
-    // H2D copies of a batch are queued asynchronously (pinned sources) ahead of its kernel.
+    // Batches bounded by encoded bytes so that the transient device footprint stays small.  Two slots: the blocks of
+    // batch b + 1 are queued on the copy stream into the other staging buffer before batch b is scanned.  (Measured on
+    // B200 with 128 MB batches: no gain over one large batch — the scan's small descriptor upload queues behind the next
+    // batch's bulk copies on the same H2D copy engine — so batches stay large: one batch for anything below 2 GB.)
     const size_t BATCH_BYTES = 2048ull << 20;
     std::vector<kx_agg_out> part(static_cast<size_t>(naggs));
     std::vector<std::vector<kx_agg_out>> parts(static_cast<size_t>(naggs));
@@ -1177,8 +1186,16 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
-    int p0 = 0;
-    while (p0 < npacks) {
+    CK(cudaStreamWaitEvent(ctx->copy_stream, e0, 0));   // uploads do not overtake earlier work on the context's stream
+
+    struct HostBatch { int p0 = 0, p1 = 0; std::vector<BlockLayout> lays; };
+    HostBatch slots[2];
+    DevBuf* dstage[2] = {&ctx->d_stage, &ctx->d_stage2};
+    PinBuf* haux[2] = {&ctx->h_aux, &ctx->h_aux2};
+
+    // parse the blocks of packs [p0, p1), lay them out in slot `sl`'s staging buffer and queue the uploads
+    auto prepare = [&](int sl, int p0) -> int {
+        HostBatch& B = slots[sl];
         size_t bytes = 0; int p1 = p0;
         while (p1 < npacks) {
             size_t b = 0;
@@ -1186,17 +1203,20 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             if (p1 > p0 && bytes + b > BATCH_BYTES) break;
             bytes += b; ++p1;
         }
+        B.p0 = p0; B.p1 = p1;
         const int nb = p1 - p0;
         // pass 1: parse headers, lay the batch out in the staging arena (256 B aligned streams)
-        std::vector<BlockLayout> lays(size_t(nb) * nfields);
+        B.lays.clear();
+        B.lays.resize(size_t(nb) * nfields);
+        std::vector<BlockLayout>& lays = B.lays;
         std::vector<size_t> off_stream(lays.size(), 0), off_a64(lays.size(), 0), off_a32(lays.size(), 0), off_blob(lays.size(), 0), aux_src(lays.size(), 0);
         size_t dev_bytes = 0, aux_bytes = 0;
         for (int p = 0; p < nb; ++p) {
             for (int f = 0; f < nfields; ++f) {
                 size_t bi = size_t(p0 + p) * nfields + f, li = size_t(p) * nfields + f;
                 std::string err;
-                rc = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lays[li], err);
-                if (rc) return fail(ctx, rc, "kx_scan_host: " + err);
+                int rc2 = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lays[li], err);
+                if (rc2) return fail(ctx, rc2, "kx_scan_host: " + err);
                 BlockLayout& lay = lays[li];
                 if (lay.owned.empty() && lay.stream_len) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.stream_len + STREAM_PAD, 256); }
                 aux_src[li] = aux_bytes;
@@ -1205,7 +1225,6 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             }
         }
         // host-built arrays (dictionaries, run values/ends, transcoded streams) go through one pinned buffer
-        const size_t aux_dev0 = dev_bytes;
         for (size_t li = 0; li < lays.size(); ++li) {
             BlockLayout& lay = lays[li];
             if (!lay.owned.empty()) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.owned.size() + STREAM_PAD, 256); }
@@ -1213,43 +1232,51 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             if (!lay.aux32.empty()) { off_a32[li] = dev_bytes; dev_bytes += round_up(lay.aux32.size() * 4 + STREAM_PAD, 256); }
             if (!lay.blob.empty()) { off_blob[li] = dev_bytes; dev_bytes += round_up(lay.blob.size() + STREAM_PAD, 256); }
         }
-        (void)aux_dev0;
-        CK(ctx->d_stage.reserve(dev_bytes + 256));
-        CK(ctx->h_aux.reserve(aux_bytes + 64));
-        uint8_t* dbase = static_cast<uint8_t*>(ctx->d_stage.p);
-        uint8_t* hbase = static_cast<uint8_t*>(ctx->h_aux.p);
+        CK(dstage[sl]->reserve(dev_bytes + 256));
+        CK(haux[sl]->reserve(aux_bytes + 64));
+        uint8_t* dbase = static_cast<uint8_t*>(dstage[sl]->p);
+        uint8_t* hbase = static_cast<uint8_t*>(haux[sl]->p);
+        cudaStream_t cs = ctx->copy_stream;
         // pass 2: queue the copies (asynchronous when the caller's blocks are pinned)
         for (size_t li = 0; li < lays.size(); ++li) {
             BlockLayout& lay = lays[li];
             ColView& v = lay.view;
             uint8_t* hp = hbase + aux_src[li];
             if (lay.owned.empty()) {
-                if (lay.stream_len) CK(cudaMemcpyAsync(dbase + off_stream[li], lay.stream, lay.stream_len, cudaMemcpyHostToDevice, ctx->stream));
+                if (lay.stream_len) CK(cudaMemcpyAsync(dbase + off_stream[li], lay.stream, lay.stream_len, cudaMemcpyHostToDevice, cs));
             } else {
                 std::memcpy(hp, lay.owned.data(), lay.owned.size());
-                CK(cudaMemcpyAsync(dbase + off_stream[li], hp, lay.owned.size(), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(dbase + off_stream[li], hp, lay.owned.size(), cudaMemcpyHostToDevice, cs));
                 hp += round_up(lay.owned.size(), 16);
             }
             if (!lay.aux64.empty()) {
                 std::memcpy(hp, lay.aux64.data(), lay.aux64.size() * 8);
-                CK(cudaMemcpyAsync(dbase + off_a64[li], hp, lay.aux64.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(dbase + off_a64[li], hp, lay.aux64.size() * 8, cudaMemcpyHostToDevice, cs));
                 hp += round_up(lay.aux64.size() * 8, 16);
             }
             if (!lay.aux32.empty()) {
                 std::memcpy(hp, lay.aux32.data(), lay.aux32.size() * 4);
-                CK(cudaMemcpyAsync(dbase + off_a32[li], hp, lay.aux32.size() * 4, cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(dbase + off_a32[li], hp, lay.aux32.size() * 4, cudaMemcpyHostToDevice, cs));
                 hp += round_up(lay.aux32.size() * 4, 16);
             }
             if (!lay.blob.empty()) {
                 std::memcpy(hp, lay.blob.data(), lay.blob.size());
-                CK(cudaMemcpyAsync(dbase + off_blob[li], hp, lay.blob.size(), cudaMemcpyHostToDevice, ctx->stream));
+                CK(cudaMemcpyAsync(dbase + off_blob[li], hp, lay.blob.size(), cudaMemcpyHostToDevice, cs));
             }
             if (v.kind == CK_BITS || v.kind == CK_DICT || (v.kind == CK_ALP && v.width)) v.data = dbase + off_stream[li];
             if (v.kind == CK_ALP && !lay.blob.empty()) v.aux = dbase + off_blob[li];
             if (v.kind == CK_DICT) v.aux = dbase + off_a64[li];
             if (v.kind == CK_RUNEND) { v.data = dbase + off_a64[li]; v.aux = dbase + off_a32[li]; }
         }
-        auto cleanup = [&]() {};
+        CK(cudaEventRecord(ctx->ev_copy[sl], cs));
+        return KX_OK;
+    };
+
+    // scan the batch of slot `sl` once its uploads have landed
+    auto scan_slot = [&](int sl) -> int {
+        HostBatch& B = slots[sl];
+        const int p0 = B.p0, nb = B.p1 - B.p0;
+        std::vector<BlockLayout>& lays = B.lays;
         ScanJob job; job.npacks = nb;
         job.nrows.resize(size_t(nb)); job.leaf_views.resize(size_t(nb) * nleaves); job.leaf_dicts.resize(size_t(nb) * nleaves);
         job.agg_views.resize(size_t(nb) * size_t(naggs));
@@ -1269,19 +1296,32 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         if (bitsets) {
             size_t base = bitset_off[p0];
             for (int p = 0; p < nb; ++p) {
-                if (bitset_off[p0 + p] < base) { cleanup(); return fail(ctx, KX_EINVAL, "bitset_off must be ascending"); }
+                if (bitset_off[p0 + p] < base) return fail(ctx, KX_EINVAL, "bitset_off must be ascending");
                 offs.push_back(bitset_off[p0 + p] - base);
             }
-            if (base & 7) { cleanup(); return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8"); }
+            if (base & 7) return fail(ctx, KX_EINVAL, "bitset_off must be a multiple of 8");
             bdst = bitsets + base;
         }
-        rc = run_scan(ctx, prog, job, bdst, bitsets ? offs.data() : nullptr, counts ? counts + p0 : nullptr, aggs, naggs,
-                      naggs ? part.data() : nullptr);
+        CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_copy[sl], 0));
+        int rc2 = run_scan(ctx, prog, job, bdst, bitsets ? offs.data() : nullptr, counts ? counts + p0 : nullptr, aggs, naggs,
+                           naggs ? part.data() : nullptr);
         kms += ctx->last_kernel_ms; launches += ctx->last_launches;
-        cleanup();
-        if (rc) return rc;
+        if (rc2) return rc2;
         for (int j = 0; j < naggs; ++j) parts[size_t(j)].push_back(part[size_t(j)]);
-        p0 = p1;
+        return KX_OK;
+    };
+
+    auto drain = [&](int rc2) { cudaStreamSynchronize(ctx->copy_stream); cudaStreamSynchronize(ctx->stream); cudaEventDestroy(e0); cudaEventDestroy(e1); return rc2; };
+    if (npacks > 0) {
+        int sl = 0;
+        if ((rc = prepare(0, 0))) return drain(rc);
+        for (;;) {
+            const int next_p0 = slots[sl].p1;
+            if (next_p0 < npacks && (rc = prepare(sl ^ 1, next_p0))) return drain(rc);   // uploads of the next batch start now
+            if ((rc = scan_slot(sl))) return drain(rc);
+            if (next_p0 >= npacks) break;
+            sl ^= 1;
+        }
     }
     CK(cudaEventRecord(e1, ctx->stream));
     CK(cudaEventSynchronize(e1));
