@@ -163,6 +163,32 @@ def test_in_sets_of_every_size_on_packed_and_raw_blocks(ctx, t):
                 assert cnt == int(np.unpackbits(want).sum())
 
 
+def test_run_end_blocks_of_every_run_length(ctx):
+    """RunEndContainer.Match* + applyMatch (int_runend.go:224-318) for runs shorter than a bitset word, runs that span
+    many words, and both mixed in one block (the run-fill pre-pass builds words cooperatively for short runs and with
+    per-run range stores for long ones); row counts around word and warp-of-runs boundaries."""
+    rng = np.random.default_rng(21)
+    for n, lens in ((100_003, (1, 4)), (100_003, (1, 70)), (250_000, (60, 3000)), (70_001, (1, 1)), (4096, (5000, 5001)), (33, (1, 3)), (1, (1, 1))):
+        chunks, total = [], 0
+        while total < n:
+            ln = int(rng.integers(lens[0], lens[1] + 1))
+            chunks.append(np.full(ln, int(rng.integers(-50, 50)), dtype=np.int64))
+            total += ln
+        vals = np.concatenate(chunks)[:n]
+        if n < 2:
+            continue
+        blob = ko.store("runend", ko.I64, vals)
+        oc = ko.Container(ko.I64, blob)
+        for op, a, b in ((ko.EQ, 7, 0), (ko.NE, 7, 0), (ko.LT, 0, 0), (ko.GE, -10, 0), (ko.RG, -5, 5), (ko.GT, 1000, 0), (ko.LE, 1000, 0)):
+            want = oc.match(op, ko.scalar_u64(ko.I64, a), ko.scalar_u64(ko.I64, b))
+            got, cnt = ctx.container_match(ko.I64, blob, op, a, b, nrows=n)
+            assert (got == want).all(), (n, lens, op)
+            assert cnt == int(np.unpackbits(want).sum())
+        su = ko.as_u64(ko.I64, np.array([-3, 7, 11, 49], dtype=np.int64))
+        got, _ = ctx.container_match(ko.I64, blob, ko.IN, values=su, nrows=n)
+        assert (got == oc.match_set(su)).all(), (n, lens, "in")
+
+
 def test_bitset_ops(ctx):
     import knoxdb_b200 as kb
     L = ko.lib()
