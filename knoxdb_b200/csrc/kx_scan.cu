@@ -661,43 +661,13 @@ __global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, const uint64
     const uint32_t* ends = reinterpret_cast<const uint32_t*>(J.ends);
     const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(J.vals);
     uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
-    const uint32_t lane = threadIdx.x & 31u;
-    // whole warps walk 32 consecutive runs at a time (the loop bound is warp-uniform)
-    for (uint32_t k0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; k0 < J.nruns; k0 += gridDim.x * blockDim.x) {
-        const uint32_t k = k0 + lane;
-        bool p = false;
-        uint32_t start = 1, end = 0;   // empty
-        if (k < J.nruns) {
-            const uint64_t val = __ldg(vals + k);
-            p = J.is_set ? set_has(set_vals + J.a, (uint32_t)J.d, val) : ((val ^ J.wm) - J.a) <= J.d;
-            start = k ? __ldg(ends + k - 1) + 1u : 0u; end = __ldg(ends + k);   // inclusive
-            if (end >= J.nrows) end = J.nrows - 1u;
-            if (start > end) p = false;
-        }
-        // Short runs (the usual case: a word holds several runs): the warp's 32 runs cover one contiguous row range; the
-        // warp builds the words of that range together — every lane contributes its run's bits to the word at hand, one
-        // OR-reduction per word — and only the first and the last word, shared with neighbouring warps, need atomics.
-        const uint32_t lo = __shfl_sync(0xffffffffu, start, 0);
-        const uint32_t last = min(k0 + 31u, J.nruns - 1u) - k0;
-        const uint32_t hi = __shfl_sync(0xffffffffu, end, last);
-        const bool valid = k < J.nruns && start <= end;
-        if (__all_sync(0xffffffffu, !valid || end - start < 64u) && __all_sync(0xffffffffu, k >= J.nruns || start <= end) && hi >= lo && (hi >> 5) - (lo >> 5) < 96u) {
-            const uint32_t w_lo = lo >> 5, w_hi = hi >> 5;
-            for (uint32_t w = w_lo; w <= w_hi; ++w) {
-                uint32_t m = 0;
-                if (p && (start >> 5) <= w && (end >> 5) >= w) {
-                    const uint32_t b0 = (start >> 5) == w ? (start & 31u) : 0u, b1 = (end >> 5) == w ? (end & 31u) : 31u;
-                    m = (0xffffffffu << b0) & (0xffffffffu >> (31u - b1));
-                }
-                m = __reduce_or_sync(0xffffffffu, m);
-                if (lane == 0 && m) {
-                    if (w == w_lo || w == w_hi) atomicOr(out + w, m); else out[w] = m;
-                }
-            }
-            continue;
-        }
-        // long runs: every matching run sets its own range (atomics at the two edge words, plain stores in between)
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < J.nruns; k += gridDim.x * blockDim.x) {
+        uint64_t val = __ldg(vals + k);
+        bool p = J.is_set ? set_has(set_vals + J.a, (uint32_t)J.d, val) : ((val ^ J.wm) - J.a) <= J.d;
         if (!p) continue;
+        uint32_t start = k ? __ldg(ends + k - 1) + 1u : 0u, end = __ldg(ends + k);   // inclusive
+        if (end >= J.nrows) end = J.nrows - 1u;
+        if (start > end) continue;
         uint32_t w0 = start >> 5, w1 = end >> 5;
         uint32_t m0 = 0xffffffffu << (start & 31u), m1 = 0xffffffffu >> (31u - (end & 31u));
         if (w0 == w1) { atomicOr(out + w0, m0 & m1); continue; }

@@ -165,8 +165,8 @@ def test_in_sets_of_every_size_on_packed_and_raw_blocks(ctx, t):
 
 def test_run_end_blocks_of_every_run_length(ctx):
     """RunEndContainer.Match* + applyMatch (int_runend.go:224-318) for runs shorter than a bitset word, runs that span
-    many words, and both mixed in one block (the run-fill pre-pass builds words cooperatively for short runs and with
-    per-run range stores for long ones); row counts around word and warp-of-runs boundaries."""
+    many words, and both mixed in one block (the run-fill pre-pass sets every matching run's row range: atomics at the
+    edge words, plain stores in between); row counts around word boundaries."""
     rng = np.random.default_rng(21)
     for n, lens in ((100_003, (1, 4)), (100_003, (1, 70)), (250_000, (60, 3000)), (70_001, (1, 1)), (4096, (5000, 5001)), (33, (1, 3)), (1, (1, 1))):
         chunks, total = [], 0
