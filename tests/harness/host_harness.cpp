@@ -172,4 +172,26 @@ uint64_t kxh_xxh3_fixed(int nbytes, uint64_t v) {
     return 0;
 }
 
+// Byte-string blocks: the product's normalisation (normalize_string_block: container ids 16..19 → byte buffer + flat u32
+// index array) interpreted row by row with the layout rules of kx_types.h (STR_*) and the product's string_pred — the
+// scalar twin of strmatch_kernel.  Returns rows, or < 0 on a parse error.
+long kxh_str_match(const uint8_t* enc, size_t len, int mode, const uint8_t* a, size_t al, const uint8_t* b, size_t bl, uint8_t* bits) {
+    StrLayout lay; std::string err;
+    if (normalize_string_block(enc, len, lay, err)) return -1;
+    const ColView& v = lay.view;
+    const uint32_t n = v.n, m = v.naux;
+    for (uint32_t i = 0; i < n; ++i) {
+        size_t ofs = 0, ln = 0;
+        switch (v.is_raw) {
+        case STR_CONST: ofs = 0; ln = size_t(v.delta); break;
+        case STR_FIXED: ln = size_t(v.delta); ofs = size_t(i) * ln; break;
+        case STR_COMPACT: ofs = lay.idx[i]; ln = lay.idx[n + i]; break;
+        default: { uint32_t c = lay.idx[i]; ofs = lay.idx[n + c]; ln = lay.idx[n + m + c]; break; }
+        }
+        if (ofs + ln > lay.nbytes) return -2;
+        if (string_pred(mode, lay.bytes + ofs, ln, a, al, b, bl)) bits[i >> 3] |= uint8_t(1u << (i & 7));
+    }
+    return long(n);
+}
+
 }  // extern "C"

@@ -109,8 +109,20 @@ def harness():
         L.kxh_xxh3_fixed.argtypes = [C.c_int, C.c_uint64]
         L.kxh_xxh3_bytes.restype = C.c_uint64
         L.kxh_xxh3_bytes.argtypes = [vp, C.c_size_t]
+        L.kxh_str_match.restype = C.c_long
+        L.kxh_str_match.argtypes = [vp, C.c_size_t, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp]
         _h = L
     return _h
+
+
+def host_str_match(blob, n, op, a, b=b""):
+    """the product's host normalisation of a string block + its scalar string predicate, row by row (CPU)"""
+    enc = np.frombuffer(blob, dtype=np.uint8).copy()
+    bits = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
+    aa, bb = np.frombuffer(a + b"\0", dtype=np.uint8).copy(), np.frombuffer(b + b"\0", dtype=np.uint8).copy()
+    rows = harness().kxh_str_match(enc.ctypes.data, enc.size, op, aa.ctypes.data, len(a), bb.ctypes.data, len(b), bits.ctypes.data)
+    assert rows == n, rows
+    return bits[: (n + 7) // 8]
 
 
 def host_match(t, blob, n, op, a=0, b=0, values=None):

@@ -159,3 +159,27 @@ def test_alp_host_translation_matches_oracle():
                             want = oc.match(op, ua, ub)
                             got, _ = kt.host_match(t, blob, n, op, ua, ub)
                             assert (got == want).all(), (n, name, e, f, op, a, b)
+
+
+def test_string_blocks_host_normalisation_matches_the_oracle():
+    """normalize_string_block (containers 16..19 → byte buffer + flat index array) and string_pred, interpreted row by
+    row on the CPU, against the oracle's string containers for all seven modes; truncated buffers are rejected."""
+    rng = np.random.default_rng(8)
+    vocab = [b"", b"a", b"ab", b"abc", b"abd", b"tz1VSUr8wwNhLAzempoch5d6hLRiTh8Cjcjb", b"zz", bytes(range(200))]
+    ragged = [vocab[i] for i in rng.integers(0, len(vocab), 3000)]
+    fixed = [bytes(r) for r in rng.integers(0, 3, (2000, 4), dtype=np.uint8)]
+    cases = [(ko.STR_COMPACT, ragged), (ko.STR_DICT, ragged), (ko.STR_FIXED, fixed), (ko.STR_COMPACT, fixed), (ko.STR_DICT, fixed),
+             (ko.STR_CONST, [b"same"] * 100), (ko.STR_COMPACT, [b""]), (ko.STR_DICT, [b"x", b"x", b"y"])]
+    modes = ((1, ko.EQ), (2, ko.NE), (3, ko.GT), (4, ko.GE), (5, ko.LT), (6, ko.LE))
+    for kind, rows in cases:
+        blob = ko.store_str(kind, rows)
+        oc = ko.StrContainer(blob)
+        for a in (rows[0], rows[len(rows) // 2], b"", b"ab", b"\x01\x01", b"\xff"):
+            for m, kom in modes:
+                assert (kt.host_str_match(blob, len(rows), m, a) == oc.match(kom, a)).all(), (kind, m, a)
+            assert (kt.host_str_match(blob, len(rows), 9, a, a + b"\x01") == oc.match(ko.RG, a, a + b"\x01")).all(), (kind, "range", a)
+        enc = np.frombuffer(blob, dtype=np.uint8).copy()
+        bits = np.zeros(len(rows) // 8 + 16, dtype=np.uint8)
+        aa = np.zeros(4, dtype=np.uint8)
+        if len(blob) > 8:
+            assert kt.harness().kxh_str_match(enc.ctypes.data, len(blob) - 3, 1, aa.ctypes.data, 1, aa.ctypes.data, 0, bits.ctypes.data) < 0
