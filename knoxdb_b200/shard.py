@@ -57,6 +57,20 @@ def allgather_partials(local_aggs, block_types, dist=None, device=None):
     return [combine(block_types[j], [unpack_partial(allb[r, j]) for r in range(world)]) for j in range(n)]
 
 
+def allgather_window_partials(window_aggs, block_types, dist=None, device=None):
+    """Sharded series query (kx_scan_buckets per rank): window_aggs[j][k] = this rank's AggOut of value column j in
+    window k → the same shape combined over all ranks.  Still ONE collective: the nbuckets x naggs partials travel as
+    one flat array and every window cell is combined in rank order like the un-bucketed partials."""
+    flat = [a for col in window_aggs for a in col]
+    types = [t for col, t in zip(window_aggs, block_types) for _ in col]
+    out = allgather_partials(flat, types, dist, device)
+    res, i = [], 0
+    for col in window_aggs:
+        res.append(out[i:i + len(col)])
+        i += len(col)
+    return res
+
+
 class PartialExchange:
     """The one collective of a sharded query with every buffer preallocated: the per-rank 64 B partials go
     host (pinned) -> device -> all_gather_into_tensor -> host (pinned) and are combined in rank order."""
