@@ -393,7 +393,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 if (o.fixmode == FIX_ANDNOT_ALL) o.fix = v.aux + alp_mask_off(v.naux);   // resident patch bitmap
                 else {
                     const LeafSpec& ls = prog->leaves[size_t(l)];
-                    ajobs.push_back(AlpFixJob{v.aux, ls.a, ls.b, leafbits_bytes, v.naux, uint32_t(ls.mode == KX_MODE_NE ? KX_MODE_EQ : ls.mode),
+                    ajobs.push_back(AlpFixJob{v.aux, ls.a, ls.b, leafbits_bytes, v.naux, uint32_t(ls.mode == KX_MODE_NE ? uint8_t(KX_MODE_EQ) : ls.mode),
                                               o.fixmode == FIX_ANDNOT_NPRED ? 1u : 0u, 0});
                     ajob_leaf.push_back(size_t(p) * nleaves + l);
                     leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
