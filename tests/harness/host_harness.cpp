@@ -81,9 +81,11 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
     const ColView& v = hb.lay.view;
     LeafSpec leaf; leaf.type = uint8_t(block_type); leaf.mode = uint8_t(mode); leaf.a = a; leaf.b = b;
     std::vector<uint64_t> tab; int tab_log2 = 0;
+    std::vector<uint32_t> pre; int pre_log2 = 0;   // one-hash prefilter bitmap, tested before the table like leaf_hashset does
     if (set) {
         leaf.set.assign(set, set + nset); std::sort(leaf.set.begin(), leaf.set.end()); leaf.set.erase(std::unique(leaf.set.begin(), leaf.set.end()), leaf.set.end());
         leaf.has_table = build_set_table(leaf.set, tab, tab_log2);
+        if (leaf.has_table) build_set_prefilter(leaf.set, pre, pre_log2);
     }
     ColView dv = v;
     dv.data = hb.stream();   // non-null marks "has a stream" for compile_leaf
@@ -125,8 +127,10 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
         }
         case LM_HASHSET: {   // leaf_hashset: compare with the four slots of the home bucket
             uint64_t val = type_ext(v.type, field_at(hb.stream(), hb.stream_len(), row, L.width) + v.base);
+            const uint32_t idx = set_hash32(val) >> (32 - pre_log2);
+            const bool cand = (pre[idx >> 5] >> (idx & 31u)) & 1u;   // phase 1: prefilter (no false negatives allowed)
             const uint64_t* b = tab.data() + size_t(set_table_bucket(val, tab_log2)) * 4;
-            p = b[0] == val || b[1] == val || b[2] == val || b[3] == val;
+            p = cand && (b[0] == val || b[1] == val || b[2] == val || b[3] == val);
             break;
         }
         case LM_VALRANGE: p = ((hb.value(row) ^ L.wm) - L.a) <= L.d; break;

@@ -183,3 +183,25 @@ def test_string_blocks_host_normalisation_matches_the_oracle():
         aa = np.zeros(4, dtype=np.uint8)
         if len(blob) > 8:
             assert kt.harness().kxh_str_match(enc.ctypes.data, len(blob) - 3, 1, aa.ctypes.data, 1, aa.ctypes.data, 0, bits.ctypes.data) < 0
+
+
+@pytest.mark.parametrize("t", [ko.U64, ko.I64, ko.I16])
+def test_in_set_structures_have_no_false_negatives_or_positives(t):
+    """IN / NOT IN on packed and raw blocks goes through two host-built structures: a one-hash prefilter bitmap and the
+    bucketised exact table (kx_host.cpp: build_set_prefilter, build_set_table).  The harness applies them in the order
+    the device does; set sizes from 1 to 20 000 keys, members and non-members, sequential and clustered keys."""
+    rng = np.random.default_rng(13)
+    info = np.iinfo(ko.NP[t])
+    n = 20_000
+    span = min(int(info.max) - 10, 1 << 36)
+    vals = rng.integers(0, span, n, dtype=np.int64).astype(ko.NP[t])
+    for kind in ("bitpack", "raw"):
+        blob = ko.store(kind, t, vals)
+        oc = ko.Container(t, blob)
+        for nset in (1, 7, 64, 1000, 20_000):
+            members = rng.choice(vals, nset // 2 + 1)
+            seq = (np.arange(nset // 2 + 1) + int(vals[0])).astype(ko.NP[t])          # sequential keys: worst case for weak hashes
+            su = ko.as_u64(t, np.unique(np.concatenate([members, seq])))
+            for neg, op in ((False, ko.IN), (True, ko.NI)):
+                got, mode = kt.host_match(t, blob, n, op, values=su)
+                assert (got == oc.match_set(su, negate=neg)).all(), (kind, nset, neg, mode)
