@@ -30,6 +30,8 @@ struct LaneAcc { uint64_t sum, err, mn, mx; };
 
 __device__ __forceinline__ void lane_reset(LaneAcc& a) { a.sum = 0; a.err = 0; a.mn = ~0ull; a.mx = 0; }
 
+// NA = value columns the instantiation carries (2 or 4): fewer columns → fewer registers → more resident warps
+template <int NA>
 __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketParams P) {
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -46,16 +48,16 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
 
         uint32_t cur = 0xffffffffu, cnt = 0;   // window of the rows held in the lane accumulators
         uint64_t cur_lo = 1, cur_hi = 0;       // its key range [cur_lo, cur_hi)
-        LaneAcc acc[MAX_AGGS];
+        LaneAcc acc[NA];
 #pragma unroll
-        for (int j = 0; j < MAX_AGGS; ++j) lane_reset(acc[j]);
+        for (int j = 0; j < NA; ++j) lane_reset(acc[j]);
 
         auto flush = [&]() {
             if (cur == 0xffffffffu || cnt == 0) return;
             BucketCell* cell = P.table + (size_t)cur * ncell;
             atomicAdd(reinterpret_cast<unsigned long long*>(&cell[0].count), (unsigned long long)cnt);
 #pragma unroll
-            for (int j = 0; j < MAX_AGGS; ++j) {
+            for (int j = 0; j < NA; ++j) {
                 if ((uint32_t)j >= P.naggs) break;
                 BucketCell* c = cell + 1 + j;
                 atomicAdd(reinterpret_cast<unsigned long long*>(&c->count), (unsigned long long)cnt);
@@ -73,7 +75,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
         };
 
         // one matching row: find its window (the lane's current window first), fold the values in
-        auto consume = [&](uint64_t key, const uint64_t (&v)[MAX_AGGS]) {
+        auto consume = [&](uint64_t key, const uint64_t (&v)[NA]) {
             if (key < cur_lo || key >= cur_hi) {
                 flush();
                 // time-ordered packs walk the windows in order: try the NEXT window before searching (one load instead of
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
             }
             ++cnt;
 #pragma unroll
-            for (int j = 0; j < MAX_AGGS; ++j) {
+            for (int j = 0; j < NA; ++j) {
                 if ((uint32_t)j >= P.naggs) break;
                 const uint64_t bits = v[j];
                 LaneAcc& A = acc[j];
@@ -119,10 +121,10 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
         // time: the raw words of every matching row (timestamp words + values) are requested back to back and only
         // then decoded and consumed in row order, so a warp pays one memory round trip per U groups, not three per group.
         bool fast = tsv.kind == CK_BITS && tsv.width != 0;
-        const unsigned long long* vptr[MAX_AGGS];
-        uint64_t vbase[MAX_AGGS];
+        const unsigned long long* vptr[NA];
+        uint64_t vbase[NA];
 #pragma unroll
-        for (int j = 0; j < MAX_AGGS; ++j) {
+        for (int j = 0; j < NA; ++j) {
             vptr[j] = nullptr; vbase[j] = 0;
             if ((uint32_t)j < P.naggs) {
                 const ColView& av = P.views[(size_t)pack * ncell + 1 + j];
@@ -155,7 +157,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
             for (uint32_t r0 = my0; r0 < my1; r0 += U) {
                 bool on[U];
                 uint32_t t0[U], t1[U], t2[U];
-                uint64_t val[U][MAX_AGGS];
+                uint64_t val[U][NA];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const uint32_t row = r0 + u;
@@ -166,16 +168,16 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                     t1[u] = on[u] ? __ldg(wp + 1) : 0u;
                     t2[u] = (on[u] && tw > 32u) ? __ldg(wp + 2) : 0u;
 #pragma unroll
-                    for (int j = 0; j < MAX_AGGS; ++j) val[u][j] = (on[u] && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
+                    for (int j = 0; j < NA; ++j) val[u][j] = (on[u] && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (!on[u]) continue;
                     const uint32_t sh = (uint32_t)(((uint64_t)(r0 + u) * tw) & 31u);
                     const uint64_t f = (((uint64_t)__funnelshift_r(t1[u], t2[u], sh) << 32) | __funnelshift_r(t0[u], t1[u], sh)) & tmask;
-                    uint64_t v[MAX_AGGS];
+                    uint64_t v[NA];
 #pragma unroll
-                    for (int j = 0; j < MAX_AGGS; ++j) v[j] = val[u][j] + vbase[j];
+                    for (int j = 0; j < NA; ++j) v[j] = val[u][j] + vbase[j];
                     consume(type_ext(tsv.type, f + tsv.base) ^ P.ts_flip, v);
                 }
             }
@@ -192,7 +194,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                 }
                 if (anyw == 0) continue;                   // warp-uniform: groups without a match cost one load each
                 uint32_t t0[U], t1[U], t2[U];
-                uint64_t val[U][MAX_AGGS];
+                uint64_t val[U][NA];
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     const bool on = (wd[u] >> lane) & 1u;
@@ -203,16 +205,16 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                     t1[u] = on ? __ldg(wp + 1) : 0u;
                     t2[u] = (on && tw > 32u) ? __ldg(wp + 2) : 0u;
 #pragma unroll
-                    for (int j = 0; j < MAX_AGGS; ++j) val[u][j] = (on && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
+                    for (int j = 0; j < NA; ++j) val[u][j] = (on && vptr[j]) ? __ldg(vptr[j] + row) : 0ull;
                 }
 #pragma unroll
                 for (int u = 0; u < U; ++u) {
                     if (!((wd[u] >> lane) & 1u)) continue;
                     const uint32_t sh = (uint32_t)(((uint64_t)((g0 + u) * 32u + lane) * tw) & 31u);
                     const uint64_t f = (((uint64_t)__funnelshift_r(t1[u], t2[u], sh) << 32) | __funnelshift_r(t0[u], t1[u], sh)) & tmask;
-                    uint64_t v[MAX_AGGS];
+                    uint64_t v[NA];
 #pragma unroll
-                    for (int j = 0; j < MAX_AGGS; ++j) v[j] = val[u][j] + vbase[j];
+                    for (int j = 0; j < NA; ++j) v[j] = val[u][j] + vbase[j];
                     consume(type_ext(tsv.type, f + tsv.base) ^ P.ts_flip, v);
                 }
             }
@@ -222,9 +224,9 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                 const uint32_t word = __ldg(words + g);
                 if (!((word >> lane) & 1u)) continue;
                 const uint32_t row = g * 32u + lane;
-                uint64_t v[MAX_AGGS];
+                uint64_t v[NA];
 #pragma unroll
-                for (int j = 0; j < MAX_AGGS; ++j) v[j] = (uint32_t)j < P.naggs ? decode_value_at(P.views[(size_t)pack * ncell + 1 + j], row) : 0ull;
+                for (int j = 0; j < NA; ++j) v[j] = (uint32_t)j < P.naggs ? decode_value_at(P.views[(size_t)pack * ncell + 1 + j], row) : 0ull;
                 consume(decode_value_at(tsv, row) ^ P.ts_flip, v);
             }
         }
@@ -239,7 +241,7 @@ __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketPara
                     for (int off = 16; off > 0; off >>= 1) {
                         cnt += __shfl_down_sync(0xffffffffu, cnt, off);
 #pragma unroll
-                        for (int j = 0; j < MAX_AGGS; ++j) {
+                        for (int j = 0; j < NA; ++j) {
                             if ((uint32_t)j >= P.naggs) break;
                             const uint64_t s2 = __shfl_down_sync(0xffffffffu, acc[j].sum, off), e2 = __shfl_down_sync(0xffffffffu, acc[j].err, off);
                             const uint64_t mn2 = __shfl_down_sync(0xffffffffu, acc[j].mn, off), mx2 = __shfl_down_sync(0xffffffffu, acc[j].mx, off);
@@ -270,7 +272,8 @@ cudaError_t launch_bucket(const BucketParams& P, int num_sms, cudaStream_t strea
     uint32_t grid = (P.njobs + warps_per_block - 1) / warps_per_block;
     const uint32_t cap = (uint32_t)num_sms * 8u;
     if (grid > cap) grid = cap;
-    bucket_kernel<<<grid, BUCKET_THREADS, 0, stream>>>(P);
+    if (P.naggs <= 2) bucket_kernel<2><<<grid, BUCKET_THREADS, 0, stream>>>(P);
+    else bucket_kernel<4><<<grid, BUCKET_THREADS, 0, stream>>>(P);
     return cudaGetLastError();
 }
 
