@@ -30,7 +30,7 @@ struct LaneAcc { uint64_t sum, err, mn, mx; };
 
 __device__ __forceinline__ void lane_reset(LaneAcc& a) { a.sum = 0; a.err = 0; a.mn = ~0ull; a.mx = 0; }
 
-// NA = value columns the instantiation carries (2 or 4): fewer columns → fewer registers → more resident warps
+// NA = value columns the instantiation carries (1, 2 or 4): fewer columns → fewer registers → more resident warps
 template <int NA>
 __global__ void __launch_bounds__(BUCKET_THREADS) bucket_kernel(const BucketParams P) {
     const uint32_t lane = threadIdx.x & 31u;
@@ -272,7 +272,8 @@ cudaError_t launch_bucket(const BucketParams& P, int num_sms, cudaStream_t strea
     uint32_t grid = (P.njobs + warps_per_block - 1) / warps_per_block;
     const uint32_t cap = (uint32_t)num_sms * 8u;
     if (grid > cap) grid = cap;
-    if (P.naggs <= 2) bucket_kernel<2><<<grid, BUCKET_THREADS, 0, stream>>>(P);
+    if (P.naggs <= 1) bucket_kernel<1><<<grid, BUCKET_THREADS, 0, stream>>>(P);
+    else if (P.naggs <= 2) bucket_kernel<2><<<grid, BUCKET_THREADS, 0, stream>>>(P);
     else bucket_kernel<4><<<grid, BUCKET_THREADS, 0, stream>>>(P);
     return cudaGetLastError();
 }

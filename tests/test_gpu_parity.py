@@ -520,6 +520,16 @@ def test_time_bucketed_reduce(ctx, ordered):
         st = ko.bucket_reduce(ko.I64, cols["amount"], ko.I64, cols["ts"], bits, edges, st)
     assert [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res["aggs"][0]] == [(s.count, s.sum_bits, s.min_bits, s.max_bits) for s in st]
     assert int(res["bucket_counts"].sum()) < int(res["counts"].sum())
+    # the kernel has one instantiation per number of value columns (1, 2, 4): two columns and none must agree with the above
+    res2 = ctx.scan_buckets(prog, refs, F_TS, kb.INT64, edges, aggs=[(F_AMT, kb.INT64), (F_ACCT, kb.UINT64)])
+    res0 = ctx.scan_buckets(prog, refs, F_TS, kb.INT64, edges)
+    assert res2["bucket_counts"].tolist() == res["bucket_counts"].tolist() == res0["bucket_counts"].tolist()
+    assert [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res2["aggs"][0]] == [(s.count, s.sum_bits, s.min_bits, s.max_bits) for s in st]
+    sta = None
+    for cols, enc in zip(packs, blobs):
+        bits = ko.Container(ko.I64, enc[F_AMT]).match(ko.GT, ko.scalar_u64(ko.I64, 0), 0)
+        sta = ko.bucket_reduce(ko.U64, cols["acct"], ko.I64, cols["ts"], bits, edges, sta)
+    assert [(g.count, g.sum_bits, g.min_bits, g.max_bits) for g in res2["aggs"][1]] == [(s.count, s.sum_bits, s.min_bits, s.max_bits) for s in sta]
     prog.close()
     for p in range(len(nrows)):
         for f in (F_TS, F_ACCT, F_AMT, F_FAMT):
