@@ -393,7 +393,7 @@ __device__ __forceinline__ uint64_t hs_value(const uint32_t* __restrict__ sw, ui
 template <bool WIDE, bool EXT>
 __device__ __forceinline__ uint32_t leaf_hashset_t(const uint32_t* __restrict__ sw, uint32_t w, uint64_t base, uint32_t sh, bool sgn, uint32_t g0,
                                                    uint32_t Rp, uint32_t lane, const uint32_t* __restrict__ pre, uint32_t pre_log2,
-                                                   const ulonglong2* __restrict__ tab, uint32_t tab_log2) {
+                                                   const ulonglong2* __restrict__ tab, uint32_t tab_log2, uint32_t keep) {
     __builtin_assume(__isShared(sw));
     __builtin_assume(__isShared(pre));
     const uint32_t pre_shift = 32u - pre_log2;
@@ -405,6 +405,7 @@ __device__ __forceinline__ uint32_t leaf_hashset_t(const uint32_t* __restrict__ 
         const uint32_t b = __ballot_sync(0xffffffffu, (pre[idx >> 5] >> (idx & 31u)) & 1u);
         if (lane == it) cand = b;
     }
+    cand &= keep;   // rows the enclosing AND has already ruled out need no verification
     uint32_t word = 0;
     const uint32_t gbit = (g0 + lane) * 32u * w, tab_shift = 32u - tab_log2;
     while (cand) {
@@ -419,13 +420,14 @@ __device__ __forceinline__ uint32_t leaf_hashset_t(const uint32_t* __restrict__ 
 }
 
 __device__ __forceinline__ uint32_t leaf_hashset(const uint32_t* __restrict__ sw, uint32_t w, int type, uint64_t base, uint32_t g0, uint32_t Rp, uint32_t lane,
-                                              const uint32_t* __restrict__ pre, uint32_t pre_log2, const ulonglong2* __restrict__ tab, uint32_t tab_log2) {
+                                              const uint32_t* __restrict__ pre, uint32_t pre_log2, const ulonglong2* __restrict__ tab, uint32_t tab_log2,
+                                              uint32_t keep) {
     const uint32_t sh = 64u - (uint32_t)type_bits(type);
     const bool sgn = type_is_signed(type);
-    if (w > 32u) return sh ? leaf_hashset_t<true, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2)
-                           : leaf_hashset_t<true, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2);
-    return sh ? leaf_hashset_t<false, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2)
-              : leaf_hashset_t<false, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2);
+    if (w > 32u) return sh ? leaf_hashset_t<true, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2, keep)
+                           : leaf_hashset_t<true, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2, keep);
+    return sh ? leaf_hashset_t<false, true>(sw, w, base, sh, sgn, g0, Rp, lane, pre, pre_log2, tab, tab_log2, keep)
+              : leaf_hashset_t<false, false>(sw, w, base, 0u, false, g0, Rp, lane, pre, pre_log2, tab, tab_log2, keep);
 }
 
 // ---- run-end blocks (RunEndContainer.Match* + applyMatch, int_runend.go:224-318): the predicate is
@@ -857,7 +859,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         }
 
         // one leaf for one pass: sw = the leaf's staged stream (or nullptr), g0 = first group of the pass
-        auto eval_leaf = [&](uint32_t li, const uint32_t* sw, uint32_t g0, uint64_t wr) -> uint32_t {
+        // `keep`: rows (bits of this lane's word) whose result matters — the other operand of an enclosing AND
+        auto eval_leaf = [&](uint32_t li, const uint32_t* sw, uint32_t g0, uint64_t wr, uint32_t keep = 0xffffffffu) -> uint32_t {
             const PackLeaf& lf = L[li];
             uint32_t word;
             if constexpr (ONLY32) {
@@ -891,7 +894,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 const ulonglong2* tab = to != 0xffffffffu ? reinterpret_cast<const ulonglong2*>(code_smem + to)
                                                           : reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]);
                 const ColView& hv = P.views[lf.view];
-                word = leaf_hashset(sw, hv.width, hv.type, hv.base, g0, Rp, lane, code_smem + P.hs_smem_off[li], P.pre_log2[li], tab, P.tab_log2[li]);
+                word = leaf_hashset(sw, hv.width, hv.type, hv.base, g0, Rp, lane, code_smem + P.hs_smem_off[li], P.pre_log2[li], tab, P.tab_log2[li], keep);
                 break;
             }
             default: {
@@ -960,10 +963,20 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                         sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                     }
                     const bool inv = lf.neg2 && !lf.fixmode;
+                    // MatchAnd's early-out (match_core.go:44-130), per warp and pass: when this leaf is ANDed with the word
+                    // on top of the stack next, rows that word has ruled out need no work — a pass whose 1024 rows are all
+                    // ruled out skips the leaf altogether (time-range filters on ordered packs rule out whole tiles)
+                    const bool and_next = sp >= 1u && i + 1u < P.npost && P.postfix[i + 1u] == 0xFEu;
+                    const uint32_t* prev = stk + (sp ? sp - 1u : 0u) * pstride + lane;
                     for (uint32_t pass = 0; pass < passes; ++pass) {
                         const uint32_t g0 = gw0 + pass * 32u;
-                        uint32_t word = eval_leaf(op, sw, g0, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u);
-                        dst[pass * 32u] = inv ? ~word : word;
+                        const uint32_t keep = and_next ? prev[pass * 32u] : 0xffffffffu;
+                        uint32_t word = 0;
+                        if (__any_sync(0xffffffffu, keep != 0u)) {
+                            word = eval_leaf(op, sw, g0, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
+                            if (inv) word = ~word;
+                        }
+                        dst[pass * 32u] = word;
                     }
                     if (staged_leaf) release();
                     if (lf.fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
