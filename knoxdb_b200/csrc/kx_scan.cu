@@ -966,11 +966,13 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                     // MatchAnd's early-out (match_core.go:44-130), per warp and pass: when this leaf is ANDed with the word
                     // on top of the stack next, rows that word has ruled out need no work — a pass whose 1024 rows are all
                     // ruled out skips the leaf altogether (time-range filters on ordered packs rule out whole tiles)
+                    // (MatchOr's early-out, :132-215, is the mirror image: rows the other operand already matched.)
                     const bool and_next = sp >= 1u && i + 1u < P.npost && P.postfix[i + 1u] == 0xFEu;
+                    const bool or_next = sp >= 1u && i + 1u < P.npost && P.postfix[i + 1u] == 0xFFu;
                     const uint32_t* prev = stk + (sp ? sp - 1u : 0u) * pstride + lane;
                     for (uint32_t pass = 0; pass < passes; ++pass) {
                         const uint32_t g0 = gw0 + pass * 32u;
-                        const uint32_t keep = and_next ? prev[pass * 32u] : 0xffffffffu;
+                        const uint32_t keep = and_next ? prev[pass * 32u] : (or_next ? ~prev[pass * 32u] : 0xffffffffu);
                         uint32_t word = 0;
                         if (__any_sync(0xffffffffu, keep != 0u)) {
                             word = eval_leaf(op, sw, g0, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
