@@ -796,6 +796,8 @@ static bool load_u32_child(const uint8_t*& p, const uint8_t* end, std::vector<ui
     std::unique_ptr<Container> c;
     long used = parse_container(6 /* uint32 */, p, size_t(end - p), c, err);
     if (used <= 0) { if (err.empty()) err = "bad nested container of a string block"; return false; }
+    // constant / affine children encode any length in a few bytes: refuse lengths no pack can have before materialising
+    if (c->n > (size_t(1) << 26)) { err = "string block: nested container claims " + std::to_string(c->n) + " rows"; return false; }
     std::vector<uint64_t> v;
     if (!decode_container(*c, v, err)) return false;
     if (out.size() < at + v.size()) out.resize(at + v.size());
@@ -815,14 +817,16 @@ int normalize_string_block(const uint8_t* enc, size_t len, StrLayout& out, std::
     switch (enc[0]) {
     case T_STRCONST:   // string_const.go:49-69: uv(N) uv(len) val
         if (!uv(x)) return -6;
+        if (x > (uint64_t(1) << 26)) { err = "string block claims " + std::to_string(x) + " rows"; return -6; }
         v.n = uint32_t(x);
         if (!uv(x) || size_t(end - p) < x) { err = "truncated string block"; return -6; }
         v.is_raw = STR_CONST; v.delta = x; out.bytes = p; out.nbytes = size_t(x);
         break;
     case T_STRFIXED:   // string_fixed.go:59-80: uv(N) uv(sz) N*sz bytes
         if (!uv(x)) return -6;
+        if (x > (uint64_t(1) << 26)) { err = "string block claims " + std::to_string(x) + " rows"; return -6; }
         v.n = uint32_t(x);
-        if (!uv(x) || size_t(end - p) < x * v.n) { err = "truncated string block"; return -6; }
+        if (!uv(x) || (v.n && x > size_t(end - p) / v.n)) { err = "truncated string block"; return -6; }
         v.is_raw = STR_FIXED; v.delta = x; out.bytes = p; out.nbytes = size_t(x) * v.n;
         break;
     case T_STRCOMPACT: {   // string_compact.go:64-96: <Ofs> <Len> uv(len(buf)) buf

@@ -205,3 +205,27 @@ def test_in_set_structures_have_no_false_negatives_or_positives(t):
             for neg, op in ((False, ko.IN), (True, ko.NI)):
                 got, mode = kt.host_match(t, blob, n, op, values=su)
                 assert (got == oc.match_set(su, negate=neg)).all(), (kind, nset, neg, mode)
+
+
+def test_string_block_parser_survives_corrupt_buffers():
+    """kx_block_put parses bytes that come from storage: truncations and bit flips must end in an error code or in a block
+    whose every row lies inside the byte buffer (kxh_str_match checks that) — never in an out-of-bounds read."""
+    rng = np.random.default_rng(17)
+    rows = [bytes(rng.integers(97, 123, int(k), dtype=np.uint8)) for k in rng.integers(0, 12, 400)]
+    fixed = [bytes(r) for r in rng.integers(0, 256, (300, 6), dtype=np.uint8)]
+    H = kt.harness()
+    a = np.frombuffer(b"abc\0", dtype=np.uint8).copy()
+    for kind, data in ((ko.STR_COMPACT, rows), (ko.STR_DICT, rows), (ko.STR_FIXED, fixed), (ko.STR_CONST, [b"constant"] * 50)):
+        blob = np.frombuffer(ko.store_str(kind, data), dtype=np.uint8)
+        bits = np.zeros((1 << 26) // 8 + 64, dtype=np.uint8)   # the parser refuses blocks that claim more than 2^26 rows
+        for trial in range(300):
+            enc = blob.copy()
+            if trial % 3 == 0:
+                enc = enc[: int(rng.integers(1, enc.size))]                      # truncation
+            else:
+                for _ in range(int(rng.integers(1, 4))):                         # bit flips, mostly in the headers
+                    pos = int(rng.integers(0, min(enc.size, 64 if trial % 3 == 1 else enc.size)))
+                    enc[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            enc = np.ascontiguousarray(enc)
+            rc = H.kxh_str_match(enc.ctypes.data, enc.size, 1, a.ctypes.data, 3, a.ctypes.data, 0, bits.ctypes.data) if enc.size else -1
+            assert rc < 0 or rc <= (1 << 26), (kind, trial, rc)
