@@ -229,3 +229,29 @@ def test_string_block_parser_survives_corrupt_buffers():
             enc = np.ascontiguousarray(enc)
             rc = H.kxh_str_match(enc.ctypes.data, enc.size, 1, a.ctypes.data, 3, a.ctypes.data, 0, bits.ctypes.data) if enc.size else -1
             assert rc < 0 or rc <= (1 << 26), (kind, trial, rc)
+
+
+def test_integer_block_parser_survives_corrupt_buffers():
+    """the same for the integer containers: truncated and bit-flipped blocks (headers and payload) decode to an error
+    or to at most `cap` rows, never to an out-of-bounds access"""
+    rng = np.random.default_rng(23)
+    H = kt.harness()
+    n, cap = 3000, 1 << 22
+    vals = rng.integers(-1000, 1000, n).astype(np.int64)
+    dst = np.zeros(cap, dtype=np.uint64)
+    blobs = [ko.store(kind, ko.I64, np.repeat(vals[: n // 5], 5) if kind == "runend" else vals) for kind in ("raw", "bitpack", "dict", "runend", "s8b", "best")]
+    blobs += [ko.store("delta", ko.I64, base=5, delta=3, n=1000), ko.store("const", ko.I64, val=7, n=1000), ko.store("alp", ko.F64, np.round(rng.uniform(0, 99, n), 2))]
+    for bi, blob in enumerate(blobs):
+        blob = np.frombuffer(blob, dtype=np.uint8)
+        t = ko.F64 if bi == len(blobs) - 1 else ko.I64
+        for trial in range(200):
+            enc = blob.copy()
+            if trial % 3 == 0 and enc.size > 2:
+                enc = enc[: int(rng.integers(1, enc.size))]
+            else:
+                for _ in range(int(rng.integers(1, 4))):
+                    pos = int(rng.integers(0, min(enc.size, 48 if trial % 3 == 1 else enc.size)))
+                    enc[pos] ^= np.uint8(1 << int(rng.integers(0, 8)))
+            enc = np.ascontiguousarray(enc)
+            rc = H.kxh_decode(t, enc.ctypes.data, enc.size, dst.ctypes.data, cap)
+            assert rc <= cap, (bi, trial, rc)
