@@ -66,10 +66,6 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity
         __nanosleep(128);
     }
 }
-// asynchronous bulk prefetch of a global range into L2 (no completion tracking)
-__device__ __forceinline__ void tma_prefetch_l2(const void* gsrc, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
-}
 // TMA 1-D bulk copy global → shared, completion signalled on an mbarrier (SASS: UBLKCP)
 __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(smem_dst)),
