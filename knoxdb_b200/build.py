@@ -6,8 +6,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libknoxgpu.so")
-SOURCES = ["kx_scan.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_api.cu", "kx_host.cpp"]
-HEADERS = ["kx_types.h", "kx_kernels.h", "kx_host.h", "kx_xxh3.h", "kx_decode.cuh", os.path.join("..", "..", "include", "knoxgpu.h")]
+SOURCES = ["kx_scan.cu", "kx_general.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_api.cu", "kx_host.cpp"]
+HEADERS = ["kx_types.h", "kx_kernels.h", "kx_host.h", "kx_xxh3.h", "kx_decode.cuh", "kx_leaf.cuh", os.path.join("..", "..", "include", "knoxgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter,-ffp-contract=off", "-shared", "-cudart", "static"]
 
@@ -48,7 +48,7 @@ def build(force=False, verbose=False):
         return OUT
     import json
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + ["-Xptxas", "-v"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
+    cmd = [nvcc] + NVCC_FLAGS + ["-t", "0", "-Xptxas", "-v"] + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", OUT]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         sys.stderr.write(res.stdout + res.stderr)
@@ -57,7 +57,7 @@ def build(force=False, verbose=False):
         sys.stderr.write(res.stderr)
     usage = resource_usage(res.stderr)
     json.dump(usage, open(INFO, "w"), indent=1, sort_keys=True)
-    spilled = sorted(k for k, v in usage.items() if "scan_kernel" in k and (v.get("spill_stores") or v.get("spill_loads")))
+    spilled = sorted(k for k, v in usage.items() if ("scan_kernel" in k or "scan_general_kernel" in k) and (v.get("spill_stores") or v.get("spill_loads")))
     if spilled:
         os.remove(OUT)
         raise RuntimeError("register spills in " + ", ".join(spilled) + " (see knoxdb_b200/build_info.json)")

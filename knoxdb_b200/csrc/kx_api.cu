@@ -64,15 +64,20 @@ struct PinBuf {
     ~PinBuf() { if (p) cudaFreeHost(p); }
 };
 
-// slab allocator for resident blocks: 256 B aligned bump allocation, slabs are released when
-// all their blocks were dropped
-struct Slab { uint8_t* base; size_t cap, used, live; };
+// slab allocator for resident blocks: 256 B aligned extents carved first-fit out of 256 MB slabs; freed extents are
+// coalesced and reused (pack versions come and go: kx_block_put / kx_block_drop churn), a slab is returned to CUDA when
+// its last extent is released.  The HBM budget is enforced on the slabs' CAPACITY (what is really taken from the device).
+struct Slab {
+    uint8_t* base = nullptr; size_t cap = 0, live = 0;
+    std::map<size_t, size_t> free;   // offset -> bytes of every free extent (coalesced)
+};
+struct SlabAlloc { int slab = -1; size_t off = 0, bytes = 0; };
 
 struct StoredBlock {
     ColView view{};
     std::vector<uint64_t> dict;     // host copy of dictionary values (leaf translation)
     std::vector<uint8_t> cstr;      // host copy of a constant string block's value (leaf translation)
-    std::vector<std::pair<int, size_t>> allocs;   // (slab index, bytes)
+    std::vector<SlabAlloc> allocs;
     size_t enc_len = 0;
 };
 
@@ -121,10 +126,10 @@ struct kx_ctx {
 
     std::vector<Slab> slabs;
     std::unordered_map<BlockKey, StoredBlock, BlockKeyHash> store;   // one lookup per (pack, field) and query: O(1)
-    size_t store_enc_bytes = 0, store_dev_bytes = 0;
+    size_t store_enc_bytes = 0, store_dev_bytes = 0, slab_bytes = 0;   // encoded bytes registered, live extent bytes, slab capacity
 
     // scratch (grow only)
-    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_aggtype, d_tmp, d_tmp2, d_misc, d_stage, d_stage2, d_codebits, d_leafbits;
+    DevBuf d_packs, d_leaves, d_views, d_tilepack, d_counts, d_bitsets, d_partials, d_aggout, d_tmp, d_tmp2, d_misc, d_stage, d_stage2, d_codebits, d_leafbits;
     PinBuf h_desc, h_res, h_aux, h_aux2;
     cudaStream_t copy_stream = nullptr;            // kx_scan_host: uploads of batch b + 1 run beside the scan of batch b
     cudaEvent_t ev_copy[2] = {nullptr, nullptr};
@@ -146,7 +151,7 @@ struct kx_stats {
     std::vector<uint8_t> h_bloom_k;
     uint8_t* d_tab = nullptr;              // ptr | mask | k tables on the device
     bool dirty = true;
-    std::vector<std::pair<int, size_t>> allocs;   // slab allocations of the bit arrays
+    std::vector<SlabAlloc> cell_alloc;   // [nfields][npacks] slab extent of each bit array (slab = -1: none)
 };
 
 namespace {
@@ -162,33 +167,69 @@ int fail(kx_ctx* c, int code, const std::string& msg) {
             return fail(ctx, KX_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e__));       \
     } while (0)
 
+// Every C entry point runs inside this guard: host allocation failures and other C++ exceptions become error codes
+// instead of terminating the caller's process (a corrupt block must never take a database down).
+template <typename R, typename F>
+R kx_guarded(kx_ctx* ctx, F&& f) {
+    try { return f(); }
+    catch (const std::bad_alloc&) { return R(fail(ctx, KX_ENOMEM, "out of host memory")); }
+    catch (const std::exception& e) { return R(fail(ctx, KX_EINVAL, std::string("internal error: ") + e.what())); }
+}
+
 // ------------------------------------------------------------------ slab allocation
-int slab_alloc(kx_ctx* ctx, size_t bytes, uint8_t** out, int* slab_idx) {
-    bytes = round_up(bytes, 256);
+int slab_alloc(kx_ctx* ctx, size_t bytes, uint8_t** out, SlabAlloc* rec) {
+    bytes = round_up(std::max<size_t>(bytes, 1), 256);
     for (size_t i = 0; i < ctx->slabs.size(); ++i) {
         Slab& s = ctx->slabs[i];
-        if (s.base && s.cap - s.used >= bytes) {
-            *out = s.base + s.used; s.used += bytes; s.live += bytes; *slab_idx = int(i);
+        if (!s.base) continue;
+        for (auto it = s.free.begin(); it != s.free.end(); ++it) {
+            if (it->second < bytes) continue;
+            const size_t off = it->first, rest = it->second - bytes;
+            s.free.erase(it);
+            if (rest) s.free.emplace(off + bytes, rest);
+            s.live += bytes; ctx->store_dev_bytes += bytes;
+            *out = s.base + off; *rec = SlabAlloc{int(i), off, bytes};
             return KX_OK;
         }
     }
-    if (ctx->budget && ctx->store_dev_bytes + bytes > ctx->budget) return fail(ctx, KX_ENOMEM, "HBM budget exceeded");
-    size_t cap = std::max(bytes, SLAB_BYTES);
+    const size_t cap = std::max(bytes, SLAB_BYTES);
+    if (ctx->budget && ctx->slab_bytes + cap > ctx->budget) {
+        // a last, smaller slab may still fit the budget
+        if (ctx->slab_bytes + bytes > ctx->budget) return fail(ctx, KX_ENOMEM, "HBM budget exceeded");
+    }
+    const size_t take = (ctx->budget && ctx->slab_bytes + cap > ctx->budget) ? bytes : cap;
     uint8_t* p = nullptr;
-    cudaError_t e = cudaMalloc(&p, cap);
+    cudaError_t e = cudaMalloc(&p, take);
     if (e != cudaSuccess) { cudaGetLastError(); return fail(ctx, KX_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e)); }
     size_t idx = ctx->slabs.size();
     for (size_t i = 0; i < ctx->slabs.size(); ++i) if (!ctx->slabs[i].base) { idx = i; break; }
-    if (idx == ctx->slabs.size()) ctx->slabs.push_back(Slab{});
-    ctx->slabs[idx] = Slab{p, cap, bytes, bytes};
-    *out = p; *slab_idx = int(idx);
+    if (idx == ctx->slabs.size()) ctx->slabs.emplace_back();
+    Slab& s = ctx->slabs[idx];
+    s.base = p; s.cap = take; s.live = bytes; s.free.clear();
+    if (take > bytes) s.free.emplace(bytes, take - bytes);
+    ctx->slab_bytes += take; ctx->store_dev_bytes += bytes;
+    *out = p; *rec = SlabAlloc{int(idx), 0, bytes};
     return KX_OK;
 }
 
-void slab_release(kx_ctx* ctx, int idx, size_t bytes) {
-    Slab& s = ctx->slabs[size_t(idx)];
-    s.live -= round_up(bytes, 256);
-    if (s.live == 0 && s.base) { cudaFree(s.base); s = Slab{nullptr, 0, 0, 0}; }
+void slab_release(kx_ctx* ctx, const SlabAlloc& a) {
+    if (a.slab < 0) return;
+    Slab& s = ctx->slabs[size_t(a.slab)];
+    s.live -= a.bytes; ctx->store_dev_bytes -= a.bytes;
+    if (s.live == 0 && s.base) {
+        cudaFree(s.base);
+        ctx->slab_bytes -= s.cap;
+        s = Slab{};
+        return;
+    }
+    size_t off = a.off, bytes = a.bytes;
+    auto nx = s.free.lower_bound(off);
+    if (nx != s.free.begin()) {   // merge with the extent that ends where this one starts
+        auto pv = std::prev(nx);
+        if (pv->first + pv->second == off) { off = pv->first; bytes += pv->second; s.free.erase(pv); }
+    }
+    if (nx != s.free.end() && off + bytes == nx->first) { bytes += nx->second; s.free.erase(nx); }
+    s.free.emplace(off, bytes);
 }
 
 // upload one normalised block; `into` receives device pointers.  Synchronous w.r.t. the host
@@ -196,11 +237,10 @@ void slab_release(kx_ctx* ctx, int idx, size_t bytes) {
 int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
     sb.view = lay.view;
     auto put = [&](const void* src, size_t len, const uint8_t** devp) -> int {
-        uint8_t* d = nullptr; int si = 0;
-        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &si);
+        uint8_t* d = nullptr; SlabAlloc rec;
+        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &rec);
         if (rc) return rc;
-        sb.allocs.push_back({si, len + STREAM_PAD});
-        ctx->store_dev_bytes += round_up(len + STREAM_PAD, 256);
+        sb.allocs.push_back(rec);
         if (len) CK(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ctx->stream));
         // the pad only has to be addressable: rows past the end are masked, over-read bits are cut by the field mask
         *devp = d;
@@ -235,11 +275,10 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
 int upload_string_block(kx_ctx* ctx, const StrLayout& lay, StoredBlock& sb) {
     sb.view = lay.view;
     auto put = [&](const void* src, size_t len, const uint8_t** devp) -> int {
-        uint8_t* d = nullptr; int si = 0;
-        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &si);
+        uint8_t* d = nullptr; SlabAlloc rec;
+        int rc = slab_alloc(ctx, len + STREAM_PAD, &d, &rec);
         if (rc) return rc;
-        sb.allocs.push_back({si, len + STREAM_PAD});
-        ctx->store_dev_bytes += round_up(len + STREAM_PAD, 256);
+        sb.allocs.push_back(rec);
         if (len) CK(cudaMemcpyAsync(d, src, len, cudaMemcpyHostToDevice, ctx->stream));
         *devp = d;
         return KX_OK;
@@ -253,7 +292,7 @@ int upload_string_block(kx_ctx* ctx, const StrLayout& lay, StoredBlock& sb) {
 }
 
 void free_block(kx_ctx* ctx, StoredBlock& sb) {
-    for (auto& a : sb.allocs) { slab_release(ctx, a.first, a.second); ctx->store_dev_bytes -= round_up(a.second, 256); }
+    for (auto& a : sb.allocs) slab_release(ctx, a);
     sb.allocs.clear();
 }
 
@@ -440,31 +479,42 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         if (tab_words * 4u <= hs_tab_limit && (size_t(code_smem_words) + tab_words) * 4u <= 96u * 1024u) { hs_tab_smem_off[l] = code_smem_words; code_smem_words += tab_words; }
     }
     const size_t code_smem_bytes = round_up(size_t(code_smem_words) * 4, 128);
-    // Value columns of the fused reduce can be staged through the ring, agg_chunks (<= 4) stages per tile and column
-    // (KX_AGG_STAGE = never | always | <thr>: stage a tile when recent matches * thr > recent rows).  Measured on B200:
-    // reading matching rows on demand wins below ~1/3 selectivity, bulk staging above.
-    uint32_t agg_chunks = naggs ? 1 : 0, agg_dense_thr = 3;
+    // Value columns of the fused reduce can be staged through the ring: the rows of one pass are cut into agg_kp (1, 2 or 4)
+    // chunks, one ring stage each (KX_AGG_STAGE = never | always | <thr>: stage a tile when recent matches * thr > recent
+    // rows).  Measured on B200: reading matching rows on demand wins below ~1/3 selectivity, bulk staging above.
+    uint32_t agg_kp = naggs ? 1 : 0, agg_dense_thr = 3;
     if (naggs && max_agg_bits) {
         const char* e = getenv("KX_AGG_STAGE");
         if (e && !strcmp(e, "never")) agg_dense_thr = 0xffffffffu;
         else if (e && !strcmp(e, "always")) agg_dense_thr = 0;
         else if (e && atoi(e) > 0) agg_dense_thr = uint32_t(atoi(e));
-        // a chunk (1/8 … 1/1 of the tile's rows of the widest value column) must fit one ring stage
-        max_stage_bits = std::max(max_stage_bits, (max_agg_bits + 7) / 8);
-        while (agg_chunks * max_stage_bits < max_agg_bits) agg_chunks *= 2;
     }
-    // general kernels keep the AND/OR stack of every warp and the tile's final match words in shared memory
-    uint32_t stack_depth = 0;
+    // pure AND / pure OR programs keep their running match words in registers; other trees (and ALP patch corrections)
+    // use a per-warp AND/OR stack in shared memory
+    uint32_t stack_depth = 0, flat_op = 0;
     if (!simple) {
-        uint32_t sp = 0;
-        for (uint8_t op : prog->postfix) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
+        bool all_and = true, all_or = true;
+        for (uint8_t op : prog->postfix) { if (op == KX_OP_AND) all_or = false; else if (op == KX_OP_OR) all_and = false; }
+        if (!any_fix) flat_op = all_and ? 1u : (all_or ? 2u : 0u);
+        if (!flat_op) {
+            uint32_t sp = 0;
+            for (uint8_t op : prog->postfix) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
+        }
     }
-    auto extra_smem_for = [&](uint32_t r) {   // bytes behind the ring: code bitmaps, stacks, final words
-        size_t words = simple ? 0 : size_t(CONSUMER_WARPS) * stack_depth * ((r + 31) / 32) * 32 + (naggs ? size_t(2) * CONSUMER_WARPS * r : 0);
+    const uint32_t desc_words = uint32_t(nleaves * (sizeof(PackLeaf) / 4) + 2 * size_t(naggs) * (sizeof(ColView) / 4));
+    auto extra_smem_for = [&](uint32_t r) {   // bytes behind the ring: code bitmaps, stacks, descriptor caches
+        size_t words = simple ? 0 : size_t(CONSUMER_WARPS) * stack_depth * ((r + 31) / 32) * 32 + size_t(CONSUMER_WARPS) * desc_words;
         return code_smem_bytes + round_up(words * 4, 128);
     };
     const size_t stage_fixed = 32;
-    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
+    // bits per tile row a ring stage must hold: the widest staged leaf column; a staged value chunk (8 warps x 32 G rows,
+    // G = 32 / agg_kp >= 8 groups) must fit as well
+    auto stage_bits_for = [&](uint32_t r) {
+        uint32_t b = max_stage_bits;
+        if (naggs && max_agg_bits && agg_dense_thr != 0xffffffffu) b = std::max(b, (8u * max_agg_bits + r - 1) / r);
+        return b;
+    };
+    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * stage_bits_for(r) + stage_fixed, 128); };
     auto rmax_for = [&](const Geo& g) {
         const size_t fixed = code_smem_bytes / 2 + stage_fixed + 128;
         return g.budget > fixed ? (g.budget - fixed) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)) : size_t(0);
@@ -480,26 +530,32 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
         }
     } else {
-        // general kernels: one stage = one leaf column (or one value-column chunk) of a whole tile.  Large tiles let a
-        // warp run several passes through one leaf's unrolled body before it moves on (instruction-cache reuse, fewer
-        // barrier round trips per row); at least two stages must fit, more are used when the columns are narrow.
+        // general kernel: one stage = one leaf column (or one value chunk) of a whole tile.  The reduce lags one tile behind
+        // the filter, so a tile keeps several stages busy: prefer the largest tile that leaves `want` stages (KX_MIN_STAGES),
+        // else the largest one with two.  More than two value columns run one CTA per SM (accumulators stay in registers).
+        uint32_t want = naggs ? 4 : 3;
+        if (const char* e = getenv("KX_MIN_STAGES")) want = uint32_t(std::max(2, std::min(atoi(e), MAX_STAGES)));
         bool found = false;
-        for (int ctas = 2; ctas >= 1 && !found; --ctas) {
-            for (uint32_t r : {128u, 96u, 64u, 32u}) {
-                size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(ctas) - 128;
-                size_t extra = extra_smem_for(r), sb = stage_bytes_for(r);
-                if (per_cta < extra + 2 * sb) continue;
-                geo.ctas = ctas; R = r;
-                geo.stages = int(std::min<size_t>(agg_chunks > 1 ? 6 : 4, (per_cta - extra) / sb));
-                found = true;
-                break;
+        for (uint32_t need : {want, 2u}) {
+            for (int ctas = naggs > 2 ? 1 : 2; ctas >= 1 && !found; --ctas) {
+                for (uint32_t r : {128u, 96u, 64u, 32u}) {
+                    size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(ctas) - 128;
+                    size_t extra = extra_smem_for(r), sb = stage_bytes_for(r);
+                    if (per_cta < extra + need * sb) continue;
+                    geo.ctas = ctas; R = r;
+                    geo.stages = int(std::min<size_t>(MAX_STAGES, (per_cta - extra) / sb));
+                    found = true;
+                    break;
+                }
             }
+            if (found) break;
         }
         if (!found) return fail(ctx, KX_EUNSUPPORTED, "scan program does not fit the shared memory of one SM");
     }
     if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
         int c = 0, st = 0, r = 0;
-        if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 && (simple ? (r <= 32 || r % 32 == 0) : r % 32 == 0) &&
+        if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 &&
+            (simple ? (r <= 32 || r % 32 == 0) : (r % 32 == 0 && r <= 128 && c <= (naggs > 2 ? 1 : 2))) &&
             128 + size_t(st) * stage_bytes_for(uint32_t(r)) + extra_smem_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
             geo.ctas = c; geo.stages = st; R = uint32_t(r);
         }
@@ -509,6 +565,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     const uint32_t tile_rows = 256 * R;
     const size_t stage_bytes = stage_bytes_for(R);
     const size_t smem_bytes = 128 + size_t(geo.stages) * stage_bytes + extra_smem_for(R);
+    if (naggs) {   // chunks per pass of the reduce: as few as fit a stage
+        agg_kp = 1;
+        while (agg_kp < 4 && (32u / agg_kp) * std::max(max_agg_bits, 1u) > R * stage_bits_for(R)) agg_kp *= 2;
+    }
 
     uint64_t ntiles64 = 0;
     std::vector<uint32_t> tile0(size_t(npacks) + 1);
@@ -558,7 +618,13 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (!sjobs.empty()) std::memcpy(hd + off_sjobs, sjobs.data(), sizeof(StrJob) * sjobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
-    int grid = int(std::min<uint64_t>(ntiles, uint64_t(ctx->num_sms) * geo.ctas));
+    // single-leaf kernel: contiguous tile range per CTA; general kernel: chunks of sched_chunk tiles dealt round-robin
+    // (KX_SCHED_CHUNK), one tile per chunk when there are few tiles
+    uint32_t sched_chunk = 4;
+    if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, atoi(e)));
+    const uint64_t max_grid = uint64_t(ctx->num_sms) * geo.ctas;
+    if (simple || (ntiles + sched_chunk - 1) / sched_chunk < 2 * max_grid) sched_chunk = 1;
+    int grid = int(std::min<uint64_t>((uint64_t(ntiles) + sched_chunk - 1) / sched_chunk, max_grid));
     if (grid < 1) grid = 1;
     if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
@@ -571,8 +637,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     }
     if (naggs) {
         CK(ctx->d_partials.reserve(sizeof(AggPartial) * size_t(grid) * naggs));
-        CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS));
-        CK(ctx->d_aggtype.reserve(16));
+        CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS + 16));   // combined aggregates + the finished-CTA counter
     }
     CK(ctx->h_res.reserve(sizeof(unsigned long long) * size_t(npacks) + sizeof(AggPartial) * MAX_AGGS + 64));
 
@@ -596,13 +661,20 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::memcpy(P.code_smem_off, code_smem_off, sizeof(P.code_smem_off));
     P.code_smem_words = code_smem_words;
     P.code_bitmap_words = code_bitmap_words;
-    P.agg_chunks = agg_chunks;
+    P.agg_kp = agg_kp;
     P.stack_off_words = uint32_t(code_smem_bytes / 4);
     P.stack_depth = stack_depth;
+    P.desc_off_words = P.stack_off_words + uint32_t(CONSUMER_WARPS) * stack_depth * (R / 32) * 32;
+    P.desc_words = desc_words;
+    P.flat_op = flat_op;
+    P.sched_chunk = sched_chunk;
+    P.prod_sleep = getenv("KX_PROD_SLEEP") ? uint32_t(atoi(getenv("KX_PROD_SLEEP"))) : 0u;
     P.agg_dense_thr = agg_dense_thr;
     P.bitsets = dev_bits ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
     P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
     P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
+    P.agg_out = static_cast<AggPartial*>(ctx->d_aggout.p);
+    P.done = naggs ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->d_aggout.p) + sizeof(AggPartial) * MAX_AGGS) : nullptr;
     P.npacks = uint32_t(npacks); P.ntiles = ntiles;
     P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size()); P.naggs = uint32_t(naggs);
     P.R = R; P.tiles_per_pack = uniform ? (ntiles / uint32_t(npacks)) : 0; P.stage_bytes = uint32_t(stage_bytes);
@@ -615,7 +687,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     CK(cudaEventRecord(ctx->ev_start, ctx->stream));
     CK(cudaMemcpyAsync(dd, hd, desc_bytes, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemsetAsync(ctx->d_counts.p, 0, sizeof(unsigned long long) * size_t(npacks), ctx->stream));
-    if (naggs) CK(cudaMemcpyAsync(ctx->d_aggtype.p, P.agg_type, MAX_AGGS, cudaMemcpyHostToDevice, ctx->stream));
+    if (naggs) CK(cudaMemsetAsync(ctx->d_aggout.p, 0, sizeof(AggPartial) * MAX_AGGS + 16, ctx->stream));   // "no match" results, counter = 0
     CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     if (ntiles && leafbits_bytes) CK(cudaMemsetAsync(ctx->d_leafbits.p, 0, leafbits_bytes, ctx->stream));
     if (ntiles && !ajobs.empty()) {
@@ -639,13 +711,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                           static_cast<uint32_t*>(ctx->d_codebits.p), ctx->stream));
         ctx->last_launches++;
     }
-    if (ntiles) { CK(launch_scan(P, grid, smem_bytes, simple, only32, geo.ctas, ctx->stream)); ctx->last_launches++; }
-    if (naggs) {
-        if (ntiles) {
-            CK(launch_finalize(P.partials, uint32_t(grid), uint32_t(naggs), static_cast<const uint8_t*>(ctx->d_aggtype.p),
-                               static_cast<AggPartial*>(ctx->d_aggout.p), ctx->stream));
-            ctx->last_launches++;
-        } else CK(cudaMemsetAsync(ctx->d_aggout.p, 0, sizeof(AggPartial) * MAX_AGGS, ctx->stream));
+    if (ntiles) {
+        if (simple) CK(launch_scan(P, grid, smem_bytes, only32, geo.ctas, ctx->stream));
+        else CK(launch_scan_general(P, grid, smem_bytes, geo.ctas, ctx->stream));
+        ctx->last_launches++;
     }
     CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
 
@@ -835,6 +904,7 @@ extern "C" {
 int kx_abi_version(void) { return KX_ABI_VERSION; }
 
 int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
+    return kx_guarded<int>(nullptr, [&]() -> int {
     if (!out) return KX_EINVAL;
     *out = nullptr;
     int ndev = 0;
@@ -861,6 +931,7 @@ int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
     CK(cudaEventCreateWithFlags(&c->ev_copy[0], cudaEventDisableTiming)); CK(cudaEventCreateWithFlags(&c->ev_copy[1], cudaEventDisableTiming));
     *out = c.release();
     return KX_OK;
+    });
 }
 
 void kx_ctx_destroy(kx_ctx* ctx) {
@@ -889,6 +960,7 @@ void kx_host_free(kx_ctx* ctx, void* p) { if (ctx && p) { cudaSetDevice(ctx->dev
 
 int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, uint8_t block_type, const void* enc, size_t len,
                  uint32_t* nrows_out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!enc || !len) return fail(ctx, KX_EINVAL, "empty block");
@@ -910,9 +982,11 @@ int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, u
     if (nrows_out) *nrows_out = sb.view.n;
     ctx->store.emplace(key, std::move(sb));
     return KX_OK;
+    });
 }
 
 int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->store.find(BlockKey{pack, version, field});
@@ -923,6 +997,7 @@ int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field) 
     free_block(ctx, it->second);
     ctx->store.erase(it);
     return KX_OK;
+    });
 }
 
 int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes) {
@@ -935,10 +1010,12 @@ int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint
 }
 
 int kx_prog_compile(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* postfix, int npost, kx_prog** out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx || !out) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     CK(cudaSetDevice(ctx->device));
     return make_prog(ctx, leaves, nleaves, postfix, npost, out);
+    });
 }
 
 void kx_prog_free(kx_prog* prog) {
@@ -950,6 +1027,7 @@ void kx_prog_free(kx_prog* prog) {
 
 int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint8_t* bitsets, const size_t* bitset_off,
             int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog, true);
@@ -960,6 +1038,7 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
     ScanJob job;
     if ((rc = build_scan_job(ctx, prog, packs, npacks, aggs, naggs, job))) return rc;
     return run_scan(ctx, prog, job, bitsets, bitset_off, counts, aggs, naggs, agg_out);
+    });
 }
 
 }  // extern "C"
@@ -996,6 +1075,7 @@ extern "C" {
 
 int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint32_t* sel, size_t sel_cap, uint64_t* sel_off,
                    int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog, true);
@@ -1010,11 +1090,13 @@ int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, in
     if (rc) return rc;
     if (so.overflow) return fail(ctx, KX_ENOMEM, "kx_scan_select: selection buffer too small (sel_off[npacks] holds the required size)");
     return KX_OK;
+    });
 }
 
 int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint16_t ts_field, uint8_t ts_type,
                     const uint64_t* edges, int nbuckets, const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out,
                     int64_t* counts) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog, true);
@@ -1115,10 +1197,12 @@ int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, i
         }
     }
     return KX_OK;
+    });
 }
 
 int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, uint8_t block_type, const uint32_t* sel,
               const uint64_t* sel_off, void* dst) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (npacks < 0 || (npacks && (!packs || !sel_off))) return fail(ctx, KX_EINVAL, "kx_gather: bad arguments");
@@ -1149,11 +1233,13 @@ int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, 
     CK(cudaMemcpyAsync(dst, d + off_dst, size_t(total) * eb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // views / sel are host temporaries
     return KX_OK;
+    });
 }
 
 int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,
                  const void* const* blocks, const size_t* block_len, uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
                  const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog, true);
@@ -1333,6 +1419,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
     }
     ctx->last_kernel_ms = kms; ctx->last_total_ms = tms; ctx->last_launches = launches;
     return KX_OK;
+    });
 }
 
 int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_agg_out* out) {
@@ -1383,6 +1470,7 @@ int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* la
 
 // ------------------------------------------------------------------ narrow drop-ins
 int64_t kx_cmp(kx_ctx* ctx, uint8_t block_type, uint8_t mode, const void* src, size_t n, uint64_t a, uint64_t b, uint8_t* bits) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int w = type_bits(block_type);
@@ -1400,9 +1488,11 @@ int64_t kx_cmp(kx_ctx* ctx, uint8_t block_type, uint8_t mode, const void* src, s
     int64_t count = 0;
     rc = single_leaf_scan(ctx, tb.sb, block_type, mode, a, b, nullptr, 0, bits, &count);
     return rc ? rc : count;
+    });
 }
 
 int64_t kx_bitpack_cmp(kx_ctx* ctx, uint8_t mode, const void* packed, int log2, uint64_t a, uint64_t b, size_t n, uint8_t* bits) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (log2 < 0 || log2 > 64) return fail(ctx, KX_EINVAL, "kx_bitpack_cmp: bad width");
@@ -1420,6 +1510,7 @@ int64_t kx_bitpack_cmp(kx_ctx* ctx, uint8_t mode, const void* packed, int log2, 
     int64_t count = 0;
     rc = single_leaf_scan(ctx, tb.sb, KX_UINT64, mode, a, b, nullptr, 0, bits, &count);
     return rc ? rc : count;
+    });
 }
 
 static int decode_view_to_host(kx_ctx* ctx, const ColView& v, void* dst) {
@@ -1433,6 +1524,7 @@ static int decode_view_to_host(kx_ctx* ctx, const ColView& v, void* dst) {
 }
 
 int kx_bitpack_decode(kx_ctx* ctx, uint8_t block_type, const void* packed, int log2, uint64_t minv, size_t n, void* dst) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (log2 < 0 || log2 > 64 || type_bits(block_type) == 0 || type_is_float(block_type)) return fail(ctx, KX_EINVAL, "kx_bitpack_decode: bad arguments");
@@ -1447,10 +1539,12 @@ int kx_bitpack_decode(kx_ctx* ctx, uint8_t block_type, const void* packed, int l
     int rc = upload_block(ctx, lay, tb.sb);
     if (rc) return rc;
     return decode_view_to_host(ctx, tb.sb.view, dst);
+    });
 }
 
 int64_t kx_container_match(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, uint8_t mode, uint64_t a, uint64_t b,
                            const uint64_t* set, uint32_t nset, uint8_t* bits) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!enc || !len) return fail(ctx, KX_EINVAL, "kx_container_match: empty block");
@@ -1466,9 +1560,11 @@ int64_t kx_container_match(kx_ctx* ctx, uint8_t block_type, const void* enc, siz
     int64_t count = 0;
     rc = single_leaf_scan(ctx, tb.sb, block_type, mode, a, b, set, nset, bits, &count);
     return rc ? rc : count;
+    });
 }
 
 int kx_container_decode(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t len, void* dst, size_t dst_cap_rows) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (!enc || !len) return fail(ctx, KX_EINVAL, "kx_container_decode: empty block");
@@ -1482,6 +1578,7 @@ int kx_container_decode(kx_ctx* ctx, uint8_t block_type, const void* enc, size_t
     rc = upload_block(ctx, lay, tb.sb);
     if (rc) return rc;
     return decode_view_to_host(ctx, tb.sb.view, dst);
+    });
 }
 
 // ------------------------------------------------------------------ bitsets
@@ -1494,6 +1591,7 @@ static int upload_bits(kx_ctx* ctx, DevBuf& buf, const uint8_t* src, size_t nbit
 }
 
 int kx_bitset_op(kx_ctx* ctx, int op, uint8_t* dst, const uint8_t* src, size_t nbits, int* any, int* all) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (op < KX_BIT_AND || op > KX_BIT_XOR) return fail(ctx, KX_EINVAL, "kx_bitset_op: bad op");
@@ -1513,9 +1611,11 @@ int kx_bitset_op(kx_ctx* ctx, int op, uint8_t* dst, const uint8_t* src, size_t n
     if (any) *any = flags[0] != 0;
     if (all) *all = flags[1] == 0;
     return KX_OK;
+    });
 }
 
 int kx_bitset_neg(kx_ctx* ctx, uint8_t* buf, size_t nbits) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (nbits == 0) return KX_OK;
@@ -1527,9 +1627,11 @@ int kx_bitset_neg(kx_ctx* ctx, uint8_t* buf, size_t nbits) {
     CK(cudaMemcpyAsync(buf, ctx->d_tmp.p, (nbits + 7) / 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return KX_OK;
+    });
 }
 
 int64_t kx_bitset_popcount(kx_ctx* ctx, const uint8_t* buf, size_t nbits) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (nbits == 0) return 0;
@@ -1544,9 +1646,11 @@ int64_t kx_bitset_popcount(kx_ctx* ctx, const uint8_t* buf, size_t nbits) {
     CK(cudaMemcpyAsync(&c, ctx->d_misc.p, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return int64_t(c);
+    });
 }
 
 int64_t kx_bitset_indexes(kx_ctx* ctx, const uint8_t* buf, size_t nbits, uint32_t* dst) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (nbits == 0) return 0;
@@ -1568,11 +1672,13 @@ int64_t kx_bitset_indexes(kx_ctx* ctx, const uint8_t* buf, size_t nbits, uint32_
         CK(cudaStreamSynchronize(ctx->stream));
     }
     return int64_t(c);
+    });
 }
 
 // ------------------------------------------------------------------ pruning
 int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* mins, const uint64_t* maxs, const void* const* blooms,
                  const size_t* bloom_len, const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog);
@@ -1641,6 +1747,7 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* m
     CK(cudaMemcpyAsync(&c, d + off_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return int64_t(c);
+    });
 }
 
 // ------------------------------------------------------------------ resident statistics index
@@ -1651,6 +1758,7 @@ static int bloom_pow2(size_t v) {   // bloom.pow2 (internal/filter/bloom/bloom.g
 
 int kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8_t* field_types, int nfields,
                     const uint64_t* mins, const uint64_t* maxs, kx_stats** out) {
+    return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx || !out) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     *out = nullptr;
@@ -1662,7 +1770,7 @@ int kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8
     st->ctx = ctx; st->npacks = npacks; st->nfields = nfields;
     st->fields.assign(fields, fields + nfields); st->types.assign(field_types, field_types + nfields);
     const size_t cells = size_t(npacks) * nfields;
-    st->h_bloom_ptr.assign(cells, 0); st->h_bloom_mask.assign(cells, 0); st->h_bloom_k.assign(cells, 0);
+    st->h_bloom_ptr.assign(cells, 0); st->h_bloom_mask.assign(cells, 0); st->h_bloom_k.assign(cells, 0); st->cell_alloc.assign(cells, SlabAlloc{});
     CK(cudaMalloc(&st->d_mins, cells * 8));
     CK(cudaMalloc(&st->d_maxs, cells * 8));
     CK(cudaMalloc(&st->d_tab, cells * 13 + 64));
@@ -1671,6 +1779,7 @@ int kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8
     CK(cudaStreamSynchronize(ctx->stream));
     *out = st.release();
     return KX_OK;
+    });
 }
 
 void kx_stats_free(kx_stats* st) {
@@ -1679,7 +1788,7 @@ void kx_stats_free(kx_stats* st) {
     std::lock_guard<std::mutex> lk(ctx->mu);
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
-    for (auto& a : st->allocs) { slab_release(ctx, a.first, a.second); ctx->store_dev_bytes -= round_up(a.second, 256); }
+    for (auto& a : st->cell_alloc) slab_release(ctx, a);
     cudaFree(st->d_mins); cudaFree(st->d_maxs); cudaFree(st->d_tab);
     delete st;
 }
@@ -1690,11 +1799,13 @@ static int stats_bloom_slot(kx_stats* st, size_t cell, size_t m, uint32_t k, uin
     if (st->h_bloom_ptr[cell] && st->h_bloom_mask[cell] == uint32_t(m - 1)) {
         *bits = reinterpret_cast<uint8_t*>(uintptr_t(st->h_bloom_ptr[cell]));
     } else {
-        uint8_t* d = nullptr; int si = 0;
-        int rc = slab_alloc(ctx, m / 8 + 64, &d, &si);
+        // a filter of another size replaces the old one: allocate first, then give the old extent back
+        uint8_t* d = nullptr; SlabAlloc rec;
+        int rc = slab_alloc(ctx, m / 8 + 64, &d, &rec);
         if (rc) return rc;
-        st->allocs.push_back({si, m / 8 + 64});
-        ctx->store_dev_bytes += round_up(m / 8 + 64, 256);
+        if (st->h_bloom_ptr[cell]) CK(cudaStreamSynchronize(ctx->stream));   // no probe kernel may still read the old bits
+        slab_release(ctx, st->cell_alloc[cell]);
+        st->cell_alloc[cell] = rec;
         *bits = d;
     }
     st->h_bloom_ptr[cell] = uint64_t(uintptr_t(*bits)); st->h_bloom_mask[cell] = uint32_t(m - 1); st->h_bloom_k[cell] = uint8_t(k);
@@ -1703,6 +1814,7 @@ static int stats_bloom_slot(kx_stats* st, size_t cell, size_t m, uint32_t k, uin
 }
 
 int kx_stats_put_bloom(kx_stats* st, int field_index, int pack_index, const void* bloom, size_t len) {
+    return kx_guarded<int>(st ? st->ctx : nullptr, [&]() -> int {
     if (!st) return KX_EINVAL;
     kx_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1718,10 +1830,12 @@ int kx_stats_put_bloom(kx_stats* st, int field_index, int pack_index, const void
     CK(cudaMemcpyAsync(bits, b + 1, len - 1, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // the caller's buffer is not retained
     return KX_OK;
+    });
 }
 
 int kx_stats_build_bloom(kx_stats* st, int field_index, int pack_index, uint8_t block_type, const void* values, const uint32_t* offsets,
                          size_t n, int cardinality, int factor) {
+    return kx_guarded<int>(st ? st->ctx : nullptr, [&]() -> int {
     if (!st) return KX_EINVAL;
     kx_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1747,9 +1861,11 @@ int kx_stats_build_bloom(kx_stats* st, int field_index, int pack_index, uint8_t 
     CK(launch_bloom_build(dv, eb ? nullptr : doff, n, eb, reinterpret_cast<uint32_t*>(bits), uint32_t(m - 1), 4, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // host buffers are not retained
     return KX_OK;
+    });
 }
 
 int kx_stats_get_bloom(kx_stats* st, int field_index, int pack_index, void* out, size_t cap, size_t* len) {
+    return kx_guarded<int>(st ? st->ctx : nullptr, [&]() -> int {
     if (!st) return KX_EINVAL;
     kx_ctx* ctx = st->ctx;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1767,9 +1883,11 @@ int kx_stats_get_bloom(kx_stats* st, int field_index, int pack_index, void* out,
     CK(cudaMemcpyAsync(o + 1, reinterpret_cast<const void*>(uintptr_t(st->h_bloom_ptr[cell])), need - 1, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return KX_OK;
+    });
 }
 
 int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* st, const uint64_t* hashes, const uint32_t* hash_off, uint8_t* out) {
+    return kx_guarded<int64_t>(ctx, [&]() -> int64_t {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     int rc = check_prog_job(ctx, prog);
@@ -1844,6 +1962,7 @@ int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* st, const uin
     if (cudaEventElapsedTime(&ms, ctx->ev_start, ctx->ev_end) == cudaSuccess) ctx->last_total_ms = ms;
     ctx->last_launches = 1;
     return int64_t(c);
+    });
 }
 
 uint64_t kx_hash_value(uint8_t block_type, uint64_t pattern) {

@@ -1,0 +1,684 @@
+// kx_general.cu — the multi-leaf filter + fused reduce kernel of libknoxgpu (sm_100a).
+//
+// Replaces (reference, CPU, one pack at a time): filter.Match / MatchAnd / MatchOr
+// (internal/operator/filter/match_core.go:14-215) over the container matchers of internal/encode, followed by
+// CountResult / StreamResult + Reducer.Reduce (internal/query/result.go:44-152, internal/reducer/reducer.go:138-314)
+// — for a whole batch of packs in one launch, without a decoded column vector or a match bitset ever touching HBM
+// (bitsets are written only when the caller asks for them).
+//
+// Structure (persistent CTAs, 8 consumer warps + 1 TMA producer warp):
+//   * Tiles of 256 R rows (R = 32 … 128 groups of 32 rows per consumer warp) are dealt to the CTAs in chunks of
+//     `sched_chunk` consecutive tiles, round-robin: a static schedule (results are reproducible run to run) that
+//     spreads the expensive and the cheap regions of every pack (e.g. the part of a time-ordered pack a range
+//     predicate selects) over all SMs.
+//   * The producer streams, per tile, one ring stage per staged leaf column (postfix order) with TMA bulk copies.
+//   * Every consumer warp evaluates the leaves of its R groups pass by pass ("bitset word per lane").  Pure AND / pure
+//     OR programs keep the running words in registers (MatchAnd / MatchOr early-outs per warp and pass); other trees
+//     use a per-warp AND/OR stack in shared memory.
+//   * The reduce lags ONE tile behind the filter: the match words of tile t stay in registers while the warp filters
+//     tile t + 1, and the value rows of tile t arrive meanwhile — prefetched towards L2 by the lanes that own the
+//     matches (sparse tiles, read on demand afterwards) or streamed through the ring by the producer behind the leaf
+//     columns of tile t + 1 (dense tiles; the producer decides from the selectivity the consumers report).  No CTA
+//     barrier, no shared match words: a warp reduces the rows it filtered.
+//   * Lane ↔ row assignment of the reduce (the same whether the values were staged or are read on demand, so a tile
+//     gives bit-identical partial sums either way): a pass (32 groups) is cut into KP ∈ {1, 2, 4} chunks of G = 32 / KP
+//     groups; in chunk q lane l owns G consecutive rows of group q G + l mod G, starting at row (l / G) G of the
+//     group, and visits them in ascending order rotated by l mod G — the rotation makes the shared-memory reads of a
+//     staged chunk bank-conflict free (lane-private 64-bit rows, 256 B apart before the rotation).
+//   * Per-thread accumulators live in registers (the kernel is instantiated per number of value columns); a fixed
+//     shuffle tree and a fixed warp order give the per-CTA partial; the CTA that finishes last combines the partials of
+//     all CTAs in CTA order (fixed topology: bit-reproducible), so a query is ONE launch.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "kx_leaf.cuh"
+
+namespace kx {
+
+namespace {
+
+// static tile schedule shared by the producer and the consumers of a CTA
+struct TileSched {
+    const ScanParams& P;
+    uint32_t tile_rows;
+    uint32_t t = 0, t_stop = 0, cidx = 0;
+    uint32_t pack = 0, chunk = 0, pack_tiles = 0;
+    PackInfo pi{};
+
+    __device__ __forceinline__ TileSched(const ScanParams& p, uint32_t tr) : P(p), tile_rows(tr) {}
+    __device__ __forceinline__ bool open_chunk() {
+        const uint64_t t0 = (uint64_t)cidx * P.sched_chunk;
+        if (t0 >= P.ntiles) return false;
+        t = (uint32_t)t0;
+        t_stop = (uint32_t)min((uint64_t)P.ntiles, t0 + P.sched_chunk);
+        pack = P.tile_pack ? __ldg(P.tile_pack + t) : t / P.tiles_per_pack;
+        pi = P.packs[pack];
+        pack_tiles = (pi.n + tile_rows - 1) / tile_rows;
+        chunk = t - pi.tile0;
+        return true;
+    }
+    __device__ __forceinline__ bool start() { cidx = blockIdx.x; return open_chunk(); }
+    __device__ __forceinline__ bool next() {
+        if (++t < t_stop) {
+            if (++chunk >= pack_tiles) {
+                do { ++pack; pi = P.packs[pack]; } while (pi.n == 0);
+                pack_tiles = (pi.n + tile_rows - 1) / tile_rows;
+                chunk = 0;
+            }
+            return true;
+        }
+        cidx += gridDim.x;
+        return open_chunk();
+    }
+};
+
+__device__ __forceinline__ uint32_t get4(const uint32_t (&w)[4], uint32_t i) {
+    uint32_t x = w[0];
+    if (i == 1) x = w[1];
+    if (i == 2) x = w[2];
+    if (i == 3) x = w[3];
+    return x;
+}
+__device__ __forceinline__ void set4(uint32_t (&w)[4], uint32_t i, uint32_t x) {
+    if (i == 0) w[0] = x;
+    if (i == 1) w[1] = x;
+    if (i == 2) w[2] = x;
+    if (i == 3) w[3] = x;
+}
+
+template <bool F64>
+__device__ __forceinline__ void acc_raw64(AggAcc& A, uint64_t raw, uint64_t base, uint64_t flip) {
+    if (F64) {
+        double x = as_f64(raw), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
+        double t = sum + x;
+        err += (fabs(sum) >= fabs(x)) ? ((sum - t) + x) : ((x - t) + sum);
+        A.s[0] = as_u64(t); A.s[1] = as_u64(err);
+        if (x < as_f64(A.s[2])) A.s[2] = raw;
+        if (x > as_f64(A.s[3])) A.s[3] = raw;
+    } else {
+        uint64_t v = raw + base, k = v ^ flip;
+        A.s[0] += v;
+        if (k < A.s[1]) A.s[1] = k;
+        if (k > A.s[2]) A.s[2] = k;
+    }
+}
+
+// the rows of one reduce chunk this lane owns, as a bit mask rotated by `rot`: bit s ↔ row (s + rot) mod G of the lane's
+// G-row range
+__device__ __forceinline__ uint32_t lane_rows(uint32_t word, uint32_t sub, uint32_t G, uint32_t rot) {
+    if (G == 32u) return __funnelshift_r(word, word, rot);
+    const uint32_t m = (1u << G) - 1u, bits = (word >> (sub * G)) & m;
+    return ((bits >> rot) | (bits << (G - rot))) & m;
+}
+
+// raw 64-bit value column, staged chunk in shared memory: positional walk (all lanes at the same step: conflict free)
+template <bool F64>
+__device__ __forceinline__ void reduce_staged_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, uint32_t r, uint32_t G, uint32_t rot,
+                                                    uint64_t base, uint64_t flip) {
+    __builtin_assume(__isShared(vp));
+    if (!__any_sync(0xffffffffu, r != 0u)) return;
+#pragma unroll 4
+    for (uint32_t s = 0; s < G; ++s) {
+        if ((r >> s) & 1u) acc_raw64<F64>(A, vp[(s + rot) & (G - 1u)], base, flip);
+    }
+}
+
+// raw 64-bit value column read on demand from global memory: only matching rows, four loads in flight per lane
+template <bool F64>
+__device__ __forceinline__ void reduce_global_raw64(AggAcc& A, const unsigned long long* __restrict__ gp, uint32_t r, uint32_t G, uint32_t rot,
+                                                    uint64_t base, uint64_t flip) {
+    while (r) {
+        uint64_t val[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = r != 0u;
+            const uint32_t s = ok[u] ? (uint32_t)__ffs((int)r) - 1u : 0u;
+            r &= r - 1u;
+            val[u] = ok[u] ? __ldg(gp + ((s + rot) & (G - 1u))) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) acc_raw64<F64>(A, val[u], base, flip);
+    }
+}
+
+// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types, ALP): decode per row.
+// row0 = pack row of the lane's range, srow0 = the same row relative to the staged slice (`staged` may be nullptr)
+__device__ __forceinline__ void reduce_generic(AggAcc& A, const ColView& v, int type, uint32_t row0, const uint32_t* staged, uint32_t srow0, uint32_t r,
+                                               uint32_t G, uint32_t rot) {
+    while (r) {
+        const uint32_t s = (uint32_t)__ffs((int)r) - 1u;
+        r &= r - 1u;
+        const uint32_t b = (s + rot) & (G - 1u);
+        agg_add(A, type, decode_value(v, row0 + b, staged, srow0 + b));
+    }
+}
+
+// r ⊕= p for two partial aggregates (p follows r in CTA order); invalid partials (no match) are neutral
+__device__ __forceinline__ void partial_merge(AggPartial& r, const AggPartial& p, int type) {
+    if (!p.valid) return;
+    if (!r.valid) { r = p; return; }
+    r.count += p.count;
+    if (type == 9) {
+        double s = as_f64(r.sum), e = r.err;
+        fsum_merge(s, e, as_f64(p.sum), p.err);
+        r.sum = as_u64(s); r.err = e;
+        if (as_f64(p.mn) < as_f64(r.mn)) r.mn = p.mn;
+        if (as_f64(p.mx) > as_f64(r.mx)) r.mx = p.mx;
+    } else {
+        r.sum += p.sum;
+        if (p.mn < r.mn) r.mn = p.mn;
+        if (p.mx > r.mx) r.mx = p.mx;
+    }
+}
+
+}  // namespace
+
+// NA = value columns reduced by this instantiation (0: filter only; the NA = 4 instantiation also serves 3)
+template <int NA, int MINB>
+__global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const ScanParams P) {
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint8_t* stage_base = smem + 128;
+    __shared__ AggAcc warp_acc[CONSUMER_WARPS];
+    __shared__ unsigned long long warp_cnt[CONSUMER_WARPS];
+    __shared__ unsigned int sm_match, sm_wtiles;   // matches / (warp, tile) pairs finished so far: selectivity feedback for the producer
+    __shared__ uint32_t stage_flag[MAX_STAGES];    // per ring slot: 1 = the value columns of the PREVIOUS tile follow this tile's leaf stages
+    constexpr bool AGG = NA > 0;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    const uint32_t R = P.R, tile_rows = R * 32u * CONSUMER_WARPS, nstages = P.stages, passes = R >> 5;
+    const uint32_t nl = P.nleaves, na = AGG ? P.naggs : 0u;
+    uint32_t* code_smem = reinterpret_cast<uint32_t*>(stage_base + (size_t)nstages * P.stage_bytes);   // bitmaps / prefilters / small tables
+    // reduce chunks: KP per pass, G groups each; a staged chunk = one slice of G groups (32 G rows) per consumer warp
+    const uint32_t KP = AGG ? P.agg_kp : 1u, G = 32u / KP, lgG = 31u - (uint32_t)__clz((int)G);
+
+    if (threadIdx.x == 0) {
+        sm_match = 0; sm_wtiles = 0;
+        for (uint32_t s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    TileSched ts(P, tile_rows);
+
+    if (warp == CONSUMER_WARPS) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0 && ts.start()) {
+            uint32_t s = 0, ph = 0;
+            auto acquire = [&]() {
+                if (P.prod_sleep) mbar_wait_relaxed(&empty_bar[s], ph ^ 1u); else mbar_wait(&empty_bar[s], ph ^ 1u);   // slot released by all consumer warps
+            };
+            auto advance = [&]() { if (++s == nstages) { s = 0; ph ^= 1u; } };
+            auto load_stream = [&](const uint8_t* data, size_t off, uint32_t w, uint32_t rows, uint32_t flag) {
+                acquire();
+                if (!data) w = 0;
+                const uint32_t bytes = w ? ((((rows * w + 7u) >> 3) + 15u) & ~15u) : 0u;
+                stage_flag[s] = flag;                       // published by the arrive below (release) / the consumers' wait (acquire)
+                mbar_expect_tx(&full_bar[s], bytes);        // arrive (count 1) + expected bytes
+                if (bytes) tma_load_1d(stage_base + (size_t)s * P.stage_bytes, data + off, bytes, &full_bar[s]);
+                advance();
+            };
+            // the value columns of one (finished) tile: per column, pass and chunk one stage of eight slices
+            auto load_values = [&](uint32_t vpack, uint32_t row0, uint32_t n) {
+                for (uint32_t j = 0; j < na; ++j) {
+                    const ColView& v = P.views[P.agg_view0 + (size_t)vpack * na + j];
+                    if (!agg_stageable(v)) continue;
+                    const uint32_t slice_rows = 32u * G, slice_bytes = slice_rows / 8u * v.width;
+                    for (uint32_t pass = 0; pass < passes; ++pass) {
+                        for (uint32_t q = 0; q < KP; ++q) {
+                            acquire();
+                            stage_flag[s] = 1u;
+                            uint32_t total = 0;
+                            for (uint32_t w = 0; w < CONSUMER_WARPS; ++w) {
+                                const uint32_t r0 = row0 + ((w * R + pass * 32u + q * G) << 5);
+                                const uint32_t nr = r0 < n ? min(slice_rows, n - r0) : 0u;
+                                total += nr ? ((((nr * v.width + 7u) >> 3) + 15u) & ~15u) : 0u;
+                            }
+                            mbar_expect_tx(&full_bar[s], total);
+                            for (uint32_t w = 0; w < CONSUMER_WARPS; ++w) {
+                                const uint32_t r0 = row0 + ((w * R + pass * 32u + q * G) << 5);
+                                const uint32_t nr = r0 < n ? min(slice_rows, n - r0) : 0u;
+                                if (!nr) continue;
+                                const uint32_t bytes = (((nr * v.width + 7u) >> 3) + 15u) & ~15u;
+                                tma_load_1d(stage_base + (size_t)s * P.stage_bytes + (size_t)w * slice_bytes, v.data + (size_t)(r0 >> 3) * v.width, bytes, &full_bar[s]);
+                            }
+                            advance();
+                        }
+                    }
+                }
+            };
+            uint32_t pf_m0 = 0, pf_d0 = 0;   // selectivity feedback snapshot
+            bool dense = P.agg_dense_thr == 0;
+            auto decide = [&]() -> uint32_t {
+                if (P.agg_dense_thr != 0 && P.agg_dense_thr != 0xffffffffu) {
+                    const uint32_t m = *(volatile unsigned int*)&sm_match, d = *(volatile unsigned int*)&sm_wtiles;
+                    if (d - pf_d0 >= CONSUMER_WARPS) {
+                        dense = (uint64_t)(m - pf_m0) * P.agg_dense_thr * CONSUMER_WARPS > (uint64_t)(d - pf_d0) * tile_rows;
+                        pf_m0 = m; pf_d0 = d;
+                    }
+                }
+                return dense ? 1u : 0u;
+            };
+            bool have_prev = false;
+            uint32_t prev_pack = 0, prev_row0 = 0, prev_n = 0;
+            do {
+                const uint32_t row0 = ts.chunk * tile_rows, rows = min(tile_rows, ts.pi.n - row0);
+                const PackLeaf* L = P.leaves + (size_t)ts.pack * nl;
+                const size_t tile_byte0 = (size_t)ts.chunk * (tile_rows / 8u);   // * width = first byte of the tile in a stream
+                const uint32_t flag = (AGG && have_prev) ? decide() : 0u;
+                bool told = false;
+                for (uint32_t i = 0; i < P.npost; ++i) {
+                    const uint32_t op = P.postfix[i];
+                    if (op >= 0x80u) continue;
+                    if (L[op].data) { load_stream(L[op].data, tile_byte0 * L[op].width, L[op].width, rows, flag); told = true; }
+                    if (L[op].fixmode) { load_stream(L[op].fix, tile_byte0, 1u, rows, flag); told = true; }      // ALP patch correction stream
+                }
+                if constexpr (AGG) {
+                    if (!told) load_stream(nullptr, 0, 0u, 0u, flag);   // no leaf column is staged: an empty stage carries the decision
+                    if (flag) load_values(prev_pack, prev_row0, prev_n);
+                    prev_pack = ts.pack; prev_row0 = row0; prev_n = ts.pi.n; have_prev = true;
+                }
+            } while (ts.next());
+            if constexpr (AGG) {
+                if (have_prev) {   // the value columns of the last tile
+                    const uint32_t flag = decide();
+                    load_stream(nullptr, 0, 0u, 0u, flag);
+                    if (flag) load_values(prev_pack, prev_row0, prev_n);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumers: unpack + filter + reduce =====================
+    AggAcc acc[AGG ? NA : 1];
+#pragma unroll
+    for (int j = 0; j < (AGG ? NA : 1); ++j) acc[j] = agg_identity(AGG ? P.agg_type[j] : 0);
+    unsigned long long nmatch = 0;   // matches this thread accounted for (per-CTA totals only)
+    uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
+    const uint32_t gw0 = warp * R;   // first group (of the tile) of this warp
+    // shared memory behind the bitmaps: the warp's AND/OR stack (general trees only) and its descriptor cache
+    // (the current pack's leaves; the value-column views of the current and the previous pack)
+    uint32_t* stk = code_smem + P.stack_off_words + warp * (P.stack_depth * passes * 32u);
+    uint32_t* wdesc = code_smem + P.desc_off_words + warp * P.desc_words;
+    const PackLeaf* L = reinterpret_cast<const PackLeaf*>(wdesc);
+    const ColView* AV = reinterpret_cast<const ColView*>(wdesc + nl * (sizeof(PackLeaf) / 4u));   // [2][na]
+    uint32_t cur_pack = 0xffffffffu, desc_sel = 0;
+
+    auto flush_count = [&](uint32_t pk) {
+        uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
+        if (P.counts && lane == 0 && c) atomicAdd(P.counts + pk, (unsigned long long)c);
+        lane_cnt = 0;
+    };
+
+    {
+        // hash-set leaves: prefilter bitmaps (and small exact tables) are the same for every pack — copy them into shared
+        // memory once per CTA
+        bool any = false;
+        for (uint32_t l = 0; l < nl; ++l) {
+            if (!P.pre_log2[l]) continue;
+            any = true;
+            const uint32_t npre = (1u << P.pre_log2[l]) >> 5;
+            for (uint32_t i = threadIdx.x; i < npre; i += CONSUMER_WARPS * 32u) code_smem[P.hs_smem_off[l] + i] = __ldg(P.set_pre + P.pre_off[l] + i);
+            if (P.hs_tab_smem_off[l] != 0xffffffffu) {
+                const uint32_t nt = 8u << P.tab_log2[l];
+                const uint32_t* src = reinterpret_cast<const uint32_t*>(P.set_tabs + P.tab_off[l]);
+                for (uint32_t i = threadIdx.x; i < nt; i += CONSUMER_WARPS * 32u) code_smem[P.hs_tab_smem_off[l] + i] = __ldg(src + i);
+            }
+        }
+        if (any) asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+    }
+
+    uint32_t s = 0, ph = 0;
+    auto release = [&]() {   // this warp is done with ring stage s
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (++s == nstages) { s = 0; ph ^= 1u; }
+    };
+
+    // ---- the lagging reduce: match words of the previous tile (registers), where its rows are, which views describe it
+    uint32_t wprev[4] = {0u, 0u, 0u, 0u};
+    bool have_prev = false;
+    uint32_t prev_row0 = 0, prev_sel = 0;
+    auto reduce_prev = [&](bool dense) {
+        const uint32_t gl = lane & (G - 1u), sub = lane >> lgG, rot = gl;
+#pragma unroll
+        for (int j = 0; j < (AGG ? NA : 0); ++j) {
+            if ((uint32_t)j >= na) break;
+            const ColView& v = AV[prev_sel * na + j];
+            const int type = P.agg_type[j];
+            const bool staged = dense && agg_stageable(v);
+            const bool raw64 = v.kind == CK_BITS && v.width == 64;
+            const uint64_t flip = type_is_signed(type) ? 0x8000000000000000ull : 0ull;
+            const uint32_t slice_bytes = 4u * G * v.width;   // 32 G rows of the column
+            AggAcc a = acc[j];
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                const uint32_t wp = get4(wprev, pass);
+                for (uint32_t q = 0; q < KP; ++q) {
+                    if (staged) mbar_wait(&full_bar[s], ph);
+                    const uint32_t word = KP == 1u ? wp : __shfl_sync(0xffffffffu, wp, q * G + gl);
+                    const uint32_t r = lane_rows(word, sub, G, rot);
+                    const uint32_t srow0 = gl * 32u + sub * G;                                               // first row of the lane's range inside the warp's slice
+                    const uint32_t row0 = prev_row0 + ((gw0 + pass * 32u + q * G) << 5) + srow0;            // … and inside the pack
+                    const uint8_t* stg = stage_base + (size_t)s * P.stage_bytes + (size_t)warp * slice_bytes;
+                    if (raw64) {
+                        if (staged) {
+                            const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(stg) + srow0;
+                            if (type == 9) reduce_staged_raw64<true>(a, vp, r, G, rot, 0ull, 0ull);
+                            else reduce_staged_raw64<false>(a, vp, r, G, rot, v.base, flip);
+                        } else {
+                            const unsigned long long* gp = reinterpret_cast<const unsigned long long*>(v.data) + row0;
+                            if (type == 9) reduce_global_raw64<true>(a, gp, r, G, rot, 0ull, 0ull);
+                            else reduce_global_raw64<false>(a, gp, r, G, rot, v.base, flip);
+                        }
+                    } else {
+                        reduce_generic(a, v, type, row0, staged ? reinterpret_cast<const uint32_t*>(stg) : nullptr, srow0, r, G, rot);
+                    }
+                    if (staged) release();
+                }
+            }
+            acc[j] = a;
+        }
+    };
+
+    if (ts.start()) {
+        do {
+            const uint32_t pack = ts.pack, n = ts.pi.n;
+            const uint32_t pack_row0 = ts.chunk * tile_rows;          // first row of the tile within the pack
+            if (pack != cur_pack) {
+                // new pack: this warp caches its descriptors; the consumers copy its code bitmaps (built by codeset_kernel)
+                if (cur_pack != 0xffffffffu) flush_count(cur_pack);
+                __syncwarp();
+                desc_sel ^= 1u;
+                {
+                    const uint32_t* src = reinterpret_cast<const uint32_t*>(P.leaves + (size_t)pack * nl);
+                    for (uint32_t i = lane; i < nl * (uint32_t)(sizeof(PackLeaf) / 4u); i += 32u) wdesc[i] = __ldg(src + i);
+                    if (AGG) {
+                        const uint32_t* vsrc = reinterpret_cast<const uint32_t*>(P.views + P.agg_view0 + (size_t)pack * na);
+                        uint32_t* vdst = wdesc + nl * (uint32_t)(sizeof(PackLeaf) / 4u) + desc_sel * na * (uint32_t)(sizeof(ColView) / 4u);
+                        for (uint32_t i = lane; i < na * (uint32_t)(sizeof(ColView) / 4u); i += 32u) vdst[i] = __ldg(vsrc + i);
+                    }
+                }
+                __syncwarp();
+                if (P.code_bitmap_words) {
+                    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));   // everybody is done with the previous pack's bitmaps
+                    for (uint32_t l = 0; l < nl; ++l) {
+                        if (L[l].mode != LM_CODESET) continue;
+                        const uint32_t nw = (((1u << L[l].width) + (uint32_t)L[l].wm + 31u) >> 5) + 1u;
+                        const uint32_t* src = P.code_bits + L[l].a;
+                        uint32_t* dst = code_smem + P.code_smem_off[l];
+                        for (uint32_t i = threadIdx.x; i < nw; i += CONSUMER_WARPS * 32u) dst[i] = __ldg(src + i);
+                    }
+                    asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+                }
+                cur_pack = pack;
+            }
+            const LeafEnv env{P, code_smem, n, pack_row0};
+
+            // ---- leaves and the AND/OR program.  Every staged leaf column is one ring stage holding the column's slice of
+            // the whole tile; a leaf is evaluated for ALL passes of the warp before the next one is touched (its unrolled
+            // body stays hot in the instruction cache).
+            uint32_t w[4] = {0u, 0u, 0u, 0u};
+            bool told = false, dense = false;   // the producer's staging decision (previous tile) arrives with the tile's first ring stage
+            if (P.flat_op) {
+                // pure AND (1) / pure OR (2) program: running words in registers.  MatchAnd's early-out (match_core.go:44-130),
+                // per warp and pass: rows the words so far have ruled out need no work — a pass whose 1024 rows are all ruled
+                // out skips the leaf altogether (time-range filters on ordered packs rule out whole tiles); MatchOr's
+                // early-out (:132-215) is the mirror image: rows that already matched.
+                const bool is_and = P.flat_op == 1u;
+                bool first = true;
+                for (uint32_t i = 0; i < P.npost; ++i) {
+                    const uint32_t op = P.postfix[i];
+                    if (op >= 0x80u) continue;
+                    const PackLeaf& lf = L[op];
+                    const uint32_t* sw = nullptr;
+                    const bool staged_leaf = lf.data != nullptr;
+                    if (staged_leaf) {
+                        mbar_wait(&full_bar[s], ph);
+                        if (!told) { dense = stage_flag[s] != 0; told = true; }
+                        sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+                    }
+                    for (uint32_t pass = 0; pass < passes; ++pass) {
+                        const uint32_t g0 = gw0 + pass * 32u;
+                        const uint32_t cur = get4(w, pass);
+                        const uint32_t keep = first ? 0xffffffffu : (is_and ? cur : ~cur);
+                        if (__any_sync(0xffffffffu, keep != 0u)) {
+                            uint32_t word = eval_leaf(env, lf, op, sw, g0, 32u, lane, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
+                            if (lf.neg2) word = ~word;
+                            set4(w, pass, first ? word : (is_and ? (cur & word) : (cur | word)));
+                        }
+                    }
+                    if (staged_leaf) release();
+                    first = false;
+                }
+            } else {
+                // general tree: the per-pass words wait on the warp's stack in shared memory (lane-private columns)
+                const uint32_t pstride = passes * 32u;
+                uint32_t sp = 0;
+                for (uint32_t i = 0; i < P.npost; ++i) {
+                    const uint32_t op = P.postfix[i];
+                    if (op < 0x80u) {
+                        const PackLeaf& lf = L[op];
+                        uint32_t* dst = stk + sp * pstride + lane;
+                        const uint32_t* sw = nullptr;
+                        const bool staged_leaf = lf.data != nullptr;
+                        if (staged_leaf) {
+                            mbar_wait(&full_bar[s], ph);
+                            if (!told) { dense = stage_flag[s] != 0; told = true; }
+                            sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+                        }
+                        const bool inv = lf.neg2 && !lf.fixmode;
+                        const bool and_next = sp >= 1u && i + 1u < P.npost && P.postfix[i + 1u] == 0xFEu;
+                        const bool or_next = sp >= 1u && i + 1u < P.npost && P.postfix[i + 1u] == 0xFFu;
+                        const uint32_t* prev = stk + (sp ? sp - 1u : 0u) * pstride + lane;
+                        for (uint32_t pass = 0; pass < passes; ++pass) {
+                            const uint32_t g0 = gw0 + pass * 32u;
+                            const uint32_t keep = and_next ? prev[pass * 32u] : (or_next ? ~prev[pass * 32u] : 0xffffffffu);
+                            uint32_t word = 0;
+                            if (__any_sync(0xffffffffu, keep != 0u)) {
+                                word = eval_leaf(env, lf, op, sw, g0, 32u, lane, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
+                                if (inv) word = ~word;
+                            }
+                            dst[pass * 32u] = word;
+                        }
+                        if (staged_leaf) release();
+                        if (lf.fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
+                            mbar_wait(&full_bar[s], ph);
+                            if (!told) { dense = stage_flag[s] != 0; told = true; }
+                            const uint32_t* fw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+                            __builtin_assume(__isShared(fw));
+                            for (uint32_t pass = 0; pass < passes; ++pass) {
+                                const uint32_t fx = fw[gw0 + pass * 32u + lane];
+                                uint32_t word = dst[pass * 32u];
+                                word = lf.fixmode == FIX_OR_PRED ? (word | fx) : (word & ~fx);
+                                dst[pass * 32u] = lf.neg2 ? ~word : word;
+                            }
+                            release();
+                        }
+                        ++sp;
+                    } else {
+                        --sp;
+                        uint32_t* x = stk + (sp - 1u) * pstride + lane;
+                        const uint32_t* y = stk + sp * pstride + lane;
+                        for (uint32_t pass = 0; pass < passes; ++pass)
+                            x[pass * 32u] = (op == 0xFEu) ? (x[pass * 32u] & y[pass * 32u]) : (x[pass * 32u] | y[pass * 32u]);
+                    }
+                }
+                for (uint32_t pass = 0; pass < passes; ++pass) set4(w, pass, stk[pass * 32u + lane]);
+            }
+
+            // ---- outputs of the tile: tail masking (match_core.go semantics: tail bits zero), bitset words (coalesced 128 B
+            // per warp), per-pack match count
+            uint32_t tile_cnt = 0;
+            for (uint32_t pass = 0; pass < passes; ++pass) {
+                const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(gw0 + pass * 32u + lane) * 32u;
+                uint32_t valid = 0;
+                if (wr < n) {
+                    const uint32_t left = n - (uint32_t)wr;
+                    valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+                }
+                const uint32_t word = get4(w, pass) & valid;
+                set4(w, pass, word);
+                if (P.bitsets && wr < n) *reinterpret_cast<uint32_t*>(P.bitsets + ts.pi.bitset_off + (wr >> 3)) = word;
+                tile_cnt += __popc(word);
+            }
+            lane_cnt += tile_cnt;
+
+            if constexpr (AGG) {
+                nmatch += tile_cnt;   // per-CTA totals only: any partition of the matches over threads will do
+                const uint32_t c = __reduce_add_sync(0xffffffffu, tile_cnt);
+                if (lane == 0) { atomicAdd(&sm_match, c); atomicAdd(&sm_wtiles, 1u); }   // selectivity feedback for the producer
+                if (!told) {   // no leaf column was staged: the decision sits in an empty stage
+                    mbar_wait(&full_bar[s], ph);
+                    dense = stage_flag[s] != 0;
+                    release();
+                }
+                // the previous tile's value rows have had this tile's filter time to arrive
+                if (have_prev) reduce_prev(dense);
+                // this tile's turn comes after the next filter: start pulling its matching rows towards L2 now (raw 64-bit
+                // columns; skipped while the producer is staging whole tiles anyway)
+                if (c && !dense) {
+#pragma unroll
+                    for (int j = 0; j < NA; ++j) {
+                        if ((uint32_t)j >= na) break;
+                        const ColView& v = AV[desc_sel * na + j];
+                        if (v.kind != CK_BITS || v.width != 64) continue;
+                        for (uint32_t pass = 0; pass < passes; ++pass) {
+                            uint32_t word = get4(w, pass);
+                            if (!word) continue;
+                            const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + pack_row0 + (gw0 + pass * 32u + lane) * 32u;
+                            if (__popc(word) <= 4) {
+                                while (word) {
+                                    const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
+                                    word &= word - 1u;
+                                    asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + b));
+                                }
+                            } else {
+#pragma unroll
+                                for (int k = 0; k < 8; ++k)
+                                    if ((word >> (4 * k)) & 0xfu) asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + 4 * k));
+                            }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int p = 0; p < 4; ++p) wprev[p] = w[p];
+                prev_row0 = pack_row0; prev_sel = desc_sel; have_prev = true;
+            }
+        } while (ts.next());
+        flush_count(cur_pack);
+        if constexpr (AGG) {
+            // the value columns of the last tile: the producer's decision arrives in an empty stage
+            mbar_wait(&full_bar[s], ph);
+            const bool dense = stage_flag[s] != 0;
+            release();
+            reduce_prev(dense);
+        }
+    }
+
+    if constexpr (AGG) {
+        // ---- per-CTA partial aggregates: fixed-order tree inside the warp, then across warps
+#pragma unroll
+        for (int j = 0; j < NA; ++j) {
+            if ((uint32_t)j >= na) break;
+            const int type = P.agg_type[j];
+            AggAcc a = acc[j];
+            unsigned long long c = nmatch;
+            for (int off = 16; off > 0; off >>= 1) {
+                AggAcc b;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) b.s[q] = __shfl_down_sync(0xffffffffu, a.s[q], off);
+                unsigned long long cb = __shfl_down_sync(0xffffffffu, c, off);
+                agg_merge(a, b, type);
+                c += cb;
+            }
+            if (lane == 0) { warp_acc[warp] = a; warp_cnt[warp] = c; }
+            // consumer-only barrier (the producer warp has exited)
+            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+            if (threadIdx.x == 0) {
+                AggAcc r = warp_acc[0];
+                unsigned long long rc = warp_cnt[0];
+                for (int q = 1; q < CONSUMER_WARPS; ++q) { agg_merge(r, warp_acc[q], type); rc += warp_cnt[q]; }
+                AggPartial o;
+                o.count = rc; o.valid = rc != 0; o.pad = 0;
+                if (type == 9) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
+                else { o.sum = r.s[0]; o.err = 0.0; o.mn = r.s[1]; o.mx = r.s[2]; }
+                P.partials[(size_t)blockIdx.x * na + j] = o;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+        }
+
+        // ---- the CTA that finishes last combines the per-CTA partials: every thread merges a contiguous run of them in
+        // index order, a fixed shuffle tree and a fixed warp order do the rest — the topology depends on the grid size
+        // only, so the result is bit-reproducible whichever CTA happens to be last (no separate launch, no serial walk)
+        __shared__ uint32_t sm_last;
+        __shared__ AggPartial warp_part[CONSUMER_WARPS];
+        if (threadIdx.x == 0) {
+            __threadfence();
+            sm_last = atomicAdd(P.done, 1u) == gridDim.x - 1u;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+        if (sm_last) {
+            __threadfence();
+            const uint32_t nparts = gridDim.x, T = CONSUMER_WARPS * 32u, per = (nparts + T - 1u) / T;
+            for (uint32_t j = 0; j < na; ++j) {
+                const int type = P.agg_type[j];
+                AggPartial r{};
+                const uint32_t i1 = min(nparts, (threadIdx.x + 1u) * per);
+                for (uint32_t i = threadIdx.x * per; i < i1; ++i) {
+                    const ulonglong2* src = reinterpret_cast<const ulonglong2*>(P.partials + (size_t)i * na + j);
+                    union { AggPartial p; ulonglong2 q[3]; } u;
+                    u.q[0] = __ldcg(src); u.q[1] = __ldcg(src + 1); u.q[2] = __ldcg(src + 2);
+                    partial_merge(r, u.p, type);
+                }
+                for (int off = 1; off < 32; off <<= 1) {   // lane l absorbs lane l + off: partials stay in index order
+                    AggPartial o;
+                    o.count = __shfl_down_sync(0xffffffffu, r.count, off);
+                    o.sum = __shfl_down_sync(0xffffffffu, r.sum, off);
+                    o.err = __shfl_down_sync(0xffffffffu, r.err, off);
+                    o.mn = __shfl_down_sync(0xffffffffu, r.mn, off);
+                    o.mx = __shfl_down_sync(0xffffffffu, r.mx, off);
+                    o.valid = __shfl_down_sync(0xffffffffu, r.valid, off);
+                    o.pad = 0;
+                    if ((lane & (2u * off - 1u)) == 0u) partial_merge(r, o, type);
+                }
+                if (lane == 0) warp_part[warp] = r;
+                asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+                if (threadIdx.x == 0) {
+                    AggPartial f = warp_part[0];
+                    for (int q = 1; q < CONSUMER_WARPS; ++q) partial_merge(f, warp_part[q], type);
+                    P.agg_out[j] = f;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
+            }
+        }
+    }
+}
+
+cudaError_t launch_scan_general(const ScanParams& P, int grid, size_t smem_bytes, int ctas_per_sm, cudaStream_t stream) {
+    int variant;
+    void (*kern)(const ScanParams);
+    if (P.naggs == 0) { variant = 0; kern = scan_general_kernel<0, 2>; }
+    else if (P.naggs == 1 && ctas_per_sm >= 2) { variant = 1; kern = scan_general_kernel<1, 2>; }
+    else if (P.naggs == 2 && ctas_per_sm >= 2) { variant = 2; kern = scan_general_kernel<2, 2>; }
+    else { variant = 3; kern = scan_general_kernel<4, 1>; }
+    // function attributes are per device and sticky: set them once per (device, variant)
+    static bool configured[64][4] = {};
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= 64 || !configured[dev][variant]) {
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SCAN_MAX_DYN_SMEM);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        if (dev >= 0 && dev < 64) configured[dev][variant] = true;
+    }
+    kern<<<grid, SCAN_THREADS, smem_bytes, stream>>>(P);
+    return cudaGetLastError();
+}
+
+}  // namespace kx

@@ -107,8 +107,10 @@ uint64_t bit_field(const uint8_t* stream, size_t stream_len, size_t row, int w) 
 
 }  // namespace
 
-long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err) {
+long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err, int depth) {
     if (len < 1) { err = "empty container"; return -1; }
+    // the reference nests at most three levels (dictionary / run-end / ALP over a leaf container): a deeper chain is corrupt
+    if (depth > 3) { err = "containers nested too deeply"; return -1; }
     auto c = std::make_unique<Container>();
     c->ctype = buf[0];
     c->type = type;
@@ -119,6 +121,8 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
         break;
     case T_DELTA:
         c->val = type_ext(type, r.uv()); c->delta = type_ext(type, r.uv()); c->n = r.uv();
+        // the matchers divide by Delta (int_delta.go:149-449: Go panics on a zero divisor); the encoder only emits Delta != 0
+        if (r.ok && c->delta == 0) { err = "delta container with zero delta"; return -1; }
         break;
     case T_BITPACK:
         c->val = type_ext(type, r.uv()); c->log2 = int(r.uv()); c->n = r.uv();
@@ -141,10 +145,10 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
     }
     case T_DICT:
     case T_RUNEND: {
-        long k = parse_container(type, r.p, r.left, c->child[0], err);
+        long k = parse_container(type, r.p, r.left, c->child[0], err, depth + 1);
         if (k < 0) return -1;
         r.take(size_t(k));
-        k = parse_container(c->ctype == T_DICT ? 7 /*uint16*/ : 6 /*uint32*/, r.p, r.left, c->child[1], err);
+        k = parse_container(c->ctype == T_DICT ? 7 /*uint16*/ : 6 /*uint32*/, r.p, r.left, c->child[1], err, depth + 1);
         if (k < 0) return -1;
         r.take(size_t(k));
         if (c->ctype == T_DICT) c->n = c->child[1]->n;
@@ -164,14 +168,14 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
         if (!r.ok || !fl) { err = "truncated container"; return -1; }
         c->alp_flags = *fl;
         if (c->alp_e > 20 || c->alp_f > 23) { err = "ALP: exponent out of range"; return -1; }
-        long k = parse_container(1 /*int64*/, r.p, r.left, c->child[0], err);
+        long k = parse_container(1 /*int64*/, r.p, r.left, c->child[0], err, depth + 1);
         if (k < 0) return -1;
         r.take(size_t(k));
         if (c->alp_flags & 1) {
-            k = parse_container(type, r.p, r.left, c->child[1], err);
+            k = parse_container(type, r.p, r.left, c->child[1], err, depth + 1);
             if (k < 0) return -1;
             r.take(size_t(k));
-            k = parse_container(6 /*uint32*/, r.p, r.left, c->child[2], err);
+            k = parse_container(6 /*uint32*/, r.p, r.left, c->child[2], err, depth + 1);
             if (k < 0) return -1;
             r.take(size_t(k));
             if (c->child[1]->n != c->child[2]->n) { err = "ALP: patches/positions length mismatch"; return -1; }
@@ -190,6 +194,8 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
 }
 
 bool decode_container(const Container& c, std::vector<uint64_t>& out, std::string& err) {
+    // constant / affine containers encode any length in a few bytes: refuse lengths no pack can have before materialising
+    if (c.n > MAX_MATERIALIZED_ROWS) { err = "container claims " + std::to_string(c.n) + " rows"; return false; }
     out.resize(c.n);
     switch (c.ctype) {
     case T_CONST:
@@ -938,7 +944,7 @@ void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& l
         }
         if (v.kind == CK_BITS && leaf.has_table && !type_is_float(t)) {
             // int_bitpack.go:249-291 / int_raw.go:339-380: decoded value looked up in the leaf's hash table
-            o.mode = LM_HASHSET; o.data = v.data; o.width = v.width;
+            o.mode = LM_HASHSET; o.data = v.data; o.width = v.width; o.a = v.base; o.fop = v.type;   // For and element type travel with the leaf
             return;
         }
         // decoded value ∈ sorted set, binary search per row (affine blocks) / per run (run-end blocks)

@@ -31,7 +31,11 @@ struct Container {
     std::unique_ptr<Container> child[3];   // dict: {Dict, Codes}; runend: {Values, Ends}; alp: {Values, Patches, Positions}
     int alp_e = 0, alp_f = 0, alp_flags = 0;
 };
-long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err);
+// `depth`: nesting level (children are parsed with depth + 1; more than three levels is refused as corrupt)
+long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<Container>& out, std::string& err, int depth = 0);
+// the largest container decode_container materialises on the host (dictionaries, run values / ends, patches, string index
+// arrays, legacy simple8b streams): 2^26 rows — far above any pack (<= 4 Mi rows); larger claims are refused as corrupt
+constexpr size_t MAX_MATERIALIZED_ROWS = size_t(1) << 26;
 bool decode_container(const Container& c, std::vector<uint64_t>& out, std::string& err);
 
 // normalised block, ready for upload

@@ -114,12 +114,12 @@ cudaError_t launch_prune_stats(const PruneStatsParams& P, cudaStream_t stream);
 cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, uint64_t n, int elem_bytes, uint32_t* bits, uint32_t mask,
                                uint32_t k, cudaStream_t stream);
 
-cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool simple, bool only32, int ctas_per_sm, cudaStream_t stream);
+// single-leaf scans without aggregates (kx_scan.cu) / everything else (kx_general.cu)
+cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_scan_general(const ScanParams& P, int grid, size_t smem_bytes, int ctas_per_sm, cudaStream_t stream);
 cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, uint32_t max_set, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);
-cudaError_t launch_finalize(const AggPartial* parts, uint32_t nparts, uint32_t naggs, const uint8_t* agg_type_dev,
-                            AggPartial* out, cudaStream_t stream);
 cudaError_t launch_bitset_op(uint32_t* dst, const uint32_t* src, uint64_t nbits, int op, unsigned int* flags, cudaStream_t stream);
 cudaError_t launch_bitset_neg(uint32_t* buf, uint64_t nbits, cudaStream_t stream);
 cudaError_t launch_bitset_popcount(const uint32_t* buf, uint64_t nbits, unsigned long long* out, cudaStream_t stream);

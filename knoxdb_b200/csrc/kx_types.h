@@ -134,6 +134,8 @@ struct ScanParams {
     uint8_t*  bitsets;         // nullable
     unsigned long long* counts; // [npacks] nullable
     AggPartial* partials;      // [gridDim.x][naggs]
+    AggPartial* agg_out;       // [naggs] combined by the CTA that finishes last
+    uint32_t* done;            // CTAs finished so far (zeroed before the launch)
     uint32_t npacks, ntiles;
     uint32_t nleaves, npost, naggs;
     uint32_t R;                // 32-row groups per warp per tile; tile rows = 256 * R; R > 32 => multiple of 32
@@ -160,13 +162,18 @@ struct ScanParams {
     uint32_t code_smem_off[MAX_LEAVES];
     uint32_t code_smem_words;
     uint32_t code_bitmap_words;       // words of that area holding per-pack code bitmaps (0: nothing to reload per pack)
-    // general kernels: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp) and the CTA's
-    // double-buffered final match words, both behind the code bitmaps (word offset from their start)
+    // general kernel: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp; trees that are not a
+    // pure AND / OR chain) and per-warp descriptor caches, both behind the code bitmaps (word offsets from their start)
     uint32_t stack_off_words;
     uint32_t stack_depth;
-    // value columns of the fused reduce: a tile's slice of one value column is split into agg_chunks (1, 2, 4 or 8)
-    // chunks, each reduced by all consumer warps; tiles that match densely get the chunks staged through the ring
-    uint32_t agg_chunks;       // >= 1 whenever naggs > 0
+    uint32_t desc_off_words;
+    uint32_t desc_words;       // words per warp: nleaves PackLeaf + 2 x naggs ColView
+    uint32_t flat_op;          // 1: the program is a pure AND of its leaves, 2: a pure OR, 0: general tree
+    uint32_t sched_chunk;      // tiles per scheduling chunk (chunks are dealt round-robin to the CTAs)
+    uint32_t prod_sleep;       // producer polls released ring slots with a sleep in between (tuning hook)
+    // value columns of the fused reduce: the rows of one pass (32 groups per warp) are reduced in agg_kp (1, 2 or 4) chunks;
+    // tiles that match densely get the chunks staged through the ring (one slice of 32 / agg_kp groups per warp and stage)
+    uint32_t agg_kp;           // >= 1 whenever naggs > 0
     uint32_t agg_dense_thr;    // stage the tile when recent matches * thr > recent rows; 0 = always, 0xffffffff = never
 };
 

@@ -126,7 +126,7 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
             break;
         }
         case LM_HASHSET: {   // leaf_hashset: compare with the four slots of the home bucket
-            uint64_t val = type_ext(v.type, field_at(hb.stream(), hb.stream_len(), row, L.width) + v.base);
+            uint64_t val = type_ext(L.fop, field_at(hb.stream(), hb.stream_len(), row, L.width) + L.a);   // For / element type travel with the leaf
             const uint32_t idx = set_hash32(val) >> (32 - pre_log2);
             const bool cand = (pre[idx >> 5] >> (idx & 31u)) & 1u;   // phase 1: prefilter (no false negatives allowed)
             const uint64_t* b = tab.data() + size_t(set_table_bucket(val, tab_log2)) * 4;

@@ -61,7 +61,7 @@ def test_product_does_not_reference_the_oracle():
     """the product path must never route through oracle/ (no CPU fallback)"""
     for dirpath, _, files in os.walk(os.path.join(ROOT, "knoxdb_b200")):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".h")):
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh")):
                 src = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "knox_oracle" not in src and "libknox_oracle" not in src and "import oracle" not in src, f
 
@@ -76,7 +76,8 @@ def test_scan_kernels_do_not_spill():
     if not os.path.exists(kbuild.INFO):
         kbuild.build(force=True)
     usage = json.load(open(kbuild.INFO))
-    scans = {k: v for k, v in usage.items() if "scan_kernel" in k and "exclusive" not in k}
-    assert len(scans) >= 5, sorted(usage)
+    scans = {k: v for k, v in usage.items() if ("scan_kernel" in k or "scan_general_kernel" in k) and "exclusive" not in k}
+    assert len(scans) >= 7, sorted(usage)
     for k, v in scans.items():
-        assert v["spill_stores"] == 0 and v["spill_loads"] == 0 and v["registers"] <= 96, (k, v)
+        one_cta = "ILi4ELi1E" in k   # the instantiation for 3-4 value columns runs one CTA per SM (accumulators in registers)
+        assert v["spill_stores"] == 0 and v["spill_loads"] == 0 and v.get("stack", 0) == 0 and v["registers"] <= (224 if one_cta else 96), (k, v)

@@ -255,3 +255,55 @@ def test_integer_block_parser_survives_corrupt_buffers():
             enc = np.ascontiguousarray(enc)
             rc = H.kxh_decode(t, enc.ctypes.data, enc.size, dst.ctypes.data, cap)
             assert rc <= cap, (bi, trial, rc)
+
+
+def _uv(x):
+    """pkg/num/varint.go PutUvarint"""
+    if x <= 240:
+        return bytes([x])
+    if x <= 2287:
+        y = x - 240
+        return bytes([241 + (y >> 8), y & 0xFF])
+    if x <= 67823:
+        y = x - 2288
+        return bytes([249, y >> 8, y & 0xFF])
+    nb = max(3, (x.bit_length() + 7) // 8)
+    return bytes([247 + nb]) + x.to_bytes(nb, "big")
+
+
+def test_crafted_block_headers_are_refused_not_fatal():
+    """headers a bit flip cannot reach but a corrupt store can hold: a few bytes that claim billions of rows in a nested
+    child (materialised on the host), a chain of nested dictionary ids (recursion), an affine block with a zero delta
+    (the matchers divide by it).  All must end in an error code (rc < 0): no allocation of gigabytes, no stack overflow,
+    no SIGFPE."""
+    H = kt.harness()
+    dst = np.zeros(1 << 16, dtype=np.uint64)
+    bits = np.zeros((1 << 16) // 8, dtype=np.uint8)
+    huge = (1 << 32) - 1
+    const_huge = bytes([1]) + _uv(5) + _uv(huge)                     # IntConstant, 4 G rows in 7 bytes
+    delta_huge = bytes([2]) + _uv(0) + _uv(1) + _uv(huge)            # IntDelta
+    codes_ok = bytes([1]) + _uv(0) + _uv(100)                        # 100 codes, all 0
+    crafted = {
+        "dict over a 4 G-row constant dictionary": bytes([5]) + const_huge + codes_ok,
+        "dict with 4 G constant codes": bytes([5]) + bytes([1]) + _uv(7) + _uv(1) + const_huge,
+        "run-end with 4 G affine ends": bytes([3]) + const_huge + delta_huge,
+        "nested dictionary ids": bytes([5]) * 100000,
+        "nested run-end ids": bytes([3]) * 100000,
+        "dict of dict of dict of dict": bytes([5, 5, 5, 5, 5]) + codes_ok * 8,
+        "zero delta": bytes([2]) + _uv(10) + _uv(0) + _uv(1000),
+        "s8b with 4 G rows and no words": bytes([6]) + _uv(0) + _uv(huge) + _uv(0),
+    }
+    for name, blob in crafted.items():
+        enc = np.frombuffer(blob, dtype=np.uint8).copy()
+        rc = H.kxh_decode(ko.I64, enc.ctypes.data, enc.size, dst.ctypes.data, dst.size)
+        assert rc < 0, (name, rc)
+        rc = H.kxh_match(ko.I64, enc.ctypes.data, enc.size, ko.LT, 5, 0, None, 0, bits.ctypes.data, None)
+        assert rc < 0, (name, rc)
+    # ALP: 4 G patch positions behind a tiny value stream
+    alp = bytes([13]) + _uv(2) + _uv(0) + bytes([1]) + bytes([1]) + _uv(3) + _uv(10) + bytes([10]) + _uv(0) + _uv(huge) + delta_huge
+    enc = np.frombuffer(alp, dtype=np.uint8).copy()
+    assert H.kxh_decode(ko.F64, enc.ctypes.data, enc.size, dst.ctypes.data, dst.size) < 0
+    # a zero-delta block must also be refused on the matcher path the reference would divide in
+    enc = np.frombuffer(crafted["zero delta"], dtype=np.uint8).copy()
+    for op in (ko.EQ, ko.LT, ko.RG):
+        assert H.kxh_match(ko.I64, enc.ctypes.data, enc.size, op, 10, 20, None, 0, bits.ctypes.data, None) < 0
