@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define KX_ABI_VERSION 1
+#define KX_ABI_VERSION 2
 
 /* error codes */
 enum {
@@ -63,6 +63,7 @@ typedef struct kx_prog kx_prog;
  * New (no reference counterpart; closest: engine options, pkg/knox/interface.go:29-50).
  * device: CUDA ordinal; hbm_budget: max bytes of resident blocks (0 = 80% of free HBM). */
 int  kx_abi_version(void);
+int  kx_device_count(void);                /* usable CUDA devices (0 without a driver / device) */
 int  kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out);
 void kx_ctx_destroy(kx_ctx* ctx);
 const char* kx_last_error(kx_ctx* ctx);   /* ctx may be NULL: error of the last failed kx_ctx_create */
@@ -83,7 +84,10 @@ void  kx_host_free(kx_ctx* ctx, void* p);
 int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, uint8_t block_type,
                  const void* enc, size_t len, uint32_t* nrows_out);
 int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field);
-int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes);
+/* device_bytes = bytes of the live blocks (256 B granules); slab_bytes = device memory the store really holds (capacity of
+ * its slabs: freed extents are coalesced and reused, a slab returns to CUDA when its last block is dropped); the HBM
+ * budget of kx_ctx_create bounds slab_bytes.  Any out pointer may be NULL. */
+int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes, uint64_t* slab_bytes);
 
 /* ---------------------------------------------------------------- predicate program
  * One leaf = one filter.Filter (internal/operator/filter/filter.go) with its Matcher
@@ -135,6 +139,33 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
             uint8_t* bitsets, const size_t* bitset_off, int64_t* counts,
             const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out);
 
+/* kx_scan with every option in one argument block — and the one the reader binding uses, because it takes ROW MASKS:
+ * between filter.Match and bits.Indexes / aggregation the reference's reader clears the bits of rows that a live
+ * journal has tombstoned or that the transaction may not see (internal/pack/table/reader.go:347-413: `hits` is
+ * AND-NOT'ed with the exclude mask from engine.TableReader.WithMask, engine/interface.go:96-106, and with the rows
+ * whose $xmin / $xmax fail the snapshot).  row_masks (nullable) holds per pack one bitset of ceil(n/8) bytes in HOST
+ * memory, or NULL for "all rows": bit i SET = row i stays eligible (the caller passes ¬(tombstones ∪ invisible)).  The
+ * mask is ANDed into the filter result on the device, so counts, bitsets, selection vectors and the fused aggregates all
+ * see it.  (Alternative without a mask: add `$rid NIN {tombstoned rids}` and range leaves on `$xmin` / `$xmax` to the
+ * program — INTEGRATION.md §4.)
+ * Outputs are all nullable: bitsets + bitset_off as in kx_scan; counts; sel / sel_cap / sel_off as in kx_scan_select (not
+ * together with bitsets); aggs / agg_out; flags & KX_SCAN_SHARDED combines agg_out and *total_count over all ranks of
+ * the communicator like kx_scan_sharded. */
+#define KX_SCAN_SHARDED 1u
+typedef struct kx_scan_args {
+    uint32_t struct_size;               /* sizeof(kx_scan_args) */
+    uint32_t flags;
+    const kx_packref* packs;
+    int32_t npacks, naggs;
+    const uint8_t* const* row_masks;    /* [npacks], entries may be NULL */
+    uint8_t* bitsets; const size_t* bitset_off;
+    int64_t* counts;
+    uint32_t* sel; size_t sel_cap; uint64_t* sel_off;
+    const kx_agg_req* aggs; kx_agg_out* agg_out;
+    int64_t* total_count;               /* KX_SCAN_SHARDED */
+} kx_scan_args;
+int kx_scan_ex(kx_ctx* ctx, const kx_prog* prog, const kx_scan_args* args);
+
 /* kx_scan that hands back SELECTION VECTORS instead of bitsets: what the reader and PhysicalFilter do with a match
  * bitset — sel := bits.Indexes(hits); pack.WithSelection(sel) (internal/pack/table/reader.go:432-436,
  * internal/operator/filter.go:29-37, Bitset.Indexes internal/bitset/iterator.go:269-290).  The bitsets stay on the
@@ -164,7 +195,8 @@ int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, 
  * (nullable): npacks per-pack match counts of the filter, as in kx_scan. */
 int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks,
                     uint16_t ts_field, uint8_t ts_type, const uint64_t* edges, int nbuckets,
-                    const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out, int64_t* counts);
+                    const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out, int64_t* counts,
+                    const uint8_t* const* row_masks /* nullable: see kx_scan_ex */);
 
 /* Same scan over blocks that still live in HOST memory (cold device cache): the blocks of
  * all referenced fields are uploaded, scanned and dropped in pipelined batches.
@@ -181,8 +213,46 @@ int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_a
 
 /* Timing of the last kx_scan / kx_scan_host on this ctx (CUDA events on the scan stream):
  * kernel_ms = device time of the scan kernels only, total_ms = first copy/launch → results
- * on host.  launches = kernels launched.  (QueryStats: internal/query/stats.go:15-60) */
+ * on host.  launches = kernels launched. */
 int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* launches);
+
+/* The counters a query reports through QueryStats (internal/query/stats.go:15-60: rows_scanned, packs_scanned,
+ * rows_matched, scan_time …) for the last kx_scan* call on this ctx, so that the Go adapter can feed
+ * stats.Count / stats.Tick with what the device did (one call covers what the reference counts pack by pack in
+ * reader.go:330-345). */
+typedef struct kx_query_stats {
+    uint64_t rows_scanned;     /* rows of all packs of the call */
+    uint64_t packs_scanned;
+    uint64_t rows_matched;     /* sum of the per-pack match counts */
+    uint64_t scan_time_ns;     /* device time of the scan kernels (CUDA events) */
+    uint64_t total_time_ns;    /* first copy / launch → results on the host */
+    uint32_t kernel_launches;
+    uint32_t reserved;
+} kx_query_stats;
+int kx_last_query_stats(kx_ctx* ctx, kx_query_stats* out);
+
+/* ---------------------------------------------------------------- multi-GPU: pack-sharded scans
+ * Packs are independent (internal/pack/table/reader.go:299-449 keeps no cross-pack state): a table is sharded by pack
+ * key over the GPUs of one box — one kx_ctx per GPU, blocks registered on the owning GPU only, no data-path collective.
+ * Per query the ranks exchange ONE 208-byte record each (match count + partial aggregates) with one NCCL all-gather
+ * that the library enqueues on the scan stream behind the scan kernel, and combine the records in rank order on the
+ * device: every rank returns the bit-identical total.  NCCL is bound at run time (libnccl.so.2; KX_NCCL_LIB overrides).
+ *
+ * kx_comm_unique_id: rank 0 creates the communicator id (ncclGetUniqueId) and hands its KX_COMM_ID_BYTES to the other
+ *                    ranks by any means (the Go host: over the channel that starts its per-GPU workers).
+ * kx_comm_init:      every rank, once per ctx (collective: returns when all ranks joined).  nranks = 1 needs no id.
+ * kx_scan_sharded:   kx_scan over this rank's packs (possibly none); counts (nullable) = this rank's per-pack counts;
+ *                    agg_out / total_count = combined over ALL ranks.  Collective: every rank of the communicator must
+ *                    call it for every query, in the same order.
+ * kx_comm_allgather: the same exchange for caller-defined partials (e.g. the window table of a sharded
+ *                    kx_scan_buckets): bytes from every rank, concatenated in rank order into recv (host buffers). */
+#define KX_COMM_ID_BYTES 128
+int kx_comm_unique_id(void* id_out, size_t cap);
+int kx_comm_init(kx_ctx* ctx, int nranks, int rank, const void* id, size_t id_len);
+int kx_comm_info(kx_ctx* ctx, int* nranks, int* rank, int* nccl_version);
+int kx_scan_sharded(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, int64_t* counts,
+                    const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, int64_t* total_count);
+int kx_comm_allgather(kx_ctx* ctx, const void* send, void* recv, size_t bytes);
 
 /* ---------------------------------------------------------------- narrow drop-ins
  * Host-pointer kernels with the signatures of the reference's leaf functions; used behind

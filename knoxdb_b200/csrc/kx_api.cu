@@ -18,6 +18,7 @@
 #include <vector>
 
 #include "../../include/knoxgpu.h"
+#include "kx_comm.h"
 #include "kx_host.h"
 #include "kx_kernels.h"
 #include "kx_types.h"
@@ -136,6 +137,12 @@ struct kx_ctx {
 
     double last_kernel_ms = 0, last_total_ms = 0;
     int last_launches = 0;
+    // QueryStats counters of the last scan (internal/query/stats.go:15-60)
+    uint64_t last_rows_scanned = 0, last_packs_scanned = 0, last_rows_matched = 0;
+
+    // pack-sharded scans: communicator (run-time bound NCCL) and the exchange scratch [own | nranks gathered | combined]
+    CommState* comm = nullptr;
+    DevBuf d_xchg;
 };
 
 // device-resident statistics index (zone maps + bloom filters), see include/knoxgpu.h
@@ -316,12 +323,56 @@ struct SelectOut {
     bool overflow = false;
 };
 
+// optional cross-rank combine of a scan's totals (kx_scan_sharded)
+struct ShardOut { int64_t* total_count = nullptr; };
+
+// enqueue on the scan stream: pack this rank's record (sum of the per-pack counts + combined aggregates), ONE all-gather,
+// combine in rank order.  Afterwards the combined record sits at xchg_final(ctx).
+const RankPartial* xchg_final(kx_ctx* ctx) { return static_cast<const RankPartial*>(ctx->d_xchg.p) + 1 + comm_nranks(ctx->comm); }
+int enqueue_exchange(kx_ctx* ctx, uint32_t npacks, uint32_t naggs, const uint8_t* agg_type) {
+    const int nranks = comm_nranks(ctx->comm);
+    CK(ctx->d_xchg.reserve(sizeof(RankPartial) * size_t(nranks + 2)));
+    RankPartial* xs = static_cast<RankPartial*>(ctx->d_xchg.p);
+    CK(launch_xchg_pack(static_cast<const unsigned long long*>(ctx->d_counts.p), npacks, static_cast<const AggPartial*>(ctx->d_aggout.p), naggs, xs, ctx->stream));
+    std::string err;
+    if (comm_allgather(ctx->comm, xs, xs + 1, sizeof(RankPartial), ctx->stream, err)) return fail(ctx, KX_ECUDA, "kx_scan_sharded: " + err);
+    CK(launch_xchg_combine(xs + 1, uint32_t(nranks), naggs, agg_type, xs + 1 + nranks, ctx->stream));
+    ctx->last_launches += 2 + (nranks > 1 ? 1 : 0);
+    return KX_OK;
+}
+
+// device partial → C ABI result (SumReducer wraps in T; float64 sums carry their compensation term)
+kx_agg_out agg_result(const AggPartial& a, int t) {
+    kx_agg_out o{};
+    o.count = int64_t(a.count); o.valid = a.valid ? 1 : 0;
+    if (a.valid) {
+        if (t == KX_FLOAT64) {
+            double hi, s; std::memcpy(&hi, &a.sum, 8);
+            s = hi + a.err;
+            std::memcpy(&o.sum_bits, &s, 8);
+            o.sum_err = (hi - s) + a.err;
+            o.min_bits = a.mn; o.max_bits = a.mx;
+        } else {
+            uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
+            o.sum_bits = type_ext(t, a.sum);     // SumReducer wraps in T
+            o.min_bits = a.mn ^ flip; o.max_bits = a.mx ^ flip;
+        }
+    }
+    return o;
+}
+
 // keep_layout (optional): leave the match bitsets on the device (ctx->d_bitsets, pack i at keep_layout[i]; PackInfo table
 // at the start of ctx->d_packs) for a follow-up kernel on the same stream (kx_scan_buckets)
 int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bitsets, const size_t* bitset_off,
              int64_t* counts, const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, SelectOut* so = nullptr,
-             std::vector<size_t>* keep_layout = nullptr) {
+             std::vector<size_t>* keep_layout = nullptr, ShardOut* sh = nullptr, const uint8_t* const* row_masks = nullptr) {
     const int npacks = job.npacks, nleaves = int(prog->leaves.size());
+    // Row masks (TableReader.WithMask, engine/interface.go:96-106; the tombstone / visibility step of reader.go:347-413):
+    // one more leaf, ANDed last — a 1-bit column per pack that the scan streams like a run-end pre-pass result
+    const bool masked = row_masks != nullptr;
+    const int nl = nleaves + (masked ? 1 : 0);
+    std::vector<uint8_t> post(prog->postfix);
+    if (masked) { post.push_back(uint8_t(nleaves)); post.push_back(KX_OP_AND); }
     // selection vectors are extracted from device-resident bitsets laid out back to back (8-byte aligned)
     std::vector<size_t> sel_layout;
     const bool dev_bits = bitsets != nullptr || so != nullptr || keep_layout != nullptr;
@@ -340,8 +391,24 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         int t = aggs[j].block_type;
         if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
     }
+    ctx->last_rows_scanned = ctx->last_packs_scanned = ctx->last_rows_matched = 0;
     if (npacks == 0) {
         for (int j = 0; j < naggs; ++j) agg_out[j] = kx_agg_out{};
+        if (!sh) return KX_OK;
+        // a rank whose shard is empty still takes part in the query's collective
+        uint8_t types[MAX_AGGS] = {};
+        for (int j = 0; j < naggs; ++j) types[j] = aggs[j].block_type;
+        CK(ctx->d_counts.reserve(8));
+        CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS + 16));
+        CK(ctx->h_res.reserve(sizeof(RankPartial) + 64));
+        CK(cudaMemsetAsync(ctx->d_aggout.p, 0, sizeof(AggPartial) * MAX_AGGS + 16, ctx->stream));
+        int rc = enqueue_exchange(ctx, 0, uint32_t(naggs), types);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->h_res.p, xchg_final(ctx), sizeof(RankPartial), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const RankPartial* rp = static_cast<const RankPartial*>(ctx->h_res.p);
+        if (sh->total_count) *sh->total_count = int64_t(rp->total_count);
+        for (int j = 0; j < naggs; ++j) agg_out[j] = agg_result(rp->agg[j], aggs[j].block_type);
         return KX_OK;
     }
     if (bitsets && !bitset_off) return fail(ctx, KX_EINVAL, "bitsets without bitset_off");
@@ -349,13 +416,14 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (so && !counts) { sel_counts.resize(size_t(npacks)); counts = sel_counts.data(); }
 
     // ---- per-pack / per-leaf descriptors (host), pinned staging
-    size_t sz_packs = sizeof(PackInfo) * size_t(npacks), sz_leaves = sizeof(PackLeaf) * size_t(npacks) * size_t(nleaves);
+    size_t sz_packs = sizeof(PackInfo) * size_t(npacks), sz_leaves = sizeof(PackLeaf) * size_t(npacks) * size_t(nl);
     size_t nviews = size_t(npacks) * size_t(nleaves + naggs), sz_views = sizeof(ColView) * nviews;
     size_t off_leaves = round_up(sz_packs, 256), off_views = off_leaves + round_up(sz_leaves, 256);
     size_t off_tiles = off_views + round_up(sz_views, 256);
 
     // translate every leaf for every pack; the widest staged bits/row over all packs decides the tile
-    std::vector<PackLeaf> pl(size_t(npacks) * size_t(nleaves));
+    std::vector<PackLeaf> pl(size_t(npacks) * size_t(nl));
+    std::vector<std::pair<size_t, int>> mask_jobs;   // (byte offset in the leaf-bit scratch, pack) of every row mask
     std::vector<CodesetJob> cjobs;
     std::vector<RunFillJob> rjobs;
     std::vector<size_t> rjob_leaf;     // index into pl of each run-fill job
@@ -369,9 +437,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     size_t leafbits_bytes = 0;
     uint32_t max_runs = 0;
     uint32_t max_stage_bits = 0, code_words = 0, max_code_set = 0;
-    uint32_t code_leaf_words[MAX_LEAVES] = {};   // per leaf: largest code bitmap of any pack (cached in shared memory by the scan)
+    uint32_t code_leaf_words[MAX_SCAN_LEAVES] = {};   // per leaf: largest code bitmap of any pack (cached in shared memory by the scan)
     uint32_t max_agg_bits = 0;                   // widest value column that can be staged through the ring
-    bool hash_leaf[MAX_LEAVES] = {};             // leaf is looked up in its hash set (LM_HASHSET) for some pack
+    bool hash_leaf[MAX_SCAN_LEAVES] = {};             // leaf is looked up in its hash set (LM_HASHSET) for some pack
     bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
     uint64_t total_rows = 0;
     bool uniform = true;
@@ -380,7 +448,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         for (int l = 0; l < nleaves; ++l) {
             const ColView& v = job.leaf_views[size_t(p) * nleaves + l];
             if (v.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
-            PackLeaf& o = pl[size_t(p) * nleaves + l];
+            PackLeaf& o = pl[size_t(p) * nl + l];
             if (prog->leaves[size_t(l)].type == KX_BYTES) {
                 // byte-string leaf (StringMatcher.Match*, internal/encode/string_*.go): constant blocks are decided here
                 // (string_const.go:113-153), every other layout by strmatch_kernel into a 1-bit column the scan streams
@@ -396,7 +464,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                     o.mode = all ? LM_ALL : LM_NONE;
                 } else {
                     sjobs.push_back(StrJob{v, leafbits_bytes, ls.sa_off, uint32_t(ls.sa.size()), ls.sb_off, uint32_t(ls.sb.size()), uint32_t(ls.mode), 0});
-                    sjob_leaf.push_back(size_t(p) * nleaves + l);
+                    sjob_leaf.push_back(size_t(p) * nl + l);
                     leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                     max_str_rows = std::max(max_str_rows, v.n);
                     o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
@@ -420,7 +488,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
                 // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
                 rjobs.push_back(RunFillJob{v.data, v.aux, o.a, o.d, o.wm, leafbits_bytes, v.naux, v.n, o.mode == LM_SET ? 1u : 0u, 0});
-                rjob_leaf.push_back(size_t(p) * nleaves + l);
+                rjob_leaf.push_back(size_t(p) * nl + l);
                 leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                 max_runs = std::max(max_runs, v.naux);
                 o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
@@ -434,13 +502,25 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                     const LeafSpec& ls = prog->leaves[size_t(l)];
                     ajobs.push_back(AlpFixJob{v.aux, ls.a, ls.b, leafbits_bytes, v.naux, uint32_t(ls.mode == KX_MODE_NE ? uint8_t(KX_MODE_EQ) : ls.mode),
                                               o.fixmode == FIX_ANDNOT_NPRED ? 1u : 0u, 0});
-                    ajob_leaf.push_back(size_t(p) * nleaves + l);
+                    ajob_leaf.push_back(size_t(p) * nl + l);
                     leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                     max_patches = std::max(max_patches, v.naux);
                 }
             }
             bits = std::max(bits, uint32_t(leaf_stage_width(o)));
             if (o.mode != LM_RANGE32 && o.mode != LM_NONE && o.mode != LM_ALL) only32 = false;
+        }
+        if (masked) {
+            PackLeaf& o = pl[size_t(p) * nl + nleaves];
+            o = PackLeaf{};
+            only32 = false;
+            if (!row_masks[p] || job.nrows[size_t(p)] == 0) o.mode = LM_ALL;   // no mask for this pack: every row stays eligible
+            else {
+                mask_jobs.push_back({leafbits_bytes, p});
+                leafbits_bytes += round_up((size_t(job.nrows[size_t(p)]) + 7) / 8 + STREAM_PAD, 256);
+                o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
+                bits = std::max(bits, 1u);
+            }
         }
         for (int j = 0; j < naggs; ++j) {
             const ColView& av = job.agg_views[size_t(p) * naggs + j];
@@ -457,14 +537,14 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // tiles in a 2-deep ring beat small tiles in a deep ring (per-tile barrier/dispatch cost, larger TMA
     // copies), narrow ALU-bound columns like 3 CTAs per SM, wide ones 2 (or 1 when 8192 rows need > 50 KB).
     struct Geo { int ctas, stages; size_t budget; };
-    const bool simple = nleaves == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
+    const bool simple = nl == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
     const bool simple32 = only32 && simple;
     // dictionary-code bitmaps cached in shared memory behind the ring
-    uint32_t code_smem_off[MAX_LEAVES] = {}, code_smem_words = 0;
+    uint32_t code_smem_off[MAX_SCAN_LEAVES] = {}, code_smem_words = 0;
     for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
     // hash-set leaves: prefilter bitmap (<= 16 KB) and, when it is small (<= 16 KB: sets up to ~500 keys), the exact table
     // in shared memory too; larger tables stay in global memory (L2) and only candidates are verified against them
-    uint32_t hs_smem_off[MAX_LEAVES] = {}, hs_tab_smem_off[MAX_LEAVES] = {};
+    uint32_t hs_smem_off[MAX_SCAN_LEAVES] = {}, hs_tab_smem_off[MAX_SCAN_LEAVES] = {};
     uint32_t hs_tab_limit = 16u * 1024u;
     if (const char* e = getenv("KX_HASH_SMEM_KB")) hs_tab_limit = uint32_t(atoi(e)) * 1024u;   // tuning hook
     const uint32_t code_bitmap_words = code_smem_words;
@@ -494,14 +574,14 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     uint32_t stack_depth = 0, flat_op = 0;
     if (!simple) {
         bool all_and = true, all_or = true;
-        for (uint8_t op : prog->postfix) { if (op == KX_OP_AND) all_or = false; else if (op == KX_OP_OR) all_and = false; }
+        for (uint8_t op : post) { if (op == KX_OP_AND) all_or = false; else if (op == KX_OP_OR) all_and = false; }
         if (!any_fix) flat_op = all_and ? 1u : (all_or ? 2u : 0u);
         if (!flat_op) {
             uint32_t sp = 0;
-            for (uint8_t op : prog->postfix) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
+            for (uint8_t op : post) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
         }
     }
-    const uint32_t desc_words = uint32_t(nleaves * (sizeof(PackLeaf) / 4) + 2 * size_t(naggs) * (sizeof(ColView) / 4));
+    const uint32_t desc_words = uint32_t(nl * (sizeof(PackLeaf) / 4) + 2 * size_t(naggs) * (sizeof(ColView) / 4));
     auto extra_smem_for = [&](uint32_t r) {   // bytes behind the ring: code bitmaps, stacks, descriptor caches
         size_t words = simple ? 0 : size_t(CONSUMER_WARPS) * stack_depth * ((r + 31) / 32) * 32 + size_t(CONSUMER_WARPS) * desc_words;
         return code_smem_bytes + round_up(words * 4, 128);
@@ -589,6 +669,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         for (size_t i = 0; i < rjobs.size(); ++i) pl[rjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + rjobs[i].out_off;
         for (size_t i = 0; i < ajobs.size(); ++i) pl[ajob_leaf[i]].fix = static_cast<const uint8_t*>(ctx->d_leafbits.p) + ajobs[i].out_off;
         for (size_t i = 0; i < sjobs.size(); ++i) pl[sjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + sjobs[i].out_off;
+        for (auto& mj : mask_jobs) pl[size_t(mj.second) * nl + nleaves].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + mj.first;
     }
 
     CK(ctx->h_desc.reserve(desc_bytes));
@@ -639,7 +720,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         CK(ctx->d_partials.reserve(sizeof(AggPartial) * size_t(grid) * naggs));
         CK(ctx->d_aggout.reserve(sizeof(AggPartial) * MAX_AGGS + 16));   // combined aggregates + the finished-CTA counter
     }
-    CK(ctx->h_res.reserve(sizeof(unsigned long long) * size_t(npacks) + sizeof(AggPartial) * MAX_AGGS + 64));
+    CK(ctx->h_res.reserve(sizeof(unsigned long long) * size_t(npacks) + sizeof(RankPartial) + 128));
 
     uint8_t* dd = static_cast<uint8_t*>(ctx->d_packs.p);
     ScanParams P{};
@@ -650,10 +731,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.set_vals = prog->dev_sets;
     P.set_tabs = prog->dev_tabs;
     P.code_bits = static_cast<const uint32_t*>(ctx->d_codebits.p);
-    std::memcpy(P.tab_off, prog->tab_off, sizeof(P.tab_off));
-    std::memcpy(P.tab_log2, prog->tab_log2, sizeof(P.tab_log2));
+    std::memcpy(P.tab_off, prog->tab_off, sizeof(prog->tab_off));
+    std::memcpy(P.tab_log2, prog->tab_log2, sizeof(prog->tab_log2));
     P.set_pre = prog->dev_pres;
-    std::memcpy(P.pre_off, prog->pre_off, sizeof(P.pre_off));
+    std::memcpy(P.pre_off, prog->pre_off, sizeof(prog->pre_off));
     for (int l = 0; l < MAX_LEAVES; ++l) P.pre_log2[l] = hash_leaf[l] ? prog->pre_log2[l] : 0;
     std::memcpy(P.hs_smem_off, hs_smem_off, sizeof(P.hs_smem_off));
     std::memcpy(P.hs_tab_smem_off, hs_tab_smem_off, sizeof(P.hs_tab_smem_off));
@@ -676,11 +757,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.agg_out = static_cast<AggPartial*>(ctx->d_aggout.p);
     P.done = naggs ? reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(ctx->d_aggout.p) + sizeof(AggPartial) * MAX_AGGS) : nullptr;
     P.npacks = uint32_t(npacks); P.ntiles = ntiles;
-    P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size()); P.naggs = uint32_t(naggs);
+    P.nleaves = uint32_t(nl); P.npost = uint32_t(post.size()); P.naggs = uint32_t(naggs);
     P.R = R; P.tiles_per_pack = uniform ? (ntiles / uint32_t(npacks)) : 0; P.stage_bytes = uint32_t(stage_bytes);
-    std::memcpy(P.set_off, prog->set_off, sizeof(P.set_off));
+    std::memcpy(P.set_off, prog->set_off, sizeof(prog->set_off));
     P.agg_view0 = uint32_t(size_t(npacks) * nleaves); P.leaf_view0 = 0;
-    std::memcpy(P.postfix, prog->postfix.data(), prog->postfix.size());
+    std::memcpy(P.postfix, post.data(), post.size());
     for (int j = 0; j < naggs; ++j) P.agg_type[j] = aggs[j].block_type;
     if (uniform && P.tiles_per_pack == 0) P.tiles_per_pack = 1;   // all packs empty
 
@@ -690,6 +771,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (naggs) CK(cudaMemsetAsync(ctx->d_aggout.p, 0, sizeof(AggPartial) * MAX_AGGS + 16, ctx->stream));   // "no match" results, counter = 0
     CK(cudaEventRecord(ctx->ev_k0, ctx->stream));
     if (ntiles && leafbits_bytes) CK(cudaMemsetAsync(ctx->d_leafbits.p, 0, leafbits_bytes, ctx->stream));
+    if (ntiles) for (auto& mj : mask_jobs)   // the caller's masks (host memory) land behind the zero fill, before any kernel reads them
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(ctx->d_leafbits.p) + mj.first, row_masks[mj.second], (size_t(job.nrows[size_t(mj.second)]) + 7) / 8,
+                           cudaMemcpyHostToDevice, ctx->stream));
     if (ntiles && !ajobs.empty()) {
         CK(launch_alpfix(reinterpret_cast<const AlpFixJob*>(dd + off_ajobs), uint32_t(ajobs.size()), max_patches,
                          static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
@@ -716,6 +800,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         else CK(launch_scan_general(P, grid, smem_bytes, geo.ctas, ctx->stream));
         ctx->last_launches++;
     }
+    if (sh) { int rc = enqueue_exchange(ctx, uint32_t(npacks), uint32_t(naggs), P.agg_type); if (rc) return rc; }
     CK(cudaEventRecord(ctx->ev_k1, ctx->stream));
 
     // ---- results back to the host
@@ -738,8 +823,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             CK(cudaMemcpyAsync(so->sel, ctx->d_tmp2.p, size_t(total_matches) * 4, cudaMemcpyDeviceToHost, ctx->stream));
         }
     }
-    if (counts) CK(cudaMemcpyAsync(hr, ctx->d_counts.p, res_counts, cudaMemcpyDeviceToHost, ctx->stream));
-    if (naggs) CK(cudaMemcpyAsync(hr + round_up(res_counts, 64), ctx->d_aggout.p, sizeof(AggPartial) * size_t(naggs), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(hr, ctx->d_counts.p, res_counts, cudaMemcpyDeviceToHost, ctx->stream));   // also feeds the QueryStats counters
+    RankPartial* h_rp = reinterpret_cast<RankPartial*>(hr + round_up(res_counts, 64));
+    if (sh) CK(cudaMemcpyAsync(h_rp, xchg_final(ctx), sizeof(RankPartial), cudaMemcpyDeviceToHost, ctx->stream));   // combined over all ranks
+    else if (naggs) CK(cudaMemcpyAsync(h_rp->agg, ctx->d_aggout.p, sizeof(AggPartial) * size_t(naggs), cudaMemcpyDeviceToHost, ctx->stream));
     if (bitsets && bitset_total) CK(cudaMemcpyAsync(bitsets, ctx->d_bitsets.p, bitset_total, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaEventRecord(ctx->ev_end, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -749,27 +836,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
 
     if (counts) for (int p = 0; p < npacks; ++p) counts[p] = int64_t(reinterpret_cast<unsigned long long*>(hr)[p]);
     if (so) for (int p = 0; p < npacks; ++p) so->off[p + 1] = so->off[p] + uint64_t(counts[p]);
-    const AggPartial* fin = reinterpret_cast<const AggPartial*>(hr + round_up(res_counts, 64));
-    for (int j = 0; j < naggs; ++j) {
-        kx_agg_out o{};
-        const AggPartial& a = fin[j];
-        int t = aggs[j].block_type;
-        o.count = int64_t(a.count); o.valid = a.valid ? 1 : 0;
-        if (a.valid) {
-            if (t == KX_FLOAT64) {
-                double hi, s; std::memcpy(&hi, &a.sum, 8);
-                s = hi + a.err;
-                std::memcpy(&o.sum_bits, &s, 8);
-                o.sum_err = (hi - s) + a.err;
-                o.min_bits = a.mn; o.max_bits = a.mx;
-            } else {
-                uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
-                o.sum_bits = type_ext(t, a.sum);     // SumReducer wraps in T
-                o.min_bits = a.mn ^ flip; o.max_bits = a.mx ^ flip;
-            }
-        }
-        agg_out[j] = o;
-    }
+    for (int j = 0; j < naggs; ++j) agg_out[j] = agg_result(h_rp->agg[j], aggs[j].block_type);
+    if (sh && sh->total_count) *sh->total_count = int64_t(h_rp->total_count);
+    ctx->last_rows_scanned = total_rows; ctx->last_packs_scanned = uint64_t(npacks);
+    for (int p = 0; p < npacks; ++p) ctx->last_rows_matched += reinterpret_cast<unsigned long long*>(hr)[p];
     return KX_OK;
 }
 
@@ -806,7 +876,7 @@ int single_leaf_scan(kx_ctx* ctx, const StoredBlock& sb, uint8_t block_type, uin
 
 int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* postfix, int npost, kx_prog** out) {
     if (!leaves || nleaves < 1 || nleaves > MAX_LEAVES) return fail(ctx, KX_EINVAL, "program needs 1..8 leaves");
-    if (!postfix || npost < 1 || npost > MAX_POSTFIX) return fail(ctx, KX_EINVAL, "bad postfix length");
+    if (!postfix || npost < 1 || npost > 2 * MAX_LEAVES) return fail(ctx, KX_EINVAL, "bad postfix length");
     int depth = 0;
     for (int i = 0; i < npost; ++i) {
         if (postfix[i] < 0x80) { if (postfix[i] >= nleaves) return fail(ctx, KX_EINVAL, "postfix references unknown leaf"); depth++; }
@@ -903,6 +973,12 @@ extern "C" {
 
 int kx_abi_version(void) { return KX_ABI_VERSION; }
 
+int kx_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
 int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
     return kx_guarded<int>(nullptr, [&]() -> int {
     if (!out) return KX_EINVAL;
@@ -943,6 +1019,7 @@ void kx_ctx_destroy(kx_ctx* ctx) {
     if (ctx->ev_copy[0]) cudaEventDestroy(ctx->ev_copy[0]);
     if (ctx->ev_copy[1]) cudaEventDestroy(ctx->ev_copy[1]);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    comm_destroy(ctx->comm);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -1000,12 +1077,13 @@ int kx_block_drop(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field) 
     });
 }
 
-int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes) {
+int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint64_t* device_bytes, uint64_t* slab_bytes) {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (nblocks) *nblocks = ctx->store.size();
     if (encoded_bytes) *encoded_bytes = ctx->store_enc_bytes;
     if (device_bytes) *device_bytes = ctx->store_dev_bytes;
+    if (slab_bytes) *slab_bytes = ctx->slab_bytes;
     return KX_OK;
 }
 
@@ -1038,6 +1116,96 @@ int kx_scan(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npack
     ScanJob job;
     if ((rc = build_scan_job(ctx, prog, packs, npacks, aggs, naggs, job))) return rc;
     return run_scan(ctx, prog, job, bitsets, bitset_off, counts, aggs, naggs, agg_out);
+    });
+}
+
+int kx_scan_sharded(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, int64_t* counts,
+                    const kx_agg_req* aggs, int naggs, kx_agg_out* agg_out, int64_t* total_count) {
+    return kx_guarded<int>(ctx, [&]() -> int {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog, true);
+    if (rc) return rc;
+    if (npacks < 0 || (npacks && !packs)) return fail(ctx, KX_EINVAL, "bad pack list");
+    if (naggs < 0 || naggs > MAX_AGGS || (naggs && (!aggs || !agg_out))) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
+    CK(cudaSetDevice(ctx->device));
+    ScanJob job;
+    if ((rc = build_scan_job(ctx, prog, packs, npacks, aggs, naggs, job))) return rc;
+    ShardOut sh; sh.total_count = total_count;
+    return run_scan(ctx, prog, job, nullptr, nullptr, counts, aggs, naggs, agg_out, nullptr, nullptr, &sh);
+    });
+}
+
+int kx_scan_ex(kx_ctx* ctx, const kx_prog* prog, const kx_scan_args* a) {
+    return kx_guarded<int>(ctx, [&]() -> int {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    int rc = check_prog_job(ctx, prog, true);
+    if (rc) return rc;
+    if (!a || a->struct_size < sizeof(kx_scan_args)) return fail(ctx, KX_EINVAL, "kx_scan_ex: bad argument block");
+    if (a->npacks < 0 || (a->npacks && !a->packs)) return fail(ctx, KX_EINVAL, "bad pack list");
+    if (a->naggs < 0 || a->naggs > MAX_AGGS || (a->naggs && (!a->aggs || !a->agg_out))) return fail(ctx, KX_EINVAL, "aggregate buffers missing");
+    const bool want_sel = a->sel_off != nullptr;
+    if (want_sel && (a->bitsets || (a->sel_cap && !a->sel))) return fail(ctx, KX_EINVAL, "kx_scan_ex: selection vectors and host bitsets cannot be requested together");
+    CK(cudaSetDevice(ctx->device));
+    ScanJob job;
+    if ((rc = build_scan_job(ctx, prog, a->packs, a->npacks, a->aggs, a->naggs, job))) return rc;
+    SelectOut so; so.sel = a->sel; so.cap = a->sel_cap; so.off = a->sel_off;
+    ShardOut sh; sh.total_count = a->total_count;
+    rc = run_scan(ctx, prog, job, a->bitsets, a->bitset_off, a->counts, a->aggs, a->naggs, a->agg_out, want_sel ? &so : nullptr, nullptr,
+                  (a->flags & KX_SCAN_SHARDED) ? &sh : nullptr, a->row_masks);
+    if (rc) return rc;
+    if (want_sel && so.overflow) return fail(ctx, KX_ENOMEM, "kx_scan_ex: selection buffer too small (sel_off[npacks] holds the required size)");
+    return KX_OK;
+    });
+}
+
+int kx_comm_unique_id(void* id_out, size_t cap) {
+    if (!id_out || cap < KX_COMM_ID_BYTES) return KX_EINVAL;
+    std::string err;
+    if (comm_unique_id(id_out, err)) return fail(nullptr, KX_EUNSUPPORTED, "kx_comm_unique_id: " + err);
+    return KX_OK;
+}
+
+int kx_comm_init(kx_ctx* ctx, int nranks, int rank, const void* id, size_t id_len) {
+    return kx_guarded<int>(ctx, [&]() -> int {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nranks < 1 || rank < 0 || rank >= nranks || (nranks > 1 && (!id || id_len < KX_COMM_ID_BYTES))) return fail(ctx, KX_EINVAL, "kx_comm_init: bad arguments");
+    if (ctx->comm) return fail(ctx, KX_EINVAL, "kx_comm_init: this context already has a communicator");
+    CK(cudaSetDevice(ctx->device));
+    std::string err;
+    if (comm_create(nranks, rank, id, &ctx->comm, err)) return fail(ctx, KX_EUNSUPPORTED, "kx_comm_init: " + err);
+    return KX_OK;
+    });
+}
+
+int kx_comm_info(kx_ctx* ctx, int* nranks, int* rank, int* nccl_version) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (nranks) *nranks = comm_nranks(ctx->comm);
+    if (rank) *rank = comm_rank(ctx->comm);
+    if (nccl_version) *nccl_version = ctx->comm && comm_nranks(ctx->comm) > 1 ? comm_nccl_version() : 0;
+    return KX_OK;
+}
+
+int kx_comm_allgather(kx_ctx* ctx, const void* send, void* recv, size_t bytes) {
+    return kx_guarded<int>(ctx, [&]() -> int {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!bytes) return KX_OK;
+    if (!send || !recv) return fail(ctx, KX_EINVAL, "kx_comm_allgather: null buffers");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nranks = size_t(comm_nranks(ctx->comm)), padded = round_up(bytes, 16);
+    CK(ctx->d_tmp.reserve(padded * (nranks + 1)));
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
+    CK(cudaMemcpyAsync(d, send, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    std::string err;
+    if (comm_allgather(ctx->comm, d, d + padded, padded, ctx->stream, err)) return fail(ctx, KX_ECUDA, "kx_comm_allgather: " + err);
+    for (size_t r = 0; r < nranks; ++r)
+        CK(cudaMemcpyAsync(static_cast<uint8_t*>(recv) + r * bytes, d + padded * (r + 1), bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return KX_OK;
     });
 }
 
@@ -1095,7 +1263,7 @@ int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, in
 
 int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, int npacks, uint16_t ts_field, uint8_t ts_type,
                     const uint64_t* edges, int nbuckets, const kx_agg_req* aggs, int naggs, int64_t* bucket_counts, kx_agg_out* out,
-                    int64_t* counts) {
+                    int64_t* counts, const uint8_t* const* row_masks) {
     return kx_guarded<int>(ctx, [&]() -> int {
     if (!ctx) return KX_EINVAL;
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -1125,7 +1293,7 @@ int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, i
         for (int c = 0; c <= naggs; ++c)
             if (views[size_t(p) * (naggs + 1) + c].n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "blocks of one pack differ in length");
     std::vector<size_t> layout;
-    rc = run_scan(ctx, prog, job, nullptr, nullptr, counts, nullptr, 0, nullptr, nullptr, &layout);
+    rc = run_scan(ctx, prog, job, nullptr, nullptr, counts, nullptr, 0, nullptr, nullptr, &layout, nullptr, row_masks);
     if (rc) return rc;
     const double scan_kernel_ms = ctx->last_kernel_ms, scan_total_ms = ctx->last_total_ms;
 
@@ -1269,6 +1437,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
     std::vector<kx_agg_out> part(static_cast<size_t>(naggs));
     std::vector<std::vector<kx_agg_out>> parts(static_cast<size_t>(naggs));
     double kms = 0, tms = 0; int launches = 0;
+    uint64_t q_rows = 0, q_packs = 0, q_match = 0;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
     CK(cudaEventRecord(e0, ctx->stream));
@@ -1392,6 +1561,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         int rc2 = run_scan(ctx, prog, job, bdst, bitsets ? offs.data() : nullptr, counts ? counts + p0 : nullptr, aggs, naggs,
                            naggs ? part.data() : nullptr);
         kms += ctx->last_kernel_ms; launches += ctx->last_launches;
+        q_rows += ctx->last_rows_scanned; q_packs += ctx->last_packs_scanned; q_match += ctx->last_rows_matched;
         if (rc2) return rc2;
         for (int j = 0; j < naggs; ++j) parts[size_t(j)].push_back(part[size_t(j)]);
         return KX_OK;
@@ -1418,6 +1588,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         else kx_agg_combine(aggs[j].block_type, parts[size_t(j)].data(), int(parts[size_t(j)].size()), &agg_out[j]);
     }
     ctx->last_kernel_ms = kms; ctx->last_total_ms = tms; ctx->last_launches = launches;
+    ctx->last_rows_scanned = q_rows; ctx->last_packs_scanned = q_packs; ctx->last_rows_matched = q_match;
     return KX_OK;
     });
 }
@@ -1465,6 +1636,14 @@ int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* la
     if (kernel_ms) *kernel_ms = ctx->last_kernel_ms;
     if (total_ms) *total_ms = ctx->last_total_ms;
     if (launches) *launches = ctx->last_launches;
+    return KX_OK;
+}
+
+int kx_last_query_stats(kx_ctx* ctx, kx_query_stats* out) {
+    if (!ctx || !out) return KX_EINVAL;
+    out->rows_scanned = ctx->last_rows_scanned; out->packs_scanned = ctx->last_packs_scanned; out->rows_matched = ctx->last_rows_matched;
+    out->scan_time_ns = uint64_t(ctx->last_kernel_ms * 1e6); out->total_time_ns = uint64_t(ctx->last_total_ms * 1e6);
+    out->kernel_launches = uint32_t(ctx->last_launches); out->reserved = 0;
     return KX_OK;
 }
 

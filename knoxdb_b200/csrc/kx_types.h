@@ -117,7 +117,8 @@ struct AggPartial {
 
 constexpr int MAX_LEAVES = 8;
 constexpr int MAX_AGGS = 4;
-constexpr int MAX_POSTFIX = 2 * MAX_LEAVES;
+constexpr int MAX_SCAN_LEAVES = MAX_LEAVES + 1;   // the leaves of a program + the row mask of a masked scan
+constexpr int MAX_POSTFIX = 2 * MAX_SCAN_LEAVES;
 
 constexpr int CONSUMER_WARPS = 8;
 constexpr int SCAN_THREADS = (CONSUMER_WARPS + 1) * 32;   // + 1 TMA producer warp
@@ -142,24 +143,24 @@ struct ScanParams {
     uint32_t stages;           // depth of the TMA ring (<= MAX_STAGES)
     uint32_t tiles_per_pack;   // uniform case
     uint32_t stage_bytes;
-    uint32_t set_off[MAX_LEAVES + 1];
-    uint32_t tab_off[MAX_LEAVES];     // LM_HASHSET: first u64 of the leaf's table in set_tabs
-    uint8_t  tab_log2[MAX_LEAVES];    //             log2(#buckets) >= 1
+    uint32_t set_off[MAX_SCAN_LEAVES + 1];
+    uint32_t tab_off[MAX_SCAN_LEAVES];     // LM_HASHSET: first u64 of the leaf's table in set_tabs
+    uint8_t  tab_log2[MAX_SCAN_LEAVES];    //             log2(#buckets) >= 1
     // LM_HASHSET: a one-hash prefilter bitmap of 2^pre_log2 bits per leaf (bit set_hash32(v) >> (32 - pre_log2)), copied
     // into shared memory at hs_smem_off[l] (word offset behind the code bitmaps); the exact table is copied to
     // hs_tab_smem_off[l] as well when it is small (0xffffffff: looked up in global memory)
     const uint32_t* set_pre;          // concatenated prefilter bitmaps
-    uint32_t pre_off[MAX_LEAVES];     // first word of the leaf's bitmap in set_pre
-    uint8_t  pre_log2[MAX_LEAVES];    // 0: leaf has no table
-    uint32_t hs_smem_off[MAX_LEAVES];
-    uint32_t hs_tab_smem_off[MAX_LEAVES];
+    uint32_t pre_off[MAX_SCAN_LEAVES];     // first word of the leaf's bitmap in set_pre
+    uint8_t  pre_log2[MAX_SCAN_LEAVES];    // 0: leaf has no table
+    uint32_t hs_smem_off[MAX_SCAN_LEAVES];
+    uint32_t hs_tab_smem_off[MAX_SCAN_LEAVES];
     uint32_t agg_view0;        // views[agg_view0 + pack * naggs + j]
     uint32_t leaf_view0;       // views[leaf_view0 + pack * nleaves + l]
     uint8_t  postfix[MAX_POSTFIX];
     uint8_t  agg_type[MAX_AGGS];
     // LM_CODESET leaves: the current pack's code bitmap of leaf l is cached in shared memory (after the ring) at word
     // code_smem_off[l]; code_smem_words = size of that area (0: the program has no such leaf)
-    uint32_t code_smem_off[MAX_LEAVES];
+    uint32_t code_smem_off[MAX_SCAN_LEAVES];
     uint32_t code_smem_words;
     uint32_t code_bitmap_words;       // words of that area holding per-pack code bitmaps (0: nothing to reload per pack)
     // general kernel: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp; trees that are not a

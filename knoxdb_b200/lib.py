@@ -14,14 +14,18 @@ NP = {INT64: np.int64, INT32: np.int32, INT16: np.int16, INT8: np.int8, UINT64: 
       UINT16: np.uint16, UINT8: np.uint8, FLOAT64: np.float64, FLOAT32: np.float32}
 
 ABI_SYMBOLS = [
-    "kx_abi_version", "kx_ctx_create", "kx_ctx_destroy", "kx_last_error", "kx_host_alloc", "kx_host_free",
+    "kx_abi_version", "kx_device_count", "kx_ctx_create", "kx_ctx_destroy", "kx_last_error", "kx_host_alloc", "kx_host_free",
     "kx_block_put", "kx_block_drop", "kx_store_stats", "kx_prog_compile", "kx_prog_free", "kx_scan", "kx_scan_host",
     "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
     "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
     "kx_hash_value", "kx_hash_bytes",
     "kx_scan_select", "kx_gather", "kx_scan_buckets",
     "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
+    "kx_scan_ex", "kx_last_query_stats", "kx_comm_unique_id", "kx_comm_init", "kx_comm_info", "kx_scan_sharded", "kx_comm_allgather",
 ]
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
+GUARD = 32          # bytes of 0xFA behind every output buffer the binding allocates (internal/cmp/tests/gen.go:13-44)
 
 
 class KnoxError(RuntimeError):
@@ -41,6 +45,34 @@ class _PackRef(C.Structure):
 
 class _AggReq(C.Structure):
     _fields_ = [("field", C.c_uint16), ("block_type", C.c_uint8), ("reserved", C.c_uint8)]
+
+
+class ScanArgs(C.Structure):
+    _fields_ = [("struct_size", C.c_uint32), ("flags", C.c_uint32), ("packs", C.POINTER(_PackRef)), ("npacks", C.c_int32), ("naggs", C.c_int32),
+                ("row_masks", C.POINTER(C.c_void_p)), ("bitsets", C.c_void_p), ("bitset_off", C.c_void_p), ("counts", C.c_void_p),
+                ("sel", C.c_void_p), ("sel_cap", C.c_size_t), ("sel_off", C.c_void_p), ("aggs", C.POINTER(_AggReq)), ("agg_out", C.c_void_p),
+                ("total_count", C.POINTER(C.c_int64))]
+
+
+SCAN_SHARDED = 1
+
+
+class QueryStats(C.Structure):
+    _fields_ = [("rows_scanned", C.c_uint64), ("packs_scanned", C.c_uint64), ("rows_matched", C.c_uint64), ("scan_time_ns", C.c_uint64),
+                ("total_time_ns", C.c_uint64), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+def guarded(nbytes_or_count, dtype=np.uint8):
+    """zeroed output array followed by GUARD bytes of 0xFA (the reference poisons the slack of its test outputs the same way);
+    check_guard() proves that a kernel / copy did not write past the end"""
+    item = np.dtype(dtype).itemsize
+    raw = np.zeros(int(nbytes_or_count) * item + GUARD, dtype=np.uint8)
+    raw[int(nbytes_or_count) * item:] = 0xFA
+    return raw[:int(nbytes_or_count) * item].view(dtype), raw
+
+
+def check_guard(raw):
+    assert (raw[-GUARD:] == 0xFA).all(), "libknoxgpu wrote past the end of an output buffer"
 
 
 class AggOut(C.Structure):
@@ -75,6 +107,7 @@ def lib():
     vp, u8p, u64p, sz = C.c_void_p, C.POINTER(C.c_uint8), C.POINTER(C.c_uint64), C.c_size_t
     sig = {
         "kx_abi_version": (C.c_int, []),
+        "kx_device_count": (C.c_int, []),
         "kx_ctx_create": (C.c_int, [C.c_int, sz, C.POINTER(vp)]),
         "kx_ctx_destroy": (None, [vp]),
         "kx_last_error": (C.c_char_p, [vp]),
@@ -82,13 +115,13 @@ def lib():
         "kx_host_free": (None, [vp, vp]),
         "kx_block_put": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint16, C.c_uint8, vp, sz, C.POINTER(C.c_uint32)]),
         "kx_block_drop": (C.c_int, [vp, C.c_uint32, C.c_uint32, C.c_uint16]),
-        "kx_store_stats": (C.c_int, [vp, u64p, u64p, u64p]),
+        "kx_store_stats": (C.c_int, [vp, u64p, u64p, u64p, u64p]),
         "kx_prog_compile": (C.c_int, [vp, C.POINTER(_Leaf), C.c_int, vp, C.c_int, C.POINTER(vp)]),
         "kx_prog_free": (None, [vp]),
         "kx_scan": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_scan_select": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, sz, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_scan_buckets": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, C.c_int, C.POINTER(_AggReq), C.c_int, vp,
-                                      C.POINTER(AggOut), vp]),
+                                      C.POINTER(AggOut), vp, vp]),
         "kx_gather": (C.c_int, [vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, vp, vp]),
         "kx_scan_host": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_agg_combine": (C.c_int, [C.c_uint8, C.POINTER(AggOut), C.c_int, C.POINTER(AggOut)]),
@@ -111,6 +144,13 @@ def lib():
         "kx_prune_stats": (C.c_int64, [vp, vp, vp, vp, vp, vp]),
         "kx_hash_value": (C.c_uint64, [C.c_uint8, C.c_uint64]),
         "kx_hash_bytes": (C.c_uint64, [vp, sz]),
+        "kx_scan_ex": (C.c_int, [vp, vp, C.POINTER(ScanArgs)]),
+        "kx_last_query_stats": (C.c_int, [vp, C.POINTER(QueryStats)]),
+        "kx_comm_unique_id": (C.c_int, [vp, sz]),
+        "kx_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
+        "kx_comm_info": (C.c_int, [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+        "kx_scan_sharded": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut), C.POINTER(C.c_int64)]),
+        "kx_comm_allgather": (C.c_int, [vp, vp, vp, sz]),
     }
     assert sorted(sig) == sorted(ABI_SYMBOLS)
     for name, (res, args) in sig.items():
@@ -249,9 +289,52 @@ class Context:
         self._check(lib().kx_block_drop(self.h, pack, version, field))
 
     def store_stats(self):
-        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
-        self._check(lib().kx_store_stats(self.h, C.byref(a), C.byref(b), C.byref(c)))
-        return {"blocks": a.value, "encoded_bytes": b.value, "device_bytes": c.value}
+        a, b, c, d = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        self._check(lib().kx_store_stats(self.h, C.byref(a), C.byref(b), C.byref(c), C.byref(d)))
+        return {"blocks": a.value, "encoded_bytes": b.value, "device_bytes": c.value, "slab_bytes": d.value}
+
+    # ---- multi-GPU: pack-sharded scans (one context per GPU / rank)
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the communicator id (ncclGetUniqueId) to hand to the other ranks"""
+        buf = np.zeros(COMM_ID_BYTES, dtype=np.uint8)
+        rc = lib().kx_comm_unique_id(_ptr(buf), buf.size)
+        if rc != 0:
+            raise KnoxError(rc, (lib().kx_last_error(None) or b"").decode())
+        return buf
+
+    def comm_init(self, nranks, rank, comm_id=None):
+        cid = None if comm_id is None else np.ascontiguousarray(comm_id, dtype=np.uint8)
+        self._check(lib().kx_comm_init(self.h, nranks, rank, _ptr(cid), 0 if cid is None else cid.size))
+
+    def comm_info(self):
+        n, r, v = C.c_int(), C.c_int(), C.c_int()
+        self._check(lib().kx_comm_info(self.h, C.byref(n), C.byref(r), C.byref(v)))
+        return {"nranks": n.value, "rank": r.value, "nccl_version": v.value}
+
+    def scan_sharded(self, prog, packs, aggs=(), want_counts=True):
+        """kx_scan_sharded: this rank's packs in, totals combined over all ranks out (collective).
+        Returns dict(counts (local, per pack), total_count (global), aggs (global))."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        counts = np.zeros(max(len(refs), 1), dtype=np.int64) if want_counts else None
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs), 1))()
+        total = C.c_int64()
+        self._check(lib().kx_scan_sharded(self.h, prog.h, refs, len(refs), _ptr(counts), areq, len(aggs), aout, C.byref(total)))
+        return {"counts": None if counts is None else counts[:len(refs)], "total_count": total.value, "aggs": list(aout)[:len(aggs)]}
+
+    def comm_allgather(self, send):
+        """every rank contributes the same number of bytes; returns [nranks, nbytes] uint8 in rank order"""
+        send = np.ascontiguousarray(send).view(np.uint8).reshape(-1)
+        n = self.comm_info()["nranks"]
+        recv = np.zeros((n, send.size), dtype=np.uint8)
+        self._check(lib().kx_comm_allgather(self.h, _ptr(send), _ptr(recv), send.size))
+        return recv
+
+    def last_query_stats(self):
+        q = QueryStats()
+        self._check(lib().kx_last_query_stats(self.h, C.byref(q)))
+        return {k: getattr(q, k) for k, _ in QueryStats._fields_ if k != "reserved"}
 
     # ---- scans
     @staticmethod
@@ -275,10 +358,12 @@ class Context:
         offs = bits = None
         if want_bitsets:
             offs, total = self.bitset_layout(nrows)
-            bits = bitset_buf if bitset_buf is not None else np.zeros(total, dtype=np.uint8)
+            bits, raw = (bitset_buf, None) if bitset_buf is not None else guarded(total)
         areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
         aout = (AggOut * max(len(aggs), 1))()
         self._check(lib().kx_scan(self.h, prog.h, refs, len(packs), _ptr(bits), _ptr(offs), _ptr(counts), areq, len(aggs), aout))
+        if want_bitsets and raw is not None:
+            check_guard(raw)
         out = {"counts": counts, "aggs": list(aout)[:len(aggs)]}
         if want_bitsets:
             out["bitsets"] = [bits[int(o):int(o) + (int(n) + 7) // 8] for o, n in zip(offs, nrows)]
@@ -304,7 +389,58 @@ class Context:
             break
         return {"sel": sel[:int(sel_off[n])], "sel_off": sel_off, "counts": counts, "aggs": list(aout)[:len(aggs)]}
 
-    def scan_buckets(self, prog, packs, ts_field, ts_type, edges, aggs=()):
+    def scan_ex(self, prog, packs, nrows=None, masks=None, want_bitsets=False, want_sel=False, sel_cap=None, aggs=(), sharded=False):
+        """kx_scan_ex: masks = per pack None or a bitset (np.uint8, bit set = row stays eligible).
+        Returns dict(counts, aggs[, bitsets][, sel, sel_off][, total_count])."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        n = len(refs)
+        a = ScanArgs()
+        a.struct_size = C.sizeof(ScanArgs); a.flags = SCAN_SHARDED if sharded else 0
+        a.packs = refs; a.npacks = n; a.naggs = len(aggs)
+        keep = []
+        if masks is not None:
+            keep = [None if m is None else np.ascontiguousarray(m, dtype=np.uint8) for m in masks]
+            mp = (C.c_void_p * max(n, 1))(*[None if m is None else m.ctypes.data for m in keep])
+            a.row_masks = mp
+        counts = np.zeros(max(n, 1), dtype=np.int64)
+        a.counts = counts.ctypes.data
+        offs = bits = raw = None
+        if want_bitsets:
+            offs, total = self.bitset_layout(nrows)
+            bits, raw = guarded(total)
+            a.bitsets = raw.ctypes.data; a.bitset_off = offs.ctypes.data
+        areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
+        aout = (AggOut * max(len(aggs), 1))()
+        a.aggs = areq; a.agg_out = C.cast(aout, C.c_void_p)
+        total_count = C.c_int64()
+        a.total_count = C.pointer(total_count)
+        sel = sel_off = sraw = None
+        if want_sel:
+            sel_off = np.zeros(n + 1, dtype=np.uint64)
+            cap = 1 << 16 if sel_cap is None else sel_cap
+            while True:
+                sel, sraw = guarded(cap, np.uint32)
+                a.sel = sraw.ctypes.data; a.sel_cap = cap; a.sel_off = sel_off.ctypes.data
+                rc = lib().kx_scan_ex(self.h, prog.h, C.byref(a))
+                if rc == -3 and int(sel_off[n]) > cap:
+                    cap = int(sel_off[n])
+                    continue
+                self._check(rc)
+                check_guard(sraw)
+                break
+        else:
+            self._check(lib().kx_scan_ex(self.h, prog.h, C.byref(a)))
+        out = {"counts": counts[:n], "aggs": list(aout)[:len(aggs)]}
+        if want_bitsets:
+            check_guard(raw)
+            out["bitsets"] = [bits[int(o):int(o) + (int(k) + 7) // 8] for o, k in zip(offs, nrows)]
+        if want_sel:
+            out["sel"], out["sel_off"] = sel[:int(sel_off[n])], sel_off
+        if sharded:
+            out["total_count"] = total_count.value
+        return out
+
+    def scan_buckets(self, prog, packs, ts_field, ts_type, edges, aggs=(), masks=None):
         """kx_scan_buckets → dict(bucket_counts (nbuckets), aggs: per value column a list of nbuckets AggOut, counts (npacks)).
         edges: nbuckets + 1 ascending window starts (values of the timestamp column's type)."""
         refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
@@ -315,7 +451,11 @@ class Context:
         bcounts = np.zeros(max(nb, 1), dtype=np.int64)
         areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
         aout = (AggOut * max(len(aggs) * max(nb, 1), 1))()
-        self._check(lib().kx_scan_buckets(self.h, prog.h, refs, n, ts_field, ts_type, _ptr(e), nb, areq, len(aggs), _ptr(bcounts), aout, _ptr(counts)))
+        mp = keep = None
+        if masks is not None:
+            keep = [None if m is None else np.ascontiguousarray(m, dtype=np.uint8) for m in masks]
+            mp = (C.c_void_p * max(n, 1))(*[None if m is None else m.ctypes.data for m in keep])
+        self._check(lib().kx_scan_buckets(self.h, prog.h, refs, n, ts_field, ts_type, _ptr(e), nb, areq, len(aggs), _ptr(bcounts), aout, _ptr(counts), mp))
         return {"bucket_counts": bcounts[:nb], "aggs": [[aout[j * nb + k] for k in range(nb)] for j in range(len(aggs))], "counts": counts}
 
     def gather(self, packs, field, block_type, sel, sel_off):
@@ -323,9 +463,10 @@ class Context:
         refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
         sel = np.ascontiguousarray(sel, dtype=np.uint32)
         sel_off = np.ascontiguousarray(sel_off, dtype=np.uint64)
-        out = np.zeros(max(int(sel_off[-1]), 1), dtype=NP[block_type])
-        self._check(lib().kx_gather(self.h, refs, len(refs), field, block_type, _ptr(sel), _ptr(sel_off), _ptr(out)))
-        return out[:int(sel_off[-1])]
+        out, raw = guarded(int(sel_off[-1]), NP[block_type])
+        self._check(lib().kx_gather(self.h, refs, len(refs), field, block_type, _ptr(sel), _ptr(sel_off), _ptr(raw)))
+        check_guard(raw)
+        return out
 
     def scan_host(self, prog, fields, blocks, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
         """fields: [(field id, block type)]; blocks: per pack a list of encoded blocks (np.uint8 arrays) per field."""
@@ -339,11 +480,13 @@ class Context:
         offs = bits = None
         if want_bitsets:
             offs, total = self.bitset_layout(nrows)
-            bits = bitset_buf if bitset_buf is not None else np.zeros(total, dtype=np.uint8)
+            bits, raw = (bitset_buf, None) if bitset_buf is not None else guarded(total)
         areq = (_AggReq * max(len(aggs), 1))(*[_AggReq(f, t, 0) for f, t in aggs])
         aout = (AggOut * max(len(aggs), 1))()
         self._check(lib().kx_scan_host(self.h, prog.h, npacks, _ptr(fid), _ptr(fty), nf, ptrs, lens, _ptr(bits), _ptr(offs),
                                        _ptr(counts), areq, len(aggs), aout))
+        if want_bitsets and raw is not None:
+            check_guard(raw)
         out = {"counts": counts, "aggs": list(aout)[:len(aggs)]}
         if want_bitsets:
             out["bitsets"] = [bits[int(o):int(o) + (int(n) + 7) // 8] for o, n in zip(offs, nrows)]
@@ -357,39 +500,44 @@ class Context:
     # ---- narrow drop-ins
     def cmp(self, block_type, mode, src, a, b=0):
         src = np.ascontiguousarray(src, dtype=NP[block_type])
-        bits = np.zeros((src.size + 7) // 8 + 8, dtype=np.uint8)
-        cnt = self._check(lib().kx_cmp(self.h, block_type, mode, _ptr(src), src.size, pattern(block_type, a), pattern(block_type, b), _ptr(bits)))
-        return bits[:(src.size + 7) // 8], cnt
+        bits, raw = guarded((src.size + 7) // 8)
+        cnt = self._check(lib().kx_cmp(self.h, block_type, mode, _ptr(src), src.size, pattern(block_type, a), pattern(block_type, b), _ptr(raw)))
+        check_guard(raw)
+        return bits, cnt
 
     def bitpack_cmp(self, mode, packed, log2, a, b, n):
         packed = np.ascontiguousarray(packed)
-        bits = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
-        cnt = self._check(lib().kx_bitpack_cmp(self.h, mode, _ptr(packed), log2, _u64(a), _u64(b), n, _ptr(bits)))
-        return bits[:(n + 7) // 8], cnt
+        bits, raw = guarded((n + 7) // 8)
+        cnt = self._check(lib().kx_bitpack_cmp(self.h, mode, _ptr(packed), log2, _u64(a), _u64(b), n, _ptr(raw)))
+        check_guard(raw)
+        return bits, cnt
 
     def bitpack_decode(self, block_type, packed, log2, minv, n):
         packed = np.ascontiguousarray(packed)
-        out = np.zeros(max(n, 1), dtype=NP[block_type])
-        self._check(lib().kx_bitpack_decode(self.h, block_type, _ptr(packed), log2, _u64(minv), n, _ptr(out)))
-        return out[:n]
+        out, raw = guarded(n, NP[block_type])
+        self._check(lib().kx_bitpack_decode(self.h, block_type, _ptr(packed), log2, _u64(minv), n, _ptr(raw)))
+        check_guard(raw)
+        return out
 
     def container_match(self, block_type, enc, mode, a=0, b=0, values=None, nrows=None):
         enc = np.frombuffer(enc, dtype=np.uint8) if not isinstance(enc, np.ndarray) else enc
-        bits = np.zeros((nrows + 7) // 8 + 8, dtype=np.uint8)
+        bits, raw = guarded((nrows + 7) // 8)
         s = None
         if values is not None:
             s = np.asarray(values)
             s = s.astype(np.int64).view(np.uint64) if s.dtype.kind == "i" else s.astype(np.uint64)
             s = np.ascontiguousarray(s)
         cnt = self._check(lib().kx_container_match(self.h, block_type, _ptr(enc), enc.size, mode, pattern(block_type, a),
-                                                   pattern(block_type, b), _ptr(s), 0 if s is None else s.size, _ptr(bits)))
-        return bits[:(nrows + 7) // 8], cnt
+                                                   pattern(block_type, b), _ptr(s), 0 if s is None else s.size, _ptr(raw)))
+        check_guard(raw)
+        return bits, cnt
 
     def container_decode(self, block_type, enc, nrows):
         enc = np.frombuffer(enc, dtype=np.uint8) if not isinstance(enc, np.ndarray) else enc
-        out = np.zeros(max(nrows, 1), dtype=NP[block_type])
-        self._check(lib().kx_container_decode(self.h, block_type, _ptr(enc), enc.size, _ptr(out), nrows))
-        return out[:nrows]
+        out, raw = guarded(nrows, NP[block_type])
+        self._check(lib().kx_container_decode(self.h, block_type, _ptr(enc), enc.size, _ptr(raw), nrows))
+        check_guard(raw)
+        return out
 
     def bitset_op(self, op, dst, src, nbits):
         dst = np.ascontiguousarray(dst, dtype=np.uint8).copy()
@@ -409,8 +557,10 @@ class Context:
 
     def bitset_indexes(self, buf, nbits):
         buf = np.ascontiguousarray(buf, dtype=np.uint8)
-        out = np.zeros(nbits + 8, dtype=np.uint32)
-        n = self._check(lib().kx_bitset_indexes(self.h, _ptr(buf), nbits, _ptr(out)))
+        cnt = int(np.unpackbits(buf[:(nbits + 7) // 8], bitorder="little")[:nbits].sum())
+        out, raw = guarded(cnt, np.uint32)   # exactly as many ids as bits are set: any extra write hits the guard
+        n = self._check(lib().kx_bitset_indexes(self.h, _ptr(buf), nbits, _ptr(raw)))
+        check_guard(raw)
         return out[:n]
 
     def prune(self, prog, mins, maxs, blooms=None, hashes=None):

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     for name in decl:
         assert hasattr(L, name), f"{name} declared in knoxgpu.h but not exported"
     assert sorted(decl) == sorted(kb.ABI_SYMBOLS)
-    assert L.kx_abi_version() == 1
+    assert L.kx_abi_version() == 2
 
 
 def test_library_is_sm100a_native():
