@@ -15,7 +15,9 @@ import "C"
 
 import (
 	"errors"
+	"fmt"
 	"math"
+	"runtime"
 	"unsafe"
 
 	"blockwatch.cc/knoxdb/internal/operator/filter"
@@ -69,31 +71,33 @@ type Program struct {
 func (p *Program) Close() { C.kx_prog_free(p.h); p.h = nil }
 
 // pattern returns the 64-bit operand pattern the C ABI expects: sign-extended integers, IEEE bits
-// for floats (include/knoxgpu.h, kx_leaf).
-func pattern(v any) uint64 {
+// for floats (include/knoxgpu.h, kx_leaf).  Operand types the library does not scan (int, uint, bool,
+// time.Time, named types, 128/256-bit integers) are an error: a filter must never run with a zero operand
+// because its value could not be translated.
+func pattern(v any) (uint64, error) {
 	switch x := v.(type) {
 	case int64:
-		return uint64(x)
+		return uint64(x), nil
 	case int32:
-		return uint64(int64(x))
+		return uint64(int64(x)), nil
 	case int16:
-		return uint64(int64(x))
+		return uint64(int64(x)), nil
 	case int8:
-		return uint64(int64(x))
+		return uint64(int64(x)), nil
 	case uint64:
-		return x
+		return x, nil
 	case uint32:
-		return uint64(x)
+		return uint64(x), nil
 	case uint16:
-		return uint64(x)
+		return uint64(x), nil
 	case uint8:
-		return uint64(x)
+		return uint64(x), nil
 	case float64:
-		return math.Float64bits(x)
+		return math.Float64bits(x), nil
 	case float32:
-		return uint64(math.Float32bits(x))
+		return uint64(math.Float32bits(x)), nil
 	}
-	return 0
+	return 0, fmt.Errorf("knoxgpu: unsupported filter operand type %T", v)
 }
 
 // flatten lists the members of an IN/NIN set.  Set members are already `uint64(v)` of the column
@@ -132,11 +136,21 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 				// byte-string leaf (bytesMatcher, internal/operator/filter/match_bytes.go): operand bytes travel in a C
 				// copy behind `set`, nset = 1, a / b = lengths (RANGE: lower bound followed by the upper bound)
 				var lo, hi []byte
+				var ok bool
 				if f.Mode == types.FilterModeRange {
-					rg := f.Value.([2]any)
-					lo, hi = rg[0].([]byte), rg[1].([]byte)
+					rg, isRange := f.Value.([2]any)
+					if !isRange {
+						return fmt.Errorf("knoxgpu: range filter carries %T", f.Value)
+					}
+					lo, ok = rg[0].([]byte)
+					if ok {
+						hi, ok = rg[1].([]byte)
+					}
 				} else {
-					lo = f.Value.([]byte)
+					lo, ok = f.Value.([]byte)
+				}
+				if !ok {
+					return fmt.Errorf("knoxgpu: byte-string filter carries %T", f.Value)
 				}
 				p := C.malloc(C.size_t(len(lo) + len(hi) + 1))
 				buf := unsafe.Slice((*byte)(p), len(lo)+len(hi)+1)
@@ -148,12 +162,32 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 				leaves = append(leaves, l)
 				return nil
 			}
+			if f.Type == types.BlockBytes {
+				// IN / NOT IN on byte strings are matched by a hash set of strings in the reference
+				// (match_bytes.go); the library has no string sets: keep such filters on the stock path
+				return errors.New("knoxgpu: IN/NIN on byte-string columns is not supported")
+			}
 			switch f.Mode {
 			case types.FilterModeRange:
-				rg := f.Value.([2]any)
-				l.a, l.b = C.uint64_t(pattern(rg[0])), C.uint64_t(pattern(rg[1]))
+				rg, ok := f.Value.([2]any)
+				if !ok {
+					return fmt.Errorf("knoxgpu: range filter carries %T", f.Value)
+				}
+				lo, err := pattern(rg[0])
+				if err != nil {
+					return err
+				}
+				hi, err := pattern(rg[1])
+				if err != nil {
+					return err
+				}
+				l.a, l.b = C.uint64_t(lo), C.uint64_t(hi)
 			case types.FilterModeIn, types.FilterModeNotIn:
-				set := flatten(f.Matcher.Value().(*xroar.Bitmap))
+				bm, ok := f.Matcher.Value().(*xroar.Bitmap)
+				if !ok {
+					return fmt.Errorf("knoxgpu: set filter carries %T", f.Matcher.Value())
+				}
+				set := flatten(bm)
 				if len(set) > 0 {
 					p := C.malloc(C.size_t(8 * len(set)))
 					copy(unsafe.Slice((*uint64)(p), len(set)), set)
@@ -161,7 +195,11 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 					l.set, l.nset = (*C.uint64_t)(p), C.uint32_t(len(set))
 				}
 			default:
-				l.a = C.uint64_t(pattern(f.Value))
+				a, err := pattern(f.Value)
+				if err != nil {
+					return err
+				}
+				l.a = C.uint64_t(a)
 			}
 			post = append(post, C.uint8_t(len(leaves)))
 			leaves = append(leaves, l)
@@ -181,8 +219,14 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 		}
 		return nil
 	}
+	if root == nil {
+		return nil, errors.New("knoxgpu: empty filter tree")
+	}
 	if err := walk(root); err != nil {
 		return nil, err
+	}
+	if len(leaves) == 0 || len(post) == 0 {
+		return nil, errors.New("knoxgpu: filter tree without leaves") // (a match-all query needs no scan)
 	}
 	var h *C.kx_prog
 	if rc := C.kx_prog_compile(c.h, &leaves[0], C.int(len(leaves)), &post[0], C.int(len(post)), &h); rc != 0 {
@@ -262,4 +306,124 @@ func CombineAgg(t types.BlockType, parts []AggOut) AggOut {
 		C.kx_agg_combine(C.uint8_t(t), &in[0], C.int(len(in)), &o)
 	}
 	return AggOut{int64(o.count), uint64(o.sum_bits), float64(o.sum_err), uint64(o.min_bits), uint64(o.max_bits), o.valid != 0}
+}
+
+// ScanArgs collects the optional inputs / outputs of ScanEx (kx_scan_ex).
+type ScanArgs struct {
+	Keys, Versions []uint32
+	// Masks[i] (may be nil) holds one bit per row of pack i, bit set = row stays eligible: the complement of the
+	// reader's exclusion step — tombstoned rids from the journal and rows whose $xmin / $xmax fail the snapshot
+	// (internal/pack/table/reader.go:347-413; engine.TableReader.WithMask, internal/engine/interface.go:96-106).
+	Masks [][]byte
+	// outputs (all optional)
+	Bits      []byte   // per-pack bitsets at Offs[i] (multiples of 8)
+	Offs      []uint64 // …
+	Counts    []int64
+	Sel       []uint32 // selection vectors (not together with Bits); SelOff has len(Keys)+1 entries
+	SelOff    []uint64
+	AggFields []uint16
+	AggTypes  []types.BlockType
+	Sharded   bool // combine aggregates and TotalCount over all ranks of the communicator (collective)
+}
+
+// ScanEx is Scan with row masks, selection vectors and the cross-rank combine in one call.  Returns the aggregates
+// and, for sharded scans, the match count over all ranks.
+func (c *Context) ScanEx(prog *Program, a *ScanArgs) ([]AggOut, int64, error) {
+	n := len(a.Keys)
+	refs := make([]C.kx_packref, n+1)
+	for i := 0; i < n; i++ {
+		refs[i] = C.kx_packref{pack: C.uint32_t(a.Keys[i]), version: C.uint32_t(a.Versions[i])}
+	}
+	reqs := make([]C.kx_agg_req, len(a.AggFields)+1)
+	outs := make([]C.kx_agg_out, len(a.AggFields)+1)
+	for i := range a.AggFields {
+		reqs[i] = C.kx_agg_req{field: C.uint16_t(a.AggFields[i]), block_type: C.uint8_t(a.AggTypes[i])}
+	}
+	var total C.int64_t
+	args := C.kx_scan_args{struct_size: C.uint32_t(unsafe.Sizeof(C.kx_scan_args{})), packs: &refs[0], npacks: C.int32_t(n),
+		naggs: C.int32_t(len(a.AggFields)), aggs: &reqs[0], agg_out: &outs[0], total_count: &total}
+	if a.Sharded {
+		args.flags = C.KX_SCAN_SHARDED
+	}
+	// cgo: a C struct must not carry Go pointers to Go pointers, so the mask table lives in C memory and the masks
+	// are pinned for the duration of the call
+	var pin runtime.Pinner
+	defer pin.Unpin()
+	if len(a.Masks) == n && n > 0 {
+		tab := (*[1 << 28]*C.uint8_t)(C.malloc(C.size_t(n) * C.size_t(unsafe.Sizeof(uintptr(0)))))[:n:n]
+		defer C.free(unsafe.Pointer(&tab[0]))
+		for i, m := range a.Masks {
+			tab[i] = nil
+			if m != nil {
+				pin.Pin(unsafe.SliceData(m))
+				tab[i] = (*C.uint8_t)(unsafe.SliceData(m))
+			}
+		}
+		args.row_masks = (**C.uint8_t)(unsafe.Pointer(&tab[0]))
+	}
+	if a.Bits != nil {
+		pin.Pin(unsafe.SliceData(a.Bits)); pin.Pin(unsafe.SliceData(a.Offs))
+		args.bitsets = (*C.uint8_t)(unsafe.SliceData(a.Bits))
+		args.bitset_off = (*C.size_t)(unsafe.Pointer(unsafe.SliceData(a.Offs)))
+	}
+	if a.Counts != nil {
+		pin.Pin(unsafe.SliceData(a.Counts))
+		args.counts = (*C.int64_t)(unsafe.Pointer(unsafe.SliceData(a.Counts)))
+	}
+	if a.SelOff != nil {
+		pin.Pin(unsafe.SliceData(a.SelOff))
+		args.sel_off = (*C.uint64_t)(unsafe.Pointer(unsafe.SliceData(a.SelOff)))
+		if len(a.Sel) > 0 {
+			pin.Pin(unsafe.SliceData(a.Sel))
+			args.sel, args.sel_cap = (*C.uint32_t)(unsafe.SliceData(a.Sel)), C.size_t(len(a.Sel))
+		}
+	}
+	pin.Pin(&refs[0]); pin.Pin(&reqs[0]); pin.Pin(&outs[0]); pin.Pin(&total)
+	if rc := C.kx_scan_ex(c.h, prog.h, &args); rc != 0 {
+		return nil, 0, c.err()
+	}
+	res := make([]AggOut, len(a.AggFields))
+	for i := range res {
+		o := outs[i]
+		res[i] = AggOut{int64(o.count), uint64(o.sum_bits), float64(o.sum_err), uint64(o.min_bits), uint64(o.max_bits), o.valid != 0}
+	}
+	return res, int64(total), nil
+}
+
+// QueryStats mirrors kx_query_stats: the counters the reference reports through query.QueryStats
+// (internal/query/stats.go:15-60) for the last scan on this context.
+type QueryStats struct {
+	RowsScanned, PacksScanned, RowsMatched uint64
+	ScanTimeNs, TotalTimeNs                uint64
+	KernelLaunches                         uint32
+}
+
+func (c *Context) LastQueryStats() QueryStats {
+	var q C.kx_query_stats
+	C.kx_last_query_stats(c.h, &q)
+	return QueryStats{uint64(q.rows_scanned), uint64(q.packs_scanned), uint64(q.rows_matched), uint64(q.scan_time_ns), uint64(q.total_time_ns),
+		uint32(q.kernel_launches)}
+}
+
+// ---- multi-GPU: one Context per GPU, packs sharded by key, one NCCL all-gather per query inside the library
+
+// CommID creates the communicator id on rank 0 (ncclGetUniqueId); hand the bytes to the other ranks.
+func CommID() ([]byte, error) {
+	id := make([]byte, C.KX_COMM_ID_BYTES)
+	if rc := C.kx_comm_unique_id(unsafe.Pointer(&id[0]), C.size_t(len(id))); rc != 0 {
+		return nil, errors.New(C.GoString(C.kx_last_error(nil)))
+	}
+	return id, nil
+}
+
+// CommInit joins the communicator (collective: returns when all ranks called it).  One goroutine per GPU.
+func (c *Context) CommInit(nranks, rank int, id []byte) error {
+	var p unsafe.Pointer
+	if len(id) > 0 {
+		p = unsafe.Pointer(&id[0])
+	}
+	if rc := C.kx_comm_init(c.h, C.int(nranks), C.int(rank), p, C.size_t(len(id))); rc != 0 {
+		return c.err()
+	}
+	return nil
 }

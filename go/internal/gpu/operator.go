@@ -13,28 +13,150 @@ import (
 	"blockwatch.cc/knoxdb/internal/types"
 )
 
-// Filter is a drop-in operator.PushOperator (internal/operator/operator.go:31-42) for PhysicalFilter
-// (internal/operator/filter.go:29-37).  PhysicalFilter calls filter.Match per pack; this operator batches
-// BatchSize packs per kx_scan call so that one kernel launch covers the whole batch, then applies the same
-// post-processing (All → WithSelection(nil), else WithSelection(bits.Indexes(nil))) and hands the packs
-// downstream one by one.  Packs must have been registered with Context.PutBlock when they were loaded.
-type Filter struct {
+// BatchScan is a batching SOURCE: an operator.PullOperator (internal/operator/operator.go:31-35) that wraps the
+// upstream source of a pipeline (PhysicalTableScan without a filter, internal/operator/table_scan.go:15-47) and
+// replaces the pair "source → PhysicalFilter" (internal/operator/filter.go:29-37).
+//
+// Why a source and not a PushOperator: PhysicalPipeline.Execute (internal/operator/pipeline.go:103-161) pulls ONE
+// pack per call, treats ResultMore from an operator as "no output yet" and drops out of the loop, and finalize
+// only ever calls the sink.  An operator in the middle therefore cannot hold packs back and hand them out later:
+// they would be lost.  A source can: Next pulls up to BatchSize packs from upstream, evaluates the filter for all
+// of them with ONE kx_scan_ex call (selection vectors come back from the device), attaches the selections exactly
+// like PhysicalFilter does (WithSelection(nil) when every row matches, else the ids), and then hands the packs out
+// one per Next call.  Packs without a match are released and skipped — what Reader.nextQueryMatch does
+// (internal/pack/table/reader.go:336-345).  After upstream reports ResultDone the remaining packs are drained
+// before BatchScan itself reports ResultDone, so nothing is ever dropped.  BatchSize = 1 degenerates to the
+// reference's per-pack behaviour.
+//
+// MaskFn (optional) supplies the reader's exclusion step for a pack (tombstones ∪ invisible rows, as "eligible"
+// bits): reader.go:347-413.  Packs must have been registered with Context.PutBlock when they were loaded.
+type BatchScan struct {
 	ctx       *Context
 	prog      *Program
+	src       operator.PullOperator
 	BatchSize int
-	batch     []*pack.Package
+	MaskFn    func(*pack.Package) []byte
 	ready     []*pack.Package
+	srcDone   bool
 	err       error
+	stats     QueryStats
 }
 
-var _ operator.PushOperator = (*Filter)(nil)
+var _ operator.PullOperator = (*BatchScan)(nil)
 
-func NewFilter(ctx *Context, node *filter.Node, batch int) (*Filter, error) {
+func NewBatchScan(ctx *Context, src operator.PullOperator, node *filter.Node, batch int) (*BatchScan, error) {
 	prog, err := ctx.Compile(node)
 	if err != nil {
 		return nil, err
 	}
-	return &Filter{ctx: ctx, prog: prog, BatchSize: batch}, nil
+	if batch < 1 {
+		batch = 1
+	}
+	return &BatchScan{ctx: ctx, prog: prog, src: src, BatchSize: batch}, nil
+}
+
+func (op *BatchScan) Next(ctx context.Context) (*pack.Package, operator.Result) {
+	for len(op.ready) == 0 {
+		if op.srcDone {
+			return nil, operator.ResultDone
+		}
+		if err := op.fill(ctx); err != nil {
+			op.err = err
+			return nil, operator.ResultError // errors are stored and fetched with Err(), like every operator
+		}
+	}
+	p := op.ready[0]
+	op.ready = op.ready[1:]
+	return p, operator.ResultOK
+}
+
+// fill pulls the next batch from upstream and filters it on the device.
+func (op *BatchScan) fill(ctx context.Context) error {
+	batch := make([]*pack.Package, 0, op.BatchSize)
+	for len(batch) < op.BatchSize && !op.srcDone {
+		p, res := op.src.Next(ctx)
+		switch res {
+		case operator.ResultError:
+			return op.src.Err()
+		case operator.ResultDone:
+			op.srcDone = true
+		case operator.ResultOK:
+			if p == nil {
+				return operator.ErrNilPack
+			}
+			batch = append(batch, p)
+		default:
+			return operator.ErrTodo // a source never answers 'more' (pipeline.go:119-120)
+		}
+	}
+	n := len(batch)
+	if n == 0 {
+		return nil
+	}
+	a := &ScanArgs{Keys: make([]uint32, n), Versions: make([]uint32, n), Counts: make([]int64, n), SelOff: make([]uint64, n+1)}
+	rows := 0
+	for i, p := range batch {
+		a.Keys[i], a.Versions[i] = p.Key(), p.Version()
+		rows += p.Len()
+	}
+	if op.MaskFn != nil {
+		a.Masks = make([][]byte, n)
+		for i, p := range batch {
+			a.Masks[i] = op.MaskFn(p)
+		}
+	}
+	a.Sel = make([]uint32, rows) // worst case: every row matches
+	if _, _, err := op.ctx.ScanEx(op.prog, a); err != nil {
+		return err
+	}
+	st := op.ctx.LastQueryStats()
+	op.stats.RowsScanned += st.RowsScanned
+	op.stats.PacksScanned += st.PacksScanned
+	op.stats.RowsMatched += st.RowsMatched
+	op.stats.ScanTimeNs += st.ScanTimeNs
+	for i, p := range batch {
+		switch cnt := int(a.Counts[i]); {
+		case cnt == 0:
+			p.Release() // no match: the reader skips such packs (reader.go:336-345)
+		case cnt == p.Len():
+			op.ready = append(op.ready, p.WithSelection(nil))
+		default:
+			op.ready = append(op.ready, p.WithSelection(a.Sel[a.SelOff[i]:a.SelOff[i+1]:a.SelOff[i+1]]))
+		}
+	}
+	return nil
+}
+
+// Stats returns what the reference's reader feeds into query.QueryStats (internal/query/stats.go:15-60).
+func (op *BatchScan) Stats() QueryStats { return op.stats }
+func (op *BatchScan) Err() error       { return op.err }
+func (op *BatchScan) Close() {
+	for _, p := range op.ready {
+		p.Release()
+	}
+	op.ready = nil
+	op.src.Close()
+	op.prog.Close()
+}
+
+// Filter is the per-pack PushOperator with the exact contract of PhysicalFilter (one pack in, the same pack out,
+// ResultOK): a 1:1 replacement for pipelines that cannot change their source.  It never returns ResultMore and
+// never holds a pack back, so PhysicalPipeline.Execute loses nothing; batching needs BatchScan.
+type Filter struct {
+	ctx  *Context
+	prog *Program
+	bits []byte
+	err  error
+}
+
+var _ operator.PushOperator = (*Filter)(nil)
+
+func NewFilter(ctx *Context, node *filter.Node) (*Filter, error) {
+	prog, err := ctx.Compile(node)
+	if err != nil {
+		return nil, err
+	}
+	return &Filter{ctx: ctx, prog: prog}, nil
 }
 
 func (op *Filter) Process(_ context.Context, src *pack.Package) (*pack.Package, operator.Result) {
@@ -42,60 +164,25 @@ func (op *Filter) Process(_ context.Context, src *pack.Package) (*pack.Package, 
 		op.err = operator.ErrNilPack
 		return nil, operator.ResultError
 	}
-	op.batch = append(op.batch, src)
-	if len(op.batch) >= op.BatchSize {
-		if err := op.flush(); err != nil {
-			op.err = err
-			return nil, operator.ResultError // errors are stored and fetched with Err(), like every operator
-		}
+	nb := (((src.Len() + 7) >> 3) + 7) &^ 7
+	if cap(op.bits) < nb {
+		op.bits = make([]byte, nb)
 	}
-	return op.pop()
+	counts := []int64{0}
+	if _, err := op.ctx.Scan(op.prog, []uint32{src.Key()}, []uint32{src.Version()}, op.bits[:nb], []uint64{0}, counts, nil, nil); err != nil {
+		op.err = err
+		return nil, operator.ResultError
+	}
+	b := bitset.NewFromBytes(op.bits[:nb], src.Len()).ResetCount(int(counts[0]))
+	if b.All() {
+		src.WithSelection(nil)
+	} else {
+		src.WithSelection(b.Indexes(nil))
+	}
+	return src, operator.ResultOK
 }
 
-// pop hands out one finished pack; ResultMore tells the pipeline to call again without new input.
-func (op *Filter) pop() (*pack.Package, operator.Result) {
-	if len(op.ready) == 0 {
-		return nil, operator.ResultMore
-	}
-	p := op.ready[0]
-	op.ready = op.ready[1:]
-	if len(op.ready) > 0 {
-		return p, operator.ResultMore
-	}
-	return p, operator.ResultOK
-}
-
-func (op *Filter) flush() error {
-	n := len(op.batch)
-	if n == 0 {
-		return nil
-	}
-	keys, vers := make([]uint32, n), make([]uint32, n)
-	offs, counts := make([]uint64, n), make([]int64, n)
-	total := 0
-	for i, p := range op.batch {
-		keys[i], vers[i] = p.Key(), p.Version()
-		offs[i] = uint64(total)
-		total += (((p.Len() + 7) >> 3) + 7) &^ 7 // offsets must be multiples of 8
-	}
-	bits := make([]byte, total)
-	if _, err := op.ctx.Scan(op.prog, keys, vers, bits, offs, counts, nil, nil); err != nil {
-		return err
-	}
-	for i, p := range op.batch {
-		b := bitset.NewFromBytes(bits[offs[i]:], p.Len()).ResetCount(int(counts[i]))
-		if b.All() {
-			p.WithSelection(nil)
-		} else {
-			p.WithSelection(b.Indexes(nil))
-		}
-		op.ready = append(op.ready, p)
-	}
-	op.batch = op.batch[:0]
-	return nil
-}
-
-func (op *Filter) Finalize(_ context.Context) error { return op.flush() }
+func (op *Filter) Finalize(_ context.Context) error { return nil }
 func (op *Filter) Err() error                       { return op.err }
 func (op *Filter) Close()                           { op.prog.Close() }
 
@@ -110,6 +197,8 @@ type AggSink struct {
 	typs   []types.BlockType
 	keys   []uint32
 	vers   []uint32
+	masks  [][]byte
+	MaskFn func(*engine.Package) []byte // optional: eligible-row bits of a pack (reader.go:347-413)
 	rows   int
 }
 
@@ -121,6 +210,9 @@ func NewAggSink(ctx *Context, prog *Program, fields []uint16, typs []types.Block
 
 func (s *AggSink) Append(_ engine.Context, p *engine.Package) error {
 	s.keys, s.vers = append(s.keys, p.Key()), append(s.vers, p.Version())
+	if s.MaskFn != nil {
+		s.masks = append(s.masks, s.MaskFn(p))
+	}
 	s.rows += p.Len()
 	return nil
 }
@@ -128,6 +220,7 @@ func (s *AggSink) Append(_ engine.Context, p *engine.Package) error {
 func (s *AggSink) Len() int { return s.rows }
 
 // Finish runs the fused filter + reduce over every appended pack and returns one AggOut per value column.
-func (s *AggSink) Finish() ([]AggOut, error) {
-	return s.ctx.Scan(s.prog, s.keys, s.vers, nil, nil, nil, s.fields, s.typs)
+// sharded = true combines the result over all ranks of the communicator (every rank must call Finish).
+func (s *AggSink) Finish(sharded bool) ([]AggOut, int64, error) {
+	return s.ctx.ScanEx(s.prog, &ScanArgs{Keys: s.keys, Versions: s.vers, Masks: s.masks, AggFields: s.fields, AggTypes: s.typs, Sharded: sharded})
 }

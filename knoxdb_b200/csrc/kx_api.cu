@@ -613,12 +613,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         // general kernel: one stage = one leaf column (or one value chunk) of a whole tile.  The reduce lags one tile behind
         // the filter, so a tile keeps several stages busy: prefer the largest tile that leaves `want` stages (KX_MIN_STAGES),
         // else the largest one with two.  More than two value columns run one CTA per SM (accumulators stay in registers).
-        uint32_t want = naggs ? 4 : 3;
+        uint32_t want = 2;
         if (const char* e = getenv("KX_MIN_STAGES")) want = uint32_t(std::max(2, std::min(atoi(e), MAX_STAGES)));
         bool found = false;
         for (uint32_t need : {want, 2u}) {
             for (int ctas = naggs > 2 ? 1 : 2; ctas >= 1 && !found; --ctas) {
-                for (uint32_t r : {128u, 96u, 64u, 32u}) {
+                for (uint32_t r : {64u, 32u}) {
                     size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(ctas) - 128;
                     size_t extra = extra_smem_for(r), sb = stage_bytes_for(r);
                     if (per_cta < extra + need * sb) continue;
@@ -635,7 +635,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
         int c = 0, st = 0, r = 0;
         if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 &&
-            (simple ? (r <= 32 || r % 32 == 0) : (r % 32 == 0 && r <= 128 && c <= (naggs > 2 ? 1 : 2))) &&
+            (simple ? (r <= 32 || r % 32 == 0) : (r % 32 == 0 && r <= 64 && c <= (naggs > 2 ? 1 : 2))) &&
             128 + size_t(st) * stage_bytes_for(uint32_t(r)) + extra_smem_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
             geo.ctas = c; geo.stages = st; R = uint32_t(r);
         }
@@ -704,9 +704,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     uint32_t sched_chunk = 4;
     if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, atoi(e)));
     const uint64_t max_grid = uint64_t(ctx->num_sms) * geo.ctas;
-    if (simple || (ntiles + sched_chunk - 1) / sched_chunk < 2 * max_grid) sched_chunk = 1;
-    int grid = int(std::min<uint64_t>((uint64_t(ntiles) + sched_chunk - 1) / sched_chunk, max_grid));
+    if (simple) sched_chunk = 1;
+    int grid = int(std::min<uint64_t>(ntiles, max_grid));
     if (grid < 1) grid = 1;
+    const uint32_t sched_rounds = uint32_t(uint64_t(ntiles) / (uint64_t(grid) * sched_chunk));   // full rounds of chunks; the rest goes tile by tile
     if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
     CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
@@ -749,6 +750,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.desc_words = desc_words;
     P.flat_op = flat_op;
     P.sched_chunk = sched_chunk;
+    P.sched_rounds = sched_rounds;
     P.prod_sleep = getenv("KX_PROD_SLEEP") ? uint32_t(atoi(getenv("KX_PROD_SLEEP"))) : 0u;
     P.agg_dense_thr = agg_dense_thr;
     P.bitsets = dev_bits ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;

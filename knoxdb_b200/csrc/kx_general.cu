@@ -7,7 +7,7 @@
 // (bitsets are written only when the caller asks for them).
 //
 // Structure (persistent CTAs, 8 consumer warps + 1 TMA producer warp):
-//   * Tiles of 256 R rows (R = 32 … 128 groups of 32 rows per consumer warp) are dealt to the CTAs in chunks of
+//   * Tiles of 256 R rows (R = 32 or 64 groups of 32 rows per consumer warp: one or two passes) are dealt to the CTAs in chunks of
 //     `sched_chunk` consecutive tiles, round-robin: a static schedule (results are reproducible run to run) that
 //     spreads the expensive and the cheap regions of every pack (e.g. the part of a time-ordered pack a range
 //     predicate selects) over all SMs.
@@ -37,27 +37,48 @@ namespace kx {
 
 namespace {
 
-// static tile schedule shared by the producer and the consumers of a CTA
+// static tile schedule shared by the producer and the consumers of a CTA: `sched_rounds` full rounds in which CTA b
+// takes chunk (round * gridDim + b) of sched_chunk consecutive tiles, then the remaining tiles one by one (round-robin):
+// no CTA gets more than one tile above the average, whatever the chunk size
 struct TileSched {
     const ScanParams& P;
     uint32_t tile_rows;
-    uint32_t t = 0, t_stop = 0, cidx = 0;
+    uint32_t t = 0, t_stop = 0, round = 0;
     uint32_t pack = 0, chunk = 0, pack_tiles = 0;
     PackInfo pi{};
 
     __device__ __forceinline__ TileSched(const ScanParams& p, uint32_t tr) : P(p), tile_rows(tr) {}
     __device__ __forceinline__ bool open_chunk() {
-        const uint64_t t0 = (uint64_t)cidx * P.sched_chunk;
-        if (t0 >= P.ntiles) return false;
+        uint64_t t0;
+        if (round < P.sched_rounds) {
+            t0 = ((uint64_t)round * gridDim.x + blockIdx.x) * P.sched_chunk;
+            t_stop = (uint32_t)(t0 + P.sched_chunk);
+        } else {
+            t0 = (uint64_t)P.sched_rounds * gridDim.x * P.sched_chunk + (uint64_t)(round - P.sched_rounds) * gridDim.x + blockIdx.x;
+            if (t0 >= P.ntiles) return false;
+            t_stop = (uint32_t)t0 + 1u;
+        }
         t = (uint32_t)t0;
-        t_stop = (uint32_t)min((uint64_t)P.ntiles, t0 + P.sched_chunk);
         pack = P.tile_pack ? __ldg(P.tile_pack + t) : t / P.tiles_per_pack;
         pi = P.packs[pack];
         pack_tiles = (pi.n + tile_rows - 1) / tile_rows;
         chunk = t - pi.tile0;
         return true;
     }
-    __device__ __forceinline__ bool start() { cidx = blockIdx.x; return open_chunk(); }
+    // pack of the tile this CTA handles next (uniform packs only; 0xffffffff: unknown / none): lets the consumers warm
+    // its descriptors while they filter the current tile — with small scheduling chunks almost every tile is another pack
+    __device__ __forceinline__ uint32_t peek_pack() const {
+        if (P.tile_pack) return 0xffffffffu;
+        uint64_t tn;
+        if (t + 1u < t_stop) tn = (uint64_t)t + 1u;
+        else {
+            const uint32_t r = round + 1u;
+            tn = r < P.sched_rounds ? ((uint64_t)r * gridDim.x + blockIdx.x) * P.sched_chunk
+                                    : (uint64_t)P.sched_rounds * gridDim.x * P.sched_chunk + (uint64_t)(r - P.sched_rounds) * gridDim.x + blockIdx.x;
+        }
+        return tn < P.ntiles ? (uint32_t)(tn / P.tiles_per_pack) : 0xffffffffu;
+    }
+    __device__ __forceinline__ bool start() { round = 0; return open_chunk(); }
     __device__ __forceinline__ bool next() {
         if (++t < t_stop) {
             if (++chunk >= pack_tiles) {
@@ -67,24 +88,10 @@ struct TileSched {
             }
             return true;
         }
-        cidx += gridDim.x;
+        ++round;
         return open_chunk();
     }
 };
-
-__device__ __forceinline__ uint32_t get4(const uint32_t (&w)[4], uint32_t i) {
-    uint32_t x = w[0];
-    if (i == 1) x = w[1];
-    if (i == 2) x = w[2];
-    if (i == 3) x = w[3];
-    return x;
-}
-__device__ __forceinline__ void set4(uint32_t (&w)[4], uint32_t i, uint32_t x) {
-    if (i == 0) w[0] = x;
-    if (i == 1) w[1] = x;
-    if (i == 2) w[2] = x;
-    if (i == 3) w[3] = x;
-}
 
 template <bool F64>
 __device__ __forceinline__ void acc_raw64(AggAcc& A, uint64_t raw, uint64_t base, uint64_t flip) {
@@ -184,8 +191,12 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
     uint8_t* stage_base = smem + 128;
     __shared__ AggAcc warp_acc[CONSUMER_WARPS];
     __shared__ unsigned long long warp_cnt[CONSUMER_WARPS];
-    __shared__ unsigned int sm_match, sm_wtiles;   // matches / (warp, tile) pairs finished so far: selectivity feedback for the producer
-    __shared__ uint32_t stage_flag[MAX_STAGES];    // per ring slot: 1 = the value columns of the PREVIOUS tile follow this tile's leaf stages
+    __shared__ unsigned int sm_match[CONSUMER_WARPS], sm_wtiles[CONSUMER_WARPS];   // per warp: matches / tiles finished so far — selectivity feedback for the producer (plain stores)
+    // The staging decision of every tile is EXACT: the producer waits until all consumer warps have published the tile's
+    // match count (they are already filtering the next tile, whose leaf columns are in flight), decides, records the
+    // decision in a small ring and bumps sm_decided; the consumers read it when they get to the tile's reduce.
+    __shared__ uint32_t sm_dense[8];
+    __shared__ unsigned int sm_decided;
     constexpr bool AGG = NA > 0;
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
@@ -196,7 +207,8 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
     const uint32_t KP = AGG ? P.agg_kp : 1u, G = 32u / KP, lgG = 31u - (uint32_t)__clz((int)G);
 
     if (threadIdx.x == 0) {
-        sm_match = 0; sm_wtiles = 0;
+        for (int w = 0; w < CONSUMER_WARPS; ++w) { sm_match[w] = 0; sm_wtiles[w] = 0; }
+        sm_decided = 0;
         for (uint32_t s = 0; s < nstages; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -212,11 +224,10 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                 if (P.prod_sleep) mbar_wait_relaxed(&empty_bar[s], ph ^ 1u); else mbar_wait(&empty_bar[s], ph ^ 1u);   // slot released by all consumer warps
             };
             auto advance = [&]() { if (++s == nstages) { s = 0; ph ^= 1u; } };
-            auto load_stream = [&](const uint8_t* data, size_t off, uint32_t w, uint32_t rows, uint32_t flag) {
+            auto load_stream = [&](const uint8_t* data, size_t off, uint32_t w, uint32_t rows) {
+                if (!data) return;                          // (the consumers test the same pointer)
                 acquire();
-                if (!data) w = 0;
                 const uint32_t bytes = w ? ((((rows * w + 7u) >> 3) + 15u) & ~15u) : 0u;
-                stage_flag[s] = flag;                       // published by the arrive below (release) / the consumers' wait (acquire)
                 mbar_expect_tx(&full_bar[s], bytes);        // arrive (count 1) + expected bytes
                 if (bytes) tma_load_1d(stage_base + (size_t)s * P.stage_bytes, data + off, bytes, &full_bar[s]);
                 advance();
@@ -230,7 +241,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                     for (uint32_t pass = 0; pass < passes; ++pass) {
                         for (uint32_t q = 0; q < KP; ++q) {
                             acquire();
-                            stage_flag[s] = 1u;
                             uint32_t total = 0;
                             for (uint32_t w = 0; w < CONSUMER_WARPS; ++w) {
                                 const uint32_t r0 = row0 + ((w * R + pass * 32u + q * G) << 5);
@@ -250,56 +260,65 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                     }
                 }
             };
-            uint32_t pf_m0 = 0, pf_d0 = 0;   // selectivity feedback snapshot
-            bool dense = P.agg_dense_thr == 0;
-            auto decide = [&]() -> uint32_t {
-                if (P.agg_dense_thr != 0 && P.agg_dense_thr != 0xffffffffu) {
-                    const uint32_t m = *(volatile unsigned int*)&sm_match, d = *(volatile unsigned int*)&sm_wtiles;
-                    if (d - pf_d0 >= CONSUMER_WARPS) {
-                        dense = (uint64_t)(m - pf_m0) * P.agg_dense_thr * CONSUMER_WARPS > (uint64_t)(d - pf_d0) * tile_rows;
-                        pf_m0 = m; pf_d0 = d;
+            // decision for the tile with sequence number `seq` (0-based, in this CTA's schedule): wait for its match count
+            uint32_t m_seen = 0;
+            auto decide = [&](uint32_t seq, uint32_t rows) -> bool {
+                uint32_t m;
+                for (;;) {
+                    uint32_t done = 0xffffffffu;
+                    m = 0;
+                    for (int w = 0; w < CONSUMER_WARPS; ++w) {
+                        done = min(done, *(volatile unsigned int*)&sm_wtiles[w]);
+                        m += *(volatile unsigned int*)&sm_match[w];
                     }
+                    if (done > seq) break;
+                    __nanosleep(64);
                 }
-                return dense ? 1u : 0u;
+                // (a warp that ran ahead may already have added the next tile's matches: the count is cumulative, the
+                // surplus is not counted again next time; the decision only has to be the SAME for all consumers)
+                const uint32_t cnt = m - m_seen;
+                m_seen = m;
+                const bool dense = P.agg_dense_thr == 0u ? true : (P.agg_dense_thr == 0xffffffffu ? false : (uint64_t)cnt * P.agg_dense_thr > rows);
+                sm_dense[seq & 7u] = dense ? 1u : 0u;
+                __threadfence_block();
+                *(volatile unsigned int*)&sm_decided = seq + 1u;
+                return dense;
             };
             bool have_prev = false;
-            uint32_t prev_pack = 0, prev_row0 = 0, prev_n = 0;
+            uint32_t prev_pack = 0, prev_row0 = 0, prev_n = 0, prev_rows = 0, seq = 0;
             do {
                 const uint32_t row0 = ts.chunk * tile_rows, rows = min(tile_rows, ts.pi.n - row0);
                 const PackLeaf* L = P.leaves + (size_t)ts.pack * nl;
                 const size_t tile_byte0 = (size_t)ts.chunk * (tile_rows / 8u);   // * width = first byte of the tile in a stream
-                const uint32_t flag = (AGG && have_prev) ? decide() : 0u;
-                bool told = false;
                 for (uint32_t i = 0; i < P.npost; ++i) {
                     const uint32_t op = P.postfix[i];
                     if (op >= 0x80u) continue;
-                    if (L[op].data) { load_stream(L[op].data, tile_byte0 * L[op].width, L[op].width, rows, flag); told = true; }
-                    if (L[op].fixmode) { load_stream(L[op].fix, tile_byte0, 1u, rows, flag); told = true; }      // ALP patch correction stream
+                    load_stream(L[op].data, tile_byte0 * L[op].width, L[op].width, rows);
+                    if (L[op].fixmode) load_stream(L[op].fix, tile_byte0, 1u, rows);      // ALP patch correction stream
                 }
                 if constexpr (AGG) {
-                    if (!told) load_stream(nullptr, 0, 0u, 0u, flag);   // no leaf column is staged: an empty stage carries the decision
-                    if (flag) load_values(prev_pack, prev_row0, prev_n);
-                    prev_pack = ts.pack; prev_row0 = row0; prev_n = ts.pi.n; have_prev = true;
+                    // the previous tile's value columns follow this tile's leaf columns — if it matched densely
+                    if (have_prev && decide(seq - 1u, prev_rows)) load_values(prev_pack, prev_row0, prev_n);
+                    prev_pack = ts.pack; prev_row0 = row0; prev_n = ts.pi.n; prev_rows = rows; have_prev = true;
                 }
+                ++seq;
             } while (ts.next());
             if constexpr (AGG) {
-                if (have_prev) {   // the value columns of the last tile
-                    const uint32_t flag = decide();
-                    load_stream(nullptr, 0, 0u, 0u, flag);
-                    if (flag) load_values(prev_pack, prev_row0, prev_n);
-                }
+                if (have_prev && decide(seq - 1u, prev_rows)) load_values(prev_pack, prev_row0, prev_n);   // the value columns of the last tile
             }
         }
         return;
     }
 
     // ===================== consumers: unpack + filter + reduce =====================
+    // (passes <= 2: R is 32 or 64, so the per-pass match words are two named registers and every pass loop is unrolled)
     AggAcc acc[AGG ? NA : 1];
 #pragma unroll
     for (int j = 0; j < (AGG ? NA : 1); ++j) acc[j] = agg_identity(AGG ? P.agg_type[j] : 0);
     unsigned long long nmatch = 0;   // matches this thread accounted for (per-CTA totals only)
     uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
     const uint32_t gw0 = warp * R;   // first group (of the tile) of this warp
+    const bool two = passes == 2u;
     // shared memory behind the bitmaps: the warp's AND/OR stack (general trees only) and its descriptor cache
     // (the current pack's leaves; the value-column views of the current and the previous pack)
     uint32_t* stk = code_smem + P.stack_off_words + warp * (P.stack_depth * passes * 32u);
@@ -333,15 +352,16 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
     }
 
     uint32_t s = 0, ph = 0;
+    const uint32_t full0 = smem_addr(full_bar), empty0 = smem_addr(empty_bar);   // 32-bit shared addresses of the ring barriers
     auto release = [&]() {   // this warp is done with ring stage s
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty_bar[s]);
+        if (lane == 0) mbar_arrive_a(empty0 + s * 8u);
         if (++s == nstages) { s = 0; ph ^= 1u; }
     };
 
     // ---- the lagging reduce: match words of the previous tile (registers), where its rows are, which views describe it
-    uint32_t wprev[4] = {0u, 0u, 0u, 0u};
-    bool have_prev = false;
+    uint32_t wp0 = 0u, wp1 = 0u, fb_match = 0u, fb_tiles = 0u, seq = 0u;   // seq: tiles this warp has filtered
+    bool have_prev = false, prev_any = false;
     uint32_t prev_row0 = 0, prev_sel = 0;
     auto reduce_prev = [&](bool dense) {
         const uint32_t gl = lane & (G - 1u), sub = lane >> lgG, rot = gl;
@@ -349,16 +369,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
         for (int j = 0; j < (AGG ? NA : 0); ++j) {
             if ((uint32_t)j >= na) break;
             const ColView& v = AV[prev_sel * na + j];
-            const int type = P.agg_type[j];
             const bool staged = dense && agg_stageable(v);
+            if (!staged && !prev_any) continue;   // nothing matched in this warp's rows and no ring stage to consume
+            const int type = P.agg_type[j];
             const bool raw64 = v.kind == CK_BITS && v.width == 64;
             const uint64_t flip = type_is_signed(type) ? 0x8000000000000000ull : 0ull;
             const uint32_t slice_bytes = 4u * G * v.width;   // 32 G rows of the column
             AggAcc a = acc[j];
-            for (uint32_t pass = 0; pass < passes; ++pass) {
-                const uint32_t wp = get4(wprev, pass);
+#pragma unroll
+            for (uint32_t pass = 0; pass < 2u; ++pass) {
+                if (pass >= passes) break;
+                const uint32_t wp = pass ? wp1 : wp0;
                 for (uint32_t q = 0; q < KP; ++q) {
-                    if (staged) mbar_wait(&full_bar[s], ph);
+                    if (staged) mbar_wait_a(full0 + s * 8u, ph);
                     const uint32_t word = KP == 1u ? wp : __shfl_sync(0xffffffffu, wp, q * G + gl);
                     const uint32_t r = lane_rows(word, sub, G, rot);
                     const uint32_t srow0 = gl * 32u + sub * G;                                               // first row of the lane's range inside the warp's slice
@@ -416,13 +439,23 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                 }
                 cur_pack = pack;
             }
+            if (warp == 0) {
+                // warm the descriptors of this CTA's next tile (L1 / L2 prefetch; they are read a whole tile from now)
+                const uint32_t np = ts.peek_pack();
+                if (np != 0xffffffffu && np != pack) {
+                    const char* a = nullptr;
+                    if (lane < 4u) { if (lane * 128u < nl * (uint32_t)sizeof(PackLeaf) + 127u) a = reinterpret_cast<const char*>(P.leaves + (size_t)np * nl) + lane * 128u; }
+                    else if (lane < 6u) { if (AGG && (lane - 4u) * 128u < na * (uint32_t)sizeof(ColView) + 127u) a = reinterpret_cast<const char*>(P.views + P.agg_view0 + (size_t)np * na) + (lane - 4u) * 128u; }
+                    else if (lane == 6u) a = reinterpret_cast<const char*>(P.packs + np);
+                    if (a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
+                }
+            }
             const LeafEnv env{P, code_smem, n, pack_row0};
+            const uint64_t wr0 = (uint64_t)pack_row0 + (uint64_t)(gw0 + lane) * 32u;   // first pack row of this lane's word, pass 0 (pass 1: + 1024)
 
             // ---- leaves and the AND/OR program.  Every staged leaf column is one ring stage holding the column's slice of
-            // the whole tile; a leaf is evaluated for ALL passes of the warp before the next one is touched (its unrolled
-            // body stays hot in the instruction cache).
-            uint32_t w[4] = {0u, 0u, 0u, 0u};
-            bool told = false, dense = false;   // the producer's staging decision (previous tile) arrives with the tile's first ring stage
+            // the whole tile; a leaf is evaluated for both passes of the warp before the next one is touched.
+            uint32_t w0 = 0u, w1 = 0u;
             if (P.flat_op) {
                 // pure AND (1) / pure OR (2) program: running words in registers.  MatchAnd's early-out (match_core.go:44-130),
                 // per warp and pass: rows the words so far have ruled out need no work — a pass whose 1024 rows are all ruled
@@ -433,22 +466,26 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                 for (uint32_t i = 0; i < P.npost; ++i) {
                     const uint32_t op = P.postfix[i];
                     if (op >= 0x80u) continue;
-                    const PackLeaf& lf = L[op];
+                    const PackLeaf lf = L[op];   // registers: the fields a leaf kind needs are read once per tile
                     const uint32_t* sw = nullptr;
                     const bool staged_leaf = lf.data != nullptr;
                     if (staged_leaf) {
-                        mbar_wait(&full_bar[s], ph);
-                        if (!told) { dense = stage_flag[s] != 0; told = true; }
+                        mbar_wait_a(full0 + s * 8u, ph);
                         sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                     }
-                    for (uint32_t pass = 0; pass < passes; ++pass) {
-                        const uint32_t g0 = gw0 + pass * 32u;
-                        const uint32_t cur = get4(w, pass);
-                        const uint32_t keep = first ? 0xffffffffu : (is_and ? cur : ~cur);
+                    const uint32_t flipw = lf.neg2 ? 0xffffffffu : 0u;
+                    {
+                        const uint32_t keep = first ? 0xffffffffu : (is_and ? w0 : ~w0);
                         if (__any_sync(0xffffffffu, keep != 0u)) {
-                            uint32_t word = eval_leaf(env, lf, op, sw, g0, 32u, lane, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
-                            if (lf.neg2) word = ~word;
-                            set4(w, pass, first ? word : (is_and ? (cur & word) : (cur | word)));
+                            const uint32_t word = eval_leaf(env, lf, op, sw, gw0, 32u, lane, wr0, keep) ^ flipw;
+                            w0 = first ? word : (is_and ? (w0 & word) : (w0 | word));
+                        }
+                    }
+                    if (two) {
+                        const uint32_t keep = first ? 0xffffffffu : (is_and ? w1 : ~w1);
+                        if (__any_sync(0xffffffffu, keep != 0u)) {
+                            const uint32_t word = eval_leaf(env, lf, op, sw, gw0 + 32u, 32u, lane, wr0 + 1024u, keep) ^ flipw;
+                            w1 = first ? word : (is_and ? (w1 & word) : (w1 | word));
                         }
                     }
                     if (staged_leaf) release();
@@ -466,8 +503,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                         const uint32_t* sw = nullptr;
                         const bool staged_leaf = lf.data != nullptr;
                         if (staged_leaf) {
-                            mbar_wait(&full_bar[s], ph);
-                            if (!told) { dense = stage_flag[s] != 0; told = true; }
+                            mbar_wait_a(full0 + s * 8u, ph);
                             sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                         }
                         const bool inv = lf.neg2 && !lf.fixmode;
@@ -479,15 +515,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                             const uint32_t keep = and_next ? prev[pass * 32u] : (or_next ? ~prev[pass * 32u] : 0xffffffffu);
                             uint32_t word = 0;
                             if (__any_sync(0xffffffffu, keep != 0u)) {
-                                word = eval_leaf(env, lf, op, sw, g0, 32u, lane, (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u, keep);
+                                word = eval_leaf(env, lf, op, sw, g0, 32u, lane, wr0 + pass * 1024u, keep);
                                 if (inv) word = ~word;
                             }
                             dst[pass * 32u] = word;
                         }
                         if (staged_leaf) release();
                         if (lf.fixmode) {   // ALP: correct the rows that are patches (1-bit stream in the next stage)
-                            mbar_wait(&full_bar[s], ph);
-                            if (!told) { dense = stage_flag[s] != 0; told = true; }
+                            mbar_wait_a(full0 + s * 8u, ph);
                             const uint32_t* fw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
                             __builtin_assume(__isShared(fw));
                             for (uint32_t pass = 0; pass < passes; ++pass) {
@@ -507,49 +542,55 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                             x[pass * 32u] = (op == 0xFEu) ? (x[pass * 32u] & y[pass * 32u]) : (x[pass * 32u] | y[pass * 32u]);
                     }
                 }
-                for (uint32_t pass = 0; pass < passes; ++pass) set4(w, pass, stk[pass * 32u + lane]);
+                w0 = stk[lane];
+                if (two) w1 = stk[32u + lane];
             }
 
-            // ---- outputs of the tile: tail masking (match_core.go semantics: tail bits zero), bitset words (coalesced 128 B
-            // per warp), per-pack match count
-            uint32_t tile_cnt = 0;
-            for (uint32_t pass = 0; pass < passes; ++pass) {
-                const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(gw0 + pass * 32u + lane) * 32u;
-                uint32_t valid = 0;
-                if (wr < n) {
+            // ---- outputs of the tile: tail masking (match_core.go semantics: tail bits zero; only the last tile of a pack has
+            // a tail), bitset words (coalesced 128 B per warp), per-pack match count
+            if (pack_row0 + tile_rows > n) {
+                auto tail = [&](uint32_t word, uint64_t wr) -> uint32_t {
+                    if (wr >= n) return 0u;
                     const uint32_t left = n - (uint32_t)wr;
-                    valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
-                }
-                const uint32_t word = get4(w, pass) & valid;
-                set4(w, pass, word);
-                if (P.bitsets && wr < n) *reinterpret_cast<uint32_t*>(P.bitsets + ts.pi.bitset_off + (wr >> 3)) = word;
-                tile_cnt += __popc(word);
+                    return left >= 32u ? word : (word & ((1u << left) - 1u));
+                };
+                w0 = tail(w0, wr0);
+                w1 = two ? tail(w1, wr0 + 1024u) : 0u;
             }
+            if (P.bitsets) {
+                if (wr0 < n) *reinterpret_cast<uint32_t*>(P.bitsets + ts.pi.bitset_off + (wr0 >> 3)) = w0;
+                if (two && wr0 + 1024u < n) *reinterpret_cast<uint32_t*>(P.bitsets + ts.pi.bitset_off + ((wr0 + 1024u) >> 3)) = w1;
+            }
+            const uint32_t tile_cnt = __popc(w0) + __popc(w1);
             lane_cnt += tile_cnt;
 
             if constexpr (AGG) {
                 nmatch += tile_cnt;   // per-CTA totals only: any partition of the matches over threads will do
-                const uint32_t c = __reduce_add_sync(0xffffffffu, tile_cnt);
-                if (lane == 0) { atomicAdd(&sm_match, c); atomicAdd(&sm_wtiles, 1u); }   // selectivity feedback for the producer
-                if (!told) {   // no leaf column was staged: the decision sits in an empty stage
-                    mbar_wait(&full_bar[s], ph);
-                    dense = stage_flag[s] != 0;
-                    release();
+                const bool any_now = __any_sync(0xffffffffu, tile_cnt != 0u);
+                if (any_now) fb_match += __reduce_add_sync(0xffffffffu, tile_cnt);
+                ++fb_tiles;
+                if (lane == 0) { *(volatile unsigned int*)&sm_match[warp] = fb_match; *(volatile unsigned int*)&sm_wtiles[warp] = fb_tiles; }   // the producer decides on these
+                // the previous tile's value rows have had this tile's filter time to arrive: staged by the producer when the
+                // tile matched densely (its decision is exact and waits for nothing but this publication), else prefetched
+                bool dense = false;
+                if (have_prev) {
+                    while (*(volatile unsigned int*)&sm_decided < seq) {}
+                    dense = sm_dense[(seq - 1u) & 7u] != 0u;
+                    if (dense || prev_any) reduce_prev(dense);
                 }
-                // the previous tile's value rows have had this tile's filter time to arrive
-                if (have_prev) reduce_prev(dense);
                 // this tile's turn comes after the next filter: start pulling its matching rows towards L2 now (raw 64-bit
                 // columns; skipped while the producer is staging whole tiles anyway)
-                if (c && !dense) {
+                if (any_now && tile_cnt <= 8u) {   // (a lane with many matches sits in a dense tile: the producer will stage it)
 #pragma unroll
                     for (int j = 0; j < NA; ++j) {
                         if ((uint32_t)j >= na) break;
                         const ColView& v = AV[desc_sel * na + j];
                         if (v.kind != CK_BITS || v.width != 64) continue;
-                        for (uint32_t pass = 0; pass < passes; ++pass) {
-                            uint32_t word = get4(w, pass);
+#pragma unroll
+                        for (uint32_t pass = 0; pass < 2u; ++pass) {
+                            uint32_t word = pass ? w1 : w0;
                             if (!word) continue;
-                            const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + pack_row0 + (gw0 + pass * 32u + lane) * 32u;
+                            const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + (wr0 + pass * 1024u);
                             if (__popc(word) <= 4) {
                                 while (word) {
                                     const uint32_t b = (uint32_t)__ffs((int)word) - 1u;
@@ -564,18 +605,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                         }
                     }
                 }
-#pragma unroll
-                for (int p = 0; p < 4; ++p) wprev[p] = w[p];
-                prev_row0 = pack_row0; prev_sel = desc_sel; have_prev = true;
+                wp0 = w0; wp1 = w1;
+                prev_row0 = pack_row0; prev_sel = desc_sel; have_prev = true; prev_any = any_now;
+                ++seq;
             }
         } while (ts.next());
         flush_count(cur_pack);
         if constexpr (AGG) {
-            // the value columns of the last tile: the producer's decision arrives in an empty stage
-            mbar_wait(&full_bar[s], ph);
-            const bool dense = stage_flag[s] != 0;
-            release();
-            reduce_prev(dense);
+            // the value columns of the last tile
+            while (*(volatile unsigned int*)&sm_decided < seq) {}
+            const bool dense = sm_dense[(seq - 1u) & 7u] != 0u;
+            if (dense || prev_any) reduce_prev(dense);
         }
     }
 

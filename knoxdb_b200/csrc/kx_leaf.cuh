@@ -24,16 +24,34 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_addr(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    // try_wait suspends the thread in hardware until the phase completes or the time hint (ns) runs out: the loop spins
+    // a handful of times per wait instead of burning issue slots the other warps of the SM need
     asm volatile(
         "{\n"
         ".reg .pred P1;\n"
         "KX_WAIT:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
         "@P1 bra KX_DONE;\n"
         "bra KX_WAIT;\n"
         "KX_DONE:\n"
-        "}\n" ::"r"(smem_addr(bar)), "r"(parity)
+        "}\n" ::"r"(smem_addr(bar)), "r"(parity), "r"(20000u)
         : "memory");
+}
+// the same on a precomputed 32-bit shared-memory address (no generic → shared conversion per call)
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_addr, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "KX_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+        "@P1 bra KX_DONE;\n"
+        "bra KX_WAIT;\n"
+        "KX_DONE:\n"
+        "}\n" ::"r"(bar_addr), "r"(parity), "r"(20000u)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_addr) : "memory");
 }
 // producer-side wait: the producer only has to notice a released slot "soon"; sleeping between polls keeps its
 // spin loop from stealing issue slots (and power) from the eight consumer warps of the CTA

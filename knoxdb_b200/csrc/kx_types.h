@@ -170,7 +170,8 @@ struct ScanParams {
     uint32_t desc_off_words;
     uint32_t desc_words;       // words per warp: nleaves PackLeaf + 2 x naggs ColView
     uint32_t flat_op;          // 1: the program is a pure AND of its leaves, 2: a pure OR, 0: general tree
-    uint32_t sched_chunk;      // tiles per scheduling chunk (chunks are dealt round-robin to the CTAs)
+    uint32_t sched_chunk;      // tiles per scheduling chunk (chunks are dealt round-robin to the CTAs) …
+    uint32_t sched_rounds;     // … for this many full rounds; the remaining tiles are dealt one by one
     uint32_t prod_sleep;       // producer polls released ring slots with a sleep in between (tuning hook)
     // value columns of the fused reduce: the rows of one pass (32 groups per warp) are reduced in agg_kp (1, 2 or 4) chunks;
     // tiles that match densely get the chunks staged through the ring (one slice of 32 / agg_kp groups per warp and stage)

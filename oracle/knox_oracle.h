@@ -188,6 +188,9 @@ int  ko_match_range(int type, int op, uint64_t a, uint64_t b, uint64_t minv, uin
 
 /* ---- CPU baseline driver (bench.py only): fused bitpack compare over many packs with
  *      nthreads pthreads; returns total matches. ---- */
+/* AVX-512 (VBMI) version of ko_bitpack_cmp for the CPU baseline (ko_simd.c); 0 = not taken, use the scalar port */
+int ko_simd_available(void);
+int ko_bitpack_cmp_simd(int op, const uint64_t* src, int log2, uint64_t a, uint64_t b, size_t n, uint8_t* bits);
 int64_t ko_baseline_bitpack_scan(const uint64_t* const* packs, const size_t* nrows, size_t npacks,
                                  int log2, int op, uint64_t a, uint64_t b,
                                  uint8_t* const* bitsets, int nthreads);

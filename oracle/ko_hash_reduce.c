@@ -297,7 +297,7 @@ int ko_match_range(int type, int op, uint64_t a, uint64_t b, uint64_t minv, uint
  * partitioned over nthreads.  Each pack runs the fused bitpack compare (a8) + popcount. */
 typedef struct {
     const uint64_t* const* packs; const size_t* nrows; size_t lo, hi;
-    int log2, op; uint64_t a, b; uint8_t* const* bitsets; int64_t total;
+    int log2, op; uint64_t a, b; uint8_t* const* bitsets; int64_t total; int simd;
 } bl_arg;
 
 static void* bl_worker(void* p) {
@@ -306,23 +306,28 @@ static void* bl_worker(void* p) {
     for (size_t i = g->lo; i < g->hi; i++) {
         size_t n = g->nrows[i];
         memset(g->bitsets[i], 0, (n + 7) / 8);
-        ko_bitpack_cmp(g->op, g->packs[i], g->log2, g->a, g->b, n, g->bitsets[i]);
+        if (!(g->simd && ko_bitpack_cmp_simd(g->op, g->packs[i], g->log2, g->a, g->b, n, g->bitsets[i])))
+            ko_bitpack_cmp(g->op, g->packs[i], g->log2, g->a, g->b, n, g->bitsets[i]);
         tot += ko_bitset_popcount(g->bitsets[i], n);
     }
     g->total = tot;
     return NULL;
 }
 
+/* nthreads < 0: |nthreads| threads running the scalar port only (the shape of the reference's generated Go code);
+ * nthreads > 0: the AVX-512 kernel of ko_simd.c where the host has VBMI (packs must be padded by 64 readable bytes) */
 int64_t ko_baseline_bitpack_scan(const uint64_t* const* packs, const size_t* nrows, size_t npacks,
                                  int log2, int op, uint64_t a, uint64_t b,
                                  uint8_t* const* bitsets, int nthreads) {
+    int simd = nthreads > 0;
+    if (nthreads < 0) nthreads = -nthreads;
     if (nthreads < 1) nthreads = 1;
     if ((size_t)nthreads > npacks) nthreads = (int)(npacks ? npacks : 1);
     pthread_t* th = (pthread_t*)malloc(sizeof(pthread_t) * (size_t)nthreads);
     bl_arg* args = (bl_arg*)calloc((size_t)nthreads, sizeof(bl_arg));
     for (int t = 0; t < nthreads; t++) {
         args[t] = (bl_arg){packs, nrows, npacks * (size_t)t / (size_t)nthreads, npacks * (size_t)(t + 1) / (size_t)nthreads,
-                           log2, op, a, b, bitsets, 0};
+                           log2, op, a, b, bitsets, 0, simd};
         pthread_create(&th[t], NULL, bl_worker, &args[t]);
     }
     int64_t tot = 0;

@@ -69,7 +69,7 @@ def main():
         "ts90f": ([rg(0.9)], [(5, kb.FLOAT64)]),
         "ts90if": ([rg(0.9)], [(3, kb.INT64), (5, kb.FLOAT64)]),
     }
-    geos = [None, "2,4,32", "2,3,32", "2,2,64", "2,2,32", "1,4,64", "1,6,64", "1,8,32", "1,3,128", "1,2,128"]
+    geos = [None, "2,4,32", "2,3,32", "2,2,64", "2,2,32", "1,4,64", "1,6,64", "1,3,64"]
     chunks = ["1", "2", "4", "8", "16"]
     if args.quick:
         geos, chunks = [None, "2,4,32", "2,2,64", "1,4,64"], ["1", "4"]

@@ -103,6 +103,8 @@ def lib():
             "ko_str_match": (None, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp]),
             "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
             "ko_baseline_bitpack_scan": (C.c_int64, [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_int]),
+            "ko_simd_available": (C.c_int, []),
+            "ko_bitpack_cmp_simd": (C.c_int, [C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, vp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)

@@ -369,3 +369,31 @@ def test_string_containers_round_trip_and_match_like_bytes_compare():
                 b = a + b"\x01" if op == ko.RG else b""
                 want = kt.pack_bits(np.array([fn(v, a, b) for v in data]))
                 assert (c.match(op, a, b) == want).all(), (kind, op, a)
+
+
+def test_simd_baseline_kernel_equals_the_scalar_port():
+    """bench.py's CPU baseline may run an AVX-512 version of the fused bit-pack compare (oracle/ko_simd.c): it must
+    produce the bitset words of the scalar port (the restatement of bitpack/cmp.go) for every width, operator and
+    operand shape, including operands outside the field range and ragged tails"""
+    L = ko.lib()
+    if not L.ko_simd_available():
+        pytest.skip("host CPU has no AVX-512 VBMI")
+    rng = np.random.default_rng(77)
+    taken = 0
+    for w in range(1, 65):
+        for n in (64, 640 + 17, 4096 + 63):
+            vals = kt.rnd_bits(rng, n, w)
+            packed = np.zeros(L.ko_bitpack_size(w, n) // 8 + 16, dtype=np.uint64)   # + 64 readable bytes behind the stream
+            L.ko_bitpack_encode(ko._p(packed), ko._p(vals), n, w, 0)
+            mask = (1 << w) - 1 if w < 64 else 2**64 - 1
+            picks = [0, 1, int(vals[3]), int(vals[n // 2]), mask, min(mask + 1, 2**64 - 1), 2**64 - 1]
+            for op in (ko.EQ, ko.NE, ko.LT, ko.LE, ko.GT, ko.GE, ko.RG):
+                for a in picks:
+                    b = min(2**64 - 1, a + int(rng.integers(0, max(2, mask // 3 + 1)))) if op == ko.RG else 0
+                    want = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
+                    got = np.zeros((n + 7) // 8 + 8, dtype=np.uint8)
+                    L.ko_bitpack_cmp(op, ko._p(packed), w, a, b, n, ko._p(want))
+                    if L.ko_bitpack_cmp_simd(op, ko._p(packed), w, a, b, n, ko._p(got)):
+                        taken += 1
+                        assert (got == want).all(), (w, n, op, a, b)
+    assert taken > 1000
