@@ -65,19 +65,6 @@ struct TileSched {
         chunk = t - pi.tile0;
         return true;
     }
-    // pack of the tile this CTA handles next (uniform packs only; 0xffffffff: unknown / none): lets the consumers warm
-    // its descriptors while they filter the current tile — with small scheduling chunks almost every tile is another pack
-    __device__ __forceinline__ uint32_t peek_pack() const {
-        if (P.tile_pack) return 0xffffffffu;
-        uint64_t tn;
-        if (t + 1u < t_stop) tn = (uint64_t)t + 1u;
-        else {
-            const uint32_t r = round + 1u;
-            tn = r < P.sched_rounds ? ((uint64_t)r * gridDim.x + blockIdx.x) * P.sched_chunk
-                                    : (uint64_t)P.sched_rounds * gridDim.x * P.sched_chunk + (uint64_t)(r - P.sched_rounds) * gridDim.x + blockIdx.x;
-        }
-        return tn < P.ntiles ? (uint32_t)(tn / P.tiles_per_pack) : 0xffffffffu;
-    }
     __device__ __forceinline__ bool start() { round = 0; return open_chunk(); }
     __device__ __forceinline__ bool next() {
         if (++t < t_stop) {
@@ -438,17 +425,6 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                     asm volatile("bar.sync 1, %0;" ::"n"(CONSUMER_WARPS * 32));
                 }
                 cur_pack = pack;
-            }
-            if (warp == 0) {
-                // warm the descriptors of this CTA's next tile (L1 / L2 prefetch; they are read a whole tile from now)
-                const uint32_t np = ts.peek_pack();
-                if (np != 0xffffffffu && np != pack) {
-                    const char* a = nullptr;
-                    if (lane < 4u) { if (lane * 128u < nl * (uint32_t)sizeof(PackLeaf) + 127u) a = reinterpret_cast<const char*>(P.leaves + (size_t)np * nl) + lane * 128u; }
-                    else if (lane < 6u) { if (AGG && (lane - 4u) * 128u < na * (uint32_t)sizeof(ColView) + 127u) a = reinterpret_cast<const char*>(P.views + P.agg_view0 + (size_t)np * na) + (lane - 4u) * 128u; }
-                    else if (lane == 6u) a = reinterpret_cast<const char*>(P.packs + np);
-                    if (a) asm volatile("prefetch.global.L1 [%0];" ::"l"(a));
-                }
             }
             const LeafEnv env{P, code_smem, n, pack_row0};
             const uint64_t wr0 = (uint64_t)pack_row0 + (uint64_t)(gw0 + lane) * 32u;   // first pack row of this lane's word, pass 0 (pass 1: + 1024)

@@ -112,6 +112,13 @@ void    ko_container_match_set(const ko_container* c, int negate, const uint64_t
 
 /* ---- ALP float64: internal/encode/float_alp.go, internal/encode/alp/{constants,encoder,decoder}.go ---- */
 #define KO_TFLOATALP 13
+#define KO_TFLOATALPRD 14
+/* ALP-RD (ko_alprd.c): left / right split of the IEEE bits; the cut (Shift) is kept in ko_container.log2 */
+size_t  ko_store_alprd(uint8_t* dst, int type, const uint64_t* vals, size_t n, int shift /* < 0: analyse */);
+long    ko_alprd_load(ko_container* c, const uint8_t* buf, size_t len);
+uint64_t ko_alprd_get(const ko_container* c, size_t i);
+void    ko_alprd_decode_all(const ko_container* c, uint64_t* dst);
+void    ko_alprd_match(const ko_container* c, int op, uint64_t a, uint64_t b, uint8_t* bits);
 int64_t ko_alp_encode_single(double v, int e, int f, int* ok);   /* Encoder.EncodeSingle */
 int64_t ko_alp_encode_above(double v, int e, int f);
 int64_t ko_alp_encode_below(double v, int e, int f);

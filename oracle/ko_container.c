@@ -98,6 +98,12 @@ long ko_container_load(int type, const uint8_t* buf, size_t len, ko_container** 
         p = buf + k;
         break;
     }
+    case KO_TFLOATALPRD: { /* float_alprd.go:86-107 */
+        long k = ko_alprd_load(c, buf, len);
+        if (k < 0) { ko_container_free(c); return -1; }
+        p = buf + k;
+        break;
+    }
     default:
         free(c);
         return -1;
@@ -141,6 +147,7 @@ static size_t run_of(const ko_container* ends, size_t i) {
 uint64_t ko_container_get(const ko_container* c, size_t i) {
     switch (c->ctype) {
     case KO_TFLOATALP: return ko_alp_get(c, i);
+    case KO_TFLOATALPRD: return ko_alprd_get(c, i);
     case KO_TCONST: return c->val;
     case KO_TDELTA: return ext(c->type, (uint64_t)i * c->delta + c->val);
     case KO_TBITPACK: {
@@ -165,6 +172,7 @@ uint64_t ko_container_get(const ko_container* c, size_t i) {
 void ko_container_decode(const ko_container* c, uint64_t* dst) {
     switch (c->ctype) {
     case KO_TFLOATALP: ko_alp_decode_all(c, dst); return;
+    case KO_TFLOATALPRD: ko_alprd_decode_all(c, dst); return;
     case KO_TS8B: {
         uint64_t* tmp = (uint64_t*)malloc((c->n + 128) * 8);
         ko_s8b_decode(tmp, c->n + 128, (const uint64_t*)c->payload, c->payload_len / 8, 0);
@@ -465,6 +473,7 @@ void ko_container_match(const ko_container* c, int op, uint64_t a, uint64_t b, u
     case KO_TDICT: match_dict(c, op, a, b, bits); return;
     case KO_TS8B: match_s8b(c, op, a, b, bits); return;
     case KO_TFLOATALP: ko_alp_match(c, op, a, b, bits); return;
+    case KO_TFLOATALPRD: ko_alprd_match(c, op, a, b, bits); return;
     case KO_TRUNEND: { /* int_runend.go:224-294 */
         size_t nr = c->child[0]->n;
         uint8_t* vbits = (uint8_t*)calloc((nr + 7) / 8 + 8, 1);

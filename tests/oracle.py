@@ -103,6 +103,7 @@ def lib():
             "ko_str_match": (None, [vp, C.c_int, vp, C.c_size_t, vp, C.c_size_t, vp]),
             "ko_match_range": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
             "ko_baseline_bitpack_scan": (C.c_int64, [vp, vp, C.c_size_t, C.c_int, C.c_int, C.c_uint64, C.c_uint64, vp, C.c_int]),
+            "ko_store_alprd": (C.c_size_t, [vp, C.c_int, vp, C.c_size_t, C.c_int]),
             "ko_simd_available": (C.c_int, []),
             "ko_bitpack_cmp_simd": (C.c_int, [C.c_int, vp, C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, vp]),
         }
@@ -214,6 +215,11 @@ def store(kind, type_, values=None, **kw):
         n = L.ko_store_delta(_p(buf), scalar_u64(type_, kw["base"]), scalar_u64(type_, kw["delta"]), kw["n"])
         return buf[:n].tobytes()
     v = as_u64(type_, values)
+    if kind == "alprd":   # FloatAlpRdContainer[float64,uint64] / [float32,uint32]; shift: the cut (default: analysed)
+        assert type_ in (F64, F32)
+        buf = np.zeros(3 * L.ko_store_bound(U64, v.size) + 64, dtype=np.uint8)
+        n = L.ko_store_alprd(_p(buf), type_, _p(v), v.size, kw.get("shift", -1))
+        return buf[:n].tobytes()
     if kind == "alp":   # FloatAlpContainer[float64,int64]; e/f: exponents (default: chosen by sampling)
         assert type_ == F64
         buf = np.zeros(3 * L.ko_store_bound(I64, v.size) + 64, dtype=np.uint8)
