@@ -255,12 +255,12 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
     };
     int rc;
     const ColView& v = lay.view;
-    if (v.kind == CK_BITS || v.kind == CK_DICT || (v.kind == CK_ALP && v.width)) {
+    if (v.kind == CK_BITS || v.kind == CK_DICT || ((v.kind == CK_ALP || v.kind == CK_ALPRD) && v.width)) {
         const void* src = lay.owned.empty() ? (const void*)lay.stream : (const void*)lay.owned.data();
         size_t len = lay.owned.empty() ? lay.stream_len : lay.owned.size();
         if ((rc = put(src, len, &sb.view.data))) return rc;
     }
-    if (v.kind == CK_ALP && !lay.blob.empty()) {
+    if ((v.kind == CK_ALP || v.kind == CK_ALPRD) && !lay.blob.empty()) {   // ALP: patch blob; ALP-RD: the left bit stream
         if ((rc = put(lay.blob.data(), lay.blob.size(), &sb.view.aux))) return rc;
     }
     if (v.kind == CK_DICT) {
@@ -271,7 +271,7 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
         if ((rc = put(lay.aux64.data(), lay.aux64.size() * 8, &sb.view.data))) return rc;
         if ((rc = put(lay.aux32.data(), lay.aux32.size() * 4, &sb.view.aux))) return rc;
     }
-    if (!lay.owned.empty() || v.kind == CK_DICT || v.kind == CK_RUNEND || v.kind == CK_ALP) {
+    if (!lay.owned.empty() || v.kind == CK_DICT || v.kind == CK_RUNEND || v.kind == CK_ALP || v.kind == CK_ALPRD) {
         // host-owned temporaries (lay.owned / aux vectors) die with `lay`: finish the copies now
         CK(cudaStreamSynchronize(ctx->stream));
     }
@@ -341,6 +341,13 @@ int enqueue_exchange(kx_ctx* ctx, uint32_t npacks, uint32_t naggs, const uint8_t
     return KX_OK;
 }
 
+// float32 zone maps / operands travel as float64 patterns on the device (exact widening; same ordering, NaN stays NaN)
+uint64_t f32_to_f64_bits(uint64_t pat) {
+    uint32_t u = uint32_t(pat); float f; std::memcpy(&f, &u, 4);
+    double d = double(f); uint64_t o; std::memcpy(&o, &d, 8);
+    return o;
+}
+
 // device partial → C ABI result (SumReducer wraps in T; float64 sums carry their compensation term)
 kx_agg_out agg_result(const AggPartial& a, int t) {
     kx_agg_out o{};
@@ -352,6 +359,16 @@ kx_agg_out agg_result(const AggPartial& a, int t) {
             std::memcpy(&o.sum_bits, &s, 8);
             o.sum_err = (hi - s) + a.err;
             o.min_bits = a.mn; o.max_bits = a.mx;
+        } else if (t == KX_FLOAT32) {
+            // float32 columns are reduced in float64 on the device (every float32 is exact in float64) and rounded ONCE here:
+            // closer to the exact sum than SumReducer[float32]'s running float32 sum (reducer.go:173-178), equal for min / max
+            double hi, mn, mx; std::memcpy(&hi, &a.sum, 8); std::memcpy(&mn, &a.mn, 8); std::memcpy(&mx, &a.mx, 8);
+            const double s = hi + a.err;
+            const float fs = float(s), fmn = float(mn), fmx = float(mx);
+            uint32_t u; std::memcpy(&u, &fs, 4); o.sum_bits = u;
+            std::memcpy(&u, &fmn, 4); o.min_bits = u;
+            std::memcpy(&u, &fmx, 4); o.max_bits = u;
+            o.sum_err = s - double(fs);
         } else {
             uint64_t flip = type_is_signed(t) ? 0x8000000000000000ull : 0;
             o.sum_bits = type_ext(t, a.sum);     // SumReducer wraps in T
@@ -389,7 +406,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (naggs < 0 || naggs > MAX_AGGS) return fail(ctx, KX_EINVAL, "too many aggregates");
     for (int j = 0; j < naggs; ++j) {
         int t = aggs[j].block_type;
-        if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
+        if (type_bits(t) == 0) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
     }
     ctx->last_rows_scanned = ctx->last_packs_scanned = ctx->last_rows_matched = 0;
     if (npacks == 0) {
@@ -431,6 +448,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::vector<size_t> ajob_leaf;
     std::vector<StrJob> sjobs;          // byte-string leaves: predicate per row in a pre-pass (strmatch_kernel)
     std::vector<size_t> sjob_leaf;
+    std::vector<ValJob> vjobs;          // ALP-RD leaves: decode + float compare per row in a pre-pass (valmatch_kernel)
+    std::vector<size_t> vjob_leaf;
+    uint32_t max_val_rows = 0;
     uint32_t max_str_rows = 0;
     uint32_t max_patches = 0;
     bool any_fix = false;
@@ -467,6 +487,23 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                     sjob_leaf.push_back(size_t(p) * nl + l);
                     leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                     max_str_rows = std::max(max_str_rows, v.n);
+                    o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
+                    bits = std::max(bits, 1u);
+                }
+                continue;
+            }
+            if (v.kind == CK_ALPRD) {
+                // ALP-RD block: FloatAlpRdContainer.Match* decode and run the float compare kernels (float_alprd.go:181-211);
+                // here a pre-pass decodes every row at index and writes the leaf's 1-bit column
+                const LeafSpec& ls = prog->leaves[size_t(l)];
+                o = PackLeaf{};
+                only32 = false;
+                if (v.n == 0 || ls.mode == KX_MODE_IN || ls.mode == KX_MODE_NIN) o.mode = LM_NONE;   // (float IN / NIN never compile)
+                else {
+                    vjobs.push_back(ValJob{v, ls.a, ls.b, leafbits_bytes, uint32_t(ls.mode), 0});
+                    vjob_leaf.push_back(size_t(p) * nl + l);
+                    leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
+                    max_val_rows = std::max(max_val_rows, v.n);
                     o.mode = LM_BITS; o.width = 1;   // o.data is patched once the scratch buffer is reserved
                     bits = std::max(bits, 1u);
                 }
@@ -663,12 +700,14 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     size_t off_rjobs = off_cjobs + round_up(sizeof(CodesetJob) * cjobs.size(), 256);
     size_t off_ajobs = off_rjobs + round_up(sizeof(RunFillJob) * rjobs.size(), 256);
     size_t off_sjobs = off_ajobs + round_up(sizeof(AlpFixJob) * ajobs.size(), 256);
-    size_t desc_bytes = off_sjobs + round_up(sizeof(StrJob) * sjobs.size(), 256);
+    size_t off_vjobs = off_sjobs + round_up(sizeof(StrJob) * sjobs.size(), 256);
+    size_t desc_bytes = off_vjobs + round_up(sizeof(ValJob) * vjobs.size(), 256);
     if (leafbits_bytes) {
         CK(ctx->d_leafbits.reserve(leafbits_bytes));
         for (size_t i = 0; i < rjobs.size(); ++i) pl[rjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + rjobs[i].out_off;
         for (size_t i = 0; i < ajobs.size(); ++i) pl[ajob_leaf[i]].fix = static_cast<const uint8_t*>(ctx->d_leafbits.p) + ajobs[i].out_off;
         for (size_t i = 0; i < sjobs.size(); ++i) pl[sjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + sjobs[i].out_off;
+        for (size_t i = 0; i < vjobs.size(); ++i) pl[vjob_leaf[i]].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + vjobs[i].out_off;
         for (auto& mj : mask_jobs) pl[size_t(mj.second) * nl + nleaves].data = static_cast<const uint8_t*>(ctx->d_leafbits.p) + mj.first;
     }
 
@@ -697,6 +736,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (!rjobs.empty()) std::memcpy(hd + off_rjobs, rjobs.data(), sizeof(RunFillJob) * rjobs.size());
     if (!ajobs.empty()) std::memcpy(hd + off_ajobs, ajobs.data(), sizeof(AlpFixJob) * ajobs.size());
     if (!sjobs.empty()) std::memcpy(hd + off_sjobs, sjobs.data(), sizeof(StrJob) * sjobs.size());
+    if (!vjobs.empty()) std::memcpy(hd + off_vjobs, vjobs.data(), sizeof(ValJob) * vjobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
     // single-leaf kernel: contiguous tile range per CTA; general kernel: chunks of sched_chunk tiles dealt round-robin
@@ -784,6 +824,10 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (ntiles && !sjobs.empty()) {
         CK(launch_strmatch(reinterpret_cast<const StrJob*>(dd + off_sjobs), uint32_t(sjobs.size()), max_str_rows, prog->dev_strs,
                            static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
+        ctx->last_launches++;
+    }
+    if (ntiles && !vjobs.empty()) {
+        CK(launch_valmatch(reinterpret_cast<const ValJob*>(dd + off_vjobs), uint32_t(vjobs.size()), max_val_rows, static_cast<uint8_t*>(ctx->d_leafbits.p), ctx->stream));
         ctx->last_launches++;
     }
     if (ntiles && !rjobs.empty()) {
@@ -1279,7 +1323,7 @@ int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, i
         if ((edges[k] ^ ts_flip) > (edges[k + 1] ^ ts_flip)) return fail(ctx, KX_EINVAL, "window edges must ascend");
     for (int j = 0; j < naggs; ++j) {
         int t = aggs[j].block_type;
-        if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "aggregate over unsupported block type");
+        if (type_bits(t) == 0 || t == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_scan_buckets: float32 value columns are not supported (widen them to float64)");
     }
     // the scan proper: filter -> match bitsets that stay on the device; the window column and the value columns ride
     // along as "aggregate" views of the job (looked up, not reduced by the scan)
@@ -1520,8 +1564,8 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
                 std::memcpy(hp, lay.blob.data(), lay.blob.size());
                 CK(cudaMemcpyAsync(dbase + off_blob[li], hp, lay.blob.size(), cudaMemcpyHostToDevice, cs));
             }
-            if (v.kind == CK_BITS || v.kind == CK_DICT || (v.kind == CK_ALP && v.width)) v.data = dbase + off_stream[li];
-            if (v.kind == CK_ALP && !lay.blob.empty()) v.aux = dbase + off_blob[li];
+            if (v.kind == CK_BITS || v.kind == CK_DICT || ((v.kind == CK_ALP || v.kind == CK_ALPRD) && v.width)) v.data = dbase + off_stream[li];
+            if ((v.kind == CK_ALP || v.kind == CK_ALPRD) && !lay.blob.empty()) v.aux = dbase + off_blob[li];
             if (v.kind == CK_DICT) v.aux = dbase + off_a64[li];
             if (v.kind == CK_RUNEND) { v.data = dbase + off_a64[li]; v.aux = dbase + off_a32[li]; }
         }
@@ -1605,6 +1649,7 @@ int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_a
         const kx_agg_out& p = parts[i];
         if (!p.valid) continue;
         double ps = 0; std::memcpy(&ps, &p.sum_bits, 8);
+        if (t == KX_FLOAT32) { uint32_t u = uint32_t(p.sum_bits); float f; std::memcpy(&f, &u, 4); ps = double(f); }   // + sum_err = the float64 partial sum
         if (!r.valid) {
             r = p; fs = ps; fe = p.sum_err;
             continue;
@@ -1616,6 +1661,13 @@ int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_a
             fs = tt; fe += p.sum_err + c;
             double a, b; std::memcpy(&a, &r.min_bits, 8); std::memcpy(&b, &p.min_bits, 8); if (b < a) r.min_bits = p.min_bits;
             std::memcpy(&a, &r.max_bits, 8); std::memcpy(&b, &p.max_bits, 8); if (b > a) r.max_bits = p.max_bits;
+        } else if (t == KX_FLOAT32) {
+            double tt = fs + ps;
+            double c = (std::abs(fs) >= std::abs(ps)) ? ((fs - tt) + ps) : ((ps - tt) + fs);
+            fs = tt; fe += p.sum_err + c;
+            auto f32 = [](uint64_t pat) { uint32_t u = uint32_t(pat); float f; std::memcpy(&f, &u, 4); return f; };
+            if (f32(p.min_bits) < f32(r.min_bits)) r.min_bits = p.min_bits;
+            if (f32(p.max_bits) > f32(r.max_bits)) r.max_bits = p.max_bits;
         } else {
             r.sum_bits = type_ext(t, r.sum_bits + p.sum_bits);
             bool sg = type_is_signed(t);
@@ -1628,6 +1680,11 @@ int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_a
         double s = fs + fe;
         std::memcpy(&r.sum_bits, &s, 8);
         r.sum_err = (fs - s) + fe;
+    }
+    if (r.valid && t == KX_FLOAT32) {
+        const double s = fs + fe;
+        const float f = float(s); uint32_t u; std::memcpy(&u, &f, 4);
+        r.sum_bits = u; r.sum_err = s - double(f);
     }
     *out = r;
     return KX_OK;
@@ -1872,6 +1929,7 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* m
     const size_t cells = size_t(npacks) * nleaves;
 
     PruneParams P{};
+    bool any_f32 = false;
     P.npacks = uint32_t(npacks); P.nleaves = uint32_t(nleaves); P.npost = uint32_t(prog->postfix.size());
     std::memcpy(P.postfix, prog->postfix.data(), prog->postfix.size());
     for (int l = 0; l < nleaves; ++l) {
@@ -1882,8 +1940,17 @@ int64_t kx_prune(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint64_t* m
         pl.flip = type_is_signed(s.type) ? 0x8000000000000000ull : 0;
         pl.mode = s.mode; pl.is_float = type_is_float(s.type);
         pl.set_off = s.set_off; pl.nset = uint32_t(s.set.size());
-        if (s.type == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_prune: float32 zone maps are not supported");
+        if (s.type == KX_FLOAT32) { pl.a = f32_to_f64_bits(s.a); pl.b = f32_to_f64_bits(s.b); any_f32 = true; }
         if (s.type == KX_BYTES) return fail(ctx, KX_EUNSUPPORTED, "kx_prune: byte-string columns need the resident index (kx_prune_stats)");
+    }
+    std::vector<uint64_t> wmins, wmaxs;   // float32 columns: zone maps widened to float64 patterns
+    if (any_f32) {
+        wmins.assign(mins, mins + cells); wmaxs.assign(maxs, maxs + cells);
+        for (int l = 0; l < nleaves; ++l) {
+            if (prog->leaves[size_t(l)].type != KX_FLOAT32) continue;
+            for (int p = 0; p < npacks; ++p) { size_t c = size_t(p) * nleaves + l; wmins[c] = f32_to_f64_bits(wmins[c]); wmaxs[c] = f32_to_f64_bits(wmaxs[c]); }
+        }
+        mins = wmins.data(); maxs = wmaxs.data();
     }
     size_t nhash = 0;
     if (blooms) { for (int l = 0; l <= nleaves; ++l) P.hash_off[l] = hash_off[l]; nhash = hash_off[nleaves]; }
@@ -1955,8 +2022,12 @@ int kx_stats_create(kx_ctx* ctx, int npacks, const uint16_t* fields, const uint8
     CK(cudaMalloc(&st->d_mins, cells * 8));
     CK(cudaMalloc(&st->d_maxs, cells * 8));
     CK(cudaMalloc(&st->d_tab, cells * 13 + 64));
-    CK(cudaMemcpyAsync(st->d_mins, mins, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(st->d_maxs, maxs, cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    std::vector<uint64_t> wmins(mins, mins + cells), wmaxs(maxs, maxs + cells);
+    for (int f = 0; f < nfields; ++f)   // float32 columns: zone maps widened to float64 patterns (the prune kernels compare float64)
+        if (field_types[f] == KX_FLOAT32)
+            for (int p = 0; p < npacks; ++p) { size_t c = size_t(f) * npacks + p; wmins[c] = f32_to_f64_bits(wmins[c]); wmaxs[c] = f32_to_f64_bits(wmaxs[c]); }
+    CK(cudaMemcpyAsync(st->d_mins, wmins.data(), cells * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(st->d_maxs, wmaxs.data(), cells * 8, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     *out = st.release();
     return KX_OK;
@@ -2089,7 +2160,6 @@ int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* st, const uin
         for (int f = 0; f < st->nfields; ++f) if (st->fields[size_t(f)] == s.field) { fi = f; break; }
         if (fi < 0) return fail(ctx, KX_ENOTFOUND, "kx_prune_stats: leaf field has no statistics column");
         if (st->types[size_t(fi)] != s.type) return fail(ctx, KX_EINVAL, "kx_prune_stats: leaf / statistics type mismatch");
-        if (s.type == KX_FLOAT32) return fail(ctx, KX_EUNSUPPORTED, "kx_prune_stats: float32 zone maps are not supported");
         P.leaf_field[l] = uint8_t(fi);
         P.leaf_nozone[l] = s.type == KX_BYTES;
         PruneLeaf& pl = P.leaves[l];
@@ -2098,10 +2168,12 @@ int64_t kx_prune_stats(kx_ctx* ctx, const kx_prog* prog, kx_stats* st, const uin
         pl.flip = type_is_signed(s.type) ? 0x8000000000000000ull : 0;
         pl.mode = s.mode; pl.is_float = type_is_float(s.type);
         pl.set_off = s.set_off; pl.nset = uint32_t(s.set.size());
+        const uint64_t probe_a = pl.a;   // bloom probes hash the value in its own type
+        if (s.type == KX_FLOAT32) { pl.a = f32_to_f64_bits(s.a); pl.b = f32_to_f64_bits(s.b); }
         if (hashes) { P.hash_off[l] = hash_off[l]; continue; }
         // probe hashes of numeric EQ / IN operands: hash.HashT(v) (internal/hash/hash.go:67-92)
         P.hash_off[l] = uint32_t(own_hashes.size());
-        if (s.type != KX_BYTES && s.mode == KX_MODE_EQ) own_hashes.push_back(kx_hash_value(s.type, pl.a));
+        if (s.type != KX_BYTES && s.mode == KX_MODE_EQ) own_hashes.push_back(kx_hash_value(s.type, probe_a));
         if (s.type != KX_BYTES && s.mode == KX_MODE_IN) for (uint64_t v : s.set) own_hashes.push_back(kx_hash_value(s.type, v));
     }
     P.hash_off[nleaves] = hashes ? hash_off[nleaves] : uint32_t(own_hashes.size());

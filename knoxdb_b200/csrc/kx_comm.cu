@@ -173,7 +173,7 @@ __global__ void xchg_combine_kernel(const RankPartial* __restrict__ recs, uint32
             if (!p.valid) continue;
             if (!acc.valid) { acc = p; continue; }
             acc.count += p.count;
-            if (type == 9) {
+            if (type == 9 || type == 10) {
                 double s = as_f64(acc.sum), e = acc.err, s2 = as_f64(p.sum);
                 double t = s + s2;
                 double c = (fabs(s) >= fabs(s2)) ? ((s - t) + s2) : ((s2 - t) + s);

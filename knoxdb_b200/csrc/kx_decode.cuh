@@ -66,6 +66,14 @@ __device__ __forceinline__ uint64_t decode_value(const ColView& v, uint32_t row,
         uint32_t k = run_of_row(reinterpret_cast<const uint32_t*>(v.aux), v.naux, row);
         return __ldg(reinterpret_cast<const unsigned long long*>(v.data) + k);
     }
+    case CK_ALPRD: {   // DecoderRD.DecodeValue (internal/encode/alp/rd.go:212-219): bits = uint64(left) << shift | right
+        const uint32_t lw = v.naux & 0xffu, shift = (v.naux >> 16) & 0xffu;
+        uint64_t l = (lw ? load_field(reinterpret_cast<const uint32_t*>(v.aux), (uint64_t)row * lw, lw) : 0ull) + v.pad;
+        if ((v.naux >> 8) & 0xffu) l = ((l < 4u ? v.delta >> (16u * (uint32_t)l) : v.extra >> (16u * ((uint32_t)l - 4u))) & 0xffffull);
+        const uint64_t r = (v.width ? load_field(reinterpret_cast<const uint32_t*>(v.data), (uint64_t)row * v.width, v.width) : 0ull) + v.base;
+        const uint64_t bits = ((l & 0xffffull) << shift) | r;
+        return v.type == 10 ? (uint64_t)(uint32_t)bits : bits;
+    }
     case CK_ALP: {   // Decoder.DecodeValue (internal/encode/alp/decoder.go:97-124): patch or T(val) * F10[f] * IF10[e]
         if (v.naux) {
             const uint32_t* pm = reinterpret_cast<const uint32_t*>(v.aux + alp_mask_off(v.naux));

@@ -154,7 +154,7 @@ __device__ __forceinline__ void partial_merge(AggPartial& r, const AggPartial& p
     if (!p.valid) return;
     if (!r.valid) { r = p; return; }
     r.count += p.count;
-    if (type == 9) {
+    if (type == 9 || type == 10) {
         double s = as_f64(r.sum), e = r.err;
         fsum_merge(s, e, as_f64(p.sum), p.err);
         r.sum = as_u64(s); r.err = e;
@@ -620,7 +620,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_general_kernel(const 
                 for (int q = 1; q < CONSUMER_WARPS; ++q) { agg_merge(r, warp_acc[q], type); rc += warp_cnt[q]; }
                 AggPartial o;
                 o.count = rc; o.valid = rc != 0; o.pad = 0;
-                if (type == 9) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
+                if (type == 9 || type == 10) { o.sum = r.s[0]; o.err = as_f64(r.s[1]); o.mn = r.s[2]; o.mx = r.s[3]; }
                 else { o.sum = r.s[0]; o.err = 0.0; o.mn = r.s[1]; o.mx = r.s[2]; }
                 P.partials[(size_t)blockIdx.x * na + j] = o;
             }

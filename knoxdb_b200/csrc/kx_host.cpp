@@ -183,6 +183,21 @@ long parse_container(int type, const uint8_t* buf, size_t len, std::unique_ptr<C
         c->n = c->child[0]->n;
         break;
     }
+    case T_FLOATALPRD: {   // float_alprd.go:78-107: <Left int container of uint16> <Right int container of uint64 / uint32> uv(Shift)
+        if (!type_is_float(type)) { err = "ALP-RD container in a non-float block"; return -1; }
+        long k = parse_container(7 /*uint16*/, r.p, r.left, c->child[0], err, depth + 1);
+        if (k < 0) return -1;
+        r.take(size_t(k));
+        k = parse_container(type == 9 ? 5 /*uint64*/ : 6 /*uint32*/, r.p, r.left, c->child[1], err, depth + 1);
+        if (k < 0) return -1;
+        r.take(size_t(k));
+        c->log2 = int(r.uv());   // the cut: right = low `Shift` bits, left = the (at most 16) bits above
+        if (!r.ok) { err = "truncated container"; return -1; }
+        if (c->log2 < 0 || c->log2 >= type_bits(type) || type_bits(type) - c->log2 > 16) { err = "ALP-RD: bad shift"; return -1; }
+        if (c->child[0]->n != c->child[1]->n) { err = "ALP-RD: left/right length mismatch"; return -1; }
+        c->n = c->child[0]->n;
+        break;
+    }
     default:
         err = "unsupported container type " + std::to_string(c->ctype);
         return -1;
@@ -246,6 +261,12 @@ bool decode_container(const Container& c, std::vector<uint64_t>& out, std::strin
             if (!decode_container(*c.child[1], pv, err) || !decode_container(*c.child[2], pp, err)) return false;
             for (size_t k = 0; k < pp.size(); k++) { if (pp[k] >= c.n) { err = "ALP: patch position out of range"; return false; } out[pp[k]] = pv[k]; }
         }
+        return true;
+    }
+    case T_FLOATALPRD: {
+        std::vector<uint64_t> l, r;
+        if (!decode_container(*c.child[0], l, err) || !decode_container(*c.child[1], r, err)) return false;
+        for (size_t i = 0; i < c.n; i++) { uint64_t b = ((l[i] & 0xffff) << c.log2) | r[i]; out[i] = c.type == 10 ? uint64_t(uint32_t(b)) : b; }
         return true;
     }
     case T_RUNEND: {
@@ -364,6 +385,55 @@ int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, 
                 v.extra = v.base + (v.width ? bit_field(st, sl, pp[0], v.width) : 0);
             }
         }
+        return 0;
+    }
+    case T_FLOATALPRD: {
+        // both halves stay bit streams on the device: the right one verbatim (always bit-packed by the encoder), the left one
+        // verbatim too — bit-packed left values or the bit-packed codes of a dictionary of at most eight uint16 entries
+        // (float_alprd.go:148-160).  Any other child shape (never written by the encoder) is re-packed once here.
+        const Container &lc = *c->child[0], &rc = *c->child[1];
+        v.kind = CK_ALPRD; v.is_raw = 0;
+        uint32_t lw = 0, isdict = 0; uint64_t lfor = 0;
+        auto repack = [&](const Container& x, std::vector<uint8_t>& dst, uint32_t& w, uint64_t& base) -> bool {
+            std::vector<uint64_t> vals;
+            if (!decode_container(x, vals, err)) return false;
+            uint64_t mn = ~0ull, mx = 0;
+            for (uint64_t q : vals) { mn = std::min(mn, q); mx = std::max(mx, q); }
+            if (vals.empty()) mn = mx = 0;
+            w = uint32_t(log2_range(mn, mx)); base = mn;
+            for (auto& q : vals) q -= mn;
+            if (w) pack_stream(vals, int(w), dst);
+            return true;
+        };
+        if (rc.ctype == T_BITPACK) { v.width = uint8_t(rc.log2); v.base = rc.val; out.stream = rc.payload; out.stream_len = rc.payload_len; }
+        else if (rc.ctype == T_CONST) { v.width = 0; v.base = rc.val; }
+        else { uint32_t w = 0; uint64_t b = 0; if (!repack(rc, out.owned, w, b)) return -6; v.width = uint8_t(w); v.base = b; }
+        bool done = false;
+        if (lc.ctype == T_BITPACK) {
+            lw = uint32_t(lc.log2); lfor = lc.val & 0xffff;
+            out.blob.assign(lc.payload, lc.payload + lc.payload_len);
+            done = true;
+        } else if (lc.ctype == T_CONST) {
+            lw = 0; lfor = lc.val & 0xffff; done = true;
+        } else if (lc.ctype == T_DICT && lc.child[1]->ctype == T_BITPACK && lc.child[0]->n <= 8) {
+            std::vector<uint64_t> dv;
+            if (!decode_container(*lc.child[0], dv, err)) return -6;
+            for (size_t k = 0; k < dv.size(); k++) (k < 4 ? v.delta : v.extra) |= (dv[k] & 0xffff) << (16 * (k & 3));
+            const Container& codes = *lc.child[1];
+            if (codes.val + ((codes.log2 >= 16) ? 0xffffull : ((1ull << codes.log2) - 1)) >= 8 && codes.log2) {
+                // codes could exceed the eight slots only in a corrupt block: check them
+                std::vector<uint64_t> cv;
+                if (!decode_container(codes, cv, err)) return -6;
+                for (uint64_t q : cv) if (q >= dv.size()) { err = "ALP-RD: left code outside its dictionary"; return -6; }
+            } else if (codes.val >= dv.size() && codes.n) { err = "ALP-RD: left code outside its dictionary"; return -6; }
+            lw = uint32_t(codes.log2); lfor = codes.val & 0xffff; isdict = 1;
+            out.blob.assign(codes.payload, codes.payload + codes.payload_len);
+            done = true;
+        }
+        if (!done) { uint32_t w = 0; uint64_t b = 0; if (!repack(lc, out.blob, w, b)) return -6; lw = w; lfor = b & 0xffff; }
+        out.blob.resize(out.blob.size() + 64, 0);   // readable slack behind the left stream
+        v.naux = lw | (isdict << 8) | (uint32_t(c->log2) << 16);
+        v.pad = uint32_t(lfor);
         return 0;
     }
     case T_S8B: {

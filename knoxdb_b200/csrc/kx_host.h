@@ -13,7 +13,7 @@
 namespace kx {
 
 // container ids, internal/encode/container.go:20-55
-enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATALP = 13, T_FLOATRAW = 15,
+enum : int { T_CONST = 1, T_DELTA = 2, T_RUNEND = 3, T_BITPACK = 4, T_DICT = 5, T_S8B = 6, T_RAW = 7, T_FLOATALP = 13, T_FLOATALPRD = 14, T_FLOATRAW = 15,
              T_STRCONST = 16, T_STRFIXED = 17, T_STRCOMPACT = 18, T_STRDICT = 19 };
 // types.FilterMode, internal/types/mode.go:14-23
 enum : int { M_EQ = 1, M_NE = 2, M_GT = 3, M_GE = 4, M_LT = 5, M_LE = 6, M_IN = 7, M_NIN = 8, M_RANGE = 9 };

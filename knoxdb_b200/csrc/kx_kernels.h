@@ -60,6 +60,16 @@ struct StrJob {
 };
 cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_rows, const uint8_t* pool, uint8_t* out_base, cudaStream_t stream);
 
+// one leaf of valmatch_kernel: bit i of the leaf bitset at out_base + out_off = float predicate on the value decoded at row i
+// (ALP-RD blocks: FloatAlpRdContainer.Match*, internal/encode/float_alprd.go:181-211)
+struct ValJob {
+    ColView view;
+    uint64_t a, b;         // operands (IEEE bits of the block's float type)
+    uint64_t out_off;      // byte offset of the leaf bitset
+    uint32_t mode, pad;    // types.FilterMode (EQ, NE, GT, GE, LT, LE, RANGE)
+};
+cudaError_t launch_valmatch(const ValJob* jobs, uint32_t njobs, uint32_t max_rows, uint8_t* out_base, cudaStream_t stream);
+
 // one ALP leaf of alpfix_kernel: bit pos[k] of the correction stream = pred(patch value k) (invert: !pred)
 struct AlpFixJob {
     const uint8_t* blob;   // patch blob of the block (positions | values | bitmap)

@@ -543,12 +543,13 @@ __device__ __forceinline__ uint64_t as_u64(double d) { return (uint64_t)__double
 
 __device__ __forceinline__ AggAcc agg_identity(int type) {
     AggAcc A;
-    if (type == 9) { A.s[0] = 0; A.s[1] = 0; A.s[2] = 0x7ff0000000000000ull; A.s[3] = 0xfff0000000000000ull; }
+    if (type == 9 || type == 10) { A.s[0] = 0; A.s[1] = 0; A.s[2] = 0x7ff0000000000000ull; A.s[3] = 0xfff0000000000000ull; }
     else { A.s[0] = 0; A.s[1] = ~0ull; A.s[2] = 0; A.s[3] = 0; }
     return A;
 }
 
 __device__ __forceinline__ void agg_add(AggAcc& A, int type, uint64_t bits) {
+    if (type == 10) { bits = as_u64((double)__uint_as_float((uint32_t)bits)); type = 9; }   // float32 columns accumulate in float64 (exact widening)
     if (type == 9) {   // float64: compensated running sum (deterministic per thread)
         double x = as_f64(bits), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
         double t = sum + x;
@@ -574,7 +575,7 @@ __device__ __forceinline__ void fsum_merge(double& s, double& e, double s2, doub
 
 // merge B into A (identities merge as no-ops)
 __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) {
-    if (type == 9) {
+    if (type == 9 || type == 10) {
         double s = as_f64(A.s[0]), e = as_f64(A.s[1]);
         fsum_merge(s, e, as_f64(B.s[0]), as_f64(B.s[1]));
         A.s[0] = as_u64(s); A.s[1] = as_u64(e);

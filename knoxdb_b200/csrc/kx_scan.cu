@@ -31,8 +31,9 @@ namespace kx {
 // Dictionary-set translation (DictionaryContainer.translateSet, int_dict.go:400-440) on the device: one thread per
 // SET value binary-searches the pack's dictionary (sorted, unique, in T order: `flip` maps it to unsigned order) and
 // sets the bit of the code it finds.  Runs on the scan stream right before scan_kernel; blockIdx.y = (pack, leaf) job.
-__global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, const uint64_t* __restrict__ set_vals, uint32_t* __restrict__ out) {
-    const CodesetJob J = jobs[blockIdx.y];
+__global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, uint32_t njobs, const uint64_t* __restrict__ set_vals, uint32_t* __restrict__ out) {
+  for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {   // (gridDim.y is capped at 65535 jobs per launch)
+    const CodesetJob J = jobs[jb];
     const unsigned long long* dict = reinterpret_cast<const unsigned long long*>(J.dict);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < J.nset; i += gridDim.x * blockDim.x) {
         const uint64_t val = __ldg(set_vals + J.set_off + i), key = val ^ J.flip;
@@ -43,13 +44,15 @@ __global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, const uint64
         }
         if (lo < J.ndict && __ldg(dict + lo) == val) atomicOr(out + J.out_off + (lo >> 5), 1u << (lo & 31u));
     }
+  }
 }
 
 // ALP blocks: rows that are patches carry their true value outside the encoded stream.  One thread per patch
 // evaluates the float predicate on it (the loops over `vals, pos` of float_alp.go:238-495) and sets the bit of
 // its row in the leaf's correction stream (zeroed before the launch), which the scan ORs in / ANDs out.
-__global__ void alpfix_kernel(const AlpFixJob* __restrict__ jobs, uint8_t* __restrict__ out_base) {
-    const AlpFixJob J = jobs[blockIdx.y];
+__global__ void alpfix_kernel(const AlpFixJob* __restrict__ jobs, uint32_t njobs, uint8_t* __restrict__ out_base) {
+  for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {
+    const AlpFixJob J = jobs[jb];
     const uint32_t* pos = reinterpret_cast<const uint32_t*>(J.blob);
     const double* vals = reinterpret_cast<const double*>(J.blob + alp_vals_off(J.np));
     uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
@@ -67,13 +70,15 @@ __global__ void alpfix_kernel(const AlpFixJob* __restrict__ jobs, uint8_t* __res
         }
         if (p != (J.invert != 0)) { uint32_t r = pos[k]; atomicOr(out + (r >> 5), 1u << (r & 31u)); }
     }
+  }
 }
 
 // Run-end blocks: the predicate is evaluated once per RUN by this pre-pass (RunEndContainer.Match* +
 // applyMatch, internal/encode/int_runend.go:224-318: match the run values, SetRange(start, end) per
 // matching run); the scan kernel then streams the resulting per-leaf bitset like a 1-bit column.
-__global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, const uint64_t* __restrict__ set_vals, uint8_t* __restrict__ out_base) {
-    const RunFillJob J = jobs[blockIdx.y];
+__global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, uint32_t njobs, const uint64_t* __restrict__ set_vals, uint8_t* __restrict__ out_base) {
+  for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {
+    const RunFillJob J = jobs[jb];
     const uint32_t* ends = reinterpret_cast<const uint32_t*>(J.ends);
     const unsigned long long* vals = reinterpret_cast<const unsigned long long*>(J.vals);
     uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
@@ -90,6 +95,41 @@ __global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, const uint64
         atomicOr(out + w0, m0);
         for (uint32_t w = w0 + 1; w < w1; ++w) out[w] = 0xffffffffu;   // words owned by this run alone
         atomicOr(out + w1, m1);
+    }
+  }
+}
+
+// Value pre-pass: decode at index + IEEE compare per row, one thread per row, one ballot per 32 rows → the leaf's 1-bit
+// column (streamed by the scan like a run-end pre-pass result).  Used for ALP-RD blocks, whose reference matchers decode
+// chunk by chunk and run the float compare kernels (float_alprd.go:181-211, cmp/float.go:13-242).
+__global__ void valmatch_kernel(const ValJob* __restrict__ jobs, uint32_t njobs, uint8_t* __restrict__ out_base) {
+    for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {
+        const ValJob& J = jobs[jb];
+        const ColView v = J.view;
+        uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
+        const uint32_t nw = (v.n + 31u) >> 5;
+        const bool f32 = v.type == 10;
+        const double a = f32 ? (double)__uint_as_float((uint32_t)J.a) : __longlong_as_double((long long)J.a);
+        const double b = f32 ? (double)__uint_as_float((uint32_t)J.b) : __longlong_as_double((long long)J.b);
+        for (uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nw; w += (gridDim.x * blockDim.x) >> 5) {
+            const uint32_t row = w * 32u + (threadIdx.x & 31u);
+            bool p = false;
+            if (row < v.n) {
+                const uint64_t bits = decode_value(v, row, nullptr, 0);
+                const double x = f32 ? (double)__uint_as_float((uint32_t)bits) : __longlong_as_double((long long)bits);   // float32 → float64 is exact
+                switch (J.mode) {
+                case 1: p = x == a; break;
+                case 2: p = x != a; break;
+                case 3: p = x > a; break;
+                case 4: p = x >= a; break;
+                case 5: p = x < a; break;
+                case 6: p = x <= a; break;
+                default: p = a <= x && x <= b; break;
+                }
+            }
+            const uint32_t word = __ballot_sync(0xffffffffu, p);
+            if ((threadIdx.x & 31u) == 0) out[w] = word;
+        }
     }
 }
 
@@ -532,11 +572,19 @@ cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool o
     return cudaGetLastError();
 }
 
+cudaError_t launch_valmatch(const ValJob* jobs, uint32_t njobs, uint32_t max_rows, uint8_t* out_base, cudaStream_t stream) {
+    if (njobs == 0 || max_rows == 0) return cudaSuccess;
+    uint32_t gx = (max_rows + 255u) / 256u;
+    if (gx > 148u * 8u) gx = 148u * 8u;
+    valmatch_kernel<<<dim3(gx, njobs < 65535u ? njobs : 65535u), 256, 0, stream>>>(jobs, njobs, out_base);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream) {
     if (njobs == 0 || max_patches == 0) return cudaSuccess;
     uint32_t gx = (max_patches + 255u) / 256u;
     if (gx > 148u) gx = 148u;
-    alpfix_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs, out_base);
+    alpfix_kernel<<<dim3(gx, njobs < 65535u ? njobs : 65535u), 256, 0, stream>>>(jobs, njobs, out_base);
     return cudaGetLastError();
 }
 
@@ -544,7 +592,7 @@ cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_
     if (njobs == 0 || max_runs == 0) return cudaSuccess;
     uint32_t gx = (max_runs + 255u) / 256u;
     if (gx > 148u * 4u) gx = 148u * 4u;
-    runfill_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs, set_vals, out_base);
+    runfill_kernel<<<dim3(gx, njobs < 65535u ? njobs : 65535u), 256, 0, stream>>>(jobs, njobs, set_vals, out_base);
     return cudaGetLastError();
 }
 
@@ -552,7 +600,7 @@ cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, uint32_t max_
     if (njobs == 0 || max_set == 0) return cudaSuccess;
     uint32_t gx = (max_set + 127u) / 128u;
     if (gx > 32u) gx = 32u;
-    codeset_kernel<<<dim3(gx, njobs), 128, 0, stream>>>(jobs, set_vals, out);
+    codeset_kernel<<<dim3(gx, njobs < 65535u ? njobs : 65535u), 128, 0, stream>>>(jobs, njobs, set_vals, out);
     return cudaGetLastError();
 }
 

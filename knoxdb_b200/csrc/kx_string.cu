@@ -40,9 +40,11 @@ __device__ __forceinline__ bool str_pred(uint32_t mode, const uint8_t* __restric
 
 constexpr uint32_t STR_DICT_SMEM_ENTRIES = 32768;   // dictionary predicate bitmap in shared memory: 4 KB
 
-__global__ void __launch_bounds__(256) strmatch_kernel(const StrJob* __restrict__ jobs, const uint8_t* __restrict__ pool, uint8_t* __restrict__ out_base) {
+__global__ void __launch_bounds__(256) strmatch_kernel(const StrJob* __restrict__ jobs, uint32_t njobs, const uint8_t* __restrict__ pool, uint8_t* __restrict__ out_base) {
     __shared__ uint32_t dict_bits[STR_DICT_SMEM_ENTRIES / 32];
-    const StrJob& J = jobs[blockIdx.y];
+  for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {   // (gridDim.y is capped at 65535 jobs per launch)
+    __syncthreads();   // the previous job's dictionary bitmap is no longer read
+    const StrJob& J = jobs[jb];
     const ColView& v = J.view;
     const uint32_t n = v.n, layout = v.is_raw;
     const uint8_t* a = pool + J.a_off;
@@ -85,6 +87,7 @@ __global__ void __launch_bounds__(256) strmatch_kernel(const StrJob* __restrict_
         const uint32_t w = __ballot_sync(0xffffffffu, p);
         if (lane == 0) out[g] = w;   // rows past n are zero: the tail bits of the bitset stay clear
     }
+  }
 }
 
 cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_rows, const uint8_t* pool, uint8_t* out_base, cudaStream_t stream) {
@@ -92,7 +95,7 @@ cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_row
     uint32_t gx = (max_rows + 256u * 8u - 1u) / (256u * 8u);   // ~8 groups per warp
     if (gx > 148u * 4u) gx = 148u * 4u;
     if (gx < 1u) gx = 1u;
-    strmatch_kernel<<<dim3(gx, njobs), 256, 0, stream>>>(jobs, pool, out_base);
+    strmatch_kernel<<<dim3(gx, njobs < 65535u ? njobs : 65535u), 256, 0, stream>>>(jobs, njobs, pool, out_base);
     return cudaGetLastError();
 }
 

@@ -29,6 +29,10 @@ enum ColKind : uint8_t {
                     // value = double(field + base) * F10[factor] * IF10[exponent]; delta = exponent << 8 | factor;
                     // aux = patch blob [positions u32 x naux | values u64 x naux | patch bitmap u32 x ceil(n/32)],
                     // extra = the encoded replacement value stored at patch positions
+    CK_ALPRD = 8,   // FloatAlpRd (float64 / float32): IEEE bits = (left << shift) | right.  data = RIGHT bit stream (`width`
+                    // bits per row, value = field + base); aux = LEFT bit stream (lw bits per row, value = field + pad);
+                    // naux = lw | is_dict << 8 | shift << 16; left values that are dictionary codes index the <= 8
+                    // uint16 entries packed into delta (entries 0..3) and extra (4..7)
     CK_STR = 7,     // byte strings (BlockBytes): data = byte buffer, aux = u32 index array, is_raw = STR_* layout,
                     // delta = row size (STR_FIXED / STR_CONST), naux = dictionary entries (STR_DICT), base = bytes in data
 };

@@ -185,6 +185,12 @@ static void reduce_one(int type, uint64_t v, ko_agg* st) {
         memcpy(&mn, &st->min_bits, 8); memcpy(&mx, &st->max_bits, 8);
         if (!st->valid || mx < d) memcpy(&st->max_bits, &d, 8);
         if (!st->valid || mn > d) memcpy(&st->min_bits, &d, 8);
+    } else if (type == KO_F32) {   /* SumReducer[float32]: the running sum is a float32 */
+        uint32_t u = (uint32_t)v, w; float d, s, mn, mx; memcpy(&d, &u, 4);
+        w = (uint32_t)st->sum_bits; memcpy(&s, &w, 4); s += d; memcpy(&w, &s, 4); st->sum_bits = w;
+        w = (uint32_t)st->min_bits; memcpy(&mn, &w, 4); w = (uint32_t)st->max_bits; memcpy(&mx, &w, 4);
+        if (!st->valid || mx < d) st->max_bits = u;
+        if (!st->valid || mn > d) st->min_bits = u;
     } else if (type == KO_I64 || type == KO_I32 || type == KO_I16 || type == KO_I8) {
         st->sum_bits += v; /* wraps mod 2^64 like int64 `+=` */
         if (!st->valid || (int64_t)st->max_bits < (int64_t)v) st->max_bits = v;
