@@ -216,6 +216,12 @@ int kx_agg_combine(uint8_t block_type, const kx_agg_out* parts, int nparts, kx_a
  * on host.  launches = kernels launched. */
 int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* launches);
 
+/* Test hook.  With KX_GUARD=1 in the environment (read when the library is loaded) every device scratch / result buffer of
+ * the library is allocated exactly as large as needed and followed by 256 bytes of 0xFA (the reference poisons the slack of
+ * its test outputs the same way, internal/cmp/tests/gen.go:13-44); this call returns how many of those zones were
+ * overwritten (0 = no kernel or copy wrote past the end of a buffer), KX_EUNSUPPORTED when guard mode is off. */
+int kx_debug_check_guards(kx_ctx* ctx);
+
 /* The counters a query reports through QueryStats (internal/query/stats.go:15-60: rows_scanned, packs_scanned,
  * rows_matched, scan_time …) for the last kx_scan* call on this ctx, so that the Go adapter can feed
  * stats.Count / stats.Tick with what the device did (one call covers what the reference counts pack by pack in

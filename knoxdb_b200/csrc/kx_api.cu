@@ -35,10 +35,30 @@ constexpr size_t SLAB_BYTES = 256ull << 20;
 
 size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Guard mode (KX_GUARD=1 in the environment when the library is loaded; tests only — compute-sanitizer is not available on
+// every pool): device scratch buffers are allocated EXACTLY as large as asked, followed by a 256 B zone of 0xFA, and
+// kx_debug_check_guards() verifies the zones: a kernel or copy that writes past the end of a result / scratch buffer is caught
+// (the reference poisons the slack of its own test outputs the same way, internal/cmp/tests/gen.go:13-44).
+constexpr size_t GUARD_BYTES = 256;
+bool guard_mode() { static const bool g = getenv("KX_GUARD") && atoi(getenv("KX_GUARD")) != 0; return g; }
+struct DevBuf;
+std::vector<DevBuf*>& guarded_bufs() { static std::vector<DevBuf*> v; return v; }
+std::mutex& guarded_mu() { static std::mutex m; return m; }
+
 // grow-only device / pinned buffers
 struct DevBuf {
-    void* p = nullptr; size_t cap = 0;
+    void* p = nullptr; size_t cap = 0, asked = 0;
     cudaError_t reserve(size_t n) {
+        if (guard_mode()) {
+            if (p && n == asked) return cudaSuccess;
+            if (p) cudaFree(p); else { std::lock_guard<std::mutex> lk(guarded_mu()); guarded_bufs().push_back(this); }
+            p = nullptr; cap = 0; asked = n;
+            cudaError_t e = cudaMalloc(&p, n + GUARD_BYTES);
+            if (e == cudaSuccess) { cap = n; e = cudaMemset(p, 0, n); }
+            if (e == cudaSuccess) e = cudaMemset(static_cast<uint8_t*>(p) + n, 0xFA, GUARD_BYTES);
+            if (e == cudaSuccess) e = cudaDeviceSynchronize();
+            return e;
+        }
         if (n <= cap) return cudaSuccess;
         if (p) cudaFree(p);
         p = nullptr; cap = 0;
@@ -50,7 +70,18 @@ struct DevBuf {
         if (e == cudaSuccess) e = cudaDeviceSynchronize();
         return e;
     }
-    ~DevBuf() { if (p) cudaFree(p); }
+    // guard mode: is the zone behind the buffer intact?
+    bool guard_intact() const {
+        if (!guard_mode() || !p) return true;
+        uint8_t z[GUARD_BYTES];
+        if (cudaMemcpy(z, static_cast<const uint8_t*>(p) + asked, GUARD_BYTES, cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+        for (uint8_t b : z) if (b != 0xFA) return false;
+        return true;
+    }
+    ~DevBuf() {
+        if (guard_mode()) { std::lock_guard<std::mutex> lk(guarded_mu()); auto& v = guarded_bufs(); v.erase(std::remove(v.begin(), v.end(), this), v.end()); }
+        if (p) cudaFree(p);
+    }
 };
 struct PinBuf {
     void* p = nullptr; size_t cap = 0;
@@ -1847,6 +1878,18 @@ int kx_last_scan_stats(kx_ctx* ctx, double* kernel_ms, double* total_ms, int* la
     if (total_ms) *total_ms = ctx->last_total_ms;
     if (launches) *launches = ctx->last_launches;
     return KX_OK;
+}
+
+int kx_debug_check_guards(kx_ctx* ctx) {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (!guard_mode()) return KX_EUNSUPPORTED;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    int bad = 0;
+    std::lock_guard<std::mutex> lk2(guarded_mu());
+    for (DevBuf* b : guarded_bufs()) if (!b->guard_intact()) ++bad;
+    return bad;
 }
 
 int kx_last_query_stats(kx_ctx* ctx, kx_query_stats* out) {

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "kx_hash_value", "kx_hash_bytes",
     "kx_scan_select", "kx_gather", "kx_scan_buckets",
     "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
-    "kx_scan_ex", "kx_last_query_stats", "kx_comm_unique_id", "kx_comm_init", "kx_comm_info", "kx_scan_sharded", "kx_comm_allgather",
+    "kx_scan_ex", "kx_debug_check_guards", "kx_last_query_stats", "kx_comm_unique_id", "kx_comm_init", "kx_comm_info", "kx_scan_sharded", "kx_comm_allgather",
 ]
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
@@ -145,6 +145,7 @@ def lib():
         "kx_hash_value": (C.c_uint64, [C.c_uint8, C.c_uint64]),
         "kx_hash_bytes": (C.c_uint64, [vp, sz]),
         "kx_scan_ex": (C.c_int, [vp, vp, C.POINTER(ScanArgs)]),
+        "kx_debug_check_guards": (C.c_int, [vp]),
         "kx_last_query_stats": (C.c_int, [vp, C.POINTER(QueryStats)]),
         "kx_comm_unique_id": (C.c_int, [vp, sz]),
         "kx_comm_init": (C.c_int, [vp, C.c_int, C.c_int, vp, sz]),
@@ -330,6 +331,10 @@ class Context:
         recv = np.zeros((n, send.size), dtype=np.uint8)
         self._check(lib().kx_comm_allgather(self.h, _ptr(send), _ptr(recv), send.size))
         return recv
+
+    def check_guards(self):
+        """guard mode (KX_GUARD=1): number of device buffers whose trailing guard zone was overwritten"""
+        return self._check(lib().kx_debug_check_guards(self.h))
 
     def last_query_stats(self):
         q = QueryStats()
