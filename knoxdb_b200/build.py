@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libknoxgpu.so")
-SOURCES = ["kx_scan.cu", "kx_general.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_comm.cu", "kx_api.cu", "kx_host.cpp"]
+SOURCES = ["kx_scan.cu", "kx_general.cu", "kx_warp.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_comm.cu", "kx_api.cu", "kx_host.cpp"]
 HEADERS = ["kx_types.h", "kx_kernels.h", "kx_host.h", "kx_xxh3.h", "kx_decode.cuh", "kx_leaf.cuh", "kx_comm.h", os.path.join("..", "..", "include", "knoxgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter,-ffp-contract=off"]

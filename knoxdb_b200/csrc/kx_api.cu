@@ -424,10 +424,17 @@ kx_agg_out agg_result(const AggPartial& a, int t) {
     return o;
 }
 
+// shared-memory layout of the warp-autonomous kernel for one program (ScanParams::w_*)
+struct WarpGeo {
+    uint32_t wd, stages, warps, ncols, stage_bytes, stage_off, warp_bytes;
+    uint8_t slot[32];
+    uint16_t slot_off[32], col_off[MAX_SCAN_LEAVES], fix_off[MAX_SCAN_LEAVES];
+};
+
 // everything the launch + result phase of a scan needs (filled by run_scan, or taken from the plan cache)
 struct LaunchArgs {
     ScanParams P{};
-    int grid = 1; size_t smem_bytes = 0; bool simple = true, only32 = true; int ctas = 2;
+    int grid = 1; size_t smem_bytes = 0; bool simple = true, only32 = true, warp = false; int ctas = 2;
     int npacks = 0, naggs = 0; uint32_t ntiles = 0; uint64_t total_rows = 0;
     const uint8_t* hd = nullptr; uint8_t* dd = nullptr; size_t desc_bytes = 0;   // descriptor block: host staging → device (hd == nullptr: already resident)
     size_t leafbits_bytes = 0; uint32_t code_words = 0;
@@ -479,6 +486,7 @@ int launch_and_collect(kx_ctx* ctx, LaunchArgs& A) {
     }
     if (ntiles) {
         if (A.simple) CK(launch_scan(P, A.grid, A.smem_bytes, A.only32, A.ctas, ctx->stream));
+        else if (A.warp) CK(launch_scan_warp(P, A.grid, A.smem_bytes, ctx->stream));
         else CK(launch_scan_general(P, A.grid, A.smem_bytes, A.ctas, ctx->stream));
         ctx->last_launches++;
     }
@@ -541,7 +549,7 @@ struct PlanKey {
 };
 uint64_t env_knobs_hash() {   // the tuning hooks change the plan: they are part of the key
     uint64_t h = 1469598103934665603ull;
-    for (const char* k : {"KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES", "KX_HASH_SMEM_KB"}) {
+    for (const char* k : {"KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES", "KX_HASH_SMEM_KB", "KX_GENERAL", "KX_WARP_GEOMETRY"}) {
         const char* v = getenv(k);
         for (const char* c = v ? v : ""; *c; ++c) h = (h ^ uint8_t(*c)) * 1099511628211ull;
         h = (h ^ 0xff) * 1099511628211ull;
@@ -806,9 +814,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     struct Geo { int ctas, stages; size_t budget; };
     const bool simple = nl == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
     const bool simple32 = only32 && simple;
-    // dictionary-code bitmaps cached in shared memory behind the ring
+    // multi-leaf programs and fused reduces run the warp-autonomous kernel (kx_warp.cu); KX_GENERAL=v2 selects the older
+    // producer/consumer kernel (kx_general.cu) for comparison
+    const bool use_warp = !simple && !(getenv("KX_GENERAL") && !strcmp(getenv("KX_GENERAL"), "v2"));
+    // dictionary-code bitmaps cached in shared memory behind the ring (the warp kernel reads them in place)
     uint32_t code_smem_off[MAX_SCAN_LEAVES] = {}, code_smem_words = 0;
-    for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
+    if (!use_warp) for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
     // hash-set leaves: prefilter bitmap (<= 16 KB) and, when it is small (<= 16 KB: sets up to ~500 keys), the exact table
     // in shared memory too; larger tables stay in global memory (L2) and only candidates are verified against them
     uint32_t hs_smem_off[MAX_SCAN_LEAVES] = {}, hs_tab_smem_off[MAX_SCAN_LEAVES] = {};
@@ -876,6 +887,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
             R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
         }
+    } else if (use_warp) {
+        // warp-autonomous kernel: chosen below (per-warp rings)
     } else {
         // general kernel: one stage = one leaf column (or one value chunk) of a whole tile.  The reduce lags one tile behind
         // the filter, so a tile keeps several stages busy: prefer the largest tile that leaves `want` stages (KX_MIN_STAGES),
@@ -909,19 +922,95 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     }
     // small scans: prefer more, smaller tiles so that every CTA of the persistent grid gets work
     while (R > 32 && total_rows / (uint64_t(256) * R) < uint64_t(4) * ctx->num_sms * geo.ctas) R -= 32;
+    // ---- warp-autonomous kernel: a tile is 1024 wd rows of ONE warp; a ring stage holds one slot per staged column
+    // (leaf streams in postfix order, ALP correction streams behind their leaf); every warp of the single CTA per SM owns
+    // `stages` stages plus its match words, AND/OR stack and descriptor cache
+    WarpGeo wg{};
+    if (use_warp) {
+        uint32_t leaf_w[MAX_SCAN_LEAVES] = {};
+        bool leaf_fixs[MAX_SCAN_LEAVES] = {};
+        for (int p = 0; p < npacks; ++p)
+            for (size_t l = 0; l < nl; ++l) {
+                const PackLeaf& o = pl[size_t(p) * nl + l];
+                const uint32_t w = o.data ? o.width : (o.mode == LM_BITS ? 1u : 0u);   // (pre-pass columns get their pointer below)
+                leaf_w[l] = std::max(leaf_w[l], w);
+                if (o.fixmode) leaf_fixs[l] = true;
+            }
+        const uint32_t max_warps = naggs > 2 ? 8u : 16u;
+        auto layout = [&](uint32_t wd, uint32_t stages, WarpGeo& g) {
+            g = WarpGeo{};
+            g.wd = wd; g.stages = stages;
+            size_t off = 0;
+            uint32_t ns = 0;
+            for (uint8_t op : post) {
+                if (op >= 0x80) continue;
+                if (leaf_w[op]) {
+                    g.col_off[op] = uint16_t(off / 16); g.slot[ns] = op; g.slot_off[ns] = uint16_t(off / 16); ++ns;
+                    off += round_up(size_t(128) * wd * leaf_w[op], 16) + 16;   // (+ 16: the hash-set walk reads two words past a field)
+                }
+                if (leaf_fixs[op]) {
+                    g.fix_off[op] = uint16_t(off / 16); g.slot[ns] = uint8_t(op | 0x80); g.slot_off[ns] = uint16_t(off / 16); ++ns;
+                    off += size_t(128) * wd + 16;
+                }
+            }
+            if (ns == 0) { g.slot[0] = 0xff; g.slot_off[0] = 0; ns = 1; }   // nothing staged: the barrier still gets one (empty) arrival per tile
+            g.ncols = ns;
+            g.stage_bytes = uint32_t(round_up(std::max<size_t>(off, 16), 128));
+            const size_t fixed = 128 + size_t(2) * wd * 128 + size_t(stack_depth) * wd * 128 + size_t(desc_words) * 4;
+            g.stage_off = uint32_t(round_up(fixed, 128));
+            g.warp_bytes = g.stage_off + stages * g.stage_bytes;
+            const size_t room = WARP_MAX_DYN_SMEM > code_smem_bytes ? WARP_MAX_DYN_SMEM - code_smem_bytes : 0;
+            g.warps = uint32_t(std::min<size_t>(max_warps, room / g.warp_bytes));
+        };
+        // preference (measured, profiles/r2_tune_warp.txt): 2048-row tiles beat 1024-row tiles even when only 10-12 warps
+        // fit beside them (per-tile control code is amortised over twice the rows); all 16 warps with two stages beat 12 with three
+        const uint32_t cand[][3] = {{2, 2, 16}, {2, 3, 12}, {2, 2, 10}, {1, 3, 16}, {1, 2, 1}};
+        bool found = false;
+        for (auto& c : cand) {
+            layout(c[0], c[1], wg);
+            if (wg.warps >= std::min(c[2], max_warps)) { found = true; break; }
+        }
+        if (!found) return fail(ctx, KX_EUNSUPPORTED, "scan program does not fit the shared memory of one SM");
+        if (const char* e = getenv("KX_WARP_GEOMETRY")) {   // tuning hook: "wd,stages,warps"
+            int a = 0, b = 0, c = 0;
+            if (sscanf(e, "%d,%d,%d", &a, &b, &c) == 3 && (a == 1 || a == 2 || a == 4) && b >= 2 && b <= 4 && c >= 1 && c <= int(max_warps)) {
+                WarpGeo t{};
+                layout(uint32_t(a), uint32_t(b), t);
+                if (t.warps >= 1) { wg = t; wg.warps = std::min<uint32_t>(wg.warps, uint32_t(c)); }
+            }
+        }
+        // small scans: prefer more, smaller tiles so that every warp of the persistent grid gets work
+        while (wg.wd > 1 && total_rows / (uint64_t(1024) * wg.wd) < uint64_t(4) * ctx->num_sms * wg.warps) {
+            const uint32_t keep_warps = wg.warps;
+            layout(wg.wd / 2, wg.stages, wg);
+            wg.warps = std::min(wg.warps, keep_warps);
+        }
+        R = 4 * wg.wd;   // tile rows = 256 R = 1024 wd
+        geo.ctas = 1; geo.stages = int(wg.stages);
+    }
     const uint32_t tile_rows = 256 * R;
-    const size_t stage_bytes = stage_bytes_for(R);
-    const size_t smem_bytes = 128 + size_t(geo.stages) * stage_bytes + extra_smem_for(R);
+    const size_t stage_bytes = use_warp ? wg.stage_bytes : stage_bytes_for(R);
+    const size_t smem_bytes = use_warp ? size_t(wg.warps) * wg.warp_bytes + code_smem_bytes : 128 + size_t(geo.stages) * stage_bytes + extra_smem_for(R);
     if (naggs) {   // chunks per pass of the reduce: as few as fit a stage
         agg_kp = 1;
         while (agg_kp < 4 && (32u / agg_kp) * std::max(max_agg_bits, 1u) > R * stage_bits_for(R)) agg_kp *= 2;
     }
 
+    // scheduling units.  Single-leaf kernel: a tile; general kernel (v2): a tile, dealt in chunks of sched_chunk; warp kernel:
+    // a CHUNK of up to sched_chunk tiles of one pack spread evenly over the pack (tiles j, j + nch, j + 2 nch, …: every chunk
+    // samples all regions of a time-ordered pack, so chunks cost the same whatever part of the pack a range predicate
+    // selects, and a warp changes pack once per chunk) — `tile0` / `ntiles` / `tile_pack` count chunks there
+    uint32_t sched_chunk = use_warp ? 8 : 4;
+    if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, std::min(atoi(e), 64)));
+    if (simple) sched_chunk = 1;
+    if (use_warp)   // small scans: smaller chunks first, so that every warp of the persistent grid gets work
+        while (sched_chunk > 1 && total_rows / (uint64_t(tile_rows) * sched_chunk) < uint64_t(4) * ctx->num_sms * wg.warps) sched_chunk /= 2;
     uint64_t ntiles64 = 0;
     std::vector<uint32_t> tile0(size_t(npacks) + 1);
     for (int p = 0; p < npacks; ++p) {
         tile0[size_t(p)] = uint32_t(ntiles64);
-        ntiles64 += (uint64_t(job.nrows[size_t(p)]) + tile_rows - 1) / tile_rows;
+        const uint64_t tiles = (uint64_t(job.nrows[size_t(p)]) + tile_rows - 1) / tile_rows;
+        ntiles64 += use_warp ? (tiles + sched_chunk - 1) / sched_chunk : tiles;
     }
     if (ntiles64 > 0xfffffff0ull) return fail(ctx, KX_EINVAL, "too many tiles in one scan call");
     const uint32_t ntiles = uint32_t(ntiles64);
@@ -971,13 +1060,11 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // ---- launch geometry: persistent grid, static contiguous tile ranges
     // single-leaf kernel: contiguous tile range per CTA; general kernel: chunks of sched_chunk tiles dealt round-robin
     // (KX_SCHED_CHUNK), one tile per chunk when there are few tiles
-    uint32_t sched_chunk = 4;
-    if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, atoi(e)));
     const uint64_t max_grid = uint64_t(ctx->num_sms) * geo.ctas;
-    if (simple) sched_chunk = 1;
-    int grid = int(std::min<uint64_t>(ntiles, max_grid));
+    int grid = int(std::min<uint64_t>(use_warp ? (uint64_t(ntiles) + wg.warps - 1) / std::max(wg.warps, 1u) : ntiles, max_grid));
     if (grid < 1) grid = 1;
-    const uint32_t sched_rounds = uint32_t(uint64_t(ntiles) / (uint64_t(grid) * sched_chunk));   // full rounds of chunks; the rest goes tile by tile
+    // full rounds of chunks (dealt to CTAs, or to the warps of the grid); the rest goes tile by tile
+    const uint32_t sched_rounds = use_warp ? 0u : uint32_t(uint64_t(ntiles) / (uint64_t(grid) * sched_chunk));
     if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
     CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
@@ -1023,6 +1110,13 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.sched_rounds = sched_rounds;
     P.prod_sleep = getenv("KX_PROD_SLEEP") ? uint32_t(atoi(getenv("KX_PROD_SLEEP"))) : 0u;
     P.agg_dense_thr = agg_dense_thr;
+    if (use_warp) {
+        P.w_wd = wg.wd; P.w_warps = wg.warps; P.w_warp_bytes = wg.warp_bytes; P.w_stage_off = wg.stage_off; P.w_ncols = wg.ncols;
+        std::memcpy(P.w_slot, wg.slot, sizeof(P.w_slot));
+        std::memcpy(P.w_slot_off, wg.slot_off, sizeof(P.w_slot_off));
+        std::memcpy(P.w_col_off, wg.col_off, sizeof(P.w_col_off));
+        std::memcpy(P.w_fix_off, wg.fix_off, sizeof(P.w_fix_off));
+    }
     P.bitsets = dev_bits ? static_cast<uint8_t*>(ctx->d_bitsets.p) : nullptr;
     P.counts = static_cast<unsigned long long*>(ctx->d_counts.p);
     P.partials = static_cast<AggPartial*>(ctx->d_partials.p);
@@ -1038,7 +1132,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (uniform && P.tiles_per_pack == 0) P.tiles_per_pack = 1;   // all packs empty
 
     LaunchArgs A;
-    A.P = P; A.grid = grid; A.smem_bytes = smem_bytes; A.simple = simple; A.only32 = only32; A.ctas = geo.ctas;
+    A.P = P; A.grid = grid; A.smem_bytes = smem_bytes; A.simple = simple; A.only32 = only32; A.ctas = geo.ctas; A.warp = use_warp;
     A.npacks = npacks; A.naggs = naggs; A.ntiles = ntiles; A.total_rows = total_rows;
     A.hd = hd; A.dd = dd; A.desc_bytes = desc_bytes;
     A.leafbits_bytes = leafbits_bytes; A.code_words = code_words;

@@ -80,93 +80,6 @@ struct TileSched {
     }
 };
 
-template <bool F64>
-__device__ __forceinline__ void acc_raw64(AggAcc& A, uint64_t raw, uint64_t base, uint64_t flip) {
-    if (F64) {
-        double x = as_f64(raw), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
-        double t = sum + x;
-        err += (fabs(sum) >= fabs(x)) ? ((sum - t) + x) : ((x - t) + sum);
-        A.s[0] = as_u64(t); A.s[1] = as_u64(err);
-        if (x < as_f64(A.s[2])) A.s[2] = raw;
-        if (x > as_f64(A.s[3])) A.s[3] = raw;
-    } else {
-        uint64_t v = raw + base, k = v ^ flip;
-        A.s[0] += v;
-        if (k < A.s[1]) A.s[1] = k;
-        if (k > A.s[2]) A.s[2] = k;
-    }
-}
-
-// the rows of one reduce chunk this lane owns, as a bit mask rotated by `rot`: bit s ↔ row (s + rot) mod G of the lane's
-// G-row range
-__device__ __forceinline__ uint32_t lane_rows(uint32_t word, uint32_t sub, uint32_t G, uint32_t rot) {
-    if (G == 32u) return __funnelshift_r(word, word, rot);
-    const uint32_t m = (1u << G) - 1u, bits = (word >> (sub * G)) & m;
-    return ((bits >> rot) | (bits << (G - rot))) & m;
-}
-
-// raw 64-bit value column, staged chunk in shared memory: positional walk (all lanes at the same step: conflict free)
-template <bool F64>
-__device__ __forceinline__ void reduce_staged_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, uint32_t r, uint32_t G, uint32_t rot,
-                                                    uint64_t base, uint64_t flip) {
-    __builtin_assume(__isShared(vp));
-    if (!__any_sync(0xffffffffu, r != 0u)) return;
-#pragma unroll 4
-    for (uint32_t s = 0; s < G; ++s) {
-        if ((r >> s) & 1u) acc_raw64<F64>(A, vp[(s + rot) & (G - 1u)], base, flip);
-    }
-}
-
-// raw 64-bit value column read on demand from global memory: only matching rows, four loads in flight per lane
-template <bool F64>
-__device__ __forceinline__ void reduce_global_raw64(AggAcc& A, const unsigned long long* __restrict__ gp, uint32_t r, uint32_t G, uint32_t rot,
-                                                    uint64_t base, uint64_t flip) {
-    while (r) {
-        uint64_t val[4];
-        bool ok[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            ok[u] = r != 0u;
-            const uint32_t s = ok[u] ? (uint32_t)__ffs((int)r) - 1u : 0u;
-            r &= r - 1u;
-            val[u] = ok[u] ? __ldg(gp + ((s + rot) & (G - 1u))) : 0ull;
-        }
-#pragma unroll
-        for (int u = 0; u < 4; ++u)
-            if (ok[u]) acc_raw64<F64>(A, val[u], base, flip);
-    }
-}
-
-// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types, ALP): decode per row.
-// row0 = pack row of the lane's range, srow0 = the same row relative to the staged slice (`staged` may be nullptr)
-__device__ __forceinline__ void reduce_generic(AggAcc& A, const ColView& v, int type, uint32_t row0, const uint32_t* staged, uint32_t srow0, uint32_t r,
-                                               uint32_t G, uint32_t rot) {
-    while (r) {
-        const uint32_t s = (uint32_t)__ffs((int)r) - 1u;
-        r &= r - 1u;
-        const uint32_t b = (s + rot) & (G - 1u);
-        agg_add(A, type, decode_value(v, row0 + b, staged, srow0 + b));
-    }
-}
-
-// r ⊕= p for two partial aggregates (p follows r in CTA order); invalid partials (no match) are neutral
-__device__ __forceinline__ void partial_merge(AggPartial& r, const AggPartial& p, int type) {
-    if (!p.valid) return;
-    if (!r.valid) { r = p; return; }
-    r.count += p.count;
-    if (type == 9 || type == 10) {
-        double s = as_f64(r.sum), e = r.err;
-        fsum_merge(s, e, as_f64(p.sum), p.err);
-        r.sum = as_u64(s); r.err = e;
-        if (as_f64(p.mn) < as_f64(r.mn)) r.mn = p.mn;
-        if (as_f64(p.mx) > as_f64(r.mx)) r.mx = p.mx;
-    } else {
-        r.sum += p.sum;
-        if (p.mn < r.mn) r.mn = p.mn;
-        if (p.mx > r.mx) r.mx = p.mx;
-    }
-}
-
 }  // namespace
 
 // NA = value columns reduced by this instantiation (0: filter only; the NA = 4 instantiation also serves 3)

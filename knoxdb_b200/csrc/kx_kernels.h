@@ -101,6 +101,7 @@ struct BucketParams {
 cudaError_t launch_bucket(const BucketParams& P, int num_sms, cudaStream_t stream);
 
 constexpr size_t SCAN_MAX_DYN_SMEM = 200 * 1024;   // dynamic shared memory the scan kernel may ask for
+constexpr size_t WARP_MAX_DYN_SMEM = 224 * 1024;   // … and the warp-autonomous kernel (one CTA per SM)
 
 // pruning over a device-resident statistics index (kx_stats): statistics are column-major [field][pack]
 struct PruneStatsParams {
@@ -127,6 +128,7 @@ cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, u
 // single-leaf scans without aggregates (kx_scan.cu) / everything else (kx_general.cu)
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
 cudaError_t launch_scan_general(const ScanParams& P, int grid, size_t smem_bytes, int ctas_per_sm, cudaStream_t stream);
+cudaError_t launch_scan_warp(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream);   // kx_warp.cu: one CTA per SM
 cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_codeset(const CodesetJob* jobs, uint32_t njobs, uint32_t max_set, const uint64_t* set_vals, uint32_t* out, cudaStream_t stream);

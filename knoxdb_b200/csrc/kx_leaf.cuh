@@ -313,10 +313,11 @@ __device__ __forceinline__ uint32_t leaf_float(const uint32_t* __restrict__ sw, 
 // copy the current pack's bitmap (<= 8 KB) into shared memory and each lane tests the 32 codes of its own
 // group.  The bitmap covers every code a W-bit field can produce (the host sizes and zeroes it), so there
 // is no bounds check; bits are shifted in row by row.
-template <int W>
+// GBM: the bitmap is read from global memory (L1-resident: <= 8 KB per pack and leaf) instead of a shared-memory copy
+template <int W, bool GBM>
 __device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg, uint32_t code_base, const uint32_t* __restrict__ bm) {
     __builtin_assume(__isShared(seg));
-    __builtin_assume(__isShared(bm));   // the pack's code bitmap is cached in shared memory (one LDS per row)
+    if constexpr (!GBM) __builtin_assume(__isShared(bm));   // the pack's code bitmap is cached in shared memory (one LDS per row)
     uint32_t x[W + 1];
     if constexpr (W % 4 == 0) {
 #pragma unroll
@@ -341,15 +342,16 @@ __device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg
         const int bit = j * W, wi = bit >> 5, sh = bit & 31;
         uint32_t f = (sh + W <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
         uint32_t code = (f & ((1u << W) - 1u)) + code_base;
-        uint32_t wv = bm[code >> 5];
+        uint32_t wv = GBM ? __ldg(bm + (code >> 5)) : bm[code >> 5];
         word = __funnelshift_r(word, __funnelshift_r(wv, 0u, code), 1);   // shift bit (code & 31) of wv in from the top
     }
     return word;   // after 32 steps row j sits at bit j
 }
 
+template <bool GBM>
 static __device__ __noinline__ uint32_t leaf_code32_dispatch(const uint32_t* __restrict__ seg, uint32_t w, uint32_t code_base, const uint32_t* __restrict__ bm) {
     switch (w) {
-#define KX_CASE(W) case W: return leaf_code32<W>(seg, code_base, bm);
+#define KX_CASE(W) case W: return leaf_code32<W, GBM>(seg, code_base, bm);
         KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
         KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
 #undef KX_CASE
@@ -357,10 +359,11 @@ static __device__ __noinline__ uint32_t leaf_code32_dispatch(const uint32_t* __r
     return 0;
 }
 
+template <bool GBM>
 __device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  uint32_t code_base, const uint32_t* __restrict__ bm) {
     if (lane >= Rp) return 0;
-    return leaf_code32_dispatch(sw + (size_t)(g0 + lane) * w, w, code_base, bm);   // dictionary codes are uint16: w <= 16
+    return leaf_code32_dispatch<GBM>(sw + (size_t)(g0 + lane) * w, w, code_base, bm);   // dictionary codes are uint16: w <= 16
 }
 
 // ---- IN / NOT IN on a bit-packed / raw integer block (int_bitpack.go:249-291, int_raw.go:339-380).
@@ -489,6 +492,8 @@ struct LeafEnv {
 // One leaf (index `li` of the program) for one pass of 32 groups: sw = the leaf's staged stream (or nullptr), g0 = first
 // group of the pass within the tile, wr = first pack row of this lane's word.  `keep`: rows (bits of this lane's word)
 // whose result matters — the other operand of an enclosing AND / OR.  Returns the word with the leaf's `neg` applied.
+// GBM: dictionary-code bitmaps are read in place (global memory) instead of from the CTA's shared-memory copy.
+template <bool GBM = false>
 __device__ __forceinline__ uint32_t eval_leaf(const LeafEnv& E, const PackLeaf& lf, uint32_t li, const uint32_t* sw, uint32_t g0, uint32_t Rp,
                                               uint32_t lane, uint64_t wr, uint32_t keep) {
     const ScanParams& P = E.P;
@@ -512,7 +517,7 @@ __device__ __forceinline__ uint32_t eval_leaf(const LeafEnv& E, const PackLeaf& 
     }
     case LM_BITS: __builtin_assume(__isShared(sw)); word = lane < Rp ? sw[g0 + lane] : 0u; break;   // precomputed leaf bitset (pre-pass kernels, row masks)
     case LM_CODESET:
-        word = leaf_codeset(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, E.code_smem + P.code_smem_off[li]);
+        word = leaf_codeset<GBM>(sw, lf.width, g0, Rp, lane, (uint32_t)lf.wm, GBM ? P.code_bits + lf.a : E.code_smem + P.code_smem_off[li]);
         break;
     case LM_HASHSET: {   // a = For of the block, fop = its element type
         const uint32_t to = P.hs_tab_smem_off[li];
@@ -529,6 +534,148 @@ __device__ __forceinline__ uint32_t eval_leaf(const LeafEnv& E, const PackLeaf& 
     }
     }
     return lf.neg ? ~word : word;
+}
+
+// ------------------------------------------------------------------------------ one leaf, all words of a warp's tile
+// (warp-autonomous kernel, kx_warp.cu).  A tile is wd x 1024 rows; word j of lane l covers rows [32 (32 j + l), + 32).
+// The loop over the words sits INSIDE the per-width / per-kind code, so the leaf is dispatched once per tile, its
+// loop-invariant operands are prepared once, and the unrolled row code of one width runs wd times back to back.
+struct WordsIO {
+    uint32_t* dst;          // lane-private column (+ 32 words per step) the results go to
+    const uint32_t* opnd;   // lane-private column of the other operand of the enclosing AND / OR (nullptr: none)
+    uint32_t keep_inv;      // 0: rows whose operand bit is 1 matter (AND); ~0: rows whose operand bit is 0 (OR)
+    uint32_t comb;          // 0: dst = word (0 when the whole word was skipped), 1: dst = opnd & word, 2: dst = opnd | word
+    uint32_t flip;          // XORed onto the leaf's word (NE / GT / NIN … and the float-level NOT)
+    uint32_t wd;
+};
+
+template <class F>
+__device__ __forceinline__ void words_loop(const WordsIO& io, F f) {
+#pragma unroll 1
+    for (uint32_t j = 0; j < io.wd; ++j) {
+        const uint32_t opnd = io.opnd ? io.opnd[j * 32u] : 0u;
+        const uint32_t keep = io.opnd ? (opnd ^ io.keep_inv) : 0xffffffffu;
+        if (__any_sync(0xffffffffu, keep != 0u)) {   // MatchAnd / MatchOr early-out per warp and word
+            const uint32_t word = f(j, keep) ^ io.flip;
+            io.dst[j * 32u] = io.comb == 0u ? word : (io.comb == 1u ? (opnd & word) : (opnd | word));
+        } else if (io.comb == 0u) {
+            io.dst[j * 32u] = 0u;
+        }
+    }
+}
+
+template <bool SUB>
+static __device__ __noinline__ void leaf_b32_words(const uint32_t* __restrict__ seg0, uint32_t lane, uint32_t w, uint32_t a_top, uint32_t lim, WordsIO io) {
+    switch (w) {
+#define KX_CASE(W) case W: words_loop(io, [&](uint32_t j, uint32_t) { return leaf_b32<W, SUB>(seg0 + j * (32u * W), lane, a_top, lim); }); break;
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+        KX_CASE(17) KX_CASE(18) KX_CASE(19) KX_CASE(20) KX_CASE(21) KX_CASE(22) KX_CASE(23) KX_CASE(24)
+        KX_CASE(25) KX_CASE(26) KX_CASE(27) KX_CASE(28) KX_CASE(29) KX_CASE(30) KX_CASE(31) KX_CASE(32)
+#undef KX_CASE
+    }
+}
+
+template <bool SUB>
+static __device__ __noinline__ void leaf_b64_words(const uint32_t* __restrict__ seg0, uint32_t w, uint64_t a_top, uint64_t lim, WordsIO io) {
+    switch (w) {
+#define KX_CASE(W) case W: words_loop(io, [&](uint32_t j, uint32_t) { return leaf_b64<W, SUB>(seg0 + j * (32u * W), a_top, lim); }); break;
+        KX_CASE(33) KX_CASE(34) KX_CASE(35) KX_CASE(36) KX_CASE(37) KX_CASE(38) KX_CASE(39) KX_CASE(40)
+        KX_CASE(41) KX_CASE(42) KX_CASE(43) KX_CASE(44) KX_CASE(45) KX_CASE(46) KX_CASE(47) KX_CASE(48)
+        KX_CASE(49) KX_CASE(50) KX_CASE(51) KX_CASE(52) KX_CASE(53) KX_CASE(54) KX_CASE(55) KX_CASE(56)
+        KX_CASE(57) KX_CASE(58) KX_CASE(59) KX_CASE(60) KX_CASE(61) KX_CASE(62) KX_CASE(63)
+#undef KX_CASE
+    }
+}
+
+template <bool GBM>
+static __device__ __noinline__ void leaf_code32_words(const uint32_t* __restrict__ seg0, uint32_t w, uint32_t code_base, const uint32_t* __restrict__ bm, WordsIO io) {
+    switch (w) {
+#define KX_CASE(W) case W: words_loop(io, [&](uint32_t j, uint32_t) { return leaf_code32<W, GBM>(seg0 + j * (32u * W), code_base, bm); }); break;
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+#undef KX_CASE
+    }
+}
+
+// sw = the leaf's staged slice of the tile (or nullptr), wr0 = first pack row of this lane's word 0; io.flip carries the
+// inversions the caller wants on top of the leaf's own `neg`
+template <bool GBM>
+__device__ __forceinline__ void eval_leaf_words(const LeafEnv& E, const PackLeaf& lf, uint32_t li, const uint32_t* sw, uint32_t lane, uint32_t wr0, WordsIO io) {
+    const ScanParams& P = E.P;
+    if (lf.neg) io.flip = ~io.flip;
+    const uint32_t w = lf.width;
+    switch (lf.mode) {
+    case LM_NONE: words_loop(io, [](uint32_t, uint32_t) { return 0u; }); break;
+    case LM_ALL: words_loop(io, [](uint32_t, uint32_t) { return 0xffffffffu; }); break;
+    case LM_RANGE32: {
+        const uint32_t k = 32u - w, a = (uint32_t)lf.a, d = (uint32_t)lf.d;
+        const uint32_t a_top = a << k, lim = (d << k) | ((1u << k) - 1u);   // k == 0: a, d
+        const uint32_t* seg0 = sw + (size_t)lane * w;
+        if (a) leaf_b32_words<true>(seg0, lane, w, a_top, lim, io);
+        else leaf_b32_words<false>(seg0, lane, w, 0u, lim, io);
+        break;
+    }
+    case LM_RANGE64: {
+        if (w > 32u && w < 64u) {
+            const uint32_t k = 64u - w;
+            const uint64_t a_top = lf.a << k, lim = (lf.d << k) | ((1ull << k) - 1ull);
+            const uint32_t* seg0 = sw + (size_t)lane * w;
+            if (lf.a) leaf_b64_words<true>(seg0, w, a_top, lim, io);
+            else leaf_b64_words<false>(seg0, w, 0ull, lim, io);
+        } else {
+            const uint64_t a = lf.a, d = lf.d, wm = lf.wm;
+            words_loop(io, [&](uint32_t j, uint32_t) { return leaf_range64(sw, w, j * 32u, 32u, lane, a, d, wm); });
+        }
+        break;
+    }
+    case LM_FLOAT: {
+        const uint32_t fop = lf.fop;
+        const uint64_t a = lf.a, d = lf.d;
+        words_loop(io, [&](uint32_t j, uint32_t) { return leaf_float(sw, w, j * 32u, 32u, lane, fop, a, d); });
+        break;
+    }
+    case LM_ROWRANGE: {
+        // rows [a, a+d] of the pack → bits of this lane's words
+        const uint64_t lo = lf.a, hi = lf.a + lf.d;
+        words_loop(io, [&](uint32_t j, uint32_t) {
+            const uint64_t wr = (uint64_t)wr0 + j * 1024u;
+            uint32_t word = 0;
+            if (hi >= wr && lo < wr + 32u) {
+                const uint32_t b0 = lo > wr ? (uint32_t)(lo - wr) : 0u;
+                const uint32_t b1 = hi < wr + 31u ? (uint32_t)(hi - wr) : 31u;
+                word = (0xffffffffu >> (31u - b1)) & (0xffffffffu << b0);
+            }
+            return word;
+        });
+        break;
+    }
+    case LM_BITS: {   // precomputed leaf bitset (pre-pass kernels, row masks)
+        __builtin_assume(__isShared(sw));
+        words_loop(io, [&](uint32_t j, uint32_t) { return sw[j * 32u + lane]; });
+        break;
+    }
+    case LM_CODESET:
+        leaf_code32_words<GBM>(sw + (size_t)lane * w, w, (uint32_t)lf.wm, GBM ? P.code_bits + lf.a : E.code_smem + P.code_smem_off[li], io);
+        break;
+    case LM_HASHSET: {   // a = For of the block, fop = its element type
+        const uint32_t to = P.hs_tab_smem_off[li];
+        const ulonglong2* tab = to != 0xffffffffu ? reinterpret_cast<const ulonglong2*>(E.code_smem + to)
+                                                  : reinterpret_cast<const ulonglong2*>(P.set_tabs + P.tab_off[li]);
+        const uint32_t* pre = E.code_smem + P.hs_smem_off[li];
+        const uint32_t pre_log2 = P.pre_log2[li], tab_log2 = P.tab_log2[li];
+        const int type = lf.fop;
+        const uint64_t base = lf.a;
+        words_loop(io, [&](uint32_t j, uint32_t keep) { return leaf_hashset(sw, w, type, base, j * 32u, 32u, lane, pre, pre_log2, tab, tab_log2, keep); });
+        break;
+    }
+    default: {
+        const ColView& v = P.views[lf.view];
+        if (v.kind == CK_RUNEND) words_loop(io, [&](uint32_t j, uint32_t) { return leaf_runend(lf, v, wr0 + j * 1024u, E.nrows, true, P.set_vals); });
+        else words_loop(io, [&](uint32_t j, uint32_t) { return leaf_generic(lf, v, lf.data ? sw : nullptr, E.pack_row0, j * 32u, 32u, lane, E.nrows, P.set_vals); });
+        break;
+    }
+    }
 }
 
 // ------------------------------------------------------------------------------ aggregates
@@ -587,5 +734,94 @@ __device__ __forceinline__ void agg_merge(AggAcc& A, const AggAcc& B, int type) 
         if (B.s[2] > A.s[2]) A.s[2] = B.s[2];
     }
 }
+
+// ------------------------------------------------------------------------------ reduce helpers shared by the fused kernels
+template <bool F64>
+__device__ __forceinline__ void acc_raw64(AggAcc& A, uint64_t raw, uint64_t base, uint64_t flip) {
+    if (F64) {
+        double x = as_f64(raw), sum = as_f64(A.s[0]), err = as_f64(A.s[1]);
+        double t = sum + x;
+        err += (fabs(sum) >= fabs(x)) ? ((sum - t) + x) : ((x - t) + sum);
+        A.s[0] = as_u64(t); A.s[1] = as_u64(err);
+        if (x < as_f64(A.s[2])) A.s[2] = raw;
+        if (x > as_f64(A.s[3])) A.s[3] = raw;
+    } else {
+        uint64_t v = raw + base, k = v ^ flip;
+        A.s[0] += v;
+        if (k < A.s[1]) A.s[1] = k;
+        if (k > A.s[2]) A.s[2] = k;
+    }
+}
+
+// the rows of one reduce chunk this lane owns, as a bit mask rotated by `rot`: bit s ↔ row (s + rot) mod G of the lane's
+// G-row range
+__device__ __forceinline__ uint32_t lane_rows(uint32_t word, uint32_t sub, uint32_t G, uint32_t rot) {
+    if (G == 32u) return __funnelshift_r(word, word, rot);
+    const uint32_t m = (1u << G) - 1u, bits = (word >> (sub * G)) & m;
+    return ((bits >> rot) | (bits << (G - rot))) & m;
+}
+
+// raw 64-bit value column, staged chunk in shared memory: positional walk (all lanes at the same step: conflict free)
+template <bool F64>
+__device__ __forceinline__ void reduce_staged_raw64(AggAcc& A, const unsigned long long* __restrict__ vp, uint32_t r, uint32_t G, uint32_t rot,
+                                                    uint64_t base, uint64_t flip) {
+    __builtin_assume(__isShared(vp));
+    if (!__any_sync(0xffffffffu, r != 0u)) return;
+#pragma unroll 4
+    for (uint32_t s = 0; s < G; ++s) {
+        if ((r >> s) & 1u) acc_raw64<F64>(A, vp[(s + rot) & (G - 1u)], base, flip);
+    }
+}
+
+// raw 64-bit value column read on demand from global memory: only matching rows, four loads in flight per lane
+template <bool F64>
+__device__ __forceinline__ void reduce_global_raw64(AggAcc& A, const unsigned long long* __restrict__ gp, uint32_t r, uint32_t G, uint32_t rot,
+                                                    uint64_t base, uint64_t flip) {
+    while (r) {
+        uint64_t val[4];
+        bool ok[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            ok[u] = r != 0u;
+            const uint32_t s = ok[u] ? (uint32_t)__ffs((int)r) - 1u : 0u;
+            r &= r - 1u;
+            val[u] = ok[u] ? __ldg(gp + ((s + rot) & (G - 1u))) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (ok[u]) acc_raw64<F64>(A, val[u], base, flip);
+    }
+}
+
+// any other value column layout (bit-packed, dictionary, affine, run-end, narrow types, ALP): decode per row.
+// row0 = pack row of the lane's range, srow0 = the same row relative to the staged slice (`staged` may be nullptr)
+__device__ __forceinline__ void reduce_generic(AggAcc& A, const ColView& v, int type, uint32_t row0, const uint32_t* staged, uint32_t srow0, uint32_t r,
+                                               uint32_t G, uint32_t rot) {
+    while (r) {
+        const uint32_t s = (uint32_t)__ffs((int)r) - 1u;
+        r &= r - 1u;
+        const uint32_t b = (s + rot) & (G - 1u);
+        agg_add(A, type, decode_value(v, row0 + b, staged, srow0 + b));
+    }
+}
+
+// r ⊕= p for two partial aggregates (p follows r in CTA order); invalid partials (no match) are neutral
+__device__ __forceinline__ void partial_merge(AggPartial& r, const AggPartial& p, int type) {
+    if (!p.valid) return;
+    if (!r.valid) { r = p; return; }
+    r.count += p.count;
+    if (type == 9 || type == 10) {
+        double s = as_f64(r.sum), e = r.err;
+        fsum_merge(s, e, as_f64(p.sum), p.err);
+        r.sum = as_u64(s); r.err = e;
+        if (as_f64(p.mn) < as_f64(r.mn)) r.mn = p.mn;
+        if (as_f64(p.mx) > as_f64(r.mx)) r.mx = p.mx;
+    } else {
+        r.sum += p.sum;
+        if (p.mn < r.mn) r.mn = p.mn;
+        if (p.mx > r.mx) r.mx = p.mx;
+    }
+}
+
 
 }  // namespace kx

@@ -181,6 +181,17 @@ struct ScanParams {
     // tiles that match densely get the chunks staged through the ring (one slice of 32 / agg_kp groups per warp and stage)
     uint32_t agg_kp;           // >= 1 whenever naggs > 0
     uint32_t agg_dense_thr;    // stage the tile when recent matches * thr > recent rows; 0 = always, 0xffffffff = never
+    // warp-autonomous kernel (kx_warp.cu): every warp runs its own TMA ring over tiles of 1024 w_wd rows; a ring stage holds
+    // one slot per staged column of the program (leaf streams in postfix order, ALP patch-correction streams behind their leaf)
+    uint32_t w_wd;             // bitset words per lane and tile (1, 2 or 4)
+    uint32_t w_warps;          // warps of a CTA that take tiles
+    uint32_t w_warp_bytes;     // shared memory of one warp (barriers, tile queue, match words, stack, descriptors, ring)
+    uint32_t w_stage_off;      // first ring stage inside a warp's area (bytes)
+    uint32_t w_ncols;          // slots per stage (>= 1; lane i of the warp issues the copy of slot i)
+    uint8_t  w_slot[32];       // slot -> leaf index, | 0x80: the leaf's fix stream; 0xff: nothing to copy
+    uint16_t w_slot_off[32];   // slot -> offset inside a stage, in 16-byte units
+    uint16_t w_col_off[MAX_SCAN_LEAVES];   // leaf -> offset of its stream inside a stage (16-byte units)
+    uint16_t w_fix_off[MAX_SCAN_LEAVES];   // leaf -> offset of its fix stream
 };
 
 // can the value column be streamed through the ring (bit stream of fixed width per row)?

@@ -25,7 +25,7 @@ import oracle as ko                 # noqa: E402  (encoder of the synthetic bloc
 from sweep_configs import raw_block   # noqa: E402
 
 M1 = 1 << 20
-KNOBS = ("KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES")
+KNOBS = ("KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES", "KX_GENERAL", "KX_WARP_GEOMETRY")
 
 
 def main():
@@ -34,6 +34,8 @@ def main():
     ap.add_argument("--cases", default="dict64,hash64,ts0.1,ts10,ts50,ts90,ts90f")
     ap.add_argument("--npacks", type=int, default=256)
     ap.add_argument("--quick", action="store_true")
+    ap.add_argument("--minimal", action="store_true", help="default, dense-prefetch modes and the v2 kernel only")
+    ap.add_argument("--v2", action="store_true", help="sweep the older producer/consumer kernel (KX_GENERAL=v2) instead of the warp kernel")
     args = ap.parse_args()
     rng = np.random.default_rng(1)
     ctx = kb.Context(0)
@@ -94,8 +96,18 @@ def main():
         base_ms, base_sig = run(prog, aggs)
         print(f"{name:8s} default                                  {base_ms:8.4f} ms  {npacks * M1 / base_ms / 1e6:8.1f} Grows/s", flush=True)
         results.append({"case": name, "knobs": {}, "kernel_ms": base_ms})
-        combos = [{"KX_SCAN_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(geos, chunks)]
-        combos += [{"KX_PROD_SLEEP": "1"}, {"KX_AGG_STAGE": "never"}, {"KX_AGG_STAGE": "always"}, {"KX_AGG_STAGE": "2"}, {"KX_AGG_STAGE": "5"}]
+        if args.v2:
+            combos = [{"KX_GENERAL": "v2", "KX_SCAN_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(geos, chunks)]
+            combos += [{"KX_GENERAL": "v2", "KX_PROD_SLEEP": "1"}] + [{"KX_GENERAL": "v2", "KX_AGG_STAGE": a} for a in ("never", "always", "2", "5")]
+        else:
+            wgeos = [None, "1,2,16", "1,3,16", "1,4,16", "2,2,16", "2,3,16", "2,2,12", "2,3,12", "4,2,16", "4,2,8", "2,2,8"]
+            wchunks = ["1", "2", "4", "8", "16"]
+            if args.quick:
+                wgeos, wchunks = [None, "1,2,16", "2,2,16", "2,3,12", "4,2,8"], ["4", "8", "16"]
+            combos = [{"KX_WARP_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(wgeos, wchunks)]
+            combos += [{"KX_AGG_STAGE": a} for a in ("never", "always", "2", "5", "8")] + [{"KX_PROD_SLEEP": "1"}, {"KX_PROD_SLEEP": "2"}, {"KX_GENERAL": "v2"}]
+            if args.minimal:
+                combos = [{"KX_PROD_SLEEP": "1"}, {"KX_AGG_STAGE": "2"}, {"KX_AGG_STAGE": "5"}, {"KX_GENERAL": "v2"}]
         for combo in combos:
             for k in KNOBS:
                 os.environ.pop(k, None)
