@@ -3,7 +3,8 @@
 Every source is compiled to its own object (in parallel; unchanged sources are not recompiled) and the objects are
 linked into the shared library.  `ptxas -v` of every CUDA source is parsed per file: registers, stack frame and spill
 bytes of each kernel land in build_info.json, and the build FAILS when a single-leaf scan kernel spills at all or the
-general scan kernel spills more than a few registers (a spill in these persistent kernels slows every path of them)."""
+warp-autonomous scan kernel spills more than a few registers (a spill in these persistent kernels slows every path of
+them)."""
 import concurrent.futures
 import json
 import os
@@ -15,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 OUT = os.path.join(HERE, "libknoxgpu.so")
-SOURCES = ["kx_scan.cu", "kx_general.cu", "kx_warp.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_comm.cu", "kx_api.cu", "kx_host.cpp"]
+SOURCES = ["kx_scan.cu", "kx_warp.cu", "kx_bucket.cu", "kx_string.cu", "kx_stats.cu", "kx_comm.cu", "kx_api.cu", "kx_host.cpp"]
 HEADERS = ["kx_types.h", "kx_kernels.h", "kx_host.h", "kx_xxh3.h", "kx_decode.cuh", "kx_leaf.cuh", "kx_comm.h", os.path.join("..", "..", "include", "knoxgpu.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-Wall,-Wextra,-Wno-unused-parameter,-ffp-contract=off"]
@@ -96,7 +97,7 @@ def build(force=False, verbose=False):
         spill = max(v.get("spill_stores", 0), v.get("spill_loads", 0))
         if "scan_kernel" in k and "exclusive" not in k and spill:
             bad.append(k)
-        if "scan_general_kernel" in k and spill > (2 * GENERAL_SPILL_LIMIT if "ILi4ELi1E" in k else GENERAL_SPILL_LIMIT):   # (3-4 value columns: cold instantiation)
+        if "scan_warp_kernel" in k and spill > GENERAL_SPILL_LIMIT:
             bad.append(k)
     if bad:
         os.remove(OUT)

@@ -301,6 +301,34 @@ int upload_block(kx_ctx* ctx, const BlockLayout& lay, StoredBlock& sb) {
     };
     int rc;
     const ColView& v = lay.view;
+    if (lay.s8b) {
+        // Simple8b: codewords → device scratch, selector counts + widest value, exclusive scan, then the fixed-width stream
+        const uint32_t nwords = uint32_t(lay.stream_len / 8);
+        const size_t off_counts = round_up(lay.stream_len, 256), off_meta = off_counts + round_up(size_t(nwords) * 4 + 4, 256);
+        CK(ctx->d_tmp2.reserve(off_meta + 64));
+        uint8_t* scratch = static_cast<uint8_t*>(ctx->d_tmp2.p);
+        if (nwords) CK(cudaMemcpyAsync(scratch, lay.stream, lay.stream_len, cudaMemcpyHostToDevice, ctx->stream));
+        uint32_t* counts = reinterpret_cast<uint32_t*>(scratch + off_counts);
+        unsigned long long* total = reinterpret_cast<unsigned long long*>(scratch + off_meta);
+        uint32_t* maxbits = reinterpret_cast<uint32_t*>(scratch + off_meta + 8);
+        CK(launch_s8b_count(scratch, nwords, counts, maxbits, total, ctx->stream));
+        struct { unsigned long long total; uint32_t maxbits, pad; } meta{};
+        CK(cudaMemcpyAsync(&meta, total, sizeof(meta), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (meta.total < v.n) return fail(ctx, KX_EFORMAT, "kx_block_put: simple8b: short stream");
+        sb.view.width = uint8_t(meta.maxbits);
+        sb.view.kind = meta.maxbits ? CK_BITS : CK_CONST;
+        if (meta.maxbits) {
+            const size_t bytes = round_up((size_t(v.n) * meta.maxbits + 7) / 8, 8);
+            uint8_t* d = nullptr; SlabAlloc rec;
+            if ((rc = slab_alloc(ctx, bytes + STREAM_PAD, &d, &rec))) return rc;
+            sb.allocs.push_back(rec);
+            CK(cudaMemsetAsync(d, 0, bytes + STREAM_PAD, ctx->stream));
+            CK(launch_s8b_pack(scratch, nwords, counts, v.n, meta.maxbits, d, ctx->stream));
+            sb.view.data = d;
+        }
+        return KX_OK;
+    }
     if (v.kind == CK_BITS || v.kind == CK_DICT || ((v.kind == CK_ALP || v.kind == CK_ALPRD) && v.width)) {
         const void* src = lay.owned.empty() ? (const void*)lay.stream : (const void*)lay.owned.data();
         size_t len = lay.owned.empty() ? lay.stream_len : lay.owned.size();
@@ -434,7 +462,7 @@ struct WarpGeo {
 // everything the launch + result phase of a scan needs (filled by run_scan, or taken from the plan cache)
 struct LaunchArgs {
     ScanParams P{};
-    int grid = 1; size_t smem_bytes = 0; bool simple = true, only32 = true, warp = false; int ctas = 2;
+    int grid = 1; size_t smem_bytes = 0; bool simple = true, only32 = true; int ctas = 2;
     int npacks = 0, naggs = 0; uint32_t ntiles = 0; uint64_t total_rows = 0;
     const uint8_t* hd = nullptr; uint8_t* dd = nullptr; size_t desc_bytes = 0;   // descriptor block: host staging → device (hd == nullptr: already resident)
     size_t leafbits_bytes = 0; uint32_t code_words = 0;
@@ -486,8 +514,7 @@ int launch_and_collect(kx_ctx* ctx, LaunchArgs& A) {
     }
     if (ntiles) {
         if (A.simple) CK(launch_scan(P, A.grid, A.smem_bytes, A.only32, A.ctas, ctx->stream));
-        else if (A.warp) CK(launch_scan_warp(P, A.grid, A.smem_bytes, ctx->stream));
-        else CK(launch_scan_general(P, A.grid, A.smem_bytes, A.ctas, ctx->stream));
+        else CK(launch_scan_warp(P, A.grid, A.smem_bytes, ctx->stream));
         ctx->last_launches++;
     }
     if (A.sh) { int rc = enqueue_exchange(ctx, uint32_t(npacks), uint32_t(naggs), P.agg_type); if (rc) return rc; }
@@ -549,7 +576,7 @@ struct PlanKey {
 };
 uint64_t env_knobs_hash() {   // the tuning hooks change the plan: they are part of the key
     uint64_t h = 1469598103934665603ull;
-    for (const char* k : {"KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES", "KX_HASH_SMEM_KB", "KX_GENERAL", "KX_WARP_GEOMETRY"}) {
+    for (const char* k : {"KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_AGG_STAGE", "KX_HASH_SMEM_KB", "KX_WARP_GEOMETRY"}) {
         const char* v = getenv(k);
         for (const char* c = v ? v : ""; *c; ++c) h = (h ^ uint8_t(*c)) * 1099511628211ull;
         h = (h ^ 0xff) * 1099511628211ull;
@@ -696,7 +723,6 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     uint32_t max_runs = 0;
     uint32_t max_stage_bits = 0, code_words = 0, max_code_set = 0;
     uint32_t code_leaf_words[MAX_SCAN_LEAVES] = {};   // per leaf: largest code bitmap of any pack (cached in shared memory by the scan)
-    uint32_t max_agg_bits = 0;                   // widest value column that can be staged through the ring
     bool hash_leaf[MAX_SCAN_LEAVES] = {};             // leaf is looked up in its hash set (LM_HASHSET) for some pack
     bool only32 = true;   // every leaf of every pack is a <= 32-bit packed range test (or all / none)
     uint64_t total_rows = 0;
@@ -800,7 +826,6 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         for (int j = 0; j < naggs; ++j) {
             const ColView& av = job.agg_views[size_t(p) * naggs + j];
             if (av.n != job.nrows[size_t(p)]) return fail(ctx, KX_EINVAL, "value block length differs from pack");
-            if (agg_stageable(av)) max_agg_bits = std::max<uint32_t>(max_agg_bits, av.width);
         }
         max_stage_bits = std::max(max_stage_bits, bits);
         total_rows += job.nrows[size_t(p)];
@@ -814,9 +839,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     struct Geo { int ctas, stages; size_t budget; };
     const bool simple = nl == 1 && naggs == 0 && !any_fix;   // patch corrections need the general ring protocol
     const bool simple32 = only32 && simple;
-    // multi-leaf programs and fused reduces run the warp-autonomous kernel (kx_warp.cu); KX_GENERAL=v2 selects the older
-    // producer/consumer kernel (kx_general.cu) for comparison
-    const bool use_warp = !simple && !(getenv("KX_GENERAL") && !strcmp(getenv("KX_GENERAL"), "v2"));
+    // multi-leaf programs, patch corrections and fused reduces run the warp-autonomous kernel (kx_warp.cu)
+    const bool use_warp = !simple;
     // dictionary-code bitmaps cached in shared memory behind the ring (the warp kernel reads them in place)
     uint32_t code_smem_off[MAX_SCAN_LEAVES] = {}, code_smem_words = 0;
     if (!use_warp) for (int l = 0; l < nleaves; ++l) { code_smem_off[l] = code_smem_words; code_smem_words += code_leaf_words[l]; }
@@ -837,18 +861,17 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         if (tab_words * 4u <= hs_tab_limit && (size_t(code_smem_words) + tab_words) * 4u <= 96u * 1024u) { hs_tab_smem_off[l] = code_smem_words; code_smem_words += tab_words; }
     }
     const size_t code_smem_bytes = round_up(size_t(code_smem_words) * 4, 128);
-    // Value columns of the fused reduce can be staged through the ring: the rows of one pass are cut into agg_kp (1, 2 or 4)
-    // chunks, one ring stage each (KX_AGG_STAGE = never | always | <thr>: stage a tile when recent matches * thr > recent
-    // rows).  Measured on B200: reading matching rows on demand wins below ~1/3 selectivity, bulk staging above.
-    uint32_t agg_kp = naggs ? 1 : 0, agg_dense_thr = 3;
-    if (naggs && max_agg_bits) {
+    // fused reduce: a tile whose matches * thr exceed its rows reads the value rows of every lane with 128-bit loads (dense
+    // walk), others read matching rows on demand (KX_AGG_STAGE = never | always | <thr>; tuning hook)
+    uint32_t agg_dense_thr = 3;
+    if (naggs) {
         const char* e = getenv("KX_AGG_STAGE");
         if (e && !strcmp(e, "never")) agg_dense_thr = 0xffffffffu;
         else if (e && !strcmp(e, "always")) agg_dense_thr = 0;
         else if (e && atoi(e) > 0) agg_dense_thr = uint32_t(atoi(e));
     }
-    // pure AND / pure OR programs keep their running match words in registers; other trees (and ALP patch corrections)
-    // use a per-warp AND/OR stack in shared memory
+    // pure AND / pure OR programs combine into one running word per lane; other trees (and ALP patch corrections) use a
+    // per-warp AND/OR stack in shared memory
     uint32_t stack_depth = 0, flat_op = 0;
     if (!simple) {
         bool all_and = true, all_or = true;
@@ -860,19 +883,8 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
         }
     }
     const uint32_t desc_words = uint32_t(nl * (sizeof(PackLeaf) / 4) + 2 * size_t(naggs) * (sizeof(ColView) / 4));
-    auto extra_smem_for = [&](uint32_t r) {   // bytes behind the ring: code bitmaps, stacks, descriptor caches
-        size_t words = simple ? 0 : size_t(CONSUMER_WARPS) * stack_depth * ((r + 31) / 32) * 32 + size_t(CONSUMER_WARPS) * desc_words;
-        return code_smem_bytes + round_up(words * 4, 128);
-    };
     const size_t stage_fixed = 32;
-    // bits per tile row a ring stage must hold: the widest staged leaf column; a staged value chunk (8 warps x 32 G rows,
-    // G = 32 / agg_kp >= 8 groups) must fit as well
-    auto stage_bits_for = [&](uint32_t r) {
-        uint32_t b = max_stage_bits;
-        if (naggs && max_agg_bits && agg_dense_thr != 0xffffffffu) b = std::max(b, (8u * max_agg_bits + r - 1) / r);
-        return b;
-    };
-    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * stage_bits_for(r) + stage_fixed, 128); };
+    auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
     auto rmax_for = [&](const Geo& g) {
         const size_t fixed = code_smem_bytes / 2 + stage_fixed + 128;
         return g.budget > fixed ? (g.budget - fixed) / (size_t(32) * std::max<uint32_t>(max_stage_bits, 1)) : size_t(0);
@@ -887,36 +899,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             if (rmax < 32) { geo = g1; rmax = rmax_for(geo); }
             R = rmax >= 32 ? uint32_t(std::min<size_t>(rmax / 32 * 32, 256)) : uint32_t(std::max<size_t>(rmax, 1));
         }
-    } else if (use_warp) {
-        // warp-autonomous kernel: chosen below (per-warp rings)
-    } else {
-        // general kernel: one stage = one leaf column (or one value chunk) of a whole tile.  The reduce lags one tile behind
-        // the filter, so a tile keeps several stages busy: prefer the largest tile that leaves `want` stages (KX_MIN_STAGES),
-        // else the largest one with two.  More than two value columns run one CTA per SM (accumulators stay in registers).
-        uint32_t want = 2;
-        if (const char* e = getenv("KX_MIN_STAGES")) want = uint32_t(std::max(2, std::min(atoi(e), MAX_STAGES)));
-        bool found = false;
-        for (uint32_t need : {want, 2u}) {
-            for (int ctas = naggs > 2 ? 1 : 2; ctas >= 1 && !found; --ctas) {
-                for (uint32_t r : {64u, 32u}) {
-                    size_t per_cta = SCAN_MAX_DYN_SMEM / size_t(ctas) - 128;
-                    size_t extra = extra_smem_for(r), sb = stage_bytes_for(r);
-                    if (per_cta < extra + need * sb) continue;
-                    geo.ctas = ctas; R = r;
-                    geo.stages = int(std::min<size_t>(MAX_STAGES, (per_cta - extra) / sb));
-                    found = true;
-                    break;
-                }
-            }
-            if (found) break;
-        }
-        if (!found) return fail(ctx, KX_EUNSUPPORTED, "scan program does not fit the shared memory of one SM");
     }
     if (const char* e = getenv("KX_SCAN_GEOMETRY")) {   // tuning hook: "ctas,stages,R"
         int c = 0, st = 0, r = 0;
         if (sscanf(e, "%d,%d,%d", &c, &st, &r) == 3 && c >= 1 && c <= 3 && st >= 2 && st <= MAX_STAGES && r >= 1 &&
-            (simple ? (r <= 32 || r % 32 == 0) : (r % 32 == 0 && r <= 64 && c <= (naggs > 2 ? 1 : 2))) &&
-            128 + size_t(st) * stage_bytes_for(uint32_t(r)) + extra_smem_for(uint32_t(r)) <= SCAN_MAX_DYN_SMEM / size_t(c)) {
+            simple && (r <= 32 || r % 32 == 0) &&
+            128 + size_t(st) * stage_bytes_for(uint32_t(r)) + code_smem_bytes <= SCAN_MAX_DYN_SMEM / size_t(c)) {
             geo.ctas = c; geo.stages = st; R = uint32_t(r);
         }
     }
@@ -990,17 +978,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     }
     const uint32_t tile_rows = 256 * R;
     const size_t stage_bytes = use_warp ? wg.stage_bytes : stage_bytes_for(R);
-    const size_t smem_bytes = use_warp ? size_t(wg.warps) * wg.warp_bytes + code_smem_bytes : 128 + size_t(geo.stages) * stage_bytes + extra_smem_for(R);
-    if (naggs) {   // chunks per pass of the reduce: as few as fit a stage
-        agg_kp = 1;
-        while (agg_kp < 4 && (32u / agg_kp) * std::max(max_agg_bits, 1u) > R * stage_bits_for(R)) agg_kp *= 2;
-    }
+    const size_t smem_bytes = use_warp ? size_t(wg.warps) * wg.warp_bytes + code_smem_bytes : 128 + size_t(geo.stages) * stage_bytes + code_smem_bytes;
 
-    // scheduling units.  Single-leaf kernel: a tile; general kernel (v2): a tile, dealt in chunks of sched_chunk; warp kernel:
-    // a CHUNK of up to sched_chunk tiles of one pack spread evenly over the pack (tiles j, j + nch, j + 2 nch, …: every chunk
+    // scheduling units.  Single-leaf kernel: a tile (contiguous tile range per CTA); warp kernel: a CHUNK of up to sched_chunk tiles of one pack spread evenly over the pack (tiles j, j + nch, j + 2 nch, …: every chunk
     // samples all regions of a time-ordered pack, so chunks cost the same whatever part of the pack a range predicate
     // selects, and a warp changes pack once per chunk) — `tile0` / `ntiles` / `tile_pack` count chunks there
-    uint32_t sched_chunk = use_warp ? 8 : 4;
+    uint32_t sched_chunk = 8;
     if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, std::min(atoi(e), 64)));
     if (simple) sched_chunk = 1;
     if (use_warp)   // small scans: smaller chunks first, so that every warp of the persistent grid gets work
@@ -1058,13 +1041,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (!vjobs.empty()) std::memcpy(hd + off_vjobs, vjobs.data(), sizeof(ValJob) * vjobs.size());
 
     // ---- launch geometry: persistent grid, static contiguous tile ranges
-    // single-leaf kernel: contiguous tile range per CTA; general kernel: chunks of sched_chunk tiles dealt round-robin
-    // (KX_SCHED_CHUNK), one tile per chunk when there are few tiles
     const uint64_t max_grid = uint64_t(ctx->num_sms) * geo.ctas;
     int grid = int(std::min<uint64_t>(use_warp ? (uint64_t(ntiles) + wg.warps - 1) / std::max(wg.warps, 1u) : ntiles, max_grid));
     if (grid < 1) grid = 1;
-    // full rounds of chunks (dealt to CTAs, or to the warps of the grid); the rest goes tile by tile
-    const uint32_t sched_rounds = use_warp ? 0u : uint32_t(uint64_t(ntiles) / (uint64_t(grid) * sched_chunk));
     if (code_words) CK(ctx->d_codebits.reserve(size_t(code_words) * 4));
 
     CK(ctx->d_counts.reserve(sizeof(unsigned long long) * size_t(npacks)));
@@ -1100,15 +1079,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     std::memcpy(P.code_smem_off, code_smem_off, sizeof(P.code_smem_off));
     P.code_smem_words = code_smem_words;
     P.code_bitmap_words = code_bitmap_words;
-    P.agg_kp = agg_kp;
-    P.stack_off_words = uint32_t(code_smem_bytes / 4);
     P.stack_depth = stack_depth;
-    P.desc_off_words = P.stack_off_words + uint32_t(CONSUMER_WARPS) * stack_depth * (R / 32) * 32;
-    P.desc_words = desc_words;
     P.flat_op = flat_op;
     P.sched_chunk = sched_chunk;
-    P.sched_rounds = sched_rounds;
-    P.prod_sleep = getenv("KX_PROD_SLEEP") ? uint32_t(atoi(getenv("KX_PROD_SLEEP"))) : 0u;
     P.agg_dense_thr = agg_dense_thr;
     if (use_warp) {
         P.w_wd = wg.wd; P.w_warps = wg.warps; P.w_warp_bytes = wg.warp_bytes; P.w_stage_off = wg.stage_off; P.w_ncols = wg.ncols;
@@ -1132,7 +1105,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (uniform && P.tiles_per_pack == 0) P.tiles_per_pack = 1;   // all packs empty
 
     LaunchArgs A;
-    A.P = P; A.grid = grid; A.smem_bytes = smem_bytes; A.simple = simple; A.only32 = only32; A.ctas = geo.ctas; A.warp = use_warp;
+    A.P = P; A.grid = grid; A.smem_bytes = smem_bytes; A.simple = simple; A.only32 = only32; A.ctas = geo.ctas;
     A.npacks = npacks; A.naggs = naggs; A.ntiles = ntiles; A.total_rows = total_rows;
     A.hd = hd; A.dd = dd; A.desc_bytes = desc_bytes;
     A.leafbits_bytes = leafbits_bytes; A.code_words = code_words;
@@ -1358,14 +1331,15 @@ int kx_block_put(kx_ctx* ctx, uint32_t pack, uint32_t version, uint16_t field, u
                                     : normalize_block(block_type, static_cast<const uint8_t*>(enc), len, lay, err);
     if (rc) return fail(ctx, rc, "kx_block_put: " + err);
     BlockKey key{pack, version, field};
+    // the new block is uploaded BEFORE a resident one with the same key is released: a failed put leaves the store as it was
+    StoredBlock sb;
+    rc = block_type == KX_BYTES ? upload_string_block(ctx, slay, sb) : upload_block(ctx, lay, sb);
+    // the caller's buffer may be reused after return (cgo rule): finish the copy
+    if (!rc && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, KX_ECUDA, "kx_block_put: copy failed");
+    if (rc) { free_block(ctx, sb); return rc; }
     ctx->store_epoch++;
     auto it = ctx->store.find(key);
     if (it != ctx->store.end()) { ctx->store_enc_bytes -= it->second.enc_len; free_block(ctx, it->second); ctx->store.erase(it); }
-    StoredBlock sb;
-    rc = block_type == KX_BYTES ? upload_string_block(ctx, slay, sb) : upload_block(ctx, lay, sb);
-    if (rc) { free_block(ctx, sb); return rc; }
-    // the caller's buffer may be reused after return (cgo rule): finish the copy
-    CK(cudaStreamSynchronize(ctx->stream));
     sb.enc_len = len;
     ctx->store_enc_bytes += len;
     if (nrows_out) *nrows_out = sb.view.n;

@@ -437,15 +437,12 @@ int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, 
         return 0;
     }
     case T_S8B: {
-        // legacy scheme (never selected for new data, context.go:275-282): transcode to a
-        // min-FOR bit stream once at registration so the scan kernels see one stream format
-        std::vector<uint64_t> vals;
-        if (!decode_container(*c, vals, err)) return -6;
-        uint64_t mx = 0;
-        for (auto& x : vals) { x = x - c->val; mx = std::max(mx, x); }
-        int w = log2_range(0, mx);
-        v.kind = w == 0 ? CK_CONST : CK_BITS; v.base = c->val; v.width = uint8_t(w); v.is_raw = 0;
-        if (w) pack_stream(vals, w, out.owned);
+        // legacy scheme (never selected for new data, context.go:275-282): transcoded ON THE DEVICE to a min-FOR bit stream
+        // once at registration (s8b_count_kernel / s8b_pack_kernel), so the scan kernels see one stream format
+        if (c->payload_len % 8) { err = "simple8b: stream is not a whole number of words"; return -6; }
+        v.kind = CK_BITS; v.base = c->val; v.width = 0; v.is_raw = 0;
+        out.stream = c->payload; out.stream_len = c->payload_len;
+        out.s8b = true;
         return 0;
     }
     case T_DICT: {

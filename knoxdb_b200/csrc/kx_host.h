@@ -47,6 +47,9 @@ struct BlockLayout {
     std::vector<uint64_t> aux64;        // dict values (CK_DICT) or run values (CK_RUNEND → data)
     std::vector<uint32_t> aux32;        // run ends (CK_RUNEND → aux)
     std::vector<uint8_t> blob;          // CK_ALP patch blob (positions | values | patch bitmap), uploaded as aux
+    // top-level Simple8b block: `stream` holds the 64-bit codewords; the device transcodes them into a fixed-width bit
+    // stream at upload (width and kind of the view are filled in then)
+    bool s8b = false;
 };
 
 // ALP float64 arithmetic of the reference (internal/encode/alp/{constants,encoder,decoder}.go), host side:

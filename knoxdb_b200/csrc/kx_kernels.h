@@ -127,7 +127,6 @@ cudaError_t launch_bloom_build(const uint8_t* values, const uint32_t* offsets, u
 
 // single-leaf scans without aggregates (kx_scan.cu) / everything else (kx_general.cu)
 cudaError_t launch_scan(const ScanParams& P, int grid, size_t smem_bytes, bool only32, int ctas_per_sm, cudaStream_t stream);
-cudaError_t launch_scan_general(const ScanParams& P, int grid, size_t smem_bytes, int ctas_per_sm, cudaStream_t stream);
 cudaError_t launch_scan_warp(const ScanParams& P, int grid, size_t smem_bytes, cudaStream_t stream);   // kx_warp.cu: one CTA per SM
 cudaError_t launch_alpfix(const AlpFixJob* jobs, uint32_t njobs, uint32_t max_patches, uint8_t* out_base, cudaStream_t stream);
 cudaError_t launch_runfill(const RunFillJob* jobs, uint32_t njobs, uint32_t max_runs, const uint64_t* set_vals, uint8_t* out_base, cudaStream_t stream);
@@ -142,6 +141,10 @@ cudaError_t launch_select(const PackInfo* packs, uint32_t npacks, const uint8_t*
 cudaError_t launch_gather(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
                           int elem_bytes, void* dst, cudaStream_t stream);
 cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream);
+// Simple8b transcode at registration: counts[i] = values of codeword i → exclusive row offsets (in place), *maxbits = widest
+// value, *total = values in the stream; then every value is written into a zeroed `width`-bit LSB-first stream
+cudaError_t launch_s8b_count(const void* words, uint32_t nwords, uint32_t* counts, uint32_t* maxbits, unsigned long long* total, cudaStream_t stream);
+cudaError_t launch_s8b_pack(const void* words, uint32_t nwords, const uint32_t* offs, uint32_t nrows, uint32_t width, void* out, cudaStream_t stream);
 cudaError_t launch_prune(const PruneParams& P, cudaStream_t stream);
 
 }  // namespace kx

@@ -372,6 +372,52 @@ __global__ void exclusive_scan_kernel(uint32_t* v, uint32_t n, unsigned long lon
     if (threadIdx.x == 0) *total = carry;
 }
 
+// ------------------------------------------------------------------------------ Simple8b (legacy container 6) on the device
+// s8b.Decode (internal/encode/s8b/generic/decode.go:15-81) as a two-pass transcode at registration: pass 1 reads every
+// 64-bit codeword's selector (top 4 bits; {128,128,60,30,20,15,12,10,8,7,6,5,4,3,2,1} values of
+// {0,0,1,2,3,4,5,6,7,8,10,12,15,20,30,60} bits, encode.go:32-42) and records its value count and the widest value it holds;
+// an exclusive scan turns the counts into row offsets; pass 2 writes every value into the fixed-width LSB-first bit stream
+// the scan kernels read (64-bit atomic ORs into a zeroed buffer: neighbouring codewords share output words).
+__device__ __constant__ uint8_t S8B_COUNT[16] = {128, 128, 60, 30, 20, 15, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1};
+__device__ __constant__ uint8_t S8B_BITS[16] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 60};
+
+__global__ void s8b_count_kernel(const unsigned long long* __restrict__ words, uint32_t nwords, uint32_t* __restrict__ counts, uint32_t* __restrict__ maxbits) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t mb = 0;
+    if (i < nwords) {
+        const unsigned long long w = words[i];
+        const uint32_t sel = (uint32_t)(w >> 60), cnt = S8B_COUNT[sel], bits = S8B_BITS[sel];
+        counts[i] = cnt;
+        if (sel == 1u) mb = 1u;
+        else if (sel > 1u) {
+            unsigned long long any = 0;   // OR of the fields: its bit length is the widest value of the word
+            const unsigned long long m = bits >= 64u ? ~0ull : ((1ull << bits) - 1ull);
+            for (uint32_t q = 0; q < cnt; ++q) any |= (w >> (q * bits)) & m;
+            mb = any ? 64u - (uint32_t)__clzll((long long)any) : 0u;
+        }
+    }
+    mb = __reduce_max_sync(0xffffffffu, mb);
+    if ((threadIdx.x & 31u) == 0u && mb) atomicMax(maxbits, mb);
+}
+
+__global__ void s8b_pack_kernel(const unsigned long long* __restrict__ words, uint32_t nwords, const uint32_t* __restrict__ offs, uint32_t nrows, uint32_t width,
+                                unsigned long long* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const unsigned long long w = words[i];
+    const uint32_t sel = (uint32_t)(w >> 60), cnt = S8B_COUNT[sel], bits = S8B_BITS[sel];
+    const unsigned long long m = bits >= 64u ? ~0ull : ((1ull << bits) - 1ull);
+    uint32_t row = offs[i];
+    for (uint32_t q = 0; q < cnt && row < nrows; ++q, ++row) {
+        const unsigned long long f = sel == 0u ? 0ull : (sel == 1u ? 1ull : ((w >> (q * bits)) & m));
+        if (!f) continue;
+        const unsigned long long bit = (unsigned long long)row * width;
+        const uint32_t sh = (uint32_t)(bit & 63ull);
+        atomicOr(out + (bit >> 6), f << sh);
+        if (sh + width > 64u) atomicOr(out + (bit >> 6) + 1, f >> (64u - sh));
+    }
+}
+
 __global__ void bitset_scatter_kernel(const uint32_t* buf, uint64_t nbits, const uint32_t* block_offs, uint32_t* dst) {
     uint64_t nwords = (nbits + 31) >> 5;
     uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
@@ -645,6 +691,20 @@ cudaError_t launch_gather(const ColView* views, const unsigned long long* sel_of
     if (total == 0) return cudaSuccess;
     int grid = grid_for(total, 148 * 16);
     gather_kernel<<<grid ? grid : 1, 256, 0, stream>>>(views, sel_off, npacks, sel, total, elem_bytes, reinterpret_cast<uint8_t*>(dst));
+    return cudaGetLastError();
+}
+cudaError_t launch_s8b_count(const void* words, uint32_t nwords, uint32_t* counts, uint32_t* maxbits, unsigned long long* total, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(maxbits, 0, 4, stream);
+    if (e != cudaSuccess) return e;
+    if (nwords == 0) return cudaMemsetAsync(total, 0, 8, stream);
+    s8b_count_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(words), nwords, counts, maxbits);
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(counts, nwords, total);
+    return cudaGetLastError();
+}
+cudaError_t launch_s8b_pack(const void* words, uint32_t nwords, const uint32_t* offs, uint32_t nrows, uint32_t width, void* out, cudaStream_t stream) {
+    if (nwords == 0 || width == 0) return cudaSuccess;
+    s8b_pack_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(words), nwords, offs, nrows, width,
+                                                            reinterpret_cast<unsigned long long*>(out));
     return cudaGetLastError();
 }
 cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream) {

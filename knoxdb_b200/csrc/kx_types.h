@@ -167,20 +167,11 @@ struct ScanParams {
     uint32_t code_smem_off[MAX_SCAN_LEAVES];
     uint32_t code_smem_words;
     uint32_t code_bitmap_words;       // words of that area holding per-pack code bitmaps (0: nothing to reload per pack)
-    // general kernel: per-warp AND/OR stack (stack_depth slots x passes x 32 lanes words per warp; trees that are not a
-    // pure AND / OR chain) and per-warp descriptor caches, both behind the code bitmaps (word offsets from their start)
-    uint32_t stack_off_words;
-    uint32_t stack_depth;
-    uint32_t desc_off_words;
-    uint32_t desc_words;       // words per warp: nleaves PackLeaf + 2 x naggs ColView
+    uint32_t stack_depth;      // warp kernel: slots of the per-warp AND/OR stack (trees that are not a pure AND / OR chain)
     uint32_t flat_op;          // 1: the program is a pure AND of its leaves, 2: a pure OR, 0: general tree
-    uint32_t sched_chunk;      // tiles per scheduling chunk (chunks are dealt round-robin to the CTAs) …
-    uint32_t sched_rounds;     // … for this many full rounds; the remaining tiles are dealt one by one
-    uint32_t prod_sleep;       // producer polls released ring slots with a sleep in between (tuning hook)
-    // value columns of the fused reduce: the rows of one pass (32 groups per warp) are reduced in agg_kp (1, 2 or 4) chunks;
-    // tiles that match densely get the chunks staged through the ring (one slice of 32 / agg_kp groups per warp and stage)
-    uint32_t agg_kp;           // >= 1 whenever naggs > 0
-    uint32_t agg_dense_thr;    // stage the tile when recent matches * thr > recent rows; 0 = always, 0xffffffff = never
+    uint32_t sched_chunk;      // warp kernel: tiles per scheduling chunk (spread evenly over one pack; chunks go round-robin to the warps)
+    // fused reduce: a tile is read with the dense walk when matches * thr > rows; 0 = always, 0xffffffff = never
+    uint32_t agg_dense_thr;
     // warp-autonomous kernel (kx_warp.cu): every warp runs its own TMA ring over tiles of 1024 w_wd rows; a ring stage holds
     // one slot per staged column of the program (leaf streams in postfix order, ALP patch-correction streams behind their leaf)
     uint32_t w_wd;             // bitset words per lane and tile (1, 2 or 4)

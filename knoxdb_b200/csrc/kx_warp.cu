@@ -340,19 +340,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                     // this tile's turn comes after the next filter: start pulling its value rows towards L2 now
                     const uint32_t rows = min(tile_rows, n - pack_row0);
                     if (P.agg_dense_thr != 0xffffffffu) dense_now = P.agg_dense_thr == 0u || (uint64_t)__reduce_add_sync(0xffffffffu, tile_cnt) * P.agg_dense_thr > rows;
-                    if (dense_now && P.prod_sleep == 2u) {   // (tuning hook) every lane prefetches the two 128 B lines of its own rows
-                        for (uint32_t jq = 0; jq < na; ++jq) {
-                            const ColView& v = AV[desc_sel * na + jq];
-                            if (v.kind != CK_BITS || v.width != 64) continue;
-                            for (uint32_t jw = 0; jw < wd; ++jw) {
-                                if (!mwc[jw * 32u + lane]) continue;
-                                const unsigned long long* vp = reinterpret_cast<const unsigned long long*>(v.data) + (wr0 + jw * 1024u);
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(vp));
-                                asm volatile("prefetch.global.L2 [%0];" ::"l"(vp + 16));
-                            }
-                        }
-                    } else if (dense_now) {
-                        if (lane < na && P.prod_sleep == 0u) {
+                    if (dense_now) {
+                        if (lane < na) {
                             const ColView& v = AV[desc_sel * na + lane];
                             if (agg_stageable(v)) {
                                 const uint32_t bytes = (((rows * v.width + 7u) >> 3) + 15u) & ~15u;

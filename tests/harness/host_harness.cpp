@@ -25,6 +25,39 @@ uint64_t field_at(const uint8_t* s, size_t len, uint64_t row, int w) {
     return uint64_t(acc >> sh) & width_mask(w);
 }
 
+// scalar emulation of the device-side Simple8b transcode (s8b_count_kernel / s8b_pack_kernel in kx_scan.cu): codewords →
+// fixed-width LSB-first stream of (value - For), width = widest value
+bool s8b_transcode(BlockLayout& lay) {
+    static const int CNT[16] = {128, 128, 60, 30, 20, 15, 12, 10, 8, 7, 6, 5, 4, 3, 2, 1};
+    static const int BITS[16] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 8, 10, 12, 15, 20, 30, 60};
+    std::vector<uint64_t> f;
+    for (size_t wi = 0; wi + 8 <= lay.stream_len; wi += 8) {
+        uint64_t w; std::memcpy(&w, lay.stream + wi, 8);
+        const int sel = int(w >> 60);
+        for (int q = 0; q < CNT[sel]; q++) f.push_back(sel == 0 ? 0 : sel == 1 ? 1 : (w >> (q * BITS[sel])) & width_mask(BITS[sel]));
+    }
+    if (f.size() < lay.view.n) return false;
+    uint64_t any = 0;
+    for (uint64_t x : f) any |= x;
+    const int w = any ? 64 - __builtin_clzll(any) : 0;
+    lay.view.width = uint8_t(w);
+    lay.view.kind = w ? CK_BITS : CK_CONST;
+    lay.owned.assign((size_t(lay.view.n) * size_t(w) + 7) / 8 + 16, 0);
+    for (uint32_t r = 0; r < lay.view.n && w; r++) {
+        const uint64_t bit = uint64_t(r) * uint64_t(w);
+        for (int k = 0; k < w; k++)
+            if ((f[r] >> k) & 1) lay.owned[(bit + k) >> 3] |= uint8_t(1u << ((bit + k) & 7));
+    }
+    lay.s8b = false;
+    return true;
+}
+
+int normalize(int block_type, const uint8_t* enc, size_t len, BlockLayout& lay, std::string& err) {
+    int rc = normalize_block(block_type, enc, len, lay, err);
+    if (!rc && lay.s8b && !s8b_transcode(lay)) { err = "simple8b: short stream"; return -6; }
+    return rc;
+}
+
 struct HostBlock {
     BlockLayout lay;
     const uint8_t* stream() const { return lay.owned.empty() ? lay.stream : lay.owned.data(); }
@@ -77,7 +110,7 @@ extern "C" {
 long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_t a, uint64_t b,
                const uint64_t* set, uint32_t nset, uint8_t* bits, int* mode_out) {
     HostBlock hb; std::string err;
-    if (normalize_block(block_type, enc, len, hb.lay, err)) return -1;
+    if (normalize(block_type, enc, len, hb.lay, err)) return -1;
     const ColView& v = hb.lay.view;
     LeafSpec leaf; leaf.type = uint8_t(block_type); leaf.mode = uint8_t(mode); leaf.a = a; leaf.b = b;
     std::vector<uint64_t> tab; int tab_log2 = 0;
@@ -158,7 +191,7 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
 
 long kxh_decode(int block_type, const uint8_t* enc, size_t len, uint64_t* dst, size_t cap) {
     HostBlock hb; std::string err;
-    if (normalize_block(block_type, enc, len, hb.lay, err)) return -1;
+    if (normalize(block_type, enc, len, hb.lay, err)) return -1;
     if (hb.lay.view.n > cap) return -2;
     for (uint32_t r = 0; r < hb.lay.view.n; r++) dst[r] = hb.value(r);
     return long(hb.lay.view.n);
@@ -166,7 +199,7 @@ long kxh_decode(int block_type, const uint8_t* enc, size_t len, uint64_t* dst, s
 
 int kxh_view_kind(int block_type, const uint8_t* enc, size_t len) {
     BlockLayout lay; std::string err;
-    if (normalize_block(block_type, enc, len, lay, err)) return -1;
+    if (normalize(block_type, enc, len, lay, err)) return -1;
     return lay.view.kind;
 }
 

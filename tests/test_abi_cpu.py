@@ -67,8 +67,10 @@ def test_product_does_not_reference_the_oracle():
 
 
 def test_scan_kernels_do_not_spill():
-    """ptxas -v of the build: the persistent scan kernels run at the 96-register budget of two 9-warp CTAs per SM; a
-    spill there slows every code path of the kernel down (measured: 2x), so the build refuses to produce one."""
+    """ptxas -v of the build: the single-leaf scan kernels run at the 96-register budget of two 9-warp CTAs per SM and must
+    not spill at all (a spill there slows every code path of the kernel down; measured: 2x); the warp-autonomous kernel
+    (one 16-warp CTA per SM, 128 registers) may keep a few words of cold state around its leaf calls in local memory.
+    The build refuses to produce a library that breaks either rule."""
     import json
     import os
     from knoxdb_b200 import build as kbuild
@@ -76,10 +78,11 @@ def test_scan_kernels_do_not_spill():
     if not os.path.exists(kbuild.INFO):
         kbuild.build(force=True)
     usage = json.load(open(kbuild.INFO))
-    scans = {k: v for k, v in usage.items() if ("scan_kernel" in k or "scan_general_kernel" in k) and "exclusive" not in k}
+    scans = {k: v for k, v in usage.items() if ("scan_kernel" in k or "scan_warp_kernel" in k) and "exclusive" not in k}
     assert len(scans) >= 7, sorted(usage)
     for k, v in scans.items():
-        one_cta = "ILi4ELi1E" in k   # the instantiation for 3-4 value columns runs one CTA per SM
-        general = "scan_general_kernel" in k
-        limit = 0 if not general else (2 * kbuild.GENERAL_SPILL_LIMIT if one_cta else kbuild.GENERAL_SPILL_LIMIT)   # cold state around the leaf calls
-        assert max(v["spill_stores"], v["spill_loads"]) <= limit and v["registers"] <= (224 if one_cta else 96), (k, v)
+        spill = max(v["spill_stores"], v["spill_loads"])
+        if "scan_warp_kernel" in k:
+            assert spill <= kbuild.GENERAL_SPILL_LIMIT and v["registers"] <= (255 if "ILi4ELi256E" in k else 128), (k, v)
+        else:
+            assert spill == 0 and v["registers"] <= 96, (k, v)
