@@ -68,20 +68,27 @@ struct WarpSched {
     }
 };
 
-// raw 64-bit value column, dense tile: the lane's 32 rows are 256 contiguous bytes — sixteen 128-bit loads, all in flight
-// before the first use (rows in ascending order, like the on-demand walk: bit-identical sums).  Measured against a
-// transposed walk with fully coalesced 64-bit loads (lane l on rows 32 k + l): the lane-private walk is 1.4x faster
-// although it asks L2 for every sector twice (profiles/r2_tune_warp.txt).
+// raw 64-bit value column, dense tile: the lane's 32 rows are 256 contiguous bytes — eight 256-bit loads (one whole 32 B
+// sector each: 128-bit loads would ask L2 for every sector twice), all in flight before the first use; rows in ascending
+// order, like the on-demand walk: bit-identical sums.  (Measured against a transposed walk with fully coalesced 64-bit
+// loads, lane l on rows 32 k + l: the lane-private walk is 1.4x faster, profiles/r2_tune_warp.txt.)
+struct U64x4 { unsigned long long a, b, c, d; };
+__device__ __forceinline__ U64x4 ldg256(const unsigned long long* p) {
+    U64x4 v;
+    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
+    return v;
+}
 template <bool F64>
 __device__ __forceinline__ void reduce_dense_raw64(AggAcc& A, const unsigned long long* __restrict__ gp, uint32_t r, uint64_t base, uint64_t flip) {
-    const ulonglong2* g2 = reinterpret_cast<const ulonglong2*>(gp);
-    ulonglong2 v[16];
+    U64x4 v[8];
 #pragma unroll
-    for (int u = 0; u < 16; ++u) v[u] = __ldg(g2 + u);
+    for (int u = 0; u < 8; ++u) v[u] = ldg256(gp + 4 * u);
 #pragma unroll
-    for (int u = 0; u < 16; ++u) {
-        if ((r >> (2 * u)) & 1u) acc_raw64<F64>(A, v[u].x, base, flip);
-        if ((r >> (2 * u + 1)) & 1u) acc_raw64<F64>(A, v[u].y, base, flip);
+    for (int u = 0; u < 8; ++u) {
+        if ((r >> (4 * u)) & 1u) acc_raw64<F64>(A, v[u].a, base, flip);
+        if ((r >> (4 * u + 1)) & 1u) acc_raw64<F64>(A, v[u].b, base, flip);
+        if ((r >> (4 * u + 2)) & 1u) acc_raw64<F64>(A, v[u].c, base, flip);
+        if ((r >> (4 * u + 3)) & 1u) acc_raw64<F64>(A, v[u].d, base, flip);
     }
 }
 

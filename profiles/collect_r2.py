@@ -37,8 +37,9 @@ def raw_metrics(path):
 
 def main():
     for name, (launch, rows) in CASES.items():
-        det = os.path.join(SRC, f"prof_r2_{name}_details.txt")
-        raw = os.path.join(SRC, f"prof_r2_{name}_raw.csv")
+        tag = "r2" if name == "w20" else "r2b"   # r2b: captures of the warp-autonomous kernel (profiles/run_ncu_r2b.sh)
+        det = os.path.join(SRC, f"prof_{tag}_{name}_details.txt")
+        raw = os.path.join(SRC, f"prof_{tag}_{name}_raw.csv")
         if not os.path.exists(det):
             print("missing", det)
             continue
@@ -46,7 +47,7 @@ def main():
         m = raw_metrics(raw)
         rec = {
             "kernel": "kx::" + m["Kernel Name"].replace("void ", ""),
-            "launch": launch + f" (profiles/run_ncu_r2.sh, case r2_{name})",
+            "launch": launch + f" (profiles/run_ncu_{tag}.sh, case {tag}_{name})",
             "rows": rows,
             "dram_bytes_read": to_bytes(m["dram__bytes_read.sum"]),
             "dram_bytes_write": to_bytes(m["dram__bytes_write.sum"]),
@@ -60,7 +61,7 @@ def main():
         json.dump(rec, open(os.path.join(DST, f"r2_ncu_{name}_traffic.json"), "w"), indent=1)
         print(name, rec["duration_us_under_ncu"], "us", rec["dram_bytes_read"] / 1e6, "MB read")
     for name in ("c3dict", "w20"):
-        s = os.path.join(SRC, f"prof_r2_{name}_source.csv.gz")
+        s = os.path.join(SRC, f"prof_{'r2' if name == 'w20' else 'r2b'}_{name}_source.csv.gz")
         if os.path.exists(s):
             shutil.copy(s, os.path.join(DST, f"r2_ncu_{name}_source.csv.gz"))
     for a, b in (("launches_r2.csv", "r2_launches_bench.csv"), ("r2_sweep_configs.json", "r2_sweep_configs.json")):
