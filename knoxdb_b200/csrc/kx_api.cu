@@ -454,7 +454,7 @@ kx_agg_out agg_result(const AggPartial& a, int t) {
 
 // shared-memory layout of the warp-autonomous kernel for one program (ScanParams::w_*)
 struct WarpGeo {
-    uint32_t wd, stages, warps, ncols, stage_bytes, stage_off, warp_bytes;
+    uint32_t wd, stages, warps, ncols, stage_bytes, stage_off, warp_bytes, mw_slots, chunk_rows;
     uint8_t slot[32];
     uint16_t slot_off[32], col_off[MAX_SCAN_LEAVES], fix_off[MAX_SCAN_LEAVES];
 };
@@ -882,7 +882,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             for (uint8_t op : post) { if (op < 0x80) ++sp; else --sp; stack_depth = std::max(stack_depth, sp); }
         }
     }
-    const uint32_t desc_words = uint32_t(nl * (sizeof(PackLeaf) / 4) + 2 * size_t(naggs) * (sizeof(ColView) / 4));
+    auto desc_words_for = [&](uint32_t slots) { return uint32_t(nl * (sizeof(PackLeaf) / 4) + size_t(slots) * size_t(naggs) * (sizeof(ColView) / 4)); };
     const size_t stage_fixed = 32;
     auto stage_bytes_for = [&](uint32_t r) { return round_up(size_t(32) * r * max_stage_bits + stage_fixed, 128); };
     auto rmax_for = [&](const Geo& g) {
@@ -943,8 +943,12 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             }
             if (ns == 0) { g.slot[0] = 0xff; g.slot_off[0] = 0; ns = 1; }   // nothing staged: the barrier still gets one (empty) arrival per tile
             g.ncols = ns;
-            g.stage_bytes = uint32_t(round_up(std::max<size_t>(off, 16), 128));
-            const size_t fixed = 128 + size_t(2) * wd * 128 + size_t(stack_depth) * wd * 128 + size_t(desc_words) * 4;
+            // (a fused reduce streams the raw 64-bit value columns of densely matching tiles through the same stages, in
+            // chunks of stage_bytes / 8 rows: keep a stage at 4 KB or more then)
+            g.stage_bytes = uint32_t(round_up(std::max<size_t>(off, naggs ? 4096 : 16), 128));
+            g.mw_slots = stages + 2;
+            g.chunk_rows = (g.stage_bytes / 8) & ~31u;
+            const size_t fixed = 256 + size_t(g.mw_slots) * wd * 128 + size_t(stack_depth) * wd * 128 + size_t(desc_words_for(g.mw_slots)) * 4;
             g.stage_off = uint32_t(round_up(fixed, 128));
             g.warp_bytes = g.stage_off + stages * g.stage_bytes;
             const size_t room = WARP_MAX_DYN_SMEM > code_smem_bytes ? WARP_MAX_DYN_SMEM - code_smem_bytes : 0;
@@ -1085,6 +1089,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     P.agg_dense_thr = agg_dense_thr;
     if (use_warp) {
         P.w_wd = wg.wd; P.w_warps = wg.warps; P.w_warp_bytes = wg.warp_bytes; P.w_stage_off = wg.stage_off; P.w_ncols = wg.ncols;
+        P.w_mw_slots = wg.mw_slots; P.w_chunk_rows = wg.chunk_rows;
         std::memcpy(P.w_slot, wg.slot, sizeof(P.w_slot));
         std::memcpy(P.w_slot_off, wg.slot_off, sizeof(P.w_slot_off));
         std::memcpy(P.w_col_off, wg.col_off, sizeof(P.w_col_off));

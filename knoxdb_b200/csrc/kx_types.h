@@ -176,9 +176,11 @@ struct ScanParams {
     // one slot per staged column of the program (leaf streams in postfix order, ALP patch-correction streams behind their leaf)
     uint32_t w_wd;             // bitset words per lane and tile (1, 2 or 4)
     uint32_t w_warps;          // warps of a CTA that take tiles
-    uint32_t w_warp_bytes;     // shared memory of one warp (barriers, tile queue, match words, stack, descriptors, ring)
+    uint32_t w_warp_bytes;     // shared memory of one warp (barriers, stage queue, tile records, match words, stack, descriptors, ring)
     uint32_t w_stage_off;      // first ring stage inside a warp's area (bytes)
     uint32_t w_ncols;          // slots per stage (>= 1; lane i of the warp issues the copy of slot i)
+    uint32_t w_mw_slots;       // match-word slots / pending-tile records / value-view sets per warp (stages + 2)
+    uint32_t w_chunk_rows;     // rows of a raw 64-bit value chunk streamed through a ring stage (multiple of 32)
     uint8_t  w_slot[32];       // slot -> leaf index, | 0x80: the leaf's fix stream; 0xff: nothing to copy
     uint16_t w_slot_off[32];   // slot -> offset inside a stage, in 16-byte units
     uint16_t w_col_off[MAX_SCAN_LEAVES];   // leaf -> offset of its stream inside a stage (16-byte units)

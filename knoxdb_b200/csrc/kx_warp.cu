@@ -68,34 +68,6 @@ struct WarpSched {
     }
 };
 
-// raw 64-bit value column, dense tile: the lane's 32 rows are 256 contiguous bytes — eight 256-bit loads (one whole 32 B
-// sector each: 128-bit loads would ask L2 for every sector twice), all in flight before the first use; rows in ascending
-// order, like the on-demand walk: bit-identical sums.  (Measured against a transposed walk with fully coalesced 64-bit
-// loads, lane l on rows 32 k + l: the lane-private walk is 1.4x faster, profiles/r2_tune_warp.txt.)
-struct U64x4 { unsigned long long a, b, c, d; };
-__device__ __forceinline__ U64x4 ldg256(const unsigned long long* p) {
-    U64x4 v;
-    asm volatile("ld.global.nc.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(v.a), "=l"(v.b), "=l"(v.c), "=l"(v.d) : "l"(p));
-    return v;
-}
-template <bool F64>
-__device__ __forceinline__ void reduce_dense_raw64(AggAcc& A, const unsigned long long* __restrict__ gp, uint32_t r, uint64_t base, uint64_t flip) {
-    U64x4 v[8];
-#pragma unroll
-    for (int u = 0; u < 8; ++u) v[u] = ldg256(gp + 4 * u);
-#pragma unroll
-    for (int u = 0; u < 8; ++u) {
-        if ((r >> (4 * u)) & 1u) acc_raw64<F64>(A, v[u].a, base, flip);
-        if ((r >> (4 * u + 1)) & 1u) acc_raw64<F64>(A, v[u].b, base, flip);
-        if ((r >> (4 * u + 2)) & 1u) acc_raw64<F64>(A, v[u].c, base, flip);
-        if ((r >> (4 * u + 3)) & 1u) acc_raw64<F64>(A, v[u].d, base, flip);
-    }
-}
-
-__device__ __forceinline__ void l2_prefetch_bulk(const void* p, uint32_t bytes) {
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
-}
-
 }  // namespace
 
 // NA = value columns reduced by this instantiation (0: filter only; the NA = 4 instantiation also serves 3)
@@ -136,15 +108,17 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
 
     if (warp < WPC) {
         uint8_t* wb = smem + (size_t)warp * P.w_warp_bytes;
+        const uint32_t T = P.w_mw_slots;                                 // match-word slots / tile records / value-view sets kept per warp
         uint64_t* full_bar = reinterpret_cast<uint64_t*>(wb);            // [S] (S <= 4)
-        uint4* fifo = reinterpret_cast<uint4*>(wb + 64);                 // [S] tile queue: pack, first row, rows of the pack
-        uint32_t* mw = reinterpret_cast<uint32_t*>(wb + 128);            // [2][wd * 32] match words: this tile / the previous one
-        uint32_t* stk = mw + 2u * wd * 32u;                              // [stack_depth][wd * 32]
-        uint32_t* wdesc = stk + P.stack_depth * wd * 32u;                // nl PackLeaf + 2 na ColView
+        uint4* fifo = reinterpret_cast<uint4*>(wb + 64);                 // [S] what each ring stage holds: a tile's leaf columns or a value chunk
+        uint4* tmeta = reinterpret_cast<uint4*>(wb + 128);               // [T <= 8] tiles whose reduce is pending: first row, rows of the pack, view set, raw-column mask
+        uint32_t* mw = reinterpret_cast<uint32_t*>(wb + 256);            // [T][wd * 32] match words of the last T tiles
+        uint32_t* stk = mw + T * wd * 32u;                               // [stack_depth][wd * 32]
+        uint32_t* wdesc = stk + P.stack_depth * wd * 32u;                // nl PackLeaf + T na ColView
         uint8_t* stage0 = wb + P.w_stage_off;
         const PackLeaf* L = reinterpret_cast<const PackLeaf*>(wdesc);
-        const ColView* AV = reinterpret_cast<const ColView*>(wdesc + nl * (uint32_t)(sizeof(PackLeaf) / 4u));   // [2][na]
-        const uint32_t NC = P.w_ncols, stage_bytes = P.stage_bytes;
+        const ColView* AV = reinterpret_cast<const ColView*>(wdesc + nl * (uint32_t)(sizeof(PackLeaf) / 4u));   // [T][na]
+        const uint32_t NC = P.w_ncols, stage_bytes = P.stage_bytes, CR = P.w_chunk_rows;
         const uint32_t slot = blockIdx.x * WPC + warp, nslots = gridDim.x * WPC;
 
         if (lane == 0) {
@@ -153,8 +127,10 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
         }
         __syncwarp();
 
-        // ---- issue side: the warp's own tile cursor, `stages` tiles ahead of the one being evaluated.  Lane i keeps the
-        // stream pointer / width of column i for the cursor's pack in registers.
+        // ---- issue side.  A free ring stage takes, in this order: the next value chunk of a tile that matched densely (its
+        // raw 64-bit value columns are streamed through the ring in chunks of CR rows, behind the leaf columns that were
+        // already in flight), else the leaf columns of the warp's next tile (`ic`: the warp's own cursor, ahead of the tile
+        // being evaluated; lane i keeps the stream pointer / width of column i for the cursor's pack in registers).
         WarpSched ic;
         ic.u = slot;
         ic.open(P, tile_rows);
@@ -162,10 +138,38 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
         const uint8_t* iss_data = nullptr;
         uint32_t iss_sl = 0xffu;
         if (lane < NC) { iss_sl = P.w_slot[lane]; iss_off = (uint32_t)P.w_slot_off[lane] * 16u; }
-        auto issue = [&](uint32_t st) {
+        // queue of dense tiles and the cursor inside its head tile, packed into one register (the state lives across every
+        // leaf call): bits 0-14 slot ids (3 bits each, head lowest), 15-17 entries, 18-19 value column, 20-31 chunk
+        uint32_t dqs = 0;
+        auto issue = [&](uint32_t st) -> bool {
+            if (AGG && (dqs & 0x38000u)) {
+                const uint32_t h = dqs & 7u, vq_j = (dqs >> 18) & 3u, vq_c = dqs >> 20;
+                const uint4 tm = tmeta[h];                                   // x: first row, y: rows of the pack, z: view set, w: raw-column mask
+                const uint32_t rows_tile = min(tile_rows, tm.y - tm.x), c0 = vq_c * CR, rows = min(CR, rows_tile - c0);
+                const uint32_t bytes = (rows * 8u + 15u) & ~15u;
+                if (lane == 0) fifo[st] = make_uint4(0u, c0, rows, 0x80000000u | (h << 8) | vq_j);
+                if (lane < NC) {
+                    mbar_expect_tx(&full_bar[st], lane == 0 ? bytes : 0u);
+                    if (lane == 0) {
+                        const ColView& v = AV[tm.z * na + vq_j];
+                        tma_load_1d(stage0 + (size_t)st * stage_bytes, v.data + ((size_t)tm.x + c0) * 8u, bytes, &full_bar[st]);
+                    }
+                }
+                if ((vq_c + 1u) * CR < rows_tile) dqs += 1u << 20;           // next chunk
+                else {                                                       // next raw column of the tile, else the next dense tile
+                    const uint32_t rest = tm.w >> (vq_j + 1u);
+                    if (rest) dqs = (dqs & 0x3ffffu & ~0xc0000u) | ((vq_j + (uint32_t)__ffs((int)rest)) << 18);
+                    else {
+                        const uint32_t cnt = ((dqs >> 15) & 7u) - 1u, ids = (dqs & 0x7fffu) >> 3;
+                        dqs = ids | (cnt << 15);
+                        if (cnt) dqs |= ((uint32_t)__ffs((int)tmeta[ids & 7u].w) - 1u) << 18;
+                    }
+                }
+                return true;
+            }
             if (!ic.valid) {
                 if (lane == 0) fifo[st] = make_uint4(END_PACK, 0u, 0u, 0u);
-                return;
+                return false;
             }
             const uint32_t pack = ic.pack, row0 = ic.tile * tile_rows, n = ic.n;
             if (pack != iss_pack) {
@@ -185,29 +189,34 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                 if (bytes) tma_load_1d(stage0 + (size_t)st * stage_bytes + iss_off, iss_data + (size_t)(row0 >> 3) * iss_w, bytes, &full_bar[st]);
             }
             ic.next(P, nslots, tile_rows);
+            return true;
         };
-        for (uint32_t st = 0; st < S; ++st) issue(st);
+        uint32_t live = 0;               // ring stages that hold work
+        for (uint32_t st = 0; st < S; ++st) live += issue(st) ? 1u : 0u;
         __syncwarp();
 
         // ---- evaluate side
         uint32_t lane_cnt = 0;           // matches of the current pack seen by this lane
-        uint32_t cur_pack = END_PACK, desc_sel = 0, cb = 0;
+        uint32_t cur_pack = END_PACK, desc_sel = 0, tslot = 0, cur_rawmask = 0;   // tslot: slot of the tile being evaluated (tile k uses slot k mod T)
         uint8_t* bits_base = nullptr;
         auto flush_count = [&](uint32_t pk) {
             const uint32_t c = __reduce_add_sync(0xffffffffu, lane_cnt);
             if (P.counts && lane == 0 && c) atomicAdd(P.counts + pk, (unsigned long long)c);
             lane_cnt = 0;
         };
+        // value columns that are not streamed through the ring — every column of a sparse tile, the bit-packed / dictionary /
+        // … columns of a dense one — are read on demand ONE tile behind the filter (their rows were prefetched towards L2)
         bool have_prev = false, prev_any = false, prev_dense = false;
-        uint32_t prev_row0 = 0, prev_sel = 0, prev_n = 0;
+        uint32_t prev_row0 = 0, prev_sel = 0, prev_slot = 0;
         auto reduce_prev = [&]() {
-            const uint32_t* mwp = mw + (cb ^ 1u) * wd * 32u;
+            const uint32_t* mwp = mw + prev_slot * wd * 32u;
 #pragma unroll
             for (int j = 0; j < (AGG ? NA : 0); ++j) {
                 if ((uint32_t)j >= na) break;
                 const ColView& v = AV[prev_sel * na + j];
                 const int type = P.agg_type[j];
                 const bool raw64 = v.kind == CK_BITS && v.width == 64;
+                if (raw64 && prev_dense) continue;   // comes through the ring
                 const uint64_t flip = type_is_signed(type) ? 0x8000000000000000ull : 0ull, base = v.base;
                 AggAcc a = acc[j];
 #pragma unroll 1
@@ -217,13 +226,8 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                     const uint32_t row0 = prev_row0 + (jw * 32u + lane) * 32u;   // first pack row of the lane's word
                     if (raw64) {
                         const unsigned long long* gp = reinterpret_cast<const unsigned long long*>(v.data) + row0;
-                        if (prev_dense && row0 + 32u <= prev_n) {
-                            if (type == 9) reduce_dense_raw64<true>(a, gp, r, 0ull, 0ull);
-                            else reduce_dense_raw64<false>(a, gp, r, base, flip);
-                        } else {
-                            if (type == 9) reduce_global_raw64<true>(a, gp, r, 32u, 0u, 0ull, 0ull);
-                            else reduce_global_raw64<false>(a, gp, r, 32u, 0u, base, flip);
-                        }
+                        if (type == 9) reduce_global_raw64<true>(a, gp, r, 32u, 0u, 0ull, 0ull);
+                        else reduce_global_raw64<false>(a, gp, r, 32u, 0u, base, flip);
                     } else {
                         reduce_generic(a, v, type, row0, nullptr, 0u, r, 32u, 0u);
                     }
@@ -231,17 +235,64 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                 acc[j] = a;
             }
         };
+        // one value chunk of a dense tile, staged in the ring: rows c0 … c0 + rows of the tile, lane l on rows 32 q + l (whole
+        // 256 B shared-memory rows per step: conflict free); the match bit of such a row is bit l of the word of group
+        // c0 / 32 + q, read as a broadcast
+        auto reduce_chunk = [&](const uint8_t* stage, uint32_t h, uint32_t jcol, uint32_t c0, uint32_t rows) {
+            const uint4 tm = tmeta[h];
+            const uint32_t* mwt = mw + h * wd * 32u + (c0 >> 5);
+            const unsigned long long* sv = reinterpret_cast<const unsigned long long*>(stage) + lane;
+            __builtin_assume(__isShared(sv));
+            const uint32_t steps = (rows + 31u) >> 5;
+#pragma unroll
+            for (int j = 0; j < (AGG ? NA : 0); ++j) {
+                if ((uint32_t)j != jcol) continue;
+                const ColView& v = AV[tm.z * na + j];
+                const int type = P.agg_type[j];
+                const uint64_t flip = type_is_signed(type) ? 0x8000000000000000ull : 0ull, base = v.base;
+                AggAcc a = acc[j];
+                if (type == 9) {
+#pragma unroll 4
+                    for (uint32_t q = 0; q < steps; ++q)
+                        if ((mwt[q] >> lane) & 1u) acc_raw64<true>(a, sv[q * 32u], 0ull, 0ull);
+                } else {
+#pragma unroll 4
+                    for (uint32_t q = 0; q < steps; ++q)
+                        if ((mwt[q] >> lane) & 1u) acc_raw64<false>(a, sv[q * 32u], base, flip);
+                }
+                acc[j] = a;
+            }
+        };
 
-        uint32_t s = 0, ph = 0;
-        for (;;) {
+        uint32_t s = 0, phbits = 0;      // phbits: parity of every stage's barrier (a stage that held nothing is not waited on)
+        while (live || (AGG && (dqs & 0x38000u))) {   // (a dense tile found after the last refill still has its value chunks to queue)
             const uint4 e = fifo[s];
             const uint32_t pack = e.x, pack_row0 = e.y, n = e.z;
-            if (pack == END_PACK) break;
+            if (pack == END_PACK) {      // nothing was issued into this stage last time round: something may be pending now
+                __syncwarp();
+                live += issue(s) ? 1u : 0u;
+                __syncwarp();
+                if (++s == S) s = 0;
+                continue;
+            }
+            const uint8_t* stage = stage0 + (size_t)s * stage_bytes;
+            if (AGG && (e.w & 0x80000000u)) {
+                // ---- a value chunk of a dense tile
+                mbar_wait(&full_bar[s], (phbits >> s) & 1u);
+                phbits ^= 1u << s;
+                reduce_chunk(stage, (e.w >> 8) & 15u, e.w & 0xffu, e.y, e.z);
+                __syncwarp();
+                --live;
+                live += issue(s) ? 1u : 0u;
+                __syncwarp();
+                if (++s == S) s = 0;
+                continue;
+            }
             if (pack != cur_pack) {
                 // new pack: the warp caches its descriptors
                 if (cur_pack != END_PACK) flush_count(cur_pack);
                 __syncwarp();
-                desc_sel ^= 1u;
+                if (++desc_sel == T) desc_sel = 0;
                 {
                     const uint32_t* src = reinterpret_cast<const uint32_t*>(P.leaves + (size_t)pack * nl);
                     for (uint32_t i = lane; i < nl * (uint32_t)(sizeof(PackLeaf) / 4u); i += 32u) wdesc[i] = __ldg(src + i);
@@ -254,13 +305,19 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                 if (P.bitsets) bits_base = P.bitsets + P.packs[pack].bitset_off;
                 __syncwarp();
                 cur_pack = pack;
+                cur_rawmask = 0;
+                if (AGG)
+                    for (uint32_t j = 0; j < na; ++j) {
+                        const ColView& v = AV[desc_sel * na + j];
+                        if (v.kind == CK_BITS && v.width == 64) cur_rawmask |= 1u << j;
+                    }
             }
             const LeafEnv env{P, code_smem, n, pack_row0};
             const uint32_t wr0 = pack_row0 + lane * 32u;   // first pack row of this lane's word 0 (word j: + 1024 j)
-            uint32_t* mwc = mw + cb * wd * 32u;
-            const uint8_t* stage = stage0 + (size_t)s * stage_bytes;
+            uint32_t* mwc = mw + tslot * wd * 32u;
 
-            mbar_wait(&full_bar[s], ph);   // every staged column of the tile has landed
+            mbar_wait(&full_bar[s], (phbits >> s) & 1u);   // every staged column of the tile has landed
+            phbits ^= 1u << s;
 
             if (P.flat_op) {
                 // pure AND (1) / pure OR (2) program.  MatchAnd's early-out (match_core.go:44-130), per warp and word: a word
@@ -317,9 +374,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                 for (uint32_t j = 0; j < wd; ++j) mwc[j * 32u + lane] = stk[j * 32u + lane];
             }
 
-            // ---- the stage is free: the copies of the tile `stages` ahead go into it while this one is finished
+            // ---- the stage is free: refill it (a value chunk of a dense tile that is waiting, else the leaf columns of the tile
+            // `stages` ahead) while this tile is finished
             __syncwarp();
-            issue(s);
+            --live;
+            live += issue(s) ? 1u : 0u;
 
             // ---- outputs of the tile: tail masking (match_core.go semantics: tail bits zero; only the last tile of a pack has
             // a tail), bitset words (coalesced 128 B per warp and word), per-pack match count
@@ -344,18 +403,17 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                 const bool any_now = __any_sync(0xffffffffu, tile_cnt != 0u);
                 bool dense_now = false;
                 if (any_now) {
-                    // this tile's turn comes after the next filter: start pulling its value rows towards L2 now
                     const uint32_t rows = min(tile_rows, n - pack_row0);
                     if (P.agg_dense_thr != 0xffffffffu) dense_now = P.agg_dense_thr == 0u || (uint64_t)__reduce_add_sync(0xffffffffu, tile_cnt) * P.agg_dense_thr > rows;
+                    dense_now = dense_now && cur_rawmask != 0u;
                     if (dense_now) {
-                        if (lane < na) {
-                            const ColView& v = AV[desc_sel * na + lane];
-                            if (agg_stageable(v)) {
-                                const uint32_t bytes = (((rows * v.width + 7u) >> 3) + 15u) & ~15u;
-                                l2_prefetch_bulk(v.data + (size_t)(pack_row0 >> 3) * v.width, bytes);
-                            }
-                        }
+                        // the tile's raw value columns follow through the ring (from the next free stage on)
+                        if (lane == 0) tmeta[tslot] = make_uint4(pack_row0, n, desc_sel, cur_rawmask);
+                        const uint32_t cnt = (dqs >> 15) & 7u;
+                        if (cnt == 0u) dqs = ((uint32_t)__ffs((int)cur_rawmask) - 1u) << 18;
+                        dqs = (dqs & ~0x38000u) | (tslot << (3u * cnt)) | ((cnt + 1u) << 15);
                     } else if (tile_cnt != 0u && tile_cnt <= 8u * wd) {
+                        // this tile's turn comes after the next filter: start pulling its matching rows towards L2 now
 #pragma unroll
                         for (int j = 0; j < NA; ++j) {
                             if ((uint32_t)j >= na) break;
@@ -381,10 +439,11 @@ __global__ void __launch_bounds__(THREADS, 1) scan_warp_kernel(const ScanParams 
                     }
                 }
                 if (have_prev && prev_any) reduce_prev();
-                cb ^= 1u;
-                prev_row0 = pack_row0; prev_sel = desc_sel; prev_n = n; have_prev = true; prev_any = any_now; prev_dense = dense_now;
+                prev_row0 = pack_row0; prev_sel = desc_sel; prev_slot = tslot; have_prev = true; prev_any = any_now; prev_dense = dense_now;
             }
-            if (++s == S) { s = 0; ph ^= 1u; }
+            if (++tslot == T) tslot = 0;
+            __syncwarp();
+            if (++s == S) s = 0;
         }
         if (cur_pack != END_PACK) flush_count(cur_pack);
         if constexpr (AGG) {

@@ -25,7 +25,7 @@ import oracle as ko                 # noqa: E402  (encoder of the synthetic bloc
 from sweep_configs import raw_block   # noqa: E402
 
 M1 = 1 << 20
-KNOBS = ("KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_PROD_SLEEP", "KX_AGG_STAGE", "KX_MIN_STAGES", "KX_GENERAL", "KX_WARP_GEOMETRY")
+KNOBS = ("KX_SCAN_GEOMETRY", "KX_SCHED_CHUNK", "KX_AGG_STAGE", "KX_WARP_GEOMETRY")
 
 
 def main():
@@ -107,7 +107,7 @@ def main():
             combos = [{"KX_WARP_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(wgeos, wchunks)]
             combos += [{"KX_AGG_STAGE": a} for a in ("never", "always", "2", "5", "8")] + [{"KX_PROD_SLEEP": "1"}, {"KX_PROD_SLEEP": "2"}, {"KX_GENERAL": "v2"}]
             if args.minimal:
-                combos = [{"KX_PROD_SLEEP": "1"}, {"KX_AGG_STAGE": "2"}, {"KX_AGG_STAGE": "5"}, {"KX_GENERAL": "v2"}]
+                combos = [{"KX_AGG_STAGE": "never"}, {"KX_AGG_STAGE": "5"}] + [{"KX_WARP_GEOMETRY": g} for g in ("2,2,11", "2,2,10", "2,2,8", "1,2,16", "1,3,16", "2,3,8")]
         for combo in combos:
             for k in KNOBS:
                 os.environ.pop(k, None)
