@@ -149,6 +149,10 @@ struct kx_prog {
     std::vector<uint8_t> strs;           // operands of the byte-string leaves
     uint8_t* dev_strs = nullptr;
     bool prune_only = false;             // has a byte-string leaf: usable with kx_prune* only
+    ~kx_prog() {   // (also runs when kx_prog_compile fails half way: no device buffer outlives the host struct)
+        if (dev_sets) cudaFree(dev_sets);
+        if (dev_strs) cudaFree(dev_strs);
+    }
 };
 
 struct kx_ctx {
@@ -205,6 +209,11 @@ struct kx_stats {
     uint8_t* d_tab = nullptr;              // ptr | mask | k tables on the device
     bool dirty = true;
     std::vector<SlabAlloc> cell_alloc;   // [nfields][npacks] slab extent of each bit array (slab = -1: none)
+    ~kx_stats() {   // (also runs when kx_stats_create fails half way)
+        if (d_mins) cudaFree(d_mins);
+        if (d_maxs) cudaFree(d_maxs);
+        if (d_tab) cudaFree(d_tab);
+    }
 };
 
 namespace {
@@ -1157,8 +1166,7 @@ int single_leaf_scan(kx_ctx* ctx, const StoredBlock& sb, uint8_t block_type, uin
     job.leaf_dicts = {sb.dict.empty() ? nullptr : sb.dict.data()};
     size_t off = 0;
     rc = run_scan(ctx, prog, job, bits, &off, count, nullptr, 0, nullptr);
-    if (prog->dev_sets) cudaFree(prog->dev_sets);
-    delete prog;
+    delete prog;   // (its destructor frees the device copies of the sets)
     return rc;
 }
 
@@ -1283,7 +1291,7 @@ int kx_ctx_create(int device, size_t hbm_budget, kx_ctx** out) {
     CK(cudaSetDevice(device));
     cudaDeviceProp prop{};
     CK(cudaGetDeviceProperties(&prop, device));
-    if (prop.major < 9) return fail(nullptr, KX_ENODEV, "libknoxgpu needs an sm_100a (Blackwell) device");
+    if (prop.major != 10) return fail(nullptr, KX_ENODEV, "libknoxgpu holds sm_100a code only: it needs a compute capability 10.x (Blackwell B200) device");
     auto c = std::make_unique<kx_ctx>();
     c->device = device;
     c->num_sms = prop.multiProcessorCount;
@@ -1390,8 +1398,7 @@ int kx_prog_compile(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8
 
 void kx_prog_free(kx_prog* prog) {
     if (!prog) return;
-    if (prog->dev_sets) { cudaSetDevice(prog->ctx->device); cudaFree(prog->dev_sets); }
-    if (prog->dev_strs) { cudaSetDevice(prog->ctx->device); cudaFree(prog->dev_strs); }
+    cudaSetDevice(prog->ctx->device);
     delete prog;
 }
 
@@ -1688,6 +1695,8 @@ int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, 
         if (it->second.view.type != block_type) return fail(ctx, KX_EINVAL, "kx_gather: block type mismatch");
         if (sel_off[p + 1] < sel_off[p]) return fail(ctx, KX_EINVAL, "kx_gather: sel_off must ascend");
         views[size_t(p)] = it->second.view;
+        for (uint64_t i = sel_off[p]; i < sel_off[p + 1]; ++i)   // a row id past the block would be an out-of-bounds device read
+            if (sel[i] >= it->second.view.n) return fail(ctx, KX_EINVAL, "kx_gather: row id " + std::to_string(sel[i]) + " outside pack " + std::to_string(packs[p].pack));
     }
     // device layout: views | sel_off | sel | dst
     size_t off_so = round_up(sizeof(ColView) * size_t(npacks), 256), off_sel = off_so + round_up(8 * (size_t(npacks) + 1), 256);
@@ -2308,7 +2317,6 @@ void kx_stats_free(kx_stats* st) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     for (auto& a : st->cell_alloc) slab_release(ctx, a);
-    cudaFree(st->d_mins); cudaFree(st->d_maxs); cudaFree(st->d_tab);
     delete st;
 }
 

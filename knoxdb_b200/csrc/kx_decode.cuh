@@ -60,6 +60,7 @@ __device__ __forceinline__ uint64_t decode_value(const ColView& v, uint32_t row,
         uint64_t code = staged ? load_field(staged, (uint64_t)row_in_tile * v.width, v.width)
                                : load_field(reinterpret_cast<const uint32_t*>(v.data), (uint64_t)row * v.width, v.width);
         code += v.delta;
+        if (code >= v.naux) code = v.naux ? v.naux - 1u : 0u;   // (a corrupt code stream must not read past the dictionary)
         return __ldg(reinterpret_cast<const unsigned long long*>(v.aux) + code);
     }
     case CK_RUNEND: {
