@@ -998,6 +998,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     // selects, and a warp changes pack once per chunk) — `tile0` / `ntiles` / `tile_pack` count chunks there
     uint32_t sched_chunk = 8;
     if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, std::min(atoi(e), 64)));
+    while (sched_chunk & (sched_chunk - 1)) sched_chunk &= sched_chunk - 1;   // a power of two (the kernel shifts)
     if (simple) sched_chunk = 1;
     if (use_warp)   // small scans: smaller chunks first, so that every warp of the persistent grid gets work
         while (sched_chunk > 1 && total_rows / (uint64_t(tile_rows) * sched_chunk) < uint64_t(4) * ctx->num_sms * wg.warps) sched_chunk /= 2;

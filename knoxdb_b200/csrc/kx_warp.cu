@@ -54,8 +54,9 @@ struct WarpSched {
         pack = P.tile_pack ? __ldg(P.tile_pack + u) : u / P.tiles_per_pack;
         const PackInfo pi = P.packs[pack];
         n = pi.n;
-        tiles = (n + tile_rows - 1) / tile_rows;
-        nch = (tiles + P.sched_chunk - 1) / P.sched_chunk;
+        // (tile_rows and sched_chunk are powers of two: shifts instead of two integer divisions per chunk)
+        tiles = (n + tile_rows - 1) >> (31 - __clz((int)tile_rows));
+        nch = (tiles + P.sched_chunk - 1) >> (31 - __clz((int)P.sched_chunk));
         tile = u - pi.tile0;
         step = 0;
         valid = true;
