@@ -14,6 +14,7 @@ package gpu
 import "C"
 
 import (
+	"encoding/binary"
 	"errors"
 	"fmt"
 	"math"
@@ -163,9 +164,28 @@ func (c *Context) Compile(root *filter.Node) (*Program, error) {
 				return nil
 			}
 			if f.Type == types.BlockBytes {
-				// IN / NOT IN on byte strings are matched by a hash set of strings in the reference
-				// (match_bytes.go); the library has no string sets: keep such filters on the stock path
-				return errors.New("knoxgpu: IN/NIN on byte-string columns is not supported")
+				// IN / NOT IN on byte strings (bytesInSetMatcher / bytesNotInSetMatcher, match_bytes.go:392-520): the set
+				// travels as nset little-endian uint32 lengths followed by the concatenated bytes, a = buffer size
+				vals, ok := f.Value.([][]byte)
+				if !ok || len(vals) == 0 {
+					return fmt.Errorf("knoxgpu: byte-string set filter carries %T", f.Value)
+				}
+				size := 4 * len(vals)
+				for _, v := range vals {
+					size += len(v)
+				}
+				p := C.malloc(C.size_t(size + 1))
+				buf := unsafe.Slice((*byte)(p), size+1)
+				pos := 4 * len(vals)
+				for i, v := range vals {
+					binary.LittleEndian.PutUint32(buf[4*i:], uint32(len(v)))
+					pos += copy(buf[pos:], v)
+				}
+				cbufs = append(cbufs, p)
+				l.set, l.nset, l.a = (*C.uint64_t)(p), C.uint32_t(len(vals)), C.uint64_t(size)
+				post = append(post, C.uint8_t(len(leaves)))
+				leaves = append(leaves, l)
+				return nil
 			}
 			switch f.Mode {
 			case types.FilterModeRange:

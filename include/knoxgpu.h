@@ -97,7 +97,10 @@ int kx_store_stats(kx_ctx* ctx, uint64_t* nblocks, uint64_t* encoded_bytes, uint
  * member, internal/encode/int_raw.go:339-357); order and duplicates do not matter.
  * Byte-string leaves (block_type KX_BYTES; types.StringMatcher, internal/encode/string_match.go:13-188: the seven
  * scalar modes, bytes.Equal / bytes.Compare row by row): nset = 1, `set` points to the operand BYTES, a = length of
- * the operand, and for RANGE b = length of the upper bound that follows it.  A KX_BYTES leaf with nset = 0 carries
+ * the operand, and for RANGE b = length of the upper bound that follows it.  IN / NIN on byte strings
+ * (bytesInSetMatcher / bytesNotInSetMatcher, internal/operator/filter/match_bytes.go:392-520: exact membership in the
+ * de-duplicated set): nset = number of strings, `set` points to nset little-endian uint32 lengths followed by the
+ * concatenated string bytes, a = size of that buffer in bytes.  A KX_BYTES leaf with nset = 0 carries
  * no operand and can only be used for pruning (bloom probes with caller-supplied hashes). */
 typedef struct kx_leaf {
     uint16_t field;

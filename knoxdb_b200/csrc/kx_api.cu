@@ -753,10 +753,13 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                     const std::vector<uint8_t>* cv = job.leaf_cstr.empty() ? nullptr : job.leaf_cstr[size_t(p) * nleaves + l];
                     static const std::vector<uint8_t> empty;
                     if (!cv) cv = &empty;
-                    const bool all = v.n != 0 && string_pred(ls.mode, cv->data(), cv->size(), ls.sa.data(), ls.sa.size(), ls.sb.data(), ls.sb.size());
+                    const bool is_set = ls.mode == KX_MODE_IN || ls.mode == KX_MODE_NIN;
+                    const bool all = v.n != 0 && (is_set ? string_set_pred(ls.mode, cv->data(), cv->size(), ls.sa.data(), uint32_t(ls.a))
+                                                          : string_pred(ls.mode, cv->data(), cv->size(), ls.sa.data(), ls.sa.size(), ls.sb.data(), ls.sb.size()));
                     o.mode = all ? LM_ALL : LM_NONE;
                 } else {
-                    sjobs.push_back(StrJob{v, leafbits_bytes, ls.sa_off, uint32_t(ls.sa.size()), ls.sb_off, uint32_t(ls.sb.size()), uint32_t(ls.mode), 0});
+                    const bool is_set = ls.mode == KX_MODE_IN || ls.mode == KX_MODE_NIN;   // a_len = number of strings of the set then
+                    sjobs.push_back(StrJob{v, leafbits_bytes, ls.sa_off, is_set ? uint32_t(ls.a) : uint32_t(ls.sa.size()), ls.sb_off, uint32_t(ls.sb.size()), uint32_t(ls.mode), 0});
                     sjob_leaf.push_back(size_t(p) * nl + l);
                     leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                     max_str_rows = std::max(max_str_rows, v.n);
@@ -1202,6 +1205,41 @@ int make_prog(kx_ctx* ctx, const kx_leaf* leaves, int nleaves, const uint8_t* po
                 s.sa_off = uint32_t(p->strs.size()); p->strs.insert(p->strs.end(), s.sa.begin(), s.sa.end());
                 s.sb_off = uint32_t(p->strs.size()); p->strs.insert(p->strs.end(), s.sb.begin(), s.sb.end());
                 s.a = s.b = 0;
+                s.has_str = true;
+            } else if ((in.mode == KX_MODE_IN || in.mode == KX_MODE_NIN) && in.nset >= 1 && in.set) {
+                // row-level set membership (match_bytes.go:392-520): the strings are sorted (bytes.Compare order) and
+                // de-duplicated like slicex.OrderedBytes.SetUnique; the device pool gets [count x (offset, length)] + bytes
+                const uint8_t* ob = reinterpret_cast<const uint8_t*>(in.set);
+                const uint64_t head = uint64_t(in.nset) * 4;
+                if (in.nset > (1u << 20) || in.a < head || in.a > (1ull << 28)) return fail(ctx, KX_EINVAL, "leaf: bad byte-string set");
+                std::vector<std::pair<const uint8_t*, uint32_t>> items;
+                uint64_t pos = head;
+                for (uint32_t i = 0; i < in.nset; ++i) {
+                    uint32_t len; std::memcpy(&len, ob + size_t(i) * 4, 4);
+                    if (pos + len > in.a) return fail(ctx, KX_EINVAL, "leaf: byte-string set overruns its buffer");
+                    items.push_back({ob + pos, len});
+                    pos += len;
+                }
+                auto less = [](const std::pair<const uint8_t*, uint32_t>& x, const std::pair<const uint8_t*, uint32_t>& y) {
+                    const int c = std::memcmp(x.first, y.first, std::min(x.second, y.second));
+                    return c < 0 || (c == 0 && x.second < y.second);
+                };
+                std::sort(items.begin(), items.end(), less);
+                items.erase(std::unique(items.begin(), items.end(), [&](const auto& x, const auto& y) { return !less(x, y) && !less(y, x); }), items.end());
+                while (p->strs.size() & 3) p->strs.push_back(0);   // the (offset, length) table is read as uint32
+                s.sa_off = uint32_t(p->strs.size());
+                const uint32_t cnt = uint32_t(items.size());
+                s.sa.resize(size_t(cnt) * 8);                       // host copy of the table + bytes (constant blocks are decided on the host)
+                uint32_t boff = cnt * 8;
+                for (uint32_t i = 0; i < cnt; ++i) {
+                    std::memcpy(s.sa.data() + size_t(i) * 8, &boff, 4);
+                    std::memcpy(s.sa.data() + size_t(i) * 8 + 4, &items[i].second, 4);
+                    boff += items[i].second;
+                }
+                for (auto& it : items) s.sa.insert(s.sa.end(), it.first, it.first + it.second);
+                p->strs.insert(p->strs.end(), s.sa.begin(), s.sa.end());
+                s.sb_off = s.sa_off;
+                s.a = cnt; s.b = 0;                                 // a = number of distinct strings
                 s.has_str = true;
             } else {
                 // no operand: the leaf takes part in pruning only (bloom probes with caller-supplied hashes)

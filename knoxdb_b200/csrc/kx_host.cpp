@@ -952,6 +952,21 @@ bool string_pred(int mode, const uint8_t* v, size_t vl, const uint8_t* a, size_t
     return false;
 }
 
+// membership in a sorted, de-duplicated set laid out as [count x (offset u32, length u32)] + bytes (offsets from the table start)
+bool string_set_pred(int mode, const uint8_t* v, size_t vl, const uint8_t* table, uint32_t count) {
+    uint32_t lo = 0, hi = count;
+    bool found = false;
+    while (lo < hi) {
+        const uint32_t m = (lo + hi) / 2;
+        uint32_t off, len;
+        std::memcpy(&off, table + size_t(m) * 8, 4); std::memcpy(&len, table + size_t(m) * 8 + 4, 4);
+        const int c = bytes_compare(v, vl, table + off, len);
+        if (c == 0) { found = true; break; }
+        if (c < 0) hi = m; else lo = m + 1;
+    }
+    return mode == M_IN ? found : !found;
+}
+
 void build_set_prefilter(const std::vector<uint64_t>& set, std::vector<uint32_t>& words, int& log2bits) {
     int lg = 10;
     while (lg < 17 && (size_t(1) << lg) < set.size() * 256) ++lg;

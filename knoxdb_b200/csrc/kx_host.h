@@ -95,6 +95,8 @@ inline uint32_t set_table_bucket(uint64_t v, int log2nb) { return set_hash32(v) 
 // One-hash prefilter bitmap of the set (2^log2bits bits, ~256 bits per key, 1 Ki … 128 Ki bits): the scan tests it for
 // every row out of shared memory and consults the exact table only for the rows that pass.
 void build_set_prefilter(const std::vector<uint64_t>& set, std::vector<uint32_t>& words, int& log2bits);
+// byte-string IN / NIN against a sorted set table ([count x (offset, length)] + bytes), bytes.Compare order
+bool string_set_pred(int mode, const uint8_t* v, size_t vl, const uint8_t* table, uint32_t count);
 
 // Translate one leaf for one block.  dict_host: host copy of the block's dictionary values
 // (CK_DICT only).  view_index: index of the block's ColView in the launch's view table.

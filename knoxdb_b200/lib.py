@@ -195,6 +195,14 @@ class Leaf:
             b = bytes(b) if isinstance(b, (bytes, bytearray)) else b""
             self.a, self.b = len(a), len(b) if mode == RANGE else 0
             self.bytes = np.frombuffer(bytes(a) + (b if mode == RANGE else b"") + b"\0" * 8, dtype=np.uint8).copy()
+        if block_type == BYTES and values is not None and mode in (IN, NIN):
+            # set of byte strings: uint32 lengths, then the bytes (include/knoxgpu.h); a = size of the buffer
+            items = [bytes(v) for v in values]
+            buf = np.asarray([len(v) for v in items], dtype="<u4").tobytes() + b"".join(items)
+            self.a, self.b = len(buf), 0
+            self.bytes = np.frombuffer(buf + b"\0" * 8, dtype=np.uint8).copy()
+            self.nbytes_set = len(items)
+            values = None
         if values is not None:
             arr = np.asarray(values)
             if arr.dtype.kind == "i":
@@ -217,7 +225,7 @@ class Program:
                 arr[i].nset = lf.set.size
                 arr[i].set = lf.set.ctypes.data_as(C.POINTER(C.c_uint64))
             if getattr(lf, "bytes", None) is not None:
-                arr[i].nset = 1
+                arr[i].nset = getattr(lf, "nbytes_set", 1)
                 arr[i].set = C.cast(lf.bytes.ctypes.data, C.POINTER(C.c_uint64))
         h = C.c_void_p()
         ctx._check(lib().kx_prog_compile(ctx.h, arr, len(self.leaves), _ptr(self.postfix), self.postfix.size, C.byref(h)))

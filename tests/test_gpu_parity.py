@@ -548,6 +548,39 @@ def _string_rows(rng, n, shape):
 
 
 @pytest.mark.parametrize("shape", ["fixed20", "dups", "ragged", "const"])
+def test_string_in_sets(ctx, shape):
+    """bytesInSetMatcher / bytesNotInSetMatcher (internal/operator/filter/match_bytes.go:392-520: a row matches iff its bytes
+    are a member of the de-duplicated set): sets of 1 … 300 strings with members, non-members, duplicates, the empty string
+    and proper prefixes, on every string container; the truth is Python's own bytes membership on the oracle's rows."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(12)
+    for n in (1, 33, 1000, 20_011):
+        rows = _string_rows(rng, n, shape)
+        kinds = [k for k in (ko.STR_CONST, ko.STR_FIXED, ko.STR_COMPACT, ko.STR_DICT) if ko.store_str(k, rows) is not None]
+        if n > 5000:
+            kinds = [k for k in kinds if k != ko.STR_DICT or shape in ("dups", "const")]
+        sets = [[rows[0]], [b""], [rows[n // 2], rows[n // 2], b"zz-not-there"], [rows[-1][:-1], rows[-1] + b"\x00"],
+                [rows[i] for i in rng.integers(0, n, 40)] + [b"", b"ab"],
+                [bytes(rng.integers(0, 256, int(k), dtype=np.uint8)) for k in rng.integers(0, 30, 300)] + [rows[n // 3]]]
+        for kind in kinds:
+            blob = ko.store_str(kind, rows)
+            oc = ko.StrContainer(blob)
+            assert ctx.block_put(320, 1, 9, kb.BYTES, blob) == n
+            got_rows = [oc.get(i) for i in range(min(n, 50))]
+            assert got_rows == rows[: len(got_rows)]
+            for members in sets:
+                ms = set(members)
+                truth = np.fromiter((r in ms for r in rows), dtype=bool, count=n)
+                for mode, want_bool in ((kb.IN, truth), (kb.NIN, ~truth)):
+                    prog = kb.Program(ctx, [kb.Leaf(9, kb.BYTES, mode, values=members)])
+                    res = ctx.scan(prog, [(320, 1)], nrows=[n], want_bitsets=True)
+                    assert (res["bitsets"][0] == kt.pack_bits(want_bool)).all(), (shape, n, kind, mode, len(members))
+                    assert int(res["counts"][0]) == int(want_bool.sum())
+                    prog.close()
+            ctx.block_drop(320, 1, 9)
+
+
+@pytest.mark.parametrize("shape", ["fixed20", "dups", "ragged", "const"])
 def test_string_blocks_match_row_by_row(ctx, shape):
     """types.StringMatcher on the string containers (internal/encode/string_{const,fixed,compact,dict}.go, matchers
     string_match.go:13-188): the seven modes, operands that are members, non-members, prefixes and the empty string,
