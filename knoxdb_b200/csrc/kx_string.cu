@@ -26,21 +26,25 @@ __device__ __forceinline__ int bytes_cmp(const uint8_t* __restrict__ v, uint32_t
     return vl < al ? -1 : (vl > al ? 1 : 0);
 }
 
+// IN / NOT IN (bytesInSetMatcher, internal/operator/filter/match_bytes.go:392-520): binary search in the sorted set;
+// a = [al x (offset, length)] + bytes
+static __device__ __noinline__ bool str_in_set(uint32_t mode, const uint8_t* __restrict__ v, uint32_t vl, const uint8_t* __restrict__ a, uint32_t al) {
+    const uint32_t* tab = reinterpret_cast<const uint32_t*>(a);
+    uint32_t lo = 0, hi = al;
+    bool found = false;
+    while (lo < hi) {
+        const uint32_t m = (lo + hi) >> 1;
+        const int c = bytes_cmp(v, vl, a + __ldg(tab + 2 * m), __ldg(tab + 2 * m + 1));
+        if (c == 0) { found = true; break; }
+        if (c < 0) hi = m; else lo = m + 1;
+    }
+    return mode == 7u ? found : !found;
+}
+
 __device__ __forceinline__ bool str_pred(uint32_t mode, const uint8_t* __restrict__ v, uint32_t vl, const uint8_t* __restrict__ a, uint32_t al,
                                          const uint8_t* __restrict__ b, uint32_t bl) {
+    if (mode == 7u || mode == 8u) return str_in_set(mode, v, vl, a, al);   // IN / NOT IN: out of line, the scalar modes keep their code
     switch (mode) {
-    case 7: case 8: {   // IN / NOT IN (match_bytes.go:392-520): binary search in the sorted set; a = [al x (offset, length)] + bytes
-        const uint32_t* tab = reinterpret_cast<const uint32_t*>(a);
-        uint32_t lo = 0, hi = al;
-        bool found = false;
-        while (lo < hi) {
-            const uint32_t m = (lo + hi) >> 1;
-            const int c = bytes_cmp(v, vl, a + __ldg(tab + 2 * m), __ldg(tab + 2 * m + 1));
-            if (c == 0) { found = true; break; }
-            if (c < 0) hi = m; else lo = m + 1;
-        }
-        return mode == 7 ? found : !found;
-    }
     case 1: return vl == al && bytes_cmp(v, vl, a, al) == 0;          // MatchEqual (length first: most rows differ there or in byte 0)
     case 2: return !(vl == al && bytes_cmp(v, vl, a, al) == 0);       // MatchNotEqual
     case 3: return bytes_cmp(v, vl, a, al) > 0;
