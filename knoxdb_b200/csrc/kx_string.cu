@@ -57,7 +57,7 @@ __device__ __forceinline__ bool str_pred(uint32_t mode, const uint8_t* __restric
 
 constexpr uint32_t STR_DICT_SMEM_ENTRIES = 32768;   // dictionary predicate bitmap in shared memory: 4 KB
 
-__global__ void __launch_bounds__(256) strmatch_kernel(const StrJob* __restrict__ jobs, uint32_t njobs, const uint8_t* __restrict__ pool, uint8_t* __restrict__ out_base) {
+__global__ void __launch_bounds__(256, 8) strmatch_kernel(const StrJob* __restrict__ jobs, uint32_t njobs, const uint8_t* __restrict__ pool, uint8_t* __restrict__ out_base) {
     __shared__ uint32_t dict_bits[STR_DICT_SMEM_ENTRIES / 32];
   for (uint32_t jb = blockIdx.y; jb < njobs; jb += gridDim.y) {   // (gridDim.y is capped at 65535 jobs per launch)
     __syncthreads();   // the previous job's dictionary bitmap is no longer read

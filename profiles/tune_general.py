@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
-"""tune_general.py — sweep the general (multi-leaf filter + fused reduce) kernel's knobs over BASELINE config 3 shapes:
-tile geometry (KX_SCAN_GEOMETRY = ctas,stages,R), scheduling chunk (KX_SCHED_CHUNK), producer polling (KX_PROD_SLEEP)
-and the staging threshold (KX_AGG_STAGE).  Every combination must reproduce the default run's counts and integer
+"""tune_general.py — sweep the warp-autonomous (multi-leaf filter + fused reduce) kernel's knobs over BASELINE config 3 shapes:
+tile geometry (KX_WARP_GEOMETRY = wd,stages,warps), scheduling chunk (KX_SCHED_CHUNK) and the dense-tile threshold
+(KX_AGG_STAGE).  Every combination must reproduce the default run's counts and integer
 aggregates bit for bit (float sums: bit for bit as well — the lane/row assignment does not depend on the knobs'
 staging decision).  Used to choose the defaults in kx_api.cu (run_scan); not part of the product path.
 
@@ -35,7 +35,6 @@ def main():
     ap.add_argument("--npacks", type=int, default=256)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="default, dense-prefetch modes and the v2 kernel only")
-    ap.add_argument("--v2", action="store_true", help="sweep the older producer/consumer kernel (KX_GENERAL=v2) instead of the warp kernel")
     args = ap.parse_args()
     rng = np.random.default_rng(1)
     ctx = kb.Context(0)
@@ -96,16 +95,13 @@ def main():
         base_ms, base_sig = run(prog, aggs)
         print(f"{name:8s} default                                  {base_ms:8.4f} ms  {npacks * M1 / base_ms / 1e6:8.1f} Grows/s", flush=True)
         results.append({"case": name, "knobs": {}, "kernel_ms": base_ms})
-        if args.v2:
-            combos = [{"KX_GENERAL": "v2", "KX_SCAN_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(geos, chunks)]
-            combos += [{"KX_GENERAL": "v2", "KX_PROD_SLEEP": "1"}] + [{"KX_GENERAL": "v2", "KX_AGG_STAGE": a} for a in ("never", "always", "2", "5")]
-        else:
+        if True:
             wgeos = [None, "1,2,16", "1,3,16", "1,4,16", "2,2,16", "2,3,16", "2,2,12", "2,3,12", "4,2,16", "4,2,8", "2,2,8"]
             wchunks = ["1", "2", "4", "8", "16"]
             if args.quick:
                 wgeos, wchunks = [None, "1,2,16", "2,2,16", "2,3,12", "4,2,8"], ["4", "8", "16"]
             combos = [{"KX_WARP_GEOMETRY": g, "KX_SCHED_CHUNK": c} for g, c in itertools.product(wgeos, wchunks)]
-            combos += [{"KX_AGG_STAGE": a} for a in ("never", "always", "2", "5", "8")] + [{"KX_PROD_SLEEP": "1"}, {"KX_PROD_SLEEP": "2"}, {"KX_GENERAL": "v2"}]
+            combos += [{"KX_AGG_STAGE": a} for a in ("never", "always", "2", "5", "8")]
             if args.minimal:
                 combos = [{"KX_AGG_STAGE": "never"}, {"KX_AGG_STAGE": "5"}] + [{"KX_WARP_GEOMETRY": g} for g in ("2,2,11", "2,2,10", "2,2,8", "1,2,16", "1,3,16", "2,3,8")]
         for combo in combos:
