@@ -186,6 +186,15 @@ int kx_scan_select(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, in
 int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, uint8_t block_type,
               const uint32_t* sel, const uint64_t* sel_off, void* dst);
 
+/* StringContainer.AppendTo(dst, sel) for a batch of packs: the byte-string twin of kx_gather
+ * (internal/encode/string_{const,fixed,compact,dict}.go AppendTo with a selection; query/result.go:196-264 copies the
+ * selected rows of bytes columns like any other result column).  Row i of the selection (i < sel_off[npacks]) occupies
+ * out[out_off[i] .. out_off[i+1]); out_off has sel_off[npacks] + 1 entries.  If the rows hold more than out_cap bytes
+ * nothing is written to out, KX_ENOMEM is returned and out_off[sel_off[npacks]] holds the required capacity (the
+ * kx_scan_select convention; out may be NULL with out_cap = 0 to ask for the size). */
+int kx_gather_bytes(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field,
+                    const uint32_t* sel, const uint64_t* sel_off, uint64_t* out_off, uint8_t* out, size_t out_cap);
+
 /* Scan + TIME-BUCKETED reduce (group by time window): what a series query does with every streamed row —
  * t = Interval.TruncateRelative(ts, Range.From) picks the window, Bucket.Push feeds the window's reducer
  * (pkg/series/series.go:192-256, internal/reducer/bucket_native.go:104-167) — for the order-independent reducers

@@ -798,9 +798,9 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
                 code_leaf_words[l] = std::max(code_leaf_words[l], nw);
             }
             if (o.mode == LM_HASHSET) hash_leaf[l] = true;
-            if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET)) {
+            if (v.kind == CK_RUNEND && (o.mode == LM_VALRANGE || o.mode == LM_SET || o.mode == LM_RUNRANGE)) {
                 // run-end blocks: predicate per run in a pre-pass, the scan streams the resulting 1-bit column
-                rjobs.push_back(RunFillJob{v.data, v.aux, o.a, o.d, o.wm, leafbits_bytes, v.naux, v.n, o.mode == LM_SET ? 1u : 0u, 0});
+                rjobs.push_back(RunFillJob{v.data, v.aux, o.a, o.d, o.wm, leafbits_bytes, v.naux, v.n, o.mode == LM_SET ? 1u : (o.mode == LM_RUNRANGE ? 2u : 0u), 0});
                 rjob_leaf.push_back(size_t(p) * nl + l);
                 leafbits_bytes += round_up((size_t(v.n) + 7) / 8 + STREAM_PAD, 256);
                 max_runs = std::max(max_runs, v.naux);
@@ -1003,8 +1003,31 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
     if (const char* e = getenv("KX_SCHED_CHUNK")) sched_chunk = uint32_t(std::max(1, std::min(atoi(e), 64)));
     while (sched_chunk & (sched_chunk - 1)) sched_chunk &= sched_chunk - 1;   // a power of two (the kernel shifts)
     if (simple) sched_chunk = 1;
-    if (use_warp)   // small scans: smaller chunks first, so that every warp of the persistent grid gets work
+    if (use_warp) {   // small scans: smaller chunks first, so that every warp of the persistent grid gets work
         while (sched_chunk > 1 && total_rows / (uint64_t(tile_rows) * sched_chunk) < uint64_t(4) * ctx->num_sms * wg.warps) sched_chunk /= 2;
+        // the chunks are dealt round-robin to num_sms x warps pipelines, so the scan takes ceil(chunks / pipelines) rounds:
+        // with few rounds the last, partly filled one costs up to 1 / rounds of the run (128 packs x 1 Mi rows at 8 tiles per
+        // chunk: 3.46 -> 4 rounds, 13 % idle).  Halve the chunk while that removes more than the ~3 % a smaller chunk costs
+        // (one descriptor reload per chunk, profiles/r2_tune_warp.txt) — unless the caller pinned it
+        if (!getenv("KX_SCHED_CHUNK")) {
+            const uint64_t slots = uint64_t(ctx->num_sms) * wg.warps;
+            auto fill = [&](uint32_t c) {
+                uint64_t units = 0;
+                for (int p = 0; p < npacks; ++p) {
+                    const uint64_t tiles = (uint64_t(job.nrows[size_t(p)]) + tile_rows - 1) / tile_rows;
+                    units += (tiles + c - 1) / c;
+                }
+                const uint64_t rounds = (units + slots - 1) / slots;
+                return rounds ? double(units) / double(rounds * slots) : 1.0;
+            };
+            double f = fill(sched_chunk);
+            while (sched_chunk > 1 && f < 0.95) {
+                const double f2 = fill(sched_chunk / 2);
+                if (f2 < f + 0.03) break;
+                sched_chunk /= 2; f = f2;
+            }
+        }
+    }
     uint64_t ntiles64 = 0;
     std::vector<uint32_t> tile0(size_t(npacks) + 1);
     for (int p = 0; p < npacks; ++p) {
@@ -1749,6 +1772,64 @@ int kx_gather(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, 
                      reinterpret_cast<const uint32_t*>(d + off_sel), total, eb, d + off_dst, ctx->stream));
     CK(cudaMemcpyAsync(dst, d + off_dst, size_t(total) * eb, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));   // views / sel are host temporaries
+    return KX_OK;
+    });
+}
+
+int kx_gather_bytes(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t field, const uint32_t* sel, const uint64_t* sel_off,
+                    uint64_t* out_off, uint8_t* out, size_t out_cap) {
+    return kx_guarded<int>(ctx, [&]() -> int {
+    if (!ctx) return KX_EINVAL;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (npacks < 0 || (npacks && (!packs || !sel_off)) || !out_off) return fail(ctx, KX_EINVAL, "kx_gather_bytes: bad arguments");
+    out_off[0] = 0;
+    if (npacks == 0 || sel_off[npacks] == 0) return KX_OK;
+    if (!sel) return fail(ctx, KX_EINVAL, "kx_gather_bytes: null selection");
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t total = sel_off[npacks];
+    if (total >= 0xffffffffull) return fail(ctx, KX_EUNSUPPORTED, "kx_gather_bytes: more than 2^32 - 1 selected rows in one call");
+    std::vector<ColView> views(static_cast<size_t>(npacks));
+    for (int p = 0; p < npacks; ++p) {
+        auto it = ctx->store.find(BlockKey{packs[p].pack, packs[p].version, field});
+        if (it == ctx->store.end()) return fail(ctx, KX_ENOTFOUND, "kx_gather_bytes: block not resident: pack " + std::to_string(packs[p].pack));
+        const ColView& v = it->second.view;
+        if (v.kind != CK_STR) return fail(ctx, KX_EINVAL, "kx_gather_bytes: not a byte-string block");
+        if (sel_off[p + 1] < sel_off[p]) return fail(ctx, KX_EINVAL, "kx_gather_bytes: sel_off must ascend");
+        views[size_t(p)] = v;
+        for (uint64_t i = sel_off[p]; i < sel_off[p + 1]; ++i)
+            if (sel[i] >= v.n) return fail(ctx, KX_EINVAL, "kx_gather_bytes: row id " + std::to_string(sel[i]) + " outside pack " + std::to_string(packs[p].pack));
+    }
+    // device layout: views | sel_off | sel | offsets (total + 1, 32-bit) | grand total | bytes
+    const size_t off_so = round_up(sizeof(ColView) * size_t(npacks), 256), off_sel = off_so + round_up(8 * (size_t(npacks) + 1), 256);
+    const size_t off_len = off_sel + round_up(size_t(total) * 4, 256), off_tot = off_len + round_up((size_t(total) + 1) * 4, 256);
+    const size_t off_out = off_tot + 256;   // (off_tot: 64-bit byte total, + 8: the scan's own 32-bit-carried total, unused)
+    const size_t cap = size_t(std::min<uint64_t>(out_cap, 0xfffffffeull));
+    CK(ctx->d_tmp.reserve(off_out + cap + 64));
+    uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
+    const ColView* dviews = reinterpret_cast<const ColView*>(d);
+    const unsigned long long* dso = reinterpret_cast<const unsigned long long*>(d + off_so);
+    const uint32_t* dsel = reinterpret_cast<const uint32_t*>(d + off_sel);
+    uint32_t* dlen = reinterpret_cast<uint32_t*>(d + off_len);
+    CK(cudaMemcpyAsync(d, views.data(), sizeof(ColView) * size_t(npacks), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + off_so, sel_off, 8 * (size_t(npacks) + 1), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d + off_sel, sel, size_t(total) * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(launch_strgather_len(dviews, dso, uint32_t(npacks), dsel, total, dlen, reinterpret_cast<unsigned long long*>(d + off_tot), ctx->stream));
+    CK(launch_exclusive_scan(dlen, uint32_t(total), reinterpret_cast<unsigned long long*>(d + off_tot + 8), ctx->stream));
+    unsigned long long need = 0;
+    CK(cudaMemcpyAsync(&need, d + off_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> offs32(size_t(total));
+    if (need > 0xfffffffeull) return fail(ctx, KX_EUNSUPPORTED, "kx_gather_bytes: more than 4 GiB of row bytes in one call");
+    if (need > out_cap || (need && !out)) {   // like kx_scan_select: report the capacity the caller must bring
+        out_off[total] = need;
+        return fail(ctx, KX_ENOMEM, "kx_gather_bytes: the selected rows hold " + std::to_string(need) + " bytes");
+    }
+    CK(launch_strgather_copy(dviews, dso, uint32_t(npacks), dsel, total, dlen, d + off_out, ctx->stream));
+    CK(cudaMemcpyAsync(offs32.data(), dlen, size_t(total) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (need) CK(cudaMemcpyAsync(out, d + off_out, size_t(need), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint64_t i = 0; i < total; ++i) out_off[i] = offs32[size_t(i)];
+    out_off[total] = need;
     return KX_OK;
     });
 }

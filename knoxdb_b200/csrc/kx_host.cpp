@@ -466,6 +466,9 @@ int normalize_block(int type, const uint8_t* enc, size_t len, BlockLayout& out, 
         if (!decode_container(*c->child[0], out.aux64, err) || !decode_container(*c->child[1], ends, err)) return -6;
         out.aux32.assign(ends.begin(), ends.end());
         v.kind = CK_RUNEND; v.naux = uint32_t(ends.size());
+        // an affine Values child keeps its (For, Delta): the reference matches it with DeltaContainer's index arithmetic
+        // (int_runend.go:224-283 → int_delta.go:149-449), rounding quirk included — compile_leaf does the same over the runs
+        if (c->child[0]->ctype == T_DELTA && c->child[0]->n == ends.size()) { v.is_raw = 1; v.base = c->child[0]->val; v.delta = c->child[0]->delta; }
         return 0;
     }
     }
@@ -1059,6 +1062,16 @@ void compile_leaf(const ColView& v, const uint64_t* dict_host, const LeafSpec& l
         if (o.mode != LM_NONE && o.mode != LM_ALL) { o.data = v.data; o.width = v.width; }
         return;
     case CK_RUNEND:  // RunEndContainer.Match*: predicate on the run values, int_runend.go:224-318
+        if (v.is_raw) {
+            // Values is a DeltaContainer: its closed-form matchers pick a range of RUN indexes (LM_ROWRANGE over naux runs);
+            // the run pre-pass turns the runs of that range into rows (applyMatch, int_runend.go:296-318)
+            ColView dv{};
+            dv.kind = CK_DELTA; dv.type = v.type; dv.base = v.base; dv.delta = v.delta; dv.n = v.naux;
+            compile_delta(o, dv, mode, leaf.a, leaf.b);
+            if (o.mode == LM_ROWRANGE) o.mode = LM_RUNRANGE;
+            o.view = view_index;
+            return;
+        }
         compile_valrange(o, t, mode, leaf.a, leaf.b);
         return;
     }

@@ -44,7 +44,7 @@ struct CodesetJob {
 struct RunFillJob {
     const uint8_t* vals;   // u64 run values
     const uint8_t* ends;   // u32 inclusive run ends
-    uint64_t a, d, wm;     // LM_VALRANGE operands, or (set offset, set size) for LM_SET
+    uint64_t a, d, wm;     // LM_VALRANGE operands, (set offset, set size) for LM_SET, or (first run, runs - 1) for LM_RUNRANGE
     uint64_t out_off;      // byte offset of the leaf bitset
     uint32_t nruns, nrows;
     uint32_t is_set, pad;
@@ -59,6 +59,11 @@ struct StrJob {
     uint32_t mode, pad;    // types.FilterMode (EQ, NE, GT, GE, LT, LE, RANGE)
 };
 cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_rows, const uint8_t* pool, uint8_t* out_base, cudaStream_t stream);
+cudaError_t launch_strgather_len(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                                 uint32_t* lens, unsigned long long* nbytes, cudaStream_t stream);
+cudaError_t launch_strgather_copy(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                                  const uint32_t* offs, uint8_t* out, cudaStream_t stream);
+cudaError_t launch_exclusive_scan(uint32_t* v, uint32_t n, unsigned long long* total, cudaStream_t stream);
 
 // one leaf of valmatch_kernel: bit i of the leaf bitset at out_base + out_off = float predicate on the value decoded at row i
 // (ALP-RD blocks: FloatAlpRdContainer.Match*, internal/encode/float_alprd.go:181-211)

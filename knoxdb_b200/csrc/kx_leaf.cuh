@@ -444,7 +444,7 @@ __device__ __forceinline__ uint32_t leaf_runend(const PackLeaf& L, const ColView
     while (r < rend && k < v.naux) {
         uint32_t hi = min(__ldg(ends + k), rend - 1u);     // inclusive
         uint64_t val = __ldg(vals + k);
-        bool p = (L.mode == LM_SET) ? set_has(sets + L.a, (uint32_t)L.d, val) : ((val ^ L.wm) - L.a) <= L.d;
+        bool p = (L.mode == LM_SET) ? set_has(sets + L.a, (uint32_t)L.d, val) : (L.mode == LM_RUNRANGE) ? ((uint64_t)k - L.a) <= L.d : ((val ^ L.wm) - L.a) <= L.d;
         if (p) word |= (0xffffffffu >> (31u - (hi - grow0))) & (0xffffffffu << (r - grow0));
         r = hi + 1u; ++k;
     }

@@ -84,7 +84,8 @@ __global__ void runfill_kernel(const RunFillJob* __restrict__ jobs, uint32_t njo
     uint32_t* out = reinterpret_cast<uint32_t*>(out_base + J.out_off);
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < J.nruns; k += gridDim.x * blockDim.x) {
         uint64_t val = __ldg(vals + k);
-        bool p = J.is_set ? set_has(set_vals + J.a, (uint32_t)J.d, val) : ((val ^ J.wm) - J.a) <= J.d;
+        bool p = J.is_set == 2u ? ((uint64_t)k - J.a) <= J.d   // affine run values: the closed form chose a range of runs
+                 : J.is_set ? set_has(set_vals + J.a, (uint32_t)J.d, val) : ((val ^ J.wm) - J.a) <= J.d;
         if (!p) continue;
         uint32_t start = k ? __ldg(ends + k - 1) + 1u : 0u, end = __ldg(ends + k);   // inclusive
         if (end >= J.nrows) end = J.nrows - 1u;
@@ -705,6 +706,10 @@ cudaError_t launch_s8b_pack(const void* words, uint32_t nwords, const uint32_t* 
     if (nwords == 0 || width == 0) return cudaSuccess;
     s8b_pack_kernel<<<(nwords + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const unsigned long long*>(words), nwords, offs, nrows, width,
                                                             reinterpret_cast<unsigned long long*>(out));
+    return cudaGetLastError();
+}
+cudaError_t launch_exclusive_scan(uint32_t* v, uint32_t n, unsigned long long* total, cudaStream_t stream) {
+    exclusive_scan_kernel<<<1, 1024, 0, stream>>>(v, n, total);
     return cudaGetLastError();
 }
 cudaError_t launch_decode(const ColView& v, void* dst, cudaStream_t stream) {

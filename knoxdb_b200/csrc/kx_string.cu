@@ -107,6 +107,72 @@ __global__ void __launch_bounds__(256, 8) strmatch_kernel(const StrJob* __restri
   }
 }
 
+// (offset, length) of row `row` of a string block inside its byte buffer
+__device__ __forceinline__ void str_row(const ColView& v, uint32_t row, uint32_t& ofs, uint32_t& len) {
+    const uint32_t* idx = reinterpret_cast<const uint32_t*>(v.aux);
+    switch (v.is_raw) {
+    case STR_FIXED: len = (uint32_t)v.delta; ofs = row * len; break;
+    case STR_COMPACT: ofs = __ldg(idx + row); len = __ldg(idx + v.n + row); break;
+    case STR_DICT: { const uint32_t c = __ldg(idx + row); ofs = __ldg(idx + v.n + c); len = __ldg(idx + v.n + v.naux + c); break; }
+    default: ofs = 0; len = (uint32_t)v.delta; break;   // STR_CONST
+    }
+}
+
+// StringContainer.AppendTo(dst, sel) for a batch of packs (internal/encode/string_{const,fixed,compact,dict}.go AppendTo with
+// a selection; query/result.go:196-264 copies the selected rows of bytes columns like any other result column).
+// Pass 1: one thread per selected row writes the row's length; an exclusive scan turns the lengths into offsets;
+// pass 2: one WARP per selected row copies its bytes (lane-strided: coalesced for long rows, one transaction for short ones).
+__global__ void strgather_len_kernel(const ColView* __restrict__ views, const unsigned long long* __restrict__ sel_off, uint32_t npacks,
+                                     const uint32_t* __restrict__ sel, uint64_t total, uint32_t* __restrict__ lens,
+                                     unsigned long long* __restrict__ nbytes) {
+    unsigned long long mine = 0;   // 64-bit grand total beside the 32-bit offsets (a selection of 4 GiB or more is refused, not wrapped)
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t lo = 0, hi = npacks;   // last pack with sel_off <= i
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sel_off[m] <= i) lo = m; else hi = m; }
+        uint32_t ofs, len;
+        str_row(views[lo], sel[i], ofs, len);
+        lens[i] = len;
+        mine += len;
+    }
+    for (int off = 16; off > 0; off >>= 1) mine += __shfl_down_sync(0xffffffffu, mine, off);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(nbytes, mine);
+}
+
+__global__ void strgather_copy_kernel(const ColView* __restrict__ views, const unsigned long long* __restrict__ sel_off, uint32_t npacks,
+                                      const uint32_t* __restrict__ sel, uint64_t total, const uint32_t* __restrict__ offs, uint8_t* __restrict__ out) {
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint64_t warps = ((uint64_t)gridDim.x * blockDim.x) >> 5;
+    for (uint64_t i = (blockIdx.x * (uint64_t)blockDim.x + threadIdx.x) >> 5; i < total; i += warps) {
+        uint32_t lo = 0, hi = npacks;
+        while (hi - lo > 1) { uint32_t m = (lo + hi) >> 1; if (sel_off[m] <= i) lo = m; else hi = m; }
+        const ColView& v = views[lo];
+        uint32_t ofs, len;
+        str_row(v, sel[i], ofs, len);
+        const uint8_t* src = v.data + ofs;
+        uint8_t* dst = out + offs[i];
+        for (uint32_t b = lane; b < len; b += 32u) dst[b] = src[b];
+    }
+}
+
+cudaError_t launch_strgather_len(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                                 uint32_t* lens, unsigned long long* nbytes, cudaStream_t stream) {
+    cudaError_t e = cudaMemsetAsync(nbytes, 0, 8, stream);
+    if (e != cudaSuccess || total == 0) return e;
+    uint64_t g = (total + 255u) / 256u;
+    if (g > 148u * 16u) g = 148u * 16u;
+    strgather_len_kernel<<<(unsigned)g, 256, 0, stream>>>(views, sel_off, npacks, sel, total, lens, nbytes);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_strgather_copy(const ColView* views, const unsigned long long* sel_off, uint32_t npacks, const uint32_t* sel, uint64_t total,
+                                  const uint32_t* offs, uint8_t* out, cudaStream_t stream) {
+    if (total == 0) return cudaSuccess;
+    uint64_t g = (total + 7u) / 8u;   // 8 warps per block, one row per warp and step
+    if (g > 148u * 16u) g = 148u * 16u;
+    strgather_copy_kernel<<<(unsigned)g, 256, 0, stream>>>(views, sel_off, npacks, sel, total, offs, out);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_strmatch(const StrJob* jobs, uint32_t njobs, uint32_t max_rows, const uint8_t* pool, uint8_t* out_base, cudaStream_t stream) {
     if (njobs == 0 || max_rows == 0) return cudaSuccess;
     uint32_t gx = (max_rows + 256u * 8u - 1u) / (256u * 8u);   // ~8 groups per warp

@@ -77,6 +77,8 @@ enum LeafMode : uint8_t {
     LM_HASHSET = 9,   // staged integer stream: T(field + base) looked up in the leaf's bucketised hash table
     LM_BITS = 10,     // staged stream IS the leaf's bitset, 1 bit per row (run-end blocks: filled per run by
                       // runfill_kernel right before the scan)
+    LM_RUNRANGE = 11, // run-end block whose run values are affine: RUN index in [a, a + d] (host-side only: becomes a
+                      // runfill_kernel job and then LM_BITS)
 };
 
 struct PackLeaf {

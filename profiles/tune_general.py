@@ -35,6 +35,7 @@ def main():
     ap.add_argument("--npacks", type=int, default=256)
     ap.add_argument("--quick", action="store_true")
     ap.add_argument("--minimal", action="store_true", help="default, dense-prefetch modes and the v2 kernel only")
+    ap.add_argument("--chunks-only", action="store_true", help="default (chunk chosen by run_scan) against pinned KX_SCHED_CHUNK values")
     args = ap.parse_args()
     rng = np.random.default_rng(1)
     ctx = kb.Context(0)
@@ -104,6 +105,8 @@ def main():
             combos += [{"KX_AGG_STAGE": a} for a in ("never", "always", "2", "5", "8")]
             if args.minimal:
                 combos = [{"KX_AGG_STAGE": "never"}, {"KX_AGG_STAGE": "5"}] + [{"KX_WARP_GEOMETRY": g} for g in ("2,2,11", "2,2,10", "2,2,8", "1,2,16", "1,3,16", "2,3,8")]
+        if args.chunks_only:
+            combos = [{"KX_SCHED_CHUNK": c} for c in ("1", "2", "4", "8", "16")]
         for combo in combos:
             for k in KNOBS:
                 os.environ.pop(k, None)

@@ -167,6 +167,12 @@ long kxh_match(int block_type, const uint8_t* enc, size_t len, int mode, uint64_
             break;
         }
         case LM_VALRANGE: p = ((hb.value(row) ^ L.wm) - L.a) <= L.d; break;
+        case LM_RUNRANGE: {   // runfill_kernel: the run that holds the row lies in the range of runs the closed form chose
+            size_t lo = 0, hi = hb.lay.aux32.size();
+            while (lo < hi) { size_t m = (lo + hi) / 2; if (hb.lay.aux32[m] >= row) hi = m; else lo = m + 1; }
+            p = (uint64_t(lo) - L.a) <= L.d;
+            break;
+        }
         }
         if (L.neg && L.mode != LM_NONE && L.mode != LM_ALL) p = !p;
         if (L.fixmode) {   // ALP patch correction (alpfix_kernel + the fix stage of scan_kernel)

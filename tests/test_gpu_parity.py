@@ -127,10 +127,7 @@ def test_container_match_and_decode(ctx, t):
                     for op in kt.OPS:
                         want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
                         got, cnt = ctx.container_match(t, blob, op, a, b, nrows=n)
-                        if not (got == want).all():
-                            if op == ko.RG and oc.ctype == ko.TRUNEND and oc.value_delta_sequences():
-                                want = kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](b)))
-                            assert (got == want).all(), (ko.NP[t].__name__, n, name, kind, op, a, b)
+                        assert (got == want).all(), (ko.NP[t].__name__, n, name, kind, op, a, b)
                         assert cnt == int(np.unpackbits(got).sum())
                 setv = np.unique(np.concatenate([vals[: min(3, n)], kt.typed_rand(RNG, t, 3)]))
                 su = ko.as_u64(t, setv)
@@ -187,6 +184,56 @@ def test_run_end_blocks_of_every_run_length(ctx):
         su = ko.as_u64(ko.I64, np.array([-3, 7, 11, 49], dtype=np.int64))
         got, _ = ctx.container_match(ko.I64, blob, ko.IN, values=su, nrows=n)
         assert (got == oc.match_set(su)).all(), (n, lens, "in")
+
+
+def test_run_end_blocks_with_affine_run_values_follow_the_delta_matchers(ctx):
+    """A run-end block whose Values child is a DeltaContainer (block heights with several rows each): the reference
+    matches the child with DeltaContainer's closed-form index arithmetic (int_runend.go:224-283 → int_delta.go:149-449),
+    including MatchBetween's rounding quirk for ranges that start below For between grid points.  The product does the
+    same arithmetic over the RUNS (LM_RUNRANGE → run-fill pre-pass); bit for bit against the oracle, through the narrow
+    drop-in and through a two-leaf scan with aggregates."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(33)
+    for t, base, delta, nruns in ((ko.I64, 100, 10, 23), (ko.U64, 1000, 3, 4000), (ko.I32, -50, 4, 700), (ko.I64, -10**12, 977, 9000)):
+        runs = (base + delta * np.arange(nruns)).astype(ko.NP[t])
+        vals = np.repeat(runs, rng.integers(1, 70, nruns))
+        n = len(vals)
+        blob = ko.store("runend", t, vals)
+        oc = ko.Container(t, blob)
+        assert oc.ctype == ko.TRUNEND and oc.value_delta_sequences()
+        lo_all, hi_all = int(runs.min()), int(runs.max())
+        quirk_hits = 0
+        for a in np.unique(np.r_[lo_all - 2 * delta - 1, lo_all - 1, lo_all, rng.integers(lo_all - 3 * delta, hi_all + 3 * delta, 12)]):
+            a = int(a)
+            if t == ko.U64 and a < 0:
+                continue
+            for b in (a, a + 5, a + 37 * delta + 1, hi_all + 50):
+                for op in kt.OPS:
+                    want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                    got, cnt = ctx.container_match(t, blob, op, a, b, nrows=n)
+                    assert (got == want).all(), (ko.NP[t].__name__, delta, op, a, b)
+                    assert cnt == int(np.unpackbits(want).sum())
+                    if op == ko.RG and not (want == kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](b)))).all():
+                        quirk_hits += 1
+        assert quirk_hits > 0
+    # the same block as one leaf of a scan: height BETWEEN (quirk domain) AND amount < 0 → count + sum(amount)
+    t, base, delta, nruns = ko.I64, 100, 10, 5000
+    vals = np.repeat((base + delta * np.arange(nruns)).astype(np.int64), rng.integers(1, 40, nruns))
+    n = len(vals)
+    amount = rng.integers(-10**6, 10**6, n).astype(np.int64)
+    hb = ko.store("runend", ko.I64, vals)
+    ctx.block_put(950, 1, 1, kb.INT64, hb)
+    ctx.block_put(950, 1, 2, kb.INT64, ko.store("best", ko.I64, amount))
+    prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, 95, 30_004), kb.Leaf(2, kb.INT64, kb.LT, 0)])
+    res = ctx.scan(prog, [(950, 1)], nrows=[n], want_bitsets=True, aggs=[(2, kb.INT64)])
+    want = ko.tree_eval([0, 1, 0xFE], [ko.Container(ko.I64, hb).match(ko.RG, 95, 30_004), kt.pack_bits(amount < 0)], n)
+    assert (res["bitsets"][0] == want).all()
+    st = ko.reduce(ko.I64, amount, want, None)
+    g = res["aggs"][0]
+    assert (g.count, g.sum_bits, g.min_bits, g.max_bits) == (st.count, st.sum_bits, st.min_bits, st.max_bits) and st.count > 100
+    assert not kt.unpack_bits(want, n)[0] and vals[0] == 100   # the quirk: row 0 (height 100 >= 95) is dropped, as in the reference
+    prog.close()
+    ctx.block_drop(950, 1, 1); ctx.block_drop(950, 1, 2)
 
 
 def test_bitset_ops(ctx):
@@ -740,6 +787,52 @@ def test_prune_zone_maps_and_bloom(ctx):
     bits2, n2 = ctx.prune(prog, mins.view(np.uint64), maxs.view(np.uint64))
     assert n2 >= nsurv and kt.unpack_bits(bits2, npacks)[417]
     prog.close()
+
+
+def test_string_zone_maps_are_scans_over_the_min_max_blocks(ctx):
+    """Zone maps of byte-string columns.  The reference keeps a stats pack's per-pack minima and maxima as two string BLOCKS
+    and prunes by running ordinary string matchers over them (`bytes*Matcher.MatchRangeVectors`,
+    internal/operator/filter/match_bytes.go:97-110 EQ, :165-175 GT / GE on maxs, :215-225 LT / LE on mins, :282-296 RANGE,
+    :424-429 IN via the set's min / max): candidate packs = `mins LE hi AND maxs GE lo`.  The same call sequence through the
+    C ABI: the two blocks are registered like any string block (row = data pack) and ONE two-leaf scan returns the
+    candidate bitset; checked against Python's bytes ordering (= bytes.Compare) and against the packs' real rows (a zone
+    map may keep too many packs, never too few)."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(21)
+    npacks = 3000
+    # sorted "address" table cut into packs of 1..40 rows: adjacent, occasionally overlapping [min, max] ranges
+    rows = sorted(bytes(rng.integers(97, 123, int(k), dtype=np.uint8)) for k in rng.integers(1, 24, 40 * npacks))
+    cuts = np.sort(rng.choice(np.arange(1, len(rows)), npacks - 1, replace=False))
+    packs = [rows[a:b] for a, b in zip(np.r_[0, cuts], np.r_[cuts, len(rows)])]
+    mins, maxs = [p[0] for p in packs], [p[-1] for p in packs]
+    for kind in (ko.STR_COMPACT, ko.STR_DICT):
+        bmin, bmax = ko.store_str(kind, mins), ko.store_str(kind, maxs)
+        if bmin is None or bmax is None:
+            continue
+        assert ctx.block_put(900, 1, 1, kb.BYTES, bmin) == npacks and ctx.block_put(900, 1, 2, kb.BYTES, bmax) == npacks
+
+        def candidates(lo, hi):
+            prog = kb.Program(ctx, [kb.Leaf(1, kb.BYTES, kb.LE, hi), kb.Leaf(2, kb.BYTES, kb.GE, lo)])
+            res = ctx.scan(prog, [(900, 1)], nrows=[npacks], want_bitsets=True)
+            prog.close()
+            return kt.unpack_bits(res["bitsets"][0], npacks), int(res["counts"][0])
+
+        probes = [packs[1234][len(packs[1234]) // 2], packs[0][0], packs[-1][-1], b"", b"zzzzzzzzzzzzzzzzzzzzzzzzzzzz", packs[77][0] + b"\x00"]
+        for v in probes:                                    # bytesEqualMatcher.MatchRangeVectors
+            got, cnt = candidates(v, v)
+            want = np.fromiter((mn <= v <= mx for mn, mx in zip(mins, maxs)), dtype=bool, count=npacks)
+            assert (got == want).all() and cnt == int(want.sum())
+            holds = np.fromiter((v in p for p in packs), dtype=bool, count=npacks)
+            assert not (holds & ~got).any()                 # no pack that holds the value is pruned
+        for lo, hi in ((b"d", b"f"), (b"kx", b"kxzz"), (b"", b"a"), (b"q", b"b")):   # bytesRangeMatcher.MatchRangeVectors
+            got, cnt = candidates(lo, hi)
+            want = np.fromiter((mn <= hi and mx >= lo for mn, mx in zip(mins, maxs)), dtype=bool, count=npacks)
+            assert (got == want).all() and cnt == int(want.sum())
+        members = [packs[5][0], packs[2500][-1], b"mmm"]    # bytesInSetMatcher.MatchRangeVectors: the set's min / max as a range
+        got, _ = candidates(min(members), max(members))
+        for m in members:
+            assert not (np.fromiter((m in p for p in packs), dtype=bool, count=npacks) & ~got).any()
+        ctx.block_drop(900, 1, 1); ctx.block_drop(900, 1, 2)
 
 
 def test_agg_combine_matches_single_scan(ctx):

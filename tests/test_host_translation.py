@@ -29,14 +29,9 @@ def test_leaf_translation_matches_oracle(t):
                         want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
                         got, mode = kt.host_match(t, blob, n, op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
                         modes_seen.add(mode)
+                        # (run-end blocks whose Values child is affine inherit DeltaContainer.MatchBetween's rounding quirk
+                        # in the reference: the product matches such blocks with the same index arithmetic over the runs)
                         if not (got == want).all():
-                            # run-end blocks whose Values child is an affine container inherit the
-                            # reference's MatchBetween rounding quirk; the product
-                            # evaluates the scalar predicate on run values there
-                            if op == ko.RG and oc.ctype == ko.TRUNEND and oc.value_delta_sequences():
-                                truth = kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](b)))
-                                assert (got == truth).all(), (name, kind, op, a, b)
-                                continue
                             raise AssertionError((ko.NP[t].__name__, n, name, kind, op, a, b, mode))
                 setv = np.unique(np.concatenate([vals[: min(3, n)], kt.typed_rand(RNG, t, 3)]))
                 su = ko.as_u64(t, setv)
@@ -51,6 +46,33 @@ def test_delta_quirk_is_reproduced():
     blob = ko.store("delta", ko.I64, base=100, delta=10, n=8)
     got, _ = kt.host_match(ko.I64, blob, 8, ko.RG, 95, 135)
     assert got.tolist() == ko.Container(ko.I64, blob).match(ko.RG, 95, 135).tolist() == [0b00001110]
+
+
+def test_delta_quirk_is_reproduced_under_run_end_blocks():
+    """RunEndContainer.Match* hands the predicate to its Values child (int_runend.go:224-283); an affine child answers with
+    DeltaContainer's index arithmetic over the RUNS, quirk included: run values 100, 110, … with ranges that start below For
+    and between grid points, for every operator (the encoder picks a delta child for positive steps only)."""
+    for t, base, delta in ((ko.I64, 100, 10), (ko.U64, 1000, 3), (ko.I32, -50, 4), (ko.I64, -10**12, 977)):
+        nruns = 23
+        runs = (base + delta * np.arange(nruns)).astype(ko.NP[t])
+        lens = RNG.integers(1, 9, nruns)
+        vals = np.repeat(runs, lens)
+        blob = ko.store("runend", t, vals)
+        oc = ko.Container(t, blob)
+        assert oc.ctype == ko.TRUNEND and oc.value_delta_sequences(), "the encoder must pick an affine Values child here"
+        lo_all, hi_all = int(runs.min()), int(runs.max())
+        quirk_hits = 0
+        for a in range(lo_all - 2 * abs(delta) - 1, hi_all + 2 * abs(delta) + 2, 3):
+            if t == ko.U64 and a < 0:
+                continue
+            for b in (a, a + 5, a + 37, hi_all + 50):
+                for op in kt.OPS:
+                    want = oc.match(op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                    got, _ = kt.host_match(t, blob, len(vals), op, ko.scalar_u64(t, a), ko.scalar_u64(t, b))
+                    assert (got == want).all(), (ko.NP[t].__name__, delta, op, a, b)
+                    if op == ko.RG and not (want == kt.pack_bits(kt.OPS[op](vals, ko.NP[t](a), ko.NP[t](min(b, np.iinfo(ko.NP[t]).max))))).all():
+                        quirk_hits += 1
+        assert quirk_hits > 0   # the sweep really entered the quirk domain
 
 
 @pytest.mark.parametrize("w", [0, 1, 7, 8, 13, 20, 31, 32, 33, 47, 63, 64])
