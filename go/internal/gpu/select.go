@@ -52,3 +52,31 @@ func (c *Context) Gather(keys, versions []uint32, field uint16, t types.BlockTyp
 	}
 	return nil
 }
+
+// GatherBytes is StringContainer.AppendTo(dst, sel) for a batch of packs: the byte-string twin of Gather
+// (internal/encode/string_{const,fixed,compact,dict}.go AppendTo with a selection).  Row i of the selection is
+// buf[offs[i]:offs[i+1]]; the first call asks the library for the size (KX_ENOMEM convention of kx_scan_select).
+func (c *Context) GatherBytes(keys, versions []uint32, field uint16, sel []uint32, off []uint64) (buf []byte, offs []uint64, err error) {
+	refs := make([]C.kx_packref, len(keys))
+	for i := range refs {
+		refs[i] = C.kx_packref{pack: C.uint32_t(keys[i]), version: C.uint32_t(versions[i])}
+	}
+	offs = make([]uint64, len(sel)+1)
+	if len(sel) == 0 || len(refs) == 0 {
+		return nil, offs, nil
+	}
+	capacity := 0
+	for {
+		buf = make([]byte, max(capacity, 1))
+		rc := C.kx_gather_bytes(c.h, &refs[0], C.int(len(refs)), C.uint16_t(field), (*C.uint32_t)(unsafe.SliceData(sel)),
+			(*C.uint64_t)(unsafe.SliceData(off)), (*C.uint64_t)(unsafe.SliceData(offs)), (*C.uint8_t)(unsafe.SliceData(buf)), C.size_t(capacity))
+		if rc == C.KX_ENOMEM && int(offs[len(sel)]) > capacity {
+			capacity = int(offs[len(sel)])
+			continue
+		}
+		if rc != 0 {
+			return nil, nil, c.err()
+		}
+		return buf[:offs[len(sel)]], offs, nil
+	}
+}

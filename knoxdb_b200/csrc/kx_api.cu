@@ -1802,9 +1802,9 @@ int kx_gather_bytes(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t f
     // device layout: views | sel_off | sel | offsets (total + 1, 32-bit) | grand total | bytes
     const size_t off_so = round_up(sizeof(ColView) * size_t(npacks), 256), off_sel = off_so + round_up(8 * (size_t(npacks) + 1), 256);
     const size_t off_len = off_sel + round_up(size_t(total) * 4, 256), off_tot = off_len + round_up((size_t(total) + 1) * 4, 256);
-    const size_t off_out = off_tot + 256;   // (off_tot: 64-bit byte total, + 8: the scan's own 32-bit-carried total, unused)
-    const size_t cap = size_t(std::min<uint64_t>(out_cap, 0xfffffffeull));
-    CK(ctx->d_tmp.reserve(off_out + cap + 64));
+    // (off_tot: 64-bit byte total, + 8: the scan's own 32-bit-carried total, unused); the bytes go to a second scratch buffer
+    // that is sized once the total is known
+    CK(ctx->d_tmp.reserve(off_tot + 256));
     uint8_t* d = static_cast<uint8_t*>(ctx->d_tmp.p);
     const ColView* dviews = reinterpret_cast<const ColView*>(d);
     const unsigned long long* dso = reinterpret_cast<const unsigned long long*>(d + off_so);
@@ -1818,15 +1818,17 @@ int kx_gather_bytes(kx_ctx* ctx, const kx_packref* packs, int npacks, uint16_t f
     unsigned long long need = 0;
     CK(cudaMemcpyAsync(&need, d + off_tot, 8, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    std::vector<uint32_t> offs32(size_t(total));
+    std::vector<uint32_t> offs32(static_cast<size_t>(total));
     if (need > 0xfffffffeull) return fail(ctx, KX_EUNSUPPORTED, "kx_gather_bytes: more than 4 GiB of row bytes in one call");
     if (need > out_cap || (need && !out)) {   // like kx_scan_select: report the capacity the caller must bring
         out_off[total] = need;
         return fail(ctx, KX_ENOMEM, "kx_gather_bytes: the selected rows hold " + std::to_string(need) + " bytes");
     }
-    CK(launch_strgather_copy(dviews, dso, uint32_t(npacks), dsel, total, dlen, d + off_out, ctx->stream));
+    CK(ctx->d_leafbits.reserve(size_t(need) + 64));
+    uint8_t* dout = static_cast<uint8_t*>(ctx->d_leafbits.p);
+    CK(launch_strgather_copy(dviews, dso, uint32_t(npacks), dsel, total, dlen, dout, ctx->stream));
     CK(cudaMemcpyAsync(offs32.data(), dlen, size_t(total) * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    if (need) CK(cudaMemcpyAsync(out, d + off_out, size_t(need), cudaMemcpyDeviceToHost, ctx->stream));
+    if (need) CK(cudaMemcpyAsync(out, dout, size_t(need), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (uint64_t i = 0; i < total; ++i) out_off[i] = offs32[size_t(i)];
     out_off[total] = need;
@@ -1873,7 +1875,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
     CK(cudaEventRecord(e0, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copy_stream, e0, 0));   // uploads do not overtake earlier work on the context's stream
 
-    struct HostBatch { int p0 = 0, p1 = 0; std::vector<BlockLayout> lays; };
+    struct HostBatch { int p0 = 0, p1 = 0; std::vector<BlockLayout> lays; std::vector<std::vector<uint8_t>> cstr; /* values of constant string blocks */ };
     HostBatch slots[2];
     DevBuf* dstage[2] = {&ctx->d_stage, &ctx->d_stage2};
     PinBuf* haux[2] = {&ctx->h_aux, &ctx->h_aux2};
@@ -1893,6 +1895,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         // pass 1: parse headers, lay the batch out in the staging arena (256 B aligned streams)
         B.lays.clear();
         B.lays.resize(size_t(nb) * nfields);
+        B.cstr.assign(size_t(nb) * nfields, {});
         std::vector<BlockLayout>& lays = B.lays;
         std::vector<size_t> off_stream(lays.size(), 0), off_a64(lays.size(), 0), off_a32(lays.size(), 0), off_blob(lays.size(), 0), aux_src(lays.size(), 0);
         size_t dev_bytes = 0, aux_bytes = 0;
@@ -1900,7 +1903,18 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             for (int f = 0; f < nfields; ++f) {
                 size_t bi = size_t(p0 + p) * nfields + f, li = size_t(p) * nfields + f;
                 std::string err;
-                int rc2 = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lays[li], err);
+                int rc2;
+                if (field_types[f] == KX_BYTES) {
+                    // byte-string block: the byte buffer travels verbatim like a packed stream, the flat index array like run ends
+                    StrLayout sl2;
+                    rc2 = normalize_string_block(static_cast<const uint8_t*>(blocks[bi]), block_len[bi], sl2, err);
+                    if (!rc2) {
+                        lays[li].view = sl2.view; lays[li].stream = sl2.bytes; lays[li].stream_len = sl2.nbytes; lays[li].aux32 = std::move(sl2.idx);
+                        if (sl2.view.is_raw == STR_CONST) B.cstr[li].assign(sl2.bytes, sl2.bytes + sl2.nbytes);
+                    }
+                } else {
+                    rc2 = normalize_block(field_types[f], static_cast<const uint8_t*>(blocks[bi]), block_len[bi], lays[li], err);
+                }
                 if (rc2) return fail(ctx, rc2, "kx_scan_host: " + err);
                 BlockLayout& lay = lays[li];
                 if (lay.owned.empty() && lay.stream_len) { off_stream[li] = dev_bytes; dev_bytes += round_up(lay.stream_len + STREAM_PAD, 256); }
@@ -1952,6 +1966,7 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
             if ((v.kind == CK_ALP || v.kind == CK_ALPRD) && !lay.blob.empty()) v.aux = dbase + off_blob[li];
             if (v.kind == CK_DICT) v.aux = dbase + off_a64[li];
             if (v.kind == CK_RUNEND) { v.data = dbase + off_a64[li]; v.aux = dbase + off_a32[li]; }
+            if (v.kind == CK_STR) { v.data = dbase + off_stream[li]; v.aux = dbase + off_a32[li]; }
         }
         CK(cudaEventRecord(ctx->ev_copy[sl], cs));
         return KX_OK;
@@ -1965,11 +1980,13 @@ int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks, const uint16_t* f
         ScanJob job; job.npacks = nb;
         job.nrows.resize(size_t(nb)); job.leaf_views.resize(size_t(nb) * nleaves); job.leaf_dicts.resize(size_t(nb) * nleaves);
         job.agg_views.resize(size_t(nb) * size_t(naggs));
+        job.leaf_cstr.assign(size_t(nb) * nleaves, nullptr);
         for (int p = 0; p < nb; ++p) {
             job.nrows[size_t(p)] = lays[size_t(p) * nfields].view.n;
             for (int l = 0; l < nleaves; ++l) {
                 const BlockLayout& lay = lays[size_t(p) * nfields + leaf_fi[size_t(l)]];
                 job.leaf_views[size_t(p) * nleaves + l] = lay.view;
+                if (lay.view.kind == CK_STR && lay.view.is_raw == STR_CONST) job.leaf_cstr[size_t(p) * nleaves + l] = &B.cstr[size_t(p) * nfields + leaf_fi[size_t(l)]];
                 job.leaf_dicts[size_t(p) * nleaves + l] = (lay.view.kind == CK_DICT && !lay.aux64.empty()) ? lay.aux64.data() : nullptr;
             }
             for (int j = 0; j < naggs; ++j) job.agg_views[size_t(p) * naggs + j] = lays[size_t(p) * nfields + agg_fi[size_t(j)]].view;

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "kx_agg_combine", "kx_last_scan_stats", "kx_cmp", "kx_bitpack_cmp", "kx_bitpack_decode", "kx_container_match",
     "kx_container_decode", "kx_bitset_op", "kx_bitset_neg", "kx_bitset_popcount", "kx_bitset_indexes", "kx_prune",
     "kx_hash_value", "kx_hash_bytes",
-    "kx_scan_select", "kx_gather", "kx_scan_buckets",
+    "kx_scan_select", "kx_gather", "kx_gather_bytes", "kx_scan_buckets",
     "kx_stats_create", "kx_stats_free", "kx_stats_put_bloom", "kx_stats_build_bloom", "kx_stats_get_bloom", "kx_prune_stats",
     "kx_scan_ex", "kx_debug_check_guards", "kx_last_query_stats", "kx_comm_unique_id", "kx_comm_init", "kx_comm_info", "kx_scan_sharded", "kx_comm_allgather",
 ]
@@ -123,6 +123,7 @@ def lib():
         "kx_scan_buckets": (C.c_int, [vp, vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, C.c_int, C.POINTER(_AggReq), C.c_int, vp,
                                       C.POINTER(AggOut), vp, vp]),
         "kx_gather": (C.c_int, [vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, C.c_uint8, vp, vp, vp]),
+        "kx_gather_bytes": (C.c_int, [vp, C.POINTER(_PackRef), C.c_int, C.c_uint16, vp, vp, vp, vp, C.c_size_t]),
         "kx_scan_host": (C.c_int, [vp, vp, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp, vp, C.POINTER(_AggReq), C.c_int, C.POINTER(AggOut)]),
         "kx_agg_combine": (C.c_int, [C.c_uint8, C.POINTER(AggOut), C.c_int, C.POINTER(AggOut)]),
         "kx_last_scan_stats": (C.c_int, [vp, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -480,6 +481,25 @@ class Context:
         self._check(lib().kx_gather(self.h, refs, len(refs), field, block_type, _ptr(sel), _ptr(sel_off), _ptr(raw)))
         check_guard(raw)
         return out
+
+    def gather_bytes(self, packs, field, sel, sel_off, capacity=None):
+        """kx_gather_bytes: the byte strings of `field` at the selected rows, in pack order (a list of bytes objects).
+        capacity=None asks the library for the size first (the KX_ENOMEM convention of kx_scan_select)."""
+        refs = packs if isinstance(packs, C.Array) else self.pack_refs(packs)
+        sel = np.ascontiguousarray(sel, dtype=np.uint32)
+        sel_off = np.ascontiguousarray(sel_off, dtype=np.uint64)
+        total = int(sel_off[-1])
+        offs = np.zeros(total + 1, dtype=np.uint64)
+        if capacity is None:
+            rc = lib().kx_gather_bytes(self.h, refs, len(refs), field, _ptr(sel), _ptr(sel_off), _ptr(offs), None, 0)
+            if rc not in (0, -3):   # KX_ENOMEM: offs[total] holds the required capacity
+                self._check(rc)
+            capacity = int(offs[total])
+        out, raw = guarded(capacity)
+        self._check(lib().kx_gather_bytes(self.h, refs, len(refs), field, _ptr(sel), _ptr(sel_off), _ptr(offs), _ptr(raw), capacity))
+        check_guard(raw)
+        buf = out.tobytes()
+        return [buf[int(offs[i]):int(offs[i + 1])] for i in range(total)]
 
     def scan_host(self, prog, fields, blocks, nrows=None, want_bitsets=False, want_counts=True, aggs=(), bitset_buf=None):
         """fields: [(field id, block type)]; blocks: per pack a list of encoded blocks (np.uint8 arrays) per field."""

@@ -690,6 +690,93 @@ def test_string_blocks_match_row_by_row(ctx, shape):
             ctx.block_drop(310 + p, 1, f)
 
 
+@pytest.mark.parametrize("shape", ["fixed20", "dups", "ragged", "const"])
+def test_gather_bytes_returns_the_selected_rows(ctx, shape):
+    """StringContainer.AppendTo(dst, sel) over a batch of packs (kx_gather_bytes): a string predicate picks the rows
+    (kx_scan_select), the result column is another string block of the same packs; the bytes that come back are the
+    oracle's rows at those ids, for every string container, with empty selections, empty strings and the size query."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(17)
+    nrows = [1, 33, 5000, 20_011]
+    kinds_all = (ko.STR_CONST, ko.STR_FIXED, ko.STR_COMPACT, ko.STR_DICT)
+    tables = []
+    for p, n in enumerate(nrows):
+        rows = _string_rows(rng, n, shape)
+        kinds = [k for k in kinds_all if ko.store_str(k, rows) is not None and (k != ko.STR_DICT or n <= 5000 or shape in ("dups", "const"))]
+        kind = kinds[p % len(kinds)]                       # every pack another container
+        key = rng.integers(0, 50, n).astype(np.int64)
+        assert ctx.block_put(970 + p, 1, 1, kb.INT64, ko.store("best", ko.I64, key)) == n
+        assert ctx.block_put(970 + p, 1, 2, kb.BYTES, ko.store_str(kind, rows)) == n
+        tables.append((rows, key))
+    packs = [(970 + p, 1) for p in range(len(nrows))]
+    for lo, hi in ((7, 7), (0, 49), (60, 70), (3, 20)):
+        prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, lo, hi)])
+        r = ctx.scan_select(prog, packs)
+        sel, off = r["sel"], r["sel_off"]
+        prog.close()
+        want = [rows[i] for (rows, key) in tables for i in np.nonzero((key >= lo) & (key <= hi))[0]]
+        assert int(off[-1]) == len(want)
+        got = ctx.gather_bytes(packs, 2, sel, off)
+        assert got == want, (shape, lo, hi)
+        if want:
+            exact = sum(len(w) for w in want)
+            assert ctx.gather_bytes(packs, 2, sel, off, capacity=exact) == want          # exactly as large as needed
+            if exact:
+                with pytest.raises(kb.KnoxError):
+                    ctx.gather_bytes(packs, 2, sel, off, capacity=exact - 1)             # one byte short: refused, nothing written
+    with pytest.raises(kb.KnoxError):
+        ctx.gather_bytes(packs, 1, np.zeros(1, np.uint32), np.array([0, 1, 1, 1, 1], np.uint64))   # not a string block
+    with pytest.raises(kb.KnoxError):
+        ctx.gather_bytes(packs, 2, np.array([5], np.uint32), np.array([0, 1, 1, 1, 1], np.uint64))  # row id outside pack 0 (1 row)
+    for p in range(len(nrows)):
+        ctx.block_drop(970 + p, 1, 1); ctx.block_drop(970 + p, 1, 2)
+
+
+@pytest.mark.parametrize("shape", ["fixed20", "dups", "ragged", "const"])
+def test_scan_host_takes_string_blocks(ctx, shape):
+    """kx_scan_host (cold device cache: blocks still in host memory) with a byte-string column: `height BETWEEN … AND
+    address <op> X` + sum(amount) over packs whose address blocks use every string container; the result equals the
+    resident scan's and the oracle's row by row."""
+    import knoxdb_b200 as kb
+    rng = np.random.default_rng(19)
+    nrows = [64, 5000, 20_011, 1]
+    kinds_all = (ko.STR_CONST, ko.STR_FIXED, ko.STR_COMPACT, ko.STR_DICT)
+    hb, packs = [], []
+    for p, n in enumerate(nrows):
+        rows = _string_rows(rng, n, shape)
+        kinds = [k for k in kinds_all if ko.store_str(k, rows) is not None and (k != ko.STR_DICT or n <= 5000 or shape in ("dups", "const"))]
+        blob = ko.store_str(kinds[p % len(kinds)], rows)
+        height = (100 * p + np.arange(n)).astype(np.int64)
+        amount = rng.integers(-10**6, 10**6, n).astype(np.int64)
+        hb.append([np.frombuffer(ko.store("best", ko.I64, height), np.uint8), np.frombuffer(blob, np.uint8), np.frombuffer(ko.store("best", ko.I64, amount), np.uint8)])
+        packs.append((rows, height, amount, blob))
+    fields = [(1, kb.INT64), (2, kb.BYTES), (3, kb.INT64)]
+    x = packs[1][0][777]
+    for leaf, kom, args in ((kb.Leaf(2, kb.BYTES, kb.EQ, x), ko.EQ, (x,)), (kb.Leaf(2, kb.BYTES, kb.GE, x), ko.GE, (x,)),
+                            (kb.Leaf(2, kb.BYTES, kb.RANGE, b"ab", x + b"z"), ko.RG, (b"ab", x + b"z"))):
+        prog = kb.Program(ctx, [kb.Leaf(1, kb.INT64, kb.RANGE, 10, 15_000), leaf])
+        res = ctx.scan_host(prog, fields, hb, nrows=nrows, want_bitsets=True, aggs=[(3, kb.INT64)])
+        st = None
+        for p, (rows, height, amount, blob) in enumerate(packs):
+            want = ko.tree_eval([0, 1, 0xFE], [kt.pack_bits((height >= 10) & (height <= 15_000)), ko.StrContainer(blob).match(kom, *args)], nrows[p])
+            assert (res["bitsets"][p] == want).all(), (shape, p, kom)
+            assert int(res["counts"][p]) == int(np.unpackbits(want).sum())
+            st = ko.reduce(ko.I64, amount, want, st)
+        g = res["aggs"][0]
+        assert (g.count, g.sum_bits) == (st.count, st.sum_bits)
+        if st.count:
+            assert (g.min_bits, g.max_bits) == (st.min_bits, st.max_bits)
+        prog.close()
+    # IN set over the host blocks
+    members = [packs[2][0][5], packs[0][0][0], b"not there"]
+    prog = kb.Program(ctx, [kb.Leaf(2, kb.BYTES, kb.IN, values=members)])
+    res = ctx.scan_host(prog, fields, hb, nrows=nrows, want_bitsets=True)
+    for p, (rows, *_rest) in enumerate(packs):
+        ms = set(members)
+        assert (res["bitsets"][p] == kt.pack_bits(np.fromiter((r in ms for r in rows), dtype=bool, count=nrows[p]))).all()
+    prog.close()
+
+
 def test_repeated_scans_are_bit_reproducible(ctx):
     """The general kernel shares match words between warps, recycles ring stages and lets the producer pick the way
     value columns arrive from timing-dependent feedback: a race or an order dependence would show as run-to-run
