@@ -109,6 +109,27 @@ template <int W> __device__ __forceinline__ int rot_chunks(uint32_t lane) {
 // harmless for the compare), an optional subtract, one compare and one predicated OR — no
 // ballot, no mask, and the W words arrive with 128/64/32-bit shared-memory loads.
 // The compare ((f - a) mod 2^W) <= d becomes (t - (a << K)) <= ((d << K) | (2^K - 1)), K = 32 - W.
+// Pipe balance of the row code (KX_IMAD_ROWS, chosen per translation unit).  IADD3 / LOP3 / SHF / ISETP issue on the ALU pipe (one
+// warp instruction per 2 cycles and SMSP), IMAD on the FMA pipe (same rate, in parallel).
+//   0: shift, subtract, compare, predicated OR — 3-4 ALU operations per row (the single-leaf kernel: measured equal or
+//      better there, its narrow widths are bound by issue slots, not by a pipe);
+//   1: the shift AND the subtract are ONE multiply-add — field << k == word * 2^k (mod 2^32), the multiplier read from a
+//      constant bank so that ptxas cannot strength-reduce it back to a shift — and every other row's bit is accumulated with
+//      a predicated multiply-add: 1.5 ALU + 1.5 FMA operations per row;
+//   2: multiply-add as in 1, then a carry chain: acc = 2 acc + carry(lim - t) is one IADD3 with carry-out and one
+//      add-with-carry (ptxas issues it as IMAD.X): 1 ALU + 2 FMA per row, no ISETP, no predicated instruction (the
+//      warp-autonomous kernel: 3-5 % faster on the config-3 cases, profiles/r2_tune_warp.txt §6).
+// Fields that straddle two words keep the funnel shift in every form.
+#ifndef KX_IMAD_ROWS
+#define KX_IMAD_ROWS 0
+#endif
+#if KX_IMAD_ROWS
+static __constant__ uint32_t kx_pow2[32] = {
+    0x1u, 0x2u, 0x4u, 0x8u, 0x10u, 0x20u, 0x40u, 0x80u, 0x100u, 0x200u, 0x400u, 0x800u, 0x1000u, 0x2000u, 0x4000u, 0x8000u,
+    0x10000u, 0x20000u, 0x40000u, 0x80000u, 0x100000u, 0x200000u, 0x400000u, 0x800000u, 0x1000000u, 0x2000000u, 0x4000000u, 0x8000000u,
+    0x10000000u, 0x20000000u, 0x40000000u, 0x80000000u};
+#endif
+
 template <int W, bool SUB>
 __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t lane, uint32_t a_top, uint32_t lim) {
     __builtin_assume(__isShared(seg));   // the staged stream lives in shared memory: LDS, not generic loads
@@ -136,19 +157,64 @@ __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, u
         for (int i = 0; i < W; ++i) x[i] = seg[i];
     }
     x[W] = 0;
-    uint32_t wq[4] = {0, 0, 0, 0};   // four independent accumulators: short dependency chains, one predicated OR per row
+    uint32_t wq[4] = {0, 0, 0, 0};   // four independent accumulators: short dependency chains
+#if KX_IMAD_ROWS == 2
+    // carry-chain form: accumulator q collects rows 8q … 8q+7, highest row first: acc = 2 acc + carry(lim - t), so the
+    // compare and the bit insert are one IADD3 with carry-out and one add-with-carry — no ISETP, no predicated instruction.
+    // (sub.cc leaves the hardware carry of lim + ~t + 1: set exactly when t <= lim, i.e. when the row matches.)
+    const uint32_t na_top = 0u - a_top, one = kx_pow2[0];
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+        const int j = (jj & 3) * 8 + 7 - (jj >> 2);   // interleave the four chains
+        const int bit = j * W, wi = bit >> 5, sh = bit & 31;
+        uint32_t t;
+        if (sh + W <= 32) {
+            const int k = 32 - sh - W;
+            if (SUB) t = x[wi] * kx_pow2[k] + na_top;
+            else t = k ? x[wi] * kx_pow2[k] : x[wi];
+        } else {
+            t = __funnelshift_l(x[wi], x[wi + 1], 64 - sh - W);
+            if (SUB) t = t * one + na_top;
+        }
+        uint32_t dummy;
+        asm("sub.cc.u32 %1, %2, %3;\n\taddc.u32 %0, %0, %0;" : "+r"(wq[j >> 3]), "=r"(dummy) : "r"(lim), "r"(t));
+    }
+    uint32_t word = (wq[0] | (wq[1] << 8)) | ((wq[2] << 16) | (wq[3] << 24));
+    if constexpr (W == 8 || W == 16 || W == 24 || W == 32) word = __funnelshift_l(word, word, rot_rows);
+    return word;
+#else
+#if KX_IMAD_ROWS
+    const uint32_t na_top = 0u - a_top, one = kx_pow2[0];
+#endif
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int bit = j * W, wi = bit >> 5, sh = bit & 31;
         uint32_t t;
+#if KX_IMAD_ROWS
+        if (sh + W <= 32) {
+            const int k = 32 - sh - W;
+            if (SUB) t = x[wi] * kx_pow2[k] + na_top;          // IMAD: shift and subtract in one
+            else t = k ? x[wi] * kx_pow2[k] : x[wi];
+        } else {
+            t = __funnelshift_l(x[wi], x[wi + 1], 64 - sh - W);
+            if (SUB) t = t * one + na_top;                      // the subtract alone, still off the ALU pipe
+        }
+        if (j & 1) {
+            asm("{\n.reg .pred p;\nsetp.le.u32 p, %1, %2;\n@p mad.lo.u32 %0, %3, %4, %0;\n}" : "+r"(wq[j & 3]) : "r"(t), "r"(lim), "r"(one), "r"(1u << j));
+        } else {
+            if (t <= lim) wq[j & 3] |= (1u << j);
+        }
+#else
         if (sh + W <= 32) t = x[wi] << (32 - sh - W);
         else t = __funnelshift_l(x[wi], x[wi + 1], 64 - sh - W);
         if (SUB) t -= a_top;
         if (t <= lim) wq[j & 3] |= (1u << j);
+#endif
     }
     uint32_t word = (wq[0] | wq[1]) | (wq[2] | wq[3]);
     if constexpr (W == 8 || W == 16 || W == 24 || W == 32) word = __funnelshift_l(word, word, rot_rows);
     return word;
+#endif
 }
 
 template <bool SUB>

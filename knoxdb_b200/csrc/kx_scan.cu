@@ -239,20 +239,36 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         }
 
         const uint32_t* sw = reinterpret_cast<const uint32_t*>(stage_base + (size_t)s * P.stage_bytes);
+        // the leaf's operands are read ONCE per tile into registers: through the `lf` reference every pass re-reads them from
+        // global memory (the bitset stores in between may alias as far as the compiler knows) — six dependent L1 round trips
+        // per 32-row step, which is what bounded the narrow widths
+        uint32_t t_mode = 0, t_w = 0, t_atop = 0, t_lim = 0, t_flip = 0;
+        if constexpr (ONLY32) {
+            t_mode = lf.mode; t_w = lf.width;
+            const uint32_t k = 32u - t_w, a = (uint32_t)lf.a, d = (uint32_t)lf.d;
+            t_atop = a << k; t_lim = (d << k) | ((1u << k) - 1u);   // k == 0: a, d   (leaf_range32's operands)
+            t_flip = ((lf.neg != 0) != (lf.neg2 != 0)) ? 0xffffffffu : 0u;
+        }
+        const bool t_neg2 = lf.neg2 != 0;
         mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
         for (uint32_t pass = 0; pass < passes; ++pass) {
             const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
             const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
             uint32_t word;
             if constexpr (ONLY32) {
-                if (lf.mode == LM_RANGE32) word = leaf_range32(sw, lf.width, g0, Rp, lane, (uint32_t)lf.a, (uint32_t)lf.d);
-                else word = lf.mode == LM_ALL ? 0xffffffffu : 0u;
-                if (lf.neg) word = ~word;
+                if (t_mode == LM_RANGE32) {
+                    word = 0;
+                    if (lane < Rp) {
+                        const uint32_t* seg = sw + (size_t)(g0 + lane) * t_w;
+                        word = t_atop ? leaf_b32_dispatch<true>(seg, lane, t_w, t_atop, t_lim) : leaf_b32_dispatch<false>(seg, lane, t_w, 0u, t_lim);
+                    }
+                } else word = t_mode == LM_ALL ? 0xffffffffu : 0u;
+                word ^= t_flip;
             } else {
                 LeafEnv env{P, code_smem, pi.n, pack_row0};
                 word = eval_leaf(env, lf, 0u, sw, g0, Rp, lane, wr, 0xffffffffu);
+                if (t_neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
             }
-            if (lf.neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
             if (pass + 1 == passes) {    // all shared-memory reads of this stage are done: release it early
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);

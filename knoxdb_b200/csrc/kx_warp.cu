@@ -31,6 +31,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#define KX_IMAD_ROWS 2   // row code: multiply-add + carry chain (kx_leaf.cuh)
 #include "kx_leaf.cuh"
 
 namespace kx {

@@ -11,7 +11,8 @@ import pytest
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SELECTION = ("simple8b or string_in_sets or bitset_golden or bitset_ops or multi_predicate or predicate_trees or row_masks or alprd_blocks or float32_raw or scan_select or "
-             "time_bucketed or string_blocks or alp_float or run_end or in_sets or plan or pipeline or batching or sharded_on_one_rank or cmp_random")
+             "time_bucketed or string_blocks or alp_float or run_end or in_sets or plan or pipeline or batching or sharded_on_one_rank or cmp_random or "
+             "gather_bytes or scan_host_takes or zone_maps")
 
 
 def test_selected_gpu_tests_leave_every_guard_zone_intact():
