@@ -249,7 +249,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             t_atop = a << k; t_lim = (d << k) | ((1u << k) - 1u);   // k == 0: a, d   (leaf_range32's operands)
             t_flip = ((lf.neg != 0) != (lf.neg2 != 0)) ? 0xffffffffu : 0u;
         }
-        const bool t_neg2 = lf.neg2 != 0;
+        PackLeaf lfv{};                                        // (the other leaf kinds: the whole descriptor, by value)
+        if constexpr (!ONLY32) lfv = lf;
+        const bool t_neg2 = ONLY32 ? false : lfv.neg2 != 0;
         mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
         for (uint32_t pass = 0; pass < passes; ++pass) {
             const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
@@ -266,7 +268,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 word ^= t_flip;
             } else {
                 LeafEnv env{P, code_smem, pi.n, pack_row0};
-                word = eval_leaf(env, lf, 0u, sw, g0, Rp, lane, wr, 0xffffffffu);
+                word = eval_leaf(env, lfv, 0u, sw, g0, Rp, lane, wr, 0xffffffffu);
                 if (t_neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
             }
             if (pass + 1 == passes) {    // all shared-memory reads of this stage are done: release it early

@@ -17,6 +17,7 @@ PACK_ROWS = 1 << 20   # rows per pack of the config-3 cases (profiles/sweep_conf
 CASES = {
     # name: (rows per launch, algorithmic note)
     "w20": ("256 packs x 4 Mi rows, w = 20, Less(median) -> count", 256 * (4 << 20)),
+    "w8": ("256 packs x 4 Mi rows, w = 8, Less(median) -> count (issue-bound narrow width)", 256 * (4 << 20)),
     "c3dict": ("128 packs x 1 Mi rows: ts(w=40) range 0.1 % AND acct(dict, 15-bit codes) IN{64} -> count + sum/min/max(int64 raw)", 128 * PACK_ROWS),
     "hash64": ("128 packs x 1 Mi rows: ts(w=40) range AND acct(bitpack40) IN{64} -> sum/min/max(int64 raw)", 128 * PACK_ROWS),
     "ts01": ("128 packs x 1 Mi rows: ts(w=40) range 0.1 % -> sum/min/max(int64 raw)", 128 * PACK_ROWS),
@@ -37,7 +38,7 @@ def raw_metrics(path):
 
 def main():
     for name, (launch, rows) in CASES.items():
-        tag = "r2" if name == "w20" else "r2b"   # r2b: captures of the warp-autonomous kernel (profiles/run_ncu_r2b.sh)
+        tag = "r2" if name in ("w20", "w8") else "r2b"   # r2b: captures of the warp-autonomous kernel (profiles/run_ncu_r2b.sh)
         det = os.path.join(SRC, f"prof_{tag}_{name}_details.txt")
         raw = os.path.join(SRC, f"prof_{tag}_{name}_raw.csv")
         if not os.path.exists(det):
@@ -64,7 +65,8 @@ def main():
         s = os.path.join(SRC, f"prof_{'r2' if name == 'w20' else 'r2b'}_{name}_source.csv.gz")
         if os.path.exists(s):
             shutil.copy(s, os.path.join(DST, f"r2_ncu_{name}_source.csv.gz"))
-    for a, b in (("launches_r2.csv", "r2_launches_bench.csv"), ("r2_sweep_configs.json", "r2_sweep_configs.json")):
+    for a, b in (("launches_r2.csv", "r2_launches_bench.csv"), ("r2_sweep_configs.json", "r2_sweep_configs.json"), ("sweep_final.json", "r2_sweep_configs.json"),
+                 ("bench_final.json", "r2_bench_1gpu.json"), ("bench_ref_final.json", "r2_bench_ref.json")):
         if os.path.exists(os.path.join(SRC, a)):
             shutil.copy(os.path.join(SRC, a), os.path.join(DST, b))
 
