@@ -788,7 +788,7 @@ int run_scan(kx_ctx* ctx, const kx_prog* prog, const ScanJob& job, uint8_t* bits
             compile_leaf(v, job.leaf_dicts[size_t(p) * nleaves + l], prog->leaves[size_t(l)], uint32_t(size_t(p) * nleaves + l), o);
             if (o.mode == LM_CODESET) {   // dictionary-set translation runs on the device, one job per (pack, leaf)
                 const LeafSpec& ls = prog->leaves[size_t(l)];
-                cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, 0,
+                cjobs.push_back(CodesetJob{v.aux, v.naux, ls.set_off, uint32_t(ls.set.size()), code_words, uint32_t(v.delta),
                                            type_is_signed(v.type) ? 0x8000000000000000ull : 0ull});
                 max_code_set = std::max(max_code_set, uint32_t(ls.set.size()));
                 o.a = code_words;

@@ -29,13 +29,13 @@ struct PruneParams {
     uint8_t postfix[MAX_POSTFIX];
 };
 
-// one dictionary-set translation job of codeset_kernel: bit c of out[out_off ...] = dict[c] ∈ set
+// one dictionary-set translation job of codeset_kernel: bit (c - base) of out[out_off ...] = dict[c] ∈ set
 struct CodesetJob {
     const uint8_t* dict;   // u64 dictionary values on the device
     uint32_t ndict;
     uint32_t set_off, nset;   // sorted set inside the program's set_vals
     uint32_t out_off;         // first word of the bitmap
-    uint32_t pad;
+    uint32_t base;            // min-FOR base of the code stream: bit (code - base) is set, so that the scan indexes the bitmap with the raw field
     uint64_t flip;            // sign flip that maps the dictionary's T order to unsigned order
 };
 

@@ -123,12 +123,11 @@ template <int W> __device__ __forceinline__ int rot_chunks(uint32_t lane) {
 #ifndef KX_IMAD_ROWS
 #define KX_IMAD_ROWS 0
 #endif
-#if KX_IMAD_ROWS
-static __constant__ uint32_t kx_pow2[32] = {
+static __constant__ uint32_t kx_pow2[32] = {   // 2^k from a constant bank: a multiply ptxas cannot turn back into a shift
+
     0x1u, 0x2u, 0x4u, 0x8u, 0x10u, 0x20u, 0x40u, 0x80u, 0x100u, 0x200u, 0x400u, 0x800u, 0x1000u, 0x2000u, 0x4000u, 0x8000u,
     0x10000u, 0x20000u, 0x40000u, 0x80000u, 0x100000u, 0x200000u, 0x400000u, 0x800000u, 0x1000000u, 0x2000000u, 0x4000000u, 0x8000000u,
     0x10000000u, 0x20000000u, 0x40000000u, 0x80000000u};
-#endif
 
 template <int W, bool SUB>
 __device__ __forceinline__ uint32_t leaf_b32(const uint32_t* __restrict__ seg, uint32_t lane, uint32_t a_top, uint32_t lim) {
@@ -402,14 +401,40 @@ __device__ __forceinline__ uint32_t leaf_code32(const uint32_t* __restrict__ seg
         for (int i = 0; i < W; ++i) x[i] = seg[i];
     }
     x[W] = 0;
+    // The bitmap is indexed by the FIELD (codeset_kernel subtracts the code stream's base), so a row needs no mask and no add:
+    // the word index comes from the top-aligned field (one IMAD on the FMA pipe + one shift), the bit position is the low
+    // five bits of the right-aligned field (funnel shifts ignore the garbage above): 4 ALU + 2 FMA-pipe operations per
+    // row instead of 8-9 ALU operations.
     uint32_t word = 0;
+    if constexpr (GBM) {
+        // bitmap read in place through L1 (warp-autonomous kernel): the plain form — mask, index, load, two funnel shifts —
+        // measured 7 % faster there than the multiply-add form below (the longer address chain in front of a global load)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const int bit = j * W, wi = bit >> 5, sh = bit & 31;
+            const uint32_t f = (sh + W <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
+            const uint32_t code = f & ((1u << W) - 1u);
+            const uint32_t wv = __ldg(bm + (code >> 5));
+            word = __funnelshift_r(word, __funnelshift_r(wv, 0u, code), 1);
+        }
+        return word;
+    }
+    const uint32_t w0 = (W <= 5) ? (GBM ? __ldg(bm) : bm[0]) : 0u;
 #pragma unroll
     for (int j = 0; j < 32; ++j) {
         const int bit = j * W, wi = bit >> 5, sh = bit & 31;
-        uint32_t f = (sh + W <= 32) ? (x[wi] >> sh) : __funnelshift_r(x[wi], x[wi + 1], sh);
-        uint32_t code = (f & ((1u << W) - 1u)) + code_base;
-        uint32_t wv = GBM ? __ldg(bm + (code >> 5)) : bm[code >> 5];
-        word = __funnelshift_r(word, __funnelshift_r(wv, 0u, code), 1);   // shift bit (code & 31) of wv in from the top
+        uint32_t f, wv;
+        if (sh + W <= 32) f = sh ? (x[wi] >> sh) : x[wi];
+        else f = __funnelshift_r(x[wi], x[wi + 1], sh);
+        if constexpr (W < 5) f &= (1u << W) - 1u;   // (narrower than the bit index: the garbage above the field must go)
+        if constexpr (W <= 5) {
+            wv = w0;
+        } else {
+            const uint32_t t = (sh + W <= 32) ? x[wi] * kx_pow2[32 - sh - W] : f * kx_pow2[32 - W];   // field << (32 - W)
+            const uint32_t idx = t >> (32 - W + 5);
+            wv = GBM ? __ldg(bm + idx) : bm[idx];
+        }
+        word = __funnelshift_r(word, __funnelshift_r(wv, 0u, f), 1);   // shift bit (field & 31) of wv in from the top
     }
     return word;   // after 32 steps row j sits at bit j
 }

@@ -42,7 +42,10 @@ __global__ void codeset_kernel(const CodesetJob* __restrict__ jobs, uint32_t njo
             uint32_t m = (lo + hi) >> 1;
             if ((__ldg(dict + m) ^ J.flip) < key) lo = m + 1; else hi = m;
         }
-        if (lo < J.ndict && __ldg(dict + lo) == val) atomicOr(out + J.out_off + (lo >> 5), 1u << (lo & 31u));
+        if (lo < J.ndict && __ldg(dict + lo) == val && lo >= J.base) {   // the bitmap is indexed by the FIELD of the code stream: code - base
+            const uint32_t f = lo - J.base;
+            atomicOr(out + J.out_off + (f >> 5), 1u << (f & 31u));
+        }
     }
   }
 }

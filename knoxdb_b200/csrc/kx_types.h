@@ -72,7 +72,7 @@ enum LeafMode : uint8_t {
     LM_ROWRANGE = 5,  // row index in [a, d] (affine blocks: closed-form index arithmetic)
     LM_SET = 6,       // decoded value ∈ sorted set (binary search)
     LM_VALRANGE = 7,  // decoded value v: ((v ^ flip) - a) <= d  (run-end / generic fallback)
-    LM_CODESET = 8,   // staged dictionary codes: bit (field + wm) of the pack's code bitmap at code_bits + a
+    LM_CODESET = 8,   // staged dictionary codes (code = field + wm): bit `field` of the pack's code bitmap at code_bits + a
                       // (d = number of codes); the bitmap is built on the device per (pack, leaf) and query
     LM_HASHSET = 9,   // staged integer stream: T(field + base) looked up in the leaf's bucketised hash table
     LM_BITS = 10,     // staged stream IS the leaf's bitset, 1 bit per row (run-end blocks: filled per run by
