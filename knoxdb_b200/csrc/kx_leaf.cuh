@@ -229,6 +229,26 @@ static __device__ __noinline__ uint32_t leaf_b32_dispatch(const uint32_t* __rest
     return 0;
 }
 
+// every pass of one tile (single-leaf kernel): the width dispatch sits OUTSIDE the pass loop, so a tile pays for it once and
+// the unrolled row code of one width runs `passes` times back to back; emit(pass, word) consumes the lane's bitset word.
+// seg0 = the lane's group of pass 0 (pass p: 32 groups = 32 W words further); lanes that own no group (`own` false) emit 0.
+template <bool SUB, class F>
+__device__ __forceinline__ void leaf_b32_passes(const uint32_t* __restrict__ seg0, uint32_t lane, uint32_t w, uint32_t a_top, uint32_t lim,
+                                                uint32_t passes, bool own, F emit) {
+    switch (w) {
+#define KX_CASE(W)                                                                                                          \
+    case W:                                                                                                                 \
+        _Pragma("unroll 1") for (uint32_t p = 0; p < passes; ++p)                                                           \
+            emit(p, own ? leaf_b32<W, SUB>(seg0 + (size_t)p * (32u * W), lane, a_top, lim) : 0u);                           \
+        break;
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+        KX_CASE(17) KX_CASE(18) KX_CASE(19) KX_CASE(20) KX_CASE(21) KX_CASE(22) KX_CASE(23) KX_CASE(24)
+        KX_CASE(25) KX_CASE(26) KX_CASE(27) KX_CASE(28) KX_CASE(29) KX_CASE(30) KX_CASE(31) KX_CASE(32)
+#undef KX_CASE
+    }
+}
+
 // one LM_RANGE32 leaf for one pass; lanes >= Rp own no group
 __device__ __forceinline__ uint32_t leaf_range32(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  uint32_t a, uint32_t d) {

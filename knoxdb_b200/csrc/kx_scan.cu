@@ -256,24 +256,48 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         if constexpr (!ONLY32) lfv = lf;
         const bool t_neg2 = ONLY32 ? false : lfv.neg2 != 0;
         mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
+        if constexpr (ONLY32) {
+            // the lean kernel: width dispatch once per TILE, the passes loop inside the per-width code; the per-pass output
+            // code knows whether the tile has a tail (only the last tile of a pack does)
+            const bool own = lane < Rp;
+            const uint32_t g_lane = warp * R + lane;               // this lane's group in pass 0 (pass p: + 32 p)
+            const bool plain = own && pack_row0 + tile_rows <= pi.n && pack_row0 + tile_rows > pack_row0;   // every row of the lane's words exists
+            uint8_t* bt = P.bitsets ? P.bitsets + pi.bitset_off + (size_t)(pack_row0 >> 3) + (size_t)g_lane * 4u : nullptr;
+            const uint32_t n = pi.n;
+            auto emit = [&](uint32_t pass, uint32_t word) {
+                word ^= t_flip;
+                if (plain) {
+                    if (bt) *reinterpret_cast<uint32_t*>(bt + (size_t)pass * 128u) = word;   // coalesced 128 B per warp
+                } else {
+                    // mask rows past the end of the pack (tail bits must be zero) and lanes that own no group
+                    const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g_lane + pass * 32u) * 32u;
+                    uint32_t valid = 0;
+                    if (own && wr < n) {
+                        const uint32_t left = n - (uint32_t)wr;
+                        valid = left >= 32u ? 0xffffffffu : ((1u << left) - 1u);
+                    }
+                    word &= valid;
+                    if (bt && valid) *reinterpret_cast<uint32_t*>(bt + (size_t)pass * 128u) = word;
+                }
+                lane_cnt += __popc(word);
+            };
+            if (t_mode == LM_RANGE32) {
+                const uint32_t* seg0 = sw + (size_t)g_lane * t_w;
+                if (t_atop) leaf_b32_passes<true>(seg0, lane, t_w, t_atop, t_lim, passes, own, emit);
+                else leaf_b32_passes<false>(seg0, lane, t_w, 0u, t_lim, passes, own, emit);
+            } else {
+                const uint32_t cw = t_mode == LM_ALL ? 0xffffffffu : 0u;
+                for (uint32_t pass = 0; pass < passes; ++pass) emit(pass, cw);
+            }
+            __syncwarp();                                          // all shared-memory reads of this stage are done
+            if (lane == 0) mbar_arrive(&empty_bar[s]);
+        } else {
         for (uint32_t pass = 0; pass < passes; ++pass) {
             const uint32_t g0 = warp * R + pass * 32u;         // first group (of the tile) of this pass
             const uint64_t wr = (uint64_t)pack_row0 + (uint64_t)(g0 + lane) * 32u;   // first pack row of this lane's word
-            uint32_t word;
-            if constexpr (ONLY32) {
-                if (t_mode == LM_RANGE32) {
-                    word = 0;
-                    if (lane < Rp) {
-                        const uint32_t* seg = sw + (size_t)(g0 + lane) * t_w;
-                        word = t_atop ? leaf_b32_dispatch<true>(seg, lane, t_w, t_atop, t_lim) : leaf_b32_dispatch<false>(seg, lane, t_w, 0u, t_lim);
-                    }
-                } else word = t_mode == LM_ALL ? 0xffffffffu : 0u;
-                word ^= t_flip;
-            } else {
-                LeafEnv env{P, code_smem, pi.n, pack_row0};
-                word = eval_leaf(env, lfv, 0u, sw, g0, Rp, lane, wr, 0xffffffffu);
-                if (t_neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
-            }
+            LeafEnv env{P, code_smem, pi.n, pack_row0};
+            uint32_t word = eval_leaf(env, lfv, 0u, sw, g0, Rp, lane, wr, 0xffffffffu);
+            if (t_neg2) word = ~word;   // float-level NOT of an ALP leaf without patches (with patches: general kernel)
             if (pass + 1 == passes) {    // all shared-memory reads of this stage are done: release it early
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty_bar[s]);
@@ -289,6 +313,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
             if (P.bitsets && lane < Rp && wr < pi.n)
                 *reinterpret_cast<uint32_t*>(P.bitsets + pi.bitset_off + (wr >> 3)) = word;
             lane_cnt += __popc(word);
+        }
         }
         if (++s == nstages) { s = 0; ph ^= 1u; }
 
