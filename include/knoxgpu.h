@@ -212,7 +212,8 @@ int kx_scan_buckets(kx_ctx* ctx, const kx_prog* prog, const kx_packref* packs, i
 
 /* Same scan over blocks that still live in HOST memory (cold device cache): the blocks of
  * all referenced fields are uploaded, scanned and dropped in pipelined batches.
- * blocks[i*nfields + f] / block_len[...] = encoded block of pack i, field fields[f]. */
+ * blocks[i*nfields + f] / block_len[...] = encoded block of pack i, field fields[f] (any block type kx_block_put
+ * takes, KX_BYTES included). */
 int kx_scan_host(kx_ctx* ctx, const kx_prog* prog, int npacks,
                  const uint16_t* fields, const uint8_t* field_types, int nfields,
                  const void* const* blocks, const size_t* block_len,
