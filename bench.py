@@ -288,6 +288,36 @@ def config1(ctx, kb, peak):
     return out
 
 
+def config2_widths(ctx, kb, peak):
+    """BASELINE config 2 at other widths than the headline's: bit-packed uint64, 1 Mi-row packs x 512 (>= 0.5 GiB at w = 8,
+    inputs >> L2), Less(median) -> match count per pack; parity: numpy truth on every distinct pack."""
+    M1, npacks, nd = 1 << 20, 512, 4
+    out = []
+    for w in (8, 12, 32, 48):
+        rng = np.random.default_rng(100 + w)
+        vals = [rng.integers(0, 2**w, M1, dtype=np.uint64) for _ in range(nd)]
+        for v in vals:
+            v[0], v[1] = 0, 2**w - 1          # every pack spans the full width
+        blocks = [enc_bitpack(v)[0] for v in vals]
+        for p in range(npacks):
+            ctx.block_put(200000 + p, 1, 1, kb.UINT64, blocks[p % nd])
+        refs = ctx.pack_refs([(200000 + p, 1) for p in range(npacks)])
+        nrows = [M1] * npacks
+        thr = 2**(w - 1)
+        prog = kb.Program(ctx, [kb.Leaf(1, kb.UINT64, kb.LT, thr)])
+        r = ctx.scan(prog, refs, nrows=nrows)
+        for d in range(nd):
+            assert int(r["counts"][d]) == int((vals[d] < np.uint64(thr)).sum()), "config 2 parity"
+        ms = median_kernel_ms(ctx, lambda: ctx.scan(prog, refs, nrows=nrows))
+        gbs = npacks * M1 * (w / 8.0) / (ms * 1e-3) / 1e9
+        out.append({"case": f"bit-packed uint64 w={w}, 1Mi-row packs x {npacks}, Less(median) -> count", "kernel_ms": ms, "rows_per_s": npacks * M1 / (ms * 1e-3),
+                    "bytes_per_row": w / 8.0, "achieved_GBps": gbs, "frac_of_peak": gbs / peak, "parity": "counts equal numpy on every distinct pack"})
+        prog.close()
+        for p in range(npacks):
+            ctx.block_drop(200000 + p, 1, 1)
+    return out
+
+
 def config3(ctx, kb, peak):
     """BASELINE config 3 — the north-star path: ts BETWEEN [t0, t1] AND acct IN {64 values} → count / sum / min / max over an
     int64 and a float64 amount column, 256 packs x 1 Mi rows (ts: sorted, bit-packed; acct: dictionary with 15-bit
@@ -628,7 +658,7 @@ def main():
     if rank == 0 and world == 1 and not args.no_configs:
         t0 = time.time()
         c3 = config3(ctx, kb, peak)
-        line["configs"] = {"c1": config1(ctx, kb, peak), "c3_north_star": c3, "c4": config4(ctx, kb)}
+        line["configs"] = {"c1": config1(ctx, kb, peak), "c2_widths": config2_widths(ctx, kb, peak), "c3_north_star": c3, "c4": config4(ctx, kb)}
         # the north-star kernel's own roofline: the sparse two-leaf + reduce case (what VERDICT r1 asked to lift)
         ns = c3[0]["int64"]
         t3 = ncu_traffic("r2_ncu_c3dict_traffic.json")
