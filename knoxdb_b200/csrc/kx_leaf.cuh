@@ -470,6 +470,22 @@ static __device__ __noinline__ uint32_t leaf_code32_dispatch(const uint32_t* __r
     return 0;
 }
 
+// every pass of one tile for a dictionary IN / NOT IN leaf (single-leaf kernel, bitmap in shared memory): one width dispatch
+// per tile, as leaf_b32_passes
+template <class F>
+__device__ __forceinline__ void leaf_code32_passes(const uint32_t* __restrict__ seg0, uint32_t w, const uint32_t* __restrict__ bm, uint32_t passes, bool own, F emit) {
+    switch (w) {
+#define KX_CASE(W)                                                                                                          \
+    case W:                                                                                                                 \
+        _Pragma("unroll 1") for (uint32_t p = 0; p < passes; ++p)                                                           \
+            emit(p, own ? leaf_code32<W, false>(seg0 + (size_t)p * (32u * W), 0u, bm) : 0u);                                \
+        break;
+        KX_CASE(1) KX_CASE(2) KX_CASE(3) KX_CASE(4) KX_CASE(5) KX_CASE(6) KX_CASE(7) KX_CASE(8)
+        KX_CASE(9) KX_CASE(10) KX_CASE(11) KX_CASE(12) KX_CASE(13) KX_CASE(14) KX_CASE(15) KX_CASE(16)
+#undef KX_CASE
+    }
+}
+
 template <bool GBM>
 __device__ __forceinline__ uint32_t leaf_codeset(const uint32_t* __restrict__ sw, uint32_t w, uint32_t g0, uint32_t Rp, uint32_t lane,
                                                  uint32_t code_base, const uint32_t* __restrict__ bm) {

@@ -256,16 +256,19 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
         if constexpr (!ONLY32) lfv = lf;
         const bool t_neg2 = ONLY32 ? false : lfv.neg2 != 0;
         mbar_wait(&full_bar[s], ph);                           // TMA bytes have landed
-        if constexpr (ONLY32) {
-            // the lean kernel: width dispatch once per TILE, the passes loop inside the per-width code; the per-pass output
-            // code knows whether the tile has a tail (only the last tile of a pack does)
+        const bool per_tile = ONLY32 || lfv.mode == LM_CODESET;
+        if (per_tile) {
+            // per-tile output state shared by the paths that dispatch once per TILE (the lean kernel; dictionary IN / NOT IN): the
+            // per-pass output code knows whether the tile has a tail (only the last tile of a pack does)
             const bool own = lane < Rp;
             const uint32_t g_lane = warp * R + lane;               // this lane's group in pass 0 (pass p: + 32 p)
             const bool plain = own && pack_row0 + tile_rows <= pi.n && pack_row0 + tile_rows > pack_row0;   // every row of the lane's words exists
             uint8_t* bt = P.bitsets ? P.bitsets + pi.bitset_off + (size_t)(pack_row0 >> 3) + (size_t)g_lane * 4u : nullptr;
             const uint32_t n = pi.n;
+            uint32_t flip = t_flip;
+            if constexpr (!ONLY32) flip = ((lfv.neg != 0) != t_neg2) ? 0xffffffffu : 0u;
             auto emit = [&](uint32_t pass, uint32_t word) {
-                word ^= t_flip;
+                word ^= flip;
                 if (plain) {
                     if (bt) *reinterpret_cast<uint32_t*>(bt + (size_t)pass * 128u) = word;   // coalesced 128 B per warp
                 } else {
@@ -281,13 +284,17 @@ __global__ void __launch_bounds__(SCAN_THREADS, MINB) scan_kernel(const ScanPara
                 }
                 lane_cnt += __popc(word);
             };
-            if (t_mode == LM_RANGE32) {
-                const uint32_t* seg0 = sw + (size_t)g_lane * t_w;
-                if (t_atop) leaf_b32_passes<true>(seg0, lane, t_w, t_atop, t_lim, passes, own, emit);
-                else leaf_b32_passes<false>(seg0, lane, t_w, 0u, t_lim, passes, own, emit);
+            if constexpr (ONLY32) {
+                if (t_mode == LM_RANGE32) {
+                    const uint32_t* seg0 = sw + (size_t)g_lane * t_w;
+                    if (t_atop) leaf_b32_passes<true>(seg0, lane, t_w, t_atop, t_lim, passes, own, emit);
+                    else leaf_b32_passes<false>(seg0, lane, t_w, 0u, t_lim, passes, own, emit);
+                } else {
+                    const uint32_t cw = t_mode == LM_ALL ? 0xffffffffu : 0u;
+                    for (uint32_t pass = 0; pass < passes; ++pass) emit(pass, cw);
+                }
             } else {
-                const uint32_t cw = t_mode == LM_ALL ? 0xffffffffu : 0u;
-                for (uint32_t pass = 0; pass < passes; ++pass) emit(pass, cw);
+                leaf_code32_passes(sw + (size_t)g_lane * lfv.width, lfv.width, code_smem + P.code_smem_off[0], passes, own, emit);
             }
             __syncwarp();                                          // all shared-memory reads of this stage are done
             if (lane == 0) mbar_arrive(&empty_bar[s]);
